@@ -1,0 +1,858 @@
+// oracle.cpp -- CPU restatement of the reference's normals -> RSD -> GRSD path.
+// TEST INFRASTRUCTURE ONLY (see oracle.h).  Compile with -O2 -ffp-contract=off so
+// that fp32 expressions are evaluated exactly as written (no FMA contraction).
+//
+// Reference citations are relative to /root/reference.
+#include "oracle.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <unordered_map>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+struct Nb {
+  float d2;
+  int32_t idx;
+};
+inline bool nb_less(const Nb& a, const Nb& b) {
+  return a.d2 < b.d2 || (a.d2 == b.d2 && a.idx < b.idx);
+}
+
+inline bool finite3(const float* p) {
+  return std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]);
+}
+
+// ---------------------------------------------------------------------------
+// Uniform grid used only to make the oracle's radius search O(N k); the result
+// set is defined purely by orc_d2() <= r2 and is checked against brute force.
+// ---------------------------------------------------------------------------
+class CellGrid {
+ public:
+  CellGrid(const float* xyz, int n, double r) : xyz_(xyz), n_(n) {
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    int nf = 0;
+    for (int i = 0; i < n; ++i) {
+      const float* p = xyz + 3 * (size_t)i;
+      if (!finite3(p)) continue;
+      ++nf;
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = std::min(lo[a], (double)p[a]);
+        hi[a] = std::max(hi[a], (double)p[a]);
+      }
+    }
+    if (nf == 0) {
+      for (int a = 0; a < 3; ++a) lo[a] = hi[a] = 0;
+    }
+    cell_ = r * 1.001 + 1e-9;
+    if (!(cell_ > 0)) cell_ = 1e-9;
+    for (int a = 0; a < 3; ++a) {
+      lo_[a] = lo[a];
+      dim_[a] = (int64_t)std::floor((hi[a] - lo[a]) / cell_) + 1;
+    }
+    // keep the dense table bounded; otherwise use a hash map
+    double cells = (double)dim_[0] * (double)dim_[1] * (double)dim_[2];
+    dense_ = cells <= 6.4e7;
+    std::vector<std::pair<uint64_t, int32_t>> keyed;
+    keyed.reserve(nf);
+    for (int i = 0; i < n; ++i) {
+      const float* p = xyz + 3 * (size_t)i;
+      if (!finite3(p)) continue;
+      keyed.emplace_back(key_of(p), i);
+    }
+    std::sort(keyed.begin(), keyed.end());
+    order_.resize(keyed.size());
+    for (size_t i = 0; i < keyed.size(); ++i) order_[i] = keyed[i].second;
+    if (dense_) {
+      start_.assign((size_t)cells + 1, 0);
+      for (auto& kv : keyed) start_[kv.first + 1]++;
+      for (size_t c = 0; c < (size_t)cells; ++c) start_[c + 1] += start_[c];
+    } else {
+      size_t i = 0;
+      while (i < keyed.size()) {
+        size_t j = i;
+        while (j < keyed.size() && keyed[j].first == keyed[i].first) ++j;
+        map_[keyed[i].first] = std::make_pair((int32_t)i, (int32_t)j);
+        i = j;
+      }
+    }
+  }
+
+  // All surface points with d2 <= r2 of q, unsorted.
+  void query(const float* q, float r2, std::vector<Nb>& out) const {
+    out.clear();
+    if (!finite3(q)) return;
+    int64_t c[3];
+    for (int a = 0; a < 3; ++a) c[a] = (int64_t)std::floor(((double)q[a] - lo_[a]) / cell_);
+    for (int64_t z = c[2] - 1; z <= c[2] + 1; ++z) {
+      if (z < 0 || z >= dim_[2]) continue;
+      for (int64_t y = c[1] - 1; y <= c[1] + 1; ++y) {
+        if (y < 0 || y >= dim_[1]) continue;
+        for (int64_t x = c[0] - 1; x <= c[0] + 1; ++x) {
+          if (x < 0 || x >= dim_[0]) continue;
+          uint64_t key = (uint64_t)((z * dim_[1] + y) * dim_[0] + x);
+          int32_t b, e;
+          if (dense_) {
+            b = start_[key];
+            e = start_[key + 1];
+          } else {
+            auto it = map_.find(key);
+            if (it == map_.end()) continue;
+            b = it->second.first;
+            e = it->second.second;
+          }
+          for (int32_t s = b; s < e; ++s) {
+            int32_t j = order_[s];
+            float d2 = orc_d2(xyz_ + 3 * (size_t)j, q);
+            if (d2 <= r2) out.push_back({d2, j});
+          }
+        }
+      }
+    }
+  }
+
+ private:
+  uint64_t key_of(const float* p) const {
+    int64_t c[3];
+    for (int a = 0; a < 3; ++a) {
+      c[a] = (int64_t)std::floor(((double)p[a] - lo_[a]) / cell_);
+      c[a] = std::min(std::max(c[a], (int64_t)0), dim_[a] - 1);
+    }
+    return (uint64_t)((c[2] * dim_[1] + c[1]) * dim_[0] + c[0]);
+  }
+  const float* xyz_;
+  int n_;
+  double cell_, lo_[3];
+  int64_t dim_[3];
+  bool dense_;
+  std::vector<int32_t> order_, start_;
+  std::unordered_map<uint64_t, std::pair<int32_t, int32_t>> map_;
+};
+
+inline void sort_truncate(std::vector<Nb>& v, int max_nn) {
+  std::sort(v.begin(), v.end(), nb_less);
+  if (max_nn > 0 && (int)v.size() > max_nn) v.resize(max_nn);
+}
+
+inline float r2_of(double r) {
+  float rf = (float)r;
+  return rf * rf;
+}
+
+// ---------------------------------------------------------------------------
+// 3x3 symmetric eigen-decomposition, cyclic Jacobi in double.
+// a = {xx, xy, xz, yy, yz, zz}.  Eigenvalues ascending in w, eigenvectors in
+// the columns of v (v[r][c]).
+// ---------------------------------------------------------------------------
+void eig3_jacobi(const double a[6], double w[3], double v[3][3]) {
+  double m[3][3] = {{a[0], a[1], a[2]}, {a[1], a[3], a[4]}, {a[2], a[4], a[5]}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = std::fabs(m[0][1]) + std::fabs(m[0][2]) + std::fabs(m[1][2]);
+    if (off == 0.0) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (m[p][q] == 0.0) continue;
+        double theta = (m[q][q] - m[p][p]) / (2.0 * m[p][q]);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        if (!std::isfinite(theta)) t = 0.0;  // |theta| overflow: rotation angle ~ 0
+        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        double apq = m[p][q];
+        m[p][p] -= t * apq;
+        m[q][q] += t * apq;
+        m[p][q] = m[q][p] = 0.0;
+        int r = 3 - p - q;
+        double arp = m[r][p], arq = m[r][q];
+        m[r][p] = m[p][r] = c * arp - s * arq;
+        m[r][q] = m[q][r] = s * arp + c * arq;
+        for (int k = 0; k < 3; ++k) {
+          double vkp = v[k][p], vkq = v[k][q];
+          v[k][p] = c * vkp - s * vkq;
+          v[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int o[3] = {0, 1, 2};
+  double d[3] = {m[0][0], m[1][1], m[2][2]};
+  std::sort(o, o + 3, [&](int x, int y) { return d[x] < d[y]; });
+  double vv[3][3];
+  for (int c = 0; c < 3; ++c) {
+    w[c] = d[o[c]];
+    for (int r = 0; r < 3; ++r) vv[r][c] = v[r][o[c]];
+  }
+  std::memcpy(v, vv, sizeof(vv));
+}
+
+// PCA normal of a neighbourhood (pcl::NormalEstimation semantics [EXTERNAL];
+// call site grsd_colorCHLAC_tools.hpp:76-81).  Coordinates are taken relative to
+// the query so the double sums are exact for lattice inputs.
+void pca_normal(const float* xyz, const float* q, const std::vector<Nb>& nbs, const float* vp,
+                float out[4]) {
+  const float nan = std::numeric_limits<float>::quiet_NaN();
+  size_t k = nbs.size();
+  if (k < 3) {
+    out[0] = out[1] = out[2] = out[3] = nan;
+    return;
+  }
+  double s1[3] = {0, 0, 0}, s2[6] = {0, 0, 0, 0, 0, 0};
+  for (const Nb& nb : nbs) {
+    const float* p = xyz + 3 * (size_t)nb.idx;
+    double dx = (double)p[0] - (double)q[0], dy = (double)p[1] - (double)q[1],
+           dz = (double)p[2] - (double)q[2];
+    s1[0] += dx;
+    s1[1] += dy;
+    s1[2] += dz;
+    s2[0] += dx * dx;
+    s2[1] += dx * dy;
+    s2[2] += dx * dz;
+    s2[3] += dy * dy;
+    s2[4] += dy * dz;
+    s2[5] += dz * dz;
+  }
+  double inv = 1.0 / (double)k;
+  double mx = s1[0] * inv, my = s1[1] * inv, mz = s1[2] * inv;
+  double cov[6] = {s2[0] * inv - mx * mx, s2[1] * inv - mx * my, s2[2] * inv - mx * mz,
+                   s2[3] * inv - my * my, s2[4] * inv - my * mz, s2[5] * inv - mz * mz};
+  double w[3], v[3][3];
+  eig3_jacobi(cov, w, v);
+  double nx = v[0][0], ny = v[1][0], nz = v[2][0];
+  double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+  nx /= len;
+  ny /= len;
+  nz /= len;
+  // flipNormalTowardsViewpoint: n.(vp - p) >= 0
+  double dot = nx * ((double)vp[0] - q[0]) + ny * ((double)vp[1] - q[1]) + nz * ((double)vp[2] - q[2]);
+  if (dot < 0) {
+    nx = -nx;
+    ny = -ny;
+    nz = -nz;
+  }
+  double tr = w[0] + w[1] + w[2];
+  out[0] = (float)nx;
+  out[1] = (float)ny;
+  out[2] = (float)nz;
+  out[3] = (tr != 0.0) ? (float)std::fabs(w[0] / tr) : 0.0f;
+}
+
+// fp32 dot product evaluated as the reference writes it
+// (radius_estimation.cpp:153-155: float*float + float*float + float*float,
+// left to right, then widened to double).
+inline double cosine_f32(const float* a, const float* b) {
+  float c = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+  return (double)c;
+}
+
+// ---------------------------------------------------------------------------
+// RSD core.  In-tree variant: radius_estimation.cpp:140-202.  The neighbour list
+// is sorted by (d2, idx); `self` is excluded by index (the
+// reference skips list position 0, which is the query itself for distinct
+// points).  REF_IS_NEAREST restates pcl::RSDEstimation [EXTERNAL]: the reference
+// element is the first (nearest) neighbour, distances are measured from it and
+// neighbours farther than the radius from it are skipped.
+// ---------------------------------------------------------------------------
+void rsd_core(const float* xyz, const float* nrm, int nstride, const std::vector<Nb>& nbs,
+              int self, const float* self_normal, double radius, int ndiv, double plane_radius,
+              int flags, double* min_radius_out, double* max_radius_out) {
+  std::vector<double> mn(ndiv, +DBL_MAX), mx(ndiv, -DBL_MAX);
+  if ((flags & ORC_RSD_SEED_BIN0) && ndiv > 0) mn[0] = mx[0] = 0.0;
+  const bool nearest = (flags & ORC_RSD_REF_IS_NEAREST) != 0;
+  const float* ref_n = self_normal;
+  const float* ref_p = nullptr;
+  size_t first = 0;
+  if (nearest) {
+    if (nbs.empty()) {
+      *min_radius_out = *max_radius_out = plane_radius;
+      return;
+    }
+    ref_n = nrm + (size_t)nstride * nbs[0].idx;
+    ref_p = xyz + 3 * (size_t)nbs[0].idx;
+    first = 1;
+  }
+  for (size_t ni = first; ni < nbs.size(); ++ni) {
+    int j = nbs[ni].idx;
+    if (!nearest && j == self) continue;
+    double cosine = cosine_f32(ref_n, nrm + (size_t)nstride * j);
+    if (cosine > 1) cosine = 1;  // radius_estimation.cpp:158-159
+    if (cosine < -1) cosine = -1;
+    double angle = std::acos(cosine);
+    if (angle > M_PI / 2) angle = M_PI - angle;  // :161
+    double dist;
+    if (nearest) {
+      dist = std::sqrt((double)orc_d2(xyz + 3 * (size_t)j, ref_p));
+      if (dist > radius) continue;
+    } else {
+      dist = std::sqrt((double)nbs[ni].d2);  // :165
+    }
+    int bin = (int)std::floor(ndiv * dist / radius);  // :168
+    if (bin > ndiv - 1) bin = ndiv - 1;  // epsilon rule: the reference indexes out of bounds here
+    if (mn[bin] > angle) mn[bin] = angle;  // :171-172 (NaN falls through both)
+    if (mx[bin] < angle) mx[bin] = angle;
+  }
+  double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;
+  for (int di = 0; di < ndiv; ++di) {
+    if (mx[di] >= 0) {  // :181
+      double p_min = mn[di], p_max = mx[di];
+      double f = (di + 0.5) * radius / ndiv;
+      Amint_Amin += p_min * p_min;
+      Amint_d += p_min * f;
+      Amaxt_Amax += p_max * p_max;
+      Amaxt_d += p_max * f;
+    }
+  }
+  double max_radius = (Amint_Amin == 0) ? plane_radius : std::min(Amint_d / Amint_Amin, plane_radius);
+  double min_radius = (Amaxt_Amax == 0) ? plane_radius : std::min(Amaxt_d / Amaxt_Amax, plane_radius);
+  if (flags & ORC_RSD_SCALE_SORT) {
+    // newer pcl::computeRSD [EXTERNAL]: computed in float, scaled, then ordered
+    float a = (float)max_radius, b = (float)min_radius;  // a: from min-angle line, b: from max-angle line
+    a *= 1.1f;
+    b *= 0.9f;
+    if (a < b) {
+      min_radius = a;
+      max_radius = b;
+    } else {
+      min_radius = b;
+      max_radius = a;
+    }
+  }
+  *min_radius_out = min_radius;
+  *max_radius_out = max_radius;
+}
+
+// ---------------------------------------------------------------------------
+// kd-tree for the reference-faithful timing mode (stands in for
+// cloud_kdtree::KdTreeANN, radius_estimation.cpp:107).  Median split on the
+// widest axis, small leaf buckets, iterative radius search.
+// ---------------------------------------------------------------------------
+class KdTree {
+ public:
+  KdTree(const float* xyz, int n) : xyz_(xyz) {
+    idx_.reserve(n);
+    for (int i = 0; i < n; ++i)
+      if (finite3(xyz + 3 * (size_t)i)) idx_.push_back(i);
+    nodes_.reserve(idx_.size() / 4 + 16);
+    if (!idx_.empty()) build(0, (int)idx_.size());
+  }
+  void radius(const float* q, float r, float r2, std::vector<Nb>& out) const {
+    out.clear();
+    if (nodes_.empty() || !finite3(q)) return;
+    int stack[128], sp = 0;
+    stack[sp++] = 0;
+    while (sp) {
+      const Node& nd = nodes_[stack[--sp]];
+      if (nd.axis < 0) {
+        for (int s = nd.lo; s < nd.hi; ++s) {
+          int j = idx_[s];
+          float d2 = orc_d2(xyz_ + 3 * (size_t)j, q);
+          if (d2 <= r2) out.push_back({d2, j});
+        }
+        continue;
+      }
+      float diff = q[nd.axis] - nd.split;
+      // conservative pruning (slack keeps boundary points reachable)
+      float slack = r * 1.0001f + 1e-12f;
+      if (diff <= slack) stack[sp++] = nd.left;
+      if (diff >= -slack) stack[sp++] = nd.right;
+    }
+  }
+
+ private:
+  struct Node {
+    int axis;  // -1 leaf
+    float split;
+    int left, right, lo, hi;
+  };
+  int build(int lo, int hi) {
+    int id = (int)nodes_.size();
+    nodes_.push_back(Node{-1, 0.f, -1, -1, lo, hi});
+    if (hi - lo <= 8) return id;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int s = lo; s < hi; ++s) {
+      const float* p = xyz_ + 3 * (size_t)idx_[s];
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = std::min(mn[a], p[a]);
+        mx[a] = std::max(mx[a], p[a]);
+      }
+    }
+    int axis = 0;
+    if (mx[1] - mn[1] > mx[axis] - mn[axis]) axis = 1;
+    if (mx[2] - mn[2] > mx[axis] - mn[axis]) axis = 2;
+    if (!(mx[axis] > mn[axis])) return id;  // all duplicates: keep as leaf
+    int mid = (lo + hi) / 2;
+    std::nth_element(idx_.begin() + lo, idx_.begin() + mid, idx_.begin() + hi, [&](int a, int b) {
+      return xyz_[3 * (size_t)a + axis] < xyz_[3 * (size_t)b + axis];
+    });
+    float split = xyz_[3 * (size_t)idx_[mid] + axis];
+    int l = build(lo, mid);
+    int r = build(mid, hi);
+    nodes_[id].axis = axis;
+    nodes_[id].split = split;
+    nodes_[id].left = l;
+    nodes_[id].right = r;
+    return id;
+  }
+  const float* xyz_;
+  std::vector<int> idx_;
+  std::vector<Node> nodes_;
+};
+
+int resolve_threads(int nthreads) {
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  return nthreads;
+#else
+  (void)nthreads;
+  return 1;
+#endif
+}
+
+// 13 "half" offsets then their negations, grsd_colorCHLAC_tools.hpp:187-222
+void fill_offsets26(int32_t off[26][3]) {
+  int idx = 0;
+  for (int i = -1; i < 2; i++)
+    for (int j = -1; j < 2; j++) {
+      off[idx][0] = i;
+      off[idx][1] = j;
+      off[idx][2] = -1;
+      idx++;
+    }
+  for (int i = -1; i < 2; i++) {
+    off[idx][0] = i;
+    off[idx][1] = -1;
+    off[idx][2] = 0;
+    idx++;
+  }
+  off[idx][0] = -1;
+  off[idx][1] = 0;
+  off[idx][2] = 0;
+  for (int c = 0; c < 13; ++c)
+    for (int a = 0; a < 3; ++a) off[13 + c][a] = -off[c][a];
+}
+
+// pcl::VoxelGrid::getNeighborCentroidIndices [EXTERNAL], call site
+// grsd_colorCHLAC_tools.hpp:249.
+inline int neighbor_centroid(const float* ref, float inv_leaf, const int32_t* min_b,
+                             const int32_t* div_b, const int32_t* layout, const int32_t* disp) {
+  int ijk[3], max_b[3];
+  for (int a = 0; a < 3; ++a) {
+    ijk[a] = (int)std::floor(ref[a] * inv_leaf);
+    max_b[a] = min_b[a] + div_b[a] - 1;
+  }
+  for (int a = 0; a < 3; ++a) {
+    if (!(min_b[a] - ijk[a] <= disp[a] && max_b[a] - ijk[a] >= disp[a])) return -1;
+  }
+  int64_t lin = (int64_t)(ijk[0] + disp[0] - min_b[0]) +
+                (int64_t)(ijk[1] + disp[1] - min_b[1]) * div_b[0] +
+                (int64_t)(ijk[2] + disp[2] - min_b[2]) * div_b[0] * div_b[1];
+  return layout[lin];
+}
+
+}  // namespace
+
+extern "C" {
+
+float orc_d2(const float* a, const float* b) {
+  float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+  float xx = dx * dx, yy = dy * dy, zz = dz * dz;
+  float s = xx + yy;
+  return s + zz;
+}
+
+int orc_num_threads(void) { return resolve_threads(0); }
+
+int64_t orc_radius_search(const float* surface_xyz, int n, const float* query_xyz, int nq,
+                          double r, int max_nn, int64_t* offsets, int32_t* idx, float* d2,
+                          int64_t cap, int nthreads) {
+  CellGrid grid(surface_xyz, n, r);
+  const float r2 = r2_of(r);
+  nthreads = resolve_threads(nthreads);
+  std::vector<int64_t> counts(nq, 0);
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<Nb> nbs;
+#pragma omp for schedule(dynamic, 512)
+    for (int qi = 0; qi < nq; ++qi) {
+      grid.query(query_xyz + 3 * (size_t)qi, r2, nbs);
+      int64_t k = (int64_t)nbs.size();
+      if (max_nn > 0 && k > max_nn) k = max_nn;
+      counts[qi] = k;
+    }
+  }
+  offsets[0] = 0;
+  for (int qi = 0; qi < nq; ++qi) offsets[qi + 1] = offsets[qi] + counts[qi];
+  int64_t total = offsets[nq];
+  if (total > cap || (idx == nullptr && d2 == nullptr)) return total;
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<Nb> nbs;
+#pragma omp for schedule(dynamic, 512)
+    for (int qi = 0; qi < nq; ++qi) {
+      grid.query(query_xyz + 3 * (size_t)qi, r2, nbs);
+      sort_truncate(nbs, max_nn);
+      int64_t o = offsets[qi];
+      for (size_t s = 0; s < nbs.size(); ++s) {
+        if (idx) idx[o + s] = nbs[s].idx;
+        if (d2) d2[o + s] = nbs[s].d2;
+      }
+    }
+  }
+  return total;
+}
+
+int64_t orc_radius_search_brute(const float* surface_xyz, int n, const float* query_xyz, int nq,
+                                double r, int max_nn, int64_t* offsets, int32_t* idx, float* d2,
+                                int64_t cap) {
+  const float r2 = r2_of(r);
+  std::vector<Nb> nbs;
+  int64_t total = 0;
+  offsets[0] = 0;
+  for (int qi = 0; qi < nq; ++qi) {
+    nbs.clear();
+    const float* q = query_xyz + 3 * (size_t)qi;
+    for (int j = 0; j < n; ++j) {
+      float dd = orc_d2(surface_xyz + 3 * (size_t)j, q);
+      if (dd <= r2) nbs.push_back({dd, j});
+    }
+    sort_truncate(nbs, max_nn);
+    for (size_t s = 0; s < nbs.size(); ++s) {
+      if (total + (int64_t)s < cap) {
+        if (idx) idx[total + s] = nbs[s].idx;
+        if (d2) d2[total + s] = nbs[s].d2;
+      }
+    }
+    total += (int64_t)nbs.size();
+    offsets[qi + 1] = total;
+  }
+  return total;
+}
+
+int orc_normals(const float* xyz, int n, double r, int max_nn, const float* vp, float* out_n4,
+                int32_t* out_k, int nthreads) {
+  CellGrid grid(xyz, n, r);
+  const float r2 = r2_of(r);
+  const float zero[3] = {0, 0, 0};
+  if (!vp) vp = zero;
+  nthreads = resolve_threads(nthreads);
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<Nb> nbs;
+#pragma omp for schedule(dynamic, 512)
+    for (int i = 0; i < n; ++i) {
+      const float* q = xyz + 3 * (size_t)i;
+      grid.query(q, r2, nbs);
+      if (max_nn > 0 && (int)nbs.size() > max_nn) sort_truncate(nbs, max_nn);
+      pca_normal(xyz, q, nbs, vp, out_n4 + 4 * (size_t)i);
+      if (out_k) out_k[i] = (int32_t)nbs.size();
+    }
+  }
+  return 0;
+}
+
+int orc_rsd(const float* xyz, const float* normals, int normal_stride, int n, double r,
+            int max_nn, int ndiv, double plane_radius, int flags, float* r_min, float* r_max,
+            float* r_dif, int nthreads) {
+  if (ndiv <= 0) return -1;
+  CellGrid grid(xyz, n, r);
+  const float r2 = r2_of(r);
+  nthreads = resolve_threads(nthreads);
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<Nb> nbs;
+#pragma omp for schedule(dynamic, 512)
+    for (int i = 0; i < n; ++i) {
+      grid.query(xyz + 3 * (size_t)i, r2, nbs);
+      sort_truncate(nbs, max_nn);
+      double mn, mx;
+      rsd_core(xyz, normals, normal_stride, nbs, i, normals + (size_t)normal_stride * i, r, ndiv,
+               plane_radius, flags, &mn, &mx);
+      if (r_min) r_min[i] = (float)mn;  // radius_estimation.cpp:200-202
+      if (r_max) r_max[i] = (float)mx;
+      if (r_dif) r_dif[i] = (float)(mx - mn);
+    }
+  }
+  return 0;
+}
+
+int orc_rsd_queries(const float* surface_xyz, const float* normals, int normal_stride, int n,
+                    const float* query_xyz, int nq, double r, int max_nn, int ndiv,
+                    double plane_radius, int flags, float* r_min, float* r_max, int nthreads) {
+  if (ndiv <= 0) return -1;
+  CellGrid grid(surface_xyz, n, r);
+  const float r2 = r2_of(r);
+  nthreads = resolve_threads(nthreads);
+  const float zero_n[3] = {0, 0, 0};
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<Nb> nbs;
+#pragma omp for schedule(dynamic, 64)
+    for (int i = 0; i < nq; ++i) {
+      grid.query(query_xyz + 3 * (size_t)i, r2, nbs);
+      sort_truncate(nbs, max_nn);
+      double mn, mx;
+      rsd_core(surface_xyz, normals, normal_stride, nbs, -1, zero_n, r, ndiv, plane_radius,
+               flags | ORC_RSD_REF_IS_NEAREST, &mn, &mx);
+      r_min[i] = (float)mn;
+      r_max[i] = (float)mx;
+    }
+  }
+  return 0;
+}
+
+int orc_rsd_ref_faithful(const float* xyz, const float* normals, int normal_stride, int n,
+                         double r, int max_nn, int ndiv, double plane_radius, float* r_min,
+                         float* r_max, double* phase_s) {
+  using clk = std::chrono::steady_clock;
+  auto secs = [](clk::time_point a, clk::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
+  const float r2 = r2_of(r);
+  auto t0 = clk::now();
+  KdTree tree(xyz, n);  // radius_estimation.cpp:103-109
+  auto t1 = clk::now();
+  // materialised neighbour lists, radius_estimation.cpp:112-124
+  std::vector<std::vector<int>> points_indices(n);
+  std::vector<std::vector<float>> points_sqr_distances(n);
+  std::vector<Nb> nbs;
+  for (int cp = 0; cp < n; ++cp) {
+    tree.radius(xyz + 3 * (size_t)cp, (float)r, r2, nbs);
+    sort_truncate(nbs, max_nn);
+    points_indices[cp].resize(nbs.size());
+    points_sqr_distances[cp].resize(nbs.size());
+    for (size_t s = 0; s < nbs.size(); ++s) {
+      points_indices[cp][s] = nbs[s].idx;
+      points_sqr_distances[cp][s] = nbs[s].d2;
+    }
+  }
+  auto t2 = clk::now();
+  for (int cp = 0; cp < n; ++cp) {  // radius_estimation.cpp:140-215
+    nbs.resize(points_indices[cp].size());
+    for (size_t s = 0; s < nbs.size(); ++s) nbs[s] = {points_sqr_distances[cp][s], points_indices[cp][s]};
+    double mn, mx;
+    rsd_core(xyz, normals, normal_stride, nbs, cp, normals + (size_t)normal_stride * cp, r, ndiv,
+             plane_radius, 0, &mn, &mx);
+    if (r_min) r_min[cp] = (float)mn;
+    if (r_max) r_max[cp] = (float)mx;
+  }
+  auto t3 = clk::now();
+  if (phase_s) {
+    phase_s[0] = secs(t0, t1);
+    phase_s[1] = secs(t1, t2);
+    phase_s[2] = secs(t2, t3);
+  }
+  return 0;
+}
+
+int orc_voxel_grid(const float* xyz, int n, float leaf, int32_t* min_b, int32_t* div_b,
+                   float* centroids, int32_t* layout, int32_t* counts) {
+  // pcl::VoxelGrid::applyFilter [EXTERNAL]: inverse leaf in fp32, fp32 multiply, floor.
+  const float inv = 1.0f / leaf;
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int nf = 0;
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * (size_t)i;
+    if (!finite3(p)) continue;
+    ++nf;
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = std::min(mn[a], p[a]);
+      mx[a] = std::max(mx[a], p[a]);
+    }
+  }
+  if (nf == 0) {
+    for (int a = 0; a < 3; ++a) min_b[a] = div_b[a] = 0;
+    return 0;
+  }
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = (int32_t)std::floor(mn[a] * inv);
+    int32_t max_b = (int32_t)std::floor(mx[a] * inv);
+    div_b[a] = max_b - min_b[a] + 1;
+  }
+  int64_t cells = (int64_t)div_b[0] * div_b[1] * div_b[2];
+  std::vector<std::pair<int64_t, int32_t>> keyed;
+  keyed.reserve(nf);
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * (size_t)i;
+    if (!finite3(p)) continue;
+    int ijk0 = (int)(std::floor(p[0] * inv) - min_b[0]);
+    int ijk1 = (int)(std::floor(p[1] * inv) - min_b[1]);
+    int ijk2 = (int)(std::floor(p[2] * inv) - min_b[2]);
+    keyed.emplace_back((int64_t)ijk0 + (int64_t)ijk1 * div_b[0] + (int64_t)ijk2 * div_b[0] * div_b[1], i);
+  }
+  std::sort(keyed.begin(), keyed.end());
+  int nvox = 0;
+  if (layout)
+    for (int64_t c = 0; c < cells; ++c) layout[c] = -1;
+  size_t i = 0;
+  while (i < keyed.size()) {
+    size_t j = i;
+    double s[3] = {0, 0, 0};
+    while (j < keyed.size() && keyed[j].first == keyed[i].first) {
+      const float* p = xyz + 3 * (size_t)keyed[j].second;
+      s[0] += p[0];
+      s[1] += p[1];
+      s[2] += p[2];
+      ++j;
+    }
+    if (centroids) {
+      double cnt = (double)(j - i);
+      for (int a = 0; a < 3; ++a) centroids[3 * (size_t)nvox + a] = (float)(s[a] / cnt);
+    }
+    if (layout) layout[keyed[i].first] = nvox;
+    if (counts) counts[nvox] = (int32_t)(j - i);
+    ++nvox;
+    i = j;
+  }
+  return nvox;
+}
+
+int orc_get_type(float min_radius, float max_radius) {
+  // grsd_colorCHLAC_tools.hpp:104-116; class ids grsd_colorCHLAC_tools.h:10-16
+  if (min_radius > 0.100)
+    return 1;  // PLANE
+  else if (max_radius > 0.175)
+    return 2;  // CYLINDER
+  else if (min_radius < 0.015)
+    return 0;  // NOISE
+  else if (max_radius - min_radius < 0.050)
+    return 3;  // SPHERE
+  else
+    return 4;  // EDGE
+}
+
+void orc_offsets26(int32_t* out) {
+  int32_t off[26][3];
+  fill_offsets26(off);
+  std::memcpy(out, off, sizeof(off));
+}
+
+int orc_grsd_transitions(const float* centroids, int nvox, const int32_t* types, float leaf,
+                         const int32_t* min_b, const int32_t* div_b, const int32_t* layout,
+                         int32_t* transition36, int32_t* hist21) {
+  const float inv = 1.0f / leaf;
+  int32_t off[26][3];
+  fill_offsets26(off);
+  int32_t M[6][6];
+  std::memset(M, 0, sizeof(M));
+  for (int v = 0; v < nvox; ++v) {  // grsd_colorCHLAC_tools.hpp:230-260, hist_num == 1
+    int src = types[v];
+    for (int o = 0; o < 26; ++o) {
+      int nb = neighbor_centroid(centroids + 3 * (size_t)v, inv, min_b, div_b, layout, off[o]);
+      int nt = (nb == -1) ? 5 : types[nb];
+      M[src][nt]++;
+    }
+  }
+  if (transition36) std::memcpy(transition36, M, sizeof(M));
+  if (hist21) {  // :266-276
+    int nrf = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) hist21[nrf++] = M[i][j];
+  }
+  return 0;
+}
+
+int orc_grsd21_subdiv(const float* centroids, int nvox, const int32_t* types, float leaf,
+                      const int32_t* min_b, const int32_t* div_b, const int32_t* layout,
+                      int subdivision_size, int off_x, int off_y, int off_z, int32_t* subdiv_b,
+                      int32_t* hist21) {
+  // grsd_colorCHLAC_tools.hpp:140-161
+  if (subdivision_size < 0) return -1;
+  int hist_num = 1;
+  float inverse_subdivision_size = 0.f;
+  int sb[3] = {1, 1, 1};
+  if (subdivision_size > 0) {
+    inverse_subdivision_size = 1.0 / subdivision_size;
+    if (div_b[0] <= off_x || div_b[1] <= off_y || div_b[2] <= off_z) {
+      if (subdiv_b) subdiv_b[0] = subdiv_b[1] = subdiv_b[2] = 0;
+      return 0;
+    }
+    sb[0] = (int)std::ceil((div_b[0] - off_x) * inverse_subdivision_size);
+    sb[1] = (int)std::ceil((div_b[1] - off_y) * inverse_subdivision_size);
+    sb[2] = (int)std::ceil((div_b[2] - off_z) * inverse_subdivision_size);
+    hist_num = sb[0] * sb[1] * sb[2];
+  }
+  if (subdiv_b) {
+    subdiv_b[0] = sb[0];
+    subdiv_b[1] = sb[1];
+    subdiv_b[2] = sb[2];
+  }
+  if (!hist21) return hist_num;
+  const float inv = 1.0f / leaf;
+  int32_t off[26][3];
+  fill_offsets26(off);
+  std::vector<int32_t> M((size_t)hist_num * 36, 0);
+  for (int v = 0; v < nvox; ++v) {
+    int hist_idx = 0;
+    const float* c = centroids + 3 * (size_t)v;
+    if (hist_num != 1) {  // :233-246
+      const int tmp_x = std::floor(c[0] / leaf) - min_b[0] - off_x;
+      const int tmp_y = std::floor(c[1] / leaf) - min_b[1] - off_y;
+      const int tmp_z = std::floor(c[2] / leaf) - min_b[2] - off_z;
+      if (tmp_x < 0 || tmp_y < 0 || tmp_z < 0) continue;
+      int ix = (int)std::floor(tmp_x * inverse_subdivision_size);
+      int iy = (int)std::floor(tmp_y * inverse_subdivision_size);
+      int iz = (int)std::floor(tmp_z * inverse_subdivision_size);
+      hist_idx = ix + iy * sb[0] + iz * sb[0] * sb[1];
+    }
+    int src = types[v];
+    for (int o = 0; o < 26; ++o) {
+      int nb = neighbor_centroid(c, inv, min_b, div_b, layout, off[o]);
+      int nt = (nb == -1) ? 5 : types[nb];
+      M[(size_t)hist_idx * 36 + src * 6 + nt]++;
+    }
+  }
+  for (int h = 0; h < hist_num; ++h) {
+    int nrf = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) hist21[(size_t)h * 21 + nrf++] = M[(size_t)h * 36 + i * 6 + j];
+  }
+  return hist_num;
+}
+
+int orc_grsd21(const float* xyz, const float* normals_in, int normal_stride, int n, float leaf,
+               double r_normals, double rsd_radius_min, int rsd_flags, const float* vp,
+               int32_t* hist21, int32_t* labels, float* radii, int32_t cap_vox,
+               int32_t* nvox_out, int nthreads) {
+  std::vector<float> n4;
+  const float* nrm = normals_in;
+  int stride = normal_stride;
+  if (!nrm) {
+    n4.resize((size_t)n * 4);
+    orc_normals(xyz, n, r_normals, 0, vp, n4.data(), nullptr, nthreads);
+    nrm = n4.data();
+    stride = 4;
+  }
+  int32_t min_b[3], div_b[3];
+  int nvox = orc_voxel_grid(xyz, n, leaf, min_b, div_b, nullptr, nullptr, nullptr);
+  if (nvox_out) *nvox_out = nvox;
+  std::vector<float> cent((size_t)nvox * 3);
+  std::vector<int32_t> layout((size_t)div_b[0] * div_b[1] * div_b[2]);
+  orc_voxel_grid(xyz, n, leaf, min_b, div_b, cent.data(), layout.data(), nullptr);
+  // grsd_colorCHLAC_tools.hpp:172: std::max(rsd_radius_search, voxel_size/2 * sqrt(3)),
+  // float/2 * double -> double
+  double r_rsd = std::max(rsd_radius_min, leaf / 2 * std::sqrt(3));
+  std::vector<float> rmin(nvox), rmax(nvox);
+  // PCL RSDEstimation defaults, never overridden in the tree: nr_subdiv 5, plane_radius 0.2
+  orc_rsd_queries(xyz, nrm, stride, n, cent.data(), nvox, r_rsd, 0, 5, 0.2, rsd_flags, rmin.data(),
+                  rmax.data(), nthreads);
+  std::vector<int32_t> types(nvox);
+  for (int v = 0; v < nvox; ++v) types[v] = orc_get_type(rmin[v], rmax[v]);  // :225-228
+  for (int v = 0; v < nvox && v < cap_vox; ++v) {
+    if (labels) labels[v] = types[v];
+    if (radii) {
+      radii[2 * v] = rmin[v];
+      radii[2 * v + 1] = rmax[v];
+    }
+  }
+  return orc_grsd_transitions(cent.data(), nvox, types.data(), leaf, min_b, div_b, layout.data(),
+                              nullptr, hist21);
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+/*
+ * oracle.h -- CPU restatement of the reference's normals -> RSD -> GRSD path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (mapping-private_b200/,
+ * include/) may include, link or call this.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs use it, as the checker or
+ * as the reported CPU baseline.
+ *
+ * Parity status (see DESIGN.md "Oracle"):
+ *   - RSD arithmetic, get_type, the 26-offset table, transition counting and the
+ *     21-bin packing are restated from in-tree reference sources (cited per
+ *     function); no reference test pins their outputs -> "parity unpinned" for
+ *     normals and radii.
+ *   - voxel occupancy + neighbour lookup are pinned by known answers decoded from
+ *     color_chlac/demos/shape_data/noiseless_*_GRSD_CCHLAC.pcd (tests/golden/).
+ *   - radius search, PCA normals and VoxelGrid live in third-party code that is
+ *     absent from /root/reference (point_cloud_mapping/ANN, PCL 1.5.1 pinned at
+ *     hough_segmentation/CMakeLists.txt:5, FLANN); their published semantics are
+ *     restated and the call sites are cited.
+ *
+ * All entry points are plain C so tests can bind them with ctypes.
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* RSD behaviour flags (DESIGN.md "RSD variants"). Default 0 = in-tree
+ * LocalRadiusEstimation (cloud_algos/src/radius_estimation.cpp:140-215). */
+#define ORC_RSD_REF_IS_NEAREST 1 /* reference element = nearest surface point (PCL RSDEstimation) */
+#define ORC_RSD_SEED_BIN0 2      /* bin 0 starts at angle 0 (newer PCL) */
+#define ORC_RSD_SCALE_SORT 4     /* r_min*=1.1, r_max*=0.9, then order (newer PCL) */
+
+/* Squared distance under the documented epsilon rule: fp32, (dx*dx+dy*dy)+dz*dz,
+ * no FMA contraction. */
+float orc_d2(const float* a, const float* b);
+
+/* Radius search over `surface` for each query position.
+ *   neighbour  <=>  orc_d2(surface[j], query) <= (float)r*(float)r
+ * Results per query sorted by (d2, index) ascending and truncated to max_nn
+ * (max_nn <= 0 = unlimited) -- restates kdtree_->radiusSearch(cp, radius_, idx,
+ * d2, max_nn_) as used at radius_estimation.cpp:120 [EXTERNAL semantics].
+ * offsets has nq+1 entries. idx/d2 may be NULL (count only). Returns the total
+ * number of neighbours; if it exceeds cap only offsets are filled. */
+int64_t orc_radius_search(const float* surface_xyz, int n, const float* query_xyz, int nq,
+                          double r, int max_nn, int64_t* offsets, int32_t* idx, float* d2,
+                          int64_t cap, int nthreads);
+
+/* O(N*Q) brute-force variant of the above, for cross-checks on small inputs. */
+int64_t orc_radius_search_brute(const float* surface_xyz, int n, const float* query_xyz, int nq,
+                                double r, int max_nn, int64_t* offsets, int32_t* idx, float* d2,
+                                int64_t cap);
+
+/* PCA normals, pcl::NormalEstimation semantics [EXTERNAL] as called at
+ * grsd_colorCHLAC_tools.hpp:76-81: neighbourhood within r (self included),
+ * smallest-eigenvalue eigenvector of the covariance, curvature = l0/(l0+l1+l2),
+ * flipped so that n.(vp - p) >= 0; fewer than 3 neighbours -> NaN.
+ * out_n4: n x {nx,ny,nz,curvature}; out_k (optional): neighbour counts. */
+int orc_normals(const float* xyz, int n, double r, int max_nn, const float* vp,
+                float* out_n4, int32_t* out_k, int nthreads);
+
+/* RSD for every point of a cloud with per-point normals (stride floats apart).
+ * Restates radius_estimation.cpp:140-215.  Outputs are fp32 like the reference's
+ * channels (r_dif = (float)(double r_max - double r_min)). */
+int orc_rsd(const float* xyz, const float* normals, int normal_stride, int n, double r,
+            int max_nn, int ndiv, double plane_radius, int flags, float* r_min, float* r_max,
+            float* r_dif, int nthreads);
+
+/* RSD at arbitrary query positions over a surface cloud (the
+ * pcl::RSDEstimation + setSearchSurface use at grsd_colorCHLAC_tools.hpp:164-180). */
+int orc_rsd_queries(const float* surface_xyz, const float* normals, int normal_stride, int n,
+                    const float* query_xyz, int nq, double r, int max_nn, int ndiv,
+                    double plane_radius, int flags, float* r_min, float* r_max, int nthreads);
+
+/* Same as orc_rsd but organised like the reference: build a kd-tree, materialise
+ * every neighbour list, then run the estimation loop; the three phases are timed
+ * where the reference logs them (radius_estimation.cpp:108,125,216).
+ * phase_s[3] = {tree build, neighbour search, estimation} seconds. 1 thread. */
+int orc_rsd_ref_faithful(const float* xyz, const float* normals, int normal_stride, int n,
+                         double r, int max_nn, int ndiv, double plane_radius, float* r_min,
+                         float* r_max, double* phase_s);
+
+/* pcl::VoxelGrid with setSaveLeafLayout(true) [EXTERNAL], as used at
+ * grsd_colorCHLAC_tools.hpp:94-100.  Call with centroids == NULL to get sizes.
+ *   min_b[3], div_b[3]; returns number of occupied voxels V.
+ *   centroids: V x 3 (mean xyz, voxels ordered by linear index x-fastest)
+ *   layout: div_b[0]*div_b[1]*div_b[2] ints, voxel -> centroid index or -1
+ *   counts: V point counts (optional) */
+int orc_voxel_grid(const float* xyz, int n, float leaf, int32_t* min_b, int32_t* div_b,
+                   float* centroids, int32_t* layout, int32_t* counts);
+
+/* grsd_colorCHLAC_tools.hpp:104-116 */
+int orc_get_type(float min_radius, float max_radius);
+
+/* 26-neighbour offsets in the reference's order (grsd_colorCHLAC_tools.hpp:187-222);
+ * out: 26 x 3 ints. */
+void orc_offsets26(int32_t* out);
+
+/* Transition counting + packing for precomputed voxel labels
+ * (grsd_colorCHLAC_tools.hpp:230-292 with hist_num == 1).
+ *   transition36: 6x6 row-major M(src, nbr); hist21: upper triangle. */
+int orc_grsd_transitions(const float* centroids, int nvox, const int32_t* types, float leaf,
+                         const int32_t* min_b, const int32_t* div_b, const int32_t* layout,
+                         int32_t* transition36, int32_t* hist21);
+
+/* Whole GRSD-21 recipe for one cluster (exampleRSD.cpp:50-93 +
+ * extractGRSDSignature21): normals(r_normals) -> voxel grid(leaf) -> RSD at the
+ * centroids with r = max(rsd_radius_min, leaf/2*sqrt(3)), ndiv = 5, plane_radius
+ * = 0.2, reference element = nearest surface point -> labels -> transitions.
+ * normals_in may be NULL (then computed with viewpoint vp).  Optional debug
+ * outputs (may be NULL): labels (cap_vox), radii (cap_vox x 2), nvox. */
+int orc_grsd21(const float* xyz, const float* normals_in, int normal_stride, int n, float leaf,
+               double r_normals, double rsd_radius_min, int rsd_flags, const float* vp,
+               int32_t* hist21, int32_t* labels, float* radii, int32_t cap_vox,
+               int32_t* nvox_out, int nthreads);
+
+/* Subdivision variant (hist_num > 1), grsd_colorCHLAC_tools.hpp:140-161,233-246.
+ * Call with hist21 == NULL to get subdiv_b[3]; returns hist_num (0 if offsets
+ * exceed the grid, -1 on invalid subdivision size). */
+int orc_grsd21_subdiv(const float* centroids, int nvox, const int32_t* types, float leaf,
+                      const int32_t* min_b, const int32_t* div_b, const int32_t* layout,
+                      int subdivision_size, int off_x, int off_y, int off_z, int32_t* subdiv_b,
+                      int32_t* hist21);
+
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

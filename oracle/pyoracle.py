@@ -1,0 +1,216 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs -- never by the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+import subprocess
+
+import numpy as np
+
+_DIR = pathlib.Path(__file__).resolve().parent
+_LIB = None
+
+RSD_REF_IS_NEAREST = 1
+RSD_SEED_BIN0 = 2
+RSD_SCALE_SORT = 4
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> pathlib.Path:
+    so = _DIR / "liboracle.so"
+    src = [_DIR / "oracle.cpp", _DIR / "oracle.h"]
+    if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in src):
+        subprocess.run(["make", "-C", str(_DIR), "-B" if force else "-s", "liboracle.so"], check=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = _DIR / "liboracle.so"
+        if not so.exists():
+            build()
+        _LIB = C.CDLL(str(so))
+        _LIB.orc_radius_search.restype = C.c_int64
+        _LIB.orc_radius_search_brute.restype = C.c_int64
+        _LIB.orc_d2.restype = C.c_float
+    return _LIB
+
+
+def _xyz(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] == 3
+    return a
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty)) if a is not None else None
+
+
+def radius_search(surface, queries, r, max_nn=0, brute=False, nthreads=0):
+    """Returns (offsets int64 (nq+1), idx int32, d2 float32), sorted by (d2, idx)."""
+    L = lib()
+    s, q = _xyz(surface), _xyz(queries)
+    off = np.zeros(q.shape[0] + 1, dtype=np.int64)
+    if brute:
+        total = L.orc_radius_search_brute(_ptr(s, C.c_float), s.shape[0], _ptr(q, C.c_float), q.shape[0],
+                                          C.c_double(r), int(max_nn), _ptr(off, C.c_int64), None, None, C.c_int64(0))
+    else:
+        total = L.orc_radius_search(_ptr(s, C.c_float), s.shape[0], _ptr(q, C.c_float), q.shape[0], C.c_double(r),
+                                    int(max_nn), _ptr(off, C.c_int64), None, None, C.c_int64(0), int(nthreads))
+    idx = np.zeros(max(total, 1), dtype=np.int32)
+    d2 = np.zeros(max(total, 1), dtype=np.float32)
+    if brute:
+        L.orc_radius_search_brute(_ptr(s, C.c_float), s.shape[0], _ptr(q, C.c_float), q.shape[0], C.c_double(r),
+                                  int(max_nn), _ptr(off, C.c_int64), _ptr(idx, C.c_int32), _ptr(d2, C.c_float),
+                                  C.c_int64(total))
+    else:
+        L.orc_radius_search(_ptr(s, C.c_float), s.shape[0], _ptr(q, C.c_float), q.shape[0], C.c_double(r),
+                            int(max_nn), _ptr(off, C.c_int64), _ptr(idx, C.c_int32), _ptr(d2, C.c_float),
+                            C.c_int64(total), int(nthreads))
+    return off, idx[:total], d2[:total]
+
+
+def normals(xyz, r, max_nn=0, vp=(0.0, 0.0, 0.0), nthreads=0):
+    """Returns (n4 float32 (n,4) = nx,ny,nz,curvature ; k int32 (n,))."""
+    L = lib()
+    p = _xyz(xyz)
+    out = np.empty((p.shape[0], 4), dtype=np.float32)
+    k = np.empty(p.shape[0], dtype=np.int32)
+    v = np.asarray(vp, dtype=np.float32)
+    L.orc_normals(_ptr(p, C.c_float), p.shape[0], C.c_double(r), int(max_nn), _ptr(v, C.c_float),
+                  _ptr(out, C.c_float), _ptr(k, C.c_int32), int(nthreads))
+    return out, k
+
+
+def rsd(xyz, nrm, r, max_nn=0, ndiv=10, plane_radius=0.1, flags=0, nthreads=0):
+    """In-tree LocalRadiusEstimation arithmetic. nrm: (n,3) or (n,4). Returns r_min, r_max, r_dif."""
+    L = lib()
+    p = _xyz(xyz)
+    nn = np.ascontiguousarray(nrm, dtype=np.float32)
+    n = p.shape[0]
+    rmin = np.empty(n, np.float32)
+    rmax = np.empty(n, np.float32)
+    rdif = np.empty(n, np.float32)
+    rc = L.orc_rsd(_ptr(p, C.c_float), _ptr(nn, C.c_float), int(nn.shape[1]), n, C.c_double(r), int(max_nn),
+                   int(ndiv), C.c_double(plane_radius), int(flags), _ptr(rmin, C.c_float), _ptr(rmax, C.c_float),
+                   _ptr(rdif, C.c_float), int(nthreads))
+    assert rc == 0
+    return rmin, rmax, rdif
+
+
+def rsd_queries(surface, nrm, queries, r, max_nn=0, ndiv=5, plane_radius=0.2, flags=0, nthreads=0):
+    L = lib()
+    p, q = _xyz(surface), _xyz(queries)
+    nn = np.ascontiguousarray(nrm, dtype=np.float32)
+    rmin = np.empty(q.shape[0], np.float32)
+    rmax = np.empty(q.shape[0], np.float32)
+    rc = L.orc_rsd_queries(_ptr(p, C.c_float), _ptr(nn, C.c_float), int(nn.shape[1]), p.shape[0],
+                           _ptr(q, C.c_float), q.shape[0], C.c_double(r), int(max_nn), int(ndiv),
+                           C.c_double(plane_radius), int(flags), _ptr(rmin, C.c_float), _ptr(rmax, C.c_float),
+                           int(nthreads))
+    assert rc == 0
+    return rmin, rmax
+
+
+def rsd_ref_faithful(xyz, nrm, r, max_nn=0, ndiv=10, plane_radius=0.1):
+    """kd-tree + materialised lists + estimation, 1 thread. Returns r_min, r_max, phase seconds (3,)."""
+    L = lib()
+    p = _xyz(xyz)
+    nn = np.ascontiguousarray(nrm, dtype=np.float32)
+    n = p.shape[0]
+    rmin = np.empty(n, np.float32)
+    rmax = np.empty(n, np.float32)
+    ph = np.zeros(3, np.float64)
+    L.orc_rsd_ref_faithful(_ptr(p, C.c_float), _ptr(nn, C.c_float), int(nn.shape[1]), n, C.c_double(r),
+                           int(max_nn), int(ndiv), C.c_double(plane_radius), _ptr(rmin, C.c_float),
+                           _ptr(rmax, C.c_float), _ptr(ph, C.c_double))
+    return rmin, rmax, ph
+
+
+def voxel_grid(xyz, leaf):
+    """Returns dict(min_b, div_b, centroids (V,3), layout (cells,), counts (V,))."""
+    L = lib()
+    p = _xyz(xyz)
+    min_b = np.zeros(3, np.int32)
+    div_b = np.zeros(3, np.int32)
+    nv = L.orc_voxel_grid(_ptr(p, C.c_float), p.shape[0], C.c_float(leaf), _ptr(min_b, C.c_int32),
+                          _ptr(div_b, C.c_int32), None, None, None)
+    cent = np.zeros((max(nv, 1), 3), np.float32)
+    layout = np.zeros(max(int(np.prod(div_b.astype(np.int64))), 1), np.int32)
+    counts = np.zeros(max(nv, 1), np.int32)
+    L.orc_voxel_grid(_ptr(p, C.c_float), p.shape[0], C.c_float(leaf), _ptr(min_b, C.c_int32),
+                     _ptr(div_b, C.c_int32), _ptr(cent, C.c_float), _ptr(layout, C.c_int32), _ptr(counts, C.c_int32))
+    return dict(min_b=min_b, div_b=div_b, centroids=cent[:nv], layout=layout, counts=counts[:nv], nvox=nv)
+
+
+def get_type(rmin, rmax):
+    return lib().orc_get_type(C.c_float(rmin), C.c_float(rmax))
+
+
+def offsets26():
+    o = np.zeros((26, 3), np.int32)
+    lib().orc_offsets26(_ptr(o, C.c_int32))
+    return o
+
+
+def grsd_transitions(grid, types):
+    L = lib()
+    t = np.ascontiguousarray(types, dtype=np.int32)
+    M = np.zeros((6, 6), np.int32)
+    h = np.zeros(21, np.int32)
+    cent = np.ascontiguousarray(grid["centroids"], np.float32)
+    L.orc_grsd_transitions(_ptr(cent, C.c_float), int(grid["nvox"]), _ptr(t, C.c_int32), C.c_float(grid["leaf"]),
+                           _ptr(grid["min_b"], C.c_int32), _ptr(grid["div_b"], C.c_int32),
+                           _ptr(grid["layout"], C.c_int32), _ptr(M, C.c_int32), _ptr(h, C.c_int32))
+    return M, h
+
+
+def grsd21_subdiv(grid, types, subdivision_size, off=(0, 0, 0)):
+    L = lib()
+    t = np.ascontiguousarray(types, dtype=np.int32)
+    cent = np.ascontiguousarray(grid["centroids"], np.float32)
+    sb = np.zeros(3, np.int32)
+    args = (_ptr(cent, C.c_float), int(grid["nvox"]), _ptr(t, C.c_int32), C.c_float(grid["leaf"]),
+            _ptr(grid["min_b"], C.c_int32), _ptr(grid["div_b"], C.c_int32), _ptr(grid["layout"], C.c_int32),
+            int(subdivision_size), int(off[0]), int(off[1]), int(off[2]), _ptr(sb, C.c_int32))
+    hn = L.orc_grsd21_subdiv(*args, None)
+    if hn <= 0:
+        return hn, sb, np.zeros((0, 21), np.int32)
+    h = np.zeros((hn, 21), np.int32)
+    L.orc_grsd21_subdiv(*args, _ptr(h, C.c_int32))
+    return hn, sb, h
+
+
+def grsd21(xyz, leaf, r_normals=0.02, rsd_radius_min=0.01, rsd_flags=0, normals_in=None, vp=(0.0, 0.0, 0.0),
+           nthreads=0, cap_vox=1 << 20):
+    """Whole recipe for one cluster. Returns dict(hist21, labels, radii (V,2), nvox)."""
+    L = lib()
+    p = _xyz(xyz)
+    h = np.zeros(21, np.int32)
+    labels = np.zeros(cap_vox, np.int32)
+    radii = np.zeros((cap_vox, 2), np.float32)
+    nv = C.c_int32(0)
+    v = np.asarray(vp, dtype=np.float32)
+    nn = None
+    stride = 0
+    if normals_in is not None:
+        nn = np.ascontiguousarray(normals_in, dtype=np.float32)
+        stride = int(nn.shape[1])
+    rc = L.orc_grsd21(_ptr(p, C.c_float), _ptr(nn, C.c_float), stride, p.shape[0], C.c_float(leaf),
+                      C.c_double(r_normals), C.c_double(rsd_radius_min), int(rsd_flags), _ptr(v, C.c_float),
+                      _ptr(h, C.c_int32), _ptr(labels, C.c_int32), _ptr(radii, C.c_float), int(cap_vox),
+                      C.byref(nv), int(nthreads))
+    assert rc == 0
+    return dict(hist21=h, labels=labels[: nv.value].copy(), radii=radii[: nv.value].copy(), nvox=nv.value)
+
+
+def num_threads():
+    return lib().orc_num_threads()

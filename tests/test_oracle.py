@@ -1,0 +1,310 @@
+"""Pins the CPU oracle: brute-force / scipy cross-checks of the neighbour sets, analytic
+known answers for normals and RSD radii, the get_type truth table, hand-built voxel blocks,
+subdivision cases and the known answers decoded from the reference's shape_data goldens
+(tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+from scipy.spatial import cKDTree
+
+from mapping_private_b200 import synth
+
+
+def _sets(off, idx):
+    return [idx[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+def test_d2_rule(oracle):
+    L = oracle.lib()
+    import ctypes as C
+    a = np.array([0.1, 0.2, 0.3], np.float32)
+    b = np.array([0.11, 0.18, 0.33], np.float32)
+    d = a - b
+    want = np.float32(np.float32(np.float32(d[0] * d[0]) + np.float32(d[1] * d[1])) + np.float32(d[2] * d[2]))
+    got = L.orc_d2(a.ctypes.data_as(C.POINTER(C.c_float)), b.ctypes.data_as(C.POINTER(C.c_float)))
+    assert np.float32(got) == want
+
+
+@pytest.mark.parametrize("max_nn", [0, 20])
+def test_radius_search_vs_brute(oracle, max_nn):
+    p = synth.tabletop(6000)
+    q = p[::7]
+    o1, i1, d1 = oracle.radius_search(p, q, 0.03, max_nn=max_nn)
+    o2, i2, d2 = oracle.radius_search(p, q, 0.03, max_nn=max_nn, brute=True)
+    assert np.array_equal(o1, o2) and np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    # sorted by (d2, idx), self first
+    for s, (a, b) in enumerate(zip(o1[:-1], o1[1:])):
+        dd, ii = d1[a:b], i1[a:b]
+        assert np.all(np.diff(dd) >= 0)
+        assert dd[0] == 0.0
+
+
+def test_radius_search_vs_scipy(oracle):
+    # lattice coordinates make d2 exact, so a float64 k-d tree must agree bit-for-bit
+    p = synth.tabletop(20000)
+    r = 0.02
+    r2 = float(np.float32(r) * np.float32(r))
+    off, idx, d2 = oracle.radius_search(p, p, r)
+    tree = cKDTree(p.astype(np.float64))
+    lists = tree.query_ball_point(p.astype(np.float64), np.sqrt(r2) * (1 + 1e-9))
+    for i in range(0, p.shape[0], 13):
+        cand = np.array(lists[i])
+        dd = np.sum((p[cand].astype(np.float64) - p[i].astype(np.float64)) ** 2, axis=1)
+        want = np.sort(cand[dd <= r2])
+        got = np.sort(idx[off[i]:off[i + 1]])
+        assert np.array_equal(want, got)
+
+
+def test_radius_search_edge_cases(oracle):
+    empty = np.zeros((0, 3), np.float32)
+    off, idx, _ = oracle.radius_search(empty, empty, 0.02)
+    assert off.tolist() == [0] and idx.size == 0
+    one = np.array([[1, 2, 3]], np.float32)
+    off, idx, d2 = oracle.radius_search(one, one, 0.02)
+    assert off.tolist() == [0, 1] and idx.tolist() == [0] and d2.tolist() == [0.0]
+    # duplicates and a point exactly at the radius (inclusive rule d2 <= r2)
+    r = np.float32(0.0625)
+    p = np.array([[0, 0, 0], [0, 0, 0], [r, 0, 0], [np.nextafter(r, np.float32(1)), 0, 0], [np.nan, 0, 0]], np.float32)
+    off, idx, d2 = oracle.radius_search(p, p[:1], float(r))
+    assert idx.tolist() == [0, 1, 2]
+
+
+def test_normals_analytic(oracle):
+    plane = synth.analytic_shape("plane", 8000)
+    n4, k = oracle.normals(plane, 0.02)
+    assert np.all(np.abs(np.abs(n4[:, 2]) - 1) < 1e-6) and np.all(n4[:, 3] < 1e-6)
+    # viewpoint (0,0,0) is below the plane z=1 -> normals point down
+    assert np.all(n4[:, 2] < 0)
+    sph = synth.analytic_shape("sphere", 20000, R=0.05)
+    n4, k = oracle.normals(sph, 0.01)
+    radial = (sph - np.array([0.5, 0.5, 1.0], np.float32)) / 0.05
+    cosang = np.abs(np.sum(radial * n4[:, :3], axis=1))
+    assert np.percentile(np.degrees(np.arccos(np.clip(cosang, 0, 1))), 99) < 3.0
+    assert np.allclose(np.linalg.norm(n4[:, :3], axis=1), 1, atol=1e-6)
+    # fewer than 3 neighbours -> NaN
+    lone = np.array([[0, 0, 0], [1, 0, 0], [1, 0.001, 0]], np.float32)
+    n4, k = oracle.normals(lone, 0.02)
+    assert k.tolist() == [1, 2, 2] and np.all(np.isnan(n4))
+
+
+def test_normals_vs_numpy_pca(oracle):
+    p = synth.tabletop(5000, noise_sigma=0.0005)
+    r = 0.03
+    n4, k = oracle.normals(p, r)
+    off, idx, _ = oracle.radius_search(p, p, r)
+    for i in range(0, 5000, 97):
+        nb = p[idx[off[i]:off[i + 1]]].astype(np.float64)
+        assert nb.shape[0] == k[i]
+        w, v = np.linalg.eigh(np.cov(nb.T, bias=True))
+        n = v[:, 0]
+        if (w[1] - w[0]) / w.sum() < 1e-6:
+            continue
+        ang = np.linalg.norm(np.cross(n, n4[i, :3].astype(np.float64)))  # sin(angle), sign-insensitive
+        assert ang < 2e-6
+        assert abs(w[0] / w.sum() - n4[i, 3]) < 1e-6
+
+
+def test_rsd_analytic(oracle):
+    plane = synth.analytic_shape("plane", 8000)
+    n4, _ = oracle.normals(plane, 0.02)
+    rmin, rmax, rdif = oracle.rsd(plane, n4, 0.02)
+    assert np.all(rmin == np.float32(0.1)) and np.all(rmax == np.float32(0.1)) and np.all(rdif == 0)
+    sph = synth.analytic_shape("sphere", 20000, R=0.05)
+    n4, _ = oracle.normals(sph, 0.02)
+    rmin, rmax, _ = oracle.rsd(sph, n4, 0.02)
+    assert abs(np.median(rmin) - 0.05) < 0.0075 and abs(np.median(rmax) - 0.05) < 0.0075
+    cyl = synth.analytic_shape("cylinder", 20000, R=0.04)
+    n4, _ = oracle.normals(cyl, 0.02)
+    rmin, rmax, _ = oracle.rsd(cyl, n4, 0.02)
+    inner = np.abs(cyl[:, 2] - 1.0) < 0.12
+    assert abs(np.median(rmin[inner]) - 0.04) < 0.006
+    assert np.median(rmax[inner]) == np.float32(0.1)
+
+
+def test_rsd_matches_python_restatement(oracle):
+    """Independent pure-Python restatement of radius_estimation.cpp:140-202 on a small cloud."""
+    p = synth.tabletop(3000, noise_sigma=0.0003)
+    r, ndiv, plane_r = 0.03, 10, 0.1
+    n4, _ = oracle.normals(p, r)
+    for max_nn in (0, 25):
+        rmin, rmax, rdif = oracle.rsd(p, n4, r, max_nn=max_nn, ndiv=ndiv, plane_radius=plane_r)
+        off, idx, d2 = oracle.radius_search(p, p, r, max_nn=max_nn)
+        nf = n4[:, :3]
+        for cp in range(0, 3000, 41):
+            mn = [np.inf] * ndiv
+            mx = [-np.inf] * ndiv
+            for s in range(off[cp], off[cp + 1]):
+                j = idx[s]
+                if j == cp:
+                    continue
+                c = np.float32(np.float32(np.float32(nf[cp, 0] * nf[j, 0]) + np.float32(nf[cp, 1] * nf[j, 1])) + np.float32(nf[cp, 2] * nf[j, 2]))
+                c = min(1.0, max(-1.0, float(c)))
+                ang = np.arccos(c)
+                if ang > np.pi / 2:
+                    ang = np.pi - ang
+                b = min(ndiv - 1, int(np.floor(ndiv * np.sqrt(float(d2[s])) / r)))
+                mn[b] = min(mn[b], ang)
+                mx[b] = max(mx[b], ang)
+            a_nn = a_nd = a_xx = a_xd = 0.0
+            for di in range(ndiv):
+                if mx[di] >= 0:
+                    f = (di + 0.5) * r / ndiv
+                    a_nn += mn[di] * mn[di]
+                    a_nd += mn[di] * f
+                    a_xx += mx[di] * mx[di]
+                    a_xd += mx[di] * f
+            want_max = plane_r if a_nn == 0 else min(a_nd / a_nn, plane_r)
+            want_min = plane_r if a_xx == 0 else min(a_xd / a_xx, plane_r)
+            assert abs(rmin[cp] - want_min) <= 1e-6 * want_min
+            assert abs(rmax[cp] - want_max) <= 1e-6 * want_max
+            assert abs(rdif[cp] - (want_max - want_min)) <= 1e-6
+
+
+def test_rsd_degenerate_inputs(oracle):
+    # isolated point and NaN normals -> plane_radius
+    p = np.array([[0, 0, 0], [1, 0, 0], [1.001, 0, 0]], np.float32)
+    n = np.array([[0, 0, 1], [np.nan, 0, 0], [0, 0, 1]], np.float32)
+    rmin, rmax, rdif = oracle.rsd(p, n, 0.02, plane_radius=0.1)
+    assert np.all(rmin == np.float32(0.1)) and np.all(rmax == np.float32(0.1))
+    # identical normals -> all angles 0 -> zero denominators -> plane_radius
+    q = synth.analytic_shape("plane", 500)
+    nn = np.tile(np.array([[0, 0, 1]], np.float32), (500, 1))
+    rmin, rmax, _ = oracle.rsd(q, nn, 0.02)
+    assert np.all(rmin == np.float32(0.1))
+
+
+def test_ref_faithful_equals_streaming(oracle):
+    p = synth.tabletop(4000)
+    n4, _ = oracle.normals(p, 0.02)
+    for max_nn in (0, 30):
+        a, b, _ = oracle.rsd(p, n4, 0.02, max_nn=max_nn)
+        c, d, ph = oracle.rsd_ref_faithful(p, n4, 0.02, max_nn=max_nn)
+        assert np.array_equal(a, c) and np.array_equal(b, d) and np.all(ph >= 0)
+
+
+def test_get_type_truth_table(oracle):
+    f = np.float32
+    up = lambda x: float(np.nextafter(f(x), f(10)))
+    dn = lambda x: float(np.nextafter(f(x), f(-10)))
+    # grsd_colorCHLAC_tools.hpp:104-116 (fp32 arguments against double literals)
+    assert oracle.get_type(up(0.100), 0.2) == 1  # PLANE
+    assert oracle.get_type(0.2, 0.2) == 1
+    assert oracle.get_type(dn(0.100), up(0.175)) == 2  # CYLINDER
+    assert oracle.get_type(0.05, 0.2) == 2
+    assert oracle.get_type(dn(0.015), 0.1) == 0  # NOISE
+    assert oracle.get_type(0.0, 0.0) == 0
+    assert oracle.get_type(0.05, 0.055) == 3  # SPHERE
+    assert oracle.get_type(0.02, 0.0699) == 3
+    assert oracle.get_type(0.02, 0.0701) == 4  # EDGE
+    assert oracle.get_type(0.05, 0.15) == 4
+    # float(0.1) > 0.1 (double) because float(0.1) = 0.100000001490116
+    assert oracle.get_type(float(f(0.1)), 0.2) == 1
+    assert oracle.get_type(float(f(0.015)), float(f(0.015))) == 0  # float(0.015) < 0.015
+
+
+def test_offsets26(oracle):
+    o = oracle.offsets26()
+    assert o[0].tolist() == [-1, -1, -1] and o[8].tolist() == [1, 1, -1]
+    assert o[9].tolist() == [-1, -1, 0] and o[11].tolist() == [1, -1, 0] and o[12].tolist() == [-1, 0, 0]
+    assert np.array_equal(o[13:], -o[:13])
+    assert len({tuple(r) for r in o.tolist()}) == 26 and (0, 0, 0) not in {tuple(r) for r in o.tolist()}
+
+
+def test_voxel_grid_semantics(oracle):
+    leaf = 0.01
+    p = np.array([[0.001, 0.001, 0.001], [0.009, 0.003, 0.005], [0.011, 0.001, 0.001], [-0.001, 0.0, 0.0]], np.float32)
+    g = oracle.voxel_grid(p, leaf)
+    assert g["min_b"].tolist() == [-1, 0, 0] and g["div_b"].tolist() == [3, 1, 1] and g["nvox"] == 3
+    assert g["counts"].tolist() == [1, 2, 1]
+    assert np.allclose(g["centroids"][1], [0.005, 0.002, 0.003], atol=1e-7)
+    assert g["layout"].tolist() == [0, 1, 2]
+
+
+def test_transitions_hand_block(oracle):
+    """3x3x3 fully occupied block, centre voxel labelled SPHERE(3), rest PLANE(1)."""
+    leaf = np.float32(0.01)
+    ii, jj, kk = np.meshgrid(range(3), range(3), range(3), indexing="ij")
+    pts = (np.stack([ii, jj, kk], -1).reshape(-1, 3) + 0.5) * 0.01
+    pts = pts.astype(np.float32)
+    g = oracle.voxel_grid(pts, float(leaf))
+    g["leaf"] = float(leaf)
+    assert g["nvox"] == 27
+    types = np.ones(27, np.int32)
+    centre = g["layout"][1 + 1 * 3 + 1 * 9]
+    types[centre] = 3
+    M, h = oracle.grsd_transitions(g, types)
+    # per-voxel in-grid neighbours: 8 corners x7, 12 edges x11, 6 faces x17, centre x26
+    occupied_pairs = 8 * 7 + 12 * 11 + 6 * 17 + 26
+    assert M.sum() == 27 * 26
+    assert M[3, 1] == 26 and M[1, 3] == 26 and M[3, 3] == 0 and M[3, 5] == 0
+    assert M[1, 1] == occupied_pairs - 52
+    assert M[1, 5] == 27 * 26 - occupied_pairs
+    # packing: upper triangle, row-major (grsd_colorCHLAC_tools.hpp:271-275)
+    want = [M[i, j] for i in range(6) for j in range(i, 6)]
+    assert h.tolist() == want and h[20] == 0
+
+
+def test_subdivision_cases(oracle):
+    leaf = 0.01
+    ii, jj, kk = np.meshgrid(range(4), range(4), range(2), indexing="ij")
+    pts = ((np.stack([ii, jj, kk], -1).reshape(-1, 3) + 0.5) * 0.01).astype(np.float32)
+    g = oracle.voxel_grid(pts, leaf)
+    g["leaf"] = leaf
+    types = np.ones(g["nvox"], np.int32)
+    hn, sb, h = oracle.grsd21_subdiv(g, types, 2)
+    assert sb.tolist() == [2, 2, 1] and hn == 4 and h.shape == (4, 21)
+    _, h1 = oracle.grsd_transitions(g, types)
+    assert np.array_equal(h.sum(0), h1)  # subdivisions partition the voxels
+    assert np.all(h.sum(1) == 8 * 26)
+    # offsets >= grid size -> zero vector (grsd_colorCHLAC_tools.hpp:150-153)
+    hn, sb, h = oracle.grsd21_subdiv(g, types, 2, off=(4, 0, 0))
+    assert hn == 0 and sb.tolist() == [0, 0, 0]
+    # negative subdivision size is rejected (:158-161)
+    hn, _, _ = oracle.grsd21_subdiv(g, types, -1)
+    assert hn == -1
+    # offset skips the voxels below it (:243)
+    hn, sb, h = oracle.grsd21_subdiv(g, types, 2, off=(1, 0, 0))
+    assert sb.tolist() == [2, 2, 1] and h.sum() == (3 * 4 * 2) * 26
+    # subdivision_size 0 -> one histogram
+    hn, sb, h = oracle.grsd21_subdiv(g, types, 0)
+    assert hn == 1 and np.array_equal(h[0], h1)
+
+
+@pytest.mark.parametrize("shape", ["plane", "sphere", "cylinder", "torus", "cone"])
+def test_shape_data_known_answers(oracle, kat, shape):
+    """Voxel occupancy + neighbour lookup against the counts decoded from the reference's
+    *_GRSD_CCHLAC.pcd goldens (older revision: 13 half offsets, leaf 0.01)."""
+    xyz = kat[f"{shape}_xyz"]
+    counts = kat[f"{shape}_counts20"]
+    nz = counts[counts != 0]
+    g = oracle.voxel_grid(xyz, 0.01)
+    g["leaf"] = 0.01
+    V = g["nvox"]
+    types = np.ones(V, np.int32)
+    M, _ = oracle.grsd_transitions(g, types)
+    pairs_half = M[1, 1] // 2
+    empties_half = 13 * V - pairs_half
+    assert M[1, 1] % 2 == 0 and M[1, 5] == 26 * V - 2 * pairs_half
+    if shape == "cone":  # two classes in the golden; cross-class pairs were dropped by the old packing
+        assert empties_half == nz[0] + nz[2] == 2113 and V == 308
+    else:
+        assert nz.tolist() == [empties_half, pairs_half]
+        assert 13 * V == nz.sum()
+    expected_V = {"plane": 325, "sphere": 391, "cylinder": 377, "torus": 147, "cone": 308}[shape]
+    assert V == expected_V
+
+
+def test_grsd21_pipeline_smoke(oracle, kat):
+    out = oracle.grsd21(kat["sphere_xyz"], 0.01)
+    assert out["nvox"] == 391 and out["hist21"].sum() == 391 * 26 and out["hist21"][20] == 0
+    assert np.all((out["labels"] >= 0) & (out["labels"] <= 4))
+    plane = oracle.grsd21(kat["plane_xyz"], 0.01)
+    assert np.all(plane["labels"] == 1)  # exact plane -> every voxel PLANE
+    assert plane["hist21"][6] == 2 * 1188 and plane["hist21"][10] == 26 * 325 - 2 * 1188
+
+
+def test_grsd21_cluster_generator(oracle):
+    xyz, off = synth.clusters(3, 1300, 2500)
+    assert off[0] == 0 and off[-1] == xyz.shape[0]
+    for c in range(3):
+        out = oracle.grsd21(xyz[off[c]:off[c + 1]], 0.025)
+        assert 0 < out["hist21"].sum() <= out["nvox"] * 26  # lower triangle is dropped
