@@ -1,0 +1,142 @@
+/*
+ * cloud_algos_b200.h -- C ABI of libcloudalgos_b200.so, the B200 (sm_100a) implementation of
+ * the normals -> RSD -> GRSD hot path of cloud_algos.
+ *
+ * This is the drop-in boundary: plain C types, caller-allocated outputs, no STL / torch / ROS
+ * types.  The C++ plugin shim (mapping-private_b200/host), bench.py and the tests bind exactly
+ * these symbols.  Each entry point cites the reference interface it replaces (paths relative to
+ * the reference tree).  There is no CPU fallback: every call fails with CAB_ERR_CUDA when no
+ * sm_100a device is usable.
+ *
+ * Threading: a cab_ctx owns one CUDA stream and a grow-only device arena; a context must not
+ * be used from two threads at once, different contexts are independent (the reference runs
+ * each plugin instance on the single ros::spin() thread, cloud_algos.h:106-117).
+ * Every call is synchronous: results are valid when it returns.
+ */
+#ifndef CLOUD_ALGOS_B200_H
+#define CLOUD_ALGOS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAB_OK 0
+#define CAB_ERR_ARG (-1)   /* bad argument / call order */
+#define CAB_ERR_CUDA (-2)  /* CUDA runtime error, no device, wrong architecture */
+#define CAB_ERR_OOM (-3)   /* device allocation failed / grid too large */
+#define CAB_ERR_STATE (-4) /* required stage has not been run (no cloud, no grid, no normals) */
+
+/* RSD behaviour flags.  0 = in-tree LocalRadiusEstimation
+ * (cloud_algos/src/radius_estimation.cpp:140-215). */
+#define CAB_RSD_SEED_BIN0 2  /* bin 0 starts at angle 0 (newer pcl::computeRSD) */
+#define CAB_RSD_SCALE_SORT 4 /* r_min*=1.1, r_max*=0.9, then ordered (newer pcl::computeRSD) */
+
+typedef struct cab_ctx cab_ctx;
+
+typedef struct cab_config {
+  int32_t device;       /* CUDA device ordinal */
+  int32_t exact;        /* 1: fp64 neighbour sums + fp64 acos (bit-reproducible on lattice inputs); 0: fp32 fast path */
+  int64_t max_table_cells; /* budget for the dense cell table (0 = default 2^28) */
+} cab_config;
+
+typedef struct cab_timings {
+  float build_ms;   /* last cab_build_grid: bounds + keys + radix sort + reorder + tables */
+  float normals_ms; /* last cab_normals kernel(s) */
+  float rsd_ms;     /* last cab_rsd kernel(s) */
+  float grsd_ms;    /* last cab_grsd_batch, all kernels */
+  float h2d_ms, d2h_ms; /* copies inside the last upload / download calls */
+  int64_t n_points, n_valid, n_packets, n_rows, n_cells;
+  int64_t neighbour_sum; /* sum over queries of in-radius neighbours of the last normals/rsd pass */
+  int64_t candidate_sum; /* sum over queries of candidates tested in that pass */
+  int64_t kernel_launches; /* kernels launched by this library since cab_create (own + CUB) */
+} cab_timings;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int cab_create(const cab_config* cfg, cab_ctx** out);
+void cab_destroy(cab_ctx* ctx);
+/* Message of the last failing call on ctx (ctx may be NULL for cab_create failures). */
+const char* cab_last_error(const cab_ctx* ctx);
+
+/* ---- cloud ---------------------------------------------------------------------------
+ * Replaces the deep copy + `new cloud_kdtree::KdTreeANN(*cloud)` input stage
+ * (radius_estimation.cpp:75-78,103-109): points[] as AoS floats, `stride` floats apart
+ * (3 for geometry_msgs::Point32, 4 for PCL PointXYZ).  Non-finite points are kept at their
+ * index but never become neighbours. */
+int cab_upload_cloud(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride);
+/* Same, for a batch of independent segmented clusters: offsets[nclusters+1] into xyz.
+ * Neighbourhoods never cross cluster boundaries (table_memory_grsd.cpp:913 loops clusters). */
+int cab_upload_clusters(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride,
+                        const int32_t* offsets, int32_t nclusters);
+/* Device-resident variant (xyz already in HBM, e.g. a torch tensor's data_ptr). */
+int cab_set_cloud_device(cab_ctx* ctx, const float* d_xyz, int64_t n, int32_t stride);
+
+/* Builds the search structure that replaces the kd-tree (radius_estimation.cpp:107;
+ * pcl::KdTreeFLANN at grsd_colorCHLAC_tools.hpp:79,175): device radix sort of
+ * (row, x) keys, cell offsets, 32-query packets.  `cell` must be >= every radius used later. */
+int cab_build_grid(cab_ctx* ctx, float cell);
+
+/* Query sharding for multi-GPU runs: this context only computes packets
+ * [rank*P/world, (rank+1)*P/world) of the sorted order. Default (0,1). */
+int cab_set_shard(cab_ctx* ctx, int32_t rank, int32_t world);
+/* Sorted-order element range [begin, end) covered by this context's shard. */
+int cab_shard_range(const cab_ctx* ctx, int64_t* begin, int64_t* end);
+
+/* ---- normals -------------------------------------------------------------------------
+ * Replaces pcl::NormalEstimation::compute with setRadiusSearch(r)
+ * (grsd_colorCHLAC_tools.hpp:76-81; the cloud_algos/NormalEstimation plugin slot,
+ * plugins.xml:3-7).  out: n x {nx, ny, nz, curvature} in input order, may be NULL to keep the
+ * result on the device only.  max_nn <= 0: unlimited. */
+int cab_normals(cab_ctx* ctx, float r, int32_t max_nn, const float vp[3], float* nxyz_curv);
+/* Provide normals computed elsewhere (the LocalRadiusEstimation plugin receives them as the
+ * nx,ny,nz channels, radius_estimation.cpp:58-68).  Three SoA arrays of n floats. */
+int cab_set_normals(cab_ctx* ctx, const float* nx, const float* ny, const float* nz);
+
+/* ---- RSD -----------------------------------------------------------------------------
+ * Replaces HOT LOOP 1 + 2 of LocalRadiusEstimation::process (radius_estimation.cpp:118-202):
+ * radius search (<= max_nn nearest, self excluded), per-distance-bin min/max normal angle,
+ * the two least-squares fits capped at plane_radius.  r_min / r_max: n floats each in input
+ * order, may be NULL. */
+int cab_rsd(cab_ctx* ctx, double r, int32_t max_nn, int32_t ndiv, double plane_radius,
+            int32_t flags, float* r_min, float* r_max);
+
+/* ---- parity / debug ------------------------------------------------------------------
+ * Neighbour index sets of queries [q0, q1) (input order) as the radius search returns them
+ * (radius_estimation.cpp:120), unsorted.  offsets: q1-q0+1 entries.  idx/d2 may be NULL
+ * (count only); returns total or <0. */
+int64_t cab_neighbors_debug(cab_ctx* ctx, float r, int32_t max_nn, int64_t q0, int64_t q1,
+                            int64_t* offsets, int32_t* idx, float* d2, int64_t cap);
+
+/* ---- GRSD ----------------------------------------------------------------------------
+ * Replaces getVoxelGrid + extractGRSDSignature21 (grsd_colorCHLAC_tools.hpp:94-100,131-294)
+ * for a batch of clusters, the work of cloud_algos/GlobalRSD as called from
+ * table_memory_grsd.cpp:974-996.  normals: n x 3 floats (SoA arrays) or all NULL to compute
+ * them with radius r_normals.  RSD radius = max(rsd_radius_min, leaf/2*sqrt(3)), nr_subdiv 5,
+ * plane_radius 0.2, reference element = nearest surface point.
+ * hist21: nclusters x 21 int32 (upper triangle of the 6x6 transition matrix). */
+int cab_grsd_batch(cab_ctx* ctx, const float* xyz, int32_t stride, const int32_t* offsets,
+                   int32_t nclusters, float leaf, float r_normals, double rsd_radius_min,
+                   int32_t rsd_flags, const float vp[3], const float* nx, const float* ny,
+                   const float* nz, int32_t* hist21);
+/* Per-voxel results of the last cab_grsd_batch (voxels ordered by cluster, then linear voxel
+ * index).  vox_offsets: nclusters+1. Any pointer may be NULL. Returns total voxels. */
+int64_t cab_grsd_voxels(cab_ctx* ctx, int64_t* vox_offsets, float* centroids_xyz, float* r_min,
+                        float* r_max, int32_t* labels, int64_t cap);
+
+/* ---- device plumbing (bench / multi-GPU) ---------------------------------------------- */
+#define CAB_BUF_POS_SORTED 0  /* float4[n]  x,y,z,0 in sorted order */
+#define CAB_BUF_NRM_SORTED 1  /* float4[n]  nx,ny,nz,curvature in sorted order */
+#define CAB_BUF_RSD_SORTED 2  /* float2[n]  r_min,r_max in sorted order */
+#define CAB_BUF_PERM 3        /* int32[n]   sorted position -> input index */
+void* cab_device_ptr(cab_ctx* ctx, int32_t which);
+void* cab_stream(cab_ctx* ctx); /* cudaStream_t all work of this context is enqueued on */
+/* Copy device results (sorted order) to host arrays in input order. Any pointer may be NULL. */
+int cab_download(cab_ctx* ctx, float* nxyz_curv, float* r_min, float* r_max);
+
+int cab_profile(const cab_ctx* ctx, cab_timings* out);
+int cab_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

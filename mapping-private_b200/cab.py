@@ -1,0 +1,226 @@
+"""ctypes binding of libcloudalgos_b200.so (the C ABI in include/cloud_algos_b200.h).
+
+There is no fallback of any kind: if the shared library or a B200 is missing every entry point
+raises CabError.  numpy arrays are host buffers; the *_device helpers take raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+import subprocess
+
+import numpy as np
+
+_DIR = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _DIR / "csrc" / "libcloudalgos_b200.so"
+_LIB = None
+
+RSD_SEED_BIN0 = 2
+RSD_SCALE_SORT = 4
+BUF_POS_SORTED, BUF_NRM_SORTED, BUF_RSD_SORTED, BUF_PERM = 0, 1, 2, 3
+
+EXPORTS = [
+    "cab_create", "cab_destroy", "cab_last_error", "cab_upload_cloud", "cab_upload_clusters",
+    "cab_set_cloud_device", "cab_build_grid", "cab_set_shard", "cab_shard_range", "cab_normals",
+    "cab_set_normals", "cab_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels",
+    "cab_device_ptr", "cab_stream", "cab_download", "cab_profile", "cab_version",
+]
+
+
+class CabError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("exact", C.c_int32), ("max_table_cells", C.c_int64)]
+
+
+class Timings(C.Structure):
+    _fields_ = [
+        ("build_ms", C.c_float), ("normals_ms", C.c_float), ("rsd_ms", C.c_float), ("grsd_ms", C.c_float),
+        ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
+        ("n_points", C.c_int64), ("n_valid", C.c_int64), ("n_packets", C.c_int64), ("n_rows", C.c_int64),
+        ("n_cells", C.c_int64), ("neighbour_sum", C.c_int64), ("candidate_sum", C.c_int64),
+        ("kernel_launches", C.c_int64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def build(force: bool = False) -> pathlib.Path:
+    """Compile the library for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", str(_DIR / "csrc"), "-j8", "libcloudalgos_b200.so"]
+    if force:
+        cmd.insert(1, "-B")
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not LIB_PATH.exists():
+            raise CabError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+        L = C.CDLL(str(LIB_PATH))
+        L.cab_last_error.restype = C.c_char_p
+        L.cab_last_error.argtypes = [C.c_void_p]
+        L.cab_neighbors_debug.restype = C.c_int64
+        L.cab_grsd_voxels.restype = C.c_int64
+        L.cab_device_ptr.restype = C.c_void_p
+        L.cab_device_ptr.argtypes = [C.c_void_p, C.c_int32]
+        L.cab_stream.restype = C.c_void_p
+        L.cab_stream.argtypes = [C.c_void_p]
+        L.cab_destroy.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+class Context:
+    """One cab_ctx: a CUDA stream plus a grow-only device arena on one GPU."""
+
+    def __init__(self, device: int = 0, exact: bool = False, max_table_cells: int = 0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        cfg = Config(device, 1 if exact else 0, max_table_cells)
+        rc = self._L.cab_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise CabError(f"cab_create failed ({rc}): {self._L.cab_last_error(None).decode()}")
+        self.n = 0
+
+    def close(self):
+        if self._h:
+            self._L.cab_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise CabError(f"{what} failed ({rc}): {self._L.cab_last_error(self._h).decode()}")
+        return rc
+
+    # ---- cloud / grid ----------------------------------------------------------------
+    def upload(self, xyz: np.ndarray):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        assert xyz.ndim == 2 and xyz.shape[1] >= 3
+        self._keep = xyz
+        self.n = xyz.shape[0]
+        self._check(self._L.cab_upload_cloud(self._h, _fp(xyz), C.c_int64(self.n), C.c_int32(xyz.shape[1])), "cab_upload_cloud")
+
+    def upload_clusters(self, xyz: np.ndarray, offsets: np.ndarray):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        self._keep = (xyz, offsets)
+        self.n = xyz.shape[0]
+        self._check(self._L.cab_upload_clusters(self._h, _fp(xyz), C.c_int64(self.n), C.c_int32(xyz.shape[1]),
+                                                _ip(offsets), C.c_int32(len(offsets) - 1)), "cab_upload_clusters")
+
+    def set_cloud_device(self, dptr: int, n: int, stride: int = 3):
+        self.n = n
+        self._check(self._L.cab_set_cloud_device(self._h, C.c_void_p(dptr), C.c_int64(n), C.c_int32(stride)),
+                    "cab_set_cloud_device")
+
+    def build_grid(self, cell: float):
+        self._check(self._L.cab_build_grid(self._h, C.c_float(cell)), "cab_build_grid")
+
+    def set_shard(self, rank: int, world: int):
+        self._check(self._L.cab_set_shard(self._h, C.c_int32(rank), C.c_int32(world)), "cab_set_shard")
+
+    def shard_range(self):
+        b, e = C.c_int64(), C.c_int64()
+        self._check(self._L.cab_shard_range(self._h, C.byref(b), C.byref(e)), "cab_shard_range")
+        return b.value, e.value
+
+    # ---- stages ----------------------------------------------------------------------
+    def normals(self, r: float, max_nn: int = 0, vp=(0.0, 0.0, 0.0), download: bool = True):
+        v = np.asarray(vp, dtype=np.float32)
+        out = np.empty((self.n, 4), np.float32) if download else None
+        self._check(self._L.cab_normals(self._h, C.c_float(r), C.c_int32(max_nn), _fp(v), _fp(out)), "cab_normals")
+        return out
+
+    def set_normals(self, nrm: np.ndarray):
+        nrm = np.asarray(nrm, dtype=np.float32)
+        nx, ny, nz = (np.ascontiguousarray(nrm[:, i]) for i in range(3))
+        self._check(self._L.cab_set_normals(self._h, _fp(nx), _fp(ny), _fp(nz)), "cab_set_normals")
+
+    def rsd(self, r: float, max_nn: int = 0, ndiv: int = 10, plane_radius: float = 0.1, flags: int = 0,
+            download: bool = True):
+        rmin = np.empty(self.n, np.float32) if download else None
+        rmax = np.empty(self.n, np.float32) if download else None
+        self._check(self._L.cab_rsd(self._h, C.c_double(r), C.c_int32(max_nn), C.c_int32(ndiv), C.c_double(plane_radius),
+                                    C.c_int32(flags), _fp(rmin), _fp(rmax)), "cab_rsd")
+        return rmin, rmax
+
+    def download(self, normals: bool = True, rsd: bool = True):
+        n4 = np.empty((self.n, 4), np.float32) if normals else None
+        rmin = np.empty(self.n, np.float32) if rsd else None
+        rmax = np.empty(self.n, np.float32) if rsd else None
+        self._check(self._L.cab_download(self._h, _fp(n4), _fp(rmin), _fp(rmax)), "cab_download")
+        return n4, rmin, rmax
+
+    def neighbors(self, r: float, q0: int, q1: int, max_nn: int = 0):
+        """Neighbour sets of queries [q0, q1): (offsets int64, idx int32, d2 float32), unsorted."""
+        off = np.zeros(q1 - q0 + 1, np.int64)
+        total = self._check(self._L.cab_neighbors_debug(self._h, C.c_float(r), C.c_int32(max_nn), C.c_int64(q0), C.c_int64(q1),
+                                                        off.ctypes.data_as(C.POINTER(C.c_int64)), None, None, C.c_int64(0)),
+                            "cab_neighbors_debug")
+        idx = np.zeros(max(total, 1), np.int32)
+        d2 = np.zeros(max(total, 1), np.float32)
+        self._check(self._L.cab_neighbors_debug(self._h, C.c_float(r), C.c_int32(max_nn), C.c_int64(q0), C.c_int64(q1),
+                                                off.ctypes.data_as(C.POINTER(C.c_int64)), _ip(idx), _fp(d2), C.c_int64(total)),
+                    "cab_neighbors_debug")
+        return off, idx[:total], d2[:total]
+
+    def grsd_batch(self, xyz: np.ndarray, offsets: np.ndarray, leaf: float, r_normals: float = 0.02,
+                   rsd_radius_min: float = 0.01, rsd_flags: int = 0, vp=(0.0, 0.0, 0.0), normals: np.ndarray | None = None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        nc = len(offsets) - 1
+        self.n = xyz.shape[0]
+        hist = np.zeros((nc, 21), np.int32)
+        v = np.asarray(vp, dtype=np.float32)
+        nx = ny = nz = None
+        if normals is not None:
+            nrm = np.asarray(normals, dtype=np.float32)
+            nx, ny, nz = (np.ascontiguousarray(nrm[:, i]) for i in range(3))
+        self._check(self._L.cab_grsd_batch(self._h, _fp(xyz), C.c_int32(xyz.shape[1]), _ip(offsets), C.c_int32(nc),
+                                           C.c_float(leaf), C.c_float(r_normals), C.c_double(rsd_radius_min),
+                                           C.c_int32(rsd_flags), _fp(v), _fp(nx), _fp(ny), _fp(nz), _ip(hist)), "cab_grsd_batch")
+        return hist
+
+    def grsd_voxels(self, nclusters: int):
+        off = np.zeros(nclusters + 1, np.int64)
+        nv = self._check(self._L.cab_grsd_voxels(self._h, off.ctypes.data_as(C.POINTER(C.c_int64)), None, None, None, None,
+                                                 C.c_int64(0)), "cab_grsd_voxels")
+        cent = np.zeros((max(nv, 1), 3), np.float32)
+        rmin = np.zeros(max(nv, 1), np.float32)
+        rmax = np.zeros(max(nv, 1), np.float32)
+        lab = np.zeros(max(nv, 1), np.int32)
+        self._check(self._L.cab_grsd_voxels(self._h, off.ctypes.data_as(C.POINTER(C.c_int64)), _fp(cent), _fp(rmin), _fp(rmax),
+                                            _ip(lab), C.c_int64(nv)), "cab_grsd_voxels")
+        return dict(offsets=off, centroids=cent[:nv], r_min=rmin[:nv], r_max=rmax[:nv], labels=lab[:nv])
+
+    # ---- plumbing --------------------------------------------------------------------
+    def device_ptr(self, which: int) -> int:
+        return self._L.cab_device_ptr(self._h, which) or 0
+
+    def stream(self) -> int:
+        return self._L.cab_stream(self._h) or 0
+
+    def profile(self) -> dict:
+        t = Timings()
+        self._check(self._L.cab_profile(self._h, C.byref(t)), "cab_profile")
+        return t.as_dict()

@@ -1,0 +1,362 @@
+// cab_api.cu -- C ABI of libcloudalgos_b200.so (see include/cloud_algos_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include <algorithm>
+#include <mutex>
+#include <numeric>
+
+#include "cab_internal.cuh"
+
+namespace cab {
+
+static thread_local std::string g_create_err;
+
+int fail(cab_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_err = buf;
+  return code;
+}
+
+int reserve(cab_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return CAB_OK;
+  if (b.p) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 8 + 256;  // grow-only arena with a little headroom
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    b.p = nullptr;
+    return fail(ctx, CAB_ERR_OOM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+  }
+  b.cap = want;
+  return CAB_OK;
+}
+
+int reserve_pinned(cab_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->h_pin_cap) return CAB_OK;
+  if (ctx->h_pin) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFreeHost(ctx->h_pin);
+    ctx->h_pin = nullptr;
+    ctx->h_pin_cap = 0;
+  }
+  size_t want = std::max<size_t>(bytes * 2, 1 << 16);
+  cudaError_t e = cudaMallocHost(&ctx->h_pin, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, CAB_ERR_OOM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+  }
+  ctx->h_pin_cap = want;
+  return CAB_OK;
+}
+
+namespace {
+
+__global__ void __launch_bounds__(256) gather_normals_kernel(const float* __restrict__ nx, const float* __restrict__ ny,
+                                                             const float* __restrict__ nz, const int* __restrict__ perm,
+                                                             int n, float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int j = perm[i];
+  out[i] = make_float4(nx[j], ny[j], nz[j], 0.f);
+}
+
+__global__ void __launch_bounds__(256) unpermute_kernel(const int* __restrict__ perm, int begin, int end,
+                                                        const float4* __restrict__ nrm, const float2* __restrict__ rsd,
+                                                        float4* __restrict__ out4, float* __restrict__ out_a,
+                                                        float* __restrict__ out_b) {
+  int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= end) return;
+  int j = perm[i];
+  if (out4) out4[j] = nrm[i];
+  if (out_a) {
+    float2 v = rsd[i];
+    out_a[j] = v.x;
+    out_b[j] = v.y;
+  }
+}
+
+int set_domains(cab_ctx* ctx, int64_t n, const int32_t* offsets, int nclusters) {
+  ctx->dom_offsets.clear();
+  if (offsets) {
+    if (nclusters < 1) return fail(ctx, CAB_ERR_ARG, "nclusters must be >= 1");
+    if (offsets[0] != 0 || offsets[nclusters] != n) return fail(ctx, CAB_ERR_ARG, "offsets must span [0, n]");
+    for (int c = 0; c < nclusters; ++c)
+      if (offsets[c + 1] < offsets[c]) return fail(ctx, CAB_ERR_ARG, "offsets must be non-decreasing");
+    ctx->dom_offsets.assign(offsets, offsets + nclusters + 1);
+  } else {
+    ctx->dom_offsets = {0, (int32_t)n};
+  }
+  ctx->n_domains = (int)ctx->dom_offsets.size() - 1;
+  size_t bytes = ctx->dom_offsets.size() * sizeof(int32_t);
+  if (int rc = reserve(ctx, ctx->b_domoff, bytes)) return rc;
+  if (int rc = reserve_pinned(ctx, bytes)) return rc;
+  std::memcpy(ctx->h_pin, ctx->dom_offsets.data(), bytes);
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_domoff.p, ctx->h_pin, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return CAB_OK;
+}
+
+int upload_impl(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride, const int32_t* offsets, int nclusters,
+                bool device_ptr) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (n < 0 || n > 0x7ffffff0ll) return fail(ctx, CAB_ERR_ARG, "n out of range");
+  if (stride < 3) return fail(ctx, CAB_ERR_ARG, "stride must be >= 3 floats");
+  if (n > 0 && !xyz) return fail(ctx, CAB_ERR_ARG, "xyz is NULL");
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->have_cloud = ctx->have_grid = ctx->have_normals = ctx->have_rsd = false;
+  if (int rc = set_domains(ctx, n, offsets, nclusters)) return rc;
+  if (device_ptr) {
+    ctx->xyz_in = xyz;
+  } else {
+    size_t bytes = (size_t)n * stride * sizeof(float);
+    if (int rc = reserve(ctx, ctx->b_xyz, std::max<size_t>(bytes, 16))) return rc;
+    CAB_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+    if (bytes) CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_xyz.p, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CAB_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+    CAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[6], ctx->ev[7]));
+    ctx->xyz_in = (const float*)ctx->b_xyz.p;
+  }
+  ctx->cloud_external = device_ptr;
+  ctx->n = n;
+  ctx->stride = stride;
+  ctx->have_cloud = true;
+  return CAB_OK;
+}
+
+}  // namespace
+
+int permute_normals_in(cab_ctx* ctx, const float* nx, const float* ny, const float* nz) {
+  const int n = (int)ctx->n;
+  cudaStream_t st = ctx->stream;
+  if (int rc = reserve(ctx, ctx->b_nrm_in, (size_t)std::max(n, 1) * 3 * sizeof(float))) return rc;
+  if (int rc = reserve(ctx, ctx->b_nrm, (size_t)std::max(n, 1) * sizeof(float4))) return rc;
+  float* d = (float*)ctx->b_nrm_in.p;
+  if (n > 0) {
+    CAB_CUDA(ctx, cudaMemcpyAsync(d, nx, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CAB_CUDA(ctx, cudaMemcpyAsync(d + n, ny, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CAB_CUDA(ctx, cudaMemcpyAsync(d + 2 * (size_t)n, nz, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    gather_normals_kernel<<<(n + 255) / 256, 256, 0, st>>>(d, d + n, d + 2 * (size_t)n, (const int*)ctx->b_perm.p, n,
+                                                           (float4*)ctx->b_nrm.p);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->have_normals = true;
+  return CAB_OK;
+}
+
+int download_results(cab_ctx* ctx, float* n4, float* rmin, float* rmax) {
+  const int n = (int)ctx->n;
+  cudaStream_t st = ctx->stream;
+  if ((rmin == nullptr) != (rmax == nullptr)) return fail(ctx, CAB_ERR_ARG, "r_min and r_max must be given together");
+  if (n4 && !ctx->have_normals) return fail(ctx, CAB_ERR_STATE, "no normals to download");
+  if (rmin && !ctx->have_rsd) return fail(ctx, CAB_ERR_STATE, "no RSD results to download");
+  if (n == 0 || (!n4 && !rmin)) return CAB_OK;
+  if (n4)
+    if (int rc = reserve(ctx, ctx->b_out4, (size_t)n * sizeof(float4))) return rc;
+  if (rmin) {
+    if (int rc = reserve(ctx, ctx->b_out1a, (size_t)n * sizeof(float))) return rc;
+    if (int rc = reserve(ctx, ctx->b_out1b, (size_t)n * sizeof(float))) return rc;
+  }
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+  unpermute_kernel<<<(n + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, 0, n, (const float4*)ctx->b_nrm.p,
+                                                    (const float2*)ctx->b_rsd.p, n4 ? (float4*)ctx->b_out4.p : nullptr,
+                                                    rmin ? (float*)ctx->b_out1a.p : nullptr,
+                                                    rmin ? (float*)ctx->b_out1b.p : nullptr);
+  CAB_LAUNCH_CHECK(ctx);
+  if (n4) CAB_CUDA(ctx, cudaMemcpyAsync(n4, ctx->b_out4.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  if (rmin) {
+    CAB_CUDA(ctx, cudaMemcpyAsync(rmin, ctx->b_out1a.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CAB_CUDA(ctx, cudaMemcpyAsync(rmax, ctx->b_out1b.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[6], ctx->ev[7]));
+  return CAB_OK;
+}
+
+}  // namespace cab
+
+using namespace cab;
+
+extern "C" {
+
+int cab_version(void) { return 100; }
+
+int cab_create(const cab_config* cfg, cab_ctx** out) {
+  if (!out) return CAB_ERR_ARG;
+  *out = nullptr;
+  cab_config c{};
+  if (cfg) c = *cfg;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, CAB_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (c.device < 0 || c.device >= ndev) return fail(nullptr, CAB_ERR_ARG, "device %d out of range [0,%d)", c.device, ndev);
+  cudaDeviceProp prop{};
+  if ((e = cudaGetDeviceProperties(&prop, c.device)) != cudaSuccess)
+    return fail(nullptr, CAB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, CAB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", c.device,
+                prop.major, prop.minor);
+  if ((e = cudaSetDevice(c.device)) != cudaSuccess)
+    return fail(nullptr, CAB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cab_ctx* ctx = new cab_ctx();
+  ctx->cfg = c;
+  ctx->device = c.device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, CAB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  if (reserve_pinned(ctx, 1 << 16) != CAB_OK) {
+    g_create_err = ctx->err;
+    cab_destroy(ctx);
+    return CAB_ERR_OOM;
+  }
+  *out = ctx;
+  return CAB_OK;
+}
+
+void cab_destroy(cab_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->b_xyz, &ctx->b_domoff, &ctx->b_domid, &ctx->b_bounds, &ctx->b_domains, &ctx->b_keys[0],
+                    &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
+                    &ctx->b_cellcnt, &ctx->b_cellstart, &ctx->b_rowpk, &ctx->b_packets, &ctx->b_nrm, &ctx->b_nrm_in,
+                    &ctx->b_rsd, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
+                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
+                    &ctx->g_vvals[1], &ctx->g_cent, &ctx->g_vcount, &ctx->g_vrad, &ctx->g_vlabel, &ctx->g_voff,
+                    &ctx->g_layout, &ctx->g_layoff, &ctx->g_vgrid, &ctx->g_hist, &ctx->g_vfirst};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* cab_last_error(const cab_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int cab_upload_cloud(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride) {
+  return upload_impl(ctx, xyz, n, stride, nullptr, 0, false);
+}
+
+int cab_upload_clusters(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride, const int32_t* offsets,
+                        int32_t nclusters) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (!offsets) return fail(ctx, CAB_ERR_ARG, "offsets is NULL");
+  return upload_impl(ctx, xyz, n, stride, offsets, nclusters, false);
+}
+
+int cab_set_cloud_device(cab_ctx* ctx, const float* d_xyz, int64_t n, int32_t stride) {
+  return upload_impl(ctx, d_xyz, n, stride, nullptr, 0, true);
+}
+
+int cab_build_grid(cab_ctx* ctx, float cell) {
+  if (!ctx) return CAB_ERR_ARG;
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return build_grid(ctx, cell);
+}
+
+int cab_set_shard(cab_ctx* ctx, int32_t rank, int32_t world) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, CAB_ERR_ARG, "bad shard %d/%d", rank, world);
+  ctx->shard_rank = rank;
+  ctx->shard_world = world;
+  return CAB_OK;
+}
+
+int cab_shard_range(const cab_ctx* ctx, int64_t* begin, int64_t* end) {
+  if (!ctx || !begin || !end) return CAB_ERR_ARG;
+  if (!ctx->have_grid) return CAB_ERR_STATE;
+  // packets are ordered by their start; the shard covers [start of packet p0, start of packet p1)
+  int p0, p1;
+  packet_range(ctx, &p0, &p1);
+  auto start_of = [&](int p) -> int64_t {
+    if (p >= ctx->n_packets) return ctx->n_valid;
+    Packet pk;
+    cudaMemcpy(&pk, (const Packet*)ctx->b_packets.p + p, sizeof(Packet), cudaMemcpyDeviceToHost);
+    return pk.start;
+  };
+  *begin = start_of(p0);
+  *end = start_of(p1);
+  return CAB_OK;
+}
+
+int cab_normals(cab_ctx* ctx, float r, int32_t max_nn, const float vp[3], float* nxyz_curv) {
+  if (!ctx) return CAB_ERR_ARG;
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (int rc = run_normals(ctx, r, max_nn, vp)) return rc;
+  if (nxyz_curv) return download_results(ctx, nxyz_curv, nullptr, nullptr);
+  return CAB_OK;
+}
+
+int cab_set_normals(cab_ctx* ctx, const float* nx, const float* ny, const float* nz) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (!ctx->have_grid) return fail(ctx, CAB_ERR_STATE, "cab_set_normals: build the grid first");
+  if (ctx->n > 0 && (!nx || !ny || !nz)) return fail(ctx, CAB_ERR_ARG, "cab_set_normals: NULL channel");
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return permute_normals_in(ctx, nx, ny, nz);
+}
+
+int cab_rsd(cab_ctx* ctx, double r, int32_t max_nn, int32_t ndiv, double plane_radius, int32_t flags, float* r_min,
+            float* r_max) {
+  if (!ctx) return CAB_ERR_ARG;
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if ((r_min == nullptr) != (r_max == nullptr)) return fail(ctx, CAB_ERR_ARG, "r_min and r_max must be given together");
+  if (int rc = run_rsd(ctx, r, max_nn, ndiv, plane_radius, flags)) return rc;
+  if (r_min) return download_results(ctx, nullptr, r_min, r_max);
+  return CAB_OK;
+}
+
+int64_t cab_neighbors_debug(cab_ctx* ctx, float r, int32_t max_nn, int64_t q0, int64_t q1, int64_t* offsets,
+                            int32_t* idx, float* d2, int64_t cap) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, CAB_ERR_CUDA, "cudaSetDevice failed");
+  return run_neighbors_debug(ctx, r, max_nn, q0, q1, offsets, idx, d2, cap);
+}
+
+void* cab_device_ptr(cab_ctx* ctx, int32_t which) {
+  if (!ctx) return nullptr;
+  switch (which) {
+    case CAB_BUF_POS_SORTED: return ctx->b_pos.p;
+    case CAB_BUF_NRM_SORTED: return ctx->b_nrm.p;
+    case CAB_BUF_RSD_SORTED: return ctx->b_rsd.p;
+    case CAB_BUF_PERM: return ctx->b_perm.p;
+    default: return nullptr;
+  }
+}
+
+void* cab_stream(cab_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int cab_download(cab_ctx* ctx, float* nxyz_curv, float* r_min, float* r_max) {
+  if (!ctx) return CAB_ERR_ARG;
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return download_results(ctx, nxyz_curv, r_min, r_max);
+}
+
+int cab_profile(const cab_ctx* ctx, cab_timings* out) {
+  if (!ctx || !out) return CAB_ERR_ARG;
+  *out = ctx->tm;
+  return CAB_OK;
+}
+
+}  // extern "C"

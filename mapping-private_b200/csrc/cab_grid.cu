@@ -1,0 +1,375 @@
+// cab_grid.cu -- device-built search structure that replaces the reference's kd-tree
+// (cloud_kdtree::KdTreeANN at cloud_algos/src/radius_estimation.cpp:107, pcl::KdTreeFLANN at
+// color_chlac/include/color_chlac/grsd_colorCHLAC_tools.hpp:79,175).
+//
+// Layout in HBM (DESIGN.md "Data layout"):
+//   rows      : (domain, cell z, cell y) tubes along x; points sorted by (row, fine x)
+//   pos       : float4[n]   sorted positions
+//   perm      : int[n]      sorted position -> input index
+//   cell_start: int[cells+1] dense CSR over (row, cell x)
+//   packets   : <=32 consecutive sorted points of one row = the work unit of one warp
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "cab_internal.cuh"
+
+namespace cab {
+
+namespace {
+
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float ord2f(unsigned u) {
+  unsigned b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  float f;
+#ifdef __CUDA_ARCH__
+  f = __uint_as_float(b);
+#else
+  std::memcpy(&f, &b, 4);
+#endif
+  return f;
+}
+
+__device__ __forceinline__ bool finite3(float x, float y, float z) {
+  return isfinite(x) && isfinite(y) && isfinite(z);
+}
+
+struct Chunk {
+  int domain, begin, end;
+};
+
+// bounds[d] = {minx,miny,minz,maxx,maxy,maxz (ordered-uint encoded), n_finite, unused}
+__global__ void __launch_bounds__(256) bounds_kernel(const float* __restrict__ xyz, int stride,
+                                                     const Chunk* __restrict__ chunks,
+                                                     unsigned* __restrict__ bounds) {
+  const Chunk ch = chunks[blockIdx.x];
+  unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+  unsigned cnt = 0;
+  for (int i = ch.begin + threadIdx.x; i < ch.end; i += blockDim.x) {
+    const float* p = xyz + (size_t)i * stride;
+    float x = p[0], y = p[1], z = p[2];
+    if (finite3(x, y, z)) {
+      unsigned e[3] = {f2ord(x), f2ord(y), f2ord(z)};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = min(mn[a], e[a]);
+        mx[a] = max(mx[a], e[a]);
+      }
+      ++cnt;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    mn[a] = __reduce_min_sync(kFull, mn[a]);
+    mx[a] = __reduce_max_sync(kFull, mx[a]);
+  }
+  cnt = __reduce_add_sync(kFull, cnt);
+  if ((threadIdx.x & 31) == 0) {
+    unsigned* b = bounds + 8 * (size_t)ch.domain;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(b + a, mn[a]);
+      atomicMax(b + 3 + a, mx[a]);
+    }
+    atomicAdd(b + 6, cnt);
+  }
+}
+
+__device__ __forceinline__ int find_domain(const int* __restrict__ domoff, int n_domains, int i) {
+  int lo = 0, hi = n_domains;  // largest d with domoff[d] <= i
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (domoff[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) key_kernel(const float* __restrict__ xyz, int stride, int n,
+                                                  const int* __restrict__ domoff, int n_domains,
+                                                  const Domain* __restrict__ domains, float inv_cell,
+                                                  unsigned long long sentinel_row,
+                                                  unsigned long long* __restrict__ keys,
+                                                  int* __restrict__ vals, int* __restrict__ cellcnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = xyz + (size_t)i * stride;
+  float x = p[0], y = p[1], z = p[2];
+  unsigned long long key = sentinel_row << kXBits;
+  if (finite3(x, y, z)) {
+    int d = (n_domains > 1) ? find_domain(domoff, n_domains, i) : 0;
+    const Domain dm = domains[d];
+    int cy = cell_coord(y, dm.oy, inv_cell, dm.ny);
+    int cz = cell_coord(z, dm.oz, inv_cell, dm.nz);
+    int xf = xfine_coord(x, dm.ox, inv_cell, dm.nx, dm.xshift);
+    long long row_local = (long long)cz * dm.ny + cy;
+    key = ((unsigned long long)(dm.row_base + row_local) << kXBits) | (unsigned)xf;
+    atomicAdd(cellcnt + dm.cell_base + row_local * dm.nx + (xf >> dm.xshift), 1);
+  }
+  keys[i] = key;
+  vals[i] = i;
+}
+
+__global__ void __launch_bounds__(256) reorder_kernel(const float* __restrict__ xyz, int stride, int n,
+                                                      const int* __restrict__ perm,
+                                                      float4* __restrict__ pos) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = xyz + (size_t)perm[i] * stride;
+  pos[i] = make_float4(p[0], p[1], p[2], 0.f);
+}
+
+// packets per row; rows are indexed globally over all domains
+__global__ void __launch_bounds__(256) row_packets_kernel(const Domain* __restrict__ domains, int n_domains,
+                                                          long long n_rows, const int* __restrict__ cell_start,
+                                                          int* __restrict__ rowpk) {
+  long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row > n_rows) return;
+  if (row == n_rows) {
+    rowpk[row] = 0;
+    return;
+  }
+  int lo = 0, hi = n_domains;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (domains[mid].row_base <= row) lo = mid; else hi = mid;
+  }
+  const Domain dm = domains[lo];
+  long long c0 = dm.cell_base + (row - dm.row_base) * dm.nx;
+  int len = cell_start[c0 + dm.nx] - cell_start[c0];
+  rowpk[row] = (len + kWarp - 1) / kWarp;
+}
+
+__global__ void __launch_bounds__(256) fill_packets_kernel(const Domain* __restrict__ domains, int n_domains,
+                                                           long long n_rows, const int* __restrict__ cell_start,
+                                                           const int* __restrict__ packet_base,
+                                                           Packet* __restrict__ packets) {
+  long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  int pb = packet_base[row], npk = packet_base[row + 1] - pb;
+  if (npk == 0) return;
+  int lo = 0, hi = n_domains;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (domains[mid].row_base <= row) lo = mid; else hi = mid;
+  }
+  const Domain dm = domains[lo];
+  long long c0 = dm.cell_base + (row - dm.row_base) * dm.nx;
+  int start = cell_start[c0];
+  long long len = cell_start[c0 + dm.nx] - start;
+  for (int k = 0; k < npk; ++k) {
+    int a = start + (int)(k * len / npk), b = start + (int)((k + 1) * len / npk);
+    packets[pb + k] = Packet{a, b - a, (int)(row - dm.row_base), lo};
+  }
+}
+
+}  // namespace
+
+int build_grid(cab_ctx* ctx, float cell) {
+  if (!ctx->have_cloud) return fail(ctx, CAB_ERR_STATE, "cab_build_grid: no cloud uploaded");
+  if (!(cell > 0.f) || !std::isfinite(cell)) return fail(ctx, CAB_ERR_ARG, "cab_build_grid: cell must be > 0");
+  const int n = (int)ctx->n;
+  const int nd = ctx->n_domains;
+  cudaStream_t st = ctx->stream;
+  ctx->have_grid = ctx->have_normals = ctx->have_rsd = false;
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+
+  // ---- bounds per domain --------------------------------------------------------------
+  std::vector<Chunk> chunks;
+  const int kChunk = 1 << 16;
+  for (int d = 0; d < nd; ++d) {
+    int b = ctx->dom_offsets[d], e = ctx->dom_offsets[d + 1];
+    if (b == e) chunks.push_back(Chunk{d, b, e});
+    for (int s = b; s < e; s += kChunk) chunks.push_back(Chunk{d, s, std::min(e, s + kChunk)});
+  }
+  if (int rc = reserve(ctx, ctx->b_misc, chunks.size() * sizeof(Chunk))) return rc;
+  if (int rc = reserve(ctx, ctx->b_bounds, (size_t)nd * 8 * sizeof(unsigned))) return rc;
+  if (int rc = reserve_pinned(ctx, std::max((size_t)nd * 8 * sizeof(unsigned), chunks.size() * sizeof(Chunk)) + 64))
+    return rc;
+  std::memcpy(ctx->h_pin, chunks.data(), chunks.size() * sizeof(Chunk));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_misc.p, ctx->h_pin, chunks.size() * sizeof(Chunk), cudaMemcpyHostToDevice, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  {
+    std::vector<unsigned> init((size_t)nd * 8);
+    for (int d = 0; d < nd; ++d) {
+      unsigned* b = init.data() + 8 * (size_t)d;
+      b[0] = b[1] = b[2] = 0xffffffffu;
+      b[3] = b[4] = b[5] = 0u;
+      b[6] = b[7] = 0u;
+    }
+    std::memcpy(ctx->h_pin, init.data(), init.size() * sizeof(unsigned));
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_bounds.p, ctx->h_pin, init.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+  }
+  if (!chunks.empty()) {
+    bounds_kernel<<<(unsigned)chunks.size(), 256, 0, st>>>(ctx->xyz_in, ctx->stride, (const Chunk*)ctx->b_misc.p,
+                                                           (unsigned*)ctx->b_bounds.p);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->b_bounds.p, (size_t)nd * 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+
+  // ---- domain geometry (host, tiny) ---------------------------------------------------
+  double max_abs = 0;
+  const unsigned* hb = (const unsigned*)ctx->h_pin;
+  int64_t n_valid = 0;
+  for (int d = 0; d < nd; ++d) {
+    if (hb[8 * d + 6] == 0) continue;
+    n_valid += hb[8 * d + 6];
+    for (int a = 0; a < 6; ++a) max_abs = std::max(max_abs, (double)std::fabs(ord2f(hb[8 * d + a])));
+  }
+  // effective cell: >= requested + slack for fp32 rounding of (v - origin) * inv_cell
+  double ulp = std::ldexp(1.0, (max_abs > 0 ? (int)std::floor(std::log2(max_abs)) : 0) - 23);
+  double cell_eff = (double)cell * (1.0 + 1.0 / 1024.0) + 8.0 * ulp;
+  ctx->cell = cell;
+  ctx->cell_eff = (float)cell_eff;
+  ctx->inv_cell = 1.0f / ctx->cell_eff;
+  ctx->domains.assign(nd, Domain{});
+  ctx->dom_bounds.assign((size_t)nd * 6, 0.f);
+  ctx->dom_count.assign(nd, 0u);
+  for (int d = 0; d < nd; ++d) {
+    ctx->dom_count[d] = hb[8 * d + 6];
+    if (hb[8 * d + 6])
+      for (int a = 0; a < 6; ++a) ctx->dom_bounds[6 * (size_t)d + a] = ord2f(hb[8 * d + a]);
+  }
+  int64_t rows = 0, cells = 0;
+  const int64_t budget = ctx->cfg.max_table_cells > 0 ? ctx->cfg.max_table_cells : ((int64_t)1 << 28);
+  for (int d = 0; d < nd; ++d) {
+    Domain& dm = ctx->domains[d];
+    dm.row_base = rows;
+    dm.cell_base = cells;
+    if (hb[8 * d + 6] == 0) {
+      dm.ox = dm.oy = dm.oz = 0.f;
+      dm.nx = dm.ny = dm.nz = 1;
+    } else {
+      float lo[3], hi[3];
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = ord2f(hb[8 * d + a]);
+        hi[a] = ord2f(hb[8 * d + 3 + a]);
+      }
+      dm.ox = lo[0];
+      dm.oy = lo[1];
+      dm.oz = lo[2];
+      double ext[3] = {(double)hi[0] - lo[0], (double)hi[1] - lo[1], (double)hi[2] - lo[2]};
+      int64_t nn[3];
+      for (int a = 0; a < 3; ++a) nn[a] = (int64_t)std::floor(ext[a] / cell_eff) + 2;  // +1 slack cell
+      if (nn[0] > (1 << kXBits) || nn[1] * nn[2] > ((int64_t)1 << 40))
+        return fail(ctx, CAB_ERR_OOM, "cab_build_grid: extent / cell too large for the dense grid");
+      dm.nx = (int)nn[0];
+      dm.ny = (int)nn[1];
+      dm.nz = (int)nn[2];
+    }
+    dm.xshift = 0;
+    while (dm.xshift < 8 && ((int64_t)dm.nx << (dm.xshift + 1)) <= (1 << kXBits)) dm.xshift++;
+    rows += (int64_t)dm.ny * dm.nz;
+    cells += (int64_t)dm.ny * dm.nz * dm.nx;
+    if (cells > budget)
+      return fail(ctx, CAB_ERR_OOM, "cab_build_grid: dense cell table needs > %lld cells (budget %lld)",
+                  (long long)cells, (long long)budget);
+  }
+  ctx->n_rows = rows;
+  ctx->n_cells = cells;
+  ctx->n_valid = (int)n_valid;
+
+  if (int rc = reserve(ctx, ctx->b_domains, nd * sizeof(Domain))) return rc;
+  if (int rc = reserve_pinned(ctx, nd * sizeof(Domain))) return rc;
+  std::memcpy(ctx->h_pin, ctx->domains.data(), nd * sizeof(Domain));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_domains.p, ctx->h_pin, nd * sizeof(Domain), cudaMemcpyHostToDevice, st));
+
+  // ---- keys + cell histogram ----------------------------------------------------------
+  const size_t ncell1 = (size_t)cells + 1;
+  if (int rc = reserve(ctx, ctx->b_keys[0], (size_t)n * 8)) return rc;
+  if (int rc = reserve(ctx, ctx->b_keys[1], (size_t)n * 8)) return rc;
+  if (int rc = reserve(ctx, ctx->b_vals[0], (size_t)n * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->b_perm, (size_t)n * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->b_cellcnt, ncell1 * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->b_cellstart, ncell1 * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->b_pos, (size_t)std::max(n, 1) * sizeof(float4))) return rc;
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_cellcnt.p, 0, ncell1 * 4, st));
+  if (n > 0) {
+    key_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, (const int*)ctx->b_domoff.p, nd,
+                                                (const Domain*)ctx->b_domains.p, ctx->inv_cell,
+                                                (unsigned long long)rows, (unsigned long long*)ctx->b_keys[0].p,
+                                                (int*)ctx->b_vals[0].p, (int*)ctx->b_cellcnt.p);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+
+  // ---- radix sort by (row, fine x) ----------------------------------------------------
+  int row_bits = 1;
+  while (((int64_t)1 << row_bits) <= rows) ++row_bits;
+  const int end_bit = std::min(64, kXBits + row_bits);
+  size_t tmp_sort = 0, tmp_scan1 = 0, tmp_scan2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const int*)nullptr, (int*)nullptr, n, 0, end_bit, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan1, (const int*)nullptr, (int*)nullptr, (int)ncell1, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan2, (const int*)nullptr, (int*)nullptr, (int)(rows + 1), st);
+  size_t tmp_bytes = std::max(tmp_sort, std::max(tmp_scan1, tmp_scan2));
+  if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_bytes + 16)) return rc;
+  if (n > 0) {
+    CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_bytes, (const unsigned long long*)ctx->b_keys[0].p,
+                                                  (unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
+                                                  (int*)ctx->b_perm.p, n, 0, end_bit, st));
+    ctx->tm.kernel_launches += 1 + (end_bit + 7) / 8;  // onesweep: histogram + one kernel per digit
+    reorder_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, (const int*)ctx->b_perm.p,
+                                                    (float4*)ctx->b_pos.p);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_bytes, (const int*)ctx->b_cellcnt.p,
+                                              (int*)ctx->b_cellstart.p, (int)ncell1, st));
+  ctx->tm.kernel_launches += 2;
+
+  // ---- packets ------------------------------------------------------------------------
+  if (int rc = reserve(ctx, ctx->b_rowpk, (size_t)(rows + 1) * 4 * 2)) return rc;
+  int* rowpk = (int*)ctx->b_rowpk.p;
+  int* packet_base = rowpk + (rows + 1);
+  row_packets_kernel<<<(unsigned)((rows + 1 + 255) / 256), 256, 0, st>>>((const Domain*)ctx->b_domains.p, nd, rows,
+                                                                        (const int*)ctx->b_cellstart.p, rowpk);
+  CAB_LAUNCH_CHECK(ctx);
+  CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_bytes, rowpk, packet_base, (int)(rows + 1), st));
+  ctx->tm.kernel_launches += 2;
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, packet_base + rows, 4, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->n_packets = *(const int*)ctx->h_pin;
+  if (int rc = reserve(ctx, ctx->b_packets, (size_t)std::max(ctx->n_packets, 1) * sizeof(Packet))) return rc;
+  if (rows > 0) {
+    fill_packets_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const Domain*)ctx->b_domains.p, nd, rows,
+                                                                      (const int*)ctx->b_cellstart.p, packet_base,
+                                                                      (Packet*)ctx->b_packets.p);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.build_ms, ctx->ev[0], ctx->ev[1]));
+  ctx->tm.n_points = ctx->n;
+  ctx->tm.n_valid = ctx->n_valid;
+  ctx->tm.n_packets = ctx->n_packets;
+  ctx->tm.n_rows = rows;
+  ctx->tm.n_cells = cells;
+  ctx->have_grid = true;
+  return CAB_OK;
+}
+
+GridView grid_view(const cab_ctx* ctx) {
+  GridView g{};
+  g.pos = (const float4*)ctx->b_pos.p;
+  g.perm = (const int*)ctx->b_perm.p;
+  g.cell_start = (const int*)ctx->b_cellstart.p;
+  g.packets = (const Packet*)ctx->b_packets.p;
+  g.domains = (const Domain*)ctx->b_domains.p;
+  g.n_valid = ctx->n_valid;
+  g.n_packets = ctx->n_packets;
+  g.inv_cell = ctx->inv_cell;
+  return g;
+}
+
+void packet_range(const cab_ctx* ctx, int* p0, int* p1) {
+  int64_t P = ctx->n_packets;
+  *p0 = (int)(P * ctx->shard_rank / ctx->shard_world);
+  *p1 = (int)(P * (ctx->shard_rank + 1) / ctx->shard_world);
+}
+
+}  // namespace cab

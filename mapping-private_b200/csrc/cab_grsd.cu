@@ -1,0 +1,524 @@
+// cab_grsd.cu -- Global RSD for a batch of segmented clusters.
+// Replaces, per cluster, getVoxelGrid + extractGRSDSignature21
+// (color_chlac/include/color_chlac/grsd_colorCHLAC_tools.hpp:94-100 and :131-294):
+//   pcl::VoxelGrid(leaf, saveLeafLayout)  -> voxel keys, centroids, dense leaf layout
+//   pcl::RSDEstimation at the centroids over the full-resolution cloud + normals (:164-180)
+//   get_type (:104-116), 26-neighbour transition counting (:230-260), 21-bin packing (:266-276).
+// All clusters are processed together: they are independent "domains" of one search grid, so
+// neighbourhoods never cross clusters.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "cab_internal.cuh"
+
+namespace cab {
+
+namespace {
+
+struct VoxGrid {  // per cluster
+  int min_b[3];
+  int div_b[3];
+  long long layout_base;  // into the concatenated leaf layouts
+  int vox_first;          // first voxel (global index) of this cluster
+  int pad;
+};
+
+__device__ __forceinline__ int find_dom(const int* __restrict__ domoff, int nd, int i) {
+  int lo = 0, hi = nd;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (domoff[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// voxel key of every input point: (cluster << 32) | linear voxel index, x fastest.
+// pcl::VoxelGrid::applyFilter [EXTERNAL]: ijk = floor(p * inverse_leaf) - min_b, fp32 multiply.
+__global__ void __launch_bounds__(256) voxel_key_kernel(const float* __restrict__ xyz, int stride, int n,
+                                                        const int* __restrict__ domoff, int nd,
+                                                        const VoxGrid* __restrict__ vg, float inv_leaf,
+                                                        unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = xyz + (size_t)i * stride;
+  const float x = p[0], y = p[1], z = p[2];
+  unsigned long long key = ~0ull;  // non-finite points sort last and are dropped
+  if (isfinite(x) && isfinite(y) && isfinite(z)) {
+    const int d = nd > 1 ? find_dom(domoff, nd, i) : 0;
+    const VoxGrid g = vg[d];
+    const int i0 = (int)floorf(__fmul_rn(x, inv_leaf)) - g.min_b[0];
+    const int i1 = (int)floorf(__fmul_rn(y, inv_leaf)) - g.min_b[1];
+    const int i2 = (int)floorf(__fmul_rn(z, inv_leaf)) - g.min_b[2];
+    const unsigned lin = (unsigned)(i0 + i1 * g.div_b[0] + i2 * g.div_b[0] * g.div_b[1]);
+    key = ((unsigned long long)d << 32) | lin;
+  }
+  keys[i] = key;
+  vals[i] = i;
+}
+
+// One warp per voxel: centroid = (float)(sum_double / count); fills the leaf layout.
+__global__ void __launch_bounds__(256) centroid_kernel(const float* __restrict__ xyz, int stride,
+                                                       const unsigned long long* __restrict__ ukeys,
+                                                       const int* __restrict__ ucount, const int* __restrict__ ustart,
+                                                       const int* __restrict__ sorted_idx, int nvox,
+                                                       const VoxGrid* __restrict__ vg, float4* __restrict__ cent,
+                                                       int* __restrict__ layout) {
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (v >= nvox) return;
+  const int b = ustart[v], c = ucount[v];
+  double sx = 0, sy = 0, sz = 0;
+  for (int s = lane; s < c; s += kWarp) {
+    const float* p = xyz + (size_t)sorted_idx[b + s] * stride;
+    sx += (double)p[0];
+    sy += (double)p[1];
+    sz += (double)p[2];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    sx += __shfl_xor_sync(kFull, sx, o);
+    sy += __shfl_xor_sync(kFull, sy, o);
+    sz += __shfl_xor_sync(kFull, sz, o);
+  }
+  if (lane == 0) {
+    const double cnt = (double)c;
+    cent[v] = make_float4((float)(sx / cnt), (float)(sy / cnt), (float)(sz / cnt), 0.f);
+    const unsigned long long key = ukeys[v];
+    const int d = (int)(key >> 32);
+    layout[vg[d].layout_base + (unsigned)(key & 0xffffffffu)] = v - vg[d].vox_first;
+  }
+}
+
+struct VRsdArgs {
+  GridView g;
+  const float4* nrm;     // sorted order
+  const float4* cent;    // voxel centroids
+  const unsigned long long* ukeys;
+  int nvox;
+  float r2;
+  int ndiv, flags;
+  double radius, plane_radius;
+  float skip_thr;        // smallest fp32 d2 whose sqrt((double)d2) > radius
+  float bin_thr[9];      // ndiv + 1 entries
+  float2* radii;         // out r_min, r_max
+  int* labels;
+};
+
+// grsd_colorCHLAC_tools.hpp:104-116: fp32 radii compared against double literals
+__device__ __forceinline__ int get_type(float min_radius, float max_radius) {
+  if ((double)min_radius > 0.100) return 1;       // PLANE
+  if ((double)max_radius > 0.175) return 2;       // CYLINDER
+  if ((double)min_radius < 0.015) return 0;       // NOISE
+  if ((double)(max_radius - min_radius) < 0.050) return 3;  // SPHERE
+  return 4;                                        // EDGE
+}
+
+constexpr int kVDiv = 8;  // max nr_subdiv of the voxel RSD (PCL default 5)
+
+// One warp per voxel centroid.  pcl::RSDEstimation semantics [EXTERNAL] (call site :164-180):
+// neighbours = surface points within r of the centroid; reference element = the nearest one
+// (ties: smallest input index); angles/distances are measured from it; pairs farther than r from
+// it are skipped.
+__global__ void __launch_bounds__(256) voxel_rsd_kernel(const VRsdArgs a) {
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (v >= a.nvox) return;
+  const GridView& g = a.g;
+  const float4 q = a.cent[v];
+  const int d = (int)(a.ukeys[v] >> 32);
+  const Domain dm = g.domains[d];
+  const int cy = cell_coord(q.y, dm.oy, g.inv_cell, dm.ny), cz = cell_coord(q.z, dm.oz, g.inv_cell, dm.nz);
+  const int cx = xfine_coord(q.x, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift;
+  const int cxlo = max(cx - 1, 0), cxhi = min(cx + 1, dm.nx - 1);
+  int rb = 0, re = 0;
+  if (lane < 9) {
+    const int y = cy + lane % 3 - 1, z = cz + lane / 3 - 1;
+    if (y >= 0 && y < dm.ny && z >= 0 && z < dm.nz) {
+      const long long c = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
+      rb = g.cell_start[c + cxlo];
+      re = g.cell_start[c + cxhi + 1];
+    }
+  }
+  // pass 1: nearest surface point by (d2, input index)
+  float bd2 = INFINITY;
+  int bidx = INT_MAX, bpos = -1;
+  for (int t = 0; t < 9; ++t) {
+    const int b = __shfl_sync(kFull, rb, t), e = __shfl_sync(kFull, re, t);
+    for (int j = b + lane; j < e; j += kWarp) {
+      const float4 c = g.pos[j];
+      const float d2 = d2_rule(c.x, c.y, c.z, q.x, q.y, q.z);
+      if (d2 <= a.r2) {
+        const int id = g.perm[j];
+        if (d2 < bd2 || (d2 == bd2 && id < bidx)) {
+          bd2 = d2;
+          bidx = id;
+          bpos = j;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float od2 = __shfl_xor_sync(kFull, bd2, o);
+    const int oid = __shfl_xor_sync(kFull, bidx, o), op = __shfl_xor_sync(kFull, bpos, o);
+    if (od2 < bd2 || (od2 == bd2 && oid < bidx)) {
+      bd2 = od2;
+      bidx = oid;
+      bpos = op;
+    }
+  }
+  // per-lane bins: .lo = cosine of smallest |value| (largest angle), .hi = largest |value|
+  float lo[kVDiv], hi[kVDiv];
+#pragma unroll
+  for (int b = 0; b < kVDiv; ++b) {
+    lo[b] = INFINITY;
+    hi[b] = 0.f;
+  }
+  if ((a.flags & CAB_RSD_SEED_BIN0) && lane == 0) lo[0] = hi[0] = 1.f;
+  if (bpos >= 0) {
+    const float4 rp = g.pos[bpos];
+    const float4 rn = a.nrm[bpos];
+    for (int t = 0; t < 9; ++t) {
+      const int b = __shfl_sync(kFull, rb, t), e = __shfl_sync(kFull, re, t);
+      for (int j = b + lane; j < e; j += kWarp) {
+        if (j == bpos) continue;
+        const float4 c = g.pos[j];
+        if (!(d2_rule(c.x, c.y, c.z, q.x, q.y, q.z) <= a.r2)) continue;
+        const float dd = d2_rule(c.x, c.y, c.z, rp.x, rp.y, rp.z);
+        if (dd >= a.skip_thr) continue;  // dist > max_dist
+        const float4 nm = a.nrm[j];
+        // pcl::computeRSD: normals[*i] * normals[*begin], fp32, left to right
+        float cs = __fadd_rn(__fadd_rn(__fmul_rn(nm.x, rn.x), __fmul_rn(nm.y, rn.y)), __fmul_rn(nm.z, rn.z));
+        if (cs > 1.f) cs = 1.f;
+        if (cs < -1.f) cs = -1.f;
+        int bin = 0;
+#pragma unroll
+        for (int b = 1; b < kVDiv; ++b) bin += (b < a.ndiv && dd >= a.bin_thr[b]) ? 1 : 0;
+        const float ac = fabsf(cs);
+#pragma unroll
+        for (int b = 0; b < kVDiv; ++b)
+          if (b == bin) {
+            if (ac < fabsf(lo[b])) lo[b] = cs;
+            if (ac >= fabsf(hi[b])) hi[b] = cs;
+          }
+      }
+    }
+  }
+  // warp-reduce the bins (extremes of |cosine|)
+#pragma unroll
+  for (int b = 0; b < kVDiv; ++b) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ol = __shfl_xor_sync(kFull, lo[b], o), oh = __shfl_xor_sync(kFull, hi[b], o);
+      if (fabsf(ol) < fabsf(lo[b])) lo[b] = ol;
+      // keep the update rule "later >= wins" irrelevant: only |value| matters for the angle up to 1 ulp
+      if (fabsf(oh) > fabsf(hi[b])) hi[b] = oh;
+    }
+  }
+  if (lane == 0) {
+    double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;
+#pragma unroll
+    for (int di = 0; di < kVDiv; ++di) {
+      if (di < a.ndiv && fabsf(lo[di]) <= 1.f) {
+        double p_min = acos((double)hi[di]), p_max = acos((double)lo[di]);
+        if (p_min > M_PI / 2) p_min = M_PI - p_min;
+        if (p_max > M_PI / 2) p_max = M_PI - p_max;
+        const double f = (di + 0.5) * a.radius / a.ndiv;
+        Amint_Amin = __dadd_rn(Amint_Amin, __dmul_rn(p_min, p_min));
+        Amint_d = __dadd_rn(Amint_d, __dmul_rn(p_min, f));
+        Amaxt_Amax = __dadd_rn(Amaxt_Amax, __dmul_rn(p_max, p_max));
+        Amaxt_d = __dadd_rn(Amaxt_d, __dmul_rn(p_max, f));
+      }
+    }
+    const double max_radius = (Amint_Amin == 0) ? a.plane_radius : fmin(Amint_d / Amint_Amin, a.plane_radius);
+    const double min_radius = (Amaxt_Amax == 0) ? a.plane_radius : fmin(Amaxt_d / Amaxt_Amax, a.plane_radius);
+    float rmin = (float)min_radius, rmax = (float)max_radius;
+    if (a.flags & CAB_RSD_SCALE_SORT) {
+      const float x = rmax * 1.1f, y = rmin * 0.9f;
+      rmin = fminf(x, y);
+      rmax = fmaxf(x, y);
+    }
+    a.radii[v] = make_float2(rmin, rmax);
+    a.labels[v] = get_type(rmin, rmax);
+  }
+}
+
+__constant__ int c_off26[26][3];
+
+// One block per cluster: 6x6 transition matrix in shared memory (integer atomics), then the
+// upper triangle is packed into 21 bins (grsd_colorCHLAC_tools.hpp:230-276, hist_num == 1).
+__global__ void __launch_bounds__(128) transitions_kernel(const VoxGrid* __restrict__ vg, const int* __restrict__ vox_off,
+                                                          const float4* __restrict__ cent, const int* __restrict__ labels,
+                                                          const int* __restrict__ layout, float inv_leaf,
+                                                          int* __restrict__ hist21) {
+  __shared__ int M[36];
+  const int d = blockIdx.x;
+  if (threadIdx.x < 36) M[threadIdx.x] = 0;
+  __syncthreads();
+  const VoxGrid g = vg[d];
+  const int v0 = vox_off[d], v1 = vox_off[d + 1];
+  const int work = (v1 - v0) * 26;
+  for (int w = threadIdx.x; w < work; w += blockDim.x) {
+    const int v = v0 + w / 26, o = w % 26;
+    const float4 c = cent[v];
+    // pcl::VoxelGrid::getNeighborCentroidIndices [EXTERNAL]: ijk = floor(ref * inverse_leaf)
+    const int i0 = (int)floorf(__fmul_rn(c.x, inv_leaf)), i1 = (int)floorf(__fmul_rn(c.y, inv_leaf)),
+              i2 = (int)floorf(__fmul_rn(c.z, inv_leaf));
+    const int n0 = i0 + c_off26[o][0] - g.min_b[0], n1 = i1 + c_off26[o][1] - g.min_b[1],
+              n2 = i2 + c_off26[o][2] - g.min_b[2];
+    int nt = 5;  // EMPTY
+    if (n0 >= 0 && n0 < g.div_b[0] && n1 >= 0 && n1 < g.div_b[1] && n2 >= 0 && n2 < g.div_b[2]) {
+      const int nb = layout[g.layout_base + n0 + (long long)n1 * g.div_b[0] + (long long)n2 * g.div_b[0] * g.div_b[1]];
+      if (nb >= 0) nt = labels[v0 + nb];
+    }
+    atomicAdd(&M[labels[v] * 6 + nt], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nrf = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) hist21[d * 21 + nrf++] = M[i * 6 + j];
+  }
+}
+
+float d2_threshold(double radius, float r2_hi, bool (*pred)(double, double, int, int), int b, int ndiv) {
+  // smallest fp32 d2 in [0, r2_hi] with pred true (pred monotone in d2); INFINITY if none
+  if (!pred(std::sqrt((double)r2_hi), radius, b, ndiv)) return INFINITY;
+  if (pred(0.0, radius, b, ndiv)) return 0.f;
+  uint32_t lo = 0, hi;
+  std::memcpy(&hi, &r2_hi, 4);
+  while (hi - lo > 1) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    float f;
+    std::memcpy(&f, &mid, 4);
+    if (pred(std::sqrt((double)f), radius, b, ndiv)) hi = mid; else lo = mid;
+  }
+  float f;
+  std::memcpy(&f, &hi, 4);
+  return f;
+}
+bool pred_bin(double dist, double radius, int b, int ndiv) { return (int)std::floor(ndiv * dist / radius) >= b; }
+bool pred_skip(double dist, double radius, int, int) { return dist > radius; }
+
+}  // namespace
+
+int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_t* hist21) {
+  const int n = (int)ctx->n, nd = ctx->n_domains;
+  cudaStream_t st = ctx->stream;
+  if (!(leaf > 0.f)) return fail(ctx, CAB_ERR_ARG, "cab_grsd_batch: leaf must be > 0");
+  const int ndiv = 5;              // PCL RSDEstimation default nr_subdiv, never overridden in the reference tree
+  const double plane_radius = 0.2;  // PCL default plane_radius
+
+  // ---- voxel grid descriptors (host, tiny) ---------------------------------------------
+  const float inv_leaf = 1.0f / leaf;
+  std::vector<VoxGrid> vg(nd);
+  long long layout_total = 0;
+  for (int d = 0; d < nd; ++d) {
+    VoxGrid& g = vg[d];
+    g.layout_base = layout_total;
+    g.vox_first = 0;
+    if (ctx->dom_count[d] == 0) {
+      for (int a = 0; a < 3; ++a) g.min_b[a] = 0, g.div_b[a] = 0;
+      continue;
+    }
+    long long cells = 1;
+    for (int a = 0; a < 3; ++a) {
+      g.min_b[a] = (int)std::floor(ctx->dom_bounds[6 * (size_t)d + a] * inv_leaf);
+      const int max_b = (int)std::floor(ctx->dom_bounds[6 * (size_t)d + 3 + a] * inv_leaf);
+      g.div_b[a] = max_b - g.min_b[a] + 1;
+      cells *= g.div_b[a];
+    }
+    if (cells > 0x7fffffffll) return fail(ctx, CAB_ERR_OOM, "cab_grsd_batch: voxel grid of cluster %d too large", d);
+    layout_total += cells;
+  }
+  if (layout_total > ((long long)1 << 31)) return fail(ctx, CAB_ERR_OOM, "cab_grsd_batch: leaf layouts too large");
+
+  if (int rc = reserve(ctx, ctx->g_vgrid, nd * sizeof(VoxGrid))) return rc;
+  if (int rc = reserve(ctx, ctx->g_vkeys[0], (size_t)std::max(n, 1) * 8)) return rc;
+  if (int rc = reserve(ctx, ctx->g_vkeys[1], (size_t)std::max(n, 1) * 8)) return rc;
+  if (int rc = reserve(ctx, ctx->g_vvals[0], (size_t)std::max(n, 1) * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->g_vvals[1], (size_t)std::max(n, 1) * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->g_layout, (size_t)std::max<long long>(layout_total, 1) * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->g_hist, (size_t)nd * 21 * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->g_voff, (size_t)(nd + 1) * 4)) return rc;
+  // unique voxel arrays are bounded by n
+  if (int rc = reserve(ctx, ctx->g_vfirst, ((size_t)std::max(n, 1) + 1) * 8 + 16)) return rc;       // unique keys (+ num_runs)
+  if (int rc = reserve(ctx, ctx->g_vcount, ((size_t)std::max(n, 1) + 1) * 4 * 2)) return rc;       // counts + starts
+
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+  if (int rc = reserve_pinned(ctx, nd * sizeof(VoxGrid) + (nd + 1) * 8)) return rc;
+  std::memcpy(ctx->h_pin, vg.data(), nd * sizeof(VoxGrid));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->g_vgrid.p, ctx->h_pin, nd * sizeof(VoxGrid), cudaMemcpyHostToDevice, st));
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->g_layout.p, 0xff, (size_t)std::max<long long>(layout_total, 1) * 4, st));
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->g_hist.p, 0, (size_t)nd * 21 * 4, st));
+
+  unsigned long long* ukeys = (unsigned long long*)ctx->g_vfirst.p;
+  int* num_runs = (int*)((char*)ctx->g_vfirst.p + ((size_t)std::max(n, 1) + 1) * 8);
+  int* ucount = (int*)ctx->g_vcount.p;
+  int* ustart = ucount + (std::max(n, 1) + 1);
+  int nvox = 0;
+  std::vector<int> vox_off(nd + 1, 0);
+  if (n > 0) {
+    voxel_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, (const int*)ctx->b_domoff.p, nd,
+                                                      (const VoxGrid*)ctx->g_vgrid.p, inv_leaf,
+                                                      (unsigned long long*)ctx->g_vkeys[0].p, (int*)ctx->g_vvals[0].p);
+    CAB_LAUNCH_CHECK(ctx);
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (const int*)nullptr, (int*)nullptr, n, 0, 64, st);
+    cub::DeviceRunLengthEncode::Encode(nullptr, t2, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                       (int*)nullptr, (int*)nullptr, n, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, t3, (const int*)nullptr, (int*)nullptr, n + 1, st);
+    size_t tmp = std::max(t1, std::max(t2, t3));
+    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp + 16)) return rc;
+    int dom_bits = 1;
+    while ((1 << dom_bits) < nd) ++dom_bits;
+    CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp, (const unsigned long long*)ctx->g_vkeys[0].p,
+                                                  (unsigned long long*)ctx->g_vkeys[1].p, (const int*)ctx->g_vvals[0].p,
+                                                  (int*)ctx->g_vvals[1].p, n, 0, 64, st));
+    CAB_CUDA(ctx, cub::DeviceRunLengthEncode::Encode(ctx->b_cubtmp.p, tmp, (const unsigned long long*)ctx->g_vkeys[1].p,
+                                                     ukeys, ucount, num_runs, n, st));
+    ctx->tm.kernel_launches += 9 + 3;
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, num_runs, 4, cudaMemcpyDeviceToHost, st));
+    CAB_CUDA(ctx, cudaStreamSynchronize(st));
+    int runs = *(const int*)ctx->h_pin;
+    // the last run may be the non-finite sentinel key
+    std::vector<unsigned long long> hkeys;
+    hkeys.resize(runs);
+    if (runs) CAB_CUDA(ctx, cudaMemcpy(hkeys.data(), ukeys, (size_t)runs * 8, cudaMemcpyDeviceToHost));
+    nvox = runs;
+    if (runs && hkeys[runs - 1] == ~0ull) nvox = runs - 1;
+    // voxel range of every cluster
+    int v = 0;
+    for (int d = 0; d < nd; ++d) {
+      vox_off[d] = v;
+      while (v < nvox && (int)(hkeys[v] >> 32) == d) ++v;
+    }
+    vox_off[nd] = v;
+    for (int d = 0; d < nd; ++d) vg[d].vox_first = vox_off[d];
+    std::memcpy(ctx->h_pin, vg.data(), nd * sizeof(VoxGrid));
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->g_vgrid.p, ctx->h_pin, nd * sizeof(VoxGrid), cudaMemcpyHostToDevice, st));
+    CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp, ucount, ustart, runs + 1, st));
+    ctx->tm.kernel_launches += 2;
+  }
+  {
+    int* hv = (int*)((char*)ctx->h_pin + nd * sizeof(VoxGrid));
+    std::memcpy(hv, vox_off.data(), (nd + 1) * 4);
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->g_voff.p, hv, (nd + 1) * 4, cudaMemcpyHostToDevice, st));
+  }
+  ctx->g_nvox = nvox;
+  ctx->g_vox_offsets.assign(vox_off.begin(), vox_off.end());
+  if (int rc = reserve(ctx, ctx->g_cent, (size_t)std::max(nvox, 1) * sizeof(float4))) return rc;
+  if (int rc = reserve(ctx, ctx->g_vrad, (size_t)std::max(nvox, 1) * sizeof(float2))) return rc;
+  if (int rc = reserve(ctx, ctx->g_vlabel, (size_t)std::max(nvox, 1) * sizeof(int))) return rc;
+
+  if (nvox > 0) {
+    const unsigned blocks = (unsigned)(((size_t)nvox * kWarp + 255) / 256);
+    centroid_kernel<<<blocks, 256, 0, st>>>(ctx->xyz_in, ctx->stride, ukeys, ucount, ustart, (const int*)ctx->g_vvals[1].p,
+                                            nvox, (const VoxGrid*)ctx->g_vgrid.p, (float4*)ctx->g_cent.p,
+                                            (int*)ctx->g_layout.p);
+    CAB_LAUNCH_CHECK(ctx);
+    VRsdArgs a{};
+    a.g = grid_view(ctx);
+    a.nrm = (const float4*)ctx->b_nrm.p;
+    a.cent = (const float4*)ctx->g_cent.p;
+    a.ukeys = ukeys;
+    a.nvox = nvox;
+    const float rf = (float)r_rsd;
+    a.r2 = rf * rf;
+    a.ndiv = ndiv;
+    a.flags = rsd_flags;
+    a.radius = r_rsd;
+    a.plane_radius = plane_radius;
+    // distances from the reference element can reach 2r: thresholds searched up to (2r)^2 * 1.01
+    const float hi2 = 4.04f * a.r2;
+    a.skip_thr = d2_threshold(r_rsd, hi2, pred_skip, 0, ndiv);
+    a.bin_thr[0] = -INFINITY;
+    for (int b = 1; b < ndiv; ++b) a.bin_thr[b] = d2_threshold(r_rsd, hi2, pred_bin, b, ndiv);
+    for (int b = ndiv; b < 9; ++b) a.bin_thr[b] = INFINITY;
+    a.radii = (float2*)ctx->g_vrad.p;
+    a.labels = (int*)ctx->g_vlabel.p;
+    voxel_rsd_kernel<<<blocks, 256, 0, st>>>(a);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  {
+    static const int off13[13][3] = {{-1, -1, -1}, {-1, 0, -1}, {-1, 1, -1}, {0, -1, -1}, {0, 0, -1}, {0, 1, -1}, {1, -1, -1},
+                                     {1, 0, -1},   {1, 1, -1},  {-1, -1, 0}, {0, -1, 0},  {1, -1, 0}, {-1, 0, 0}};
+    static int off26[26][3];
+    for (int c = 0; c < 13; ++c)
+      for (int k = 0; k < 3; ++k) {
+        off26[c][k] = off13[c][k];
+        off26[13 + c][k] = -off13[c][k];
+      }
+    CAB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_off26, off26, sizeof(off26), 0, cudaMemcpyHostToDevice, st));
+  }
+  transitions_kernel<<<nd, 128, 0, st>>>((const VoxGrid*)ctx->g_vgrid.p, (const int*)ctx->g_voff.p, (const float4*)ctx->g_cent.p,
+                                         (const int*)ctx->g_vlabel.p, (const int*)ctx->g_layout.p, inv_leaf,
+                                         (int*)ctx->g_hist.p);
+  CAB_LAUNCH_CHECK(ctx);
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+  if (hist21) CAB_CUDA(ctx, cudaMemcpyAsync(hist21, ctx->g_hist.p, (size_t)nd * 21 * 4, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.grsd_ms, ctx->ev[4], ctx->ev[5]));
+  return CAB_OK;
+}
+
+}  // namespace cab
+
+using namespace cab;
+
+extern "C" {
+
+int cab_grsd_batch(cab_ctx* ctx, const float* xyz, int32_t stride, const int32_t* offsets, int32_t nclusters, float leaf,
+                   float r_normals, double rsd_radius_min, int32_t rsd_flags, const float vp[3], const float* nx,
+                   const float* ny, const float* nz, int32_t* hist21) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (!offsets || nclusters < 1) return fail(ctx, CAB_ERR_ARG, "cab_grsd_batch: offsets / nclusters");
+  if (!(leaf > 0.f)) return fail(ctx, CAB_ERR_ARG, "cab_grsd_batch: leaf must be > 0");
+  const bool have_n = nx && ny && nz;
+  if (!have_n && (nx || ny || nz)) return fail(ctx, CAB_ERR_ARG, "cab_grsd_batch: give all of nx, ny, nz or none");
+  const int64_t n = offsets[nclusters];
+  if (int rc = cab_upload_clusters(ctx, xyz, n, stride, offsets, nclusters)) return rc;
+  // grsd_colorCHLAC_tools.hpp:172: std::max(rsd_radius_search, voxel_size/2 * sqrt(3)); float/2 * double
+  const double r_rsd = std::max(rsd_radius_min, (double)(leaf / 2) * std::sqrt(3.0));
+  float cell = (float)r_rsd;
+  if ((double)cell < r_rsd) cell = std::nextafter(cell, INFINITY);
+  if (!have_n) cell = std::max(cell, r_normals);
+  if (int rc = cab_build_grid(ctx, cell)) return rc;
+  if (have_n) {
+    if (int rc = cab_set_normals(ctx, nx, ny, nz)) return rc;
+  } else {
+    if (int rc = cab_normals(ctx, r_normals, 0, vp, nullptr)) return rc;
+  }
+  return run_grsd_batch(ctx, leaf, r_rsd, rsd_flags, hist21);
+}
+
+int64_t cab_grsd_voxels(cab_ctx* ctx, int64_t* vox_offsets, float* centroids_xyz, float* r_min, float* r_max,
+                        int32_t* labels, int64_t cap) {
+  if (!ctx) return CAB_ERR_ARG;
+  const int64_t nv = ctx->g_nvox;
+  if (vox_offsets)
+    for (size_t i = 0; i < ctx->g_vox_offsets.size(); ++i) vox_offsets[i] = ctx->g_vox_offsets[i];
+  if (nv == 0 || nv > cap) return nv;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, CAB_ERR_CUDA, "cudaSetDevice failed");
+  std::vector<float4> c(nv);
+  std::vector<float2> r(nv);
+  CAB_CUDA(ctx, cudaMemcpy(c.data(), ctx->g_cent.p, nv * sizeof(float4), cudaMemcpyDeviceToHost));
+  CAB_CUDA(ctx, cudaMemcpy(r.data(), ctx->g_vrad.p, nv * sizeof(float2), cudaMemcpyDeviceToHost));
+  if (labels) CAB_CUDA(ctx, cudaMemcpy(labels, ctx->g_vlabel.p, nv * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < nv; ++i) {
+    if (centroids_xyz) {
+      centroids_xyz[3 * i] = c[i].x;
+      centroids_xyz[3 * i + 1] = c[i].y;
+      centroids_xyz[3 * i + 2] = c[i].z;
+    }
+    if (r_min) r_min[i] = r[i].x;
+    if (r_max) r_max[i] = r[i].y;
+  }
+  return nv;
+}
+
+}  // extern "C"

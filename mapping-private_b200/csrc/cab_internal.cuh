@@ -1,0 +1,151 @@
+// cab_internal.cuh -- shared declarations of libcloudalgos_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "cloud_algos_b200.h"
+
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ < 1000
+#error "libcloudalgos_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace cab {
+
+constexpr int kWarp = 32;
+constexpr int kXBits = 20;            // sub-cell x field of the sort key
+constexpr uint32_t kFull = 0xffffffffu;
+
+// One independent neighbourhood domain: the whole cloud, or one segmented cluster.
+struct Domain {
+  float ox, oy, oz;      // grid origin
+  int nx, ny, nz;        // cells per axis
+  int xshift;            // x_fine >> xshift == cell x
+  int pad;
+  int64_t row_base;      // first row id of this domain (row = row_base + cz*ny + cy)
+  int64_t cell_base;     // first cell id (cell = cell_base + (cz*ny+cy)*nx + cx)
+};
+
+// 32-query work unit: consecutive sorted points of one row.
+struct Packet {
+  int start, count;
+  int row_local;  // cz*ny + cy inside the domain
+  int domain;
+};
+
+// Read-only view of the search structure handed to kernels.
+struct GridView {
+  const float4* pos;        // sorted positions (x,y,z,0)
+  const int* perm;          // sorted -> input index
+  const int* cell_start;    // n_cells + 1
+  const Packet* packets;
+  const Domain* domains;
+  int n_valid;              // finite points (sorted positions [0, n_valid))
+  int n_packets;
+  float inv_cell;           // 1 / effective cell edge
+  float xscale_unused;
+};
+
+// ---- the documented epsilon rule -------------------------------------------------------
+// d2 = (dx*dx + dy*dy) + dz*dz in fp32 with no FMA contraction; d = p - q.
+__device__ __forceinline__ float d2_rule(float px, float py, float pz, float qx, float qy, float qz) {
+  float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Cell coordinate along one axis; identical code in the key kernel and in the query kernels.
+__device__ __forceinline__ int cell_coord(float v, float origin, float inv_cell, int n) {
+  int c = (int)floorf(__fmul_rn(__fsub_rn(v, origin), inv_cell));
+  return min(max(c, 0), n - 1);
+}
+// Fine x coordinate (sub-cell resolution 2^-xshift of a cell).
+__device__ __forceinline__ int xfine_coord(float x, float ox, float inv_cell, int nx, int xshift) {
+  float s = __fmul_rn(__fsub_rn(x, ox), __fmul_rn(inv_cell, (float)(1 << xshift)));
+  int c = (int)floorf(s);
+  return min(max(c, 0), (nx << xshift) - 1);
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace cab
+
+struct cab_ctx {
+  cab_config cfg{};
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8]{};
+  std::string err;
+  cab_timings tm{};
+
+  // cloud
+  int64_t n = 0;            // points
+  int n_valid = 0;
+  int n_domains = 0;
+  bool have_cloud = false, have_grid = false, have_normals = false, have_rsd = false;
+  bool cloud_external = false;
+  const float* xyz_in = nullptr;  // device, stride floats
+  int stride = 3;
+  std::vector<int32_t> dom_offsets;  // host copy, n_domains + 1
+  std::vector<cab::Domain> domains;  // host copy
+  std::vector<float> dom_bounds;     // host copy, 6 per domain (min xyz, max xyz); valid if dom_count > 0
+  std::vector<uint32_t> dom_count;   // finite points per domain
+  float cell = 0.f, cell_eff = 0.f, inv_cell = 0.f;
+  int64_t n_rows = 0, n_cells = 0;
+  int n_packets = 0;
+  int shard_rank = 0, shard_world = 1;
+
+  // device arena (grow-only)
+  cab::DevBuf b_xyz, b_domoff, b_domid, b_bounds, b_domains, b_keys[2], b_vals[2], b_cubtmp, b_pos,
+      b_perm, b_cellcnt, b_cellstart, b_rowpk, b_packets, b_nrm, b_nrm_in, b_rsd, b_kcount, b_stats,
+      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc;
+  // pinned staging
+  void* h_pin = nullptr;
+  size_t h_pin_cap = 0;
+
+  // GRSD results of the last batch
+  cab::DevBuf g_vkeys[2], g_vvals[2], g_cent, g_vcount, g_vrad, g_vlabel, g_voff, g_layout, g_layoff,
+      g_vgrid, g_hist, g_vfirst;
+  int64_t g_nvox = 0;
+  std::vector<int64_t> g_vox_offsets;
+};
+
+namespace cab {
+
+int fail(cab_ctx* ctx, int code, const char* fmt, ...);
+int reserve(cab_ctx* ctx, DevBuf& b, size_t bytes);
+int reserve_pinned(cab_ctx* ctx, size_t bytes);
+GridView grid_view(const cab_ctx* ctx);
+void packet_range(const cab_ctx* ctx, int* p0, int* p1);
+
+#define CAB_CUDA(ctx, call)                                                                  \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return cab::fail((ctx), CAB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                       __FILE__, __LINE__);                                                  \
+  } while (0)
+
+#define CAB_LAUNCH_CHECK(ctx)                                                                \
+  do {                                                                                       \
+    (ctx)->tm.kernel_launches++;                                                             \
+    CAB_CUDA((ctx), cudaGetLastError());                                                     \
+  } while (0)
+
+// stage entry points (each enqueues on ctx->stream; callers synchronise)
+int build_grid(cab_ctx* ctx, float cell);
+int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3]);
+int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, int flags);
+int run_thresholds(cab_ctx* ctx, float r, int max_nn);  // max_nn truncation thresholds
+int64_t run_neighbors_debug(cab_ctx* ctx, float r, int max_nn, int64_t q0, int64_t q1, int64_t* offsets,
+                            int32_t* idx, float* d2, int64_t cap);
+int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_t* hist21);
+int permute_normals_in(cab_ctx* ctx, const float* nx, const float* ny, const float* nz);
+int download_results(cab_ctx* ctx, float* n4, float* rmin, float* rmax);
+
+}  // namespace cab

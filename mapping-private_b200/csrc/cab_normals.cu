@@ -1,0 +1,228 @@
+// cab_normals.cu -- radius-neighbourhood PCA normals.
+// Replaces pcl::NormalEstimation::compute with setRadiusSearch(r) as called at
+// color_chlac/include/color_chlac/grsd_colorCHLAC_tools.hpp:76-81 (and exampleRSD.cpp:51-58,
+// computeGRSD.cpp:101-106, hough_segmentation/src/rsd.cpp:65-72): neighbours with d2 <= r2
+// (self included), covariance about the centroid, eigenvector of the smallest eigenvalue,
+// curvature = l0 / (l0+l1+l2), flipped towards the viewpoint; fewer than 3 neighbours -> NaN.
+#include <cmath>
+
+#include "cab_internal.cuh"
+#include "cab_traverse.cuh"
+
+namespace cab {
+
+namespace {
+
+// Cyclic Jacobi on a symmetric 3x3 (a = xx,xy,xz,yy,yz,zz).  Returns the smallest eigenvalue and
+// its eigenvector.  Everything stays in registers (fully unrolled, no dynamic indexing).
+template <typename T, int kSweeps>
+__device__ __forceinline__ void smallest_eigen(T a00, T a01, T a02, T a11, T a12, T a22, T& lam, T& nx, T& ny,
+                                               T& nz) {
+  T v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+#define CAB_ROT(app, aqq, apq, arp, arq, v0p, v0q, v1p, v1q, v2p, v2q)          \
+  if (apq != T(0)) {                                                           \
+    T theta = (aqq - app) / (T(2) * apq);                                      \
+    T t = T(1) / (fabs(theta) + sqrt(theta * theta + T(1)));                   \
+    t = theta < T(0) ? -t : t;                                                 \
+    T c = T(1) / sqrt(t * t + T(1)), s = t * c;                                \
+    app -= t * apq;                                                            \
+    aqq += t * apq;                                                            \
+    apq = T(0);                                                                \
+    T x = arp, y = arq;                                                        \
+    arp = c * x - s * y;                                                       \
+    arq = s * x + c * y;                                                       \
+    x = v0p; y = v0q; v0p = c * x - s * y; v0q = s * x + c * y;                \
+    x = v1p; y = v1q; v1p = c * x - s * y; v1q = s * x + c * y;                \
+    x = v2p; y = v2q; v2p = c * x - s * y; v2q = s * x + c * y;                \
+  }
+#pragma unroll 1
+  for (int sweep = 0; sweep < kSweeps; ++sweep) {
+    if (a01 == T(0) && a02 == T(0) && a12 == T(0)) break;
+    CAB_ROT(a00, a11, a01, a02, a12, v00, v01, v10, v11, v20, v21)  // (p,q)=(0,1), r=2
+    CAB_ROT(a00, a22, a02, a01, a12, v00, v02, v10, v12, v20, v22)  // (0,2), r=1
+    CAB_ROT(a11, a22, a12, a01, a02, v01, v02, v11, v12, v21, v22)  // (1,2), r=0
+  }
+#undef CAB_ROT
+  lam = a00; nx = v00; ny = v10; nz = v20;
+  if (a11 < lam) { lam = a11; nx = v01; ny = v11; nz = v21; }
+  if (a22 < lam) { lam = a22; nx = v02; ny = v12; nz = v22; }
+}
+
+struct NormalsArgs {
+  GridView g;
+  int p0, p1;
+  float r, r2;
+  float vpx, vpy, vpz;
+  float4* nrm;              // sorted order
+  int* kcount;              // sorted order
+  const float* thr_d2;      // optional max_nn thresholds (sorted order), may be null
+  const int* thr_idx;
+  unsigned long long* stats;  // [0] neighbour sum, [1] candidate sum
+};
+
+template <bool kExact>
+__global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const NormalsArgs a) {
+  __shared__ float4 tile[kWarpsPerBlock][kWarp];
+  __shared__ unsigned long long blk_stats[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pid = a.p0 + blockIdx.x * kWarpsPerBlock + warp;
+  if (threadIdx.x < 2) blk_stats[threadIdx.x] = 0;
+  __syncthreads();
+  if (pid < a.p1) {
+    const GridView& g = a.g;
+    const PacketCtx pc = load_packet(g, pid, lane, a.r);
+    const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
+    const float r2 = a.r2;
+    // optional max_nn truncation: accept (d2, input idx) <= (thr_d2, thr_idx)
+    const bool use_thr = a.thr_d2 != nullptr;
+    float td2 = 0.f;
+    int tidx = 0;
+    if (use_thr) {
+      td2 = a.thr_d2[pc.qi];
+      tidx = a.thr_idx[pc.qi];
+    }
+    using Acc = typename std::conditional<kExact, double, float>::type;
+    Acc s1x = 0, s1y = 0, s1z = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    int k = 0;
+    float4* my_tile = tile[warp];
+    const int tested = for_each_chunk(
+        g, pc, lane, [&](int, bool, const float4& c) { my_tile[lane] = c; },
+        [&](int base, int cnt) {
+          const int cnt4 = (cnt + 3) & ~3;
+#pragma unroll 4
+          for (int m = 0; m < cnt4; ++m) {
+            const float4 c = my_tile[m];
+            const float dx = __fsub_rn(c.x, qx), dy = __fsub_rn(c.y, qy), dz = __fsub_rn(c.z, qz);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            bool hit = d2 <= r2;
+            if (use_thr && hit) hit = d2 < td2 || (d2 == td2 && g.perm[base + m] <= tidx);
+            if (hit) {
+              if (kExact) {
+                const double ex = dx, ey = dy, ez = dz;
+                s1x += ex; s1y += ey; s1z += ez;
+                sxx = __fma_rn(ex, ex, sxx); sxy = __fma_rn(ex, ey, sxy); sxz = __fma_rn(ex, ez, sxz);
+                syy = __fma_rn(ey, ey, syy); syz = __fma_rn(ey, ez, syz); szz = __fma_rn(ez, ez, szz);
+              } else {
+                s1x += dx; s1y += dy; s1z += dz;
+                sxx = fmaf(dx, dx, sxx); sxy = fmaf(dx, dy, sxy); sxz = fmaf(dx, dz, sxz);
+                syy = fmaf(dy, dy, syy); syz = fmaf(dy, dz, syz); szz = fmaf(dz, dz, szz);
+              }
+              ++k;
+            }
+          }
+        });
+
+    // ---- finalise: covariance about the centroid (fp64), eigen-solve ---------------------
+    float4 out;
+    if (k < 3) {
+      const float nan = __int_as_float(0x7fc00000);
+      out = make_float4(nan, nan, nan, nan);
+    } else {
+      // written with explicit roundings so the CPU oracle's plain expressions give the same bits
+      const double inv = __drcp_rn((double)k);
+      const double mx = __dmul_rn((double)s1x, inv), my = __dmul_rn((double)s1y, inv), mz = __dmul_rn((double)s1z, inv);
+      const double cxx = __dsub_rn(__dmul_rn((double)sxx, inv), __dmul_rn(mx, mx));
+      const double cxy = __dsub_rn(__dmul_rn((double)sxy, inv), __dmul_rn(mx, my));
+      const double cxz = __dsub_rn(__dmul_rn((double)sxz, inv), __dmul_rn(mx, mz));
+      const double cyy = __dsub_rn(__dmul_rn((double)syy, inv), __dmul_rn(my, my));
+      const double cyz = __dsub_rn(__dmul_rn((double)syz, inv), __dmul_rn(my, mz));
+      const double czz = __dsub_rn(__dmul_rn((double)szz, inv), __dmul_rn(mz, mz));
+      const double tr = cxx + cyy + czz;
+      double lam, nx, ny, nz;
+      if (kExact) {
+        smallest_eigen<double, 12>(cxx, cxy, cxz, cyy, cyz, czz, lam, nx, ny, nz);
+        const double len = sqrt(nx * nx + ny * ny + nz * nz);
+        nx /= len; ny /= len; nz /= len;
+        lam = (tr != 0.0) ? fabs(lam / tr) : 0.0;
+      } else {
+        const float sc = (tr > 0.0) ? (float)(1.0 / tr) : 1.f;
+        float fl, fx, fy, fz;
+        smallest_eigen<float, 6>((float)cxx * sc, (float)cxy * sc, (float)cxz * sc, (float)cyy * sc, (float)cyz * sc,
+                                 (float)czz * sc, fl, fx, fy, fz);
+        const float il = rsqrtf(fx * fx + fy * fy + fz * fz);
+        nx = fx * il; ny = fy * il; nz = fz * il;
+        lam = (tr > 0.0) ? fabsf(fl) : 0.f;
+      }
+      // flipNormalTowardsViewpoint: n.(vp - p) >= 0
+      const double dot = nx * ((double)a.vpx - qx) + ny * ((double)a.vpy - qy) + nz * ((double)a.vpz - qz);
+      if (dot < 0) { nx = -nx; ny = -ny; nz = -nz; }
+      out = make_float4((float)nx, (float)ny, (float)nz, (float)lam);
+    }
+    if (pc.active) {
+      a.nrm[pc.qi] = out;
+      a.kcount[pc.qi] = k;
+    }
+    unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ks += __shfl_xor_sync(kFull, ks, o);
+    if (lane == 0) {
+      atomicAdd(&blk_stats[0], ks);
+      atomicAdd(&blk_stats[1], (unsigned long long)tested * (unsigned)pc.count);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && blk_stats[threadIdx.x]) atomicAdd(a.stats + threadIdx.x, blk_stats[threadIdx.x]);
+}
+
+__global__ void fill_invalid_normals(float4* nrm, int* kcount, int begin, int end) {
+  int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= end) return;
+  const float nan = __int_as_float(0x7fc00000);
+  nrm[i] = make_float4(nan, nan, nan, nan);
+  kcount[i] = 0;
+}
+
+}  // namespace
+
+int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3]) {
+  if (!ctx->have_grid) return fail(ctx, CAB_ERR_STATE, "cab_normals: build the grid first");
+  if (!(r > 0.f) || r > ctx->cell * 1.0000001f)
+    return fail(ctx, CAB_ERR_ARG, "cab_normals: radius %g exceeds the grid cell %g", (double)r, (double)ctx->cell);
+  const int n = (int)ctx->n;
+  cudaStream_t st = ctx->stream;
+  if (int rc = reserve(ctx, ctx->b_nrm, (size_t)std::max(n, 1) * sizeof(float4))) return rc;
+  if (int rc = reserve(ctx, ctx->b_kcount, (size_t)std::max(n, 1) * sizeof(int))) return rc;
+  if (int rc = reserve(ctx, ctx->b_stats, 64)) return rc;
+  const bool use_thr = max_nn > 0;
+  if (use_thr)
+    if (int rc = run_thresholds(ctx, r, max_nn)) return rc;
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, 64, st));
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+  NormalsArgs a{};
+  a.g = grid_view(ctx);
+  packet_range(ctx, &a.p0, &a.p1);
+  a.r = r;
+  a.r2 = r * r;
+  a.vpx = vp ? vp[0] : 0.f;
+  a.vpy = vp ? vp[1] : 0.f;
+  a.vpz = vp ? vp[2] : 0.f;
+  a.nrm = (float4*)ctx->b_nrm.p;
+  a.kcount = (int*)ctx->b_kcount.p;
+  a.thr_d2 = use_thr ? (const float*)ctx->b_thr_d2.p : nullptr;
+  a.thr_idx = use_thr ? (const int*)ctx->b_thr_idx.p : nullptr;
+  a.stats = (unsigned long long*)ctx->b_stats.p;
+  const int np = a.p1 - a.p0;
+  if (np > 0) {
+    const unsigned blocks = (np + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (ctx->cfg.exact)
+      normals_kernel<true><<<blocks, kWarpsPerBlock * kWarp, 0, st>>>(a);
+    else
+      normals_kernel<false><<<blocks, kWarpsPerBlock * kWarp, 0, st>>>(a);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  if (n > ctx->n_valid) {
+    fill_invalid_normals<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((float4*)ctx->b_nrm.p, (int*)ctx->b_kcount.p,
+                                                                        ctx->n_valid, n);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->b_stats.p, 16, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.normals_ms, ctx->ev[2], ctx->ev[3]));
+  ctx->tm.neighbour_sum = (int64_t)((const unsigned long long*)ctx->h_pin)[0];
+  ctx->tm.candidate_sum = (int64_t)((const unsigned long long*)ctx->h_pin)[1];
+  ctx->have_normals = true;
+  return CAB_OK;
+}
+
+}  // namespace cab

@@ -1,0 +1,272 @@
+// cab_topk.cu -- max_nn truncation thresholds and the neighbour-set debug path.
+//
+// The reference keeps at most max_nn_ neighbours per query
+// (kdtree_->radiusSearch(cp, radius_, idx, d2, max_nn_), cloud_algos/src/radius_estimation.cpp:120;
+// default 150 at radius_estimation.h:82, 75 in launch/pipeline_tmp.launch:20).  The documented rule
+// is "the max_nn smallest (d2, input index) pairs".  Instead of materialising and sorting lists,
+// every query gets a threshold pair (d2*, idx*) found by a radix select over the fp32 bit pattern
+// of d2 (6 bits per traversal) plus an index tie-break; the normals / RSD kernels then accept a
+// candidate iff (d2, idx) <= (d2*, idx*).
+#include <climits>
+#include <cmath>
+#include <cstring>
+
+#include <vector>
+
+#include "cab_internal.cuh"
+#include "cab_traverse.cuh"
+
+namespace cab {
+
+namespace {
+
+constexpr int kSelWarps = 4;
+constexpr int kSelBins = 64;
+
+struct ThrArgs {
+  GridView g;
+  int p0, p1;
+  float r, r2;
+  int max_nn;
+  int first_shift;  // 30 when r2 needs bit 30/31, else 24
+  float* thr_d2;
+  int* thr_idx;
+};
+
+__global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrArgs a) {
+  __shared__ float4 tile[kSelWarps][kWarp];
+  __shared__ unsigned hist[kSelWarps][kSelBins][kWarp];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pid = a.p0 + blockIdx.x * kSelWarps + warp;
+  if (pid >= a.p1) return;
+  const GridView& g = a.g;
+  const PacketCtx pc = load_packet(g, pid, lane, a.r);
+  const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z, r2 = a.r2;
+  float4* my_tile = tile[warp];
+  auto stage = [&](int, bool, const float4& c) { my_tile[lane] = c; };
+
+  unsigned prefix = 0, mask = 0;
+  int target = a.max_nn;
+  bool need = pc.active;
+  for (int shift = a.first_shift; shift >= 0; shift -= 6) {
+    for (int b = 0; b < kSelBins; ++b) hist[warp][b][lane] = 0;
+    for_each_chunk(g, pc, lane, stage, [&](int, int cnt) {
+      for (int m = 0; m < cnt; ++m) {
+        const float4 c = my_tile[m];
+        const float d2 = d2_rule(c.x, c.y, c.z, qx, qy, qz);
+        if (d2 <= r2) {
+          const unsigned u = __float_as_uint(d2);
+          if ((u & mask) == prefix) hist[warp][(u >> shift) & (kSelBins - 1)][lane]++;
+        }
+      }
+    });
+    if (shift == a.first_shift) {  // first pass also yields k
+      int k = 0;
+      for (int b = 0; b < kSelBins; ++b) k += hist[warp][b][lane];
+      if (k <= a.max_nn) need = false;
+    }
+    if (need) {
+      int cum = 0, digit = kSelBins - 1;
+      for (int b = 0; b < kSelBins; ++b) {
+        const int c = hist[warp][b][lane];
+        if (cum + c >= target) {
+          digit = b;
+          break;
+        }
+        cum += c;
+      }
+      target -= cum;
+      prefix |= (unsigned)digit << shift;
+      mask |= (unsigned)(kSelBins - 1) << shift;
+    }
+    if (!__any_sync(kFull, need)) break;
+  }
+  // tie-break on the input index among candidates with d2 == d2*: the target-th smallest
+  const float dstar = __uint_as_float(prefix);
+  int cur = -1;
+  const int rounds = __reduce_max_sync(kFull, need ? target : 0);
+  for (int t = 0; t < rounds; ++t) {
+    int best = INT_MAX;
+    for_each_chunk(g, pc, lane, stage, [&](int base, int cnt) {
+      for (int m = 0; m < cnt; ++m) {
+        const float4 c = my_tile[m];
+        const float d2 = d2_rule(c.x, c.y, c.z, qx, qy, qz);
+        if (d2 == dstar && d2 <= r2) {
+          const int id = g.perm[base + m];
+          if (id > cur && id < best) best = id;
+        }
+      }
+    });
+    if (need && t < target) cur = best;
+  }
+  if (pc.active) {
+    a.thr_d2[pc.qi] = need ? dstar : INFINITY;
+    a.thr_idx[pc.qi] = need ? cur : INT_MAX;
+  }
+}
+
+__global__ void inverse_perm_kernel(const int* __restrict__ perm, int n, int* __restrict__ inv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[perm[i]] = i;
+}
+
+struct DbgArgs {
+  GridView g;
+  const float* xyz;
+  int stride;
+  const int* domoff;
+  int n_domains;
+  int q0, q1;
+  float r2;
+  const float* thr_d2;  // sorted order, may be null
+  const int* thr_idx;
+  const int* inv_perm;
+  const long long* offsets;  // null in the counting pass
+  int* counts;
+  int* idx;
+  float* d2out;
+};
+
+__global__ void __launch_bounds__(128) neighbors_debug_kernel(const DbgArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = a.q0 + t;
+  if (q >= a.q1) return;
+  const float* p = a.xyz + (size_t)q * a.stride;
+  const float qx = p[0], qy = p[1], qz = p[2];
+  int count = 0;
+  if (isfinite(qx) && isfinite(qy) && isfinite(qz)) {
+    int d = 0;
+    if (a.n_domains > 1) {
+      int lo = 0, hi = a.n_domains;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (a.domoff[mid] <= q) lo = mid; else hi = mid;
+      }
+      d = lo;
+    }
+    const Domain dm = a.g.domains[d];
+    const int cy = cell_coord(qy, dm.oy, a.g.inv_cell, dm.ny), cz = cell_coord(qz, dm.oz, a.g.inv_cell, dm.nz);
+    const int cx = xfine_coord(qx, dm.ox, a.g.inv_cell, dm.nx, dm.xshift) >> dm.xshift;
+    const int cxlo = max(cx - 1, 0), cxhi = min(cx + 1, dm.nx - 1);
+    float td2 = INFINITY;
+    int tidx = INT_MAX;
+    if (a.thr_d2) {
+      const int s = a.inv_perm[q];
+      td2 = a.thr_d2[s];
+      tidx = a.thr_idx[s];
+    }
+    const long long off = a.offsets ? a.offsets[t] : 0;
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1); ++z)
+      for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1); ++y) {
+        const long long c = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
+        const int b = a.g.cell_start[c + cxlo], e = a.g.cell_start[c + cxhi + 1];
+        for (int j = b; j < e; ++j) {
+          const float4 cp = a.g.pos[j];
+          const float d2 = d2_rule(cp.x, cp.y, cp.z, qx, qy, qz);
+          if (d2 <= a.r2) {
+            const int id = a.g.perm[j];
+            if (d2 < td2 || (d2 == td2 && id <= tidx)) {
+              if (a.offsets) {
+                a.idx[off + count] = id;
+                a.d2out[off + count] = d2;
+              }
+              ++count;
+            }
+          }
+        }
+      }
+  }
+  if (!a.offsets) a.counts[t] = count;
+}
+
+}  // namespace
+
+int run_thresholds(cab_ctx* ctx, float r, int max_nn) {
+  const int n = (int)ctx->n;
+  cudaStream_t st = ctx->stream;
+  if (int rc = reserve(ctx, ctx->b_thr_d2, (size_t)std::max(n, 1) * sizeof(float))) return rc;
+  if (int rc = reserve(ctx, ctx->b_thr_idx, (size_t)std::max(n, 1) * sizeof(int))) return rc;
+  ThrArgs a{};
+  a.g = grid_view(ctx);
+  packet_range(ctx, &a.p0, &a.p1);
+  a.r = r;
+  a.r2 = r * r;
+  a.max_nn = max_nn;
+  uint32_t bits;
+  std::memcpy(&bits, &a.r2, 4);
+  a.first_shift = (bits >> 30) ? 30 : 24;
+  a.thr_d2 = (float*)ctx->b_thr_d2.p;
+  a.thr_idx = (int*)ctx->b_thr_idx.p;
+  const int np = a.p1 - a.p0;
+  if (np > 0) {
+    threshold_kernel<<<(np + kSelWarps - 1) / kSelWarps, kSelWarps * kWarp, 0, st>>>(a);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  return CAB_OK;
+}
+
+int64_t run_neighbors_debug(cab_ctx* ctx, float r, int max_nn, int64_t q0, int64_t q1, int64_t* offsets, int32_t* idx,
+                            float* d2, int64_t cap) {
+  if (!ctx->have_grid) return fail(ctx, CAB_ERR_STATE, "cab_neighbors_debug: build the grid first");
+  if (q0 < 0 || q1 < q0 || q1 > ctx->n) return fail(ctx, CAB_ERR_ARG, "cab_neighbors_debug: bad query range");
+  if (!offsets) return fail(ctx, CAB_ERR_ARG, "cab_neighbors_debug: offsets is NULL");
+  if (!(r > 0.f) || r > ctx->cell * 1.0000001f)
+    return fail(ctx, CAB_ERR_ARG, "cab_neighbors_debug: radius %g exceeds the grid cell %g", (double)r, (double)ctx->cell);
+  const int nq = (int)(q1 - q0);
+  const int n = (int)ctx->n;
+  cudaStream_t st = ctx->stream;
+  offsets[0] = 0;
+  if (nq == 0) return 0;
+  DbgArgs a{};
+  a.g = grid_view(ctx);
+  a.xyz = ctx->xyz_in;
+  a.stride = ctx->stride;
+  a.domoff = (const int*)ctx->b_domoff.p;
+  a.n_domains = ctx->n_domains;
+  a.q0 = (int)q0;
+  a.q1 = (int)q1;
+  a.r2 = r * r;
+  DevBuf& scratch = ctx->b_out4;  // reuse: counts (nq ints) + offsets (nq+1 int64)
+  const size_t off_bytes = (size_t)(nq + 1) * 8, cnt_bytes = (size_t)nq * 4;
+  if (int rc = reserve(ctx, scratch, off_bytes + cnt_bytes + 64)) return rc;
+  long long* d_off = (long long*)scratch.p;
+  int* d_cnt = (int*)((char*)scratch.p + off_bytes);
+  if (max_nn > 0) {
+    int save_r = ctx->shard_rank, save_w = ctx->shard_world;
+    ctx->shard_rank = 0;
+    ctx->shard_world = 1;  // thresholds for every query
+    int rc = run_thresholds(ctx, r, max_nn);
+    ctx->shard_rank = save_r;
+    ctx->shard_world = save_w;
+    if (rc) return rc;
+    if (int rc2 = reserve(ctx, ctx->b_out1a, (size_t)n * 4)) return rc2;
+    inverse_perm_kernel<<<(n + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, n, (int*)ctx->b_out1a.p);
+    CAB_LAUNCH_CHECK(ctx);
+    a.thr_d2 = (const float*)ctx->b_thr_d2.p;
+    a.thr_idx = (const int*)ctx->b_thr_idx.p;
+    a.inv_perm = (const int*)ctx->b_out1a.p;
+  }
+  a.counts = d_cnt;
+  neighbors_debug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(a);
+  CAB_LAUNCH_CHECK(ctx);
+  std::vector<int> counts(nq);
+  CAB_CUDA(ctx, cudaMemcpyAsync(counts.data(), d_cnt, cnt_bytes, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  for (int i = 0; i < nq; ++i) offsets[i + 1] = offsets[i] + counts[i];
+  const int64_t total = offsets[nq];
+  if (!idx || !d2 || total > cap) return total;
+  if (total == 0) return 0;
+  if (int rc = reserve(ctx, ctx->b_out1b, (size_t)total * 8)) return rc;
+  CAB_CUDA(ctx, cudaMemcpyAsync(d_off, offsets, off_bytes, cudaMemcpyHostToDevice, st));
+  a.offsets = d_off;
+  a.idx = (int*)ctx->b_out1b.p;
+  a.d2out = (float*)ctx->b_out1b.p + total;
+  neighbors_debug_kernel<<<(nq + 127) / 128, 128, 0, st>>>(a);
+  CAB_LAUNCH_CHECK(ctx);
+  CAB_CUDA(ctx, cudaMemcpyAsync(idx, a.idx, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaMemcpyAsync(d2, a.d2out, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  return total;
+}
+
+}  // namespace cab

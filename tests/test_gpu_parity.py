@@ -1,0 +1,260 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on
+the same seeded inputs.  Bit-exact for neighbour sets, counts, voxel keys, labels and histograms;
+normals within 1e-4 rad (sign-insensitive); RSD radii within 1e-4 relative."""
+import numpy as np
+import pytest
+
+from mapping_private_b200 import cab, synth
+
+pytestmark = pytest.mark.gpu
+
+NORMAL_TOL_RAD = 1e-4
+RADIUS_TOL_REL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cab.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx_exact():
+    c = cab.Context(0, exact=True)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def c1():
+    return synth.tabletop(100_000)
+
+
+def _canon(off, idx, d2):
+    """Sort every query's list by (d2, idx)."""
+    q = np.repeat(np.arange(len(off) - 1), np.diff(off))
+    order = np.lexsort((idx, d2, q))
+    return idx[order], d2[order]
+
+
+def _angle(a, b):
+    """sin of the angle between two unit-vector arrays, sign-insensitive."""
+    return np.linalg.norm(np.cross(a.astype(np.float64), b.astype(np.float64)), axis=1)
+
+
+@pytest.mark.parametrize("max_nn", [0, 75])
+def test_neighbor_sets_bit_exact_c1(ctx, oracle, c1, max_nn):
+    r = 0.02
+    ctx.upload(c1)
+    ctx.build_grid(r)
+    n = c1.shape[0]
+    q0, q1 = (0, n) if max_nn == 0 else (0, 30_000)
+    off, idx, d2 = ctx.neighbors(r, q0, q1, max_nn=max_nn)
+    ooff, oidx, od2 = oracle.radius_search(c1, c1[q0:q1], r, max_nn=max_nn)
+    assert np.array_equal(off, ooff)
+    gi, gd = _canon(off, idx, d2)
+    assert np.array_equal(gi, oidx)
+    assert np.array_equal(gd.view(np.uint32), od2.view(np.uint32))
+
+
+def test_neighbor_sets_radius_boundary(ctx, oracle):
+    # points exactly at distance r (d2 == r2 in fp32) are neighbours; one ulp beyond is not
+    r = np.float32(0.0625)
+    rng = np.random.default_rng(7)
+    base = synth.quantize(rng.uniform(0.2, 0.4, size=(2000, 3)))
+    extra = []
+    for p in base[:200]:
+        extra.append(p + np.array([r, 0, 0], np.float32))
+        extra.append(p + np.array([0, np.nextafter(r, np.float32(1)), 0], np.float32))
+        extra.append(p - np.array([0, 0, r], np.float32))
+    pts = np.concatenate([base, np.array(extra, np.float32)]).astype(np.float32)
+    ctx.upload(pts)
+    ctx.build_grid(float(r))
+    off, idx, d2 = ctx.neighbors(float(r), 0, pts.shape[0])
+    ooff, oidx, od2 = oracle.radius_search(pts, pts, float(r))
+    assert np.array_equal(off, ooff)
+    gi, gd = _canon(off, idx, d2)
+    assert np.array_equal(gi, oidx) and np.array_equal(gd, od2)
+    assert np.any(gd == r * r)
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_normals_parity_c1(ctx, ctx_exact, oracle, c1, exact):
+    c = ctx_exact if exact else ctx
+    r = 0.02
+    c.upload(c1)
+    c.build_grid(r)
+    n4 = c.normals(r)
+    o4, ok = oracle.normals(c1, r)
+    prof = c.profile()
+    assert prof["neighbour_sum"] == int(ok.sum())  # neighbour counts are bit-exact
+    nan_g, nan_o = np.isnan(n4[:, 0]), np.isnan(o4[:, 0])
+    assert np.array_equal(nan_g, nan_o)
+    good = ~nan_o
+    ang = _angle(n4[good, :3], o4[good, :3])
+    tol = 2e-6 if exact else NORMAL_TOL_RAD
+    bad = ang > tol
+    # ill-conditioned neighbourhoods (two smallest eigenvalues nearly equal) are listed, not hidden
+    print(f"normals exact={exact}: max sin(angle) {ang.max():.3e}, > tol: {bad.sum()} of {good.sum()}")
+    assert bad.mean() < 1e-4
+    assert np.allclose(np.linalg.norm(n4[good, :3], axis=1), 1.0, atol=1e-5)
+    assert np.max(np.abs(n4[good, 3] - o4[good, 3])) < (1e-6 if exact else 2e-5)
+    # orientation: towards the viewpoint unless the oracle's own decision margin is tiny
+    dots = np.sum(n4[good, :3] * o4[good, :3], axis=1)
+    margin = np.abs(np.sum(o4[good, :3] * (-c1[good]), axis=1))
+    assert np.all((dots > 0) | (margin < 1e-4))
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("max_nn,ndiv,plane,flags", [(0, 10, 0.1, 0), (75, 10, 0.1, 0), (0, 5, 0.2, 2 | 4), (0, 7, 0.15, 4)])
+def test_rsd_parity_given_normals(ctx, ctx_exact, oracle, exact, max_nn, ndiv, plane, flags):
+    c = ctx_exact if exact else ctx
+    pts = synth.tabletop(40_000, noise_sigma=0.0004)
+    r = 0.03
+    o4, _ = oracle.normals(pts, r)
+    c.upload(pts)
+    c.build_grid(r)
+    c.set_normals(o4)
+    rmin, rmax = c.rsd(r, max_nn=max_nn, ndiv=ndiv, plane_radius=plane, flags=flags)
+    omin, omax, _ = oracle.rsd(pts, o4, r, max_nn=max_nn, ndiv=ndiv, plane_radius=plane, flags=flags)
+    tol = 1e-6 if exact else RADIUS_TOL_REL
+    assert np.max(np.abs(rmin - omin) / omin) <= tol
+    assert np.max(np.abs(rmax - omax) / omax) <= tol
+    if exact:
+        assert np.mean(rmin == omin) > 0.999 and np.mean(rmax == omax) > 0.999
+
+
+def test_pipeline_c1(ctx, oracle, c1):
+    """normals -> RSD entirely on the GPU (fast mode) against the oracle pipeline."""
+    r = 0.02
+    ctx.upload(c1)
+    ctx.build_grid(r)
+    n4 = ctx.normals(r)
+    rmin, rmax = ctx.rsd(r)
+    o4, _ = oracle.normals(c1, r)
+    omin, omax, _ = oracle.rsd(c1, o4, r)
+    emin = np.abs(rmin - omin) / omin
+    emax = np.abs(rmax - omax) / omax
+    print(f"pipeline: max rel err r_min {emin.max():.3e} r_max {emax.max():.3e}; "
+          f">1e-4: {(emin > 1e-4).sum()} / {(emax > 1e-4).sum()}")
+    # fp32 normals feed an ill-conditioned 1/angle^2 fit on near-planar points: bound the tail
+    assert np.mean(emin > RADIUS_TOL_REL) < 2e-3 and np.mean(emax > RADIUS_TOL_REL) < 2e-3
+    assert np.median(emin) < 1e-6 and np.median(emax) < 1e-6
+
+
+def test_pipeline_exact_mode(ctx_exact, oracle):
+    pts = synth.tabletop(30_000, noise_sigma=0.0003)
+    r = 0.02
+    ctx_exact.upload(pts)
+    ctx_exact.build_grid(r)
+    n4 = ctx_exact.normals(r)
+    rmin, rmax = ctx_exact.rsd(r)
+    o4, _ = oracle.normals(pts, r)
+    omin, omax, _ = oracle.rsd(pts, o4, r)
+    assert np.mean(np.all(n4 == o4, axis=1)) > 0.98
+    assert np.max(np.abs(rmin - omin) / omin) < RADIUS_TOL_REL
+    assert np.max(np.abs(rmax - omax) / omax) < RADIUS_TOL_REL
+
+
+def test_edge_cases(ctx, oracle):
+    # empty cloud
+    ctx.upload(np.zeros((0, 3), np.float32))
+    ctx.build_grid(0.02)
+    assert ctx.normals(0.02).shape == (0, 4)
+    rmin, rmax = ctx.rsd(0.02)
+    assert rmin.size == 0
+    # single point, duplicates, NaN / inf points
+    pts = np.array([[0, 0, 0], [0, 0, 0], [0.001, 0, 0], [0, 0.001, 0], [np.nan, 0, 0], [0.5, 0.5, 0.5],
+                    [np.inf, 0, 0], [0.001, 0.001, 0.0005]], np.float32)
+    ctx.upload(pts)
+    ctx.build_grid(0.02)
+    n4 = ctx.normals(0.02)
+    o4, ok = oracle.normals(pts, 0.02)
+    assert np.array_equal(np.isnan(n4[:, 0]), np.isnan(o4[:, 0]))
+    off, idx, d2 = ctx.neighbors(0.02, 0, pts.shape[0])
+    ooff, oidx, od2 = oracle.radius_search(pts, pts, 0.02)
+    assert np.array_equal(off, ooff)
+    gi, gd = _canon(off, idx, d2)
+    assert np.array_equal(gi, oidx)
+    ctx.set_normals(np.nan_to_num(o4[:, :3], nan=0.5))
+    rmin, rmax = ctx.rsd(0.02)
+    omin, omax, _ = oracle.rsd(pts, np.nan_to_num(o4[:, :3], nan=0.5), 0.02)
+    assert np.allclose(rmin, omin, rtol=1e-4) and np.allclose(rmax, omax, rtol=1e-4)
+    # radius larger than the grid cell is rejected, RSD without normals is rejected
+    with pytest.raises(cab.CabError):
+        ctx.normals(0.05)
+    ctx.upload(pts)
+    ctx.build_grid(0.02)
+    with pytest.raises(cab.CabError, match="missing normals"):
+        ctx.rsd(0.02)
+
+
+def test_grsd_batch_bit_exact(ctx_exact, oracle):
+    xyz, off = synth.clusters(28, 1300, 6000)
+    leaf = 0.025
+    hist = ctx_exact.grsd_batch(xyz, off, leaf, r_normals=0.02)
+    vox = ctx_exact.grsd_voxels(len(off) - 1)
+    mism = 0
+    for c in range(len(off) - 1):
+        o = oracle.grsd21(xyz[off[c]:off[c + 1]], leaf, r_normals=0.02)
+        v0, v1 = vox["offsets"][c], vox["offsets"][c + 1]
+        assert v1 - v0 == o["nvox"]
+        og = oracle.voxel_grid(xyz[off[c]:off[c + 1]], leaf)
+        assert np.array_equal(vox["centroids"][v0:v1].view(np.uint32), og["centroids"].view(np.uint32))
+        assert np.allclose(vox["r_min"][v0:v1], o["radii"][:, 0], rtol=1e-5)
+        assert np.allclose(vox["r_max"][v0:v1], o["radii"][:, 1], rtol=1e-5)
+        if not np.array_equal(vox["labels"][v0:v1], o["labels"]):
+            mism += 1
+            continue
+        assert np.array_equal(hist[c], o["hist21"])
+    assert mism == 0
+
+
+def test_grsd_batch_given_normals_and_ragged(ctx, oracle):
+    xyz, off = synth.clusters(6, 1300, 3000, seed_extra=1)
+    # add an empty cluster and a 1-point cluster
+    xyz = np.concatenate([xyz, np.array([[0.3, 0.3, 0.9]], np.float32)])
+    off = np.concatenate([off[:3], [off[3]], off[3:], [xyz.shape[0]]]).astype(np.int32)
+    nc = len(off) - 1
+    nrm = np.zeros((xyz.shape[0], 3), np.float32)
+    for c in range(nc):
+        if off[c + 1] > off[c]:
+            nrm[off[c]:off[c + 1]] = oracle.normals(xyz[off[c]:off[c + 1]], 0.02)[0][:, :3]
+    nrm = np.nan_to_num(nrm, nan=0.0)
+    hist = ctx.grsd_batch(xyz, off, 0.025, normals=nrm)
+    for c in range(nc):
+        if off[c + 1] == off[c]:
+            assert not hist[c].any()
+            continue
+        o = oracle.grsd21(xyz[off[c]:off[c + 1]], 0.025, normals_in=nrm[off[c]:off[c + 1]])
+        assert np.array_equal(hist[c], o["hist21"]), c
+
+
+def test_properties_at_full_size(ctx):
+    """C2-sized run: size-independent properties instead of an oracle comparison."""
+    pts = synth.scan(1_000_000)
+    r = 0.03
+    ctx.upload(pts)
+    ctx.build_grid(r)
+    n4 = ctx.normals(r)
+    p1 = ctx.profile()
+    rmin, rmax = ctx.rsd(r)
+    p2 = ctx.profile()
+    assert p1["neighbour_sum"] == p2["neighbour_sum"]  # both passes see the same neighbour sets
+    assert p1["n_valid"] == pts.shape[0]
+    good = ~np.isnan(n4[:, 0])
+    assert np.allclose(np.linalg.norm(n4[good, :3], axis=1), 1.0, atol=1e-5)
+    assert np.all(np.sum(n4[good, :3] * (-pts[good]), axis=1) >= -1e-4)  # oriented towards the origin
+    assert np.all(rmin <= np.float32(0.1)) and np.all(rmax <= np.float32(0.1)) and np.all(rmin > 0)
+    # idempotence and permutation invariance (lattice input: sums are exact only in exact mode,
+    # so compare within tolerance)
+    perm = np.random.default_rng(3).permutation(pts.shape[0])
+    ctx.upload(pts[perm])
+    ctx.build_grid(r)
+    n4b = ctx.normals(r)
+    rminb, rmaxb = ctx.rsd(r)
+    assert ctx.profile()["neighbour_sum"] == p1["neighbour_sum"]
+    ang = _angle(n4[perm][good[perm], :3], n4b[good[perm], :3])
+    assert np.percentile(ang, 99.9) < 1e-4
+    assert np.mean(np.abs(rminb - rmin[perm]) / rmin[perm] > 1e-4) < 2e-3
