@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: normals + RSD points/s at r = 2 cm on the 20 M-point synthetic room
+cloud (BASELINE.json config C4), query-sharded over N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference
+
+One "step" = one pass of the hot path over the cloud: grid build (replaces the kd-tree build) +
+normals + RSD.  `value` is measured with the cloud resident in HBM; `e2e` goes through the C ABI
+with pinned host buffers (H2D of the cloud, D2H of normals and radii inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "normals+RSD points/s (r=2cm)"
+UNIT = "points/s"
+RADIUS = 0.02
+NDIV = 10
+PLANE_RADIUS = 0.1
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=20_000_000, help="cloud size (default: config C4)")
+    ap.add_argument("--exact", action="store_true", help="fp64 accumulation mode")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=6_000_000)
+    return ap.parse_args()
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def slab_sample(pts, target):
+    """A contiguous x-slab of the cloud holding ~target points (keeps the surface density)."""
+    import numpy as np
+
+    if pts.shape[0] <= target:
+        return pts
+    xs = np.sort(pts[:: max(1, pts.shape[0] // 200_000), 0])
+    frac = target / pts.shape[0]
+    lo = xs[int(0.35 * len(xs))]
+    hi = xs[min(len(xs) - 1, int((0.35 + frac) * len(xs)))]
+    return np.ascontiguousarray(pts[(pts[:, 0] >= lo) & (pts[:, 0] < hi)])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_points_per_s(pts, nthreads=0):
+    """Oracle (CPU restatement) normals + RSD on the given sample, all host threads."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import pyoracle
+
+    pyoracle.build()
+    t0 = time.perf_counter()
+    n4, _ = pyoracle.normals(pts, RADIUS, nthreads=nthreads)
+    pyoracle.rsd(pts, n4, RADIUS, ndiv=NDIV, plane_radius=PLANE_RADIUS, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return pts.shape[0] / dt, dt, pyoracle.num_threads() if nthreads <= 0 else nthreads
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's algorithm on the host cores (oracle port: the reference
+    plugins need ROS/PCL/ANN, none of which exist here -- DESIGN.md "Oracle")."""
+    if rank != 0:
+        return
+    import pkgpath
+
+    pkgpath.load()
+    from mapping_private_b200 import synth
+
+    pts = synth.room(args.points)  # full cloud so that the slab has the workload's density
+    sample = slab_sample(pts, 150_000)
+    rates = []
+    cores = 1
+    for s in range(args.warmup + args.steps):
+        rate, dt, cores = cpu_points_per_s(sample)
+        if s >= args.warmup:
+            rates.append((rate, dt))
+    value = len(rates) * sample.shape[0] / sum(dt for _, dt in rates)
+    ms = 1e3 * sum(dt for _, dt in rates) / len(rates)
+    desc = f"x-slab of the room cloud, {sample.shape[0]} points per step (same density as the {args.points}-point workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4 20M-point synthetic room, normals+RSD r=2cm (bounded sample per step)", "points": args.points,
+                   "radius_m": RADIUS, "distance_div": NDIV, "plane_radius": PLANE_RADIUS, "max_nn": "unlimited"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+class _DevArray:
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and "RANK" not in os.environ:
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", "29517", str(ROOT / "bench.py")] + sys.argv[1:])
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import pkgpath
+
+    pkgpath.load()
+    from mapping_private_b200 import cab, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.points
+    pts = synth.room(n)
+    ctx = cab.Context(local_rank, exact=args.exact)
+    ctx.set_shard(rank, world)
+    d_xyz = torch.from_numpy(pts).to(dev)  # resident in HBM before the timed region
+    torch.cuda.synchronize()
+    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    ranges = None
+
+    def exchange(which, width):
+        """Concatenate the shards' results: every rank broadcasts its slice in place (NCCL/NVLink)."""
+        buf = torch.as_tensor(_DevArray(ctx.device_ptr(which), (n, width)), device=dev)
+        for g in range(world):
+            b, e = ranges[g]
+            if e > b:
+                dist.broadcast(buf[b:e], src=g)
+        torch.cuda.synchronize()
+
+    def step():
+        ctx.set_cloud_device(d_xyz.data_ptr(), n, 3)
+        ctx.build_grid(RADIUS)
+        ctx.normals(RADIUS, download=False)
+        if world > 1:
+            exchange(cab.BUF_NRM_SORTED, 4)
+        ctx.rsd(RADIUS, ndiv=NDIV, plane_radius=PLANE_RADIUS, download=False)
+        if world > 1:
+            exchange(cab.BUF_RSD_SORTED, 2)
+
+    # shard ranges are a deterministic function of the cloud; exchange them once
+    ctx.set_cloud_device(d_xyz.data_ptr(), n, 3)
+    ctx.build_grid(RADIUS)
+    if world > 1:
+        mine = ctx.shard_range()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        ranges = gathered
+    for _ in range(max(args.warmup, 3)):
+        step()
+
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.profile()["kernel_launches"]
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phases = {"build_ms": [], "normals_ms": [], "rsd_ms": []}
+    ev0.record(lib_stream)
+    for _ in range(args.steps):
+        step()
+        p = ctx.profile()
+        for k in phases:
+            phases[k].append(p[k])
+    ev1.record(lib_stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    prof = ctx.profile()
+    launches = prof["kernel_launches"] - launches0
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        ks = torch.tensor([prof["neighbour_sum"], launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(ks, op=dist.ReduceOp.SUM)
+        neighbour_sum, launches = int(ks[0].item()), int(ks[1].item())
+    else:
+        neighbour_sum = prof["neighbour_sum"]
+    ms_per_step = elapsed_ms / args.steps
+    value = n / (ms_per_step * 1e-3)
+    kbar = neighbour_sum / n
+
+    # ---- roofline of the dominant kernel (rsd_kernel), SURVEY section 8(d) accounting -------
+    peak, peak_src = hbm_peak()
+    rsd_ms = statistics.mean(phases["rsd_ms"])
+    nrm_ms = statistics.mean(phases["normals_ms"])
+    build_ms = statistics.mean(phases["build_ms"])
+    shard_pts = n / world
+    shard_k = prof["neighbour_sum"]  # this rank's queries
+    rsd_bytes = 32.0 * shard_k + 40.0 * shard_pts
+    nrm_bytes = 16.0 * shard_k + 32.0 * shard_pts
+    achieved = rsd_bytes / (rsd_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists():
+        try:
+            traffic = json.loads(tpath.read_text()).get("rsd_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    step_bytes = n * (48.0 * kbar + 72.0 + 120.0)
+    roofline = {"bound": "hbm", "kernel": "rsd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": rsd_bytes, "kernel_ms": rsd_ms,
+                "normals_kernel": {"achieved": nrm_bytes / (nrm_ms * 1e-3) / 1e9, "kernel_ms": nrm_ms,
+                                   "frac": nrm_bytes / (nrm_ms * 1e-3) / 1e9 / peak},
+                "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                               "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}}
+
+    # ---- end to end through the C ABI with pinned host buffers ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_xyz = torch.from_numpy(pts).pin_memory()
+        h_n4 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+        h_rmin = torch.empty(n, dtype=torch.float32).pin_memory()
+        h_rmax = torch.empty(n, dtype=torch.float32).pin_memory()
+        L = cab.lib()
+        import ctypes as C
+
+        def fp(t):
+            return C.cast(t.data_ptr(), C.POINTER(C.c_float))
+
+        def e2e_step():
+            ctx._check(L.cab_upload_cloud(ctx._h, fp(h_xyz), C.c_int64(n), C.c_int32(3)), "cab_upload_cloud")
+            ctx.n = n
+            ctx.build_grid(RADIUS)
+            ctx.normals(RADIUS, download=False)
+            if world > 1:
+                exchange(cab.BUF_NRM_SORTED, 4)
+            ctx.rsd(RADIUS, ndiv=NDIV, plane_radius=PLANE_RADIUS, download=False)
+            if world > 1:
+                exchange(cab.BUF_RSD_SORTED, 2)
+            ctx._check(L.cab_download(ctx._h, fp(h_n4), fp(h_rmin), fp(h_rmax)), "cab_download")
+
+        e2e_steps = max(2, min(args.steps, 5))
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": n / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(n * 12),
+               "d2h_bytes_per_step": int(n * 24), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+               "path": "cab_upload_cloud -> cab_build_grid -> cab_normals -> cab_rsd -> cab_download, pinned host buffers"}
+
+    # ---- CPU baseline (oracle port) on rank 0 at N = 1 ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = slab_sample(pts, args.cpu_sample)
+        rate, dt, cores = cpu_points_per_s(sample)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+               "sample": f"x-slab of the room cloud, {sample.shape[0]} points (same density), oracle normals+RSD streaming mode"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if not args.exact else "f64", "data": "synthetic",
+            "config": {"workload": "C4 20M-point synthetic room, normals+RSD r=2cm, query-sharded", "points": n,
+                       "radius_m": RADIUS, "distance_div": NDIV, "plane_radius": PLANE_RADIUS, "max_nn": "unlimited",
+                       "mean_neighbours": kbar, "candidates_tested_per_query": prof["candidate_sum"] / max(1.0, n / world), "l2": "inputs_larger_than_l2 (pos+normals 640 MB vs 126 MB L2)",
+                       "parallelism": f"query-shard x{world}, grid replicated, NCCL broadcast of shard results",
+                       "mode": "exact-fp64" if args.exact else "fast-fp32"},
+            "phases_ms": {"build": build_ms, "normals": nrm_ms, "rsd": rsd_ms},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

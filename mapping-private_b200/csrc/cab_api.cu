@@ -60,6 +60,17 @@ int reserve_pinned(cab_ctx* ctx, size_t bytes) {
   return CAB_OK;
 }
 
+void read_stats(cab_ctx* ctx) {
+  const unsigned long long* h = (const unsigned long long*)ctx->h_pin;
+  unsigned long long ks = 0, cs = 0;
+  for (int i = 0; i < kStatSlots; ++i) {
+    ks += h[2 * i];
+    cs += h[2 * i + 1];
+  }
+  ctx->tm.neighbour_sum = (int64_t)ks;
+  ctx->tm.candidate_sum = (int64_t)cs;
+}
+
 namespace {
 
 __global__ void __launch_bounds__(256) gather_normals_kernel(const float* __restrict__ nx, const float* __restrict__ ny,

@@ -17,6 +17,8 @@ namespace cab {
 constexpr int kWarp = 32;
 constexpr int kXBits = 20;            // sub-cell x field of the sort key
 constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kStatSlots = 64;         // spread counters (avoids same-address atomic serialisation)
+constexpr size_t kStatBytes = kStatSlots * 2 * sizeof(unsigned long long);
 
 // One independent neighbourhood domain: the whole cloud, or one segmented cluster.
 struct Domain {
@@ -122,6 +124,7 @@ int reserve(cab_ctx* ctx, DevBuf& b, size_t bytes);
 int reserve_pinned(cab_ctx* ctx, size_t bytes);
 GridView grid_view(const cab_ctx* ctx);
 void packet_range(const cab_ctx* ctx, int* p0, int* p1);
+void read_stats(cab_ctx* ctx);  // sums the kStatSlots counters staged in ctx->h_pin into ctx->tm
 
 #define CAB_CUDA(ctx, call)                                                                  \
   do {                                                                                       \

@@ -57,111 +57,159 @@ struct NormalsArgs {
   int* kcount;              // sorted order
   const float* thr_d2;      // optional max_nn thresholds (sorted order), may be null
   const int* thr_idx;
-  unsigned long long* stats;  // [0] neighbour sum, [1] candidate sum
+  unsigned long long* stats;  // kStatSlots x {neighbour sum, candidate sum}
 };
 
-template <bool kExact>
+// fp32 accumulate of one candidate, predicated on d2 <= r2 (explicit predication: the compiler's
+// branchy version costs three more issue slots per candidate).
+__device__ __forceinline__ void accum_pred(float d2, float r2, float dx, float dy, float dz, float& s1x, float& s1y,
+                                           float& s1z, float& sxx, float& sxy, float& sxz, float& syy, float& syz,
+                                           float& szz, int& k) {
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.le.f32 p, %10, %11;\n\t"
+      "@p add.f32 %0, %0, %12;\n\t"
+      "@p add.f32 %1, %1, %13;\n\t"
+      "@p add.f32 %2, %2, %14;\n\t"
+      "@p fma.rn.f32 %3, %12, %12, %3;\n\t"
+      "@p fma.rn.f32 %4, %12, %13, %4;\n\t"
+      "@p fma.rn.f32 %5, %12, %14, %5;\n\t"
+      "@p fma.rn.f32 %6, %13, %13, %6;\n\t"
+      "@p fma.rn.f32 %7, %13, %14, %7;\n\t"
+      "@p fma.rn.f32 %8, %14, %14, %8;\n\t"
+      "@p add.s32 %9, %9, 1;\n\t}"
+      : "+f"(s1x), "+f"(s1y), "+f"(s1z), "+f"(sxx), "+f"(sxy), "+f"(sxz), "+f"(syy), "+f"(syz), "+f"(szz), "+r"(k)
+      : "f"(d2), "f"(r2), "f"(dx), "f"(dy), "f"(dz));
+}
+
+template <bool kExact, bool kUseThr>
 __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const NormalsArgs a) {
-  __shared__ float4 tile[kWarpsPerBlock][kWarp];
-  __shared__ unsigned long long blk_stats[2];
+  __shared__ ChunkTile tiles[kWarpsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pid = a.p0 + blockIdx.x * kWarpsPerBlock + warp;
-  if (threadIdx.x < 2) blk_stats[threadIdx.x] = 0;
-  __syncthreads();
-  if (pid < a.p1) {
-    const GridView& g = a.g;
-    const PacketCtx pc = load_packet(g, pid, lane, a.r);
-    const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
-    const float r2 = a.r2;
-    // optional max_nn truncation: accept (d2, input idx) <= (thr_d2, thr_idx)
-    const bool use_thr = a.thr_d2 != nullptr;
-    float td2 = 0.f;
-    int tidx = 0;
-    if (use_thr) {
+  if (pid >= a.p1) return;
+  const GridView& g = a.g;
+  const PacketCtx pc = load_packet(g, pid, lane, a.r);
+  const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
+  const float r2 = a.r2;
+  ChunkTile* tile = &tiles[warp];
+  using Acc = typename std::conditional<kExact, double, float>::type;
+  Acc s1x = 0, s1y = 0, s1z = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+  int k = 0;
+  int tested;
+  if constexpr (!kExact && !kUseThr) {
+    // fast path: packed fp32x2 distance test, predicated fp32 accumulation
+    const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
+    tested = for_each_chunk(g, pc, lane, tile, [&](int, int cnt, const float4&, bool) {
+      const float4* tx = reinterpret_cast<const float4*>(tile->x);
+      const float4* ty = reinterpret_cast<const float4*>(tile->y);
+      const float4* tz = reinterpret_cast<const float4*>(tile->z);
+      const int groups = (cnt + 3) >> 2;
+#pragma unroll 2
+      for (int g4 = 0; g4 < groups; ++g4) {
+        const float4 X = tx[g4], Y = ty[g4], Z = tz[g4];
+        f32x2 dx = sub2(pack2(X.x, X.y), qx2), dy = sub2(pack2(Y.x, Y.y), qy2), dz = sub2(pack2(Z.x, Z.y), qz2);
+        f32x2 d2 = add2(add2(sq2(dx), sq2(dy)), sq2(dz));
+        float d2a, d2b, xa, xb, ya, yb, za, zb;
+        unpack2(d2, d2a, d2b); unpack2(dx, xa, xb); unpack2(dy, ya, yb); unpack2(dz, za, zb);
+        accum_pred(d2a, r2, xa, ya, za, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, k);
+        accum_pred(d2b, r2, xb, yb, zb, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, k);
+        dx = sub2(pack2(X.z, X.w), qx2); dy = sub2(pack2(Y.z, Y.w), qy2); dz = sub2(pack2(Z.z, Z.w), qz2);
+        d2 = add2(add2(sq2(dx), sq2(dy)), sq2(dz));
+        unpack2(d2, d2a, d2b); unpack2(dx, xa, xb); unpack2(dy, ya, yb); unpack2(dz, za, zb);
+        accum_pred(d2a, r2, xa, ya, za, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, k);
+        accum_pred(d2b, r2, xb, yb, zb, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, k);
+      }
+    });
+  } else {
+    // exact / truncated path: hit mask per chunk, then only the hits are visited; the candidate is
+    // fetched from the lane that staged it (warp shuffle, no shared-memory bank conflicts)
+    float td2 = INFINITY;
+    int tidx = INT_MAX;
+    if (kUseThr) {
       td2 = a.thr_d2[pc.qi];
       tidx = a.thr_idx[pc.qi];
     }
-    using Acc = typename std::conditional<kExact, double, float>::type;
-    Acc s1x = 0, s1y = 0, s1z = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-    int k = 0;
-    float4* my_tile = tile[warp];
-    const int tested = for_each_chunk(
-        g, pc, lane, [&](int, bool, const float4& c) { my_tile[lane] = c; },
-        [&](int base, int cnt) {
-          const int cnt4 = (cnt + 3) & ~3;
-#pragma unroll 4
-          for (int m = 0; m < cnt4; ++m) {
-            const float4 c = my_tile[m];
-            const float dx = __fsub_rn(c.x, qx), dy = __fsub_rn(c.y, qy), dz = __fsub_rn(c.z, qz);
+    tested = for_each_chunk(g, pc, lane, tile, [&](int base, int, const float4& c, bool) {
+      unsigned mask = chunk_hit_mask(tile, qx, qy, qz, r2);
+      const int iters = __reduce_max_sync(kFull, __popc(mask));
+      for (int it = 0; it < iters; ++it) {
+        const bool has = mask != 0;
+        const int m = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float cx = __shfl_sync(kFull, c.x, m), cy = __shfl_sync(kFull, c.y, m), cz = __shfl_sync(kFull, c.z, m);
+        if (has) {
+          const float dx = __fsub_rn(cx, qx), dy = __fsub_rn(cy, qy), dz = __fsub_rn(cz, qz);
+          bool hit = true;
+          if (kUseThr) {
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            bool hit = d2 <= r2;
-            if (use_thr && hit) hit = d2 < td2 || (d2 == td2 && g.perm[base + m] <= tidx);
-            if (hit) {
-              if (kExact) {
-                const double ex = dx, ey = dy, ez = dz;
-                s1x += ex; s1y += ey; s1z += ez;
-                sxx = __fma_rn(ex, ex, sxx); sxy = __fma_rn(ex, ey, sxy); sxz = __fma_rn(ex, ez, sxz);
-                syy = __fma_rn(ey, ey, syy); syz = __fma_rn(ey, ez, syz); szz = __fma_rn(ez, ez, szz);
-              } else {
-                s1x += dx; s1y += dy; s1z += dz;
-                sxx = fmaf(dx, dx, sxx); sxy = fmaf(dx, dy, sxy); sxz = fmaf(dx, dz, sxz);
-                syy = fmaf(dy, dy, syy); syz = fmaf(dy, dz, syz); szz = fmaf(dz, dz, szz);
-              }
-              ++k;
-            }
+            hit = d2 < td2 || (d2 == td2 && g.perm[base + m] <= tidx);
           }
-        });
-
-    // ---- finalise: covariance about the centroid (fp64), eigen-solve ---------------------
-    float4 out;
-    if (k < 3) {
-      const float nan = __int_as_float(0x7fc00000);
-      out = make_float4(nan, nan, nan, nan);
-    } else {
-      // written with explicit roundings so the CPU oracle's plain expressions give the same bits
-      const double inv = __drcp_rn((double)k);
-      const double mx = __dmul_rn((double)s1x, inv), my = __dmul_rn((double)s1y, inv), mz = __dmul_rn((double)s1z, inv);
-      const double cxx = __dsub_rn(__dmul_rn((double)sxx, inv), __dmul_rn(mx, mx));
-      const double cxy = __dsub_rn(__dmul_rn((double)sxy, inv), __dmul_rn(mx, my));
-      const double cxz = __dsub_rn(__dmul_rn((double)sxz, inv), __dmul_rn(mx, mz));
-      const double cyy = __dsub_rn(__dmul_rn((double)syy, inv), __dmul_rn(my, my));
-      const double cyz = __dsub_rn(__dmul_rn((double)syz, inv), __dmul_rn(my, mz));
-      const double czz = __dsub_rn(__dmul_rn((double)szz, inv), __dmul_rn(mz, mz));
-      const double tr = cxx + cyy + czz;
-      double lam, nx, ny, nz;
-      if (kExact) {
-        smallest_eigen<double, 12>(cxx, cxy, cxz, cyy, cyz, czz, lam, nx, ny, nz);
-        const double len = sqrt(nx * nx + ny * ny + nz * nz);
-        nx /= len; ny /= len; nz /= len;
-        lam = (tr != 0.0) ? fabs(lam / tr) : 0.0;
-      } else {
-        const float sc = (tr > 0.0) ? (float)(1.0 / tr) : 1.f;
-        float fl, fx, fy, fz;
-        smallest_eigen<float, 6>((float)cxx * sc, (float)cxy * sc, (float)cxz * sc, (float)cyy * sc, (float)cyz * sc,
-                                 (float)czz * sc, fl, fx, fy, fz);
-        const float il = rsqrtf(fx * fx + fy * fy + fz * fz);
-        nx = fx * il; ny = fy * il; nz = fz * il;
-        lam = (tr > 0.0) ? fabsf(fl) : 0.f;
+          if (hit) {
+            if constexpr (kExact) {
+              const double ex = dx, ey = dy, ez = dz;
+              s1x += ex; s1y += ey; s1z += ez;
+              sxx = __fma_rn(ex, ex, sxx); sxy = __fma_rn(ex, ey, sxy); sxz = __fma_rn(ex, ez, sxz);
+              syy = __fma_rn(ey, ey, syy); syz = __fma_rn(ey, ez, syz); szz = __fma_rn(ez, ez, szz);
+            } else {
+              s1x += dx; s1y += dy; s1z += dz;
+              sxx = fmaf(dx, dx, sxx); sxy = fmaf(dx, dy, sxy); sxz = fmaf(dx, dz, sxz);
+              syy = fmaf(dy, dy, syy); syz = fmaf(dy, dz, syz); szz = fmaf(dz, dz, szz);
+            }
+            ++k;
+          }
+        }
       }
-      // flipNormalTowardsViewpoint: n.(vp - p) >= 0
-      const double dot = nx * ((double)a.vpx - qx) + ny * ((double)a.vpy - qy) + nz * ((double)a.vpz - qz);
-      if (dot < 0) { nx = -nx; ny = -ny; nz = -nz; }
-      out = make_float4((float)nx, (float)ny, (float)nz, (float)lam);
-    }
-    if (pc.active) {
-      a.nrm[pc.qi] = out;
-      a.kcount[pc.qi] = k;
-    }
-    unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) ks += __shfl_xor_sync(kFull, ks, o);
-    if (lane == 0) {
-      atomicAdd(&blk_stats[0], ks);
-      atomicAdd(&blk_stats[1], (unsigned long long)tested * (unsigned)pc.count);
-    }
+    });
   }
-  __syncthreads();
-  if (threadIdx.x < 2 && blk_stats[threadIdx.x]) atomicAdd(a.stats + threadIdx.x, blk_stats[threadIdx.x]);
+
+  // ---- finalise: covariance about the centroid (fp64), eigen-solve ---------------------
+  float4 out;
+  if (k < 3) {
+    const float nan = __int_as_float(0x7fc00000);
+    out = make_float4(nan, nan, nan, nan);
+  } else {
+    // written with explicit roundings so the CPU oracle's plain expressions give the same bits
+    const double inv = __drcp_rn((double)k);
+    const double mx = __dmul_rn((double)s1x, inv), my = __dmul_rn((double)s1y, inv), mz = __dmul_rn((double)s1z, inv);
+    const double cxx = __dsub_rn(__dmul_rn((double)sxx, inv), __dmul_rn(mx, mx));
+    const double cxy = __dsub_rn(__dmul_rn((double)sxy, inv), __dmul_rn(mx, my));
+    const double cxz = __dsub_rn(__dmul_rn((double)sxz, inv), __dmul_rn(mx, mz));
+    const double cyy = __dsub_rn(__dmul_rn((double)syy, inv), __dmul_rn(my, my));
+    const double cyz = __dsub_rn(__dmul_rn((double)syz, inv), __dmul_rn(my, mz));
+    const double czz = __dsub_rn(__dmul_rn((double)szz, inv), __dmul_rn(mz, mz));
+    const double tr = cxx + cyy + czz;
+    double lam, nx, ny, nz;
+    if constexpr (kExact) {
+      smallest_eigen<double, 12>(cxx, cxy, cxz, cyy, cyz, czz, lam, nx, ny, nz);
+      const double len = sqrt(nx * nx + ny * ny + nz * nz);
+      nx /= len; ny /= len; nz /= len;
+      lam = (tr != 0.0) ? fabs(lam / tr) : 0.0;
+    } else {
+      const float sc = (tr > 0.0) ? (float)(1.0 / tr) : 1.f;
+      float fl, fx, fy, fz;
+      smallest_eigen<float, 6>((float)cxx * sc, (float)cxy * sc, (float)cxz * sc, (float)cyy * sc, (float)cyz * sc,
+                               (float)czz * sc, fl, fx, fy, fz);
+      const float il = rsqrtf(fx * fx + fy * fy + fz * fz);
+      nx = fx * il; ny = fy * il; nz = fz * il;
+      lam = (tr > 0.0) ? fabsf(fl) : 0.f;
+    }
+    // flipNormalTowardsViewpoint: n.(vp - p) >= 0
+    const double dot = nx * ((double)a.vpx - qx) + ny * ((double)a.vpy - qy) + nz * ((double)a.vpz - qz);
+    if (dot < 0) { nx = -nx; ny = -ny; nz = -nz; }
+    out = make_float4((float)nx, (float)ny, (float)nz, (float)lam);
+  }
+  if (pc.active) {
+    a.nrm[pc.qi] = out;
+    a.kcount[pc.qi] = k;
+  }
+  unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ks += __shfl_xor_sync(kFull, ks, o);
+  if (lane == 0) {
+    unsigned long long* slot = a.stats + 2 * (pid & (kStatSlots - 1));
+    atomicAdd(slot, ks);
+    atomicAdd(slot + 1, (unsigned long long)tested * (unsigned)pc.count);
+  }
 }
 
 __global__ void fill_invalid_normals(float4* nrm, int* kcount, int begin, int end) {
@@ -182,11 +230,11 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3]) {
   cudaStream_t st = ctx->stream;
   if (int rc = reserve(ctx, ctx->b_nrm, (size_t)std::max(n, 1) * sizeof(float4))) return rc;
   if (int rc = reserve(ctx, ctx->b_kcount, (size_t)std::max(n, 1) * sizeof(int))) return rc;
-  if (int rc = reserve(ctx, ctx->b_stats, 64)) return rc;
+  if (int rc = reserve(ctx, ctx->b_stats, kStatBytes)) return rc;
   const bool use_thr = max_nn > 0;
   if (use_thr)
     if (int rc = run_thresholds(ctx, r, max_nn)) return rc;
-  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, 64, st));
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, kStatBytes, st));
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
   NormalsArgs a{};
   a.g = grid_view(ctx);
@@ -204,10 +252,11 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3]) {
   const int np = a.p1 - a.p0;
   if (np > 0) {
     const unsigned blocks = (np + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (ctx->cfg.exact)
-      normals_kernel<true><<<blocks, kWarpsPerBlock * kWarp, 0, st>>>(a);
-    else
-      normals_kernel<false><<<blocks, kWarpsPerBlock * kWarp, 0, st>>>(a);
+    const dim3 blk(kWarpsPerBlock * kWarp);
+    if (ctx->cfg.exact && use_thr) normals_kernel<true, true><<<blocks, blk, 0, st>>>(a);
+    else if (ctx->cfg.exact) normals_kernel<true, false><<<blocks, blk, 0, st>>>(a);
+    else if (use_thr) normals_kernel<false, true><<<blocks, blk, 0, st>>>(a);
+    else normals_kernel<false, false><<<blocks, blk, 0, st>>>(a);
     CAB_LAUNCH_CHECK(ctx);
   }
   if (n > ctx->n_valid) {
@@ -216,11 +265,10 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3]) {
     CAB_LAUNCH_CHECK(ctx);
   }
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->b_stats.p, 16, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->b_stats.p, kStatBytes, cudaMemcpyDeviceToHost, st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.normals_ms, ctx->ev[2], ctx->ev[3]));
-  ctx->tm.neighbour_sum = (int64_t)((const unsigned long long*)ctx->h_pin)[0];
-  ctx->tm.candidate_sum = (int64_t)((const unsigned long long*)ctx->h_pin)[1];
+  read_stats(ctx);
   ctx->have_normals = true;
   return CAB_OK;
 }

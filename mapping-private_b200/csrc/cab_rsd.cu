@@ -2,16 +2,24 @@
 // Replaces HOT LOOP 1 + HOT LOOP 2 of cloud_algos::LocalRadiusEstimation::process
 // (cloud_algos/src/radius_estimation.cpp:118-124 and :140-202): no neighbour list is ever
 // materialised; each query keeps per-distance-bin extreme cosines in shared memory while the
-// candidate tiles stream past, then solves the two one-parameter least-squares fits.
+// candidate chunks stream past, then solves the two one-parameter least-squares fits.
 //
-// Arithmetic notes (DESIGN.md "RSD kernel"):
+// Kernel structure (DESIGN.md "RSD kernel"):
+//  phase 1  per 32-candidate chunk: packed fp32x2 distance test -> one 32-bit hit mask per query
+//  phase 2  only the hits are visited (about one candidate in four is a hit, so the per-hit work
+//           must not be paid by the misses); the candidate's position and normal are fetched from
+//           the lane that staged it with warp shuffles.
+// Arithmetic notes:
 //  * cosine is the reference's fp32 expression (nx*nx' + ny*ny') + nz*nz' (:153-155), not contracted.
 //  * angle = acos(cosine) folded at pi/2 (:160-161) is monotone in |cosine|, so per bin only the
 //    cosines of extreme |value| are tracked; acos is evaluated 2*ndiv times per query, not per pair.
 //  * the distance bin floor(ndiv*sqrt((double)d2)/radius) (:165-168) is evaluated through exact
 //    fp32 d2 thresholds computed on the host with the reference's double expression, clamped to
 //    ndiv-1 (the reference indexes out of bounds at dist == radius).
+//  * neighbours whose normal is not finite never update a bin (the reference's NaN comparisons are
+//    all false, :158-172), so they are masked out when the chunk is staged.
 #include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstring>
 
@@ -52,109 +60,110 @@ __device__ __forceinline__ double fold_angle(float c) {
   }
 }
 
-template <bool kExact>
+template <bool kExact, bool kUseThr>
 __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* ptile = reinterpret_cast<float4*>(smem_raw);                      // [W][32]
-  float4* ntile = ptile + kWarpsPerBlock * kWarp;                           // [W][32]
-  float2* bins = reinterpret_cast<float2*>(ntile + kWarpsPerBlock * kWarp);  // [W][ndiv][32]
+  ChunkTile* tiles = reinterpret_cast<ChunkTile*>(smem_raw);                 // [W]
+  float2* bins = reinterpret_cast<float2*>(tiles + kWarpsPerBlock);          // [W][ndiv][32]
   float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * a.ndiv * kWarp);  // [ndiv+1]
-  __shared__ unsigned long long blk_stats[2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ndiv = a.ndiv;
   for (int i = threadIdx.x; i <= ndiv; i += blockDim.x) thr[i] = a.bin_thr[i];
-  if (threadIdx.x < 2) blk_stats[threadIdx.x] = 0;
   __syncthreads();
   const int pid = a.p0 + blockIdx.x * kWarpsPerBlock + warp;
-  if (pid < a.p1) {
-    const GridView& g = a.g;
-    const PacketCtx pc = load_packet(g, pid, lane, a.r);
-    const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
-    const float4 nq = a.nrm[pc.qi];
-    const float r2 = a.r2;
-    const bool use_thr = a.thr_d2 != nullptr;
-    float td2 = 0.f;
-    int tidx = 0;
-    if (use_thr) {
-      td2 = a.thr_d2[pc.qi];
-      tidx = a.thr_idx[pc.qi];
-    }
-    float4* my_p = ptile + warp * kWarp;
-    float4* my_n = ntile + warp * kWarp;
-    float2* my_b = bins + (size_t)warp * ndiv * kWarp + lane;  // bin b at my_b[b * 32]
-    // .x: cosine of smallest |value| (largest angle), .y: cosine of largest |value| (smallest angle)
-    for (int b = 0; b < ndiv; ++b) my_b[b * kWarp] = make_float2(INFINITY, 0.f);
-    if (a.flags & CAB_RSD_SEED_BIN0) my_b[0] = make_float2(1.f, 1.f);
-    int k = 0;
-    const float bscale = a.bin_scale;
-    const int tested = for_each_chunk(
-        g, pc, lane,
-        [&](int j, bool valid, const float4& c) {
-          my_p[lane] = c;
-          my_n[lane] = valid ? a.nrm[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-        },
-        [&](int base, int cnt) {
-          const int cnt4 = (cnt + 3) & ~3;
-#pragma unroll 4
-          for (int m = 0; m < cnt4; ++m) {
-            const float4 c = my_p[m];
-            const float dx = __fsub_rn(c.x, qx), dy = __fsub_rn(c.y, qy), dz = __fsub_rn(c.z, qz);
-            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            bool hit = d2 <= r2;
-            if (use_thr && hit) hit = d2 < td2 || (d2 == td2 && g.perm[base + m] <= tidx);
-            if (hit) {
-              ++k;
-              if (base + m != pc.qi) {  // the query itself is skipped (:150 starts at ni = 1)
-                const float4 nm = my_n[m];
-                float cs = __fadd_rn(__fadd_rn(__fmul_rn(nq.x, nm.x), __fmul_rn(nq.y, nm.y)), __fmul_rn(nq.z, nm.z));
-                if (cs > 1.f) cs = 1.f;  // :158-159, NaN falls through
-                if (cs < -1.f) cs = -1.f;
-                const float sq = d2 > 0.f ? d2 * rsqrtf(d2) : 0.f;
-                int b = min((int)(sq * bscale), ndiv - 1);
-                if (d2 < thr[b]) --b;
-                else if (d2 >= thr[b + 1]) ++b;
-                float2 v = my_b[b * kWarp];
-                const float ac = fabsf(cs);
-                if (ac < fabsf(v.x)) v.x = cs;
-                if (ac >= fabsf(v.y)) v.y = cs;
-                my_b[b * kWarp] = v;
-              }
-            }
-          }
-        });
-
-    // ---- least-squares fit of the min / max angle lines, radius_estimation.cpp:175-202 ----
-    double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;
-    for (int di = 0; di < ndiv; ++di) {
-      const float2 v = my_b[di * kWarp];
-      if (fabsf(v.x) <= 1.f) {  // bin not empty (:181)
-        const double p_min = fold_angle<kExact>(v.y), p_max = fold_angle<kExact>(v.x);
-        const double f = (di + 0.5) * a.radius / ndiv;
-        Amint_Amin = __dadd_rn(Amint_Amin, __dmul_rn(p_min, p_min));
-        Amint_d = __dadd_rn(Amint_d, __dmul_rn(p_min, f));
-        Amaxt_Amax = __dadd_rn(Amaxt_Amax, __dmul_rn(p_max, p_max));
-        Amaxt_d = __dadd_rn(Amaxt_d, __dmul_rn(p_max, f));
+  if (pid >= a.p1) return;
+  const GridView& g = a.g;
+  const PacketCtx pc = load_packet(g, pid, lane, a.r);
+  const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
+  const float4 nq = a.nrm[pc.qi];
+  const bool q_ok = isfinite(nq.x) && isfinite(nq.y) && isfinite(nq.z);
+  const float r2 = a.r2;
+  float td2 = INFINITY;
+  int tidx = INT_MAX;
+  if (kUseThr) {
+    td2 = a.thr_d2[pc.qi];
+    tidx = a.thr_idx[pc.qi];
+  }
+  ChunkTile* tile = &tiles[warp];
+  float2* my_b = bins + (size_t)warp * ndiv * kWarp + lane;  // bin b at my_b[b * 32]
+  // .x: cosine of smallest |value| (largest angle), .y: cosine of largest |value| (smallest angle)
+  for (int b = 0; b < ndiv; ++b) my_b[b * kWarp] = make_float2(INFINITY, 0.f);
+  if (a.flags & CAB_RSD_SEED_BIN0) my_b[0] = make_float2(1.f, 1.f);
+  int k = 0;
+  const float bscale = a.bin_scale;
+  const int tested = for_each_chunk(g, pc, lane, tile, [&](int base, int, const float4& c, bool valid) {
+    // this lane's own candidate: its normal (payload for the shuffles)
+    const float4 cn = valid ? a.nrm[base + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned finite_mask = __ballot_sync(kFull, isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z));
+    unsigned mask = chunk_hit_mask(tile, qx, qy, qz, r2);
+    if (!kUseThr) k += __popc(mask);
+    // the query itself is skipped (:150 starts at ni = 1); non-finite normals never contribute
+    const unsigned self = (unsigned)(pc.qi - base);
+    if (self < 32u) mask &= ~(1u << self);
+    if (!kUseThr) mask &= q_ok ? finite_mask : 0u;
+    const int iters = __reduce_max_sync(kFull, __popc(mask));
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+      const bool has = mask != 0;
+      const int m = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float cx = __shfl_sync(kFull, c.x, m), cy = __shfl_sync(kFull, c.y, m), cz = __shfl_sync(kFull, c.z, m);
+      const float nx = __shfl_sync(kFull, cn.x, m), ny = __shfl_sync(kFull, cn.y, m), nz = __shfl_sync(kFull, cn.z, m);
+      if (has) {
+        const float d2 = d2_rule(cx, cy, cz, qx, qy, qz);
+        bool use = true;
+        if (kUseThr) {
+          use = d2 < td2 || (d2 == td2 && g.perm[base + m] <= tidx);
+          k += use ? 1 : 0;  // (the query itself passes: it was removed from the mask, add it below)
+          use = use && q_ok && ((finite_mask >> m) & 1u);
+        }
+        if (use) {
+          float cs = __fadd_rn(__fadd_rn(__fmul_rn(nq.x, nx), __fmul_rn(nq.y, ny)), __fmul_rn(nq.z, nz));
+          cs = fminf(fmaxf(cs, -1.f), 1.f);  // :158-159 (finite by construction)
+          int b = min((int)(d2 * rsqrtf(d2) * bscale), ndiv - 1);  // d2 == 0 -> NaN -> 0
+          if (d2 < thr[b]) --b;
+          else if (d2 >= thr[b + 1]) ++b;
+          float2 v = my_b[b * kWarp];
+          const float ac = fabsf(cs);
+          if (ac < fabsf(v.x)) v.x = cs;
+          if (ac >= fabsf(v.y)) v.y = cs;
+          my_b[b * kWarp] = v;
+        }
       }
     }
-    double max_radius = (Amint_Amin == 0) ? a.plane_radius : fmin(Amint_d / Amint_Amin, a.plane_radius);
-    double min_radius = (Amaxt_Amax == 0) ? a.plane_radius : fmin(Amaxt_d / Amaxt_Amax, a.plane_radius);
-    float rmin = (float)min_radius, rmax = (float)max_radius;
-    if (a.flags & CAB_RSD_SCALE_SORT) {
-      const float x = rmax * 1.1f, y = rmin * 0.9f;
-      rmin = fminf(x, y);
-      rmax = fmaxf(x, y);
-    }
-    if (pc.active) a.out[pc.qi] = make_float2(rmin, rmax);
-    unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) ks += __shfl_xor_sync(kFull, ks, o);
-    if (lane == 0) {
-      atomicAdd(&blk_stats[0], ks);
-      atomicAdd(&blk_stats[1], (unsigned long long)tested * (unsigned)pc.count);
+  });
+  if (kUseThr) k += 1;  // the query itself is always among its max_nn nearest
+
+  // ---- least-squares fit of the min / max angle lines, radius_estimation.cpp:175-202 ----
+  double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;
+  for (int di = 0; di < ndiv; ++di) {
+    const float2 v = my_b[di * kWarp];
+    if (fabsf(v.x) <= 1.f) {  // bin not empty (:181)
+      const double p_min = fold_angle<kExact>(v.y), p_max = fold_angle<kExact>(v.x);
+      const double f = (di + 0.5) * a.radius / ndiv;
+      Amint_Amin = __dadd_rn(Amint_Amin, __dmul_rn(p_min, p_min));
+      Amint_d = __dadd_rn(Amint_d, __dmul_rn(p_min, f));
+      Amaxt_Amax = __dadd_rn(Amaxt_Amax, __dmul_rn(p_max, p_max));
+      Amaxt_d = __dadd_rn(Amaxt_d, __dmul_rn(p_max, f));
     }
   }
-  __syncthreads();
-  if (threadIdx.x < 2 && blk_stats[threadIdx.x]) atomicAdd(a.stats + threadIdx.x, blk_stats[threadIdx.x]);
+  const double max_radius = (Amint_Amin == 0) ? a.plane_radius : fmin(Amint_d / Amint_Amin, a.plane_radius);
+  const double min_radius = (Amaxt_Amax == 0) ? a.plane_radius : fmin(Amaxt_d / Amaxt_Amax, a.plane_radius);
+  float rmin = (float)min_radius, rmax = (float)max_radius;
+  if (a.flags & CAB_RSD_SCALE_SORT) {
+    const float x = rmax * 1.1f, y = rmin * 0.9f;
+    rmin = fminf(x, y);
+    rmax = fmaxf(x, y);
+  }
+  if (pc.active) a.out[pc.qi] = make_float2(rmin, rmax);
+  unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ks += __shfl_xor_sync(kFull, ks, o);
+  if (lane == 0) {
+    unsigned long long* slot = a.stats + 2 * (pid & (kStatSlots - 1));
+    atomicAdd(slot, ks);
+    atomicAdd(slot + 1, (unsigned long long)tested * (unsigned)pc.count);
+  }
 }
 
 __global__ void fill_invalid_rsd(float2* out, int begin, int end, float v) {
@@ -180,6 +189,14 @@ float bin_threshold(int b, int ndiv, double radius, float r2) {
   return f;
 }
 
+template <bool kExact, bool kUseThr>
+int launch_rsd(cab_ctx* ctx, const RsdArgs& a, unsigned blocks, size_t smem) {
+  CAB_CUDA(ctx, cudaFuncSetAttribute(rsd_kernel<kExact, kUseThr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rsd_kernel<kExact, kUseThr><<<blocks, kWarpsPerBlock * kWarp, smem, ctx->stream>>>(a);
+  CAB_LAUNCH_CHECK(ctx);
+  return CAB_OK;
+}
+
 }  // namespace
 
 int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, int flags) {
@@ -192,7 +209,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   const int n = (int)ctx->n;
   cudaStream_t st = ctx->stream;
   if (int rc = reserve(ctx, ctx->b_rsd, (size_t)std::max(n, 1) * sizeof(float2))) return rc;
-  if (int rc = reserve(ctx, ctx->b_stats, 64)) return rc;
+  if (int rc = reserve(ctx, ctx->b_stats, kStatBytes)) return rc;
   const bool use_thr = max_nn > 0;
   if (use_thr)
     if (int rc = run_thresholds(ctx, rf, max_nn)) return rc;
@@ -203,10 +220,10 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   for (int b = 1; b < ndiv; ++b) thr[b] = bin_threshold(b, ndiv, r, r2);
   thr[ndiv] = INFINITY;
   if (int rc = reserve(ctx, ctx->b_misc, sizeof(thr))) return rc;
-  if (int rc = reserve_pinned(ctx, sizeof(thr))) return rc;
+  if (int rc = reserve_pinned(ctx, sizeof(thr) + kStatBytes)) return rc;
   std::memcpy(ctx->h_pin, thr, sizeof(float) * (ndiv + 1));
   CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_misc.p, ctx->h_pin, sizeof(float) * (ndiv + 1), cudaMemcpyHostToDevice, st));
-  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, 64, st));
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, kStatBytes, st));
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
   RsdArgs a{};
   a.g = grid_view(ctx);
@@ -224,19 +241,15 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   a.radius = r;
   a.plane_radius = plane_radius;
   a.stats = (unsigned long long*)ctx->b_stats.p;
-  const size_t smem = (size_t)kWarpsPerBlock * kWarp * sizeof(float4) * 2 +
-                      (size_t)kWarpsPerBlock * ndiv * kWarp * sizeof(float2) + (ndiv + 1) * sizeof(float);
+  const size_t smem = (size_t)kWarpsPerBlock * sizeof(ChunkTile) + (size_t)kWarpsPerBlock * ndiv * kWarp * sizeof(float2) +
+                      (ndiv + 1) * sizeof(float);
   const int np = a.p1 - a.p0;
   if (np > 0) {
     const unsigned blocks = (np + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (ctx->cfg.exact) {
-      CAB_CUDA(ctx, cudaFuncSetAttribute(rsd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      rsd_kernel<true><<<blocks, kWarpsPerBlock * kWarp, smem, st>>>(a);
-    } else {
-      CAB_CUDA(ctx, cudaFuncSetAttribute(rsd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      rsd_kernel<false><<<blocks, kWarpsPerBlock * kWarp, smem, st>>>(a);
-    }
-    CAB_LAUNCH_CHECK(ctx);
+    int rc;
+    if (ctx->cfg.exact) rc = use_thr ? launch_rsd<true, true>(ctx, a, blocks, smem) : launch_rsd<true, false>(ctx, a, blocks, smem);
+    else rc = use_thr ? launch_rsd<false, true>(ctx, a, blocks, smem) : launch_rsd<false, false>(ctx, a, blocks, smem);
+    if (rc) return rc;
   }
   if (n > ctx->n_valid) {
     fill_invalid_rsd<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((float2*)ctx->b_rsd.p, ctx->n_valid, n,
@@ -244,11 +257,10 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
     CAB_LAUNCH_CHECK(ctx);
   }
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->b_stats.p, 16, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->b_stats.p, kStatBytes, cudaMemcpyDeviceToHost, st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.rsd_ms, ctx->ev[4], ctx->ev[5]));
-  ctx->tm.neighbour_sum = (int64_t)((const unsigned long long*)ctx->h_pin)[0];
-  ctx->tm.candidate_sum = (int64_t)((const unsigned long long*)ctx->h_pin)[1];
+  read_stats(ctx);
   ctx->have_rsd = true;
   return CAB_OK;
 }

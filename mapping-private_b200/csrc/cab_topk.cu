@@ -34,7 +34,7 @@ struct ThrArgs {
 };
 
 __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrArgs a) {
-  __shared__ float4 tile[kSelWarps][kWarp];
+  __shared__ ChunkTile tiles[kSelWarps];
   __shared__ unsigned hist[kSelWarps][kSelBins][kWarp];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pid = a.p0 + blockIdx.x * kSelWarps + warp;
@@ -42,18 +42,16 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrA
   const GridView& g = a.g;
   const PacketCtx pc = load_packet(g, pid, lane, a.r);
   const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z, r2 = a.r2;
-  float4* my_tile = tile[warp];
-  auto stage = [&](int, bool, const float4& c) { my_tile[lane] = c; };
+  ChunkTile* tile = &tiles[warp];
 
   unsigned prefix = 0, mask = 0;
   int target = a.max_nn;
   bool need = pc.active;
   for (int shift = a.first_shift; shift >= 0; shift -= 6) {
     for (int b = 0; b < kSelBins; ++b) hist[warp][b][lane] = 0;
-    for_each_chunk(g, pc, lane, stage, [&](int, int cnt) {
+    for_each_chunk(g, pc, lane, tile, [&](int, int cnt, const float4&, bool) {
       for (int m = 0; m < cnt; ++m) {
-        const float4 c = my_tile[m];
-        const float d2 = d2_rule(c.x, c.y, c.z, qx, qy, qz);
+        const float d2 = d2_rule(tile->x[m], tile->y[m], tile->z[m], qx, qy, qz);
         if (d2 <= r2) {
           const unsigned u = __float_as_uint(d2);
           if ((u & mask) == prefix) hist[warp][(u >> shift) & (kSelBins - 1)][lane]++;
@@ -87,10 +85,9 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrA
   const int rounds = __reduce_max_sync(kFull, need ? target : 0);
   for (int t = 0; t < rounds; ++t) {
     int best = INT_MAX;
-    for_each_chunk(g, pc, lane, stage, [&](int base, int cnt) {
+    for_each_chunk(g, pc, lane, tile, [&](int base, int cnt, const float4&, bool) {
       for (int m = 0; m < cnt; ++m) {
-        const float4 c = my_tile[m];
-        const float d2 = d2_rule(c.x, c.y, c.z, qx, qy, qz);
+        const float d2 = d2_rule(tile->x[m], tile->y[m], tile->z[m], qx, qy, qz);
         if (d2 == dstar && d2 <= r2) {
           const int id = g.perm[base + m];
           if (id > cur && id < best) best = id;

@@ -1,16 +1,50 @@
-// cab_traverse.cuh -- the shared neighbour traversal of the normals / RSD / debug kernels.
+// cab_traverse.cuh -- the shared neighbour traversal of the normals / RSD / threshold kernels.
 //
 // One warp owns one packet (<= 32 consecutive sorted queries of one row, one query per lane).
 // The candidate set of the packet is 9 contiguous runs of the sorted array: rows (cy+dy, cz+dz),
 // cells [cx(xmin)-1, cx(xmax)+1].  Runs are streamed in 32-point chunks: each lane loads one
 // candidate with a coalesced 128-bit load, the chunk is staged in the warp's shared-memory tile
-// and every lane tests all staged candidates against its own query (broadcast LDS.128).
+// (SoA: x[32], y[32], z[32]) and every lane tests all staged candidates against its own query.
+//
+// The distance test uses Blackwell's packed fp32x2 pipe (FADD2 / FFMA2, PTX *.f32x2, sm_100+):
+// two candidates per instruction, each half rounded exactly like the scalar epsilon rule
+//   d2 = (dx*dx + dy*dy) + dz*dz   (fp32, round-to-nearest, no contraction).
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false, so the squares are
+// written as fma(d, d, +0), which rounds exactly like a multiply and cannot be fused further.
 #pragma once
 #include "cab_internal.cuh"
 
 namespace cab {
 
 constexpr int kWarpsPerBlock = 8;
+
+typedef unsigned long long f32x2;  // two packed floats in a 64-bit register
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// exact product (one rounding), not contractible by ptxas
+__device__ __forceinline__ f32x2 sq2(f32x2 a) { return fma2(a, a, 0ull); }
 
 struct PacketCtx {
   int start, count;   // packet
@@ -60,12 +94,18 @@ __device__ __forceinline__ PacketCtx load_packet(const GridView& g, int pid, int
   return pc;
 }
 
-// Streams every candidate chunk of the packet.  `stage(j, valid)` is called by every lane with
-// the sorted index it should load (j < run end iff valid) and must store the candidate into the
-// warp's tile(s); `body(base, cnt)` then runs with the tile visible to the whole warp.
-// Returns the number of candidates tested per query.
-template <class Stage, class Body>
-__device__ __forceinline__ int for_each_chunk(const GridView& g, const PacketCtx& pc, int lane, Stage&& stage,
+// Per-warp SoA tile of one staged chunk.
+struct alignas(16) ChunkTile {
+  float x[kWarp], y[kWarp], z[kWarp];
+};
+
+// Streams every candidate chunk of the packet.  For each chunk that intersects the packet's x
+// window: stage(j, valid) lets the caller load per-candidate payload (lane j's candidate), the
+// positions are staged into `tile`, then body(base, cnt, c) runs with the tile visible to the whole
+// warp; c is this lane's own candidate (sentinel when !valid).  Slots >= cnt hold a far-away
+// sentinel that can never pass the distance test.  Returns the candidates tested per query.
+template <class Body>
+__device__ __forceinline__ int for_each_chunk(const GridView& g, const PacketCtx& pc, int lane, ChunkTile* tile,
                                               Body&& body) {
   int tested = 0;
 #pragma unroll 1
@@ -79,14 +119,47 @@ __device__ __forceinline__ int for_each_chunk(const GridView& g, const PacketCtx
       // runs are sorted by x: skip chunks entirely outside the packet's x window
       if (__all_sync(kFull, !valid || c.x < pc.xlo || c.x > pc.xhi)) continue;
       __syncwarp();
-      stage(j, valid, c);
+      tile->x[lane] = c.x;
+      tile->y[lane] = c.y;
+      tile->z[lane] = c.z;
       __syncwarp();
       const int cnt = min(kWarp, e - base);
-      body(base, cnt);
+      body(base, cnt, c, valid);
       tested += cnt;
     }
   }
   return tested;
+}
+
+// Hit mask of one staged chunk for this lane's query: bit m set iff d2(candidate m, q) <= r2.
+// Packed fp32x2 arithmetic, 4 candidates per shared-memory broadcast load.
+__device__ __forceinline__ unsigned chunk_hit_mask(const ChunkTile* tile, float qx, float qy, float qz, float r2) {
+  const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
+  unsigned mask = 0;
+  const float4* tx = reinterpret_cast<const float4*>(tile->x);
+  const float4* ty = reinterpret_cast<const float4*>(tile->y);
+  const float4* tz = reinterpret_cast<const float4*>(tile->z);
+#pragma unroll
+  for (int g4 = 0; g4 < kWarp / 4; ++g4) {
+    const float4 X = tx[g4], Y = ty[g4], Z = tz[g4];
+    {
+      const f32x2 dx = sub2(pack2(X.x, X.y), qx2), dy = sub2(pack2(Y.x, Y.y), qy2), dz = sub2(pack2(Z.x, Z.y), qz2);
+      const f32x2 d2 = add2(add2(sq2(dx), sq2(dy)), sq2(dz));
+      float a, b;
+      unpack2(d2, a, b);
+      mask |= (a <= r2 ? 1u : 0u) << (4 * g4);
+      mask |= (b <= r2 ? 1u : 0u) << (4 * g4 + 1);
+    }
+    {
+      const f32x2 dx = sub2(pack2(X.z, X.w), qx2), dy = sub2(pack2(Y.z, Y.w), qy2), dz = sub2(pack2(Z.z, Z.w), qz2);
+      const f32x2 d2 = add2(add2(sq2(dx), sq2(dy)), sq2(dz));
+      float a, b;
+      unpack2(d2, a, b);
+      mask |= (a <= r2 ? 1u : 0u) << (4 * g4 + 2);
+      mask |= (b <= r2 ? 1u : 0u) << (4 * g4 + 3);
+    }
+  }
+  return mask;
 }
 
 }  // namespace cab
