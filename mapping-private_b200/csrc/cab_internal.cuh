@@ -18,7 +18,7 @@ constexpr int kWarp = 32;
 constexpr int kXBits = 20;            // sub-cell x field of the sort key
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kStatSlots = 64;         // spread counters (avoids same-address atomic serialisation)
-constexpr size_t kStatBytes = kStatSlots * 2 * sizeof(unsigned long long);
+constexpr size_t kStatBytes = (kStatSlots * 2 + 2) * sizeof(unsigned long long);  // + the packet work counter
 
 // One independent neighbourhood domain: the whole cloud, or one segmented cluster.
 struct Domain {

@@ -4,6 +4,7 @@
 // computeGRSD.cpp:101-106, hough_segmentation/src/rsd.cpp:65-72): neighbours with d2 <= r2
 // (self included), covariance about the centroid, eigenvector of the smallest eigenvalue,
 // curvature = l0 / (l0+l1+l2), flipped towards the viewpoint; fewer than 3 neighbours -> NaN.
+#include <algorithm>
 #include <cmath>
 
 #include "cab_internal.cuh"
@@ -85,9 +86,10 @@ template <bool kExact, bool kUseThr>
 __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const NormalsArgs a) {
   __shared__ ChunkTile tiles[kWarpsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pid = a.p0 + blockIdx.x * kWarpsPerBlock + warp;
-  if (pid >= a.p1) return;
   const GridView& g = a.g;
+  for (;;) {
+  const int pid = a.p0 + next_packet(a.stats, lane);
+  if (pid >= a.p1) break;
   const PacketCtx pc = load_packet(g, pid, lane, a.r);
   const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
   const float r2 = a.r2;
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
     atomicAdd(slot, ks);
     atomicAdd(slot + 1, (unsigned long long)tested * (unsigned)pc.count);
   }
+  }  // persistent packet loop
 }
 
 __global__ void fill_invalid_normals(float4* nrm, int* kcount, int begin, int end) {
@@ -251,12 +254,16 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3]) {
   a.stats = (unsigned long long*)ctx->b_stats.p;
   const int np = a.p1 - a.p0;
   if (np > 0) {
-    const unsigned blocks = (np + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const dim3 blk(kWarpsPerBlock * kWarp);
-    if (ctx->cfg.exact && use_thr) normals_kernel<true, true><<<blocks, blk, 0, st>>>(a);
-    else if (ctx->cfg.exact) normals_kernel<true, false><<<blocks, blk, 0, st>>>(a);
-    else if (use_thr) normals_kernel<false, true><<<blocks, blk, 0, st>>>(a);
-    else normals_kernel<false, false><<<blocks, blk, 0, st>>>(a);
+    auto grid_for = [&](const void* fn) {
+      int per_sm = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kWarpsPerBlock * kWarp, 0);
+      return (unsigned)std::min<long long>((long long)std::max(per_sm, 1) * ctx->sm_count, (np + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    };
+    if (ctx->cfg.exact && use_thr) normals_kernel<true, true><<<grid_for((const void*)normals_kernel<true, true>), blk, 0, st>>>(a);
+    else if (ctx->cfg.exact) normals_kernel<true, false><<<grid_for((const void*)normals_kernel<true, false>), blk, 0, st>>>(a);
+    else if (use_thr) normals_kernel<false, true><<<grid_for((const void*)normals_kernel<false, true>), blk, 0, st>>>(a);
+    else normals_kernel<false, false><<<grid_for((const void*)normals_kernel<false, false>), blk, 0, st>>>(a);
     CAB_LAUNCH_CHECK(ctx);
   }
   if (n > ctx->n_valid) {

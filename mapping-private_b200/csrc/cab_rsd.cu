@@ -18,6 +18,7 @@
 //    ndiv-1 (the reference indexes out of bounds at dist == radius).
 //  * neighbours whose normal is not finite never update a bin (the reference's NaN comparisons are
 //    all false, :158-172), so they are masked out when the chunk is staged.
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -60,6 +61,26 @@ __device__ __forceinline__ double fold_angle(float c) {
   }
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(unsigned addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32x2(unsigned addr, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <bool kExact, bool kUseThr>
 __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -70,99 +91,106 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
   const int ndiv = a.ndiv;
   for (int i = threadIdx.x; i <= ndiv; i += blockDim.x) thr[i] = a.bin_thr[i];
   __syncthreads();
-  const int pid = a.p0 + blockIdx.x * kWarpsPerBlock + warp;
-  if (pid >= a.p1) return;
   const GridView& g = a.g;
-  const PacketCtx pc = load_packet(g, pid, lane, a.r);
-  const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
-  const float4 nq = a.nrm[pc.qi];
-  const bool q_ok = isfinite(nq.x) && isfinite(nq.y) && isfinite(nq.z);
-  const float r2 = a.r2;
-  float td2 = INFINITY;
-  int tidx = INT_MAX;
-  if (kUseThr) {
-    td2 = a.thr_d2[pc.qi];
-    tidx = a.thr_idx[pc.qi];
-  }
   ChunkTile* tile = &tiles[warp];
   float2* my_b = bins + (size_t)warp * ndiv * kWarp + lane;  // bin b at my_b[b * 32]
-  // .x: cosine of smallest |value| (largest angle), .y: cosine of largest |value| (smallest angle)
-  for (int b = 0; b < ndiv; ++b) my_b[b * kWarp] = make_float2(INFINITY, 0.f);
-  if (a.flags & CAB_RSD_SEED_BIN0) my_b[0] = make_float2(1.f, 1.f);
-  int k = 0;
+  const unsigned bins_addr = smem_u32(my_b), thr_addr = smem_u32(thr);
+  const float r2 = a.r2;
   const float bscale = a.bin_scale;
-  const int tested = for_each_chunk(g, pc, lane, tile, [&](int base, int, const float4& c, bool valid) {
-    // this lane's own candidate: its normal (payload for the shuffles)
-    const float4 cn = valid ? a.nrm[base + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const unsigned finite_mask = __ballot_sync(kFull, isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z));
-    unsigned mask = chunk_hit_mask(tile, qx, qy, qz, r2);
-    if (!kUseThr) k += __popc(mask);
-    // the query itself is skipped (:150 starts at ni = 1); non-finite normals never contribute
-    const unsigned self = (unsigned)(pc.qi - base);
-    if (self < 32u) mask &= ~(1u << self);
-    if (!kUseThr) mask &= q_ok ? finite_mask : 0u;
-    const int iters = __reduce_max_sync(kFull, __popc(mask));
+  const int last_bin = ndiv - 1;
+  for (;;) {
+    const int pid = a.p0 + next_packet(a.stats, lane);
+    if (pid >= a.p1) break;
+    const PacketCtx pc = load_packet(g, pid, lane, a.r);
+    const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
+    const float4 nq = a.nrm[pc.qi];
+    const bool q_ok = isfinite(nq.x) && isfinite(nq.y) && isfinite(nq.z);
+    float td2 = INFINITY;
+    int tidx = INT_MAX;
+    if (kUseThr) {
+      td2 = a.thr_d2[pc.qi];
+      tidx = a.thr_idx[pc.qi];
+    }
+    // .x: cosine of smallest |value| (largest angle), .y: cosine of largest |value| (smallest angle)
+    for (int b = 0; b < ndiv; ++b) my_b[b * kWarp] = make_float2(INFINITY, 0.f);
+    if (a.flags & CAB_RSD_SEED_BIN0) my_b[0] = make_float2(1.f, 1.f);
+    int k = 0;
+    const int tested = for_each_chunk(g, pc, lane, tile, [&](int base, int, const float4& c, bool valid) {
+      // this lane's own candidate: its normal (payload for the shuffles)
+      const float4 cn = valid ? a.nrm[base + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const unsigned finite_mask = __ballot_sync(kFull, isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z));
+      unsigned mask = chunk_hit_mask(tile, qx, qy, qz, r2);
+      if (!kUseThr) k += __popc(mask);
+      // the query itself is skipped (:150 starts at ni = 1); non-finite normals never contribute
+      const unsigned self = (unsigned)(pc.qi - base);
+      if (self < 32u) mask &= ~(1u << self);
+      if (!kUseThr) mask &= q_ok ? finite_mask : 0u;
+      int iters = __reduce_max_sync(kFull, __popc(mask));
 #pragma unroll 1
-    for (int it = 0; it < iters; ++it) {
-      const bool has = mask != 0;
-      const int m = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const float cx = __shfl_sync(kFull, c.x, m), cy = __shfl_sync(kFull, c.y, m), cz = __shfl_sync(kFull, c.z, m);
-      const float nx = __shfl_sync(kFull, cn.x, m), ny = __shfl_sync(kFull, cn.y, m), nz = __shfl_sync(kFull, cn.z, m);
-      if (has) {
-        const float d2 = d2_rule(cx, cy, cz, qx, qy, qz);
-        bool use = true;
-        if (kUseThr) {
-          use = d2 < td2 || (d2 == td2 && g.perm[base + m] <= tidx);
-          k += use ? 1 : 0;  // (the query itself passes: it was removed from the mask, add it below)
-          use = use && q_ok && ((finite_mask >> m) & 1u);
-        }
-        if (use) {
-          float cs = __fadd_rn(__fadd_rn(__fmul_rn(nq.x, nx), __fmul_rn(nq.y, ny)), __fmul_rn(nq.z, nz));
-          cs = fminf(fmaxf(cs, -1.f), 1.f);  // :158-159 (finite by construction)
-          int b = min((int)(d2 * rsqrtf(d2) * bscale), ndiv - 1);  // d2 == 0 -> NaN -> 0
-          if (d2 < thr[b]) --b;
-          else if (d2 >= thr[b + 1]) ++b;
-          float2 v = my_b[b * kWarp];
-          const float ac = fabsf(cs);
-          if (ac < fabsf(v.x)) v.x = cs;
-          if (ac >= fabsf(v.y)) v.y = cs;
-          my_b[b * kWarp] = v;
+      for (; iters > 0; --iters) {
+        const int m = 31 - __clz(mask);  // highest pending hit (-1 when none: shuffles read lane 31)
+        const float cx = __shfl_sync(kFull, c.x, m), cy = __shfl_sync(kFull, c.y, m), cz = __shfl_sync(kFull, c.z, m);
+        const float nx = __shfl_sync(kFull, cn.x, m), ny = __shfl_sync(kFull, cn.y, m), nz = __shfl_sync(kFull, cn.z, m);
+        if (mask != 0) {
+          mask ^= 1u << m;
+          const float d2 = d2_rule(cx, cy, cz, qx, qy, qz);
+          bool use = true;
+          if (kUseThr) {
+            use = d2 < td2 || (d2 == td2 && g.perm[base + m] <= tidx);
+            k += use ? 1 : 0;  // (the query itself was removed from the mask, it is added below)
+            use = use && q_ok && ((finite_mask >> m) & 1u);
+          }
+          if (use) {
+            // clamping to [-1, 1] (:158-159) is monotone, so it is applied to the extremes only
+            const float cs = __fadd_rn(__fadd_rn(__fmul_rn(nq.x, nx), __fmul_rn(nq.y, ny)), __fmul_rn(nq.z, nz));
+            int b = min(__float2int_rz(d2 * rsqrt_approx(d2) * bscale), last_bin);  // d2 == 0 -> NaN -> 0
+            const unsigned ta = thr_addr + 4u * b;
+            const float tlo = lds_f32(ta), thi = lds_f32(ta + 4);
+            b += (d2 >= thi ? 1 : 0) - (d2 < tlo ? 1 : 0);
+            const unsigned ba = bins_addr + (unsigned)(kWarp * sizeof(float2)) * b;
+            float2 v = lds_f32x2(ba);
+            const float ac = fabsf(cs);
+            if (ac < fabsf(v.x)) v.x = cs;
+            if (ac >= fabsf(v.y)) v.y = cs;
+            sts_f32x2(ba, v);
+          }
         }
       }
-    }
-  });
-  if (kUseThr) k += 1;  // the query itself is always among its max_nn nearest
+    });
+    if (kUseThr) k += 1;  // the query itself is always among its max_nn nearest
 
-  // ---- least-squares fit of the min / max angle lines, radius_estimation.cpp:175-202 ----
-  double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;
-  for (int di = 0; di < ndiv; ++di) {
-    const float2 v = my_b[di * kWarp];
-    if (fabsf(v.x) <= 1.f) {  // bin not empty (:181)
-      const double p_min = fold_angle<kExact>(v.y), p_max = fold_angle<kExact>(v.x);
-      const double f = (di + 0.5) * a.radius / ndiv;
-      Amint_Amin = __dadd_rn(Amint_Amin, __dmul_rn(p_min, p_min));
-      Amint_d = __dadd_rn(Amint_d, __dmul_rn(p_min, f));
-      Amaxt_Amax = __dadd_rn(Amaxt_Amax, __dmul_rn(p_max, p_max));
-      Amaxt_d = __dadd_rn(Amaxt_d, __dmul_rn(p_max, f));
+    // ---- least-squares fit of the min / max angle lines, radius_estimation.cpp:175-202 ----
+    double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;
+    for (int di = 0; di < ndiv; ++di) {
+      const float2 v = my_b[di * kWarp];
+      if (fabsf(v.x) != INFINITY) {  // bin not empty (:181)
+        const double p_min = fold_angle<kExact>(fminf(fmaxf(v.y, -1.f), 1.f));
+        const double p_max = fold_angle<kExact>(fminf(fmaxf(v.x, -1.f), 1.f));
+        const double f = (di + 0.5) * a.radius / ndiv;
+        Amint_Amin = __dadd_rn(Amint_Amin, __dmul_rn(p_min, p_min));
+        Amint_d = __dadd_rn(Amint_d, __dmul_rn(p_min, f));
+        Amaxt_Amax = __dadd_rn(Amaxt_Amax, __dmul_rn(p_max, p_max));
+        Amaxt_d = __dadd_rn(Amaxt_d, __dmul_rn(p_max, f));
+      }
     }
-  }
-  const double max_radius = (Amint_Amin == 0) ? a.plane_radius : fmin(Amint_d / Amint_Amin, a.plane_radius);
-  const double min_radius = (Amaxt_Amax == 0) ? a.plane_radius : fmin(Amaxt_d / Amaxt_Amax, a.plane_radius);
-  float rmin = (float)min_radius, rmax = (float)max_radius;
-  if (a.flags & CAB_RSD_SCALE_SORT) {
-    const float x = rmax * 1.1f, y = rmin * 0.9f;
-    rmin = fminf(x, y);
-    rmax = fmaxf(x, y);
-  }
-  if (pc.active) a.out[pc.qi] = make_float2(rmin, rmax);
-  unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
+    const double max_radius = (Amint_Amin == 0) ? a.plane_radius : fmin(Amint_d / Amint_Amin, a.plane_radius);
+    const double min_radius = (Amaxt_Amax == 0) ? a.plane_radius : fmin(Amaxt_d / Amaxt_Amax, a.plane_radius);
+    float rmin = (float)min_radius, rmax = (float)max_radius;
+    if (a.flags & CAB_RSD_SCALE_SORT) {
+      const float x = rmax * 1.1f, y = rmin * 0.9f;
+      rmin = fminf(x, y);
+      rmax = fmaxf(x, y);
+    }
+    if (pc.active) a.out[pc.qi] = make_float2(rmin, rmax);
+    unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) ks += __shfl_xor_sync(kFull, ks, o);
-  if (lane == 0) {
-    unsigned long long* slot = a.stats + 2 * (pid & (kStatSlots - 1));
-    atomicAdd(slot, ks);
-    atomicAdd(slot + 1, (unsigned long long)tested * (unsigned)pc.count);
+    for (int o = 16; o; o >>= 1) ks += __shfl_xor_sync(kFull, ks, o);
+    if (lane == 0) {
+      unsigned long long* slot = a.stats + 2 * (pid & (kStatSlots - 1));
+      atomicAdd(slot, ks);
+      atomicAdd(slot + 1, (unsigned long long)tested * (unsigned)pc.count);
+    }
+    __syncwarp();
   }
 }
 
@@ -192,6 +220,9 @@ float bin_threshold(int b, int ndiv, double radius, float r2) {
 template <bool kExact, bool kUseThr>
 int launch_rsd(cab_ctx* ctx, const RsdArgs& a, unsigned blocks, size_t smem) {
   CAB_CUDA(ctx, cudaFuncSetAttribute(rsd_kernel<kExact, kUseThr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  CAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rsd_kernel<kExact, kUseThr>, kWarpsPerBlock * kWarp, smem));
+  blocks = std::min<unsigned>(blocks, (unsigned)std::max(per_sm, 1) * ctx->sm_count);  // persistent warps
   rsd_kernel<kExact, kUseThr><<<blocks, kWarpsPerBlock * kWarp, smem, ctx->stream>>>(a);
   CAB_LAUNCH_CHECK(ctx);
   return CAB_OK;

@@ -46,6 +46,14 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
 // exact product (one rounding), not contractible by ptxas
 __device__ __forceinline__ f32x2 sq2(f32x2 a) { return fma2(a, a, 0ull); }
 
+// Persistent warps pull packets from a global counter (stats[2*kStatSlots]): blocks never idle on
+// their slowest warp and concurrently running warps work on neighbouring packets (L2 locality).
+__device__ __forceinline__ int next_packet(unsigned long long* stats, int lane) {
+  int v = 0;
+  if (lane == 0) v = (int)atomicAdd(reinterpret_cast<unsigned int*>(stats + 2 * kStatSlots), 1u);
+  return __shfl_sync(kFull, v, 0);
+}
+
 struct PacketCtx {
   int start, count;   // packet
   int qi;             // this lane's sorted query index (clamped to a valid one)
