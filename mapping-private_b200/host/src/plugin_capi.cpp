@@ -1,0 +1,141 @@
+// plugin_capi.cpp -- a flat C wrapper around the C++ plugins so that the Python tests (ctypes)
+// can drive them exactly like the reference's callers do: look the class up by its pluginlib name,
+// init(nh), then per message pre() -> (set public fields) -> process() -> output() -> post()
+// (cloud_algos.h:79-97 of the reference; dyn_obj_store/src/table_memory_grsd.cpp:683-705,974-994).
+#include <cstring>
+#include <string>
+
+#include <pluginlib/class_loader.h>
+#include <cloud_algos/cloud_algos.h>
+#include <cloud_algos/normal_estimation.h>
+#include <cloud_algos/radius_estimation.h>
+#include <cloud_algos/global_rsd.h>
+
+using namespace cloud_algos;
+
+namespace {
+struct Handle {
+  std::string name;
+  CloudAlgo* algo = nullptr;
+  ros::NodeHandle nh{"~"};
+  ros::Publisher pub;
+  boost::shared_ptr<const sensor_msgs::PointCloud> out, aux;
+  std::string result;
+};
+}  // namespace
+
+extern "C" {
+
+void* capi_create(const char* lookup_name) {
+  static pluginlib::ClassLoader<CloudAlgo> loader("cloud_algos", "cloud_algos::CloudAlgo");
+  try {
+    loader.loadLibraryForClass(lookup_name);
+    Handle* h = new Handle();
+    h->name = lookup_name;
+    h->algo = loader.createClassInstance(lookup_name);
+    h->algo->init(h->nh);
+    h->pub = h->algo->createPublisher(h->nh);
+    return h;
+  } catch (pluginlib::PluginlibException&) {
+    return nullptr;
+  }
+}
+
+void capi_destroy(void* hv) {
+  Handle* h = (Handle*)hv;
+  if (!h) return;
+  delete h->algo;
+  delete h;
+}
+
+void capi_set_param(void* hv, const char* key, double value) { ((Handle*)hv)->nh.setParam(key, value); }
+
+// Public-field assignment after pre(), the way table_memory_grsd.cpp:975-981 pokes GlobalRSD.
+int capi_set_field(void* hv, const char* field, double value) {
+  Handle* h = (Handle*)hv;
+  const std::string f(field);
+  if (f == "verbosity_level_") { h->algo->verbosity_level_ = (int)value; return 0; }
+  if (LocalRadiusEstimation* a = dynamic_cast<LocalRadiusEstimation*>(h->algo)) {
+    if (f == "radius_") a->radius_ = value; else if (f == "max_nn_") a->max_nn_ = (int)value;
+    else if (f == "plane_radius_") a->plane_radius_ = value; else if (f == "distance_div_") a->distance_div_ = (int)value;
+    else if (f == "point_label_") a->point_label_ = (int)value; else if (f == "rmin2curvature_") a->rmin2curvature_ = value != 0;
+    else return -1;
+    return 0;
+  }
+  if (NormalEstimation* a = dynamic_cast<NormalEstimation*>(h->algo)) {
+    if (f == "radius_") a->radius_ = value; else if (f == "max_nn_") a->max_nn_ = (int)value;
+    else if (f == "vp_x_") a->vp_x_ = value; else if (f == "vp_y_") a->vp_y_ = value; else if (f == "vp_z_") a->vp_z_ = value;
+    else return -1;
+    return 0;
+  }
+  if (GlobalRSD* a = dynamic_cast<GlobalRSD*>(h->algo)) {
+    if (f == "width_") a->width_ = value; else if (f == "step_") a->step_ = (int)value;
+    else if (f == "min_voxel_pts_") a->min_voxel_pts_ = (int)value; else if (f == "label_") a->label_ = (int)value;
+    else if (f == "publish_cloud_centroids_") a->publish_cloud_centroids_ = value != 0;
+    else if (f == "publish_cloud_vrsd_") a->publish_cloud_vrsd_ = value != 0;
+    else return -1;
+    return 0;
+  }
+  return -1;
+}
+
+void capi_pre(void* hv) { ((Handle*)hv)->algo->pre(); }
+void capi_post(void* hv) { ((Handle*)hv)->algo->post(); }
+
+// process(): xyz is n x 3, channel c has `names[c]` and n values at values[c].
+const char* capi_process(void* hv, const float* xyz, int n, int nchan, const char* const* names, const float* const* values) {
+  Handle* h = (Handle*)hv;
+  boost::shared_ptr<sensor_msgs::PointCloud> in(new sensor_msgs::PointCloud());
+  in->header.frame_id = "base_link";
+  in->points.resize(n);
+  for (int i = 0; i < n; ++i) {
+    in->points[i].x = xyz[3 * i];
+    in->points[i].y = xyz[3 * i + 1];
+    in->points[i].z = xyz[3 * i + 2];
+  }
+  in->channels.resize(nchan);
+  for (int c = 0; c < nchan; ++c) {
+    in->channels[c].name = names[c];
+    in->channels[c].values.assign(values[c], values[c] + n);
+  }
+  boost::shared_ptr<const sensor_msgs::PointCloud> cin = in;
+  h->out.reset();
+  if (LocalRadiusEstimation* a = dynamic_cast<LocalRadiusEstimation*>(h->algo)) {
+    h->result = a->process(cin);
+    if (a->output_valid_) h->out = a->output();
+  } else if (NormalEstimation* a = dynamic_cast<NormalEstimation*>(h->algo)) {
+    h->result = a->process(cin);
+    if (a->output_valid_) h->out = a->output();
+  } else if (GlobalRSD* a = dynamic_cast<GlobalRSD*>(h->algo)) {
+    h->result = a->process(cin);
+    if (a->output_valid_) h->out = a->output();
+    h->aux = a->getVRSD();
+  } else {
+    h->result = "unknown plugin type";
+  }
+  if (h->algo->output_valid_ && h->out) h->pub.publish(h->out);
+  return h->result.c_str();
+}
+
+int capi_output_valid(void* hv) { return ((Handle*)hv)->algo->output_valid_ ? 1 : 0; }
+int capi_num_published(void* hv) { return ((Handle*)hv)->pub.getNumPublished(); }
+const char* capi_topic(void* hv) { return ((Handle*)hv)->pub.getTopic().c_str(); }
+
+static const sensor_msgs::PointCloud* pick(Handle* h, int which) { return which == 0 ? h->out.get() : h->aux.get(); }
+int capi_out_size(void* hv, int which) { const sensor_msgs::PointCloud* c = pick((Handle*)hv, which); return c ? (int)c->points.size() : -1; }
+int capi_out_num_channels(void* hv, int which) { const sensor_msgs::PointCloud* c = pick((Handle*)hv, which); return c ? (int)c->channels.size() : -1; }
+const char* capi_out_channel_name(void* hv, int which, int c) { return pick((Handle*)hv, which)->channels[c].name.c_str(); }
+const float* capi_out_channel(void* hv, int which, int c) { return pick((Handle*)hv, which)->channels[c].values.data(); }
+const float* capi_out_points(void* hv, int which) { const sensor_msgs::PointCloud* c = pick((Handle*)hv, which); return c->points.empty() ? nullptr : &c->points[0].x; }
+
+int capi_list_requires(void* hv, char* buf, int cap) {
+  std::string s;
+  for (auto& r : ((Handle*)hv)->algo->requires()) s += r + ",";
+  s += "|";
+  for (auto& p : ((Handle*)hv)->algo->provides()) s += p + ",";
+  std::strncpy(buf, s.c_str(), cap - 1);
+  buf[cap - 1] = 0;
+  return (int)s.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+"""ctypes driver of the host-side C++ plugins (mapping-private_b200/host/libcloud_algos.so).
+
+It calls the real C++ classes (cloud_algos::NormalEstimation, LocalRadiusEstimation, GlobalRSD)
+through the flat wrapper in host/src/plugin_capi.cpp, in the reference's call order:
+init -> pre -> (public fields) -> process -> output -> post.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+import subprocess
+
+import numpy as np
+
+_DIR = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _DIR / "host" / "libcloud_algos.so"
+_LIB = None
+
+
+def build():
+    subprocess.run(["make", "-C", str(_DIR / "host"), "-j8"], check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build()")
+        L = C.CDLL(str(LIB_PATH))
+        L.capi_create.restype = C.c_void_p
+        L.capi_create.argtypes = [C.c_char_p]
+        for f in ("capi_destroy", "capi_pre", "capi_post"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.capi_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.capi_set_field.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.capi_process.restype = C.c_char_p
+        L.capi_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.capi_output_valid.argtypes = [C.c_void_p]
+        L.capi_num_published.argtypes = [C.c_void_p]
+        L.capi_topic.restype = C.c_char_p
+        L.capi_topic.argtypes = [C.c_void_p]
+        for f in ("capi_out_size", "capi_out_num_channels"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int]
+        L.capi_out_channel_name.restype = C.c_char_p
+        L.capi_out_channel_name.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.capi_out_channel.restype = C.POINTER(C.c_float)
+        L.capi_out_channel.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.capi_out_points.restype = C.POINTER(C.c_float)
+        L.capi_out_points.argtypes = [C.c_void_p, C.c_int]
+        L.capi_list_requires.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+class Plugin:
+    def __init__(self, lookup_name: str):
+        self._L = lib()
+        self._h = self._L.capi_create(lookup_name.encode())
+        if not self._h:
+            raise KeyError(f"pluginlib: no class {lookup_name}")
+        self.name = lookup_name
+
+    def close(self):
+        if self._h:
+            self._L.capi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_param(self, key: str, value: float):
+        self._L.capi_set_param(self._h, key.encode(), float(value))
+
+    def set_field(self, field: str, value: float):
+        if self._L.capi_set_field(self._h, field.encode(), float(value)) != 0:
+            raise AttributeError(field)
+
+    def requires_provides(self):
+        buf = C.create_string_buffer(1024)
+        self._L.capi_list_requires(self._h, buf, 1024)
+        req, prov = buf.value.decode().split("|")
+        return [x for x in req.split(",") if x], [x for x in prov.split(",") if x]
+
+    def topic(self):
+        return self._L.capi_topic(self._h).decode()
+
+    def run(self, xyz: np.ndarray, channels: dict | None = None, fields: dict | None = None):
+        """pre(); set fields; process(); output(); post().  Returns (result string, output dict | None)."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        channels = channels or {}
+        names = list(channels)
+        vals = [np.ascontiguousarray(channels[k], dtype=np.float32) for k in names]
+        n = xyz.shape[0]
+        name_arr = (C.c_char_p * max(len(names), 1))(*[k.encode() for k in names])
+        val_arr = (C.c_void_p * max(len(names), 1))(*[v.ctypes.data for v in vals])
+        self._L.capi_pre(self._h)
+        for k, v in (fields or {}).items():
+            self.set_field(k, v)
+        res = self._L.capi_process(self._h, xyz.ctypes.data, n, len(names), name_arr, val_arr).decode()
+        out = self.output(0) if self._L.capi_output_valid(self._h) else None
+        self._L.capi_post(self._h)
+        return res, out
+
+    def output_valid(self):
+        return bool(self._L.capi_output_valid(self._h))
+
+    def num_published(self):
+        return self._L.capi_num_published(self._h)
+
+    def output(self, which: int = 0):
+        n = self._L.capi_out_size(self._h, which)
+        if n < 0:
+            return None
+        out = {"points": np.ctypeslib.as_array(self._L.capi_out_points(self._h, which), shape=(n, 3)).copy() if n else np.zeros((0, 3), np.float32),
+               "channels": {}}
+        for c in range(self._L.capi_out_num_channels(self._h, which)):
+            name = self._L.capi_out_channel_name(self._h, which, c).decode()
+            out["channels"][name] = (np.ctypeslib.as_array(self._L.capi_out_channel(self._h, which, c), shape=(n,)).copy()
+                                     if n else np.zeros(0, np.float32))
+        return out

@@ -1,0 +1,49 @@
+"""Host-side multi-GPU plumbing: one process per GPU, torch.distributed for the exchange steps.
+
+The path shards by queries (contiguous ranges of the sorted order) and by clusters:
+  * normals + RSD of one cloud: every rank computes its packet range; the only exchange is the
+    concatenation of the ranks' slices (normals between the two passes, radii at the end),
+    done in place with one broadcast per rank over NCCL / NVLink;
+  * GRSD of a batch of clusters: clusters are assigned to ranks longest-first; the integer
+    histograms are summed with one small all-reduce (bit-exact in any order).
+Everything here works on CPU tensors with the gloo backend, which is how it is tested.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+
+def split_range(n_items: int, world: int) -> List[Tuple[int, int]]:
+    """Same split as cab_set_shard / packet_range in csrc/cab_grid.cu: [n*r/w, n*(r+1)/w)."""
+    return [(n_items * r // world, n_items * (r + 1) // world) for r in range(world)]
+
+
+def exchange_slices(buf, ranges: Sequence[Tuple[int, int]], group=None):
+    """buf: tensor whose rows [b_g, e_g) were produced by rank g.  After the call every rank holds
+    all rows.  In place: rank g broadcasts a view of its own slice."""
+    import torch.distributed as dist
+
+    for g, (b, e) in enumerate(ranges):
+        if e > b:
+            dist.broadcast(buf[b:e], src=g, group=group)
+    return buf
+
+
+def assign_clusters_lpt(sizes: Sequence[int], world: int) -> List[List[int]]:
+    """Longest-processing-time-first assignment of clusters to ranks (deterministic)."""
+    order = sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i))
+    load = [0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += int(sizes[i])
+    return [sorted(v) for v in out]
+
+
+def allreduce_histograms(hist_full, group=None):
+    """hist_full: int32 tensor (n_clusters, 21), zero except for this rank's clusters.  Sum over ranks."""
+    import torch.distributed as dist
+
+    dist.all_reduce(hist_full, op=dist.ReduceOp.SUM, group=group)
+    return hist_full
