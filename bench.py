@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=6_000_000)
+    ap.add_argument("--workload", default="normals_rsd", choices=["normals_rsd", "grsd"],
+                    help="normals_rsd: the headline C4 metric; grsd: config C3, 512 clusters, GRSD clouds/s")
+    ap.add_argument("--clusters", type=int, default=512)
     return ap.parse_args()
 
 
@@ -161,6 +164,93 @@ def run_reference(args, rank):
     }))
 
 
+def run_grsd(args, rank, world, local_rank):
+    """Config C3: GRSD-21 of a batch of segmented clusters (2.5 cm voxels), cluster-per-GPU.
+    Host buffers in, 21 int32 bins per cluster out (the GlobalRSD plugin's work); histograms of the
+    ranks are summed with one all-reduce."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mapping_private_b200 import cab, shard, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    xyz, off = synth.clusters(args.clusters)
+    sizes = np.diff(off)
+    mine = shard.assign_clusters_lpt(sizes.tolist(), world)[rank]
+    my_xyz = np.concatenate([xyz[off[c]:off[c + 1]] for c in mine]) if mine else np.zeros((0, 3), np.float32)
+    my_off = np.concatenate([[0], np.cumsum(sizes[mine])]).astype(np.int32)
+    ctx = cab.Context(local_rank, exact=True)
+    leaf = 0.025
+
+    def step():
+        hist = torch.zeros((args.clusters, 21), dtype=torch.int32)
+        if mine:
+            h = ctx.grsd_batch(my_xyz, my_off, leaf, r_normals=0.02)
+            hist[mine] = torch.from_numpy(h)
+        if world > 1:
+            hd = hist.to(dev)
+            shard.allreduce_histograms(hd)
+            hist = hd.cpu()
+        return hist
+
+    for _ in range(max(args.warmup, 3)):
+        hist = step()
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = ctx.profile()["kernel_launches"]
+    sampler.start()
+    t0 = time.perf_counter()
+    kern_ms = []
+    for _ in range(args.steps):
+        hist = step()
+        p = ctx.profile()
+        kern_ms.append(p["build_ms"] + p["normals_ms"] + p["grsd_ms"])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctx.profile()["kernel_launches"] - l0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import pyoracle
+
+        pyoracle.build()
+        ncheck = min(args.clusters, 48)
+        t1 = time.perf_counter()
+        bad = 0
+        for c in range(ncheck):
+            o = pyoracle.grsd21(xyz[off[c]:off[c + 1]], leaf, r_normals=0.02)
+            bad += int(not np.array_equal(o["hist21"], hist[c].numpy()))
+        cdt = time.perf_counter() - t1
+        cpu = {"value": ncheck / cdt, "unit": "clouds/s", "cores": pyoracle.num_threads(), "kind": "port",
+               "sample": f"first {ncheck} clusters, oracle normals+voxel RSD+GRSD; histograms differing from the GPU: {bad}"}
+    if rank == 0:
+        ms = 1e3 * dt / args.steps
+        print(json.dumps({
+            "metric": "GRSD clouds/s", "value": args.clusters / (dt / args.steps), "unit": "clouds/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3 GRSD-21 on {args.clusters} synthetic clusters, leaf 2.5 cm, normals r=2cm, cluster-per-GPU",
+                       "points": int(off[-1]), "leaf_m": leaf, "parallelism": f"clusters LPT x{world}, int32 all-reduce of histograms",
+                       "timed": "host buffers in, histograms out (H2D + D2H inside)"},
+            "kernels_ms_per_step_rank0": statistics.mean(kern_ms), "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": args.clusters / (dt / args.steps), "unit": "clouds/s", "h2d_bytes_per_step": int(off[-1]) * 12,
+                    "d2h_bytes_per_step": args.clusters * 84},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 class _DevArray:
     def __init__(self, ptr, shape, typestr="<f4"):
         self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
@@ -185,8 +275,11 @@ def main():
     import pkgpath
 
     pkgpath.load()
-    from mapping_private_b200 import cab, synth
+    from mapping_private_b200 import cab, shard, synth
 
+    if args.workload == "grsd":
+        run_grsd(args, rank, world, local_rank)
+        return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -204,10 +297,7 @@ def main():
     def exchange(which, width):
         """Concatenate the shards' results: every rank broadcasts its slice in place (NCCL/NVLink)."""
         buf = torch.as_tensor(_DevArray(ctx.device_ptr(which), (n, width)), device=dev)
-        for g in range(world):
-            b, e = ranges[g]
-            if e > b:
-                dist.broadcast(buf[b:e], src=g)
+        shard.exchange_slices(buf, ranges)
         torch.cuda.synchronize()
 
     def step():
