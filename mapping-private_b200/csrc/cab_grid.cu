@@ -145,27 +145,31 @@ __global__ void __launch_bounds__(256) row_packets_kernel(const Domain* __restri
   rowpk[row] = (len + kWarp - 1) / kWarp;
 }
 
+// one thread per packet: find its row by binary search over the per-row packet prefix
 __global__ void __launch_bounds__(256) fill_packets_kernel(const Domain* __restrict__ domains, int n_domains,
                                                            long long n_rows, const int* __restrict__ cell_start,
-                                                           const int* __restrict__ packet_base,
+                                                           const int* __restrict__ packet_base, int n_packets,
                                                            Packet* __restrict__ packets) {
-  long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n_rows) return;
-  int pb = packet_base[row], npk = packet_base[row + 1] - pb;
-  if (npk == 0) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_packets) return;
+  long long rlo = 0, rhi = n_rows;  // largest row with packet_base[row] <= p
+  while (rhi - rlo > 1) {
+    const long long mid = (rlo + rhi) >> 1;
+    if (packet_base[mid] <= p) rlo = mid; else rhi = mid;
+  }
+  const long long row = rlo;
   int lo = 0, hi = n_domains;
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;
     if (domains[mid].row_base <= row) lo = mid; else hi = mid;
   }
   const Domain dm = domains[lo];
-  long long c0 = dm.cell_base + (row - dm.row_base) * dm.nx;
-  int start = cell_start[c0];
-  long long len = cell_start[c0 + dm.nx] - start;
-  for (int k = 0; k < npk; ++k) {
-    int a = start + (int)(k * len / npk), b = start + (int)((k + 1) * len / npk);
-    packets[pb + k] = Packet{a, b - a, (int)(row - dm.row_base), lo};
-  }
+  const long long c0 = dm.cell_base + (row - dm.row_base) * dm.nx;
+  const int start = cell_start[c0];
+  const long long len = cell_start[c0 + dm.nx] - start;
+  const int pb = packet_base[row], npk = packet_base[row + 1] - pb, k = p - pb;
+  const int a = start + (int)(k * len / npk), b = start + (int)((k + 1) * len / npk);
+  packets[p] = Packet{a, b - a, (int)(row - dm.row_base), lo};
 }
 
 }  // namespace
@@ -335,10 +339,10 @@ int build_grid(cab_ctx* ctx, float cell) {
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->n_packets = *(const int*)ctx->h_pin;
   if (int rc = reserve(ctx, ctx->b_packets, (size_t)std::max(ctx->n_packets, 1) * sizeof(Packet))) return rc;
-  if (rows > 0) {
-    fill_packets_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const Domain*)ctx->b_domains.p, nd, rows,
-                                                                      (const int*)ctx->b_cellstart.p, packet_base,
-                                                                      (Packet*)ctx->b_packets.p);
+  if (ctx->n_packets > 0) {
+    fill_packets_kernel<<<(unsigned)((ctx->n_packets + 255) / 256), 256, 0, st>>>(
+        (const Domain*)ctx->b_domains.p, nd, rows, (const int*)ctx->b_cellstart.p, packet_base, ctx->n_packets,
+        (Packet*)ctx->b_packets.p);
     CAB_LAUNCH_CHECK(ctx);
   }
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));

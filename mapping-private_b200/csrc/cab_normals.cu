@@ -90,10 +90,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
   for (;;) {
   const int pid = a.p0 + next_packet(a.stats, lane);
   if (pid >= a.p1) break;
-  const PacketCtx pc = load_packet(g, pid, lane, a.r);
+  ChunkTile* tile = &tiles[warp];
+  const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
   const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
   const float r2 = a.r2;
-  ChunkTile* tile = &tiles[warp];
   using Acc = typename std::conditional<kExact, double, float>::type;
   Acc s1x = 0, s1y = 0, s1z = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
   int k = 0;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
   if constexpr (!kExact && !kUseThr) {
     // fast path: packed fp32x2 distance test, predicated fp32 accumulation
     const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
-    tested = for_each_chunk(g, pc, lane, tile, [&](int, int cnt, const float4&, bool) {
+    tested = for_each_chunk(g, pc, lane, tile, [&](int cnt, const float4&, int, bool) {
       const float4* tx = reinterpret_cast<const float4*>(tile->x);
       const float4* ty = reinterpret_cast<const float4*>(tile->y);
       const float4* tz = reinterpret_cast<const float4*>(tile->z);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
       td2 = a.thr_d2[pc.qi];
       tidx = a.thr_idx[pc.qi];
     }
-    tested = for_each_chunk(g, pc, lane, tile, [&](int base, int, const float4& c, bool) {
+    tested = for_each_chunk(g, pc, lane, tile, [&](int, const float4& c, int, bool) {
       unsigned mask = chunk_hit_mask(tile, qx, qy, qz, r2);
       const int iters = __reduce_max_sync(kFull, __popc(mask));
       for (int it = 0; it < iters; ++it) {
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
           bool hit = true;
           if (kUseThr) {
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            hit = d2 < td2 || (d2 == td2 && g.perm[base + m] <= tidx);
+            hit = d2 < td2 || (d2 == td2 && g.perm[tile->idx[m]] <= tidx);
           }
           if (hit) {
             if constexpr (kExact) {

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
   for (;;) {
     const int pid = a.p0 + next_packet(a.stats, lane);
     if (pid >= a.p1) break;
-    const PacketCtx pc = load_packet(g, pid, lane, a.r);
+    const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
     const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
     const float4 nq = a.nrm[pc.qi];
     const bool q_ok = isfinite(nq.x) && isfinite(nq.y) && isfinite(nq.z);
@@ -115,15 +115,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
     for (int b = 0; b < ndiv; ++b) my_b[b * kWarp] = make_float2(INFINITY, 0.f);
     if (a.flags & CAB_RSD_SEED_BIN0) my_b[0] = make_float2(1.f, 1.f);
     int k = 0;
-    const int tested = for_each_chunk(g, pc, lane, tile, [&](int base, int, const float4& c, bool valid) {
+    const int tested = for_each_chunk(g, pc, lane, tile, [&](int, const float4& c, int j, bool valid) {
       // this lane's own candidate: its normal (payload for the shuffles)
-      const float4 cn = valid ? a.nrm[base + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 cn = valid ? a.nrm[j] : make_float4(0.f, 0.f, 0.f, 0.f);
       const unsigned finite_mask = __ballot_sync(kFull, isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z));
       unsigned mask = chunk_hit_mask(tile, qx, qy, qz, r2);
       if (!kUseThr) k += __popc(mask);
-      // the query itself is skipped (:150 starts at ni = 1); non-finite normals never contribute
-      const unsigned self = (unsigned)(pc.qi - base);
-      if (self < 32u) mask &= ~(1u << self);
+      // non-finite normals never contribute
       if (!kUseThr) mask &= q_ok ? finite_mask : 0u;
       int iters = __reduce_max_sync(kFull, __popc(mask));
 #pragma unroll 1
@@ -134,11 +132,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
         if (mask != 0) {
           mask ^= 1u << m;
           const float d2 = d2_rule(cx, cy, cz, qx, qy, qz);
-          bool use = true;
+          // the query itself is skipped (:150 starts at ni = 1); only a zero distance can be the query
+          bool use = !(d2 == 0.f && tile->idx[m] == pc.qi);
           if (kUseThr) {
-            use = d2 < td2 || (d2 == td2 && g.perm[base + m] <= tidx);
-            k += use ? 1 : 0;  // (the query itself was removed from the mask, it is added below)
-            use = use && q_ok && ((finite_mask >> m) & 1u);
+            const bool in = d2 < td2 || (d2 == td2 && g.perm[tile->idx[m]] <= tidx);
+            k += in ? 1 : 0;
+            use = use && in && q_ok && ((finite_mask >> m) & 1u);
           }
           if (use) {
             // clamping to [-1, 1] (:158-159) is monotone, so it is applied to the extremes only
@@ -157,7 +156,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
         }
       }
     });
-    if (kUseThr) k += 1;  // the query itself is always among its max_nn nearest
 
     // ---- least-squares fit of the min / max angle lines, radius_estimation.cpp:175-202 ----
     double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;

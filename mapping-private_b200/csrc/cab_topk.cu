@@ -40,16 +40,16 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrA
   const int pid = a.p0 + blockIdx.x * kSelWarps + warp;
   if (pid >= a.p1) return;
   const GridView& g = a.g;
-  const PacketCtx pc = load_packet(g, pid, lane, a.r);
-  const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z, r2 = a.r2;
   ChunkTile* tile = &tiles[warp];
+  const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
+  const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z, r2 = a.r2;
 
   unsigned prefix = 0, mask = 0;
   int target = a.max_nn;
   bool need = pc.active;
   for (int shift = a.first_shift; shift >= 0; shift -= 6) {
     for (int b = 0; b < kSelBins; ++b) hist[warp][b][lane] = 0;
-    for_each_chunk(g, pc, lane, tile, [&](int, int cnt, const float4&, bool) {
+    for_each_chunk(g, pc, lane, tile, [&](int cnt, const float4&, int, bool) {
       for (int m = 0; m < cnt; ++m) {
         const float d2 = d2_rule(tile->x[m], tile->y[m], tile->z[m], qx, qy, qz);
         if (d2 <= r2) {
@@ -85,11 +85,11 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrA
   const int rounds = __reduce_max_sync(kFull, need ? target : 0);
   for (int t = 0; t < rounds; ++t) {
     int best = INT_MAX;
-    for_each_chunk(g, pc, lane, tile, [&](int base, int cnt, const float4&, bool) {
+    for_each_chunk(g, pc, lane, tile, [&](int cnt, const float4&, int, bool) {
       for (int m = 0; m < cnt; ++m) {
         const float d2 = d2_rule(tile->x[m], tile->y[m], tile->z[m], qx, qy, qz);
         if (d2 == dstar && d2 <= r2) {
-          const int id = g.perm[base + m];
+          const int id = g.perm[tile->idx[m]];
           if (id > cur && id < best) best = id;
         }
       }

@@ -2,9 +2,10 @@
 //
 // One warp owns one packet (<= 32 consecutive sorted queries of one row, one query per lane).
 // The candidate set of the packet is 9 contiguous runs of the sorted array: rows (cy+dy, cz+dz),
-// cells [cx(xmin)-1, cx(xmax)+1].  Runs are streamed in 32-point chunks: each lane loads one
-// candidate with a coalesced 128-bit load, the chunk is staged in the warp's shared-memory tile
-// (SoA: x[32], y[32], z[32]) and every lane tests all staged candidates against its own query.
+// cells [cx(xmin)-1, cx(xmax)+1], trimmed to the packet's x window and concatenated into one stream
+// of 32-candidate chunks: each lane loads one candidate with a 128-bit load, the chunk is staged in
+// the warp's shared-memory tile (SoA: x[32], y[32], z[32]) and every lane tests all staged
+// candidates against its own query.
 //
 // The distance test uses Blackwell's packed fp32x2 pipe (FADD2 / FFMA2, PTX *.f32x2, sm_100+):
 // two candidates per instruction, each half rounded exactly like the scalar epsilon rule
@@ -54,13 +55,20 @@ __device__ __forceinline__ int next_packet(unsigned long long* stats, int lane) 
   return __shfl_sync(kFull, v, 0);
 }
 
+// Per-warp shared-memory tile: one staged chunk (SoA) + the packet's run table.
+struct alignas(16) ChunkTile {
+  float x[kWarp], y[kWarp], z[kWarp];
+  int idx[kWarp];      // sorted index of the staged candidate (-1: padding)
+  int run_begin[12];   // trimmed candidate runs of the packet: first sorted index
+  int run_cum[12];     // exclusive prefix of the run lengths; run_cum[9] = total candidates
+};
+
 struct PacketCtx {
   int start, count;   // packet
   int qi;             // this lane's sorted query index (clamped to a valid one)
   bool active;        // lane < count
   float4 q;           // this lane's query position
-  float xlo, xhi;     // x window for chunk culling
-  int rb, re;         // lane t < 9: candidate run t = [rb, re)
+  int total;          // candidates of the packet (all runs, trimmed to the x window)
 };
 
 __device__ __forceinline__ float warp_min(float v) {
@@ -74,7 +82,11 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ PacketCtx load_packet(const GridView& g, int pid, int lane, float r) {
+// Loads the packet and builds its candidate stream: the 9 runs (rows (cy+dy, cz+dz), cells
+// [cx(xmin)-1, cx(xmax)+1]) are trimmed to the packet's x window [xmin - r, xmax + r] by a binary
+// search over the fine x coordinate the rows are sorted by (lanes 0..8 search the lower end, lanes
+// 16..24 the upper end), then concatenated so that every 32-candidate chunk but the last is full.
+__device__ __forceinline__ PacketCtx load_packet(const GridView& g, int pid, int lane, float r, ChunkTile* tile) {
   PacketCtx pc;
   const Packet pk = g.packets[pid];
   const Domain dm = g.domains[pk.domain];
@@ -85,58 +97,81 @@ __device__ __forceinline__ PacketCtx load_packet(const GridView& g, int pid, int
   pc.q = g.pos[pc.qi];
   const float xmin = warp_min(pc.q.x), xmax = warp_max(pc.q.x);
   const float rc = r * 1.00001f;
-  pc.xlo = xmin - rc;
-  pc.xhi = xmax + rc;
   const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
   const int cxlo = max((xfine_coord(xmin, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift) - 1, 0);
   const int cxhi = min((xfine_coord(xmax, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift) + 1, dm.nx - 1);
-  pc.rb = pc.re = 0;
-  if (lane < 9) {
-    const int y = cy + lane % 3 - 1, z = cz + lane / 3 - 1;
+  // fine-x window: x >= xmin - rc  =>  xf(x) >= xf(xmin - rc) (xf is monotone), same at the top
+  const int xf_lo = xfine_coord(xmin - rc, dm.ox, g.inv_cell, dm.nx, dm.xshift);
+  const int xf_hi = xfine_coord(xmax + rc, dm.ox, g.inv_cell, dm.nx, dm.xshift);
+  const int t = lane & 15;  // run handled by this lane (lanes 0..8 lower bound, 16..24 upper bound)
+  int lo = 0, hi = 0;
+  if (t < 9) {
+    const int y = cy + t % 3 - 1, z = cz + t / 3 - 1;
     if (y >= 0 && y < dm.ny && z >= 0 && z < dm.nz) {
       const long long c = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
-      pc.rb = g.cell_start[c + cxlo];
-      pc.re = g.cell_start[c + cxhi + 1];
+      lo = g.cell_start[c + cxlo];
+      hi = g.cell_start[c + cxhi + 1];
     }
   }
+  // first index in [lo, hi) whose xf is >= key (lower half-warp) / > key (upper half-warp)
+  const int key = lane < 16 ? xf_lo : xf_hi + 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int xf = xfine_coord(g.pos[mid].x, dm.ox, g.inv_cell, dm.nx, dm.xshift);
+    if (xf < key) lo = mid + 1; else hi = mid;
+  }
+  const int end = __shfl_sync(kFull, lo, (lane + 16) & 31);
+  int len = (lane < 9) ? max(end - lo, 0) : 0;
+  int cum = len;  // inclusive scan over lanes
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    const int v = __shfl_up_sync(kFull, cum, o);
+    if (lane >= o) cum += v;
+  }
+  __syncwarp();
+  if (lane < 9) {
+    tile->run_begin[lane] = lo;
+    tile->run_cum[lane] = cum - len;
+  }
+  pc.total = __shfl_sync(kFull, cum, 8);
+  if (lane == 9) tile->run_cum[9] = pc.total;
+  __syncwarp();
   return pc;
 }
 
-// Per-warp SoA tile of one staged chunk.
-struct alignas(16) ChunkTile {
-  float x[kWarp], y[kWarp], z[kWarp];
-};
-
-// Streams every candidate chunk of the packet.  For each chunk that intersects the packet's x
-// window: stage(j, valid) lets the caller load per-candidate payload (lane j's candidate), the
-// positions are staged into `tile`, then body(base, cnt, c) runs with the tile visible to the whole
-// warp; c is this lane's own candidate (sentinel when !valid).  Slots >= cnt hold a far-away
-// sentinel that can never pass the distance test.  Returns the candidates tested per query.
+// Streams the packet's candidates in 32-candidate chunks.  Chunk c holds the stream positions
+// {lane * nchunks + c}: a strided, i.e. spatially stratified, sample of the whole candidate region, so
+// every chunk gives every query about the same number of hits (consecutive positions would make the
+// hit counts of a chunk very uneven across lanes, which the hit-compacting kernels pay for with
+// idle lanes).  Neighbouring chunks touch the same cache lines, so the loads stay L1 hits.
+// Each lane loads one candidate, the chunk is staged into `tile`, then body(cnt, c, j, valid) runs
+// with the tile visible to the whole warp: c / j are this lane's own candidate and its sorted index
+// (a far-away sentinel / -1 for the padding lanes, which are always the highest lanes).
+// Returns the candidates tested per query.
 template <class Body>
 __device__ __forceinline__ int for_each_chunk(const GridView& g, const PacketCtx& pc, int lane, ChunkTile* tile,
                                               Body&& body) {
-  int tested = 0;
+  const int nchunks = (pc.total + kWarp - 1) / kWarp;
 #pragma unroll 1
-  for (int t = 0; t < 9; ++t) {
-    const int b = __shfl_sync(kFull, pc.rb, t), e = __shfl_sync(kFull, pc.re, t);
-#pragma unroll 1
-    for (int base = b; base < e; base += kWarp) {
-      const int j = base + lane;
-      const bool valid = j < e;
-      const float4 c = valid ? g.pos[j] : make_float4(3.0e30f, 3.0e30f, 3.0e30f, 0.f);
-      // runs are sorted by x: skip chunks entirely outside the packet's x window
-      if (__all_sync(kFull, !valid || c.x < pc.xlo || c.x > pc.xhi)) continue;
-      __syncwarp();
-      tile->x[lane] = c.x;
-      tile->y[lane] = c.y;
-      tile->z[lane] = c.z;
-      __syncwarp();
-      const int cnt = min(kWarp, e - base);
-      body(base, cnt, c, valid);
-      tested += cnt;
-    }
+  for (int c0 = 0; c0 < nchunks; ++c0) {
+    const int p = lane * nchunks + c0;
+    const bool valid = p < pc.total;
+    // run containing stream position p: largest t with run_cum[t] <= p (9 runs, branch-free search)
+    int t = (p >= tile->run_cum[4]) ? 4 : 0;
+    t += (p >= tile->run_cum[t + 2]) ? 2 : 0;
+    t += (p >= tile->run_cum[t + 1]) ? 1 : 0;
+    t += (t == 7 && p >= tile->run_cum[8]) ? 1 : 0;
+    const int j = valid ? tile->run_begin[t] + (p - tile->run_cum[t]) : -1;
+    const float4 c = valid ? g.pos[j] : make_float4(3.0e30f, 3.0e30f, 3.0e30f, 0.f);
+    __syncwarp();
+    tile->x[lane] = c.x;
+    tile->y[lane] = c.y;
+    tile->z[lane] = c.z;
+    tile->idx[lane] = j;
+    __syncwarp();
+    body(__popc(__ballot_sync(kFull, valid)), c, j, valid);
   }
-  return tested;
+  return pc.total;
 }
 
 // Hit mask of one staged chunk for this lane's query: bit m set iff d2(candidate m, q) <= r2.
