@@ -152,7 +152,7 @@ def run_reference(args, rank):
     value = len(rates) * sample.shape[0] / sum(dt for _, dt in rates)
     ms = 1e3 * sum(dt for _, dt in rates) / len(rates)
     desc = f"x-slab of the room cloud, {sample.shape[0]} points per step (same density as the {args.points}-point workload)"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -236,7 +236,7 @@ def run_grsd(args, rank, world, local_rank):
                "sample": f"first {ncheck} clusters, oracle normals+voxel RSD+GRSD; histograms differing from the GPU: {bad}"}
     if rank == 0:
         ms = 1e3 * dt / args.steps
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "GRSD clouds/s", "value": args.clusters / (dt / args.steps), "unit": "clouds/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -256,8 +256,19 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
+def emit(line: str):
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, warnings) to stderr."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -300,15 +311,25 @@ def main():
         shard.exchange_slices(buf, ranges)
         torch.cuda.synchronize()
 
+    stage_s = {"build": 0.0, "normals": 0.0, "exchange_normals": 0.0, "rsd": 0.0, "exchange_rsd": 0.0}
+
     def step():
+        t0 = time.perf_counter()
         ctx.set_cloud_device(d_xyz.data_ptr(), n, 3)
         ctx.build_grid(RADIUS)
+        t1 = time.perf_counter()
         ctx.normals(RADIUS, download=False)
+        t2 = time.perf_counter()
         if world > 1:
             exchange(cab.BUF_NRM_SORTED, 4)
+        t3 = time.perf_counter()
         ctx.rsd(RADIUS, ndiv=NDIV, plane_radius=PLANE_RADIUS, download=False)
+        t4 = time.perf_counter()
         if world > 1:
             exchange(cab.BUF_RSD_SORTED, 2)
+        t5 = time.perf_counter()
+        for k, v in zip(stage_s, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+            stage_s[k] += v
 
     # shard ranges are a deterministic function of the cloud; exchange them once
     ctx.set_cloud_device(d_xyz.data_ptr(), n, 3)
@@ -329,6 +350,8 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phases = {"build_ms": [], "normals_ms": [], "rsd_ms": []}
+    for k in stage_s:
+        stage_s[k] = 0.0
     ev0.record(lib_stream)
     for _ in range(args.steps):
         step()
@@ -355,6 +378,11 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = n / (ms_per_step * 1e-3)
     kbar = neighbour_sum / n
+    my_stages = {k: 1e3 * v / args.steps for k, v in stage_s.items()}  # host wall per stage (each stage syncs)
+    per_rank = [my_stages]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, my_stages)
 
     # ---- roofline of the dominant kernel (rsd_kernel), SURVEY section 8(d) accounting -------
     peak, peak_src = hbm_peak()
@@ -444,9 +472,10 @@ def main():
                        "parallelism": f"query-shard x{world}, grid replicated, NCCL broadcast of shard results",
                        "mode": "exact-fp64" if args.exact else "fast-fp32"},
             "phases_ms": {"build": build_ms, "normals": nrm_ms, "rsd": rsd_ms},
+            "per_rank_stage_ms": per_rank,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

@@ -252,7 +252,7 @@ void cab_destroy(cab_ctx* ctx) {
                     &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
                     &ctx->b_cellcnt, &ctx->b_cellstart, &ctx->b_rowpk, &ctx->b_packets, &ctx->b_nrm, &ctx->b_nrm_in,
                     &ctx->b_rsd, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
-                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
+                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
                     &ctx->g_vvals[1], &ctx->g_cent, &ctx->g_vcount, &ctx->g_vrad, &ctx->g_vlabel, &ctx->g_voff,
                     &ctx->g_layout, &ctx->g_layoff, &ctx->g_vgrid, &ctx->g_hist, &ctx->g_vfirst};
   for (DevBuf* b : bufs)
@@ -290,6 +290,7 @@ int cab_build_grid(cab_ctx* ctx, float cell) {
 int cab_set_shard(cab_ctx* ctx, int32_t rank, int32_t world) {
   if (!ctx) return CAB_ERR_ARG;
   if (world < 1 || rank < 0 || rank >= world) return fail(ctx, CAB_ERR_ARG, "bad shard %d/%d", rank, world);
+  if (ctx->shard_world != world) ctx->shard_splits.clear();
   ctx->shard_rank = rank;
   ctx->shard_world = world;
   return CAB_OK;

@@ -125,52 +125,99 @@ __global__ void __launch_bounds__(256) reorder_kernel(const float* __restrict__ 
   pos[i] = make_float4(p[0], p[1], p[2], 0.f);
 }
 
-// packets per row; rows are indexed globally over all domains
-__global__ void __launch_bounds__(256) row_packets_kernel(const Domain* __restrict__ domains, int n_domains,
-                                                          long long n_rows, const int* __restrict__ cell_start,
-                                                          int* __restrict__ rowpk) {
-  long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row > n_rows) return;
-  if (row == n_rows) {
-    rowpk[row] = 0;
-    return;
-  }
+constexpr int kSpanCap = 4;  // a packet never covers more than about this many cells along x
+
+__device__ __forceinline__ int domain_of_cell(const Domain* __restrict__ domains, int n_domains, long long c) {
   int lo = 0, hi = n_domains;
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;
-    if (domains[mid].row_base <= row) lo = mid; else hi = mid;
+    if (domains[mid].cell_base <= c) lo = mid; else hi = mid;
   }
-  const Domain dm = domains[lo];
-  long long c0 = dm.cell_base + (row - dm.row_base) * dm.nx;
-  int len = cell_start[c0 + dm.nx] - cell_start[c0];
-  rowpk[row] = (len + kWarp - 1) / kWarp;
+  return lo;
 }
 
-// one thread per packet: find its row by binary search over the per-row packet prefix
+// A segment is a maximal run of non-empty cells of one row.  Packets are cut inside segments, so a
+// packet never straddles an empty stretch of a row (a row that crosses two distant surfaces would
+// otherwise produce packets whose x window -- and candidate set -- spans everything in between).
+// One thread per cell; the thread of a segment's first cell measures it and sets its packet count.
+__global__ void __launch_bounds__(256) segment_kernel(const Domain* __restrict__ domains, int n_domains,
+                                                      long long n_cells, const int* __restrict__ cell_start,
+                                                      int* __restrict__ segpk, int* __restrict__ seglen) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n_cells) return;
+  int npk = 0, len = 0;
+  if (c < n_cells && cell_start[c + 1] > cell_start[c]) {
+    const Domain dm = domains[domain_of_cell(domains, n_domains, c)];
+    const int cx = (int)((c - dm.cell_base) % dm.nx);
+    if (cx == 0 || cell_start[c] == cell_start[c - 1]) {  // previous cell of the row is empty
+      len = 1;
+      while (cx + len < dm.nx && cell_start[c + len + 1] > cell_start[c + len]) ++len;
+      const int pts = cell_start[c + len] - cell_start[c];
+      npk = max((pts + kWarp - 1) / kWarp, (len + kSpanCap - 1) / kSpanCap);
+      npk = min(npk, pts);
+    }
+  }
+  segpk[c] = npk;
+  seglen[c] = len;
+}
+
+// one thread per packet: find its segment by binary search over the per-cell packet prefix
 __global__ void __launch_bounds__(256) fill_packets_kernel(const Domain* __restrict__ domains, int n_domains,
-                                                           long long n_rows, const int* __restrict__ cell_start,
-                                                           const int* __restrict__ packet_base, int n_packets,
+                                                           long long n_cells, const int* __restrict__ cell_start,
+                                                           const int* __restrict__ packet_base,
+                                                           const int* __restrict__ seglen, int n_packets,
                                                            Packet* __restrict__ packets) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_packets) return;
-  long long rlo = 0, rhi = n_rows;  // largest row with packet_base[row] <= p
-  while (rhi - rlo > 1) {
-    const long long mid = (rlo + rhi) >> 1;
-    if (packet_base[mid] <= p) rlo = mid; else rhi = mid;
-  }
-  const long long row = rlo;
-  int lo = 0, hi = n_domains;
+  long long lo = 0, hi = n_cells;  // largest cell with packet_base[cell] <= p: the segment's first cell
   while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (domains[mid].row_base <= row) lo = mid; else hi = mid;
+    const long long mid = (lo + hi) >> 1;
+    if (packet_base[mid] <= p) lo = mid; else hi = mid;
   }
-  const Domain dm = domains[lo];
-  const long long c0 = dm.cell_base + (row - dm.row_base) * dm.nx;
+  const long long c0 = lo;
+  const int d = domain_of_cell(domains, n_domains, c0);
+  const Domain dm = domains[d];
   const int start = cell_start[c0];
-  const long long len = cell_start[c0 + dm.nx] - start;
-  const int pb = packet_base[row], npk = packet_base[row + 1] - pb, k = p - pb;
-  const int a = start + (int)(k * len / npk), b = start + (int)((k + 1) * len / npk);
-  packets[p] = Packet{a, b - a, (int)(row - dm.row_base), lo};
+  const long long pts = cell_start[c0 + seglen[c0]] - start;
+  const int pb = packet_base[c0], npk = packet_base[c0 + 1] - pb, k = p - pb;
+  const int a = start + (int)(k * pts / npk), b = start + (int)((k + 1) * pts / npk);
+  packets[p] = Packet{a, b - a, (int)((c0 - dm.cell_base) / dm.nx), d};
+}
+
+// cost model of a packet for the multi-GPU split: the candidates its queries will be tested against
+__global__ void __launch_bounds__(256) packet_cost_kernel(const Domain* __restrict__ domains, const Packet* __restrict__ packets,
+                                                          int n_packets, const float4* __restrict__ pos,
+                                                          const int* __restrict__ cell_start, float inv_cell,
+                                                          long long* __restrict__ cost) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_packets) return;
+  const Packet pk = packets[p];
+  const Domain dm = domains[pk.domain];
+  const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
+  const int cxlo = max((xfine_coord(pos[pk.start].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift) - 1, 0);
+  const int cxhi = min((xfine_coord(pos[pk.start + pk.count - 1].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift) + 1, dm.nx - 1);
+  long long c = 0;
+  for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1); ++z)
+    for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1); ++y) {
+      const long long b = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
+      c += cell_start[b + cxhi + 1] - cell_start[b + cxlo];
+    }
+  cost[p] = c + 64;  // + a constant per packet (setup, fit, eigen-solve)
+}
+
+// split[g] = first packet whose inclusive cost prefix reaches g/world of the total
+__global__ void split_kernel(const long long* __restrict__ cum, int n_packets, int world, int* __restrict__ split) {
+  const int g = threadIdx.x;
+  if (g > world) return;
+  if (g == 0) { split[0] = 0; return; }
+  if (g == world) { split[world] = n_packets; return; }
+  const long long target = cum[n_packets - 1] / world * g;
+  int lo = 0, hi = n_packets;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cum[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  split[g] = lo;
 }
 
 }  // namespace
@@ -354,23 +401,48 @@ int build_grid(cab_ctx* ctx, float cell) {
   ctx->tm.kernel_launches += 2;
 
   // ---- packets ------------------------------------------------------------------------
-  if (int rc = reserve(ctx, ctx->b_rowpk, (size_t)(rows + 1) * 4 * 2)) return rc;
-  int* rowpk = (int*)ctx->b_rowpk.p;
-  int* packet_base = rowpk + (rows + 1);
-  row_packets_kernel<<<(unsigned)((rows + 1 + 255) / 256), 256, 0, st>>>((const Domain*)ctx->b_domains.p, nd, rows,
-                                                                        (const int*)ctx->b_cellstart.p, rowpk);
+  if (int rc = reserve(ctx, ctx->b_rowpk, ncell1 * 4 * 3)) return rc;
+  int* segpk = (int*)ctx->b_rowpk.p;
+  int* packet_base = segpk + ncell1;
+  int* seglen = packet_base + ncell1;
+  segment_kernel<<<(unsigned)((ncell1 + 255) / 256), 256, 0, st>>>((const Domain*)ctx->b_domains.p, nd, cells,
+                                                                  (const int*)ctx->b_cellstart.p, segpk, seglen);
   CAB_LAUNCH_CHECK(ctx);
-  CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_bytes, rowpk, packet_base, (int)(rows + 1), st));
+  CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_bytes, segpk, packet_base, (int)ncell1, st));
   ctx->tm.kernel_launches += 2;
-  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, packet_base + rows, 4, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, packet_base + cells, 4, cudaMemcpyDeviceToHost, st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->n_packets = *(const int*)ctx->h_pin;
   if (int rc = reserve(ctx, ctx->b_packets, (size_t)std::max(ctx->n_packets, 1) * sizeof(Packet))) return rc;
   if (ctx->n_packets > 0) {
     fill_packets_kernel<<<(unsigned)((ctx->n_packets + 255) / 256), 256, 0, st>>>(
-        (const Domain*)ctx->b_domains.p, nd, rows, (const int*)ctx->b_cellstart.p, packet_base, ctx->n_packets,
+        (const Domain*)ctx->b_domains.p, nd, cells, (const int*)ctx->b_cellstart.p, packet_base, seglen, ctx->n_packets,
         (Packet*)ctx->b_packets.p);
     CAB_LAUNCH_CHECK(ctx);
+  }
+  // ---- cost-balanced shard boundaries (multi-GPU only) -------------------------------------
+  ctx->shard_splits.clear();
+  if (ctx->shard_world > 1 && ctx->n_packets > 0) {
+    const int np = ctx->n_packets, w = ctx->shard_world;
+    if (int rc = reserve(ctx, ctx->b_pcost, (size_t)np * 16 + (w + 1) * 4 + 64)) return rc;
+    long long* cost = (long long*)ctx->b_pcost.p;
+    long long* cum = cost + np;
+    int* split = (int*)(cum + np);
+    size_t tmp_cost = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tmp_cost, (const long long*)nullptr, (long long*)nullptr, np, st);
+    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_cost + 16)) return rc;
+    packet_cost_kernel<<<(np + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, np,
+                                                         (const float4*)ctx->b_pos.p, (const int*)ctx->b_cellstart.p,
+                                                         ctx->inv_cell, cost);
+    CAB_LAUNCH_CHECK(ctx);
+    CAB_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->b_cubtmp.p, tmp_cost, cost, cum, np, st));
+    split_kernel<<<1, 64, 0, st>>>(cum, np, w, split);
+    CAB_LAUNCH_CHECK(ctx);
+    ctx->tm.kernel_launches += 2;
+    if (w + 1 > 64) return fail(ctx, CAB_ERR_ARG, "cab_set_shard: world > 63 not supported");
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, split, (w + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CAB_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->shard_splits.assign((const int*)ctx->h_pin, (const int*)ctx->h_pin + w + 1);
   }
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -398,6 +470,11 @@ GridView grid_view(const cab_ctx* ctx) {
 }
 
 void packet_range(const cab_ctx* ctx, int* p0, int* p1) {
+  if ((int)ctx->shard_splits.size() == ctx->shard_world + 1) {
+    *p0 = ctx->shard_splits[ctx->shard_rank];
+    *p1 = ctx->shard_splits[ctx->shard_rank + 1];
+    return;
+  }
   int64_t P = ctx->n_packets;
   *p0 = (int)(P * ctx->shard_rank / ctx->shard_world);
   *p1 = (int)(P * (ctx->shard_rank + 1) / ctx->shard_world);
