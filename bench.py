@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--workload", default="normals_rsd", choices=["normals_rsd", "grsd"],
                     help="normals_rsd: the headline C4 metric; grsd: config C3, 512 clusters, GRSD clouds/s")
     ap.add_argument("--clusters", type=int, default=512)
+    ap.add_argument("--gather", action="store_true", help="N>1: also all-gather the results into every rank's HBM")
     return ap.parse_args()
 
 
@@ -311,7 +312,7 @@ def main():
         shard.exchange_slices(buf, ranges)
         torch.cuda.synchronize()
 
-    stage_s = {"build": 0.0, "normals": 0.0, "exchange_normals": 0.0, "rsd": 0.0, "exchange_rsd": 0.0}
+    stage_s = {"build": 0.0, "normals": 0.0, "unused": 0.0, "rsd": 0.0, "gather": 0.0}
 
     def step():
         t0 = time.perf_counter()
@@ -320,12 +321,11 @@ def main():
         t1 = time.perf_counter()
         ctx.normals(RADIUS, download=False)
         t2 = time.perf_counter()
-        if world > 1:
-            exchange(cab.BUF_NRM_SORTED, 4)
-        t3 = time.perf_counter()
+        t3 = time.perf_counter()  # no exchange between the passes: halo normals are recomputed locally
         ctx.rsd(RADIUS, ndiv=NDIV, plane_radius=PLANE_RADIUS, download=False)
         t4 = time.perf_counter()
-        if world > 1:
+        if world > 1 and args.gather:  # optional: every rank ends up with all results in HBM
+            exchange(cab.BUF_NRM_SORTED, 4)
             exchange(cab.BUF_RSD_SORTED, 2)
         t5 = time.perf_counter()
         for k, v in zip(stage_s, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
@@ -417,6 +417,7 @@ def main():
         h_n4 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
         h_rmin = torch.empty(n, dtype=torch.float32).pin_memory()
         h_rmax = torch.empty(n, dtype=torch.float32).pin_memory()
+        h_idx = torch.empty(n, dtype=torch.int32).pin_memory()
         L = cab.lib()
         import ctypes as C
 
@@ -428,12 +429,13 @@ def main():
             ctx.n = n
             ctx.build_grid(RADIUS)
             ctx.normals(RADIUS, download=False)
-            if world > 1:
-                exchange(cab.BUF_NRM_SORTED, 4)
             ctx.rsd(RADIUS, ndiv=NDIV, plane_radius=PLANE_RADIUS, download=False)
-            if world > 1:
-                exchange(cab.BUF_RSD_SORTED, 2)
-            ctx._check(L.cab_download(ctx._h, fp(h_n4), fp(h_rmin), fp(h_rmax)), "cab_download")
+            if world == 1:
+                ctx._check(L.cab_download(ctx._h, fp(h_n4), fp(h_rmin), fp(h_rmax)), "cab_download")
+            else:  # each rank returns its own slice (sorted order) plus the input indices it belongs to
+                b, e = ctx.shard_range()
+                ctx._check(L.cab_download_sorted(ctx._h, C.c_int64(b), C.c_int64(e), fp(h_n4), fp(h_rmin),
+                                                 C.cast(h_idx.data_ptr(), C.POINTER(C.c_int32))), "cab_download_sorted")
 
         e2e_steps = max(2, min(args.steps, 5))
         e2e_step()
@@ -450,8 +452,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": n / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(n * 12),
-               "d2h_bytes_per_step": int(n * 24), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
-               "path": "cab_upload_cloud -> cab_build_grid -> cab_normals -> cab_rsd -> cab_download, pinned host buffers"}
+               "d2h_bytes_per_step": int(n * 24) if world == 1 else int(n * 28), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+               "path": ("cab_upload_cloud -> cab_build_grid -> cab_normals -> cab_rsd -> cab_download, pinned host buffers" if world == 1 else
+                        "per rank: cab_upload_cloud (full cloud) -> cab_build_grid -> cab_normals -> cab_rsd -> cab_download_sorted "
+                        "(own slice + input indices), pinned host buffers; h2d bytes are per rank, d2h bytes summed over ranks")}
 
     # ---- CPU baseline (oracle port) on rank 0 at N = 1 ---------------------------------------
     cpu = None
@@ -469,7 +473,7 @@ def main():
             "config": {"workload": "C4 20M-point synthetic room, normals+RSD r=2cm, query-sharded", "points": n,
                        "radius_m": RADIUS, "distance_div": NDIV, "plane_radius": PLANE_RADIUS, "max_nn": "unlimited",
                        "mean_neighbours": kbar, "candidates_tested_per_query": prof["candidate_sum"] / max(1.0, n / world), "l2": "inputs_larger_than_l2 (pos+normals 640 MB vs 126 MB L2)",
-                       "parallelism": f"query-shard x{world}, grid replicated, NCCL broadcast of shard results",
+                       "parallelism": (f"query-shard x{world}, cloud+grid replicated, halo normals recomputed locally, results stay sharded" + (" then all-gathered (NCCL)" if args.gather else "")) if world > 1 else "single GPU",
                        "mode": "exact-fp64" if args.exact else "fast-fp32"},
             "phases_ms": {"build": build_ms, "normals": nrm_ms, "rsd": rsd_ms},
             "per_rank_stage_ms": per_rank,

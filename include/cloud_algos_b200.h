@@ -133,6 +133,12 @@ void* cab_stream(cab_ctx* ctx); /* cudaStream_t all work of this context is enqu
 /* Copy device results (sorted order) to host arrays in input order. Any pointer may be NULL. */
 int cab_download(cab_ctx* ctx, float* nxyz_curv, float* r_min, float* r_max);
 
+/* Copy the sorted-order slice [begin, end) of the results to host: normals (4 floats per point),
+ * radii (2 floats: r_min, r_max) and the sorted-position -> input-index map.  Any pointer may be
+ * NULL.  A rank of a sharded run downloads its own cab_shard_range this way. */
+int cab_download_sorted(cab_ctx* ctx, int64_t begin, int64_t end, float* nxyz_curv, float* rmin_rmax,
+                        int32_t* input_index);
+
 int cab_profile(const cab_ctx* ctx, cab_timings* out);
 int cab_version(void);
 

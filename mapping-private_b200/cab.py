@@ -23,7 +23,7 @@ EXPORTS = [
     "cab_create", "cab_destroy", "cab_last_error", "cab_upload_cloud", "cab_upload_clusters",
     "cab_set_cloud_device", "cab_build_grid", "cab_set_shard", "cab_shard_range", "cab_normals",
     "cab_set_normals", "cab_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels",
-    "cab_device_ptr", "cab_stream", "cab_download", "cab_profile", "cab_version",
+    "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_profile", "cab_version",
 ]
 
 
@@ -170,6 +170,16 @@ class Context:
         rmax = np.empty(self.n, np.float32) if rsd else None
         self._check(self._L.cab_download(self._h, _fp(n4), _fp(rmin), _fp(rmax)), "cab_download")
         return n4, rmin, rmax
+
+    def download_sorted(self, begin: int, end: int, normals: bool = True, rsd: bool = True):
+        """Sorted-order slice [begin, end): (n4 (m,4) | None, radii (m,2) | None, input_index (m,))."""
+        m = end - begin
+        n4 = np.empty((m, 4), np.float32) if normals else None
+        rr = np.empty((m, 2), np.float32) if rsd else None
+        idx = np.empty(m, np.int32)
+        self._check(self._L.cab_download_sorted(self._h, C.c_int64(begin), C.c_int64(end), _fp(n4), _fp(rr), _ip(idx)),
+                    "cab_download_sorted")
+        return n4, rr, idx
 
     def neighbors(self, r: float, q0: int, q1: int, max_nn: int = 0):
         """Neighbour sets of queries [q0, q1): (offsets int64, idx int32, d2 float32), unsorted."""

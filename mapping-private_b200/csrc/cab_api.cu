@@ -252,7 +252,7 @@ void cab_destroy(cab_ctx* ctx) {
                     &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
                     &ctx->b_cellcnt, &ctx->b_cellstart, &ctx->b_rowpk, &ctx->b_packets, &ctx->b_nrm, &ctx->b_nrm_in,
                     &ctx->b_rsd, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
-                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
+                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_halo_list, &ctx->b_rowflag, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
                     &ctx->g_vvals[1], &ctx->g_cent, &ctx->g_vcount, &ctx->g_vrad, &ctx->g_vlabel, &ctx->g_voff,
                     &ctx->g_layout, &ctx->g_layoff, &ctx->g_vgrid, &ctx->g_hist, &ctx->g_vfirst};
   for (DevBuf* b : bufs)
@@ -363,6 +363,28 @@ int cab_download(cab_ctx* ctx, float* nxyz_curv, float* r_min, float* r_max) {
   if (!ctx) return CAB_ERR_ARG;
   CAB_CUDA(ctx, cudaSetDevice(ctx->device));
   return download_results(ctx, nxyz_curv, r_min, r_max);
+}
+
+int cab_download_sorted(cab_ctx* ctx, int64_t begin, int64_t end, float* nxyz_curv, float* rmin_rmax, int32_t* input_index) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (!ctx->have_grid) return fail(ctx, CAB_ERR_STATE, "cab_download_sorted: no grid");
+  if (begin < 0 || end < begin || end > ctx->n) return fail(ctx, CAB_ERR_ARG, "cab_download_sorted: bad range");
+  if (nxyz_curv && !ctx->have_normals) return fail(ctx, CAB_ERR_STATE, "no normals to download");
+  if (rmin_rmax && !ctx->have_rsd) return fail(ctx, CAB_ERR_STATE, "no RSD results to download");
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t m = (size_t)(end - begin);
+  cudaStream_t st = ctx->stream;
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+  if (m && nxyz_curv)
+    CAB_CUDA(ctx, cudaMemcpyAsync(nxyz_curv, (const float4*)ctx->b_nrm.p + begin, m * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  if (m && rmin_rmax)
+    CAB_CUDA(ctx, cudaMemcpyAsync(rmin_rmax, (const float2*)ctx->b_rsd.p + begin, m * sizeof(float2), cudaMemcpyDeviceToHost, st));
+  if (m && input_index)
+    CAB_CUDA(ctx, cudaMemcpyAsync(input_index, (const int*)ctx->b_perm.p + begin, m * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[6], ctx->ev[7]));
+  return CAB_OK;
 }
 
 int cab_profile(const cab_ctx* ctx, cab_timings* out) {

@@ -10,6 +10,8 @@
 //   packets   : <=32 consecutive sorted points of one row = the work unit of one warp
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 #include <cmath>
@@ -203,6 +205,46 @@ __global__ void __launch_bounds__(256) packet_cost_kernel(const Domain* __restri
       c += cell_start[b + cxhi + 1] - cell_start[b + cxlo];
     }
   cost[p] = c + 64;  // + a constant per packet (setup, fit, eigen-solve)
+}
+
+// cells touched by the shard's own packets
+__global__ void __launch_bounds__(256) mark_cells_kernel(const Domain* __restrict__ domains, const Packet* __restrict__ packets,
+                                                         int p0, int p1, const float4* __restrict__ pos, float inv_cell,
+                                                         unsigned char* __restrict__ cell_flag) {
+  const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= p1) return;
+  const Packet pk = packets[p];
+  const Domain dm = domains[pk.domain];
+  const int c0 = xfine_coord(pos[pk.start].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift;
+  const int c1 = xfine_coord(pos[pk.start + pk.count - 1].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift;
+  const long long base = dm.cell_base + (long long)pk.row_local * dm.nx;
+  for (int c = c0; c <= c1; ++c) cell_flag[base + c] = 1;
+}
+
+// A packet needs normals on this rank if it is the shard's own or touches a cell adjacent (3x3x3) to
+// a cell of the shard: every candidate of the shard's RSD pass then has a locally computed normal
+// and no exchange between the two passes is needed.
+__global__ void __launch_bounds__(256) flag_halo_kernel(const Domain* __restrict__ domains, const Packet* __restrict__ packets,
+                                                        int n_packets, int p0, int p1, const float4* __restrict__ pos,
+                                                        float inv_cell, const unsigned char* __restrict__ cell_flag,
+                                                        unsigned char* __restrict__ flag) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_packets) return;
+  unsigned char f = (p >= p0 && p < p1) ? 1 : 0;
+  if (!f) {
+    const Packet pk = packets[p];
+    const Domain dm = domains[pk.domain];
+    const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
+    const int c0 = max((xfine_coord(pos[pk.start].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift) - 1, 0);
+    const int c1 = min((xfine_coord(pos[pk.start + pk.count - 1].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift) + 1, dm.nx - 1);
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1) && !f; ++z)
+      for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1) && !f; ++y) {
+        const long long base = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
+        for (int c = c0; c <= c1; ++c)
+          if (cell_flag[base + c]) { f = 1; break; }
+      }
+  }
+  flag[p] = f;
 }
 
 // split[g] = first packet whose inclusive cost prefix reaches g/world of the total
@@ -422,6 +464,7 @@ int build_grid(cab_ctx* ctx, float cell) {
   }
   // ---- cost-balanced shard boundaries (multi-GPU only) -------------------------------------
   ctx->shard_splits.clear();
+  ctx->n_halo_packets = -1;
   if (ctx->shard_world > 1 && ctx->n_packets > 0) {
     const int np = ctx->n_packets, w = ctx->shard_world;
     if (int rc = reserve(ctx, ctx->b_pcost, (size_t)np * 16 + (w + 1) * 4 + 64)) return rc;
@@ -443,6 +486,32 @@ int build_grid(cab_ctx* ctx, float cell) {
     CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, split, (w + 1) * 4, cudaMemcpyDeviceToHost, st));
     CAB_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->shard_splits.assign((const int*)ctx->h_pin, (const int*)ctx->h_pin + w + 1);
+    // halo packet list for the normals pass
+    int p0, p1;
+    packet_range(ctx, &p0, &p1);
+    if (int rc = reserve(ctx, ctx->b_rowflag, (size_t)cells + (size_t)np + 64)) return rc;
+    if (int rc = reserve(ctx, ctx->b_halo_list, ((size_t)np + 4) * 4)) return rc;
+    unsigned char* cell_flag = (unsigned char*)ctx->b_rowflag.p;
+    unsigned char* pflag = cell_flag + cells;
+    int* list = (int*)ctx->b_halo_list.p;
+    CAB_CUDA(ctx, cudaMemsetAsync(cell_flag, 0, (size_t)cells, st));
+    if (p1 > p0) {
+      mark_cells_kernel<<<(p1 - p0 + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, p0, p1,
+                                                              (const float4*)ctx->b_pos.p, ctx->inv_cell, cell_flag);
+      CAB_LAUNCH_CHECK(ctx);
+    }
+    flag_halo_kernel<<<(np + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, np, p0, p1,
+                                                       (const float4*)ctx->b_pos.p, ctx->inv_cell, cell_flag, pflag);
+    CAB_LAUNCH_CHECK(ctx);
+    size_t tmp_sel = 0;
+    thrust::counting_iterator<int> ids(0);
+    cub::DeviceSelect::Flagged(nullptr, tmp_sel, ids, pflag, list, list + np, np, st);
+    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_sel + 16)) return rc;
+    CAB_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_cubtmp.p, tmp_sel, ids, pflag, list, list + np, np, st));
+    ctx->tm.kernel_launches += 2;
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, list + np, 4, cudaMemcpyDeviceToHost, st));
+    CAB_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->n_halo_packets = *(const int*)ctx->h_pin;
   }
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));

@@ -101,12 +101,13 @@ struct cab_ctx {
   int64_t n_rows = 0, n_cells = 0;
   int n_packets = 0;
   int shard_rank = 0, shard_world = 1;
+  int n_halo_packets = -1;          // >= 0: normals run over b_halo_list (own + halo packets)
   std::vector<int> shard_splits;   // world + 1 packet indices, cost balanced (empty: equal counts)
 
   // device arena (grow-only)
   cab::DevBuf b_xyz, b_domoff, b_domid, b_bounds, b_domains, b_keys[2], b_vals[2], b_cubtmp, b_pos,
       b_perm, b_cellcnt, b_cellstart, b_rowpk, b_packets, b_nrm, b_nrm_in, b_rsd, b_kcount, b_stats,
-      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost;
+      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost, b_halo_list, b_rowflag;
   // pinned staging
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;

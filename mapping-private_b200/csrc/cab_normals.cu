@@ -52,6 +52,8 @@ __device__ __forceinline__ void smallest_eigen(T a00, T a01, T a02, T a11, T a12
 struct NormalsArgs {
   GridView g;
   int p0, p1;
+  const int* list;        // optional packet list (own + halo packets of a shard); null: [p0, p1)
+  const int* list_count;
   float r, r2;
   float vpx, vpy, vpz;
   float4* nrm;              // sorted order
@@ -88,8 +90,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GridView& g = a.g;
   for (;;) {
-  const int pid = a.p0 + next_packet(a.stats, lane);
-  if (pid >= a.p1) break;
+  const int wi = next_packet(a.stats, lane);
+  if (wi >= (a.list ? *a.list_count : a.p1 - a.p0)) break;
+  const int pid = a.list ? a.list[wi] : a.p0 + wi;
   ChunkTile* tile = &tiles[warp];
   const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
   const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
@@ -242,6 +245,10 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3]) {
   NormalsArgs a{};
   a.g = grid_view(ctx);
   packet_range(ctx, &a.p0, &a.p1);
+  if (ctx->n_halo_packets >= 0) {  // multi-GPU: own packets plus the rows around them
+    a.list = (const int*)ctx->b_halo_list.p;
+    a.list_count = a.list + ctx->n_packets;
+  }
   a.r = r;
   a.r2 = r * r;
   a.vpx = vp ? vp[0] : 0.f;
@@ -252,7 +259,7 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3]) {
   a.thr_d2 = use_thr ? (const float*)ctx->b_thr_d2.p : nullptr;
   a.thr_idx = use_thr ? (const int*)ctx->b_thr_idx.p : nullptr;
   a.stats = (unsigned long long*)ctx->b_stats.p;
-  const int np = a.p1 - a.p0;
+  const int np = ctx->n_halo_packets >= 0 ? ctx->n_halo_packets : a.p1 - a.p0;
   if (np > 0) {
     const dim3 blk(kWarpsPerBlock * kWarp);
     auto grid_for = [&](const void* fn) {

@@ -258,3 +258,34 @@ def test_properties_at_full_size(ctx):
     ang = _angle(n4[perm][good[perm], :3], n4b[good[perm], :3])
     assert np.percentile(ang, 99.9) < 1e-4
     assert np.mean(np.abs(rminb - rmin[perm]) / rmin[perm] > 1e-4) < 2e-3
+
+
+def test_sharded_run_equals_unsharded(ctx):
+    """Query sharding (cab_set_shard): every shard's own slice equals the single-GPU result bit for bit;
+    the shards are run one after the other on this GPU.  Normals of the rows around a shard are
+    recomputed locally (halo), so no exchange between the passes is needed."""
+    pts = synth.tabletop(60_000, noise_sigma=0.0002)
+    r = 0.02
+    ctx.set_shard(0, 1)
+    ctx.upload(pts)
+    ctx.build_grid(r)
+    n4 = ctx.normals(r)
+    rmin, rmax = ctx.rsd(r)
+    seen = np.zeros(pts.shape[0], bool)
+    W = 3
+    try:
+        for g in range(W):
+            ctx.set_shard(g, W)
+            ctx.upload(pts)
+            ctx.build_grid(r)
+            ctx.normals(r, download=False)
+            ctx.rsd(r, download=False)
+            b, e = ctx.shard_range()
+            s4, srr, idx = ctx.download_sorted(b, e)
+            assert not seen[idx].any()
+            seen[idx] = True
+            assert np.array_equal(s4.view(np.uint32), n4[idx].view(np.uint32))
+            assert np.array_equal(srr[:, 0], rmin[idx]) and np.array_equal(srr[:, 1], rmax[idx])
+    finally:
+        ctx.set_shard(0, 1)
+    assert seen.all()
