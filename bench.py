@@ -415,7 +415,7 @@ def main():
     if not args.no_e2e:
         h_xyz = torch.from_numpy(pts).pin_memory()
         h_n4 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
-        h_rmin = torch.empty(n, dtype=torch.float32).pin_memory()
+        h_rmin = torch.empty(n if world == 1 else 2 * n, dtype=torch.float32).pin_memory()
         h_rmax = torch.empty(n, dtype=torch.float32).pin_memory()
         h_idx = torch.empty(n, dtype=torch.int32).pin_memory()
         L = cab.lib()
@@ -424,18 +424,18 @@ def main():
         def fp(t):
             return C.cast(t.data_ptr(), C.POINTER(C.c_float))
 
+        vp0 = (C.c_float * 3)(0.0, 0.0, 0.0)
+
         def e2e_step():
             ctx._check(L.cab_upload_cloud(ctx._h, fp(h_xyz), C.c_int64(n), C.c_int32(3)), "cab_upload_cloud")
             ctx.n = n
             ctx.build_grid(RADIUS)
-            ctx.normals(RADIUS, download=False)
-            ctx.rsd(RADIUS, ndiv=NDIV, plane_radius=PLANE_RADIUS, download=False)
-            if world == 1:
-                ctx._check(L.cab_download(ctx._h, fp(h_n4), fp(h_rmin), fp(h_rmax)), "cab_download")
-            else:  # each rank returns its own slice (sorted order) plus the input indices it belongs to
-                b, e = ctx.shard_range()
-                ctx._check(L.cab_download_sorted(ctx._h, C.c_int64(b), C.c_int64(e), fp(h_n4), fp(h_rmin),
-                                                 C.cast(h_idx.data_ptr(), C.POINTER(C.c_int32))), "cab_download_sorted")
+            # both passes in one call: the normals leave on the copy stream while the RSD kernel runs.
+            # world > 1: each rank returns its own slice (sorted order) plus the input indices it belongs to
+            ctx._check(L.cab_normals_rsd(ctx._h, C.c_double(RADIUS), C.c_int32(0), vp0, C.c_int32(0), C.c_int32(NDIV),
+                                         C.c_double(PLANE_RADIUS), C.c_int32(0), C.c_int32(0 if world == 1 else 1), fp(h_n4),
+                                         fp(h_rmin), fp(h_rmax) if world == 1 else None,
+                                         C.cast(h_idx.data_ptr(), C.POINTER(C.c_int32)) if world > 1 else None), "cab_normals_rsd")
 
         e2e_steps = max(2, min(args.steps, 5))
         e2e_step()
@@ -453,8 +453,8 @@ def main():
             dt = float(t.item())
         e2e = {"value": n / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(n * 12),
                "d2h_bytes_per_step": int(n * 24) if world == 1 else int(n * 28), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
-               "path": ("cab_upload_cloud -> cab_build_grid -> cab_normals -> cab_rsd -> cab_download, pinned host buffers" if world == 1 else
-                        "per rank: cab_upload_cloud (full cloud) -> cab_build_grid -> cab_normals -> cab_rsd -> cab_download_sorted "
+               "path": ("cab_upload_cloud -> cab_build_grid -> cab_normals_rsd (normals D2H overlaps the RSD kernel), pinned host buffers" if world == 1 else
+                        "per rank: cab_upload_cloud (full cloud) -> cab_build_grid -> cab_normals_rsd, CAB_OUT_SHARD_SORTED "
                         "(own slice + input indices), pinned host buffers; h2d bytes are per rank, d2h bytes summed over ranks")}
 
     # ---- CPU baseline (oracle port) on rank 0 at N = 1 ---------------------------------------

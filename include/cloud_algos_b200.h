@@ -8,7 +8,7 @@
  * the reference tree).  There is no CPU fallback: every call fails with CAB_ERR_CUDA when no
  * sm_100a device is usable.
  *
- * Threading: a cab_ctx owns one CUDA stream and a grow-only device arena; a context must not
+ * Threading: a cab_ctx owns one CUDA stream (plus a copy stream used by cab_normals_rsd) and a grow-only device arena; a context must not
  * be used from two threads at once, different contexts are independent (the reference runs
  * each plugin instance on the single ros::spin() thread, cloud_algos.h:106-117).
  * Every call is synchronous: results are valid when it returns.
@@ -99,6 +99,21 @@ int cab_set_normals(cab_ctx* ctx, const float* nx, const float* ny, const float*
  * order, may be NULL. */
 int cab_rsd(cab_ctx* ctx, double r, int32_t max_nn, int32_t ndiv, double plane_radius,
             int32_t flags, float* r_min, float* r_max);
+
+/* ---- normals + RSD in one call --------------------------------------------------------
+ * The NormalEstimation -> LocalRadiusEstimation chain of sample_pipeline.yaml
+ * (cloud_algos/sample_pipeline.yaml; exampleRSD.cpp:50-93 runs the same two stages back to back)
+ * without the host round trip between the plugins: the normals are copied to the host on a second
+ * stream while the RSD kernel runs.  Same results as cab_normals((float)r) followed by cab_rsd(r).
+ * layout CAB_OUT_INPUT_ORDER: nxyz_curv n x 4, out_a = r_min[n], out_b = r_max[n] in input order
+ * (input_index unused).  layout CAB_OUT_SHARD_SORTED (multi-GPU): this context's cab_shard_range
+ * only, in sorted order: nxyz_curv m x 4, out_a = m x {r_min, r_max}, input_index[m] (out_b unused).
+ * Any output pointer may be NULL.  Host buffers should be page-locked for the overlap to happen. */
+#define CAB_OUT_INPUT_ORDER 0
+#define CAB_OUT_SHARD_SORTED 1
+int cab_normals_rsd(cab_ctx* ctx, double r, int32_t max_nn_normals, const float vp[3], int32_t max_nn_rsd,
+                    int32_t ndiv, double plane_radius, int32_t flags, int32_t layout, float* nxyz_curv,
+                    float* out_a, float* out_b, int32_t* input_index);
 
 /* ---- parity / debug ------------------------------------------------------------------
  * Neighbour index sets of queries [q0, q1) (input order) as the radius search returns them

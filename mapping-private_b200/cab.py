@@ -22,7 +22,7 @@ BUF_POS_SORTED, BUF_NRM_SORTED, BUF_RSD_SORTED, BUF_PERM = 0, 1, 2, 3
 EXPORTS = [
     "cab_create", "cab_destroy", "cab_last_error", "cab_upload_cloud", "cab_upload_clusters",
     "cab_set_cloud_device", "cab_build_grid", "cab_set_shard", "cab_shard_range", "cab_normals",
-    "cab_set_normals", "cab_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels",
+    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels",
     "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_profile", "cab_version",
 ]
 
@@ -163,6 +163,25 @@ class Context:
         self._check(self._L.cab_rsd(self._h, C.c_double(r), C.c_int32(max_nn), C.c_int32(ndiv), C.c_double(plane_radius),
                                     C.c_int32(flags), _fp(rmin), _fp(rmax)), "cab_rsd")
         return rmin, rmax
+
+    def normals_rsd(self, r: float, max_nn_normals: int = 0, vp=(0.0, 0.0, 0.0), max_nn_rsd: int = 0, ndiv: int = 10,
+                    plane_radius: float = 0.1, flags: int = 0, sorted_shard: bool = False):
+        """Both passes in one call (normals leave on the copy stream while RSD runs).
+        Input order: (n4, r_min, r_max); sorted_shard: (n4 (m,4), radii (m,2), input_index (m,))."""
+        v = np.asarray(vp, dtype=np.float32)
+        if sorted_shard:
+            b, e = self.shard_range()
+            n4 = np.empty((e - b, 4), np.float32)
+            a = np.empty((e - b, 2), np.float32)
+            bb, idx = None, np.empty(e - b, np.int32)
+        else:
+            n4 = np.empty((self.n, 4), np.float32)
+            a, bb, idx = np.empty(self.n, np.float32), np.empty(self.n, np.float32), None
+        self._check(self._L.cab_normals_rsd(self._h, C.c_double(r), C.c_int32(max_nn_normals), _fp(v), C.c_int32(max_nn_rsd),
+                                            C.c_int32(ndiv), C.c_double(plane_radius), C.c_int32(flags),
+                                            C.c_int32(1 if sorted_shard else 0), _fp(n4), _fp(a), _fp(bb), _ip(idx)),
+                    "cab_normals_rsd")
+        return (n4, a, idx) if sorted_shard else (n4, a, bb)
 
     def download(self, normals: bool = True, rsd: bool = True):
         n4 = np.empty((self.n, 4), np.float32) if normals else None

@@ -234,7 +234,13 @@ int cab_create(const cab_config* cfg, cab_ctx** out) {
     delete ctx;
     return fail(nullptr, CAB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
+  if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return fail(nullptr, CAB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming);
   if (reserve_pinned(ctx, 1 << 16) != CAB_OK) {
     g_create_err = ctx->err;
     cab_destroy(ctx);
@@ -248,6 +254,7 @@ void cab_destroy(cab_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->b_xyz, &ctx->b_domoff, &ctx->b_domid, &ctx->b_bounds, &ctx->b_domains, &ctx->b_keys[0],
                     &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
                     &ctx->b_cellcnt, &ctx->b_cellstart, &ctx->b_rowpk, &ctx->b_packets, &ctx->b_nrm, &ctx->b_nrm_in,
@@ -260,6 +267,8 @@ void cab_destroy(cab_ctx* ctx) {
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -384,6 +393,72 @@ int cab_download_sorted(cab_ctx* ctx, int64_t begin, int64_t end, float* nxyz_cu
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[6], ctx->ev[7]));
+  return CAB_OK;
+}
+
+int cab_normals_rsd(cab_ctx* ctx, double r, int32_t max_nn_normals, const float vp[3], int32_t max_nn_rsd, int32_t ndiv,
+                    double plane_radius, int32_t flags, int32_t layout, float* nxyz_curv, float* out_a, float* out_b,
+                    int32_t* input_index) {
+  if (!ctx) return CAB_ERR_ARG;
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (layout != CAB_OUT_INPUT_ORDER && layout != CAB_OUT_SHARD_SORTED)
+    return fail(ctx, CAB_ERR_ARG, "cab_normals_rsd: unknown output layout %d", layout);
+  if (layout == CAB_OUT_INPUT_ORDER && (out_a == nullptr) != (out_b == nullptr))
+    return fail(ctx, CAB_ERR_ARG, "cab_normals_rsd: r_min and r_max must be given together");
+  const int n = (int)ctx->n;
+  cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+  // pass 1 on the compute stream
+  if (int rc = run_normals(ctx, (float)r, max_nn_normals, vp)) return rc;
+  int64_t b = 0, e = 0;
+  if (layout == CAB_OUT_SHARD_SORTED)
+    if (int rc = cab_shard_range(ctx, &b, &e)) return rc;
+  const size_t m = (size_t)(e - b);
+  // the normals leave on the copy stream while pass 2 runs
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+  if (nxyz_curv && n > 0) {
+    if (layout == CAB_OUT_INPUT_ORDER) {
+      if (int rc = reserve(ctx, ctx->b_out4, (size_t)n * sizeof(float4))) return rc;
+      unpermute_kernel<<<(n + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, 0, n, (const float4*)ctx->b_nrm.p, nullptr,
+                                                        (float4*)ctx->b_out4.p, nullptr, nullptr);
+      CAB_LAUNCH_CHECK(ctx);
+      CAB_CUDA(ctx, cudaEventRecord(ctx->ev_ready, st));
+      CAB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_ready, 0));
+      CAB_CUDA(ctx, cudaMemcpyAsync(nxyz_curv, ctx->b_out4.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, cs));
+    } else if (m) {
+      CAB_CUDA(ctx, cudaEventRecord(ctx->ev_ready, st));
+      CAB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_ready, 0));
+      CAB_CUDA(ctx, cudaMemcpyAsync(nxyz_curv, (const float4*)ctx->b_nrm.p + b, m * sizeof(float4), cudaMemcpyDeviceToHost, cs));
+    }
+  }
+  if (layout == CAB_OUT_SHARD_SORTED && input_index && m)
+    CAB_CUDA(ctx, cudaMemcpyAsync(input_index, (const int*)ctx->b_perm.p + b, m * sizeof(int), cudaMemcpyDeviceToHost, cs));
+  // pass 2 (run_rsd synchronises the compute stream only)
+  int rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags);
+  if (rc == CAB_OK && out_a && n > 0) {
+    if (layout == CAB_OUT_INPUT_ORDER) {
+      rc = reserve(ctx, ctx->b_out1a, (size_t)n * sizeof(float));
+      if (rc == CAB_OK) rc = reserve(ctx, ctx->b_out1b, (size_t)n * sizeof(float));
+      if (rc == CAB_OK) {
+        unpermute_kernel<<<(n + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, 0, n, nullptr, (const float2*)ctx->b_rsd.p,
+                                                          nullptr, (float*)ctx->b_out1a.p, (float*)ctx->b_out1b.p);
+        ctx->tm.kernel_launches++;
+        cudaMemcpyAsync(out_a, ctx->b_out1a.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_b, ctx->b_out1b.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st);
+      }
+    } else if (m) {
+      cudaMemcpyAsync(out_a, (const float2*)ctx->b_rsd.p + b, m * sizeof(float2), cudaMemcpyDeviceToHost, st);
+    }
+  }
+  cudaEventRecord(ctx->ev[7], st);
+  // both streams must drain before the host buffers are valid (also on the error path: the copy
+  // stream may still be writing nxyz_curv)
+  cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(st), e3 = cudaGetLastError();
+  if (rc != CAB_OK) return rc;
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+    return fail(ctx, CAB_ERR_CUDA, "cab_normals_rsd: %s",
+                cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[6], ctx->ev[7]));
+  ctx->tm.d2h_ms -= ctx->tm.rsd_ms;  // copy time left exposed around pass 2
   return CAB_OK;
 }
 

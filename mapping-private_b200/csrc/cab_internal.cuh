@@ -81,7 +81,9 @@ struct cab_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // device->host copies that overlap the next kernel (cab_normals_rsd)
   cudaEvent_t ev[8]{};
+  cudaEvent_t ev_ready = nullptr;      // results staged for the copy stream
   std::string err;
   cab_timings tm{};
 

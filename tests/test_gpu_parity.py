@@ -289,3 +289,39 @@ def test_sharded_run_equals_unsharded(ctx):
     finally:
         ctx.set_shard(0, 1)
     assert seen.all()
+
+
+def test_fused_normals_rsd_equals_two_calls(ctx):
+    """cab_normals_rsd (normals copied out on the second stream while RSD runs) returns the bits of
+    cab_normals followed by cab_rsd, in input order and as a shard's sorted slice."""
+    pts = synth.tabletop(50_000, noise_sigma=0.0003)
+    pts[17] = np.nan  # an invalid point keeps its index
+    r = 0.02
+    ctx.set_shard(0, 1)
+    ctx.upload(pts)
+    ctx.build_grid(r)
+    n4 = ctx.normals(r)
+    rmin, rmax = ctx.rsd(r)
+    f4, fmin, fmax = ctx.normals_rsd(r)
+    assert np.array_equal(f4.view(np.uint32), n4.view(np.uint32))
+    assert np.array_equal(fmin.view(np.uint32), rmin.view(np.uint32))
+    assert np.array_equal(fmax.view(np.uint32), rmax.view(np.uint32))
+    # max_nn on both passes
+    n4t = ctx.normals(r, max_nn=40)
+    rmint, rmaxt = ctx.rsd(r, max_nn=75)
+    t4, tmin, tmax = ctx.normals_rsd(r, max_nn_normals=40, max_nn_rsd=75)
+    assert np.array_equal(t4.view(np.uint32), n4t.view(np.uint32))
+    assert np.array_equal(tmin, rmint) and np.array_equal(tmax, rmaxt)
+    try:
+        seen = np.zeros(pts.shape[0], bool)
+        for g in range(2):
+            ctx.set_shard(g, 2)
+            ctx.upload(pts)
+            ctx.build_grid(r)
+            s4, srr, idx = ctx.normals_rsd(r, sorted_shard=True)
+            seen[idx] = True
+            assert np.array_equal(s4.view(np.uint32), n4[idx].view(np.uint32))
+            assert np.array_equal(srr[:, 0], rmin[idx]) and np.array_equal(srr[:, 1], rmax[idx])
+        assert seen.sum() == pts.shape[0] - 1  # the NaN point belongs to no shard slice
+    finally:
+        ctx.set_shard(0, 1)
