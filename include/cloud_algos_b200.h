@@ -138,6 +138,49 @@ int cab_grsd_batch(cab_ctx* ctx, const float* xyz, int32_t stride, const int32_t
 int64_t cab_grsd_voxels(cab_ctx* ctx, int64_t* vox_offsets, float* centroids_xyz, float* r_min,
                         float* r_max, int32_t* labels, int64_t cap);
 
+/* The other transition signatures of grsd_colorCHLAC_tools.hpp, computed from the voxels, labels and
+ * leaf layouts the last cab_grsd_batch left on the device:
+ *   CAB_SIG_GRSD21       extractGRSDSignature21      (:131-294)  21 bins
+ *   CAB_SIG_GRSD325      extractGRSDSignature325     (:305-451)  325 bins, rotation variant
+ *   CAB_SIG_PLUSGRSD110  extractPlusGRSDSignature110 (:462-668)  110 bins, voxel-normal angle
+ * subdivision_size > 0 is the sliding-box mode (:140-161, :233-246; used by
+ * color_voxel_recognition_2/.../search_new.h:62-76): one histogram per box of subdivision_size^3
+ * voxels, boxes starting at voxel offset (off_x, off_y, off_z) of every cluster's grid; a cluster
+ * whose grid is smaller than the offsets yields no histogram (the reference returns Zero, :150-153).
+ * hist_offsets: nclusters + 1 (first histogram of every cluster); subdiv_b: nclusters x 3 boxes per
+ * axis; hist: total x dim int32 counts (the reference emits them as floats, optionally times
+ * NORMALIZE_GRSD).  Any pointer may be NULL; returns the total number of histograms or < 0. */
+#define CAB_SIG_GRSD21 0
+#define CAB_SIG_GRSD325 1
+#define CAB_SIG_PLUSGRSD110 2
+int64_t cab_grsd_signatures(cab_ctx* ctx, int32_t kind, int32_t subdivision_size, int32_t off_x, int32_t off_y,
+                            int32_t off_z, int64_t* hist_offsets, int32_t* subdiv_b, int32_t* hist, int64_t cap);
+
+/* ---- SVM classification of the signatures ---------------------------------------------
+ * The consumer of GRSD in the reference pipeline (table_memory_grsd.cpp:1000-1020): replaces, per
+ * feature vector, scaleFeature + svm_predict of cloud_algos::SVMClassification::process
+ * (svm_classification.cpp:134-155, svm_classification.h:68-86) for a libsvm C-SVC / RBF model
+ * (cloud_algos/svm/grsd_ijrr.model and the like).  The caller parses the model file
+ * (svm_load_model) and the svm-scale range file (parseScaleParameterFile, svm_classification.h:129-185)
+ * and hands over plain arrays:
+ *   labels[nr_class], nr_sv[nr_class], rho[nr_class*(nr_class-1)/2] in libsvm's pair order,
+ *   sv_coef[(nr_class-1) x total_sv], sv[total_sv x dim] dense (omitted sparse entries = 0).
+ * fmin == fmax == NULL switches scaling off (scale_self_ = scale_file_ = false). */
+int cab_svm_set_model(cab_ctx* ctx, int32_t dim, int32_t nr_class, int32_t total_sv, double gamma,
+                      const int32_t* labels, const int32_t* nr_sv, const double* rho,
+                      const double* sv_coef, const double* sv);
+int cab_svm_set_scaling(cab_ctx* ctx, int32_t dim, double lower, double upper, const double* fmin,
+                        const double* fmax);
+/* features: n x dim floats (the f1..f<dim> channels, point-major).  point_class: n predicted labels
+ * (the point_class channel, svm_classification.cpp:128,150).  dec_values (may be NULL):
+ * n x nr_class*(nr_class-1)/2 decision values. */
+int cab_svm_predict(cab_ctx* ctx, const float* features, int64_t n, int32_t dim, float* point_class,
+                    double* dec_values);
+/* Classifies the GRSD-21 histograms the last cab_grsd_batch left on the device (one per cluster;
+ * f_i = (float)count_i as the GlobalRSD plugin emits them): cluster -> class without a host round
+ * trip of the features.  point_class: nclusters floats. */
+int cab_svm_predict_grsd(cab_ctx* ctx, float* point_class);
+
 /* ---- device plumbing (bench / multi-GPU) ---------------------------------------------- */
 #define CAB_BUF_POS_SORTED 0  /* float4[n]  x,y,z,0 in sorted order */
 #define CAB_BUF_NRM_SORTED 1  /* float4[n]  nx,ny,nz,curvature in sorted order */

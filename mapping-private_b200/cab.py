@@ -17,12 +17,14 @@ _LIB = None
 
 RSD_SEED_BIN0 = 2
 RSD_SCALE_SORT = 4
+SIG_GRSD21, SIG_GRSD325, SIG_PLUSGRSD110 = 0, 1, 2
+SIG_DIM = {0: 21, 1: 325, 2: 110}
 BUF_POS_SORTED, BUF_NRM_SORTED, BUF_RSD_SORTED, BUF_PERM = 0, 1, 2, 3
 
 EXPORTS = [
     "cab_create", "cab_destroy", "cab_last_error", "cab_upload_cloud", "cab_upload_clusters",
     "cab_set_cloud_device", "cab_build_grid", "cab_set_shard", "cab_shard_range", "cab_normals",
-    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels",
+    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd",
     "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_profile", "cab_version",
 ]
 
@@ -67,6 +69,7 @@ def lib():
         L.cab_last_error.argtypes = [C.c_void_p]
         L.cab_neighbors_debug.restype = C.c_int64
         L.cab_grsd_voxels.restype = C.c_int64
+        L.cab_grsd_signatures.restype = C.c_int64
         L.cab_device_ptr.restype = C.c_void_p
         L.cab_device_ptr.argtypes = [C.c_void_p, C.c_int32]
         L.cab_stream.restype = C.c_void_p
@@ -241,6 +244,54 @@ class Context:
         self._check(self._L.cab_grsd_voxels(self._h, off.ctypes.data_as(C.POINTER(C.c_int64)), _fp(cent), _fp(rmin), _fp(rmax),
                                             _ip(lab), C.c_int64(nv)), "cab_grsd_voxels")
         return dict(offsets=off, centroids=cent[:nv], r_min=rmin[:nv], r_max=rmax[:nv], labels=lab[:nv])
+
+    def grsd_signatures(self, nclusters: int, kind: int = SIG_GRSD21, subdivision_size: int = 0, off=(0, 0, 0)):
+        """Signatures of the clusters of the last grsd_batch: dict(offsets (nc+1), subdiv_b (nc,3), hist (total, dim))."""
+        offs = np.zeros(nclusters + 1, np.int64)
+        sb = np.zeros((nclusters, 3), np.int32)
+        args = (self._h, C.c_int32(kind), C.c_int32(subdivision_size), C.c_int32(off[0]), C.c_int32(off[1]), C.c_int32(off[2]),
+                offs.ctypes.data_as(C.POINTER(C.c_int64)), _ip(sb))
+        total = self._check(self._L.cab_grsd_signatures(*args, None, C.c_int64(0)), "cab_grsd_signatures")
+        hist = np.zeros((total, SIG_DIM[kind]), np.int32)
+        if total:
+            self._check(self._L.cab_grsd_signatures(*args, _ip(hist), C.c_int64(total)), "cab_grsd_signatures")
+        return dict(offsets=offs, subdiv_b=sb, hist=hist)
+
+    # ---- SVM ---------------------------------------------------------------------------
+    def svm_set_model(self, model, scale=None):
+        """model: svm_model.SvmModel; scale: None or (lower, upper, fmin, fmax) from svm_model.parse_scale."""
+        dp = C.POINTER(C.c_double)
+        lab = np.ascontiguousarray(model.labels, np.int32)
+        nsv = np.ascontiguousarray(model.nr_sv, np.int32)
+        rho = np.ascontiguousarray(model.rho, np.float64)
+        coef = np.ascontiguousarray(model.sv_coef, np.float64)
+        sv = np.ascontiguousarray(model.sv, np.float64)
+        self._check(self._L.cab_svm_set_model(self._h, C.c_int32(sv.shape[1]), C.c_int32(lab.shape[0]), C.c_int32(sv.shape[0]),
+                                              C.c_double(model.gamma), _ip(lab), _ip(nsv), rho.ctypes.data_as(dp),
+                                              coef.ctypes.data_as(dp), sv.ctypes.data_as(dp)), "cab_svm_set_model")
+        if scale is None:
+            self._check(self._L.cab_svm_set_scaling(self._h, C.c_int32(sv.shape[1]), C.c_double(0), C.c_double(0), None, None),
+                        "cab_svm_set_scaling")
+        else:
+            lower, upper, fmin, fmax = scale
+            fmin = np.ascontiguousarray(fmin, np.float64)
+            fmax = np.ascontiguousarray(fmax, np.float64)
+            self._check(self._L.cab_svm_set_scaling(self._h, C.c_int32(fmin.shape[0]), C.c_double(lower), C.c_double(upper),
+                                                    fmin.ctypes.data_as(dp), fmax.ctypes.data_as(dp)), "cab_svm_set_scaling")
+        self._svm_pairs = lab.shape[0] * (lab.shape[0] - 1) // 2
+
+    def svm_predict(self, features: np.ndarray, want_dec: bool = False):
+        f = np.ascontiguousarray(features, np.float32)
+        out = np.zeros(f.shape[0], np.float32)
+        dec = np.zeros((f.shape[0], self._svm_pairs), np.float64) if want_dec else None
+        self._check(self._L.cab_svm_predict(self._h, _fp(f), C.c_int64(f.shape[0]), C.c_int32(f.shape[1]), _fp(out),
+                                            dec.ctypes.data_as(C.POINTER(C.c_double)) if want_dec else None), "cab_svm_predict")
+        return (out, dec) if want_dec else out
+
+    def svm_predict_grsd(self, nclusters: int):
+        out = np.zeros(nclusters, np.float32)
+        self._check(self._L.cab_svm_predict_grsd(self._h, _fp(out)), "cab_svm_predict_grsd")
+        return out
 
     # ---- plumbing --------------------------------------------------------------------
     def device_ptr(self, which: int) -> int:

@@ -126,6 +126,7 @@ int upload_impl(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride, const
   if (n > 0 && !xyz) return fail(ctx, CAB_ERR_ARG, "xyz is NULL");
   CAB_CUDA(ctx, cudaSetDevice(ctx->device));
   ctx->have_cloud = ctx->have_grid = ctx->have_normals = ctx->have_rsd = false;
+  ctx->g_min_div.clear();  // voxel state of the last cab_grsd_batch belongs to the previous cloud
   if (int rc = set_domains(ctx, n, offsets, nclusters)) return rc;
   if (device_ptr) {
     ctx->xyz_in = xyz;
@@ -261,9 +262,10 @@ void cab_destroy(cab_ctx* ctx) {
                     &ctx->b_rsd, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
                     &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_halo_list, &ctx->b_rowflag, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
                     &ctx->g_vvals[1], &ctx->g_cent, &ctx->g_vcount, &ctx->g_vrad, &ctx->g_vlabel, &ctx->g_voff,
-                    &ctx->g_layout, &ctx->g_layoff, &ctx->g_vgrid, &ctx->g_hist, &ctx->g_vfirst};
+                    &ctx->g_layout, &ctx->g_layoff, &ctx->g_vgrid, &ctx->g_hist, &ctx->g_vfirst, &ctx->g_cnrm, &ctx->g_invperm, &ctx->g_sig, &ctx->g_sigdom};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
+  svm_free(ctx);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);

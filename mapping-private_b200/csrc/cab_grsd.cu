@@ -284,6 +284,131 @@ __global__ void __launch_bounds__(128) transitions_kernel(const VoxGrid* __restr
   }
 }
 
+// ---- signature variants (GRSD-21 with subdivisions, GRSD-325, PlusGRSD-110) ----------------------
+
+__global__ void __launch_bounds__(256) inverse_perm_kernel(const int* __restrict__ perm, int n, int* __restrict__ inv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[perm[i]] = i;
+}
+
+// Mean normal of every voxel: pcl::VoxelGrid averages every field of the point type [EXTERNAL]; the
+// result is not re-normalised (grsd_colorCHLAC_tools.hpp:558).  One thread per voxel, summed in
+// (voxel, input index) order -- the radix sort is stable -- so the fp64 sums are reproducible.
+__global__ void __launch_bounds__(128) voxel_normals_kernel(const float4* __restrict__ nrm, const int* __restrict__ inv_perm,
+                                                            const int* __restrict__ ucount, const int* __restrict__ ustart,
+                                                            const int* __restrict__ sorted_idx, int nvox,
+                                                            float4* __restrict__ cnrm) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  const int b = ustart[v], c = ucount[v];
+  double sx = 0, sy = 0, sz = 0;
+  for (int s = 0; s < c; ++s) {
+    const float4 q = nrm[inv_perm[sorted_idx[b + s]]];
+    sx += (double)q.x;
+    sy += (double)q.y;
+    sz += (double)q.z;
+  }
+  const double cnt = (double)c;
+  cnrm[v] = make_float4((float)(sx / cnt), (float)(sy / cnt), (float)(sz / cnt), 0.f);
+}
+
+struct SigDom {  // per cluster
+  long long hist_base;  // first histogram of this cluster in the output
+  int sb[3];            // subdivisions per axis
+  int hist_num;         // 0: offsets exceed the grid, no output
+};
+
+constexpr int kSigSmemInts = 8192;  // histograms of a cluster are accumulated in shared memory up to this size
+
+// Eigen's Vector3f::normalize() as used at grsd_colorCHLAC_tools.hpp:559-560: v / sqrt(v.v), fp32
+__device__ __forceinline__ float3 unit_normal(float4 q) {
+  const float sq = __fadd_rn(__fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z));
+  const float len = __fsqrt_rn(sq);
+  return make_float3(__fdiv_rn(q.x, len), __fdiv_rn(q.y, len), __fdiv_rn(q.z, len));
+}
+
+// kind 0: GRSD-21 (:230-276), 1: GRSD-325 (:396-431), 2: PlusGRSD-110 (:562-637).  Block (cluster, slice):
+// counts go straight to their packed bin (entries below the diagonal of the transition matrices are
+// never read by the reference and are dropped), into shared memory when the cluster's histograms fit.
+template <int kKind>
+__global__ void __launch_bounds__(128) signature_kernel(const VoxGrid* __restrict__ vg, const SigDom* __restrict__ sd,
+                                                        const int* __restrict__ vox_off, const float4* __restrict__ cent,
+                                                        const float4* __restrict__ cnrm, const int* __restrict__ labels,
+                                                        const int* __restrict__ layout, float leaf, float inv_leaf,
+                                                        int sub, float inv_sub, int off_x, int off_y, int off_z,
+                                                        int* __restrict__ out) {
+  constexpr int kDim = kKind == 0 ? 21 : (kKind == 1 ? 325 : 110);
+  constexpr int kOff = kKind == 1 ? 13 : 26;
+  __shared__ int sh[kSigSmemInts];
+  const int d = blockIdx.x;
+  const SigDom s = sd[d];
+  if (s.hist_num == 0) return;
+  const bool use_sh = (long long)s.hist_num * kDim <= kSigSmemInts;
+  int* H = use_sh ? sh : out + s.hist_base * kDim;
+  if (use_sh) {
+    for (int i = threadIdx.x; i < s.hist_num * kDim; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+  }
+  const VoxGrid g = vg[d];
+  const int v0 = vox_off[d], v1 = vox_off[d + 1];
+  const long long work = (long long)(v1 - v0) * kOff;
+  for (long long w = (long long)blockIdx.y * blockDim.x + threadIdx.x; w < work; w += (long long)gridDim.y * blockDim.x) {
+    const int v = v0 + (int)(w / kOff), o = (int)(w % kOff);
+    const float4 c = cent[v];
+    int hist_idx = 0;
+    if (sub > 0) {  // :233-246: floor(x / voxel_size) - min_b - offset, fp32 division
+      const int tx = (int)floorf(__fdiv_rn(c.x, leaf)) - g.min_b[0] - off_x;
+      const int ty = (int)floorf(__fdiv_rn(c.y, leaf)) - g.min_b[1] - off_y;
+      const int tz = (int)floorf(__fdiv_rn(c.z, leaf)) - g.min_b[2] - off_z;
+      if (tx < 0 || ty < 0 || tz < 0) continue;
+      const int ix = (int)floorf(__fmul_rn((float)tx, inv_sub)), iy = (int)floorf(__fmul_rn((float)ty, inv_sub)),
+                iz = (int)floorf(__fmul_rn((float)tz, inv_sub));
+      hist_idx = ix + iy * s.sb[0] + iz * s.sb[0] * s.sb[1];
+    }
+    // pcl::VoxelGrid::getNeighborCentroidIndices [EXTERNAL]: ijk = floor(ref * inverse_leaf)
+    const int n0 = (int)floorf(__fmul_rn(c.x, inv_leaf)) + c_off26[o][0] - g.min_b[0],
+              n1 = (int)floorf(__fmul_rn(c.y, inv_leaf)) + c_off26[o][1] - g.min_b[1],
+              n2 = (int)floorf(__fmul_rn(c.z, inv_leaf)) + c_off26[o][2] - g.min_b[2];
+    int nb = -1;
+    if (n0 >= 0 && n0 < g.div_b[0] && n1 >= 0 && n1 < g.div_b[1] && n2 >= 0 && n2 < g.div_b[2])
+      nb = layout[g.layout_base + n0 + (long long)n1 * g.div_b[0] + (long long)n2 * g.div_b[0] * g.div_b[1]];
+    const int src = labels[v];
+    int bin = -1;
+    if (kKind == 0) {
+      const int nt = nb >= 0 ? labels[v0 + nb] : 5;
+      if (src <= nt) bin = src * 6 - src * (src - 1) / 2 + (nt - src);  // row-major upper triangle of 6x6
+    } else if (kKind == 1) {
+      if (nb >= 0) bin = src + labels[v0 + nb] * 5 + o * 25;  // EMPTY neighbours are ignored (:427-428)
+    } else {
+      const float3 sn = unit_normal(cnrm[v]);
+      if (!(isfinite(sn.x) && isfinite(sn.y) && isfinite(sn.z))) continue;  // :583
+      bin = 105 + src;  // transitions_to_empty (:595-596, :609-610)
+      if (nb >= 0) {
+        const float3 m = unit_normal(cnrm[v0 + nb]);
+        if (isfinite(m.x) && isfinite(m.y) && isfinite(m.z)) {
+          // :607-608: min(NR_DIV-1, (int) floor(sqrt(source_normal.cross(nbr).norm()) * NR_DIV))
+          const float cx = __fsub_rn(__fmul_rn(sn.y, m.z), __fmul_rn(sn.z, m.y));
+          const float cy = __fsub_rn(__fmul_rn(sn.z, m.x), __fmul_rn(sn.x, m.z));
+          const float cz = __fsub_rn(__fmul_rn(sn.x, m.y), __fmul_rn(sn.y, m.x));
+          const float cn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+          const int ab = min(6, (int)floor(__dmul_rn(sqrt((double)cn), 7.0)));
+          const int nt = labels[v0 + nb];
+          bin = src <= nt ? ab * 15 + src * 5 - src * (src - 1) / 2 + (nt - src) : -1;
+        }
+      }
+    }
+    if (bin >= 0) atomicAdd(&H[(long long)hist_idx * kDim + bin], 1);
+  }
+  if (use_sh) {
+    __syncthreads();
+    int* dst = out + s.hist_base * kDim;
+    for (int i = threadIdx.x; i < s.hist_num * kDim; i += blockDim.x) {
+      const int c = sh[i];
+      if (c) atomicAdd(dst + i, c);
+    }
+  }
+}
+
 float d2_threshold(double radius, float r2_hi, bool (*pred)(double, double, int, int), int b, int ndiv) {
   // smallest fp32 d2 in [0, r2_hi] with pred true (pred monotone in d2); INFINITY if none
   if (!pred(std::sqrt((double)r2_hi), radius, b, ndiv)) return INFINITY;
@@ -411,6 +536,14 @@ int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_
   }
   ctx->g_nvox = nvox;
   ctx->g_vox_offsets.assign(vox_off.begin(), vox_off.end());
+  ctx->g_min_div.resize((size_t)nd * 6);
+  for (int d = 0; d < nd; ++d)
+    for (int a = 0; a < 3; ++a) {
+      ctx->g_min_div[6 * (size_t)d + a] = vg[d].min_b[a];
+      ctx->g_min_div[6 * (size_t)d + 3 + a] = vg[d].div_b[a];
+    }
+  ctx->g_leaf = leaf;
+  ctx->g_have_cnrm = false;
   if (int rc = reserve(ctx, ctx->g_cent, (size_t)std::max(nvox, 1) * sizeof(float4))) return rc;
   if (int rc = reserve(ctx, ctx->g_vrad, (size_t)std::max(nvox, 1) * sizeof(float2))) return rc;
   if (int rc = reserve(ctx, ctx->g_vlabel, (size_t)std::max(nvox, 1) * sizeof(int))) return rc;
@@ -519,6 +652,91 @@ int64_t cab_grsd_voxels(cab_ctx* ctx, int64_t* vox_offsets, float* centroids_xyz
     if (r_max) r_max[i] = r[i].y;
   }
   return nv;
+}
+
+int64_t cab_grsd_signatures(cab_ctx* ctx, int32_t kind, int32_t subdivision_size, int32_t off_x, int32_t off_y,
+                            int32_t off_z, int64_t* hist_offsets, int32_t* subdiv_b, int32_t* hist, int64_t cap) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (kind < CAB_SIG_GRSD21 || kind > CAB_SIG_PLUSGRSD110) return fail(ctx, CAB_ERR_ARG, "cab_grsd_signatures: unknown kind %d", kind);
+  if (subdivision_size < 0) return fail(ctx, CAB_ERR_ARG, "cab_grsd_signatures: invalid subdivision size %d", subdivision_size);
+  const int nd = (int)ctx->g_min_div.size() / 6;
+  if (nd == 0 || ctx->g_vox_offsets.size() != (size_t)nd + 1)
+    return fail(ctx, CAB_ERR_STATE, "cab_grsd_signatures: run cab_grsd_batch first");
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, CAB_ERR_CUDA, "cudaSetDevice failed");
+  const int dim = kind == CAB_SIG_GRSD21 ? 21 : (kind == CAB_SIG_GRSD325 ? 325 : 110);
+  // subdivision bookkeeping per cluster (grsd_colorCHLAC_tools.hpp:140-161), host, tiny
+  const float inv_sub = subdivision_size > 0 ? (float)(1.0 / subdivision_size) : 0.f;
+  std::vector<SigDom> sd(nd);
+  int64_t total = 0;
+  int max_vox = 0;
+  for (int d = 0; d < nd; ++d) {
+    const int32_t* div_b = ctx->g_min_div.data() + 6 * (size_t)d + 3;
+    SigDom& s = sd[d];
+    s.hist_base = total;
+    s.sb[0] = s.sb[1] = s.sb[2] = 1;
+    s.hist_num = 1;
+    if (subdivision_size > 0) {
+      if (div_b[0] <= off_x || div_b[1] <= off_y || div_b[2] <= off_z) {
+        s.sb[0] = s.sb[1] = s.sb[2] = 0;
+        s.hist_num = 0;
+      } else {
+        s.sb[0] = (int)std::ceil((div_b[0] - off_x) * inv_sub);
+        s.sb[1] = (int)std::ceil((div_b[1] - off_y) * inv_sub);
+        s.sb[2] = (int)std::ceil((div_b[2] - off_z) * inv_sub);
+        s.hist_num = s.sb[0] * s.sb[1] * s.sb[2];
+      }
+    }
+    if (hist_offsets) hist_offsets[d] = total;
+    if (subdiv_b)
+      for (int a = 0; a < 3; ++a) subdiv_b[3 * (size_t)d + a] = s.sb[a];
+    total += s.hist_num;
+    max_vox = std::max<int>(max_vox, (int)(ctx->g_vox_offsets[d + 1] - ctx->g_vox_offsets[d]));
+  }
+  if (hist_offsets) hist_offsets[nd] = total;
+  if (!hist || total == 0) return total;
+  if (total > cap) return fail(ctx, CAB_ERR_ARG, "cab_grsd_signatures: %lld histograms, room for %lld", (long long)total, (long long)cap);
+  cudaStream_t st = ctx->stream;
+  const int n = (int)ctx->n;
+  const int nvox = (int)ctx->g_nvox;
+  if (kind == CAB_SIG_PLUSGRSD110 && !ctx->g_have_cnrm && nvox > 0) {
+    if (!ctx->have_normals) return fail(ctx, CAB_ERR_STATE, "cab_grsd_signatures: no normals");
+    if (int rc = reserve(ctx, ctx->g_invperm, (size_t)std::max(n, 1) * 4)) return rc;
+    if (int rc = reserve(ctx, ctx->g_cnrm, (size_t)nvox * sizeof(float4))) return rc;
+    inverse_perm_kernel<<<(n + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, n, (int*)ctx->g_invperm.p);
+    CAB_LAUNCH_CHECK(ctx);
+    const int* ucount = (const int*)ctx->g_vcount.p;
+    const int* ustart = ucount + (std::max(n, 1) + 1);
+    voxel_normals_kernel<<<(nvox + 127) / 128, 128, 0, st>>>((const float4*)ctx->b_nrm.p, (const int*)ctx->g_invperm.p, ucount, ustart,
+                                                            (const int*)ctx->g_vvals[1].p, nvox, (float4*)ctx->g_cnrm.p);
+    CAB_LAUNCH_CHECK(ctx);
+    ctx->g_have_cnrm = true;
+  }
+  if (int rc = reserve(ctx, ctx->g_sig, (size_t)total * dim * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->g_sigdom, (size_t)nd * sizeof(SigDom))) return rc;
+  if (int rc = reserve_pinned(ctx, (size_t)nd * sizeof(SigDom))) return rc;
+  std::memcpy(ctx->h_pin, sd.data(), (size_t)nd * sizeof(SigDom));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->g_sigdom.p, ctx->h_pin, (size_t)nd * sizeof(SigDom), cudaMemcpyHostToDevice, st));
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->g_sig.p, 0, (size_t)total * dim * 4, st));
+  if (nvox > 0) {
+    const int noff = kind == CAB_SIG_GRSD325 ? 13 : 26;
+    const unsigned slices = (unsigned)std::min<long long>(std::max<long long>(((long long)max_vox * noff + 2047) / 2048, 1), 1024);
+    const dim3 grid((unsigned)nd, slices);
+    const float leaf = ctx->g_leaf, inv_leaf = 1.0f / leaf;
+#define CAB_SIG_LAUNCH(K)                                                                                                  \
+  signature_kernel<K><<<grid, 128, 0, st>>>((const VoxGrid*)ctx->g_vgrid.p, (const SigDom*)ctx->g_sigdom.p,                \
+                                            (const int*)ctx->g_voff.p, (const float4*)ctx->g_cent.p,                      \
+                                            (const float4*)ctx->g_cnrm.p, (const int*)ctx->g_vlabel.p,                    \
+                                            (const int*)ctx->g_layout.p, leaf, inv_leaf, subdivision_size, inv_sub, off_x, \
+                                            off_y, off_z, (int*)ctx->g_sig.p)
+    if (kind == CAB_SIG_GRSD21) CAB_SIG_LAUNCH(0);
+    else if (kind == CAB_SIG_GRSD325) CAB_SIG_LAUNCH(1);
+    else CAB_SIG_LAUNCH(2);
+#undef CAB_SIG_LAUNCH
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  CAB_CUDA(ctx, cudaMemcpyAsync(hist, ctx->g_sig.p, (size_t)total * dim * 4, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  return total;
 }
 
 }  // extern "C"

@@ -74,6 +74,8 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+struct SvmState;  // cab_svm.cu
+
 }  // namespace cab
 
 struct cab_ctx {
@@ -117,8 +119,14 @@ struct cab_ctx {
   // GRSD results of the last batch
   cab::DevBuf g_vkeys[2], g_vvals[2], g_cent, g_vcount, g_vrad, g_vlabel, g_voff, g_layout, g_layoff,
       g_vgrid, g_hist, g_vfirst;
+  cab::DevBuf g_cnrm, g_invperm, g_sig, g_sigdom;
   int64_t g_nvox = 0;
   std::vector<int64_t> g_vox_offsets;
+  std::vector<int32_t> g_min_div;  // host copy of the voxel grids: min_b[3], div_b[3] per cluster
+  float g_leaf = 0.f;
+  bool g_have_cnrm = false;        // voxel mean normals computed for the last batch
+
+  cab::SvmState* svm = nullptr;    // SVM model + scaling (cab_svm.cu)
 };
 
 namespace cab {
@@ -154,5 +162,6 @@ int64_t run_neighbors_debug(cab_ctx* ctx, float r, int max_nn, int64_t q0, int64
 int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_t* hist21);
 int permute_normals_in(cab_ctx* ctx, const float* nx, const float* ny, const float* nz);
 int download_results(cab_ctx* ctx, float* n4, float* rmin, float* rmax);
+void svm_free(cab_ctx* ctx);
 
 }  // namespace cab

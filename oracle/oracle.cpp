@@ -855,4 +855,213 @@ int orc_grsd21(const float* xyz, const float* normals_in, int normal_stride, int
                               nullptr, hist21);
 }
 
+int orc_voxel_normals(const float* xyz, const float* normals, int normal_stride, int n, float leaf,
+                      float* out) {
+  // same keys and voxel order as orc_voxel_grid
+  const float inv = 1.0f / leaf;
+  int32_t min_b[3], div_b[3];
+  int nvox = orc_voxel_grid(xyz, n, leaf, min_b, div_b, nullptr, nullptr, nullptr);
+  if (nvox == 0) return 0;
+  std::vector<std::pair<int64_t, int32_t>> keyed;
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * (size_t)i;
+    if (!finite3(p)) continue;
+    int ijk0 = (int)(std::floor(p[0] * inv) - min_b[0]);
+    int ijk1 = (int)(std::floor(p[1] * inv) - min_b[1]);
+    int ijk2 = (int)(std::floor(p[2] * inv) - min_b[2]);
+    keyed.emplace_back((int64_t)ijk0 + (int64_t)ijk1 * div_b[0] + (int64_t)ijk2 * div_b[0] * div_b[1], i);
+  }
+  std::sort(keyed.begin(), keyed.end());
+  int v = 0;
+  size_t i = 0;
+  while (i < keyed.size()) {
+    size_t j = i;
+    double s[3] = {0, 0, 0};
+    while (j < keyed.size() && keyed[j].first == keyed[i].first) {
+      const float* q = normals + (size_t)normal_stride * keyed[j].second;
+      s[0] += q[0];
+      s[1] += q[1];
+      s[2] += q[2];
+      ++j;
+    }
+    const double cnt = (double)(j - i);
+    for (int a = 0; a < 3; ++a) out[3 * (size_t)v + a] = (float)(s[a] / cnt);
+    ++v;
+    i = j;
+  }
+  return v;
+}
+
+int orc_grsd_signature(int kind, const float* centroids, const float* cent_normals, int nvox,
+                       const int32_t* types, float leaf, const int32_t* min_b, const int32_t* div_b,
+                       const int32_t* layout, int subdivision_size, int off_x, int off_y, int off_z,
+                       int32_t* subdiv_b, int32_t* hist) {
+  if (kind < 0 || kind > 2) return -2;
+  if (kind == ORC_SIG_PLUSGRSD110 && !cent_normals && hist) return -2;
+  // subdivision bookkeeping, identical in the three extractors (:140-161, :322-343, :479-500)
+  if (subdivision_size < 0) return -1;
+  int hist_num = 1;
+  float inverse_subdivision_size = 0.f;
+  int sb[3] = {1, 1, 1};
+  if (subdivision_size > 0) {
+    inverse_subdivision_size = 1.0 / subdivision_size;
+    if (div_b[0] <= off_x || div_b[1] <= off_y || div_b[2] <= off_z) {
+      if (subdiv_b) subdiv_b[0] = subdiv_b[1] = subdiv_b[2] = 0;
+      return 0;
+    }
+    sb[0] = (int)std::ceil((div_b[0] - off_x) * inverse_subdivision_size);
+    sb[1] = (int)std::ceil((div_b[1] - off_y) * inverse_subdivision_size);
+    sb[2] = (int)std::ceil((div_b[2] - off_z) * inverse_subdivision_size);
+    hist_num = sb[0] * sb[1] * sb[2];
+  }
+  if (subdiv_b) {
+    subdiv_b[0] = sb[0];
+    subdiv_b[1] = sb[1];
+    subdiv_b[2] = sb[2];
+  }
+  if (!hist) return hist_num;
+  const int dim = kind == ORC_SIG_GRSD21 ? 21 : (kind == ORC_SIG_GRSD325 ? 325 : 110);
+  const float inv = 1.0f / leaf;
+  int32_t off[26][3];
+  fill_offsets26(off);
+  const int NRDIV = 7, NRCLASS = 5;  // grsd_colorCHLAC_tools.h:9,18
+  // PlusGRSD: centroid normals re-normalised in fp32 (:559-560), Eigen normalize() = v / sqrt(v.v)
+  std::vector<float> nn;
+  if (kind == ORC_SIG_PLUSGRSD110) {
+    nn.resize((size_t)nvox * 3);
+    for (int v = 0; v < nvox; ++v) {
+      const float* q = cent_normals + 3 * (size_t)v;
+      const float sq = (q[0] * q[0] + q[1] * q[1]) + q[2] * q[2];
+      const float len = std::sqrt(sq);
+      for (int a = 0; a < 3; ++a) nn[3 * (size_t)v + a] = q[a] / len;
+    }
+  }
+  // raw counters per histogram: 21 -> 6x6, 325 -> 325, 110 -> 7 x 5x5 + 5
+  const int raw = kind == ORC_SIG_GRSD21 ? 36 : (kind == ORC_SIG_GRSD325 ? 325 : NRDIV * 25 + 5);
+  std::vector<int32_t> R((size_t)hist_num * raw, 0);
+  for (int v = 0; v < nvox; ++v) {
+    int hist_idx = 0;
+    const float* c = centroids + 3 * (size_t)v;
+    if (hist_num != 1) {  // :233-246 (same text at :399-412, :565-578)
+      const int tmp_x = std::floor(c[0] / leaf) - min_b[0] - off_x;
+      const int tmp_y = std::floor(c[1] / leaf) - min_b[1] - off_y;
+      const int tmp_z = std::floor(c[2] / leaf) - min_b[2] - off_z;
+      if (tmp_x < 0 || tmp_y < 0 || tmp_z < 0) continue;
+      int ix = (int)std::floor(tmp_x * inverse_subdivision_size);
+      int iy = (int)std::floor(tmp_y * inverse_subdivision_size);
+      int iz = (int)std::floor(tmp_z * inverse_subdivision_size);
+      hist_idx = ix + iy * sb[0] + iz * sb[0] * sb[1];
+    }
+    int32_t* H = R.data() + (size_t)hist_idx * raw;
+    const int src = types[v];
+    if (kind == ORC_SIG_GRSD21) {
+      for (int o = 0; o < 26; ++o) {
+        int nb = neighbor_centroid(c, inv, min_b, div_b, layout, off[o]);
+        int nt = (nb == -1) ? 5 : types[nb];
+        H[src * 6 + nt]++;
+      }
+    } else if (kind == ORC_SIG_GRSD325) {
+      for (int o = 0; o < 13; ++o) {  // :415-429: the 13 half offsets only
+        int nb = neighbor_centroid(c, inv, min_b, div_b, layout, off[o]);
+        if (nb == -1) continue;  // "ignore EMPTY"
+        H[src + types[nb] * 5 + o * 25]++;
+      }
+    } else {
+      const float* sn = nn.data() + 3 * (size_t)v;
+      if (!(std::isfinite(sn[0]) && std::isfinite(sn[1]) && std::isfinite(sn[2]))) continue;  // :583
+      for (int o = 0; o < 26; ++o) {
+        int nb = neighbor_centroid(c, inv, min_b, div_b, layout, off[o]);
+        if (nb == -1) {
+          H[NRDIV * 25 + src]++;  // transitions_to_empty (:595-596)
+          continue;
+        }
+        const float* m = nn.data() + 3 * (size_t)nb;
+        if (std::isfinite(m[0]) && std::isfinite(m[1]) && std::isfinite(m[2])) {
+          // :607-608: min(NR_DIV-1, (int) floor(sqrt(source_normal.cross(nbr).norm()) * NR_DIV));
+          // cross and norm in fp32 (Eigen::Vector3f), the outer sqrt in double
+          const float cx = sn[1] * m[2] - sn[2] * m[1];
+          const float cy = sn[2] * m[0] - sn[0] * m[2];
+          const float cz = sn[0] * m[1] - sn[1] * m[0];
+          const float cn = std::sqrt((cx * cx + cy * cy) + cz * cz);
+          const int bin = std::min(NRDIV - 1, (int)std::floor(std::sqrt((double)cn) * NRDIV));
+          H[bin * 25 + src * 5 + types[nb]]++;
+        } else {
+          H[NRDIV * 25 + src]++;  // :609-610
+        }
+      }
+    }
+  }
+  for (int h = 0; h < hist_num; ++h) {
+    const int32_t* H = R.data() + (size_t)h * raw;
+    int32_t* out = hist + (size_t)h * dim;
+    int nrf = 0;
+    if (kind == ORC_SIG_GRSD21) {  // :266-276
+      for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) out[nrf++] = H[i * 6 + j];
+    } else if (kind == ORC_SIG_GRSD325) {
+      for (int i = 0; i < 325; ++i) out[i] = H[i];
+    } else {  // :626-636
+      for (int d = 0; d < NRDIV; ++d)
+        for (int i = 0; i < NRCLASS; ++i)
+          for (int j = i; j < NRCLASS; ++j) out[nrf++] = H[d * 25 + i * 5 + j];
+      for (int it = 0; it < NRCLASS; ++it) out[nrf++] = H[NRDIV * 25 + it];
+    }
+  }
+  return hist_num;
+}
+
+int orc_svm_predict(const float* features, int64_t n, int dim, int nr_class, int total_sv, double gamma,
+                    const int32_t* labels, const int32_t* nr_sv, const double* rho, const double* sv_coef,
+                    const double* sv, double lower, double upper, const double* fmin, const double* fmax,
+                    float* out, double* dec) {
+  const int npairs = nr_class * (nr_class - 1) / 2;
+  std::vector<int> start(nr_class, 0);
+  for (int i = 1; i < nr_class; ++i) start[i] = start[i - 1] + nr_sv[i - 1];
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < n; ++p) {
+    std::vector<double> x(dim), kvalue(total_sv), dv(npairs);
+    std::vector<int> vote(nr_class, 0);
+    for (int i = 0; i < dim; ++i) {
+      double value = features[(size_t)p * dim + i];  // svm_classification.cpp:141
+      if (fmin) {                                    // scaleFeature, svm_classification.h:68-86
+        if (fmin[i] == fmax[i]) value = 0;
+        else if (value <= fmin[i]) value = lower;
+        else if (value >= fmax[i]) value = upper;
+        else value = lower + (upper - lower) * (value - fmin[i]) / (fmax[i] - fmin[i]);
+      }
+      x[i] = value;
+    }
+    for (int s = 0; s < total_sv; ++s) {  // Kernel::k_function, RBF
+      const double* y = sv + (size_t)s * dim;
+      double sum = 0;
+      for (int i = 0; i < dim; ++i) {
+        const double d = x[i] - y[i];
+        sum += d * d;
+      }
+      kvalue[s] = std::exp(-gamma * sum);
+    }
+    int pi = 0;
+    for (int i = 0; i < nr_class; ++i)
+      for (int j = i + 1; j < nr_class; ++j) {
+        double sum = 0;
+        const int si = start[i], sj = start[j], ci = nr_sv[i], cj = nr_sv[j];
+        const double* coef1 = sv_coef + (size_t)(j - 1) * total_sv;
+        const double* coef2 = sv_coef + (size_t)i * total_sv;
+        for (int k = 0; k < ci; ++k) sum += coef1[si + k] * kvalue[si + k];
+        for (int k = 0; k < cj; ++k) sum += coef2[sj + k] * kvalue[sj + k];
+        sum -= rho[pi];
+        dv[pi] = sum;
+        if (sum > 0) ++vote[i]; else ++vote[j];
+        ++pi;
+      }
+    int best = 0;
+    for (int i = 1; i < nr_class; ++i)
+      if (vote[i] > vote[best]) best = i;
+    out[p] = (float)labels[best];
+    if (dec)
+      for (int q = 0; q < npairs; ++q) dec[(size_t)p * npairs + q] = dv[q];
+  }
+  return 0;
+}
+
 }  // extern "C"

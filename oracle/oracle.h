@@ -125,6 +125,48 @@ int orc_grsd21_subdiv(const float* centroids, int nvox, const int32_t* types, fl
                       int subdivision_size, int off_x, int off_y, int off_z, int32_t* subdiv_b,
                       int32_t* hist21);
 
+/* Mean normal of every voxel.  pcl::VoxelGrid with downsample_all_data averages every field of
+ * the point type, the normals included, and does not re-normalise them (comment at
+ * grsd_colorCHLAC_tools.hpp:558) [EXTERNAL].  out: V x 3 = (float)(sum_double / count), summed in
+ * (voxel, input index) order; voxel order as orc_voxel_grid.  Returns V. */
+int orc_voxel_normals(const float* xyz, const float* normals, int normal_stride, int n, float leaf,
+                      float* out);
+
+/* The three transition signatures of grsd_colorCHLAC_tools.hpp for precomputed voxel labels, with
+ * the subdivision / sliding-box mode (subdivision_size > 0, voxel offsets off_*):
+ *   ORC_SIG_GRSD21      extractGRSDSignature21      (:131-294)  21 bins per histogram
+ *   ORC_SIG_GRSD325     extractGRSDSignature325     (:305-451)  325 bins: src + 5*nbr + 25*offset_id
+ *                       over the 13 half offsets, EMPTY neighbours ignored (:427-428)
+ *   ORC_SIG_PLUSGRSD110 extractPlusGRSDSignature110 (:462-668)  7 normal-angle bins x 15 + 5
+ *                       to-empty; needs cent_normals (V x 3, un-normalised voxel means), which are
+ *                       normalised in fp32 like Eigen's normalize() (:559-560)
+ * Call with hist == NULL to get subdiv_b[3] and the number of histograms; returns hist_num
+ * (0 if the offsets exceed the grid, -1 on an invalid subdivision size, -2 on a bad kind).
+ * hist: hist_num x dim int32 (the reference emits them as floats, optionally x NORMALIZE_GRSD). */
+#define ORC_SIG_GRSD21 0
+#define ORC_SIG_GRSD325 1
+#define ORC_SIG_PLUSGRSD110 2
+int orc_grsd_signature(int kind, const float* centroids, const float* cent_normals, int nvox,
+                       const int32_t* types, float leaf, const int32_t* min_b, const int32_t* div_b,
+                       const int32_t* layout, int subdivision_size, int off_x, int off_y, int off_z,
+                       int32_t* subdiv_b, int32_t* hist);
+
+/* libsvm C-SVC / RBF prediction with svm-scale style feature scaling, as
+ * cloud_algos::SVMClassification::process does per point (svm_classification.cpp:134-155):
+ *   value_i = scaleFeature(i, (double)feature_i, ranges, lower, upper)   (svm_classification.h:68-86;
+ *             skipped when fmin == NULL)
+ *   class   = svm_predict(model, nodes)        [EXTERNAL: libsvm, manifest.xml:28, not vendored]
+ * svm_predict for C_SVC restated from the published algorithm: k(x, sv) = exp(-gamma * sum (x-sv)^2)
+ * accumulated in index order, one-vs-one decision values sum_i coef*k - rho in libsvm's pair order,
+ * vote, first maximum wins, label[argmax].  All in double.
+ * features: n x dim floats; labels / nr_sv: nr_class; rho: nr_class*(nr_class-1)/2;
+ * sv_coef: (nr_class-1) x total_sv; sv: total_sv x dim dense.  out: n predicted labels (as float,
+ * like the point_class channel); dec (optional): n x nr_class*(nr_class-1)/2 decision values. */
+int orc_svm_predict(const float* features, int64_t n, int dim, int nr_class, int total_sv, double gamma,
+                    const int32_t* labels, const int32_t* nr_sv, const double* rho, const double* sv_coef,
+                    const double* sv, double lower, double upper, const double* fmin, const double* fmax,
+                    float* out, double* dec);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

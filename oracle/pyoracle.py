@@ -212,5 +212,85 @@ def grsd21(xyz, leaf, r_normals=0.02, rsd_radius_min=0.01, rsd_flags=0, normals_
     return dict(hist21=h, labels=labels[: nv.value].copy(), radii=radii[: nv.value].copy(), nvox=nv.value)
 
 
+SIG_GRSD21, SIG_GRSD325, SIG_PLUSGRSD110 = 0, 1, 2
+SIG_DIM = {0: 21, 1: 325, 2: 110}
+
+
+def voxel_normals(xyz, nrm, leaf):
+    """Un-normalised mean normal of every voxel (V,3), voxel order as voxel_grid()."""
+    L = lib()
+    p = _xyz(xyz)
+    nn = np.ascontiguousarray(nrm, dtype=np.float32)
+    out = np.zeros((max(p.shape[0], 1), 3), np.float32)
+    nv = L.orc_voxel_normals(_ptr(p, C.c_float), _ptr(nn, C.c_float), int(nn.shape[1]), p.shape[0], C.c_float(leaf),
+                             _ptr(out, C.c_float))
+    return out[:nv].copy()
+
+
+def grsd_signature(kind, grid, types, cent_normals=None, subdivision_size=0, off=(0, 0, 0)):
+    """Returns (hist_num, subdiv_b (3,), hist (hist_num, dim) int32)."""
+    L = lib()
+    t = np.ascontiguousarray(types, dtype=np.int32)
+    cent = np.ascontiguousarray(grid["centroids"], np.float32)
+    cn = np.ascontiguousarray(cent_normals, np.float32) if cent_normals is not None else None
+    sb = np.zeros(3, np.int32)
+    args = (int(kind), _ptr(cent, C.c_float), _ptr(cn, C.c_float), int(grid["nvox"]), _ptr(t, C.c_int32),
+            C.c_float(grid["leaf"]), _ptr(grid["min_b"], C.c_int32), _ptr(grid["div_b"], C.c_int32),
+            _ptr(grid["layout"], C.c_int32), int(subdivision_size), int(off[0]), int(off[1]), int(off[2]),
+            _ptr(sb, C.c_int32))
+    hn = L.orc_grsd_signature(*args, None)
+    if hn <= 0:
+        return hn, sb, np.zeros((0, SIG_DIM[kind]), np.int32)
+    h = np.zeros((hn, SIG_DIM[kind]), np.int32)
+    assert L.orc_grsd_signature(*args, _ptr(h, C.c_int32)) == hn
+    return hn, sb, h
+
+
+def grsd_cluster(xyz, leaf, kind=SIG_GRSD21, subdivision_size=0, off=(0, 0, 0), r_normals=0.02, rsd_radius_min=0.01,
+                 rsd_flags=0, normals_in=None, vp=(0.0, 0.0, 0.0), nthreads=0):
+    """Whole recipe for one cluster and any signature: normals -> voxel grid -> voxel RSD -> labels ->
+    signature.  Returns dict(hist_num, subdiv_b, hist, labels, grid, cent_normals)."""
+    p = _xyz(xyz)
+    if normals_in is None:
+        n4, _ = normals(p, r_normals, vp=vp, nthreads=nthreads)
+        nrm = np.ascontiguousarray(n4[:, :3])
+    else:
+        nrm = np.ascontiguousarray(np.asarray(normals_in, np.float32)[:, :3])
+    base = grsd21(p, leaf, r_normals=r_normals, rsd_radius_min=rsd_radius_min, rsd_flags=rsd_flags, normals_in=nrm, vp=vp,
+                  nthreads=nthreads)
+    grid = voxel_grid(p, leaf)
+    grid["leaf"] = leaf
+    cn = voxel_normals(p, nrm, leaf)
+    hn, sb, h = grsd_signature(kind, grid, base["labels"], cn, subdivision_size, off)
+    return dict(hist_num=hn, subdiv_b=sb, hist=h, labels=base["labels"], grid=grid, cent_normals=cn)
+
+
+def svm_predict(model, features, scale=None, want_dec=False):
+    """model: mapping_private_b200.svm_model.SvmModel (or any object with its fields); scale: None or
+    (lower, upper, fmin, fmax).  Returns predicted labels (n,) float32 [and decision values]."""
+    L = lib()
+    f = np.ascontiguousarray(features, dtype=np.float32)
+    n, dim = f.shape
+    assert dim == model.sv.shape[1]
+    k = int(model.labels.shape[0])
+    out = np.zeros(n, np.float32)
+    dec = np.zeros((n, k * (k - 1) // 2), np.float64) if want_dec else None
+    d64 = np.ctypeslib.as_ctypes_type(np.float64)
+    lower, upper, fmin, fmax = (0.0, 0.0, None, None) if scale is None else scale
+    lab = np.ascontiguousarray(model.labels, np.int32)
+    nsv = np.ascontiguousarray(model.nr_sv, np.int32)
+    rho = np.ascontiguousarray(model.rho, np.float64)
+    coef = np.ascontiguousarray(model.sv_coef, np.float64)
+    sv = np.ascontiguousarray(model.sv, np.float64)
+    fmin = None if fmin is None else np.ascontiguousarray(fmin, np.float64)
+    fmax = None if fmax is None else np.ascontiguousarray(fmax, np.float64)
+    rc = L.orc_svm_predict(_ptr(f, C.c_float), C.c_int64(n), int(dim), k, int(sv.shape[0]), C.c_double(model.gamma),
+                           _ptr(lab, C.c_int32), _ptr(nsv, C.c_int32), _ptr(rho, d64), _ptr(coef, d64), _ptr(sv, d64),
+                           C.c_double(lower), C.c_double(upper), _ptr(fmin, d64), _ptr(fmax, d64), _ptr(out, C.c_float),
+                           _ptr(dec, d64))
+    assert rc == 0
+    return (out, dec) if want_dec else out
+
+
 def num_threads():
     return lib().orc_num_threads()

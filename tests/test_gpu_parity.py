@@ -325,3 +325,48 @@ def test_fused_normals_rsd_equals_two_calls(ctx):
         assert seen.sum() == pts.shape[0] - 1  # the NaN point belongs to no shard slice
     finally:
         ctx.set_shard(0, 1)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_grsd_signature_variants_bit_exact(ctx_exact, oracle, kind):
+    """GRSD-21 with subdivisions, GRSD-325 and PlusGRSD-110 (cab_grsd_signatures) against the oracle
+    recipe, per cluster, bit-exact; includes a cluster smaller than the offsets and an empty one."""
+    xyz, off = synth.clusters(10, 1300, 5000, seed_extra=2)
+    off = np.concatenate([off[:4], [off[4]], off[4:]]).astype(np.int32)  # an empty cluster
+    nc = len(off) - 1
+    leaf = 0.025
+    # both sides get the same point normals (a few of them NaN: such voxels count as "to empty")
+    nrm = np.zeros((xyz.shape[0], 3), np.float32)
+    for c in range(nc):
+        if off[c + 1] > off[c]:
+            nrm[off[c]:off[c + 1]] = oracle.normals(xyz[off[c]:off[c + 1]], 0.02)[0][:, :3]
+    nrm[np.random.default_rng(kind).integers(0, xyz.shape[0], 40)] = np.nan
+    hist21 = ctx_exact.grsd_batch(xyz, off, leaf, normals=nrm)
+    vox = ctx_exact.grsd_voxels(nc)
+    for sub, o in [(0, (0, 0, 0)), (2, (0, 0, 0)), (2, (1, 0, 1)), (3, (4, 0, 0))]:
+        got = ctx_exact.grsd_signatures(nc, kind, sub, o)
+        assert got["hist"].shape[1] == cab.SIG_DIM[kind]
+        for c in range(nc):
+            h0, h1 = got["offsets"][c], got["offsets"][c + 1]
+            pts = xyz[off[c]:off[c + 1]]
+            if pts.shape[0] == 0:
+                assert not got["hist"][h0:h1].any()
+                continue
+            want = oracle.grsd_cluster(pts, leaf, kind, sub, o, normals_in=nrm[off[c]:off[c + 1]])
+            v0, v1 = vox["offsets"][c], vox["offsets"][c + 1]
+            assert np.array_equal(vox["labels"][v0:v1], want["labels"])
+            assert h1 - h0 == max(want["hist_num"], 0), (c, sub, o)
+            if want["hist_num"] > 0:
+                assert np.array_equal(got["subdiv_b"][c], want["subdiv_b"])
+                assert np.array_equal(got["hist"][h0:h1], want["hist"]), (c, sub, o)
+        if kind == 0 and sub == 0:
+            assert np.array_equal(got["hist"], hist21)
+    # the sliding boxes partition the voxels when the offsets are zero
+    whole = ctx_exact.grsd_signatures(nc, kind, 0)["hist"]
+    boxes = ctx_exact.grsd_signatures(nc, kind, 2)
+    summed = np.stack([boxes["hist"][boxes["offsets"][c]:boxes["offsets"][c + 1]].sum(0) for c in range(nc)])
+    assert np.array_equal(summed, whole)
+    # state is tied to the cloud: a new upload invalidates it
+    ctx_exact.upload(xyz[:100])
+    with pytest.raises(cab.CabError, match="cab_grsd_batch first"):
+        ctx_exact.grsd_signatures(nc, kind)

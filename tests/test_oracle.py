@@ -308,3 +308,152 @@ def test_grsd21_cluster_generator(oracle):
     for c in range(3):
         out = oracle.grsd21(xyz[off[c]:off[c + 1]], 0.025)
         assert 0 < out["hist21"].sum() <= out["nvox"] * 26  # lower triangle is dropped
+
+
+def _py_signature(kind, grid, types, cn, sub=0, off=(0, 0, 0)):
+    """Independent pure-Python restatement of grsd_colorCHLAC_tools.hpp:305-451 / :462-668 (and :131-294)
+    working on integer voxel coordinates recovered from the dense layout."""
+    div = grid["div_b"].astype(int)
+    lay = grid["layout"].reshape(div[2], div[1], div[0])
+    coord = {int(lay[k, j, i]): (i, j, k) for k in range(div[2]) for j in range(div[1]) for i in range(div[0]) if lay[k, j, i] >= 0}
+    offs = [(i, j, -1) for i in (-1, 0, 1) for j in (-1, 0, 1)] + [(i, -1, 0) for i in (-1, 0, 1)] + [(-1, 0, 0)]
+    offs26 = offs + [(-a, -b, -c) for a, b, c in offs]
+    if sub > 0:
+        if any(div[a] <= off[a] for a in range(3)):
+            return 0, None
+        sb = [int(np.ceil((div[a] - off[a]) * np.float32(1.0 / sub))) for a in range(3)]
+    else:
+        sb = [1, 1, 1]
+    hn = sb[0] * sb[1] * sb[2]
+    dim = {0: 21, 1: 325, 2: 110}[kind]
+    H = np.zeros((hn, dim), np.int64)
+    tri6 = {(i, j): n for n, (i, j) in enumerate((i, j) for i in range(6) for j in range(i, 6))}
+    tri5 = {(i, j): n for n, (i, j) in enumerate((i, j) for i in range(5) for j in range(i, 5))}
+    unit = None
+    if kind == 2:
+        c32 = cn.astype(np.float32)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ln = np.sqrt((c32[:, 0] * c32[:, 0] + c32[:, 1] * c32[:, 1]) + c32[:, 2] * c32[:, 2], dtype=np.float32)
+            unit = c32 / ln[:, None]
+
+    def nbr(v, o):
+        i, j, k = coord[v]
+        a, b, c = i + o[0], j + o[1], k + o[2]
+        if 0 <= a < div[0] and 0 <= b < div[1] and 0 <= c < div[2]:
+            return int(lay[c, b, a])
+        return -1
+
+    for v in range(grid["nvox"]):
+        h = 0
+        if hn != 1:
+            t = [coord[v][a] - off[a] for a in range(3)]
+            if min(t) < 0:
+                continue
+            q = [int(np.floor(np.float32(t[a]) * np.float32(1.0 / sub))) for a in range(3)]
+            h = q[0] + q[1] * sb[0] + q[2] * sb[0] * sb[1]
+        s = int(types[v])
+        if kind == 0:
+            for o in offs26:
+                n = nbr(v, o)
+                t = 5 if n < 0 else int(types[n])
+                if s <= t:
+                    H[h, tri6[(s, t)]] += 1
+        elif kind == 1:
+            for oid, o in enumerate(offs):
+                n = nbr(v, o)
+                if n >= 0:
+                    H[h, s + 5 * int(types[n]) + 25 * oid] += 1
+        else:
+            if not np.all(np.isfinite(unit[v])):
+                continue
+            for o in offs26:
+                n = nbr(v, o)
+                if n < 0 or not np.all(np.isfinite(unit[n])):
+                    H[h, 105 + s] += 1
+                    continue
+                a, b = unit[v], unit[n]
+                cr = np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], np.float32)
+                nm = np.sqrt((cr[0] * cr[0] + cr[1] * cr[1]) + cr[2] * cr[2], dtype=np.float32)
+                d = min(6, int(np.floor(np.sqrt(np.float64(nm)) * 7)))
+                t = int(types[n])
+                if s <= t:
+                    H[h, d * 15 + tri5[(s, t)]] += 1
+    return hn, H
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("sub,off", [(0, (0, 0, 0)), (2, (0, 0, 0)), (3, (1, 0, 2)), (2, (9, 0, 0))])
+def test_signatures_match_python_restatement(oracle, kind, sub, off):
+    rng = np.random.default_rng(100 + kind)
+    leaf = 0.01
+    occ = rng.random((6, 5, 4)) < 0.6
+    ijk = np.argwhere(occ)
+    reps = rng.integers(1, 4, size=len(ijk))
+    base = np.repeat(ijk, reps, axis=0).astype(np.float64)
+    pts = synth.quantize((base + rng.uniform(0.1, 0.9, size=base.shape)) * leaf + np.array([0.3, -0.2, 0.7])).astype(np.float32)
+    nrm = rng.normal(size=pts.shape).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm[rng.integers(0, len(nrm), 5)] = np.nan  # voxels with a NaN mean normal
+    g = oracle.voxel_grid(pts, leaf)
+    g["leaf"] = leaf
+    assert g["nvox"] == len(ijk)
+    types = rng.integers(0, 5, size=g["nvox"]).astype(np.int32)
+    cn = oracle.voxel_normals(pts, nrm, leaf)
+    assert cn.shape == (g["nvox"], 3) and np.isnan(cn).any()
+    hn, sb, h = oracle.grsd_signature(kind, g, types, cn, sub, off)
+    phn, ph = _py_signature(kind, g, types, cn, sub, off)
+    assert hn == phn
+    if hn:
+        assert np.array_equal(h, ph)
+        assert h.sum() > 0
+    if kind == 0:  # the general entry point agrees with the GRSD-21 one
+        hn2, sb2, h2 = oracle.grsd21_subdiv(g, types, sub, off)
+        assert hn2 == hn and np.array_equal(sb2, sb) and np.array_equal(h2, h)
+
+
+def test_signature_hand_block(oracle):
+    """3x3x3 full block, centre SPHERE(3), rest PLANE(1), all voxel normals +z except the centre (+x)."""
+    leaf = 0.01
+    ii, jj, kk = np.meshgrid(range(3), range(3), range(3), indexing="ij")
+    pts = ((np.stack([ii, jj, kk], -1).reshape(-1, 3) + 0.5) * leaf).astype(np.float32)
+    g = oracle.voxel_grid(pts, leaf)
+    g["leaf"] = leaf
+    types = np.ones(27, np.int32)
+    centre = int(g["layout"][1 + 3 + 9])
+    types[centre] = 3
+    cn = np.tile(np.array([[0, 0, 2.0]], np.float32), (27, 1))  # un-normalised on purpose
+    cn[centre] = [0.5, 0, 0]
+    # GRSD-325: 13 half offsets; the centre sees all 13 (src 3 -> nbr 1); its 13 "upper" neighbours see it
+    hn, _, h = oracle.grsd_signature(oracle.SIG_GRSD325, g, types, None)
+    assert hn == 1 and h.shape == (1, 325)
+    h = h[0].reshape(13, 5, 5)  # [offset, nbr, src]
+    assert np.all(h[:, 1, 3] == 1) and np.all(h[:, 3, 1] == 1)
+    occupied_pairs = 8 * 7 + 12 * 11 + 6 * 17 + 26
+    assert h.sum() == occupied_pairs // 2 and h[:, 1, 1].sum() == occupied_pairs // 2 - 26
+    # PlusGRSD-110: parallel normals -> angle bin 0; centre <-> others are orthogonal -> sin = 1 -> bin 6
+    hn, _, p = oracle.grsd_signature(oracle.SIG_PLUSGRSD110, g, types, cn)
+    p = p[0]
+    tri5 = {(i, j): n for n, (i, j) in enumerate((i, j) for i in range(5) for j in range(i, 5))}
+    assert p[0 * 15 + tri5[(1, 1)]] == occupied_pairs - 52
+    assert p[6 * 15 + tri5[(1, 3)]] == 26  # (1 -> 3) ordered pairs; (3 -> 1) is below the diagonal and dropped
+    assert p[105 + 1] == 27 * 26 - occupied_pairs and p[105 + 3] == 0
+    assert p.sum() == (occupied_pairs - 52) + 26 + (27 * 26 - occupied_pairs)
+    # a NaN source normal drops the voxel, a NaN neighbour normal counts as "to empty"
+    cn2 = cn.copy()
+    cn2[centre] = np.nan
+    _, _, q = oracle.grsd_signature(oracle.SIG_PLUSGRSD110, g, types, cn2)
+    q = q[0]
+    assert q[6 * 15 + tri5[(1, 3)]] == 0 and q[105 + 1] == p[105 + 1] + 26 and q[105 + 3] == 0
+
+
+def test_grsd_cluster_recipe_all_kinds(oracle):
+    xyz, off = synth.clusters(2, 1300, 2000, seed_extra=5)
+    pts = xyz[off[0]:off[1]]
+    r21 = oracle.grsd_cluster(pts, 0.025, oracle.SIG_GRSD21)
+    assert np.array_equal(r21["hist"][0], oracle.grsd21(pts, 0.025)["hist21"])
+    r325 = oracle.grsd_cluster(pts, 0.025, oracle.SIG_GRSD325)
+    r110 = oracle.grsd_cluster(pts, 0.025, oracle.SIG_PLUSGRSD110, subdivision_size=2)
+    # every occupied (src, nbr) pair is seen once over the half offsets and twice over all 26
+    occupied = r21["hist"][0].sum() - r21["hist"][0][[5, 10, 14, 17, 19]].sum()
+    assert r325["hist"].sum() * 2 >= occupied  # 21 drops the below-diagonal ordered pairs
+    assert r110["hist_num"] == int(np.prod(r110["subdiv_b"])) and r110["hist"].shape[1] == 110
