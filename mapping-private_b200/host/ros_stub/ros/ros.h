@@ -51,12 +51,18 @@ class Subscriber {};
 
 class NodeHandle {
  public:
-  explicit NodeHandle(const std::string& ns = "") : ns_(ns), params_(std::make_shared<std::map<std::string, double>>()) {}
+  explicit NodeHandle(const std::string& ns = "")
+      : ns_(ns), params_(std::make_shared<std::map<std::string, double>>()), sparams_(std::make_shared<std::map<std::string, std::string>>()) {}
   // rosparam semantics: assign the stored value if present, else the default
   void param(const std::string& key, double& var, const double& def) const { var = has(key) ? (*params_)[key] : def; }
   void param(const std::string& key, int& var, const int& def) const { var = has(key) ? (int)(*params_)[key] : def; }
   void param(const std::string& key, bool& var, const bool& def) const { var = has(key) ? ((*params_)[key] != 0) : def; }
+  void param(const std::string& key, std::string& var, const std::string& def) const {
+    const std::string d = def;  // var and def may alias (nh.param("k", x_, x_))
+    var = sparams_->count(key) ? (*sparams_)[key] : d;
+  }
   void setParam(const std::string& key, double v) { (*params_)[key] = v; }
+  void setParam(const std::string& key, const std::string& v) { (*sparams_)[key] = v; }
   void deleteParam(const std::string& key) { params_->erase(key); }
   bool hasParam(const std::string& key) const { return has(key); }
   template <class M> Publisher advertise(const std::string& topic, int /*queue*/) { return Publisher(topic); }
@@ -64,6 +70,7 @@ class NodeHandle {
   bool has(const std::string& key) const { return params_->count(key) != 0; }
   std::string ns_;
   std::shared_ptr<std::map<std::string, double>> params_;  // shared between copies like a real handle
+  std::shared_ptr<std::map<std::string, std::string>> sparams_;
 };
 
 }  // namespace ros

@@ -10,6 +10,7 @@
 #include <cloud_algos/normal_estimation.h>
 #include <cloud_algos/radius_estimation.h>
 #include <cloud_algos/global_rsd.h>
+#include <cloud_algos/svm_classification.h>
 
 using namespace cloud_algos;
 
@@ -49,6 +50,16 @@ void capi_destroy(void* hv) {
 }
 
 void capi_set_param(void* hv, const char* key, double value) { ((Handle*)hv)->nh.setParam(key, value); }
+void capi_set_param_str(void* hv, const char* key, const char* value) { ((Handle*)hv)->nh.setParam(key, std::string(value)); }
+int capi_set_field_str(void* hv, const char* field, const char* value) {
+  const std::string f(field);
+  if (SVMClassification* a = dynamic_cast<SVMClassification*>(((Handle*)hv)->algo)) {
+    if (f == "model_file_name_") a->model_file_name_ = value; else if (f == "scale_file_name_") a->scale_file_name_ = value;
+    else return -1;
+    return 0;
+  }
+  return -1;
+}
 
 // Public-field assignment after pre(), the way table_memory_grsd.cpp:975-981 pokes GlobalRSD.
 int capi_set_field(void* hv, const char* field, double value) {
@@ -65,6 +76,11 @@ int capi_set_field(void* hv, const char* field, double value) {
   if (NormalEstimation* a = dynamic_cast<NormalEstimation*>(h->algo)) {
     if (f == "radius_") a->radius_ = value; else if (f == "max_nn_") a->max_nn_ = (int)value;
     else if (f == "vp_x_") a->vp_x_ = value; else if (f == "vp_y_") a->vp_y_ = value; else if (f == "vp_z_") a->vp_z_ = value;
+    else return -1;
+    return 0;
+  }
+  if (SVMClassification* a = dynamic_cast<SVMClassification*>(h->algo)) {
+    if (f == "scale_self_") a->scale_self_ = value != 0; else if (f == "scale_file_") a->scale_file_ = value != 0;
     else return -1;
     return 0;
   }
@@ -110,6 +126,9 @@ const char* capi_process(void* hv, const float* xyz, int n, int nchan, const cha
     h->result = a->process(cin);
     if (a->output_valid_) h->out = a->output();
     h->aux = a->getVRSD();
+  } else if (SVMClassification* a = dynamic_cast<SVMClassification*>(h->algo)) {
+    h->result = a->process(cin);
+    if (a->output_valid_) h->out = a->output();
   } else {
     h->result = "unknown plugin type";
   }

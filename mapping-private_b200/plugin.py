@@ -34,6 +34,8 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p]
         L.capi_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.capi_set_field.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.capi_set_param_str.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.capi_set_field_str.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.capi_process.restype = C.c_char_p
         L.capi_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.capi_output_valid.argtypes = [C.c_void_p]
@@ -72,11 +74,18 @@ class Plugin:
         except Exception:
             pass
 
-    def set_param(self, key: str, value: float):
-        self._L.capi_set_param(self._h, key.encode(), float(value))
+    def set_param(self, key: str, value):
+        if isinstance(value, str):
+            self._L.capi_set_param_str(self._h, key.encode(), value.encode())
+        else:
+            self._L.capi_set_param(self._h, key.encode(), float(value))
 
-    def set_field(self, field: str, value: float):
-        if self._L.capi_set_field(self._h, field.encode(), float(value)) != 0:
+    def set_field(self, field: str, value):
+        if isinstance(value, str):
+            rc = self._L.capi_set_field_str(self._h, field.encode(), value.encode())
+        else:
+            rc = self._L.capi_set_field(self._h, field.encode(), float(value))
+        if rc != 0:
             raise AttributeError(field)
 
     def requires_provides(self):

@@ -34,7 +34,28 @@ def read_pcd_xyz(path):
     return np.ascontiguousarray(a[:, :3])
 
 
+def svm_fixture():
+    """The SVM model and scale ranges the reference pipeline loads for GRSD
+    (dyn_obj_store/table_pipeline_grsd.launch: svm/grsd_ijrr.model + .scp), parsed with the repo's own
+    parser and stored as arrays (libsvm model files are data, not source)."""
+    import sys
+
+    sys.path.insert(0, str(OUT.parent.parent))
+    import pkgpath
+
+    pkgpath.load()
+    from mapping_private_b200 import svm_model
+
+    svm = pathlib.Path("/root/reference/cloud_algos/svm")
+    m = svm_model.parse_model((svm / "grsd_ijrr.model").read_text(), 21)
+    lower, upper, fmin, fmax = svm_model.parse_scale((svm / "grsd_ijrr.scp").read_text(), 21)
+    np.savez_compressed(OUT / "svm_grsd_ijrr.npz", gamma=m.gamma, labels=m.labels, nr_sv=m.nr_sv, rho=m.rho,
+                        sv_coef=m.sv_coef, sv=m.sv, lower=lower, upper=upper, fmin=fmin, fmax=fmax)
+    print("svm_grsd_ijrr:", m.nr_class, "classes,", m.total_sv, "SVs, dim", m.dim)
+
+
 def main():
+    svm_fixture()
     data = {}
     for s in SHAPES:
         xyz = read_pcd_xyz(REF / f"noiseless_{s}_blue.pcd")

@@ -25,7 +25,8 @@ def test_discovery_matches_plugins_xml(built):
     xml = (HOST / "plugins.xml").read_text()
     assert '<library path="lib/libcloud_algos">' in xml
     declared = re.findall(r'<class name="([^"]+)" type="([^"]+)" base_class_type="([^"]+)">', xml)
-    assert {d[0] for d in declared} == {"cloud_algos/NormalEstimation", "cloud_algos/LocalRadiusEstimation", "cloud_algos/GlobalRSD"}
+    assert {d[0] for d in declared} == {"cloud_algos/NormalEstimation", "cloud_algos/LocalRadiusEstimation", "cloud_algos/GlobalRSD",
+                                        "cloud_algos/SVMClassification"}
     for name, typ, base in declared:
         assert typ == name.replace("/", "::") and base == "cloud_algos::CloudAlgo"
         p = plugin.Plugin(name)  # pluginlib lookup by the reference's names
@@ -53,6 +54,23 @@ def test_missing_normals_is_reported(built):
         p = plugin.Plugin(name)
         res, out = p.run(pts, {"intensity": np.zeros(100, np.float32)})
         assert res == "missing normals" and out is None and not p.output_valid() and p.num_published() == 0
+
+
+def test_svm_plugin_surface_and_errors(built, tmp_path):
+    svm = plugin.Plugin("cloud_algos/SVMClassification")
+    assert svm.requires_provides() == (["f1"], ["point_class"])  # svm_classification.cpp:27-40
+    assert svm.topic() == "cloud_svm"
+    pts = synth.analytic_shape("plane", 10)
+    res, out = svm.run(pts, {"nx": np.zeros(10, np.float32)})
+    assert res == "missing features" and out is None and not svm.output_valid()
+    feats = {f"f{i}": np.zeros(10, np.float32) for i in range(1, 22)}
+    svm.set_param("model_file_name", str(tmp_path / "nope.model"))
+    res, out = svm.run(pts, feats)
+    assert res == "incorrect model file" and out is None
+    bad = tmp_path / "bad.model"
+    bad.write_text("svm_type nu_svc\nkernel_type rbf\nSV\n")
+    res, _ = svm.run(pts, feats, fields={"model_file_name_": str(bad)})
+    assert res == "incorrect model file"
 
 
 def test_sample_pipeline_yaml_keys(built):
@@ -115,3 +133,50 @@ def test_global_rsd_plugin_against_oracle(built, oracle):
     assert np.array_equal(hist.astype(np.int64), o["hist21"].astype(np.int64))
     vrsd = g.output(1)
     assert np.array_equal(vrsd["channels"]["point_label"].astype(np.int32), o["labels"])
+
+
+@pytest.mark.gpu
+def test_svm_plugin_against_oracle(built, oracle, tmp_path):
+    """GlobalRSD -> SVMClassification the way table_memory_grsd.cpp:974-1018 chains them, with the
+    reference's grsd_ijrr model and scale ranges written back to files in libsvm's formats."""
+    from mapping_private_b200 import svm_model
+
+    z = np.load(ROOT / "tests" / "golden" / "svm_grsd_ijrr.npz")
+    m = svm_model.SvmModel(float(z["gamma"]), z["labels"], z["nr_sv"], z["rho"], z["sv_coef"], z["sv"])
+    (tmp_path / "grsd.model").write_text(svm_model.format_model(m))
+    scp = "x\n-1 1\n" + "".join(f"{i + 1} {z['fmin'][i]:.9g} {z['fmax'][i]:.9g}\n" for i in range(21))
+    (tmp_path / "grsd.scp").write_text(scp)
+    scale = (-1.0, 1.0, z["fmin"], z["fmax"])
+    xyz, off = synth.clusters(3, 2000, 4000, seed_extra=6)
+    g = plugin.Plugin("cloud_algos/GlobalRSD")
+    svm = plugin.Plugin("cloud_algos/SVMClassification")
+    svm.set_param("model_file_name", str(tmp_path / "grsd.model"))
+    svm.set_param("scale_file_name", str(tmp_path / "grsd.scp"))
+    for c in range(3):
+        pts = xyz[off[c]:off[c + 1]]
+        nrm = np.nan_to_num(oracle.normals(pts, 0.02)[0][:, :3], nan=0.0)
+        res, grsd = g.run(pts, {"nx": nrm[:, 0], "ny": nrm[:, 1], "nz": nrm[:, 2]}, fields={"min_voxel_pts_": 0})
+        assert res == "ok"
+        res, out = svm.run(grsd["points"], grsd["channels"])
+        assert res == "ok" and svm.output_valid() and list(out["channels"])[-1] == "point_class"
+        hist = np.array([[grsd["channels"][f"f{i}"][0] for i in range(1, 22)]], np.float32)
+        assert out["channels"]["point_class"][0] == oracle.svm_predict(m, hist, scale=scale)[0]
+    # many points at once, scale_self, and no scaling at all
+    rng = np.random.default_rng(2)
+    F = (rng.random((500, 21)) ** 2 * np.maximum(z["fmax"], 1)).astype(np.float32)
+    chans = {f"f{i + 1}": F[:, i] for i in range(21)}
+    chans["point_label"] = np.full(500, 31, np.float32)
+    pts = np.zeros((500, 3), np.float32)
+    res, out = svm.run(pts, chans)
+    assert np.array_equal(out["channels"]["point_class"], oracle.svm_predict(m, F, scale=scale))
+    res, out = svm.run(pts, chans, fields={"scale_file_": 0})
+    assert np.array_equal(out["channels"]["point_class"], oracle.svm_predict(m, F))
+    # scale_self_: per-channel min / max with the reference's update rule (first value only lowers the minimum)
+    lo = np.full(21, np.finfo(np.float64).max)
+    hi = np.full(21, -np.finfo(np.float64).max)
+    for row in F.astype(np.float64):
+        low = lo > row
+        lo = np.where(low, row, lo)
+        hi = np.where(~low & (hi < row), row, hi)
+    res, out = svm.run(pts, chans, fields={"scale_self_": 1})
+    assert np.array_equal(out["channels"]["point_class"], oracle.svm_predict(m, F, scale=(-1.0, 1.0, lo, hi)))
