@@ -370,3 +370,29 @@ def test_grsd_signature_variants_bit_exact(ctx_exact, oracle, kind):
     ctx_exact.upload(xyz[:100])
     with pytest.raises(cab.CabError, match="cab_grsd_batch first"):
         ctx_exact.grsd_signatures(nc, kind)
+
+
+def test_fast_normals_count_neighbours_exactly_at_the_boundary(ctx, oracle):
+    """The fast normals pass decides most candidates with the centred-monomial test and re-tests the
+    ones near the radius with the exact rule: neighbour counts must still equal the oracle's on a
+    cloud with thousands of pairs exactly at, and one ulp beyond, the radius."""
+    r = np.float32(0.0625)
+    rng = np.random.default_rng(9)
+    base = synth.quantize(rng.uniform(0.2, 0.6, size=(6000, 3)))
+    extra = []
+    for p in base[:1500]:
+        extra.append(p + np.array([r, 0, 0], np.float32))
+        extra.append(p + np.array([0, np.nextafter(r, np.float32(1)), 0], np.float32))
+        extra.append(p - np.array([0, 0, r], np.float32))
+        extra.append(p + np.array([0, -np.nextafter(r, np.float32(0)), 0], np.float32))
+    pts = np.concatenate([base, np.array(extra, np.float32)]).astype(np.float32)
+    for cloud in (pts, pts + np.float32(37.5), synth.tabletop(30_000, noise_sigma=0.0005)):
+        rr = float(r) if cloud is not None and cloud.shape[0] == pts.shape[0] else 0.02
+        ctx.upload(cloud)
+        ctx.build_grid(rr)
+        n4 = ctx.normals(rr)
+        o4, ok = oracle.normals(cloud, rr)
+        assert ctx.profile()["neighbour_sum"] == int(ok.sum())
+        good = ~np.isnan(o4[:, 0])
+        assert np.array_equal(np.isnan(n4[:, 0]), ~good)
+        assert np.mean(_angle(n4[good, :3], o4[good, :3]) > 1e-3) < 1e-2  # random 3D cloud: ill-conditioned normals allowed
