@@ -32,6 +32,7 @@ namespace cab {
 namespace {
 
 constexpr int kMaxDiv = 64;
+constexpr float kBinBias = 1.0f / 1024.0f;  // >> error of the rsqrt bin estimate (<= 64 bins * 4e-7), << 1
 
 struct RsdArgs {
   GridView g;
@@ -86,7 +87,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ChunkTile* tiles = reinterpret_cast<ChunkTile*>(smem_raw);                 // [W]
   float2* bins = reinterpret_cast<float2*>(tiles + kWarpsPerBlock);          // [W][ndiv][32]
-  float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * a.ndiv * kWarp);  // [ndiv+1]
+  float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * a.ndiv * kWarp);  // [ndiv+1], padded to a multiple of 4
+  int* self_slot = reinterpret_cast<int*>(thr + ((a.ndiv + 4) & ~3)) + (threadIdx.x & ~31);  // [W][32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ndiv = a.ndiv;
   for (int i = threadIdx.x; i <= ndiv; i += blockDim.x) thr[i] = a.bin_thr[i];
@@ -120,9 +122,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
       const float4 cn = valid ? a.nrm[j] : make_float4(0.f, 0.f, 0.f, 0.f);
       const unsigned finite_mask = __ballot_sync(kFull, isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z));
       unsigned mask = chunk_hit_mask(tile, qx, qy, qz, r2);
-      if (!kUseThr) k += __popc(mask);
-      // non-finite normals never contribute
-      if (!kUseThr) mask &= q_ok ? finite_mask : 0u;
+      if (!kUseThr) {
+        k += __popc(mask);
+        // non-finite normals never contribute
+        mask &= q_ok ? finite_mask : 0u;
+        // the query itself is skipped (:150 starts at ni = 1).  The packet's queries are the sorted points
+        // [start, start + count): the lane that staged one of them tells the owner which bit to drop.
+        self_slot[lane] = -1;
+        __syncwarp();
+        const int own = j - pc.start;
+        if (valid && own >= 0 && own < pc.count) self_slot[own] = lane;
+        __syncwarp();
+        const int sb = self_slot[lane];
+        if (sb >= 0) mask &= ~(1u << sb);
+      }
       int iters = __reduce_max_sync(kFull, __popc(mask));
 #pragma unroll 1
       for (; iters > 0; --iters) {
@@ -132,9 +145,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
         if (mask != 0) {
           mask ^= 1u << m;
           const float d2 = d2_rule(cx, cy, cz, qx, qy, qz);
-          // the query itself is skipped (:150 starts at ni = 1); only a zero distance can be the query
-          bool use = !(d2 == 0.f && tile->idx[m] == pc.qi);
+          bool use = true;
           if (kUseThr) {
+            // the query itself is skipped (:150 starts at ni = 1); only a zero distance can be the query
+            use = !(d2 == 0.f && tile->idx[m] == pc.qi);
             const bool in = d2 < td2 || (d2 == td2 && g.perm[tile->idx[m]] <= tidx);
             k += in ? 1 : 0;
             use = use && in && q_ok && ((finite_mask >> m) & 1u);
@@ -142,16 +156,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
           if (use) {
             // clamping to [-1, 1] (:158-159) is monotone, so it is applied to the extremes only
             const float cs = __fadd_rn(__fadd_rn(__fmul_rn(nq.x, nx), __fmul_rn(nq.y, ny)), __fmul_rn(nq.z, nz));
-            int b = min(__float2int_rz(d2 * rsqrt_approx(d2) * bscale), last_bin);  // d2 == 0 -> NaN -> 0
-            const unsigned ta = thr_addr + 4u * b;
-            const float tlo = lds_f32(ta), thi = lds_f32(ta + 4);
-            b += (d2 >= thi ? 1 : 0) - (d2 < tlo ? 1 : 0);
+            // distance bin: an estimate biased low by kBinBias (the rsqrt estimate is good to ~3e-5 bins), so the
+            // bin is the estimate or the next one; the exact fp32 d2 threshold decides (d2 == 0 -> NaN -> 0)
+            const int be = min(__float2int_rz(fmaf(d2 * rsqrt_approx(d2), bscale, -kBinBias)), last_bin);
+            const int b = be + (d2 >= lds_f32(thr_addr + 4u * be + 4u) ? 1 : 0);
             const unsigned ba = bins_addr + (unsigned)(kWarp * sizeof(float2)) * b;
-            float2 v = lds_f32x2(ba);
-            const float ac = fabsf(cs);
-            if (ac < fabsf(v.x)) v.x = cs;
-            if (ac >= fabsf(v.y)) v.y = cs;
-            sts_f32x2(ba, v);
+            if constexpr (kExact) {
+              float2 v = lds_f32x2(ba);
+              const float ac = fabsf(cs);
+              if (ac < fabsf(v.x)) v.x = cs;
+              if (ac >= fabsf(v.y)) v.y = cs;
+              sts_f32x2(ba, v);
+            } else {
+              // the fast fit only needs |cosine| (acosf(|c|)): non-negative floats order like their bit
+              // patterns, so the extremes are two fire-and-forget shared-memory atomics on the lane's own slot
+              const unsigned ua = __float_as_uint(fabsf(cs));
+              asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(ba), "r"(ua) : "memory");
+              asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(ba + 4u), "r"(ua) : "memory");
+            }
           }
         }
       }
@@ -271,7 +293,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   a.plane_radius = plane_radius;
   a.stats = (unsigned long long*)ctx->b_stats.p;
   const size_t smem = (size_t)kWarpsPerBlock * sizeof(ChunkTile) + (size_t)kWarpsPerBlock * ndiv * kWarp * sizeof(float2) +
-                      (ndiv + 1) * sizeof(float);
+                      (size_t)((ndiv + 4) & ~3) * sizeof(float) + (size_t)kWarpsPerBlock * kWarp * sizeof(int);
   const int np = a.p1 - a.p0;
   if (np > 0) {
     const unsigned blocks = (np + kWarpsPerBlock - 1) / kWarpsPerBlock;
