@@ -426,9 +426,19 @@ def main():
 
         vp0 = (C.c_float * 3)(0.0, 0.0, 0.0)
 
+        my_lo, my_hi = shard.split_range(n, world)[rank]
+        d_full = torch.empty((n, 3), dtype=torch.float32, device=dev) if world > 1 else None
+
         def e2e_step():
-            ctx._check(L.cab_upload_cloud(ctx._h, fp(h_xyz), C.c_int64(n), C.c_int32(3)), "cab_upload_cloud")
-            ctx.n = n
+            if world == 1:
+                ctx._check(L.cab_upload_cloud(ctx._h, fp(h_xyz), C.c_int64(n), C.c_int32(3)), "cab_upload_cloud")
+                ctx.n = n
+            else:
+                # every rank uploads 1/world of the cloud over PCIe, the slices are all-gathered over NVLink
+                d_slice = h_xyz[my_lo:my_hi].to(dev, non_blocking=True)
+                shard.gather_cloud(d_full, d_slice, rank, world)
+                torch.cuda.synchronize()
+                ctx.set_cloud_device(d_full.data_ptr(), n, 3)
             ctx.build_grid(RADIUS)
             # both passes in one call: the normals leave on the copy stream while the RSD kernel runs.
             # world > 1: each rank returns its own slice (sorted order) plus the input indices it belongs to
@@ -451,11 +461,11 @@ def main():
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": n / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(n * 12),
+        e2e = {"value": n / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(n * 12),  # summed over ranks
                "d2h_bytes_per_step": int(n * 24) if world == 1 else int(n * 28), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
                "path": ("cab_upload_cloud -> cab_build_grid -> cab_normals_rsd (normals D2H overlaps the RSD kernel), pinned host buffers" if world == 1 else
-                        "per rank: cab_upload_cloud (full cloud) -> cab_build_grid -> cab_normals_rsd, CAB_OUT_SHARD_SORTED "
-                        "(own slice + input indices), pinned host buffers; h2d bytes are per rank, d2h bytes summed over ranks")}
+                        "per rank: H2D of 1/N of the cloud + NCCL all-gather of the slices -> cab_set_cloud_device -> cab_build_grid -> "
+                        "cab_normals_rsd, CAB_OUT_SHARD_SORTED (own slice + input indices), pinned host buffers; bytes summed over ranks")}
 
     # ---- CPU baseline (oracle port) on rank 0 at N = 1 ---------------------------------------
     cpu = None

@@ -50,6 +50,10 @@ typedef struct cab_timings {
   int64_t neighbour_sum; /* sum over queries of in-radius neighbours of the last normals/rsd pass */
   int64_t candidate_sum; /* sum over queries of candidates tested in that pass */
   int64_t kernel_launches; /* kernels launched by this library since cab_create (own + CUB) */
+  int64_t n_sorted; /* points radix-sorted by the last cab_build_grid: n_valid, or only the shard's own cells
+                       plus the cells its halo needs when the context is one shard of several (cab_set_shard) */
+  float knn_ms;       /* last cab_knn_mean_distance / cab_statistical_outliers: all grid rounds */
+  int32_t knn_rounds; /* grids built by it (the cell edge doubles until every query has its k neighbours) */
 } cab_timings;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
@@ -76,8 +80,11 @@ int cab_set_cloud_device(cab_ctx* ctx, const float* d_xyz, int64_t n, int32_t st
  * (row, x) keys, cell offsets, 32-query packets.  `cell` must be >= every radius used later. */
 int cab_build_grid(cab_ctx* ctx, float cell);
 
-/* Query sharding for multi-GPU runs: this context only computes packets
- * [rank*P/world, (rank+1)*P/world) of the sorted order. Default (0,1). */
+/* Query sharding for multi-GPU runs: this context only computes a contiguous range of the packets of
+ * the sorted order (cost-balanced split, identical on every rank).  Default (0,1).  With world > 1 the
+ * next cab_build_grid still builds the full cell table and packet list (they follow from the cell
+ * histogram) but sorts only the points of the cells this shard reads; cab_download then returns this
+ * shard's rows only -- use cab_download_sorted / CAB_OUT_SHARD_SORTED. */
 int cab_set_shard(cab_ctx* ctx, int32_t rank, int32_t world);
 /* Sorted-order element range [begin, end) covered by this context's shard. */
 int cab_shard_range(const cab_ctx* ctx, int64_t* begin, int64_t* end);
@@ -180,6 +187,22 @@ int cab_svm_predict(cab_ctx* ctx, const float* features, int64_t n, int32_t dim,
  * f_i = (float)count_i as the GlobalRSD plugin emits them): cluster -> class without a host round
  * trip of the features.  point_class: nclusters floats. */
 int cab_svm_predict_grsd(cab_ctx* ctx, float* point_class);
+
+/* ---- statistical outlier removal (next row: cloud_algos/StatisticalNoiseRemoval) ----------
+ * Replaces the kd-tree k-NN loop and the statistics of StatisticalNoiseRemoval::process
+ * (cloud_algos/src/noise_removal.cpp:84-136) on the uploaded cloud:
+ *   avg[cp] = mean distance from cp to its k - 1 nearest neighbours (k = neighborhood_size_ counts cp
+ *             itself, which is skipped, :102-111), k-NN under the documented d2 rule, ties by index;
+ *   mean / stddev of avg over the cloud, fp64, summed in input order (:112-121);
+ *   keep[cp] = |avg[cp] - mean| < alpha * stddev (:131).
+ * Non-finite points get avg = NaN, stay out of the statistics and are never kept.  cell_hint > 0 sets
+ * the edge of the first search grid (a guess of the k-th neighbour distance), <= 0 derives it from the
+ * cloud; the edge doubles until every query has k points within one edge.  avg / keep / mean / stddev
+ * may be NULL.  cab_statistical_outliers returns the number of kept points or < 0; errors mirror the
+ * plugin's checks (k < 2, alpha < 0, fewer than k points: noise_removal.cpp:51-62). */
+int cab_knn_mean_distance(cab_ctx* ctx, int32_t k, float cell_hint, double* avg);
+int64_t cab_statistical_outliers(cab_ctx* ctx, int32_t k, double alpha, float cell_hint, uint8_t* keep,
+                                 double* avg, double* mean_out, double* stddev_out);
 
 /* ---- device plumbing (bench / multi-GPU) ---------------------------------------------- */
 #define CAB_BUF_POS_SORTED 0  /* float4[n]  x,y,z,0 in sorted order */

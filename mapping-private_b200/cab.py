@@ -24,7 +24,7 @@ BUF_POS_SORTED, BUF_NRM_SORTED, BUF_RSD_SORTED, BUF_PERM = 0, 1, 2, 3
 EXPORTS = [
     "cab_create", "cab_destroy", "cab_last_error", "cab_upload_cloud", "cab_upload_clusters",
     "cab_set_cloud_device", "cab_build_grid", "cab_set_shard", "cab_shard_range", "cab_normals",
-    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd",
+    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd", "cab_knn_mean_distance", "cab_statistical_outliers",
     "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_profile", "cab_version",
 ]
 
@@ -43,7 +43,7 @@ class Timings(C.Structure):
         ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
         ("n_points", C.c_int64), ("n_valid", C.c_int64), ("n_packets", C.c_int64), ("n_rows", C.c_int64),
         ("n_cells", C.c_int64), ("neighbour_sum", C.c_int64), ("candidate_sum", C.c_int64),
-        ("kernel_launches", C.c_int64),
+        ("kernel_launches", C.c_int64), ("n_sorted", C.c_int64), ("knn_ms", C.c_float), ("knn_rounds", C.c_int32),
     ]
 
     def as_dict(self):
@@ -70,6 +70,7 @@ def lib():
         L.cab_neighbors_debug.restype = C.c_int64
         L.cab_grsd_voxels.restype = C.c_int64
         L.cab_grsd_signatures.restype = C.c_int64
+        L.cab_statistical_outliers.restype = C.c_int64
         L.cab_device_ptr.restype = C.c_void_p
         L.cab_device_ptr.argtypes = [C.c_void_p, C.c_int32]
         L.cab_stream.restype = C.c_void_p
@@ -256,6 +257,24 @@ class Context:
         if total:
             self._check(self._L.cab_grsd_signatures(*args, _ip(hist), C.c_int64(total)), "cab_grsd_signatures")
         return dict(offsets=offs, subdiv_b=sb, hist=hist)
+
+    # ---- statistical outlier removal ---------------------------------------------------
+    def knn_mean_distance(self, k: int, cell_hint: float = 0.0):
+        avg = np.zeros(self.n, np.float64)
+        self._check(self._L.cab_knn_mean_distance(self._h, C.c_int32(k), C.c_float(cell_hint),
+                                                  avg.ctypes.data_as(C.POINTER(C.c_double))), "cab_knn_mean_distance")
+        return avg
+
+    def statistical_outliers(self, k: int = 10, alpha: float = 3.0, cell_hint: float = 0.0):
+        """Returns dict(keep bool (n,), avg float64 (n,), mean, stddev, kept)."""
+        keep = np.zeros(self.n, np.uint8)
+        avg = np.zeros(self.n, np.float64)
+        mean, std = C.c_double(), C.c_double()
+        kept = self._check(self._L.cab_statistical_outliers(self._h, C.c_int32(k), C.c_double(alpha), C.c_float(cell_hint),
+                                                            keep.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                            avg.ctypes.data_as(C.POINTER(C.c_double)), C.byref(mean), C.byref(std)),
+                           "cab_statistical_outliers")
+        return dict(keep=keep.astype(bool), avg=avg, mean=mean.value, stddev=std.value, kept=int(kept))
 
     # ---- SVM ---------------------------------------------------------------------------
     def svm_set_model(self, model, scale=None):

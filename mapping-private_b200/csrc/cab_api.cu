@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) gather_normals_kernel(const float* __rest
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int j = perm[i];
+  if (j < 0) return;  // position not held by this shard (sharded sort)
   out[i] = make_float4(nx[j], ny[j], nz[j], 0.f);
 }
 
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const int* __restrict__ 
   int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= end) return;
   int j = perm[i];
+  if (j < 0) return;  // position not held by this shard (sharded sort)
   if (out4) out4[j] = nrm[i];
   if (out_a) {
     float2 v = rsd[i];
@@ -257,7 +259,7 @@ void cab_destroy(cab_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->b_xyz, &ctx->b_domoff, &ctx->b_domid, &ctx->b_bounds, &ctx->b_domains, &ctx->b_keys[0],
-                    &ctx->b_keys[1], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
+                    &ctx->b_keys[1], &ctx->b_keys[2], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_vals[2], &ctx->b_needpt, &ctx->b_substart, &ctx->b_knn_avg, &ctx->b_knn_done, &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
                     &ctx->b_cellcnt, &ctx->b_cellstart, &ctx->b_rowpk, &ctx->b_packets, &ctx->b_nrm, &ctx->b_nrm_in,
                     &ctx->b_rsd, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
                     &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_halo_list, &ctx->b_rowflag, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) key_kernel(const float* __restrict__ xyz,
     atomicAdd(cellcnt + dm.cell_base + row_local * dm.nx + (xf >> dm.xshift), 1);
   }
   keys[i] = (KeyT)key;
-  vals[i] = i;
+  if (vals) vals[i] = i;
 }
 
 __global__ void __launch_bounds__(256) reorder_kernel(const float* __restrict__ xyz, int stride, int n,
@@ -186,18 +186,29 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(const Domain* __restr
   packets[p] = Packet{a, b - a, (int)((c0 - dm.cell_base) / dm.nx), d};
 }
 
+// Cells of a row covered by the sorted positions [s0, s1] (both inside the row): the cell holding s is the
+// last one whose start is <= s.  Needs only the cell table, not the sorted points.
+__device__ __forceinline__ int cell_of_position(const int* __restrict__ row_start, int nx, int s) {
+  int lo = 0, hi = nx;  // largest c in [0, nx) with row_start[c] <= s
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (row_start[mid] <= s) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 // cost model of a packet for the multi-GPU split: the candidates its queries will be tested against
 __global__ void __launch_bounds__(256) packet_cost_kernel(const Domain* __restrict__ domains, const Packet* __restrict__ packets,
-                                                          int n_packets, const float4* __restrict__ pos,
-                                                          const int* __restrict__ cell_start, float inv_cell,
+                                                          int n_packets, const int* __restrict__ cell_start,
                                                           long long* __restrict__ cost) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_packets) return;
   const Packet pk = packets[p];
   const Domain dm = domains[pk.domain];
   const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
-  const int cxlo = max((xfine_coord(pos[pk.start].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift) - 1, 0);
-  const int cxhi = min((xfine_coord(pos[pk.start + pk.count - 1].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift) + 1, dm.nx - 1);
+  const int* row = cell_start + dm.cell_base + (long long)pk.row_local * dm.nx;
+  const int cxlo = max(cell_of_position(row, dm.nx, pk.start) - 1, 0);
+  const int cxhi = min(cell_of_position(row, dm.nx, pk.start + pk.count - 1) + 1, dm.nx - 1);
   long long c = 0;
   for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1); ++z)
     for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1); ++y) {
@@ -209,34 +220,36 @@ __global__ void __launch_bounds__(256) packet_cost_kernel(const Domain* __restri
 
 // cells touched by the shard's own packets
 __global__ void __launch_bounds__(256) mark_cells_kernel(const Domain* __restrict__ domains, const Packet* __restrict__ packets,
-                                                         int p0, int p1, const float4* __restrict__ pos, float inv_cell,
+                                                         int p0, int p1, const int* __restrict__ cell_start,
                                                          unsigned char* __restrict__ cell_flag) {
   const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= p1) return;
   const Packet pk = packets[p];
   const Domain dm = domains[pk.domain];
-  const int c0 = xfine_coord(pos[pk.start].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift;
-  const int c1 = xfine_coord(pos[pk.start + pk.count - 1].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift;
   const long long base = dm.cell_base + (long long)pk.row_local * dm.nx;
+  const int c0 = cell_of_position(cell_start + base, dm.nx, pk.start);
+  const int c1 = cell_of_position(cell_start + base, dm.nx, pk.start + pk.count - 1);
   for (int c = c0; c <= c1; ++c) cell_flag[base + c] = 1;
 }
 
 // A packet needs normals on this rank if it is the shard's own or touches a cell adjacent (3x3x3) to
 // a cell of the shard: every candidate of the shard's RSD pass then has a locally computed normal
-// and no exchange between the two passes is needed.
+// and no exchange between the two passes is needed.  With need_cell != nullptr the cells that hold the
+// candidates of every such packet are marked as well: only their points have to be sorted on this rank.
 __global__ void __launch_bounds__(256) flag_halo_kernel(const Domain* __restrict__ domains, const Packet* __restrict__ packets,
-                                                        int n_packets, int p0, int p1, const float4* __restrict__ pos,
-                                                        float inv_cell, const unsigned char* __restrict__ cell_flag,
-                                                        unsigned char* __restrict__ flag) {
+                                                        int n_packets, int p0, int p1, const int* __restrict__ cell_start,
+                                                        const unsigned char* __restrict__ cell_flag,
+                                                        unsigned char* __restrict__ flag, unsigned char* __restrict__ need_cell) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_packets) return;
   unsigned char f = (p >= p0 && p < p1) ? 1 : 0;
+  const Packet pk = packets[p];
+  const Domain dm = domains[pk.domain];
+  const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
+  const int* row = cell_start + dm.cell_base + (long long)pk.row_local * dm.nx;
+  const int c0 = max(cell_of_position(row, dm.nx, pk.start) - 1, 0);
+  const int c1 = min(cell_of_position(row, dm.nx, pk.start + pk.count - 1) + 1, dm.nx - 1);
   if (!f) {
-    const Packet pk = packets[p];
-    const Domain dm = domains[pk.domain];
-    const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
-    const int c0 = max((xfine_coord(pos[pk.start].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift) - 1, 0);
-    const int c1 = min((xfine_coord(pos[pk.start + pk.count - 1].x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift) + 1, dm.nx - 1);
     for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1) && !f; ++z)
       for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1) && !f; ++y) {
         const long long base = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
@@ -245,6 +258,66 @@ __global__ void __launch_bounds__(256) flag_halo_kernel(const Domain* __restrict
       }
   }
   flag[p] = f;
+  if (f && need_cell)
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1); ++z)
+      for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1); ++y) {
+        const long long base = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
+        for (int c = c0; c <= c1; ++c) need_cell[base + c] = 1;
+      }
+}
+
+// ---- sharded sort (multi-GPU, one domain): only the points of the needed cells are sorted on this rank ----
+// cell of a sort key: row = key >> xbits, cell x = (key & mask) >> xshift
+template <typename KeyT>
+__device__ __forceinline__ long long cell_of_key(KeyT key, int xbits, int xshift, int nx, unsigned long long n_rows) {
+  const unsigned long long row = (unsigned long long)key >> xbits;
+  if (row >= n_rows) return -1;  // sentinel row: non-finite point
+  const unsigned xf = (unsigned)((unsigned long long)key & ((1ull << xbits) - 1ull));
+  return (long long)row * nx + (xf >> xshift);
+}
+
+// flag functor of the selection: does point i lie in a cell this shard needs?
+template <typename KeyT>
+struct NeedPoint {
+  const KeyT* keys;
+  const unsigned char* need_cell;
+  int xbits, xshift, nx;
+  unsigned long long n_rows;
+  __device__ __forceinline__ bool operator()(int i) const {
+    const long long c = cell_of_key(keys[i], xbits, xshift, nx, n_rows);
+    return c >= 0 && need_cell[c] != 0;
+  }
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256) gather_keys_kernel(const KeyT* __restrict__ keys, const int* __restrict__ idx, int m,
+                                                          KeyT* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < m) out[j] = keys[idx[j]];
+}
+
+__global__ void __launch_bounds__(256) masked_count_kernel(const int* __restrict__ cellcnt, const unsigned char* __restrict__ need_cell,
+                                                           long long n_cells, int* __restrict__ out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c <= n_cells) out[c] = (c < n_cells && need_cell[c]) ? cellcnt[c] : 0;
+}
+
+// j-th element of the sorted subset -> its position in the full sorted order: every needed cell is complete
+// in the subset, so the rank inside the cell is j minus the subset's start of that cell.
+template <typename KeyT>
+__global__ void __launch_bounds__(256) scatter_sorted_kernel(const float* __restrict__ xyz, int stride, int m,
+                                                             const KeyT* __restrict__ skeys, const int* __restrict__ svals,
+                                                             int xbits, int xshift, int nx, unsigned long long n_rows,
+                                                             const int* __restrict__ cell_start, const int* __restrict__ sub_start,
+                                                             float4* __restrict__ pos, int* __restrict__ perm) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const long long c = cell_of_key(skeys[j], xbits, xshift, nx, n_rows);
+  const int gp = cell_start[c] + (j - sub_start[c]);
+  const int i = svals[j];
+  const float* p = xyz + (size_t)i * stride;
+  pos[gp] = make_float4(p[0], p[1], p[2], 0.f);
+  perm[gp] = i;
 }
 
 // split[g] = first packet whose inclusive cost prefix reaches g/world of the total
@@ -264,18 +337,13 @@ __global__ void split_kernel(const long long* __restrict__ cum, int n_packets, i
 
 }  // namespace
 
-int build_grid(cab_ctx* ctx, float cell) {
-  if (!ctx->have_cloud) return fail(ctx, CAB_ERR_STATE, "cab_build_grid: no cloud uploaded");
-  if (!(cell > 0.f) || !std::isfinite(cell)) return fail(ctx, CAB_ERR_ARG, "cab_build_grid: cell must be > 0");
-  const int n = (int)ctx->n;
+// Per-domain bounding boxes and finite-point counts of the uploaded cloud -> ctx->dom_bounds / dom_count.
+int compute_bounds(cab_ctx* ctx) {
   const int nd = ctx->n_domains;
   cudaStream_t st = ctx->stream;
-  ctx->have_grid = ctx->have_normals = ctx->have_rsd = false;
-  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-
   // ---- bounds per domain --------------------------------------------------------------
   std::vector<Chunk> chunks;
-  const int kChunk = 1 << 16;
+  const int kChunk = 1 << 13;  // ~2400 blocks for 20 M points: enough loads in flight to stream at HBM speed
   for (int d = 0; d < nd; ++d) {
     int b = ctx->dom_offsets[d], e = ctx->dom_offsets[d + 1];
     if (b == e) chunks.push_back(Chunk{d, b, e});
@@ -307,14 +375,35 @@ int build_grid(cab_ctx* ctx, float cell) {
   CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->b_bounds.p, (size_t)nd * 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
 
+  const unsigned* hb = (const unsigned*)ctx->h_pin;
+  ctx->dom_bounds.assign((size_t)nd * 6, 0.f);
+  ctx->dom_count.assign(nd, 0u);
+  for (int d = 0; d < nd; ++d) {
+    ctx->dom_count[d] = hb[8 * d + 6];
+    if (hb[8 * d + 6])
+      for (int a = 0; a < 6; ++a) ctx->dom_bounds[6 * (size_t)d + a] = ord2f(hb[8 * d + a]);
+  }
+  return CAB_OK;
+}
+
+int build_grid(cab_ctx* ctx, float cell) {
+  if (!ctx->have_cloud) return fail(ctx, CAB_ERR_STATE, "cab_build_grid: no cloud uploaded");
+  if (!(cell > 0.f) || !std::isfinite(cell)) return fail(ctx, CAB_ERR_ARG, "cab_build_grid: cell must be > 0");
+  const int n = (int)ctx->n;
+  const int nd = ctx->n_domains;
+  cudaStream_t st = ctx->stream;
+  ctx->have_grid = ctx->have_normals = ctx->have_rsd = false;
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+
+  if (int rc = compute_bounds(ctx)) return rc;
+
   // ---- domain geometry (host, tiny) ---------------------------------------------------
   double max_abs = 0;
-  const unsigned* hb = (const unsigned*)ctx->h_pin;
   int64_t n_valid = 0;
   for (int d = 0; d < nd; ++d) {
-    if (hb[8 * d + 6] == 0) continue;
-    n_valid += hb[8 * d + 6];
-    for (int a = 0; a < 6; ++a) max_abs = std::max(max_abs, (double)std::fabs(ord2f(hb[8 * d + a])));
+    if (ctx->dom_count[d] == 0) continue;
+    n_valid += ctx->dom_count[d];
+    for (int a = 0; a < 6; ++a) max_abs = std::max(max_abs, (double)std::fabs(ctx->dom_bounds[6 * (size_t)d + a]));
   }
   // effective cell: >= requested + slack for fp32 rounding of (v - origin) * inv_cell
   double ulp = std::ldexp(1.0, (max_abs > 0 ? (int)std::floor(std::log2(max_abs)) : 0) - 23);
@@ -323,27 +412,20 @@ int build_grid(cab_ctx* ctx, float cell) {
   ctx->cell_eff = (float)cell_eff;
   ctx->inv_cell = 1.0f / ctx->cell_eff;
   ctx->domains.assign(nd, Domain{});
-  ctx->dom_bounds.assign((size_t)nd * 6, 0.f);
-  ctx->dom_count.assign(nd, 0u);
-  for (int d = 0; d < nd; ++d) {
-    ctx->dom_count[d] = hb[8 * d + 6];
-    if (hb[8 * d + 6])
-      for (int a = 0; a < 6; ++a) ctx->dom_bounds[6 * (size_t)d + a] = ord2f(hb[8 * d + a]);
-  }
   int64_t rows = 0, cells = 0;
   const int64_t budget = ctx->cfg.max_table_cells > 0 ? ctx->cfg.max_table_cells : ((int64_t)1 << 28);
   for (int d = 0; d < nd; ++d) {
     Domain& dm = ctx->domains[d];
     dm.row_base = rows;
     dm.cell_base = cells;
-    if (hb[8 * d + 6] == 0) {
+    if (ctx->dom_count[d] == 0) {
       dm.ox = dm.oy = dm.oz = 0.f;
       dm.nx = dm.ny = dm.nz = 1;
     } else {
       float lo[3], hi[3];
       for (int a = 0; a < 3; ++a) {
-        lo[a] = ord2f(hb[8 * d + a]);
-        hi[a] = ord2f(hb[8 * d + 3 + a]);
+        lo[a] = ctx->dom_bounds[6 * (size_t)d + a];
+        hi[a] = ctx->dom_bounds[6 * (size_t)d + 3 + a];
       }
       dm.ox = lo[0];
       dm.oy = lo[1];
@@ -411,9 +493,9 @@ int build_grid(cab_ctx* ctx, float cell) {
     CAB_LAUNCH_CHECK(ctx);
   }
 
-  // ---- radix sort by (row, fine x) ----------------------------------------------------
+  // ---- cell table, segments and packets: all of it follows from the cell histogram alone -----------
   const int end_bit = std::min(key32 ? 32 : 64, xbits + row_bits);
-  size_t tmp_sort = 0, tmp_scan1 = 0, tmp_scan2 = 0;
+  size_t tmp_sort = 0, tmp_scan1 = 0;
   if (key32)
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr,
                                     (int*)nullptr, n, 0, end_bit, st);
@@ -421,28 +503,11 @@ int build_grid(cab_ctx* ctx, float cell) {
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
                                     (const int*)nullptr, (int*)nullptr, n, 0, end_bit, st);
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan1, (const int*)nullptr, (int*)nullptr, (int)ncell1, st);
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan2, (const int*)nullptr, (int*)nullptr, (int)(rows + 1), st);
-  size_t tmp_bytes = std::max(tmp_sort, std::max(tmp_scan1, tmp_scan2));
+  size_t tmp_bytes = std::max(tmp_sort, tmp_scan1);
   if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_bytes + 16)) return rc;
-  if (n > 0) {
-    if (key32)
-      CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_bytes, (const unsigned*)ctx->b_keys[0].p,
-                                                    (unsigned*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
-                                                    (int*)ctx->b_perm.p, n, 0, end_bit, st));
-    else
-      CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_bytes, (const unsigned long long*)ctx->b_keys[0].p,
-                                                    (unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
-                                                    (int*)ctx->b_perm.p, n, 0, end_bit, st));
-    ctx->tm.kernel_launches += 1 + (end_bit + 7) / 8;  // onesweep: histogram + one kernel per digit
-    reorder_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, (const int*)ctx->b_perm.p,
-                                                    (float4*)ctx->b_pos.p);
-    CAB_LAUNCH_CHECK(ctx);
-  }
   CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_bytes, (const int*)ctx->b_cellcnt.p,
                                               (int*)ctx->b_cellstart.p, (int)ncell1, st));
   ctx->tm.kernel_launches += 2;
-
-  // ---- packets ------------------------------------------------------------------------
   if (int rc = reserve(ctx, ctx->b_rowpk, ncell1 * 4 * 3)) return rc;
   int* segpk = (int*)ctx->b_rowpk.p;
   int* packet_base = segpk + ncell1;
@@ -462,11 +527,16 @@ int build_grid(cab_ctx* ctx, float cell) {
         (Packet*)ctx->b_packets.p);
     CAB_LAUNCH_CHECK(ctx);
   }
-  // ---- cost-balanced shard boundaries (multi-GPU only) -------------------------------------
+  // ---- cost-balanced shard boundaries and the halo (multi-GPU only) ---------------------------------
   ctx->shard_splits.clear();
   ctx->n_halo_packets = -1;
+  // one domain: the rank sorts only the points it needs (own cells, the cells of the halo packets and
+  // the candidates of those); the full sorted order keeps its layout, unneeded positions stay unwritten
+  const bool sharded_sort = ctx->shard_world > 1 && ctx->n_packets > 0 && nd == 1 && n > 0;
+  unsigned char* need_cell = nullptr;
   if (ctx->shard_world > 1 && ctx->n_packets > 0) {
     const int np = ctx->n_packets, w = ctx->shard_world;
+    if (w + 1 > 64) return fail(ctx, CAB_ERR_ARG, "cab_set_shard: world > 63 not supported");
     if (int rc = reserve(ctx, ctx->b_pcost, (size_t)np * 16 + (w + 1) * 4 + 64)) return rc;
     long long* cost = (long long*)ctx->b_pcost.p;
     long long* cum = cost + np;
@@ -475,33 +545,33 @@ int build_grid(cab_ctx* ctx, float cell) {
     cub::DeviceScan::InclusiveSum(nullptr, tmp_cost, (const long long*)nullptr, (long long*)nullptr, np, st);
     if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_cost + 16)) return rc;
     packet_cost_kernel<<<(np + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, np,
-                                                         (const float4*)ctx->b_pos.p, (const int*)ctx->b_cellstart.p,
-                                                         ctx->inv_cell, cost);
+                                                         (const int*)ctx->b_cellstart.p, cost);
     CAB_LAUNCH_CHECK(ctx);
     CAB_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->b_cubtmp.p, tmp_cost, cost, cum, np, st));
     split_kernel<<<1, 64, 0, st>>>(cum, np, w, split);
     CAB_LAUNCH_CHECK(ctx);
     ctx->tm.kernel_launches += 2;
-    if (w + 1 > 64) return fail(ctx, CAB_ERR_ARG, "cab_set_shard: world > 63 not supported");
     CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, split, (w + 1) * 4, cudaMemcpyDeviceToHost, st));
     CAB_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->shard_splits.assign((const int*)ctx->h_pin, (const int*)ctx->h_pin + w + 1);
-    // halo packet list for the normals pass
+    // halo packet list for the normals pass (+ the cells whose points this rank needs)
     int p0, p1;
     packet_range(ctx, &p0, &p1);
-    if (int rc = reserve(ctx, ctx->b_rowflag, (size_t)cells + (size_t)np + 64)) return rc;
+    if (int rc = reserve(ctx, ctx->b_rowflag, 2 * (size_t)cells + (size_t)np + 64)) return rc;
     if (int rc = reserve(ctx, ctx->b_halo_list, ((size_t)np + 4) * 4)) return rc;
     unsigned char* cell_flag = (unsigned char*)ctx->b_rowflag.p;
     unsigned char* pflag = cell_flag + cells;
+    if (sharded_sort) need_cell = pflag + np + 32;
     int* list = (int*)ctx->b_halo_list.p;
     CAB_CUDA(ctx, cudaMemsetAsync(cell_flag, 0, (size_t)cells, st));
+    if (need_cell) CAB_CUDA(ctx, cudaMemsetAsync(need_cell, 0, (size_t)cells, st));
     if (p1 > p0) {
       mark_cells_kernel<<<(p1 - p0 + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, p0, p1,
-                                                              (const float4*)ctx->b_pos.p, ctx->inv_cell, cell_flag);
+                                                              (const int*)ctx->b_cellstart.p, cell_flag);
       CAB_LAUNCH_CHECK(ctx);
     }
     flag_halo_kernel<<<(np + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, np, p0, p1,
-                                                       (const float4*)ctx->b_pos.p, ctx->inv_cell, cell_flag, pflag);
+                                                       (const int*)ctx->b_cellstart.p, cell_flag, pflag, need_cell);
     CAB_LAUNCH_CHECK(ctx);
     size_t tmp_sel = 0;
     thrust::counting_iterator<int> ids(0);
@@ -513,6 +583,84 @@ int build_grid(cab_ctx* ctx, float cell) {
     CAB_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->n_halo_packets = *(const int*)ctx->h_pin;
   }
+
+  // ---- radix sort by (row, fine x) ----------------------------------------------------
+  if (n > 0 && !sharded_sort) {
+    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_sort + 16)) return rc;
+    if (key32)
+      CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_sort, (const unsigned*)ctx->b_keys[0].p,
+                                                    (unsigned*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
+                                                    (int*)ctx->b_perm.p, n, 0, end_bit, st));
+    else
+      CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_sort, (const unsigned long long*)ctx->b_keys[0].p,
+                                                    (unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
+                                                    (int*)ctx->b_perm.p, n, 0, end_bit, st));
+    ctx->tm.kernel_launches += 1 + (end_bit + 7) / 8;  // onesweep: histogram + one kernel per digit
+    reorder_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, (const int*)ctx->b_perm.p,
+                                                    (float4*)ctx->b_pos.p);
+    CAB_LAUNCH_CHECK(ctx);
+  } else if (sharded_sort) {
+    const Domain& dm = ctx->domains[0];
+    const size_t ksz = key32 ? 4 : 8;
+    if (int rc = reserve(ctx, ctx->b_vals[1], (size_t)n * 4)) return rc;
+    if (int rc = reserve(ctx, ctx->b_keys[2], (size_t)n * 8)) return rc;
+    if (int rc = reserve(ctx, ctx->b_vals[2], (size_t)n * 4 + 16)) return rc;
+    if (int rc = reserve(ctx, ctx->b_substart, ncell1 * 4 * 2)) return rc;
+    int* masked = (int*)ctx->b_substart.p;
+    int* sub_start = masked + ncell1;
+    int* d_m = (int*)((char*)ctx->b_vals[2].p + (size_t)n * 4);  // number of selected points
+    masked_count_kernel<<<(unsigned)((ncell1 + 255) / 256), 256, 0, st>>>((const int*)ctx->b_cellcnt.p, need_cell, cells, masked);
+    CAB_LAUNCH_CHECK(ctx);
+    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_bytes + 16)) return rc;
+    CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_bytes, masked, sub_start, (int)ncell1, st));
+    // stable selection of the indices of the needed points (flags computed on the fly from the keys)
+    thrust::counting_iterator<int> all_points(0);
+    size_t tmp_selk = 0;
+    NeedPoint<unsigned> need32{(const unsigned*)ctx->b_keys[0].p, need_cell, xbits, dm.xshift, dm.nx, (unsigned long long)rows};
+    NeedPoint<unsigned long long> need64{(const unsigned long long*)ctx->b_keys[0].p, need_cell, xbits, dm.xshift, dm.nx,
+                                         (unsigned long long)rows};
+    if (key32) cub::DeviceSelect::If(nullptr, tmp_selk, all_points, (int*)nullptr, d_m, n, need32, st);
+    else cub::DeviceSelect::If(nullptr, tmp_selk, all_points, (int*)nullptr, d_m, n, need64, st);
+    size_t tmp_sel2 = std::max(tmp_selk, tmp_sort);
+    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_sel2 + 16)) return rc;
+    if (key32) CAB_CUDA(ctx, cub::DeviceSelect::If(ctx->b_cubtmp.p, tmp_sel2, all_points, (int*)ctx->b_vals[2].p, d_m, n, need32, st));
+    else CAB_CUDA(ctx, cub::DeviceSelect::If(ctx->b_cubtmp.p, tmp_sel2, all_points, (int*)ctx->b_vals[2].p, d_m, n, need64, st));
+    ctx->tm.kernel_launches += 3;
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, d_m, 4, cudaMemcpyDeviceToHost, st));
+    CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_perm.p, 0xff, (size_t)n * 4, st));  // unneeded positions: perm = -1
+    CAB_CUDA(ctx, cudaStreamSynchronize(st));
+    const int m = *(const int*)ctx->h_pin;
+    (void)ksz;
+    if (m > 0) {
+      if (key32)
+        gather_keys_kernel<unsigned><<<(m + 255) / 256, 256, 0, st>>>((const unsigned*)ctx->b_keys[0].p, (const int*)ctx->b_vals[2].p, m,
+                                                                     (unsigned*)ctx->b_keys[2].p);
+      else
+        gather_keys_kernel<unsigned long long><<<(m + 255) / 256, 256, 0, st>>>(
+            (const unsigned long long*)ctx->b_keys[0].p, (const int*)ctx->b_vals[2].p, m, (unsigned long long*)ctx->b_keys[2].p);
+      CAB_LAUNCH_CHECK(ctx);
+      if (key32)
+        CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_sel2, (const unsigned*)ctx->b_keys[2].p,
+                                                      (unsigned*)ctx->b_keys[1].p, (const int*)ctx->b_vals[2].p,
+                                                      (int*)ctx->b_vals[1].p, m, 0, end_bit, st));
+      else
+        CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_sel2, (const unsigned long long*)ctx->b_keys[2].p,
+                                                      (unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[2].p,
+                                                      (int*)ctx->b_vals[1].p, m, 0, end_bit, st));
+      ctx->tm.kernel_launches += 1 + (end_bit + 7) / 8;
+      if (key32)
+        scatter_sorted_kernel<unsigned><<<(m + 255) / 256, 256, 0, st>>>(
+            ctx->xyz_in, ctx->stride, m, (const unsigned*)ctx->b_keys[1].p, (const int*)ctx->b_vals[1].p, xbits, dm.xshift, dm.nx,
+            (unsigned long long)rows, (const int*)ctx->b_cellstart.p, sub_start, (float4*)ctx->b_pos.p, (int*)ctx->b_perm.p);
+      else
+        scatter_sorted_kernel<unsigned long long><<<(m + 255) / 256, 256, 0, st>>>(
+            ctx->xyz_in, ctx->stride, m, (const unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[1].p, xbits, dm.xshift,
+            dm.nx, (unsigned long long)rows, (const int*)ctx->b_cellstart.p, sub_start, (float4*)ctx->b_pos.p, (int*)ctx->b_perm.p);
+      CAB_LAUNCH_CHECK(ctx);
+    }
+    ctx->tm.n_sorted = m;
+  }
+  if (!sharded_sort) ctx->tm.n_sorted = ctx->n_valid;
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.build_ms, ctx->ev[0], ctx->ev[1]));

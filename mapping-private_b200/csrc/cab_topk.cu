@@ -31,6 +31,7 @@ struct ThrArgs {
   int first_shift;  // 30 when r2 needs bit 30/31, else 24
   float* thr_d2;
   int* thr_idx;
+  const unsigned char* done;  // optional, indexed by input index: queries that need no threshold any more
 };
 
 __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrArgs a) {
@@ -47,6 +48,11 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrA
   unsigned prefix = 0, mask = 0;
   int target = a.max_nn;
   bool need = pc.active;
+  if (a.done) {
+    need = need && !a.done[g.perm[pc.qi]];
+    if (!__any_sync(kFull, need)) return;  // whole packet already resolved (k-NN rounds)
+  }
+  const bool wanted = need;
   for (int shift = a.first_shift; shift >= 0; shift -= 6) {
     for (int b = 0; b < kSelBins; ++b) hist[warp][b][lane] = 0;
     for_each_chunk(g, pc, lane, tile, [&](int cnt, const float4&, int, bool) {
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrA
     });
     if (need && t < target) cur = best;
   }
-  if (pc.active) {
+  if (pc.active && wanted) {
     a.thr_d2[pc.qi] = need ? dstar : INFINITY;
     a.thr_idx[pc.qi] = need ? cur : INT_MAX;
   }
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(128) neighbors_debug_kernel(const DbgArgs a) {
 
 }  // namespace
 
-int run_thresholds(cab_ctx* ctx, float r, int max_nn) {
+int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done) {
   const int n = (int)ctx->n;
   cudaStream_t st = ctx->stream;
   if (int rc = reserve(ctx, ctx->b_thr_d2, (size_t)std::max(n, 1) * sizeof(float))) return rc;
@@ -194,6 +200,7 @@ int run_thresholds(cab_ctx* ctx, float r, int max_nn) {
   a.first_shift = (bits >> 30) ? 30 : 24;
   a.thr_d2 = (float*)ctx->b_thr_d2.p;
   a.thr_idx = (int*)ctx->b_thr_idx.p;
+  a.done = done;
   const int np = a.p1 - a.p0;
   if (np > 0) {
     threshold_kernel<<<(np + kSelWarps - 1) / kSelWarps, kSelWarps * kWarp, 0, st>>>(a);

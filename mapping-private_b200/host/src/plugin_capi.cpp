@@ -11,6 +11,7 @@
 #include <cloud_algos/radius_estimation.h>
 #include <cloud_algos/global_rsd.h>
 #include <cloud_algos/svm_classification.h>
+#include <cloud_algos/noise_removal.h>
 
 using namespace cloud_algos;
 
@@ -84,6 +85,12 @@ int capi_set_field(void* hv, const char* field, double value) {
     else return -1;
     return 0;
   }
+  if (StatisticalNoiseRemoval* a = dynamic_cast<StatisticalNoiseRemoval*>(h->algo)) {
+    if (f == "alpha_") a->alpha_ = value; else if (f == "neighborhood_size_") a->neighborhood_size_ = (int)value;
+    else if (f == "min_nr_pts_") a->min_nr_pts_ = (int)value;
+    else return -1;
+    return 0;
+  }
   if (GlobalRSD* a = dynamic_cast<GlobalRSD*>(h->algo)) {
     if (f == "width_") a->width_ = value; else if (f == "step_") a->step_ = (int)value;
     else if (f == "min_voxel_pts_") a->min_voxel_pts_ = (int)value; else if (f == "label_") a->label_ = (int)value;
@@ -127,6 +134,9 @@ const char* capi_process(void* hv, const float* xyz, int n, int nchan, const cha
     if (a->output_valid_) h->out = a->output();
     h->aux = a->getVRSD();
   } else if (SVMClassification* a = dynamic_cast<SVMClassification*>(h->algo)) {
+    h->result = a->process(cin);
+    if (a->output_valid_) h->out = a->output();
+  } else if (StatisticalNoiseRemoval* a = dynamic_cast<StatisticalNoiseRemoval*>(h->algo)) {
     h->result = a->process(cin);
     if (a->output_valid_) h->out = a->output();
   } else {

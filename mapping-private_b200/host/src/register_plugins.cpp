@@ -7,6 +7,7 @@
 #include <cloud_algos/radius_estimation.h>
 #include <cloud_algos/global_rsd.h>
 #include <cloud_algos/svm_classification.h>
+#include <cloud_algos/noise_removal.h>
 
 using namespace cloud_algos;
 
@@ -14,3 +15,4 @@ PLUGINLIB_DECLARE_CLASS(cloud_algos, NormalEstimation, cloud_algos::NormalEstima
 PLUGINLIB_DECLARE_CLASS(cloud_algos, LocalRadiusEstimation, cloud_algos::LocalRadiusEstimation, cloud_algos::CloudAlgo);
 PLUGINLIB_DECLARE_CLASS(cloud_algos, GlobalRSD, cloud_algos::GlobalRSD, cloud_algos::CloudAlgo);
 PLUGINLIB_DECLARE_CLASS(cloud_algos, SVMClassification, cloud_algos::SVMClassification, cloud_algos::CloudAlgo);
+PLUGINLIB_DECLARE_CLASS(cloud_algos, StatisticalNoiseRemoval, cloud_algos::StatisticalNoiseRemoval, cloud_algos::CloudAlgo);

@@ -29,6 +29,31 @@ def exchange_slices(buf, ranges: Sequence[Tuple[int, int]], group=None):
     return buf
 
 
+def gather_cloud(full, my_slice, rank: int, world: int, group=None):
+    """Replicates a cloud whose rows were uploaded slice-wise: rank g copied rows split_range(n, world)[g] of the
+    host cloud into `my_slice` (one H2D of n/world points per GPU); after the call `full` (n x 3, on the same
+    device) holds all rows on every rank.  One all-gather over NVLink instead of `world` full uploads over PCIe."""
+    import torch
+    import torch.distributed as dist
+
+    n = full.shape[0]
+    ranges = split_range(n, world)
+    b, e = ranges[rank]
+    assert my_slice.shape[0] == e - b
+    width = max(hi - lo for lo, hi in ranges)
+    if all(hi - lo == width for lo, hi in ranges) and full.is_contiguous():
+        dist.all_gather_into_tensor(full, my_slice.contiguous(), group=group)
+        return full
+    # ragged split: pad every slice to the widest one
+    pad = torch.zeros((width,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
+    pad[: e - b] = my_slice
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    for g, (lo, hi) in enumerate(ranges):
+        full[lo:hi] = parts[g][: hi - lo]
+    return full
+
+
 def assign_clusters_lpt(sizes: Sequence[int], world: int) -> List[List[int]]:
     """Longest-processing-time-first assignment of clusters to ranks (deterministic)."""
     order = sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i))

@@ -342,6 +342,14 @@ class KdTree {
     nodes_.reserve(idx_.size() / 4 + 16);
     if (!idx_.empty()) build(0, (int)idx_.size());
   }
+  // The k smallest (d2, index) pairs over all points, ascending (cloud_kdtree's nearestKSearch as used at
+  // noise_removal.cpp:90 [EXTERNAL semantics]; ties by input index).
+  void knn(const float* q, int k, std::vector<Nb>& out) const {
+    out.clear();
+    if (nodes_.empty() || !finite3(q) || k <= 0) return;
+    knn_rec(0, q, k, out);
+    std::sort_heap(out.begin(), out.end(), nb_less);
+  }
   void radius(const float* q, float r, float r2, std::vector<Nb>& out) const {
     out.clear();
     if (nodes_.empty() || !finite3(q)) return;
@@ -371,6 +379,29 @@ class KdTree {
     float split;
     int left, right, lo, hi;
   };
+  void knn_rec(int node, const float* q, int k, std::vector<Nb>& heap) const {  // max-heap under nb_less
+    const Node& nd = nodes_[node];
+    if (nd.axis < 0) {
+      for (int s = nd.lo; s < nd.hi; ++s) {
+        const int j = idx_[s];
+        const Nb c{orc_d2(xyz_ + 3 * (size_t)j, q), j};
+        if ((int)heap.size() < k) {
+          heap.push_back(c);
+          std::push_heap(heap.begin(), heap.end(), nb_less);
+        } else if (nb_less(c, heap.front())) {
+          std::pop_heap(heap.begin(), heap.end(), nb_less);
+          heap.back() = c;
+          std::push_heap(heap.begin(), heap.end(), nb_less);
+        }
+      }
+      return;
+    }
+    const double diff = (double)q[nd.axis] - (double)nd.split;
+    const int near = diff < 0 ? nd.left : nd.right, far = diff < 0 ? nd.right : nd.left;
+    knn_rec(near, q, k, heap);
+    // conservative pruning: the far side can only matter if the plane is not farther than the current worst
+    if ((int)heap.size() < k || diff * diff <= (double)heap.front().d2 * 1.0001 + 1e-30) knn_rec(far, q, k, heap);
+  }
   int build(int lo, int hi) {
     int id = (int)nodes_.size();
     nodes_.push_back(Node{-1, 0.f, -1, -1, lo, hi});
@@ -1062,6 +1093,56 @@ int orc_svm_predict(const float* features, int64_t n, int dim, int nr_class, int
       for (int q = 0; q < npairs; ++q) dec[(size_t)p * npairs + q] = dv[q];
   }
   return 0;
+}
+
+int orc_knn_mean_distance(const float* xyz, int n, int k, double* avg, int nthreads) {
+  if (k < 2) return -1;
+  KdTree tree(xyz, n);
+  int nfinite = 0;
+  for (int i = 0; i < n; ++i) nfinite += finite3(xyz + 3 * (size_t)i) ? 1 : 0;
+  if (k > nfinite) return -2;  // noise_removal.cpp:57-62
+  nthreads = resolve_threads(nthreads);
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<Nb> nbs;
+#pragma omp for schedule(dynamic, 256)
+    for (int cp = 0; cp < n; ++cp) {
+      const float* q = xyz + 3 * (size_t)cp;
+      if (!finite3(q)) {
+        avg[cp] = std::numeric_limits<double>::quiet_NaN();
+        continue;
+      }
+      tree.knn(q, k, nbs);
+      double a = 0.0;
+      for (int ni = 1; ni < k; ni++) a += std::sqrt((double)nbs[ni].d2);  // :104-109, the first one is cp itself
+      avg[cp] = a / (k - 1);                                                // :110
+    }
+  }
+  return 0;
+}
+
+int64_t orc_noise_filter(const double* avg, int n, double alpha, uint8_t* keep, double* mean_out, double* stddev_out) {
+  // noise_removal.cpp:113-121 over the finite points
+  double sum = 0, sq_sum = 0;
+  int64_t m = 0;
+  for (int cp = 0; cp < n; ++cp) {
+    if (std::isnan(avg[cp])) continue;
+    sum += avg[cp];
+    sq_sum += avg[cp] * avg[cp];
+    ++m;
+  }
+  const double mean = m ? sum / m : 0.0;
+  const double variance = m ? sq_sum / m - mean * mean : 0.0;
+  const double stddev = std::sqrt(variance);
+  int64_t kept = 0;
+  for (int cp = 0; cp < n; ++cp) {
+    const bool k = !std::isnan(avg[cp]) && std::fabs(avg[cp] - mean) < alpha * stddev;  // :131
+    if (keep) keep[cp] = k ? 1 : 0;
+    kept += k ? 1 : 0;
+  }
+  if (mean_out) *mean_out = mean;
+  if (stddev_out) *stddev_out = stddev;
+  return kept;
 }
 
 }  // extern "C"

@@ -167,6 +167,18 @@ int orc_svm_predict(const float* features, int64_t n, int dim, int nr_class, int
                     const double* sv, double lower, double upper, const double* fmin, const double* fmax,
                     float* out, double* dec);
 
+/* cloud_algos::StatisticalNoiseRemoval (cloud_algos/src/noise_removal.cpp:84-136):
+ *   avg[cp] = sum_{ni=1}^{k-1} sqrt((double)d2[cp][ni]) / (k-1) over the k nearest neighbours of cp
+ *             (cp itself is the first and is skipped, :104-111), d2 under the documented rule, ties
+ *             by input index [kdtree_->nearestKSearch: EXTERNAL semantics];
+ *   mean / stddev of avg over the cloud (:113-121); keep cp iff |avg - mean| < alpha * stddev (:131).
+ * Non-finite points get avg = NaN, are left out of the statistics and are never kept (the reference
+ * has no such points).  orc_knn_mean_distance returns -2 when the cloud has fewer than k finite
+ * points (:57-62), -1 for k < 2 (:51-56). */
+int orc_knn_mean_distance(const float* xyz, int n, int k, double* avg, int nthreads);
+int64_t orc_noise_filter(const double* avg, int n, double alpha, uint8_t* keep, double* mean_out,
+                         double* stddev_out);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -292,5 +292,29 @@ def svm_predict(model, features, scale=None, want_dec=False):
     return (out, dec) if want_dec else out
 
 
+def knn_mean_distance(xyz, k, nthreads=0):
+    """StatisticalNoiseRemoval's per-point mean distance to the k-1 nearest neighbours (float64, NaN for
+    non-finite points).  Raises ValueError like the plugin's checks (k < 2, fewer than k points)."""
+    L = lib()
+    p = _xyz(xyz)
+    avg = np.zeros(p.shape[0], np.float64)
+    rc = L.orc_knn_mean_distance(_ptr(p, C.c_float), p.shape[0], int(k), avg.ctypes.data_as(C.POINTER(C.c_double)), int(nthreads))
+    if rc != 0:
+        raise ValueError("not enough neighbours requested" if rc == -1 else "not enough points in the cloud")
+    return avg
+
+
+def noise_filter(avg, alpha):
+    """Returns (keep bool (n,), mean, stddev)."""
+    L = lib()
+    L.orc_noise_filter.restype = C.c_int64
+    a = np.ascontiguousarray(avg, np.float64)
+    keep = np.zeros(a.shape[0], np.uint8)
+    mean, std = C.c_double(), C.c_double()
+    L.orc_noise_filter(a.ctypes.data_as(C.POINTER(C.c_double)), a.shape[0], C.c_double(alpha),
+                       keep.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(mean), C.byref(std))
+    return keep.astype(bool), mean.value, std.value
+
+
 def num_threads():
     return lib().orc_num_threads()

@@ -15,6 +15,8 @@ rows = []
 for g in range(W):
     ctx.set_shard(g, W)
     ctx.build_grid(0.02)
+    ctx.build_grid(0.02)
+    pb = ctx.profile()
     b, e = ctx.shard_range()
     for _ in range(2):
         ctx.normals(0.02, download=False)
@@ -22,7 +24,7 @@ for g in range(W):
         ctx.rsd(0.02, download=False)
         p2 = ctx.profile()
     q = max(e - b, 1)
-    rows.append((g, b, e, p1['normals_ms'], p2['rsd_ms'], p2['neighbour_sum'] / q, p2['candidate_sum'] / q))
-for g, b, e, tn, tr, k, c in rows:
+    rows.append((g, b, e, p1['normals_ms'], p2['rsd_ms'], p2['neighbour_sum'] / q, p2['candidate_sum'] / q, pb['build_ms'], pb['n_sorted']))
+for g, b, e, tn, tr, k, c, tb, ns in rows:
     q = max(e - b, 1)
-    print(f"shard {g:3d}: [{b:9d},{e:9d}) q {q:8d} normals {tn:6.3f} ms rsd {tr:6.3f} ms k/q {k:6.1f} cand/q {c:7.1f} ns/q n {1e6*tn/q:6.2f} r {1e6*tr/q:6.2f}")
+    print(f"shard {g:3d}: [{b:9d},{e:9d}) q {q:8d} normals {tn:6.3f} ms rsd {tr:6.3f} ms k/q {k:6.1f} cand/q {c:7.1f} ns/q n {1e6*tn/q:6.2f} r {1e6*tr/q:6.2f} build {tb:6.3f} ms sorted {ns:9d} total {tb+tn+tr:6.3f} ms")

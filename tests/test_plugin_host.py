@@ -26,7 +26,7 @@ def test_discovery_matches_plugins_xml(built):
     assert '<library path="lib/libcloud_algos">' in xml
     declared = re.findall(r'<class name="([^"]+)" type="([^"]+)" base_class_type="([^"]+)">', xml)
     assert {d[0] for d in declared} == {"cloud_algos/NormalEstimation", "cloud_algos/LocalRadiusEstimation", "cloud_algos/GlobalRSD",
-                                        "cloud_algos/SVMClassification"}
+                                        "cloud_algos/SVMClassification", "cloud_algos/StatisticalNoiseRemoval"}
     for name, typ, base in declared:
         assert typ == name.replace("/", "::") and base == "cloud_algos::CloudAlgo"
         p = plugin.Plugin(name)  # pluginlib lookup by the reference's names
@@ -71,6 +71,20 @@ def test_svm_plugin_surface_and_errors(built, tmp_path):
     bad.write_text("svm_type nu_svc\nkernel_type rbf\nSV\n")
     res, _ = svm.run(pts, feats, fields={"model_file_name_": str(bad)})
     assert res == "incorrect model file"
+
+
+def test_noise_removal_plugin_surface_and_errors(built):
+    nr = plugin.Plugin("cloud_algos/StatisticalNoiseRemoval")
+    assert nr.requires_provides() == (["x", "y", "z"], ["x", "y", "z"])  # noise_removal.cpp:24-43
+    assert nr.topic() == "cloud_denoise"
+    pts = synth.analytic_shape("plane", 50)
+    res, out = nr.run(pts, fields={"neighborhood_size_": 1})
+    assert res == "ERROR: Not enough neighbors requested!" and out is None and not nr.output_valid()
+    res, out = nr.run(pts, fields={"alpha_": -1.0})
+    assert res == "ERROR: Not enough neighbors requested!"
+    # public fields persist between calls, exactly like the reference's (pre() only overrides what has a rosparam)
+    res, out = nr.run(pts[:5], fields={"alpha_": 3.0, "neighborhood_size_": 10})
+    assert res == "ERROR: Not enough points in the cloud (or too many neighbors requested)!" and out is None
 
 
 def test_sample_pipeline_yaml_keys(built):
@@ -180,3 +194,28 @@ def test_svm_plugin_against_oracle(built, oracle, tmp_path):
         hi = np.where(~low & (hi < row), row, hi)
     res, out = svm.run(pts, chans, fields={"scale_self_": 1})
     assert np.array_equal(out["channels"]["point_class"], oracle.svm_predict(m, F, scale=(-1.0, 1.0, lo, hi)))
+
+
+@pytest.mark.gpu
+def test_noise_removal_plugin_against_oracle(built, oracle):
+    rng = np.random.default_rng(4)
+    pts = np.concatenate([synth.tabletop(40_000, noise_sigma=0.0005),
+                          synth.quantize(rng.uniform([-0.6, -0.4, 0.5], [0.6, 0.4, 1.3], (400, 3)))]).astype(np.float32)
+    tag = np.arange(len(pts), dtype=np.float32)
+    nr = plugin.Plugin("cloud_algos/StatisticalNoiseRemoval")
+    nr.set_param("alpha", 2.0)
+    nr.set_param("neighborhood_size", 12)
+    res, out = nr.run(pts, {"tag": tag})
+    assert res == "ok" and nr.output_valid() and nr.num_published() == 1
+    avg = oracle.knn_mean_distance(pts, 12)
+    keep, mean, std = oracle.noise_filter(avg, 2.0)
+    margin = np.abs(np.abs(avg - mean) - 2.0 * std)
+    sure = margin > 1e-9
+    got = np.zeros(len(pts), bool)
+    got[out["channels"]["tag"].astype(np.int64)] = True
+    assert np.array_equal(got[sure], keep[sure]) and sure.mean() > 0.999
+    assert np.array_equal(out["points"], pts[got])  # kept points in input order, channels follow
+    assert keep[-400:].mean() < 0.2  # the scattered points are what gets removed
+    # the size check (noise_removal.cpp:152-158)
+    res, out = nr.run(pts, {"tag": tag}, fields={"min_nr_pts_": len(pts)})
+    assert res == "output size check failed (see min_nr_pts parameter)" and out is None and not nr.output_valid()

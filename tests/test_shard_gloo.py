@@ -57,6 +57,12 @@ def _worker(rank, world, port, tmp):
         buf[b:e] = full[b:e]
         sh.exchange_slices(buf, ranges)
         assert torch.equal(buf, full)
+        # slice-wise upload + all-gather of the cloud (ragged and even splits)
+        for npts in (1001, 1000):
+            cloud = torch.arange(npts * 3, dtype=torch.float32).reshape(npts, 3)
+            lo, hi = sh.split_range(npts, world)[rank]
+            got = sh.gather_cloud(torch.full((npts, 3), -1.0), cloud[lo:hi].clone(), rank, world)
+            assert torch.equal(got, cloud)
         # cluster-per-rank GRSD: integer histograms summed with one all-reduce
         sizes = [5, 9, 2, 7, 7, 1]
         parts = sh.assign_clusters_lpt(sizes, world)
