@@ -1,0 +1,114 @@
+// Which arithmetic form of the normals inner loop is fastest on the B200?  Synthetic loop with the real
+// instruction mix (3 broadcast LDS.128 per 4 candidates, distance test, predicated accumulation) in several
+// variants of the distance computation.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o normals_mix normals_mix.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 sq2(f32x2 a) { return fma2(a, a, 0ull); }
+
+__device__ __forceinline__ void accum_pred(float d2, float r2, float dx, float dy, float dz, float& s1x, float& s1y, float& s1z,
+                                           float& sxx, float& sxy, float& sxz, float& syy, float& syz, float& szz, int& k) {
+  asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %10, %11;\n\t@p add.f32 %0, %0, %12;\n\t@p add.f32 %1, %1, %13;\n\t@p add.f32 %2, %2, %14;\n\t"
+      "@p fma.rn.f32 %3, %12, %12, %3;\n\t@p fma.rn.f32 %4, %12, %13, %4;\n\t@p fma.rn.f32 %5, %12, %14, %5;\n\t"
+      "@p fma.rn.f32 %6, %13, %13, %6;\n\t@p fma.rn.f32 %7, %13, %14, %7;\n\t@p fma.rn.f32 %8, %14, %14, %8;\n\t@p add.s32 %9, %9, 1;\n\t}"
+      : "+f"(s1x), "+f"(s1y), "+f"(s1z), "+f"(sxx), "+f"(sxy), "+f"(sxz), "+f"(syy), "+f"(syz), "+f"(szz), "+r"(k)
+      : "f"(d2), "f"(r2), "f"(dx), "f"(dy), "f"(dz));
+}
+
+#define ITER 2048
+// MODE 0: packed, no contraction (16 packed / 4 candidates)      -- the kernel in the tree
+// MODE 1: scalar, no contraction (32 scalar)
+// MODE 2: candidates 0,1 packed, 2,3 scalar
+// MODE 3: packed with FMA chain d2 = fma(dz,dz,fma(dy,dy,dx*dx)) (12 packed)
+// MODE 4: scalar with FMA chain (24 scalar)
+template <int MODE>
+__global__ void __launch_bounds__(256) k(float* out, float seed) {
+  __shared__ __align__(16) float tx[32], ty[32], tz[32];
+  if (threadIdx.x < 32) { tx[threadIdx.x] = seed * threadIdx.x; ty[threadIdx.x] = seed * 2 * threadIdx.x; tz[threadIdx.x] = seed * 3 * threadIdx.x; }
+  __syncthreads();
+  const float qx = seed * (threadIdx.x & 31), qy = qx * 2, qz = qx * 3, r2 = seed * seed * 40.f;
+  const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
+  float s1x = 0, s1y = 0, s1z = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+  int kk = 0;
+#pragma unroll 1
+  for (int it = 0; it < ITER; ++it) {
+#pragma unroll 2
+    for (int g4 = 0; g4 < 8; ++g4) {
+      const float4 X = reinterpret_cast<const float4*>(tx)[g4], Y = reinterpret_cast<const float4*>(ty)[g4], Z = reinterpret_cast<const float4*>(tz)[g4];
+      float d2a, d2b, xa, xb, ya, yb, za, zb;
+#define PACKED(X0, X1, Y0, Y1, Z0, Z1, FMA)                                                                    \
+  {                                                                                                            \
+    const f32x2 dx = sub2(pack2(X0, X1), qx2), dy = sub2(pack2(Y0, Y1), qy2), dz = sub2(pack2(Z0, Z1), qz2);   \
+    const f32x2 d2 = FMA ? fma2(dz, dz, fma2(dy, dy, sq2(dx))) : add2(add2(sq2(dx), sq2(dy)), sq2(dz));        \
+    unpack2(d2, d2a, d2b); unpack2(dx, xa, xb); unpack2(dy, ya, yb); unpack2(dz, za, zb);                      \
+  }
+#define SCALAR(X0, Y0, Z0, FMA, D2, DX, DY, DZ)                                                                \
+  {                                                                                                            \
+    DX = __fsub_rn(X0, qx); DY = __fsub_rn(Y0, qy); DZ = __fsub_rn(Z0, qz);                                    \
+    D2 = FMA ? __fmaf_rn(DZ, DZ, __fmaf_rn(DY, DY, __fmul_rn(DX, DX)))                                         \
+             : __fadd_rn(__fadd_rn(__fmul_rn(DX, DX), __fmul_rn(DY, DY)), __fmul_rn(DZ, DZ));                  \
+  }
+#define ACC2 accum_pred(d2a, r2, xa, ya, za, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, kk); \
+             accum_pred(d2b, r2, xb, yb, zb, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, kk);
+      if (MODE == 0 || MODE == 3) {
+        PACKED(X.x, X.y, Y.x, Y.y, Z.x, Z.y, MODE == 3) ACC2
+        PACKED(X.z, X.w, Y.z, Y.w, Z.z, Z.w, MODE == 3) ACC2
+      } else if (MODE == 1 || MODE == 4) {
+        SCALAR(X.x, Y.x, Z.x, MODE == 4, d2a, xa, ya, za) SCALAR(X.y, Y.y, Z.y, MODE == 4, d2b, xb, yb, zb) ACC2
+        SCALAR(X.z, Y.z, Z.z, MODE == 4, d2a, xa, ya, za) SCALAR(X.w, Y.w, Z.w, MODE == 4, d2b, xb, yb, zb) ACC2
+      } else {
+        PACKED(X.x, X.y, Y.x, Y.y, Z.x, Z.y, false) ACC2
+        SCALAR(X.z, Y.z, Z.z, false, d2a, xa, ya, za) SCALAR(X.w, Y.w, Z.w, false, d2b, xb, yb, zb) ACC2
+      }
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s1x + s1y + s1z + sxx + sxy + sxz + syy + syz + szz + kk;
+}
+
+template <int MODE>
+void run(const char* name, int blocks_per_sm) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int blocks = sms * blocks_per_sm;
+  float* out;
+  cudaMalloc(&out, blocks * 256 * 4);
+  k<MODE><<<blocks, 256>>>(out, 0.01f);
+  cudaDeviceSynchronize();
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e9f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    k<MODE><<<blocks, 256>>>(out, 0.01f);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = ms < best ? ms : best;
+  }
+  // groups of 4 candidates per SMSP: blocks_per_sm * 8 warps / 4 SMSPs * ITER * 8
+  const double groups = (double)blocks_per_sm * 2 * ITER * 8;
+  printf("%-44s %d blocks/SM: %7.3f ms -> %6.1f cycles per 4 candidates per SMSP-warp slot\n", name, blocks_per_sm, best,
+         best * 1.965e6 / groups);
+  cudaFree(out);
+}
+
+int main() {
+  for (int b : {4, 3}) {
+    if (b == 4) {
+      run<0>("packed, no FMA (tree)", 4); run<1>("scalar, no FMA", 4); run<2>("half packed / half scalar", 4);
+      run<3>("packed, FMA chain", 4); run<4>("scalar, FMA chain", 4);
+    } else {
+      run<0>("packed, no FMA (tree)", 3); run<1>("scalar, no FMA", 3); run<2>("half packed / half scalar", 3);
+      run<3>("packed, FMA chain", 3); run<4>("scalar, FMA chain", 3);
+    }
+  }
+  return 0;
+}
