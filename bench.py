@@ -143,7 +143,7 @@ def run_reference(args, rank):
     from mapping_private_b200 import synth
 
     pts = synth.room(args.points)  # full cloud so that the slab has the workload's density
-    sample = slab_sample(pts, 150_000)
+    sample = slab_sample(pts, 1_500_000)  # ~3-4 s of work per step on 16 cores: K + W steps stay within minutes
     rates = []
     cores = 1
     for s in range(args.warmup + args.steps):
