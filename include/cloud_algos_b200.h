@@ -192,7 +192,8 @@ int cab_svm_predict_grsd(cab_ctx* ctx, float* point_class);
  * Replaces the kd-tree k-NN loop and the statistics of StatisticalNoiseRemoval::process
  * (cloud_algos/src/noise_removal.cpp:84-136) on the uploaded cloud:
  *   avg[cp] = mean distance from cp to its k - 1 nearest neighbours (k = neighborhood_size_ counts cp
- *             itself, which is skipped, :102-111), k-NN under the documented d2 rule, ties by index;
+ *             itself, which is skipped, :102-111; fp32 sqrt of the fp32 d2, summed in fp64), k-NN under
+ *             the documented d2 rule, ties by index;
  *   mean / stddev of avg over the cloud, fp64, summed in input order (:112-121);
  *   keep[cp] = |avg[cp] - mean| < alpha * stddev (:131).
  * Non-finite points get avg = NaN, stay out of the statistics and are never kept.  cell_hint > 0 sets

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) knn_mean_kernel(const 
       const float d2 = d2_rule(tile->x[m], tile->y[m], tile->z[m], qx, qy, qz);
       if (d2 <= a.r2 && (d2 < td2 || (d2 == td2 && g.perm[tile->idx[m]] <= tidx))) {
         ++cnt;
-        sum += sqrt((double)d2);  // the query itself adds sqrt(0) = 0 (:105 skips it)
+        sum += (double)__fsqrt_rn(d2);  // std::sqrt(float) at :105; the query itself adds 0 (:104 skips it)
       }
     }
   });

@@ -13,7 +13,8 @@
 //  * cosine is the reference's fp32 expression (nx*nx' + ny*ny') + nz*nz' (:153-155), not contracted.
 //  * angle = acos(cosine) folded at pi/2 (:160-161) is monotone in |cosine|, so per bin only the
 //    cosines of extreme |value| are tracked; acos is evaluated 2*ndiv times per query, not per pair.
-//  * the distance bin floor(ndiv*sqrt((double)d2)/radius) (:165-168) is evaluated through exact
+//  * the distance bin floor(ndiv*(double)sqrtf(d2)/radius) (:165-168; `sqrt` of a float under `using namespace std;`
+//    is std::sqrt(float)) is evaluated through exact
 //    fp32 d2 thresholds computed on the host with the reference's double expression, clamped to
 //    ndiv-1 (the reference indexes out of bounds at dist == radius).
 //  * neighbours whose normal is not finite never update a bin (the reference's NaN comparisons are
@@ -219,9 +220,9 @@ __global__ void fill_invalid_rsd(float2* out, int begin, int end, float v) {
   if (i < end) out[i] = make_float2(v, v);
 }
 
-// Smallest fp32 d2 whose reference bin floor(ndiv*sqrt((double)d2)/radius) is >= b.
+// Smallest fp32 d2 whose reference bin floor(ndiv*(double)sqrtf(d2)/radius) is >= b.
 float bin_threshold(int b, int ndiv, double radius, float r2) {
-  auto bin_of = [&](float d2) { return (int)std::floor(ndiv * std::sqrt((double)d2) / radius); };
+  auto bin_of = [&](float d2) { return (int)std::floor(ndiv * (double)std::sqrt(d2) / radius); };
   if (bin_of(r2) < b) return INFINITY;
   uint32_t lo = 0, hi;  // invariant: bin(lo) < b <= bin(hi); d2 >= 0 so bit patterns are ordered
   std::memcpy(&hi, &r2, 4);

@@ -291,7 +291,8 @@ void rsd_core(const float* xyz, const float* nrm, int nstride, const std::vector
       dist = std::sqrt((double)orc_d2(xyz + 3 * (size_t)j, ref_p));
       if (dist > radius) continue;
     } else {
-      dist = std::sqrt((double)nbs[ni].d2);  // :165
+      // :165 `sqrt (points_sqr_distances_[cp][ni])` on a float under `using namespace std;` (:4) is std::sqrt(float)
+      dist = (double)std::sqrt(nbs[ni].d2);
     }
     int bin = (int)std::floor(ndiv * dist / radius);  // :168
     if (bin > ndiv - 1) bin = ndiv - 1;  // epsilon rule: the reference indexes out of bounds here
@@ -1114,7 +1115,8 @@ int orc_knn_mean_distance(const float* xyz, int n, int k, double* avg, int nthre
       }
       tree.knn(q, k, nbs);
       double a = 0.0;
-      for (int ni = 1; ni < k; ni++) a += std::sqrt((double)nbs[ni].d2);  // :104-109, the first one is cp itself
+      // :104-109, the first one is cp itself; sqrt on a float under `using namespace std;` (:4) is std::sqrt(float)
+      for (int ni = 1; ni < k; ni++) a += (double)std::sqrt(nbs[ni].d2);
       avg[cp] = a / (k - 1);                                                // :110
     }
   }

@@ -168,7 +168,7 @@ int orc_svm_predict(const float* features, int64_t n, int dim, int nr_class, int
                     float* out, double* dec);
 
 /* cloud_algos::StatisticalNoiseRemoval (cloud_algos/src/noise_removal.cpp:84-136):
- *   avg[cp] = sum_{ni=1}^{k-1} sqrt((double)d2[cp][ni]) / (k-1) over the k nearest neighbours of cp
+ *   avg[cp] = sum_{ni=1}^{k-1} (double)sqrtf(d2[cp][ni]) / (k-1) over the k nearest neighbours of cp
  *             (cp itself is the first and is skipped, :104-111), d2 under the documented rule, ties
  *             by input index [kdtree_->nearestKSearch: EXTERNAL semantics];
  *   mean / stddev of avg over the cloud (:113-121); keep cp iff |avg - mean| < alpha * stddev (:131).

@@ -27,7 +27,7 @@ def test_oracle_knn_against_brute_force_and_scipy(oracle):
         d = p[i:i + 500, None, :] - p[None, :, :]
         d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
         part = np.sort(d2, axis=1)[:, :k]
-        ref[i:i + 500] = np.sqrt(part[:, 1:].astype(np.float64)).sum(1) / (k - 1)
+        ref[i:i + 500] = np.sqrt(part[:, 1:]).astype(np.float64).sum(1) / (k - 1)  # fp32 sqrt, fp64 sum
     assert np.allclose(avg, ref, rtol=1e-13, atol=0)
     dist, _ = cKDTree(pts.astype(np.float64)).query(pts.astype(np.float64), k=k)
     assert np.allclose(avg, dist[:, 1:].sum(1) / (k - 1), rtol=1e-5)

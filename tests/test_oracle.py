@@ -141,7 +141,7 @@ def test_rsd_matches_python_restatement(oracle):
                 ang = np.arccos(c)
                 if ang > np.pi / 2:
                     ang = np.pi - ang
-                b = min(ndiv - 1, int(np.floor(ndiv * np.sqrt(float(d2[s])) / r)))
+                b = min(ndiv - 1, int(np.floor(ndiv * float(np.sqrt(np.float32(d2[s]))) / r)))  # std::sqrt(float), :165
                 mn[b] = min(mn[b], ang)
                 mx[b] = max(mx[b], ang)
             a_nn = a_nd = a_xx = a_xd = 0.0
