@@ -54,6 +54,7 @@ typedef struct cab_timings {
                        plus the cells its halo needs when the context is one shard of several (cab_set_shard) */
   float knn_ms;       /* last cab_knn_mean_distance / cab_statistical_outliers: all grid rounds */
   int32_t knn_rounds; /* grids built by it (the cell edge doubles until every query has its k neighbours) */
+  float pfh_ms;       /* last cab_pfh: pair-feature, averaging and finishing kernels */
 } cab_timings;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
@@ -204,6 +205,25 @@ int cab_svm_predict_grsd(cab_ctx* ctx, float* point_class);
 int cab_knn_mean_distance(cab_ctx* ctx, int32_t k, float cell_hint, double* avg);
 int64_t cab_statistical_outliers(cab_ctx* ctx, int32_t k, double alpha, float cell_hint, uint8_t* keep,
                                  double* avg, double* mean_out, double* stddev_out);
+
+/* ---- point feature histograms (next row: cloud_algos/PointFeatureHistogram) ----------------
+ * Replaces the hot loops of PointFeatureHistogram::process (cloud_algos/src/pfh.cpp:181-350; pair features
+ * cloud_algos/include/cloud_algos/pfh.h:102-238) on the uploaded cloud with its normals (cab_set_normals or
+ * cab_normals; the grid must cover `radius`): for every point the "star" pair features alpha, beta, gamma
+ * [, delta] towards its neighbours within `radius` (<= max_nn nearest, max_nn <= 0: all), one histogram of
+ * `quantum` bins per feature with increments of 100 / k, then the options of the plugin:
+ *   CAB_PFH_AVERAGE       1/d2-weighted average of the neighbours' histograms = FPFH (average_, :303-333)
+ *   CAB_PFH_DIFFERENTIAL  bin-to-bin differences (differential_, :337-350)
+ *   CAB_PFH_CHECK_FLIP / CAB_PFH_ABS_ANGLES / CAB_PFH_USE_DIST  check_flip_, abs_angles_, use_dist_
+ * The plugin's defaults (pfh.h:83-93) are radius 0.03, max_nn 100, quantum 9, CHECK_FLIP | AVERAGE.  The
+ * combined n-D histogram (combine_) is not implemented.  hist: n x quantum * (3 or 4) floats, point-major,
+ * input order (channel f<b+1> of point i is hist[i * nbins + b]). */
+#define CAB_PFH_USE_DIST 1
+#define CAB_PFH_DIFFERENTIAL 2
+#define CAB_PFH_CHECK_FLIP 4
+#define CAB_PFH_ABS_ANGLES 8
+#define CAB_PFH_AVERAGE 16
+int cab_pfh(cab_ctx* ctx, double radius, int32_t max_nn, int32_t quantum, int32_t flags, float* hist);
 
 /* ---- device plumbing (bench / multi-GPU) ---------------------------------------------- */
 #define CAB_BUF_POS_SORTED 0  /* float4[n]  x,y,z,0 in sorted order */

@@ -15,6 +15,8 @@ _DIR = pathlib.Path(__file__).resolve().parent
 LIB_PATH = _DIR / "csrc" / "libcloudalgos_b200.so"
 _LIB = None
 
+PFH_USE_DIST, PFH_DIFFERENTIAL, PFH_CHECK_FLIP, PFH_ABS_ANGLES, PFH_AVERAGE = 1, 2, 4, 8, 16
+PFH_DEFAULT = PFH_CHECK_FLIP | PFH_AVERAGE
 RSD_SEED_BIN0 = 2
 RSD_SCALE_SORT = 4
 SIG_GRSD21, SIG_GRSD325, SIG_PLUSGRSD110 = 0, 1, 2
@@ -24,7 +26,7 @@ BUF_POS_SORTED, BUF_NRM_SORTED, BUF_RSD_SORTED, BUF_PERM = 0, 1, 2, 3
 EXPORTS = [
     "cab_create", "cab_destroy", "cab_last_error", "cab_upload_cloud", "cab_upload_clusters",
     "cab_set_cloud_device", "cab_build_grid", "cab_set_shard", "cab_shard_range", "cab_normals",
-    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd", "cab_knn_mean_distance", "cab_statistical_outliers",
+    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd", "cab_knn_mean_distance", "cab_statistical_outliers", "cab_pfh",
     "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_profile", "cab_version",
 ]
 
@@ -43,7 +45,7 @@ class Timings(C.Structure):
         ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
         ("n_points", C.c_int64), ("n_valid", C.c_int64), ("n_packets", C.c_int64), ("n_rows", C.c_int64),
         ("n_cells", C.c_int64), ("neighbour_sum", C.c_int64), ("candidate_sum", C.c_int64),
-        ("kernel_launches", C.c_int64), ("n_sorted", C.c_int64), ("knn_ms", C.c_float), ("knn_rounds", C.c_int32),
+        ("kernel_launches", C.c_int64), ("n_sorted", C.c_int64), ("knn_ms", C.c_float), ("knn_rounds", C.c_int32), ("pfh_ms", C.c_float),
     ]
 
     def as_dict(self):
@@ -257,6 +259,14 @@ class Context:
         if total:
             self._check(self._L.cab_grsd_signatures(*args, _ip(hist), C.c_int64(total)), "cab_grsd_signatures")
         return dict(offsets=offs, subdiv_b=sb, hist=hist)
+
+    # ---- point feature histograms -----------------------------------------------------
+    def pfh(self, radius: float = 0.03, max_nn: int = 100, quantum: int = 9, flags: int = PFH_DEFAULT):
+        nb = quantum * (4 if flags & PFH_USE_DIST else 3)
+        out = np.zeros((self.n, nb), np.float32)
+        self._check(self._L.cab_pfh(self._h, C.c_double(radius), C.c_int32(max_nn), C.c_int32(quantum), C.c_int32(flags), _fp(out)),
+                    "cab_pfh")
+        return out
 
     # ---- statistical outlier removal ---------------------------------------------------
     def knn_mean_distance(self, k: int, cell_hint: float = 0.0):

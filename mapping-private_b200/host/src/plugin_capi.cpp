@@ -12,6 +12,7 @@
 #include <cloud_algos/global_rsd.h>
 #include <cloud_algos/svm_classification.h>
 #include <cloud_algos/noise_removal.h>
+#include <cloud_algos/pfh.h>
 
 using namespace cloud_algos;
 
@@ -85,6 +86,15 @@ int capi_set_field(void* hv, const char* field, double value) {
     else return -1;
     return 0;
   }
+  if (PointFeatureHistogram* a = dynamic_cast<PointFeatureHistogram*>(h->algo)) {
+    if (f == "radius_") a->radius_ = value; else if (f == "max_nn_") a->max_nn_ = (int)value;
+    else if (f == "quantum_") a->quantum_ = (int)value; else if (f == "use_dist_") a->use_dist_ = value != 0;
+    else if (f == "combine_") a->combine_ = value != 0; else if (f == "differential_") a->differential_ = value != 0;
+    else if (f == "check_flip_") a->check_flip_ = value != 0; else if (f == "abs_angles_") a->abs_angles_ = value != 0;
+    else if (f == "average_") a->average_ = value != 0; else if (f == "point_label_") a->point_label_ = (int)value;
+    else return -1;
+    return 0;
+  }
   if (StatisticalNoiseRemoval* a = dynamic_cast<StatisticalNoiseRemoval*>(h->algo)) {
     if (f == "alpha_") a->alpha_ = value; else if (f == "neighborhood_size_") a->neighborhood_size_ = (int)value;
     else if (f == "min_nr_pts_") a->min_nr_pts_ = (int)value;
@@ -139,6 +149,10 @@ const char* capi_process(void* hv, const float* xyz, int n, int nchan, const cha
   } else if (StatisticalNoiseRemoval* a = dynamic_cast<StatisticalNoiseRemoval*>(h->algo)) {
     h->result = a->process(cin);
     if (a->output_valid_) h->out = a->output();
+  } else if (PointFeatureHistogram* a = dynamic_cast<PointFeatureHistogram*>(h->algo)) {
+    h->result = a->process(cin);
+    if (a->output_valid_)  // output() returns the cloud by value (pfh.h:62)
+      h->out = boost::shared_ptr<const sensor_msgs::PointCloud>(new sensor_msgs::PointCloud(a->output()));
   } else {
     h->result = "unknown plugin type";
   }

@@ -8,6 +8,7 @@
 #include <cloud_algos/global_rsd.h>
 #include <cloud_algos/svm_classification.h>
 #include <cloud_algos/noise_removal.h>
+#include <cloud_algos/pfh.h>
 
 using namespace cloud_algos;
 
@@ -16,3 +17,4 @@ PLUGINLIB_DECLARE_CLASS(cloud_algos, LocalRadiusEstimation, cloud_algos::LocalRa
 PLUGINLIB_DECLARE_CLASS(cloud_algos, GlobalRSD, cloud_algos::GlobalRSD, cloud_algos::CloudAlgo);
 PLUGINLIB_DECLARE_CLASS(cloud_algos, SVMClassification, cloud_algos::SVMClassification, cloud_algos::CloudAlgo);
 PLUGINLIB_DECLARE_CLASS(cloud_algos, StatisticalNoiseRemoval, cloud_algos::StatisticalNoiseRemoval, cloud_algos::CloudAlgo);
+PLUGINLIB_DECLARE_CLASS(cloud_algos, PointFeatureHistogram, cloud_algos::PointFeatureHistogram, cloud_algos::CloudAlgo);

@@ -1147,4 +1147,130 @@ int64_t orc_noise_filter(const double* avg, int n, double alpha, uint8_t* keep, 
   return kept;
 }
 
+int orc_pfh_pair(const float* ps, const float* ns, const float* pt, const float* nt, float d2, double max_dist,
+                 int check_flip, int abs_angles, double* f) {
+  // pfh.h:102-238, s = the query, t = the neighbour; every product below is float * double -> double
+  double dP2P1[3], u[3], v[3], w[3], tmp[3];
+  dP2P1[0] = pt[0] - ps[0];  // float - float (:107-109)
+  dP2P1[1] = pt[1] - ps[1];
+  dP2P1[2] = pt[2] - ps[2];
+  double delta = std::sqrt(d2);  // pfh.cpp:246, std::sqrt(float) under `using namespace std;`
+  if (delta <= 0) {              // :112-123
+    double delta_sqr = dP2P1[0] * dP2P1[0] + dP2P1[1] * dP2P1[1] + dP2P1[2] * dP2P1[2];
+    if (delta_sqr == 0) return 0;
+    delta = std::sqrt(delta_sqr);
+  }
+  double angle2 = -(nt[0] * dP2P1[0] + nt[1] * dP2P1[1] + nt[2] * dP2P1[2]) / delta;  // :128-130
+  const float *nsrc = ns, *ntgt = nt;
+  bool do_flip = false;
+  double gamma = 0;
+  if (check_flip) {  // :133-140
+    gamma = (ns[0] * dP2P1[0] + ns[1] * dP2P1[1] + ns[2] * dP2P1[2]) / delta;
+    if (std::acos(gamma) > std::acos(angle2)) do_flip = true;
+  }
+  if (!check_flip || do_flip) {  // :143-152
+    nsrc = nt;
+    ntgt = ns;
+    dP2P1[0] = -dP2P1[0];
+    dP2P1[1] = -dP2P1[1];
+    dP2P1[2] = -dP2P1[2];
+    gamma = angle2;
+  }
+  if (abs_angles) gamma = std::fabs(gamma);
+  u[0] = nsrc[0];
+  u[1] = nsrc[1];
+  u[2] = nsrc[2];
+  tmp[0] = dP2P1[1] * u[2] - dP2P1[2] * u[1];  // :165-167
+  tmp[1] = dP2P1[2] * u[0] - dP2P1[0] * u[2];
+  tmp[2] = dP2P1[0] * u[1] - dP2P1[1] * u[0];
+  double nrm = std::sqrt(tmp[0] * tmp[0] + tmp[1] * tmp[1] + tmp[2] * tmp[2]);
+  if (nrm == 0) return 0;  // :171-175
+  v[0] = tmp[0] / nrm;
+  v[1] = tmp[1] / nrm;
+  v[2] = tmp[2] / nrm;
+  w[0] = u[1] * v[2] - u[2] * v[1];  // :183-185
+  w[1] = u[2] * v[0] - u[0] * v[2];
+  w[2] = u[0] * v[1] - u[1] * v[0];
+  double beta = v[0] * ntgt[0] + v[1] * ntgt[1] + v[2] * ntgt[2];  // :191
+  if (abs_angles) beta = std::fabs(beta);
+  const double wy = w[0] * ntgt[0] + w[1] * ntgt[1] + w[2] * ntgt[2];
+  const double ux = u[0] * ntgt[0] + u[1] * ntgt[1] + u[2] * ntgt[2];
+  double alpha = abs_angles ? std::atan2(std::fabs(wy), std::fabs(ux)) : std::atan2(wy, ux);  // :200-205
+  delta = delta / max_dist;  // :217
+  if (abs_angles)
+    alpha = alpha / (M_PI / 2);
+  else {  // :221-226
+    alpha = (alpha + M_PI) / (2.0 * M_PI);
+    beta = (beta + 1.0) / 2.0;
+    gamma = (gamma + 1.0) / 2.0;
+  }
+  f[0] = alpha;
+  f[1] = beta;
+  f[2] = gamma;
+  f[3] = delta;
+  return 1;
+}
+
+int orc_pfh(const float* xyz, const float* normals, int normal_stride, int n, double radius, int max_nn,
+            int quantum, int flags, float* out, int nthreads) {
+  if (quantum < 1) return -1;
+  const bool use_dist = flags & ORC_PFH_USE_DIST, differential = flags & ORC_PFH_DIFFERENTIAL;
+  const bool check_flip = flags & ORC_PFH_CHECK_FLIP, abs_angles = flags & ORC_PFH_ABS_ANGLES, average = flags & ORC_PFH_AVERAGE;
+  const int nr_features = use_dist ? 4 : 3, nr_bins = quantum * nr_features;
+  CellGrid grid(xyz, n, radius);
+  const float r2 = r2_of(radius);
+  nthreads = resolve_threads(nthreads);
+  std::vector<float> hist((size_t)n * nr_bins, 0.f);
+  std::vector<std::vector<Nb>> lists(average ? n : 0);
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<Nb> nbs;
+#pragma omp for schedule(dynamic, 256)
+    for (int cp = 0; cp < n; ++cp) {
+      grid.query(xyz + 3 * (size_t)cp, r2, nbs);
+      sort_truncate(nbs, max_nn);  // pfh.cpp:186
+      float* h = hist.data() + (size_t)cp * nr_bins;
+      const double npsqr = 100.0 / nbs.size();  // :212 (inf for a non-finite point, which has no neighbours at all)
+      for (size_t ni = 1; ni < nbs.size(); ni++) {  // :217
+        const int j = nbs[ni].idx;
+        double f[4];
+        if (orc_pfh_pair(xyz + 3 * (size_t)cp, normals + (size_t)normal_stride * cp, xyz + 3 * (size_t)j,
+                         normals + (size_t)normal_stride * j, nbs[ni].d2, 2 * radius, check_flip, abs_angles, f)) {
+          for (int ft = 0; ft < nr_features; ++ft) {  // :224-228, :267-271 with a_, b_, c_, d_ = 0, 1, 2, 3
+            const int fi = std::max(0, std::min(quantum - 1, (int)std::floor(quantum * f[ft])));
+            h[ft * quantum + fi] += npsqr;  // float += double
+          }
+        } else {
+          for (int i = 0; i < nr_bins; i++) h[i] += npsqr / quantum;  // :284-286
+        }
+      }
+      if (average) lists[cp] = nbs;
+    }
+  }
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
+  for (int cp = 0; cp < n; ++cp) {
+    float* o = out + (size_t)cp * nr_bins;
+    if (!average) {
+      for (int b = 0; b < nr_bins; ++b) o[b] = hist[(size_t)cp * nr_bins + b];  // :295-300
+    } else {
+      for (int b = 0; b < nr_bins; ++b) o[b] = 0.f;
+      const std::vector<Nb>& nbs = lists[cp];
+      if (!nbs.empty()) {  // :311-312
+        double sum_weight = 0.0;
+        for (size_t ni = 1; ni < nbs.size(); ni++) {  // :317-327
+          const double weight = 1.0 / nbs[ni].d2;
+          sum_weight += weight;
+          const float* hn = hist.data() + (size_t)nbs[ni].idx * nr_bins;
+          for (int b = 0; b < nr_bins; ++b) o[b] += hn[b] * weight;
+        }
+        for (int b = 0; b < nr_bins; ++b) o[b] /= sum_weight;  // :330-331
+      }
+    }
+    if (differential)  // :337-350
+      for (int ft = 0; ft < nr_features; ++ft)
+        for (int b = quantum - 1; b > 0; b--) o[ft * quantum + b] -= o[ft * quantum + b - 1];
+  }
+  return nr_bins;
+}
+
 }  // extern "C"

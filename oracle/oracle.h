@@ -179,6 +179,28 @@ int orc_knn_mean_distance(const float* xyz, int n, int k, double* avg, int nthre
 int64_t orc_noise_filter(const double* avg, int n, double alpha, uint8_t* keep, double* mean_out,
                          double* stddev_out);
 
+/* cloud_algos::PointFeatureHistogram (cloud_algos/src/pfh.cpp:78-366, pair features at
+ * cloud_algos/include/cloud_algos/pfh.h:102-238): "star" pair features between every point and its
+ * neighbours within `radius` (<= max_nn nearest, self first and skipped), one 1-D histogram of `quantum`
+ * bins per feature (alpha, beta, gamma [, delta]) with increments of 100 / k, then -- with
+ * ORC_PFH_AVERAGE, the FPFH step -- the 1/d2-weighted average of the neighbours' histograms (:303-333) and,
+ * with ORC_PFH_DIFFERENTIAL, bin-to-bin differences (:337-350).  The combined n-D histogram mode
+ * (combine_ = true) is not restated.  out: n x nr_bins floats, point-major, nr_bins = quantum * (3 or 4).
+ * Quirks kept: a point whose only neighbour is itself gets 0/0 = NaN with ORC_PFH_AVERAGE; a duplicate
+ * neighbour (d2 == 0) yields an invalid pair (increment spread over all bins, :277-287) and an infinite
+ * weight. */
+#define ORC_PFH_USE_DIST 1
+#define ORC_PFH_DIFFERENTIAL 2
+#define ORC_PFH_CHECK_FLIP 4
+#define ORC_PFH_ABS_ANGLES 8
+#define ORC_PFH_AVERAGE 16
+int orc_pfh(const float* xyz, const float* normals, int normal_stride, int n, double radius, int max_nn,
+            int quantum, int flags, float* out, int nthreads);
+/* One pair (pfh.h:102-238): returns 0 if the pair is invalid, else 1 and alpha, beta, gamma, delta in f[4]
+ * (already normalised to [0, 1]).  d2 is the cached squared distance (:246). */
+int orc_pfh_pair(const float* ps, const float* ns, const float* pt, const float* nt, float d2, double max_dist,
+                 int check_flip, int abs_angles, double* f);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -316,5 +316,31 @@ def noise_filter(avg, alpha):
     return keep.astype(bool), mean.value, std.value
 
 
+PFH_USE_DIST, PFH_DIFFERENTIAL, PFH_CHECK_FLIP, PFH_ABS_ANGLES, PFH_AVERAGE = 1, 2, 4, 8, 16
+PFH_DEFAULT = PFH_CHECK_FLIP | PFH_AVERAGE  # the plugin's defaults produce FPFHs (pfh.h:83-93)
+
+
+def pfh(xyz, nrm, radius=0.03, max_nn=100, quantum=9, flags=PFH_DEFAULT, nthreads=0):
+    """PointFeatureHistogram (star features, optional FPFH averaging).  Returns (n, quantum * (3 or 4)) float32."""
+    L = lib()
+    p = _xyz(xyz)
+    nn = np.ascontiguousarray(nrm, dtype=np.float32)
+    nb = quantum * (4 if flags & PFH_USE_DIST else 3)
+    out = np.zeros((p.shape[0], nb), np.float32)
+    rc = L.orc_pfh(_ptr(p, C.c_float), _ptr(nn, C.c_float), int(nn.shape[1]), p.shape[0], C.c_double(radius), int(max_nn),
+                   int(quantum), int(flags), _ptr(out, C.c_float), int(nthreads))
+    assert rc == nb
+    return out
+
+
+def pfh_pair(ps, ns, pt, nt, d2, max_dist, check_flip=True, abs_angles=False):
+    L = lib()
+    a = [np.ascontiguousarray(v, np.float32) for v in (ps, ns, pt, nt)]
+    f = np.zeros(4, np.float64)
+    ok = L.orc_pfh_pair(*[_ptr(v, C.c_float) for v in a], C.c_float(d2), C.c_double(max_dist), int(check_flip), int(abs_angles),
+                        f.ctypes.data_as(C.POINTER(C.c_double)))
+    return bool(ok), f
+
+
 def num_threads():
     return lib().orc_num_threads()

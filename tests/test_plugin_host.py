@@ -26,7 +26,8 @@ def test_discovery_matches_plugins_xml(built):
     assert '<library path="lib/libcloud_algos">' in xml
     declared = re.findall(r'<class name="([^"]+)" type="([^"]+)" base_class_type="([^"]+)">', xml)
     assert {d[0] for d in declared} == {"cloud_algos/NormalEstimation", "cloud_algos/LocalRadiusEstimation", "cloud_algos/GlobalRSD",
-                                        "cloud_algos/SVMClassification", "cloud_algos/StatisticalNoiseRemoval"}
+                                        "cloud_algos/SVMClassification", "cloud_algos/StatisticalNoiseRemoval",
+                                        "cloud_algos/PointFeatureHistogram"}
     for name, typ, base in declared:
         assert typ == name.replace("/", "::") and base == "cloud_algos::CloudAlgo"
         p = plugin.Plugin(name)  # pluginlib lookup by the reference's names
@@ -85,6 +86,23 @@ def test_noise_removal_plugin_surface_and_errors(built):
     # public fields persist between calls, exactly like the reference's (pre() only overrides what has a rosparam)
     res, out = nr.run(pts[:5], fields={"alpha_": 3.0, "neighborhood_size_": 10})
     assert res == "ERROR: Not enough points in the cloud (or too many neighbors requested)!" and out is None
+
+
+def test_pfh_plugin_surface_and_errors(built):
+    pf = plugin.Plugin("cloud_algos/PointFeatureHistogram")
+    req, prov = pf.requires_provides()
+    assert req == ["x", "y", "z", "nx", "ny", "nz"] and prov == [f"f{i}" for i in range(1, 28)]  # pfh.cpp:31-76, 9 x 3 bins
+    assert pf.topic() == "cloud_pfh"
+    pts = synth.analytic_shape("plane", 50)
+    res, out = pf.run(pts, {"intensity": np.zeros(50, np.float32)})
+    assert res == "missing normals" and out is None
+    nrm = {"nx": np.zeros(50, np.float32), "ny": np.zeros(50, np.float32), "nz": np.ones(50, np.float32)}
+    res, out = pf.run(pts, nrm, fields={"combine_": 1})
+    assert res.startswith("unsupported options") and out is None and not pf.output_valid()
+    pf.set_field("combine_", 0)
+    pf.set_field("use_dist_", 1)
+    pf.set_field("point_label_", 3)
+    assert pf.requires_provides()[1] == [f"f{i}" for i in range(1, 37)] + ["point_label"]
 
 
 def test_sample_pipeline_yaml_keys(built):
@@ -219,3 +237,16 @@ def test_noise_removal_plugin_against_oracle(built, oracle):
     # the size check (noise_removal.cpp:152-158)
     res, out = nr.run(pts, {"tag": tag}, fields={"min_nr_pts_": len(pts)})
     assert res == "output size check failed (see min_nr_pts parameter)" and out is None and not nr.output_valid()
+
+
+@pytest.mark.gpu
+def test_pfh_plugin_against_oracle(built, oracle):
+    pts = synth.tabletop(15_000, noise_sigma=0.0003)
+    nrm = np.nan_to_num(oracle.normals(pts, 0.02)[0][:, :3], nan=0.0)
+    pf = plugin.Plugin("cloud_algos/PointFeatureHistogram")
+    res, out = pf.run(pts, {"nx": nrm[:, 0], "ny": nrm[:, 1], "nz": nrm[:, 2]}, fields={"point_label_": 5})
+    assert res == "ok" and list(out["channels"])[:3] == ["nx", "ny", "nz"] and list(out["channels"])[-1] == "point_label"
+    got = np.stack([out["channels"][f"f{i}"] for i in range(1, 28)], 1)
+    want = oracle.pfh(pts, nrm)  # the plugin's defaults: radius 0.03, max_nn 100, quantum 9, check_flip, average
+    assert np.allclose(got, want, rtol=2e-4, atol=2e-3)
+    assert np.all(out["channels"]["point_label"] == 5)
