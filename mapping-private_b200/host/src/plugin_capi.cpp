@@ -13,6 +13,7 @@
 #include <cloud_algos/svm_classification.h>
 #include <cloud_algos/noise_removal.h>
 #include <cloud_algos/pfh.h>
+#include <cloud_algos/pcd_io.h>
 
 using namespace cloud_algos;
 
@@ -170,6 +171,26 @@ int capi_out_num_channels(void* hv, int which) { const sensor_msgs::PointCloud* 
 const char* capi_out_channel_name(void* hv, int which, int c) { return pick((Handle*)hv, which)->channels[c].name.c_str(); }
 const float* capi_out_channel(void* hv, int which, int c) { return pick((Handle*)hv, which)->channels[c].values.data(); }
 const float* capi_out_points(void* hv, int which) { const sensor_msgs::PointCloud* c = pick((Handle*)hv, which); return c->points.empty() ? nullptr : &c->points[0].x; }
+
+// PCD I/O helpers (host/include/cloud_algos/pcd_io.h): returns the number of points, -1 on failure; xyz / nrm hold
+// up to cap points (nrm may be NULL); *has_normals tells whether the file carried normal_x/y/z.
+int capi_pcd_read(const char* name, float* xyz, float* nrm, int cap, int* has_normals) {
+  std::vector<float> p, nn;
+  if (!readPCDXYZ(name, p, &nn)) return -1;
+  const int n = (int)(p.size() / 3);
+  if (has_normals) *has_normals = nn.empty() ? 0 : 1;
+  for (int i = 0; i < n && i < cap; ++i)
+    for (int a = 0; a < 3; ++a) {
+      if (xyz) xyz[3 * i + a] = p[3 * i + a];
+      if (nrm && !nn.empty()) nrm[3 * i + a] = nn[3 * i + a];
+    }
+  return n;
+}
+int capi_write_feature(const char* name, const float* data, int hist_num, int dim, int remove_0) {
+  std::vector<std::vector<float> > f(hist_num, std::vector<float>(dim));
+  for (int h = 0; h < hist_num; ++h) f[h].assign(data + (size_t)h * dim, data + (size_t)(h + 1) * dim);
+  return writeFeature(name, f, remove_0 != 0) ? 0 : -1;
+}
 
 int capi_list_requires(void* hv, char* buf, int cap) {
   std::string s;

@@ -51,8 +51,30 @@ def lib():
         L.capi_out_points.restype = C.POINTER(C.c_float)
         L.capi_out_points.argtypes = [C.c_void_p, C.c_int]
         L.capi_list_requires.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.capi_pcd_read.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.capi_write_feature.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         _LIB = L
     return _LIB
+
+
+def pcd_read(path: str):
+    """host/include/cloud_algos/pcd_io.h readPCDXYZ: (xyz (n,3) float32, normals (n,3) | None)."""
+    L = lib()
+    has = C.c_int(0)
+    n = L.capi_pcd_read(str(path).encode(), None, None, 0, C.byref(has))
+    if n < 0:
+        raise IOError(f"cannot read {path}")
+    xyz = np.zeros((max(n, 1), 3), np.float32)
+    nrm = np.zeros((max(n, 1), 3), np.float32)
+    L.capi_pcd_read(str(path).encode(), xyz.ctypes.data_as(C.POINTER(C.c_float)), nrm.ctypes.data_as(C.POINTER(C.c_float)), n, C.byref(has))
+    return xyz[:n], (nrm[:n] if has.value else None)
+
+
+def write_feature(path: str, feature: np.ndarray, remove_0: bool = True):
+    """host/include/cloud_algos/pcd_io.h writeFeature (the reference's `FIELDS vfh` histogram file)."""
+    f = np.ascontiguousarray(feature, np.float32)
+    if lib().capi_write_feature(str(path).encode(), f.ctypes.data_as(C.POINTER(C.c_float)), f.shape[0], f.shape[1], int(remove_0)) != 0:
+        raise IOError(f"cannot write {path}")
 
 
 class Plugin:
