@@ -183,6 +183,7 @@ def run_grsd(args, rank, world, local_rank):
     sizes = np.diff(off)
     mine = shard.assign_clusters_lpt(sizes.tolist(), world)[rank]
     my_xyz = np.concatenate([xyz[off[c]:off[c + 1]] for c in mine]) if mine else np.zeros((0, 3), np.float32)
+    my_xyz = torch.from_numpy(np.ascontiguousarray(my_xyz)).pin_memory().numpy()  # page-locked host buffer (H2D at PCIe speed)
     my_off = np.concatenate([[0], np.cumsum(sizes[mine])]).astype(np.int32)
     ctx = cab.Context(local_rank, exact=True)
     leaf = 0.025
@@ -243,7 +244,7 @@ def run_grsd(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C3 GRSD-21 on {args.clusters} synthetic clusters, leaf 2.5 cm, normals r=2cm, cluster-per-GPU",
                        "points": int(off[-1]), "leaf_m": leaf, "parallelism": f"clusters LPT x{world}, int32 all-reduce of histograms",
-                       "timed": "host buffers in, histograms out (H2D + D2H inside)"},
+                       "timed": "pinned host buffers in, histograms out (H2D + D2H inside)"},
             "kernels_ms_per_step_rank0": statistics.mean(kern_ms), "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": args.clusters / (dt / args.steps), "unit": "clouds/s", "h2d_bytes_per_step": int(off[-1]) * 12,
                     "d2h_bytes_per_step": args.clusters * 84},
