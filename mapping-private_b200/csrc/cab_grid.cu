@@ -601,7 +601,6 @@ int build_grid(cab_ctx* ctx, float cell) {
     CAB_LAUNCH_CHECK(ctx);
   } else if (sharded_sort) {
     const Domain& dm = ctx->domains[0];
-    const size_t ksz = key32 ? 4 : 8;
     if (int rc = reserve(ctx, ctx->b_vals[1], (size_t)n * 4)) return rc;
     if (int rc = reserve(ctx, ctx->b_keys[2], (size_t)n * 8)) return rc;
     if (int rc = reserve(ctx, ctx->b_vals[2], (size_t)n * 4 + 16)) return rc;
@@ -630,7 +629,6 @@ int build_grid(cab_ctx* ctx, float cell) {
     CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_perm.p, 0xff, (size_t)n * 4, st));  // unneeded positions: perm = -1
     CAB_CUDA(ctx, cudaStreamSynchronize(st));
     const int m = *(const int*)ctx->h_pin;
-    (void)ksz;
     if (m > 0) {
       if (key32)
         gather_keys_kernel<unsigned><<<(m + 255) / 256, 256, 0, st>>>((const unsigned*)ctx->b_keys[0].p, (const int*)ctx->b_vals[2].p, m,

@@ -97,11 +97,10 @@ int run_knn_mean(cab_ctx* ctx, int k, float cell_hint, double* avg_host) {
   float cell = cell_hint;
   if (!(cell > 0.f)) {
     if (int rc = compute_bounds(ctx)) return rc;
-    double ext[3] = {0, 0, 0}, vol = 1;
+    double ext[3] = {0, 0, 0};
     if (ctx->dom_count.empty() || ctx->dom_count[0] == 0) return fail(ctx, CAB_ERR_ARG, "cab_knn_mean_distance: no finite points");
     for (int a = 0; a < 3; ++a) {
       ext[a] = std::max(1e-6, (double)ctx->dom_bounds[3 + a] - (double)ctx->dom_bounds[a]);
-      vol *= ext[a];
     }
     const double nv = (double)ctx->dom_count[0];
     // a surface sampled with nv points inside the box has a spacing of about sqrt(largest face / nv) (an
@@ -109,7 +108,6 @@ int run_knn_mean(cab_ctx* ctx, int k, float cell_hint, double* avg_host) {
     // about sqrt(k / pi) spacings
     const double face = std::max(ext[0] * ext[1], std::max(ext[0] * ext[2], ext[1] * ext[2]));
     const double spacing = std::sqrt(face / nv);
-    (void)vol;
     cell = (float)(spacing * std::sqrt((double)k / M_PI) * 1.5);
   }
   if ((int64_t)ctx->n < k) return fail(ctx, CAB_ERR_ARG, "cab_knn_mean_distance: %d nearest neighbors requested, but only %lld points in total", k, (long long)ctx->n);

@@ -4,9 +4,12 @@
 // (kdtree_->radiusSearch(cp, radius_, idx, d2, max_nn_), cloud_algos/src/radius_estimation.cpp:120;
 // default 150 at radius_estimation.h:82, 75 in launch/pipeline_tmp.launch:20).  The documented rule
 // is "the max_nn smallest (d2, input index) pairs".  Instead of materialising and sorting lists,
-// every query gets a threshold pair (d2*, idx*) found by a radix select over the fp32 bit pattern
-// of d2 (6 bits per traversal) plus an index tie-break; the normals / RSD kernels then accept a
-// candidate iff (d2, idx) <= (d2*, idx*).
+// every query gets a threshold pair (d2*, idx*); the normals / RSD kernels then accept a candidate iff
+// (d2, idx) <= (d2*, idx*).  Two traversals find it (value_select_kernel): a 64-bin histogram of d2 over
+// [0, r2] locates the bin holding the max_nn-th neighbour (on a surface the in-radius d2 values are spread
+// evenly, so that bin holds k / 64 candidates), the second traversal lists that bin's candidates and ranks
+// them by (d2, index).  Packets where a query's bin overflows the list (many equal distances) fall back to
+// the radix select over the fp32 bit pattern of d2 (threshold_kernel, 6 bits per traversal).
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -32,6 +35,8 @@ struct ThrArgs {
   float* thr_d2;
   int* thr_idx;
   const unsigned char* done;  // optional, indexed by input index: queries that need no threshold any more
+  unsigned char* fallback;    // per packet (relative to p0): value_select_kernel sets it, threshold_kernel honours it
+  int use_fallback;           // threshold_kernel: only the flagged packets
 };
 
 __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrArgs a) {
@@ -40,6 +45,7 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pid = a.p0 + blockIdx.x * kSelWarps + warp;
   if (pid >= a.p1) return;
+  if (a.use_fallback && !a.fallback[pid - a.p0]) return;
   const GridView& g = a.g;
   ChunkTile* tile = &tiles[warp];
   const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
@@ -105,6 +111,118 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrA
   if (pc.active && wanted) {
     a.thr_d2[pc.qi] = need ? dstar : INFINITY;
     a.thr_idx[pc.qi] = need ? cur : INT_MAX;
+  }
+}
+
+constexpr int kListCap = kSelBins / 2;  // (d2, index) pairs that fit into a lane's histogram column
+
+// Selection by value histograms (see the file comment).  hist[warp][.][lane] is the lane's private column: first
+// the 64 counters, then the list of the target bin's candidates.  A second histogram level subdivides the
+// target bin when it is too full for the list (k-NN queries: k << candidates in the radius).
+__global__ void __launch_bounds__(kSelWarps * kWarp) value_select_kernel(const ThrArgs a) {
+  __shared__ ChunkTile tiles[kSelWarps];
+  __shared__ unsigned hist[kSelWarps][kSelBins + 1][kWarp];  // row kSelBins: everything beyond the radius
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pid = a.p0 + blockIdx.x * kSelWarps + warp;
+  if (pid >= a.p1) return;
+  const GridView& g = a.g;
+  ChunkTile* tile = &tiles[warp];
+  const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
+  const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z, r2 = a.r2;
+  bool wanted = pc.active;
+  if (a.done) {
+    wanted = wanted && !a.done[g.perm[pc.qi]];
+    if (!__any_sync(kFull, wanted)) return;
+  }
+  // bins are monotone maps of d2, so they partition the candidates by distance whatever their exact edges are
+  const float scale1 = (float)kSelBins / r2;
+  auto bin1 = [&](float d2) { return min(__float2int_rz(d2 * scale1), kSelBins - 1); };
+  const unsigned col = (unsigned)__cvta_generic_to_shared(&hist[warp][0][lane]);  // this lane's column, rows 128 bytes apart
+  auto count = [&](int row) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(col + 128u * (unsigned)row) : "memory"); };
+  auto pick = [&](int target, int& bin, int& before, int& in_bin) {  // bin holding the target-th candidate (1-based)
+    int k = 0;
+    bin = -1;
+    before = in_bin = 0;
+    for (int b = 0; b < kSelBins; ++b) {
+      const int c = hist[warp][b][lane];
+      if (bin < 0 && k + c >= target) {
+        bin = b;
+        before = k;
+        in_bin = c;
+      }
+      k += c;
+    }
+    return k;
+  };
+  for (int b = 0; b <= kSelBins; ++b) hist[warp][b][lane] = 0;
+  for_each_chunk(g, pc, lane, tile, [&](int cnt, const float4&, int, bool) {
+    // no branch per candidate: whatever is not a neighbour is counted in the extra row (d2 > r2, also inf and NaN)
+    for_each_staged_d2(tile, cnt, qx, qy, qz, [&](int, float d2) { count(d2 <= r2 ? bin1(d2) : kSelBins); });
+  });
+  int t1, before1, in1;
+  const int k = pick(a.max_nn, t1, before1, in1);
+  const bool need = wanted && k > a.max_nn;  // k <= max_nn: every neighbour is kept
+  // second level: 64 sub-bins of bin t1
+  const bool deep = need && in1 > kListCap;
+  int t2 = -1, before2 = 0;
+  const float lo2 = (float)t1 / scale1, scale2 = scale1 * (float)kSelBins;
+  auto bin2 = [&](float d2) { return min(max(__float2int_rz((d2 - lo2) * scale2), 0), kSelBins - 1); };
+  bool overflow = false;
+  if (__any_sync(kFull, deep)) {
+    for (int b = 0; b <= kSelBins; ++b) hist[warp][b][lane] = 0;
+    for_each_chunk(g, pc, lane, tile, [&](int cnt, const float4&, int, bool) {
+      if (!deep) return;
+      for_each_staged_d2(tile, cnt, qx, qy, qz, [&](int, float d2) { count(d2 <= r2 && bin1(d2) == t1 ? bin2(d2) : kSelBins); });
+    });
+    if (deep) {
+      int in2;
+      pick(a.max_nn - before1, t2, before2, in2);
+      overflow = in2 > kListCap;
+    }
+  }
+  if (__any_sync(kFull, overflow)) {  // many equal distances: the radix select redoes this packet
+    if (lane == 0) a.fallback[pid - a.p0] = 1;
+    return;
+  }
+  if (__any_sync(kFull, need)) {
+    float* ld2 = reinterpret_cast<float*>(&hist[warp][0][lane]);  // entry e: d2 at row 2e, index at row 2e + 1
+    int filled = 0;
+    for_each_chunk(g, pc, lane, tile, [&](int cnt, const float4&, int, bool) {
+      if (!need) return;
+      for_each_staged_d2(tile, cnt, qx, qy, qz, [&](int m, float d2) {
+        if (d2 <= r2 && bin1(d2) == t1 && (!deep || bin2(d2) == t2) && filled < kListCap) {
+          ld2[(2 * filled) * kWarp] = d2;
+          reinterpret_cast<int*>(ld2)[(2 * filled + 1) * kWarp] = g.perm[tile->idx[m]];
+          ++filled;
+        }
+      });
+    });
+    if (need) {
+      // the remaining rank among the listed candidates, by (d2, index)
+      const int want_rank = a.max_nn - before1 - before2 - 1;
+      float sd2 = INFINITY;
+      int sidx = INT_MAX;
+      for (int e = 0; e < filled; ++e) {
+        const float d2 = ld2[(2 * e) * kWarp];
+        const int id = reinterpret_cast<const int*>(ld2)[(2 * e + 1) * kWarp];
+        int rank = 0;
+        for (int f = 0; f < filled; ++f) {
+          const float od2 = ld2[(2 * f) * kWarp];
+          const int oid = reinterpret_cast<const int*>(ld2)[(2 * f + 1) * kWarp];
+          rank += (od2 < d2 || (od2 == d2 && oid < id)) ? 1 : 0;
+        }
+        if (rank == want_rank) {
+          sd2 = d2;
+          sidx = id;
+        }
+      }
+      a.thr_d2[pc.qi] = sd2;
+      a.thr_idx[pc.qi] = sidx;
+    }
+  }
+  if (pc.active && wanted && !need) {
+    a.thr_d2[pc.qi] = INFINITY;
+    a.thr_idx[pc.qi] = INT_MAX;
   }
 }
 
@@ -203,6 +321,12 @@ int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done)
   a.done = done;
   const int np = a.p1 - a.p0;
   if (np > 0) {
+    if (int rc = reserve(ctx, ctx->b_thr_flag, (size_t)np + 16)) return rc;
+    a.fallback = (unsigned char*)ctx->b_thr_flag.p;
+    CAB_CUDA(ctx, cudaMemsetAsync(a.fallback, 0, (size_t)np, st));
+    value_select_kernel<<<(np + kSelWarps - 1) / kSelWarps, kSelWarps * kWarp, 0, st>>>(a);
+    CAB_LAUNCH_CHECK(ctx);
+    a.use_fallback = 1;  // packets whose target bin did not fit the list (flag read on the device: no host sync)
     threshold_kernel<<<(np + kSelWarps - 1) / kSelWarps, kSelWarps * kWarp, 0, st>>>(a);
     CAB_LAUNCH_CHECK(ctx);
   }

@@ -174,6 +174,34 @@ __device__ __forceinline__ int for_each_chunk(const GridView& g, const PacketCtx
   return pc.total;
 }
 
+// d2 (the documented rule, packed arithmetic) of every staged candidate against this lane's query: fn(m, d2) for
+// m = 0 .. 4 * ceil(cnt / 4) - 1; the padding candidates lie far away (d2 = inf).
+template <class Fn>
+__device__ __forceinline__ void for_each_staged_d2(const ChunkTile* tile, int cnt, float qx, float qy, float qz, Fn&& fn) {
+  const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
+  const float4* tx = reinterpret_cast<const float4*>(tile->x);
+  const float4* ty = reinterpret_cast<const float4*>(tile->y);
+  const float4* tz = reinterpret_cast<const float4*>(tile->z);
+  const int groups = (cnt + 3) >> 2;
+#pragma unroll 2
+  for (int g4 = 0; g4 < groups; ++g4) {
+    const float4 X = tx[g4], Y = ty[g4], Z = tz[g4];
+    float a, b;
+    {
+      const f32x2 dx = sub2(pack2(X.x, X.y), qx2), dy = sub2(pack2(Y.x, Y.y), qy2), dz = sub2(pack2(Z.x, Z.y), qz2);
+      unpack2(add2(add2(sq2(dx), sq2(dy)), sq2(dz)), a, b);
+      fn(4 * g4, a);
+      fn(4 * g4 + 1, b);
+    }
+    {
+      const f32x2 dx = sub2(pack2(X.z, X.w), qx2), dy = sub2(pack2(Y.z, Y.w), qy2), dz = sub2(pack2(Z.z, Z.w), qz2);
+      unpack2(add2(add2(sq2(dx), sq2(dy)), sq2(dz)), a, b);
+      fn(4 * g4 + 2, a);
+      fn(4 * g4 + 3, b);
+    }
+  }
+}
+
 // Hit mask of one staged chunk for this lane's query: bit m set iff d2(candidate m, q) <= r2.
 // Packed fp32x2 arithmetic, 4 candidates per shared-memory broadcast load.
 __device__ __forceinline__ unsigned chunk_hit_mask(const ChunkTile* tile, float qx, float qy, float qz, float r2) {
