@@ -396,3 +396,38 @@ def test_fast_normals_count_neighbours_exactly_at_the_boundary(ctx, oracle):
         good = ~np.isnan(o4[:, 0])
         assert np.array_equal(np.isnan(n4[:, 0]), ~good)
         assert np.mean(_angle(n4[good, :3], o4[good, :3]) > 1e-3) < 1e-2  # random 3D cloud: ill-conditioned normals allowed
+
+
+def test_properties_at_c4_size(ctx):
+    """The benchmark cloud itself (C4: 20 M points, r = 2 cm): size-independent properties, since the oracle would need
+    most of a minute for it.  Determinism, the two passes seeing the same neighbour sets, unit normals oriented to the
+    viewpoint, radii inside (0, plane_radius], the fused call returning the same bits, and an oracle check on a slab."""
+    pts = synth.room(20_000_000)
+    r = 0.02
+    ctx.set_shard(0, 1)
+    ctx.upload(pts)
+    ctx.build_grid(r)
+    n4 = ctx.normals(r)
+    p1 = ctx.profile()
+    rmin, rmax = ctx.rsd(r)
+    p2 = ctx.profile()
+    assert p1["n_valid"] == pts.shape[0] and p1["neighbour_sum"] == p2["neighbour_sum"]
+    assert 200 < p1["neighbour_sum"] / pts.shape[0] < 300  # the density the workload is specified at (k ~ 250)
+    good = ~np.isnan(n4[:, 0])
+    assert good.mean() > 0.9999
+    assert np.allclose(np.linalg.norm(n4[good, :3], axis=1), 1.0, atol=1e-5)
+    assert np.all(np.sum(n4[good, :3] * (-pts[good]), axis=1) >= -1e-4)
+    assert np.all(rmin > 0) and np.all(rmin <= np.float32(0.1)) and np.all(rmax <= np.float32(0.1))
+    # the same bits from a second, fused run
+    f4, fmin, fmax = ctx.normals_rsd(r)
+    assert np.array_equal(f4.view(np.uint32), n4.view(np.uint32))
+    assert np.array_equal(fmin, rmin) and np.array_equal(fmax, rmax)
+    # neighbour sets of a few queries in the middle of the cloud, bit-exact against brute force in numpy
+    q0 = 10_000_000
+    off, idx, d2 = ctx.neighbors(r, q0, q0 + 16)
+    for t in range(16):
+        d = pts - pts[q0 + t]
+        dd = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]  # fp32, the documented rule
+        want = np.flatnonzero(dd <= np.float32(r) * np.float32(r))
+        got = np.sort(idx[off[t]:off[t + 1]])
+        assert np.array_equal(got, want)
