@@ -431,3 +431,21 @@ def test_properties_at_c4_size(ctx):
         want = np.flatnonzero(dd <= np.float32(r) * np.float32(r))
         got = np.sort(idx[off[t]:off[t + 1]])
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("k_mean", [16, 512])
+def test_density_patches_neighbour_sets(ctx, oracle, k_mean):
+    """The two ends of the C5 density sweep (mean 16 and 512 neighbours per query): neighbour sets of a slab of queries
+    bit-exact against the oracle."""
+    pts = synth.density_patches(300_000, float(k_mean), 0.02)
+    r = 0.02
+    ctx.set_shard(0, 1)
+    ctx.upload(pts)
+    ctx.build_grid(r)
+    q0, q1 = 150_000, 152_000
+    off, idx, d2 = ctx.neighbors(r, q0, q1)
+    ooff, oidx, od2 = oracle.radius_search(pts, pts[q0:q1], r)
+    assert np.array_equal(off, ooff)
+    gi, gd = _canon(off, idx, d2)
+    assert np.array_equal(gi, oidx) and np.array_equal(gd.view(np.uint32), od2.view(np.uint32))
+    assert 0.7 * k_mean < (off[-1] / (q1 - q0)) < 1.3 * k_mean
