@@ -78,7 +78,9 @@ int cab_set_cloud_device(cab_ctx* ctx, const float* d_xyz, int64_t n, int32_t st
 
 /* Builds the search structure that replaces the kd-tree (radius_estimation.cpp:107;
  * pcl::KdTreeFLANN at grsd_colorCHLAC_tools.hpp:79,175): device radix sort of
- * (row, x) keys, cell offsets, 32-query packets.  `cell` must be >= every radius used later. */
+ * (row, x) keys, cell offsets, 32-query packets.  `cell` must be >= every radius used later.
+ * The cell table is dense: a cloud too spread out for it at this cell size (cfg.max_table_cells) is
+ * indexed with coarser cells -- same results, more candidates tested per query. */
 int cab_build_grid(cab_ctx* ctx, float cell);
 
 /* Query sharding for multi-GPU runs: this context only computes a contiguous range of the packets of

@@ -409,42 +409,55 @@ int build_grid(cab_ctx* ctx, float cell) {
   double ulp = std::ldexp(1.0, (max_abs > 0 ? (int)std::floor(std::log2(max_abs)) : 0) - 23);
   double cell_eff = (double)cell * (1.0 + 1.0 / 1024.0) + 8.0 * ulp;
   ctx->cell = cell;
-  ctx->cell_eff = (float)cell_eff;
-  ctx->inv_cell = 1.0f / ctx->cell_eff;
   ctx->domains.assign(nd, Domain{});
   int64_t rows = 0, cells = 0;
   const int64_t budget = ctx->cfg.max_table_cells > 0 ? ctx->cfg.max_table_cells : ((int64_t)1 << 28);
-  for (int d = 0; d < nd; ++d) {
-    Domain& dm = ctx->domains[d];
-    dm.row_base = rows;
-    dm.cell_base = cells;
-    if (ctx->dom_count[d] == 0) {
-      dm.ox = dm.oy = dm.oz = 0.f;
-      dm.nx = dm.ny = dm.nz = 1;
-    } else {
-      float lo[3], hi[3];
-      for (int a = 0; a < 3; ++a) {
-        lo[a] = ctx->dom_bounds[6 * (size_t)d + a];
-        hi[a] = ctx->dom_bounds[6 * (size_t)d + 3 + a];
+  // The cell table is dense.  A cloud too spread out for it at the requested cell size (an outdoor scan with a 2 cm
+  // radius) gets coarser cells instead of an error: any edge >= the radius is correct, the passes just test more
+  // candidates per query.
+  for (int attempt = 0;; ++attempt) {
+    rows = cells = 0;
+    double want = 0;  // cells this edge would need, as a double (it may overflow int64)
+    bool too_big = false;
+    for (int d = 0; d < nd; ++d) {
+      Domain& dm = ctx->domains[d];
+      dm.row_base = rows;
+      dm.cell_base = cells;
+      if (ctx->dom_count[d] == 0) {
+        dm.ox = dm.oy = dm.oz = 0.f;
+        dm.nx = dm.ny = dm.nz = 1;
+      } else {
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {
+          lo[a] = ctx->dom_bounds[6 * (size_t)d + a];
+          hi[a] = ctx->dom_bounds[6 * (size_t)d + 3 + a];
+        }
+        dm.ox = lo[0];
+        dm.oy = lo[1];
+        dm.oz = lo[2];
+        double ext[3] = {(double)hi[0] - lo[0], (double)hi[1] - lo[1], (double)hi[2] - lo[2]};
+        double nn[3];
+        for (int a = 0; a < 3; ++a) nn[a] = std::floor(ext[a] / cell_eff) + 2;  // +1 slack cell
+        want += nn[0] * nn[1] * nn[2];
+        if (nn[0] > (double)(1 << kXBits) || nn[1] * nn[2] > std::ldexp(1.0, 40) || want > (double)budget) {
+          too_big = true;
+          continue;
+        }
+        dm.nx = (int)nn[0];
+        dm.ny = (int)nn[1];
+        dm.nz = (int)nn[2];
       }
-      dm.ox = lo[0];
-      dm.oy = lo[1];
-      dm.oz = lo[2];
-      double ext[3] = {(double)hi[0] - lo[0], (double)hi[1] - lo[1], (double)hi[2] - lo[2]};
-      int64_t nn[3];
-      for (int a = 0; a < 3; ++a) nn[a] = (int64_t)std::floor(ext[a] / cell_eff) + 2;  // +1 slack cell
-      if (nn[0] > (1 << kXBits) || nn[1] * nn[2] > ((int64_t)1 << 40))
-        return fail(ctx, CAB_ERR_OOM, "cab_build_grid: extent / cell too large for the dense grid");
-      dm.nx = (int)nn[0];
-      dm.ny = (int)nn[1];
-      dm.nz = (int)nn[2];
+      rows += (int64_t)dm.ny * dm.nz;
+      cells += (int64_t)dm.ny * dm.nz * dm.nx;
     }
-    rows += (int64_t)dm.ny * dm.nz;
-    cells += (int64_t)dm.ny * dm.nz * dm.nx;
-    if (cells > budget)
-      return fail(ctx, CAB_ERR_OOM, "cab_build_grid: dense cell table needs > %lld cells (budget %lld)",
-                  (long long)cells, (long long)budget);
+    if (!too_big) break;
+    if (attempt >= 60 || !std::isfinite(cell_eff))
+      return fail(ctx, CAB_ERR_OOM, "cab_build_grid: no cell size fits the dense cell table (budget %lld cells)", (long long)budget);
+    cell_eff *= std::max(1.26, std::min(8.0, std::cbrt(want / (double)budget) * 1.02));
   }
+  ctx->cell_eff = (float)cell_eff;
+  if ((double)ctx->cell_eff < cell_eff) ctx->cell_eff = std::nextafter(ctx->cell_eff, INFINITY);
+  ctx->inv_cell = 1.0f / ctx->cell_eff;
   ctx->n_rows = rows;
   ctx->n_cells = cells;
   ctx->n_valid = (int)n_valid;

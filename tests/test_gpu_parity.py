@@ -449,3 +449,29 @@ def test_density_patches_neighbour_sets(ctx, oracle, k_mean):
     gi, gd = _canon(off, idx, d2)
     assert np.array_equal(gi, oidx) and np.array_equal(gd.view(np.uint32), od2.view(np.uint32))
     assert 0.7 * k_mean < (off[-1] / (q1 - q0)) < 1.3 * k_mean
+
+
+def test_spread_out_cloud_gets_coarser_cells(oracle):
+    """Two small objects 300 m apart with a 1 cm radius: a dense table of 1 cm cells would need ~10^13 entries; the grid is
+    built with coarser cells and the neighbour sets, normals and radii stay what the oracle says."""
+    a = synth.tabletop(20_000, noise_sigma=0.0003)
+    b = synth.tabletop(20_000, noise_sigma=0.0003, seed_extra=1) + np.array([300.0, -150.0, 40.0], np.float32)
+    pts = np.concatenate([a, b]).astype(np.float32)
+    r = 0.01
+    c = cab.Context(0, max_table_cells=1 << 22)
+    c.upload(pts)
+    c.build_grid(r)
+    assert c.profile()["n_cells"] <= 1 << 22
+    off, idx, d2 = c.neighbors(r, 0, pts.shape[0])
+    ooff, oidx, od2 = oracle.radius_search(pts, pts, r)
+    assert np.array_equal(off, ooff)
+    gi, gd = _canon(off, idx, d2)
+    assert np.array_equal(gi, oidx) and np.array_equal(gd.view(np.uint32), od2.view(np.uint32))
+    n4 = c.normals(r)
+    o4, ok = oracle.normals(pts, r)
+    assert c.profile()["neighbour_sum"] == int(ok.sum())
+    c.set_normals(np.nan_to_num(o4[:, :3], nan=0.0))
+    rmin, rmax = c.rsd(r)
+    omin, omax, _ = oracle.rsd(pts, np.nan_to_num(o4[:, :3], nan=0.0), r)
+    assert np.max(np.abs(rmin - omin) / omin) <= RADIUS_TOL_REL and np.max(np.abs(rmax - omax) / omax) <= RADIUS_TOL_REL
+    c.close()
