@@ -74,16 +74,59 @@ def slab_sample(pts, target):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML (what nvidia-smi reads) is polled from a
+    thread every few milliseconds, so that even a 50 ms region (8 GPUs) gets samples; nvidia-smi -lms is the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.004):
         self.index = index
+        self.period_s = period_s
         self.proc = None
+        self.thread = None
+        self.rows = []  # (sm MHz, max MHz, watts, reasons bit mask)
+        self._stop = False
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        nv = self.nvml
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            try:
+                watts = nv.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+            except Exception:
+                watts = None
+            self.rows.append((float(sm), float(mx), watts, int(mask)))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self._stop:
+            self._sample()
+            time.sleep(self.period_s)
 
     def start(self):
+        if self.nvml:
+            import threading
+
+            self._stop = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -92,6 +135,20 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.nvml:
+            self._stop = True
+            if self.thread:
+                self.thread.join(timeout=2)
+            nv = self.nvml
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            sm = [r[0] for r in self.rows]
+            mx = [r[1] for r in self.rows]
+            power = [r[2] for r in self.rows if r[2] is not None]
+            reasons = sorted(k for k, b in bits.items() if any(r[3] & b for r in self.rows))
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                    "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": reasons, "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -101,7 +158,6 @@ class ClockSampler:
             self.proc.kill()
             out = ""
         sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
@@ -116,7 +172,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def cpu_points_per_s(pts, nthreads=0):

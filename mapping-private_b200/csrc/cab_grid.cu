@@ -92,6 +92,18 @@ __device__ __forceinline__ int find_domain(const int* __restrict__ domoff, int n
   return lo;
 }
 
+// sort key of one point (+ its count in the cell histogram); the sentinel row for a non-finite point
+__device__ __forceinline__ unsigned long long point_key(float x, float y, float z, const Domain& dm, float inv_cell,
+                                                        unsigned long long sentinel_row, int xbits, int* __restrict__ cellcnt) {
+  if (!finite3(x, y, z)) return sentinel_row << xbits;
+  int cy, cz;
+  row_cells(dm, y, z, inv_cell, cy, cz);
+  const int xf = xfine_coord(x, dm.ox, inv_cell, dm.nx, dm.xshift);
+  const long long row_local = (long long)cz * dm.ny + cy;
+  atomicAdd(cellcnt + dm.cell_base + row_local * dm.nx + (xf >> dm.xshift), 1);
+  return ((unsigned long long)(dm.row_base + row_local) << xbits) | (unsigned)xf;
+}
+
 template <typename KeyT>
 __global__ void __launch_bounds__(256) key_kernel(const float* __restrict__ xyz, int stride, int n,
                                                   const int* __restrict__ domoff, int n_domains,
@@ -102,20 +114,111 @@ __global__ void __launch_bounds__(256) key_kernel(const float* __restrict__ xyz,
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* p = xyz + (size_t)i * stride;
-  float x = p[0], y = p[1], z = p[2];
-  unsigned long long key = sentinel_row << xbits;
-  if (finite3(x, y, z)) {
-    int d = (n_domains > 1) ? find_domain(domoff, n_domains, i) : 0;
-    const Domain dm = domains[d];
-    int cy = cell_coord(y, dm.oy, inv_cell, dm.ny);
-    int cz = cell_coord(z, dm.oz, inv_cell, dm.nz);
-    int xf = xfine_coord(x, dm.ox, inv_cell, dm.nx, dm.xshift);
-    long long row_local = (long long)cz * dm.ny + cy;
-    key = ((unsigned long long)(dm.row_base + row_local) << xbits) | (unsigned)xf;
-    atomicAdd(cellcnt + dm.cell_base + row_local * dm.nx + (xf >> dm.xshift), 1);
-  }
-  keys[i] = (KeyT)key;
+  const float x = p[0], y = p[1], z = p[2];
+  const int d = (n_domains > 1 && finite3(x, y, z)) ? find_domain(domoff, n_domains, i) : 0;
+  keys[i] = (KeyT)point_key(x, y, z, domains[d], inv_cell, sentinel_row, xbits, cellcnt);
   if (vals) vals[i] = i;
+}
+
+// ---- vector forms for the common layout: one domain, packed xyz (stride 3), 16-byte aligned base ----
+// A thread owns 4 consecutive points = 3 x LDG.128 (48 bytes in flight per thread: the scalar form leaves
+// too few bytes in flight to stream at HBM speed).
+struct Pts4 {
+  float x[4], y[4], z[4];
+};
+__device__ __forceinline__ Pts4 load_pts4(const float4* __restrict__ v, int g) {
+  const float4 a = __ldg(v + 3 * (size_t)g), b = __ldg(v + 3 * (size_t)g + 1), c = __ldg(v + 3 * (size_t)g + 2);
+  Pts4 p;
+  p.x[0] = a.x; p.y[0] = a.y; p.z[0] = a.z;
+  p.x[1] = a.w; p.y[1] = b.x; p.z[1] = b.y;
+  p.x[2] = b.z; p.y[2] = b.w; p.z[2] = c.x;
+  p.x[3] = c.y; p.y[3] = c.z; p.z[3] = c.w;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) bounds_vec_kernel(const float* __restrict__ xyz, int n, unsigned* __restrict__ bounds) {
+  const float4* v = reinterpret_cast<const float4*>(xyz);
+  const int n_groups = n >> 2;
+  unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+  unsigned cnt = 0;
+  auto take = [&](float x, float y, float z) {
+    if (finite3(x, y, z)) {
+      const unsigned e[3] = {f2ord(x), f2ord(y), f2ord(z)};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = min(mn[a], e[a]);
+        mx[a] = max(mx[a], e[a]);
+      }
+      ++cnt;
+    }
+  };
+#pragma unroll 2
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
+    const Pts4 p = load_pts4(v, g);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) take(p.x[k], p.y[k], p.z[k]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {  // the last n mod 4 points
+    const float* p = xyz + 3 * (size_t)(4 * n_groups + threadIdx.x);
+    take(p[0], p[1], p[2]);
+  }
+  __shared__ unsigned sh[8][7];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    mn[a] = __reduce_min_sync(kFull, mn[a]);
+    mx[a] = __reduce_max_sync(kFull, mx[a]);
+  }
+  cnt = __reduce_add_sync(kFull, cnt);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      sh[w][a] = mn[a];
+      sh[w][3 + a] = mx[a];
+    }
+    sh[w][6] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {  // one set of atomics per block
+    unsigned r = sh[0][threadIdx.x];
+    for (int k = 1; k < 8; ++k)
+      r = threadIdx.x < 3 ? min(r, sh[k][threadIdx.x]) : threadIdx.x < 6 ? max(r, sh[k][threadIdx.x]) : r + sh[k][threadIdx.x];
+    if (threadIdx.x < 3) atomicMin(bounds + threadIdx.x, r);
+    else if (threadIdx.x < 6) atomicMax(bounds + threadIdx.x, r);
+    else atomicAdd(bounds + 6, r);
+  }
+}
+
+__global__ void init_bounds_kernel(unsigned* __restrict__ bounds) {
+  if (threadIdx.x < 8) bounds[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256) key_vec_kernel(const float* __restrict__ xyz, int n, const Domain* __restrict__ domains,
+                                                      float inv_cell, unsigned long long sentinel_row, int xbits,
+                                                      KeyT* __restrict__ keys, int* __restrict__ vals, int* __restrict__ cellcnt) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_groups = n >> 2;
+  const Domain dm = domains[0];
+  if (g < n_groups) {
+    const Pts4 p = load_pts4(reinterpret_cast<const float4*>(xyz), g);
+    KeyT k[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k[j] = (KeyT)point_key(p.x[j], p.y[j], p.z[j], dm, inv_cell, sentinel_row, xbits, cellcnt);
+    if constexpr (sizeof(KeyT) == 4) {
+      reinterpret_cast<uint4*>(keys)[g] = make_uint4(k[0], k[1], k[2], k[3]);
+    } else {
+      reinterpret_cast<ulonglong2*>(keys)[2 * (size_t)g] = make_ulonglong2(k[0], k[1]);
+      reinterpret_cast<ulonglong2*>(keys)[2 * (size_t)g + 1] = make_ulonglong2(k[2], k[3]);
+    }
+    if (vals) reinterpret_cast<int4*>(vals)[g] = make_int4(4 * g, 4 * g + 1, 4 * g + 2, 4 * g + 3);
+  } else if (g == n_groups) {
+    for (int i = 4 * n_groups; i < n; ++i) {
+      const float* p = xyz + 3 * (size_t)i;
+      keys[i] = (KeyT)point_key(p[0], p[1], p[2], dm, inv_cell, sentinel_row, xbits, cellcnt);
+      if (vals) vals[i] = i;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) reorder_kernel(const float* __restrict__ xyz, int stride, int n,
@@ -218,12 +321,22 @@ __global__ void __launch_bounds__(256) packet_cost_kernel(const Domain* __restri
   cost[p] = c + 64;  // + a constant per packet (setup, fit, eigen-solve)
 }
 
+// What a rank needs to know about its shard; written by split_kernel, read by the kernels that follow it in
+// the stream (so the host does not have to wait for the split before it launches them).
+struct ShardInfo {
+  int p0, p1;              // own packets
+  int row_lo, row_hi;      // rows (inclusive) whose points this rank sorts: own rows, halo rows and their candidates
+  int sel_begin, sel_end;  // the same as a range of the global sorted order
+  int unused;
+  int n_selected;          // points selected for the sort (= sel_end - sel_begin)
+};
+
 // cells touched by the shard's own packets
 __global__ void __launch_bounds__(256) mark_cells_kernel(const Domain* __restrict__ domains, const Packet* __restrict__ packets,
-                                                         int p0, int p1, const int* __restrict__ cell_start,
+                                                         const ShardInfo* __restrict__ info, const int* __restrict__ cell_start,
                                                          unsigned char* __restrict__ cell_flag) {
-  const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= p1) return;
+  const int p = info->p0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= info->p1) return;
   const Packet pk = packets[p];
   const Domain dm = domains[pk.domain];
   const long long base = dm.cell_base + (long long)pk.row_local * dm.nx;
@@ -234,22 +347,22 @@ __global__ void __launch_bounds__(256) mark_cells_kernel(const Domain* __restric
 
 // A packet needs normals on this rank if it is the shard's own or touches a cell adjacent (3x3x3) to
 // a cell of the shard: every candidate of the shard's RSD pass then has a locally computed normal
-// and no exchange between the two passes is needed.  With need_cell != nullptr the cells that hold the
-// candidates of every such packet are marked as well: only their points have to be sorted on this rank.
+// and no exchange between the two passes is needed.
 __global__ void __launch_bounds__(256) flag_halo_kernel(const Domain* __restrict__ domains, const Packet* __restrict__ packets,
-                                                        int n_packets, int p0, int p1, const int* __restrict__ cell_start,
+                                                        int n_packets, const ShardInfo* __restrict__ info,
+                                                        const int* __restrict__ cell_start,
                                                         const unsigned char* __restrict__ cell_flag,
-                                                        unsigned char* __restrict__ flag, unsigned char* __restrict__ need_cell) {
+                                                        unsigned char* __restrict__ flag) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_packets) return;
-  unsigned char f = (p >= p0 && p < p1) ? 1 : 0;
-  const Packet pk = packets[p];
-  const Domain dm = domains[pk.domain];
-  const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
-  const int* row = cell_start + dm.cell_base + (long long)pk.row_local * dm.nx;
-  const int c0 = max(cell_of_position(row, dm.nx, pk.start) - 1, 0);
-  const int c1 = min(cell_of_position(row, dm.nx, pk.start + pk.count - 1) + 1, dm.nx - 1);
-  if (!f) {
+  unsigned char f = (p >= info->p0 && p < info->p1) ? 1 : 0;
+  if (!f && info->p1 > info->p0) {
+    const Packet pk = packets[p];
+    const Domain dm = domains[pk.domain];
+    const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
+    const int* row = cell_start + dm.cell_base + (long long)pk.row_local * dm.nx;
+    const int c0 = max(cell_of_position(row, dm.nx, pk.start) - 1, 0);
+    const int c1 = min(cell_of_position(row, dm.nx, pk.start + pk.count - 1) + 1, dm.nx - 1);
     for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1) && !f; ++z)
       for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1) && !f; ++y) {
         const long long base = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
@@ -258,34 +371,21 @@ __global__ void __launch_bounds__(256) flag_halo_kernel(const Domain* __restrict
       }
   }
   flag[p] = f;
-  if (f && need_cell)
-    for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1); ++z)
-      for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1); ++y) {
-        const long long base = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
-        for (int c = c0; c <= c1; ++c) need_cell[base + c] = 1;
-      }
 }
 
-// ---- sharded sort (multi-GPU, one domain): only the points of the needed cells are sorted on this rank ----
-// cell of a sort key: row = key >> xbits, cell x = (key & mask) >> xshift
+// ---- sharded sort (multi-GPU, one domain): only the rows the rank reads are sorted on this rank ----
+// Own packets are a contiguous range of the sorted order, hence of rows; halo packets lie within one layer
+// (ny + 1 rows) of them and their candidates within two.  Whole rows [row_lo, row_hi] are taken: the
+// selected points are then exactly the range [sel_begin, sel_end) of the global sorted order, and sorting
+// them alone reproduces that range of the full sort (the radix sort is stable and so is the selection).
 template <typename KeyT>
-__device__ __forceinline__ long long cell_of_key(KeyT key, int xbits, int xshift, int nx, unsigned long long n_rows) {
-  const unsigned long long row = (unsigned long long)key >> xbits;
-  if (row >= n_rows) return -1;  // sentinel row: non-finite point
-  const unsigned xf = (unsigned)((unsigned long long)key & ((1ull << xbits) - 1ull));
-  return (long long)row * nx + (xf >> xshift);
-}
-
-// flag functor of the selection: does point i lie in a cell this shard needs?
-template <typename KeyT>
-struct NeedPoint {
+struct RowRangePoint {
   const KeyT* keys;
-  const unsigned char* need_cell;
-  int xbits, xshift, nx;
-  unsigned long long n_rows;
+  const ShardInfo* info;
+  int xbits;
   __device__ __forceinline__ bool operator()(int i) const {
-    const long long c = cell_of_key(keys[i], xbits, xshift, nx, n_rows);
-    return c >= 0 && need_cell[c] != 0;
+    const long long row = (long long)((unsigned long long)keys[i] >> xbits);
+    return row >= info->row_lo && row <= info->row_hi;  // the sentinel row of non-finite points lies above every row
   }
 };
 
@@ -296,51 +396,161 @@ __global__ void __launch_bounds__(256) gather_keys_kernel(const KeyT* __restrict
   if (j < m) out[j] = keys[idx[j]];
 }
 
-__global__ void __launch_bounds__(256) masked_count_kernel(const int* __restrict__ cellcnt, const unsigned char* __restrict__ need_cell,
-                                                           long long n_cells, int* __restrict__ out) {
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c <= n_cells) out[c] = (c < n_cells && need_cell[c]) ? cellcnt[c] : 0;
-}
-
-// j-th element of the sorted subset -> its position in the full sorted order: every needed cell is complete
-// in the subset, so the rank inside the cell is j minus the subset's start of that cell.
-template <typename KeyT>
-__global__ void __launch_bounds__(256) scatter_sorted_kernel(const float* __restrict__ xyz, int stride, int m,
-                                                             const KeyT* __restrict__ skeys, const int* __restrict__ svals,
-                                                             int xbits, int xshift, int nx, unsigned long long n_rows,
-                                                             const int* __restrict__ cell_start, const int* __restrict__ sub_start,
-                                                             float4* __restrict__ pos, int* __restrict__ perm) {
+// j-th element of the sorted subset -> position sel_begin + j of the full sorted order
+__global__ void __launch_bounds__(256) place_sorted_kernel(const float* __restrict__ xyz, int stride, int m, int sel_begin,
+                                                           const int* __restrict__ svals, float4* __restrict__ pos,
+                                                           int* __restrict__ perm) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
-  const long long c = cell_of_key(skeys[j], xbits, xshift, nx, n_rows);
-  const int gp = cell_start[c] + (j - sub_start[c]);
   const int i = svals[j];
   const float* p = xyz + (size_t)i * stride;
-  pos[gp] = make_float4(p[0], p[1], p[2], 0.f);
-  perm[gp] = i;
+  pos[sel_begin + j] = make_float4(p[0], p[1], p[2], 0.f);
+  perm[sel_begin + j] = i;
 }
 
-// split[g] = first packet whose inclusive cost prefix reaches g/world of the total
-__global__ void split_kernel(const long long* __restrict__ cum, int n_packets, int world, int* __restrict__ split) {
-  const int g = threadIdx.x;
-  if (g > world) return;
-  if (g == 0) { split[0] = 0; return; }
-  if (g == world) { split[world] = n_packets; return; }
-  const long long target = cum[n_packets - 1] / world * g;
-  int lo = 0, hi = n_packets;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (cum[mid] < target) lo = mid + 1; else hi = mid;
+// Shard boundaries.  A rank's work is its own packets (both passes) plus the normals of its halo: the
+// packets up to one layer of rows before its first and after its last packet.  One block, thread g owns
+// cut g; a few fixed-point rounds move the cuts until own cost + kHaloWeight * halo cost is the same for
+// every rank (interior ranks have two halos, the first and last rank one).
+//   cum         inclusive prefix of the packet costs
+//   packet_base per cell: packets before the cell's segment; at a row's first cell: packets of the rows before
+constexpr int kHaloPermille = 380;  // share of the normals pass in a packet's cost (9.05 of 23.6 ms on the 20 M-point room)
+
+__device__ __forceinline__ long long cum_before(const long long* __restrict__ cum, int p) { return p > 0 ? cum[p - 1] : 0; }
+__device__ __forceinline__ int first_packet_of_row(const Domain& dm, const int* __restrict__ packet_base, long long row) {
+  const long long rows = (long long)dm.ny * dm.nz;
+  row = row < 0 ? 0 : (row > rows ? rows : row);
+  return packet_base[dm.cell_base + row * dm.nx];
+}
+
+// first packet whose inclusive cost prefix reaches t, found by one warp: 32 probes per step instead of a
+// chain of dependent loads (the cuts are on the critical path of every sharded build)
+__device__ __forceinline__ int cut_at(const long long* __restrict__ cum, int n_packets, long long t, int lane) {
+  int lo = 0, hi = n_packets;  // the answer lies in [lo, hi]
+  while (hi - lo > 32) {
+    const int step = (hi - lo + 31) / 32;
+    const long long idx = (long long)lo + (long long)lane * step;
+    const bool reached = idx >= hi || cum[idx] >= t;
+    const unsigned m = __ballot_sync(kFull, reached);
+    const int first = m ? __ffs(m) - 1 : 32;
+    if (first == 0) return lo;
+    const long long new_lo = (long long)lo + (long long)(first - 1) * step + 1;
+    if (first < 32) hi = (int)min((long long)hi, (long long)lo + (long long)first * step);
+    lo = (int)new_lo;
   }
-  split[g] = lo;
+  const int idx = lo + lane;
+  const bool reached = idx >= hi || cum[idx] >= t;
+  const unsigned m = __ballot_sync(kFull, reached);
+  return m ? min(lo + __ffs(m) - 1, hi) : hi;
+}
+
+__global__ void __launch_bounds__(1024) split_kernel(const long long* __restrict__ cum, int n_packets, int world, int rank,
+                                                     const Packet* __restrict__ packets, const Domain* __restrict__ domains,
+                                                     int n_domains, const int* __restrict__ packet_base,
+                                                     const int* __restrict__ cell_start, int* __restrict__ split,
+                                                     ShardInfo* __restrict__ info) {
+  __shared__ int s[65];
+  __shared__ long long halo[64];
+  __shared__ long long target[65];
+  const int g = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  const long long total = cum[n_packets - 1];
+  if (g == 0) {
+    s[0] = 0;
+    s[world] = n_packets;
+  }
+  for (int c = 1 + warp; c < world; c += n_warps) {  // one warp per cut
+    const int v = cut_at(cum, n_packets, total / world * c, lane);
+    if (lane == 0) s[c] = v;
+  }
+  __syncthreads();
+  for (int round = 0; round < 3; ++round) {
+    if (g < world) {
+      long long h = 0;
+      const int a = s[g], b = s[g + 1];
+      if (g > 0 && a > 0 && a < n_packets) {  // rows below the first own packet
+        const Packet pk = packets[a];
+        const Domain dm = domains[pk.domain];
+        h += cum_before(cum, a) - cum_before(cum, first_packet_of_row(dm, packet_base, (long long)pk.row_local - dm.ny - 1));
+      }
+      if (g < world - 1 && b > 0 && b < n_packets) {  // rows above the last own packet
+        const Packet pk = packets[b - 1];
+        const Domain dm = domains[pk.domain];
+        h += cum_before(cum, first_packet_of_row(dm, packet_base, (long long)pk.row_local + dm.ny + 2)) - cum_before(cum, b);
+      }
+      halo[g] = h < 0 ? 0 : h * kHaloPermille / 1000;
+    }
+    __syncthreads();
+    if (g == 0) {
+      long long sum = total;
+      for (int j = 0; j < world; ++j) sum += halo[j];
+      const long long each = sum / world, floor_own = total / (8 * (long long)world) + 1;
+      double acc = 0;
+      target[0] = 0;
+      for (int j = 0; j < world; ++j) {
+        const long long own = each - halo[j] > floor_own ? each - halo[j] : floor_own;
+        acc += (double)own;
+        target[j + 1] = (long long)acc;
+      }
+      const double scale = (double)total / acc;  // the clamp may have moved the sum
+      for (int j = 1; j < world; ++j) target[j] = (long long)((double)target[j] * scale);
+    }
+    __syncthreads();
+    for (int c = 1 + warp; c < world; c += n_warps) {
+      const int v = cut_at(cum, n_packets, target[c], lane);
+      if (lane == 0) s[c] = v;
+    }
+    __syncthreads();
+  }
+  if (g <= world) split[g] = s[g];
+  if (g == 0) {
+    ShardInfo si{};
+    si.p0 = s[rank];
+    si.p1 = s[rank + 1];
+    si.row_lo = 0;
+    si.row_hi = -1;
+    if (n_domains == 1 && si.p1 > si.p0) {
+      const Domain dm = domains[0];
+      const long long rows = (long long)dm.ny * dm.nz;
+      const long long lo = (long long)packets[si.p0].row_local - 2 * dm.ny - 2;
+      const long long hi = (long long)packets[si.p1 - 1].row_local + 2 * dm.ny + 2;
+      si.row_lo = (int)(lo < 0 ? 0 : lo);
+      si.row_hi = (int)(hi > rows - 1 ? rows - 1 : hi);
+      si.sel_begin = cell_start[(long long)si.row_lo * dm.nx];
+      si.sel_end = cell_start[((long long)si.row_hi + 1) * dm.nx];
+    }
+    *info = si;
+  }
 }
 
 }  // namespace
+
+// one domain of packed, 16-byte aligned xyz: the layout the vector kernels read
+static bool vector_layout(const cab_ctx* ctx) {
+  return ctx->n_domains == 1 && ctx->stride == 3 && (reinterpret_cast<uintptr_t>(ctx->xyz_in) & 15) == 0;
+}
 
 // Per-domain bounding boxes and finite-point counts of the uploaded cloud -> ctx->dom_bounds / dom_count.
 int compute_bounds(cab_ctx* ctx) {
   const int nd = ctx->n_domains;
   cudaStream_t st = ctx->stream;
+  if (vector_layout(ctx) && ctx->n > 0) {  // one domain, packed xyz: no chunk list, one round trip
+    if (int rc = reserve(ctx, ctx->b_bounds, 8 * sizeof(unsigned))) return rc;
+    if (int rc = reserve_pinned(ctx, 8 * sizeof(unsigned) + 64)) return rc;
+    init_bounds_kernel<<<1, 32, 0, st>>>((unsigned*)ctx->b_bounds.p);
+    CAB_LAUNCH_CHECK(ctx);
+    const int groups = (int)(ctx->n >> 2);
+    const int blocks = std::max(1, std::min((groups + 255) / 256, ctx->sm_count * 8));
+    bounds_vec_kernel<<<blocks, 256, 0, st>>>(ctx->xyz_in, (int)ctx->n, (unsigned*)ctx->b_bounds.p);
+    CAB_LAUNCH_CHECK(ctx);
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->b_bounds.p, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CAB_CUDA(ctx, cudaStreamSynchronize(st));
+    const unsigned* hb = (const unsigned*)ctx->h_pin;
+    ctx->dom_bounds.assign(6, 0.f);
+    ctx->dom_count.assign(1, hb[6]);
+    if (hb[6])
+      for (int a = 0; a < 6; ++a) ctx->dom_bounds[a] = ord2f(hb[a]);
+    return CAB_OK;
+  }
   // ---- bounds per domain --------------------------------------------------------------
   std::vector<Chunk> chunks;
   const int kChunk = 1 << 13;  // ~2400 blocks for 20 M points: enough loads in flight to stream at HBM speed
@@ -446,6 +656,13 @@ int build_grid(cab_ctx* ctx, float cell) {
         dm.nx = (int)nn[0];
         dm.ny = (int)nn[1];
         dm.nz = (int)nn[2];
+        // the slowest-varying slot gets the longer of the y and z extents: shards are slabs along it, and
+        // the more layers a slab has the smaller the share of its halo
+        dm.swap_yz = nn[1] > nn[2] ? 1 : 0;
+        if (dm.swap_yz) {
+          std::swap(dm.oy, dm.oz);
+          std::swap(dm.ny, dm.nz);
+        }
       }
       rows += (int64_t)dm.ny * dm.nz;
       cells += (int64_t)dm.ny * dm.nz * dm.nx;
@@ -492,17 +709,30 @@ int build_grid(cab_ctx* ctx, float cell) {
   if (int rc = reserve(ctx, ctx->b_cellstart, ncell1 * 4)) return rc;
   if (int rc = reserve(ctx, ctx->b_pos, (size_t)std::max(n, 1) * sizeof(float4))) return rc;
   CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_cellcnt.p, 0, ncell1 * 4, st));
-  if (n > 0) {
+  // the sharded sort of one domain selects point indices itself: no identity payload to write
+  const bool sharded_sort = ctx->shard_world > 1 && nd == 1 && n > 0;
+  int* ident = sharded_sort ? nullptr : (int*)ctx->b_vals[0].p;
+  if (n > 0 && vector_layout(ctx)) {
+    const unsigned blocks = (unsigned)(((n >> 2) + 1 + 255) / 256);
+    if (key32)
+      key_vec_kernel<unsigned><<<blocks, 256, 0, st>>>(ctx->xyz_in, n, (const Domain*)ctx->b_domains.p, ctx->inv_cell,
+                                                       (unsigned long long)rows, xbits, (unsigned*)ctx->b_keys[0].p, ident,
+                                                       (int*)ctx->b_cellcnt.p);
+    else
+      key_vec_kernel<unsigned long long><<<blocks, 256, 0, st>>>(ctx->xyz_in, n, (const Domain*)ctx->b_domains.p, ctx->inv_cell,
+                                                                 (unsigned long long)rows, xbits,
+                                                                 (unsigned long long*)ctx->b_keys[0].p, ident, (int*)ctx->b_cellcnt.p);
+    CAB_LAUNCH_CHECK(ctx);
+  } else if (n > 0) {
     if (key32)
       key_kernel<unsigned><<<(n + 255) / 256, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, (const int*)ctx->b_domoff.p, nd,
                                                             (const Domain*)ctx->b_domains.p, ctx->inv_cell,
                                                             (unsigned long long)rows, xbits, (unsigned*)ctx->b_keys[0].p,
-                                                            (int*)ctx->b_vals[0].p, (int*)ctx->b_cellcnt.p);
+                                                            ident, (int*)ctx->b_cellcnt.p);
     else
       key_kernel<unsigned long long><<<(n + 255) / 256, 256, 0, st>>>(
           ctx->xyz_in, ctx->stride, n, (const int*)ctx->b_domoff.p, nd, (const Domain*)ctx->b_domains.p, ctx->inv_cell,
-          (unsigned long long)rows, xbits, (unsigned long long*)ctx->b_keys[0].p, (int*)ctx->b_vals[0].p,
-          (int*)ctx->b_cellcnt.p);
+          (unsigned long long)rows, xbits, (unsigned long long*)ctx->b_keys[0].p, ident, (int*)ctx->b_cellcnt.p);
     CAB_LAUNCH_CHECK(ctx);
   }
 
@@ -540,61 +770,82 @@ int build_grid(cab_ctx* ctx, float cell) {
         (Packet*)ctx->b_packets.p);
     CAB_LAUNCH_CHECK(ctx);
   }
-  // ---- cost-balanced shard boundaries and the halo (multi-GPU only) ---------------------------------
+  // ---- cost-balanced shard boundaries, the halo and the selection for the sharded sort (multi-GPU only) ----
+  // Everything between the packet count and the sort size runs without a host round trip: the kernels read
+  // the rank's packet range and row range from the ShardInfo the split kernel leaves on the device.
   ctx->shard_splits.clear();
   ctx->n_halo_packets = -1;
-  // one domain: the rank sorts only the points it needs (own cells, the cells of the halo packets and
-  // the candidates of those); the full sorted order keeps its layout, unneeded positions stay unwritten
-  const bool sharded_sort = ctx->shard_world > 1 && ctx->n_packets > 0 && nd == 1 && n > 0;
-  unsigned char* need_cell = nullptr;
+  int n_selected = 0, sel_begin = 0;
   if (ctx->shard_world > 1 && ctx->n_packets > 0) {
     const int np = ctx->n_packets, w = ctx->shard_world;
     if (w + 1 > 64) return fail(ctx, CAB_ERR_ARG, "cab_set_shard: world > 63 not supported");
-    if (int rc = reserve(ctx, ctx->b_pcost, (size_t)np * 16 + (w + 1) * 4 + 64)) return rc;
+    const int split_ints = (w + 1 + 3) & ~3;  // keeps the ShardInfo behind the splits 16-byte aligned
+    const size_t tail_bytes = (size_t)split_ints * 4 + sizeof(ShardInfo);
+    if (int rc = reserve(ctx, ctx->b_pcost, (size_t)np * 16 + tail_bytes + 64)) return rc;
     long long* cost = (long long*)ctx->b_pcost.p;
     long long* cum = cost + np;
     int* split = (int*)(cum + np);
-    size_t tmp_cost = 0;
+    ShardInfo* info = (ShardInfo*)(split + split_ints);
+    size_t tmp_cost = 0, tmp_sel = 0, tmp_selk = 0;
+    thrust::counting_iterator<int> ids(0);
     cub::DeviceScan::InclusiveSum(nullptr, tmp_cost, (const long long*)nullptr, (long long*)nullptr, np, st);
-    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_cost + 16)) return rc;
+    cub::DeviceSelect::Flagged(nullptr, tmp_sel, ids, (const unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, np, st);
+    RowRangePoint<unsigned> in32{(const unsigned*)ctx->b_keys[0].p, info, xbits};
+    RowRangePoint<unsigned long long> in64{(const unsigned long long*)ctx->b_keys[0].p, info, xbits};
+    if (sharded_sort) {
+      if (key32) cub::DeviceSelect::If(nullptr, tmp_selk, ids, (int*)nullptr, (int*)nullptr, n, in32, st);
+      else cub::DeviceSelect::If(nullptr, tmp_selk, ids, (int*)nullptr, (int*)nullptr, n, in64, st);
+    }
+    size_t tmp_all = std::max(std::max(tmp_cost, tmp_sel), std::max(tmp_selk, tmp_sort));
+    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_all + 16)) return rc;
+    if (int rc = reserve(ctx, ctx->b_rowflag, (size_t)cells + (size_t)np + 64)) return rc;
+    if (int rc = reserve(ctx, ctx->b_halo_list, ((size_t)np + 4) * 4)) return rc;
+    if (int rc = reserve_pinned(ctx, tail_bytes + 64)) return rc;
+    unsigned char* cell_flag = (unsigned char*)ctx->b_rowflag.p;
+    unsigned char* pflag = cell_flag + cells;
+    int* list = (int*)ctx->b_halo_list.p;
     packet_cost_kernel<<<(np + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, np,
                                                          (const int*)ctx->b_cellstart.p, cost);
     CAB_LAUNCH_CHECK(ctx);
-    CAB_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->b_cubtmp.p, tmp_cost, cost, cum, np, st));
-    split_kernel<<<1, 64, 0, st>>>(cum, np, w, split);
+    CAB_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->b_cubtmp.p, tmp_all, cost, cum, np, st));
+    split_kernel<<<1, 32 * std::min(32, std::max(2, w)), 0, st>>>(cum, np, w, ctx->shard_rank, (const Packet*)ctx->b_packets.p, (const Domain*)ctx->b_domains.p, nd,
+                                   packet_base, (const int*)ctx->b_cellstart.p, split, info);
     CAB_LAUNCH_CHECK(ctx);
-    ctx->tm.kernel_launches += 2;
-    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, split, (w + 1) * 4, cudaMemcpyDeviceToHost, st));
-    CAB_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->shard_splits.assign((const int*)ctx->h_pin, (const int*)ctx->h_pin + w + 1);
-    // halo packet list for the normals pass (+ the cells whose points this rank needs)
-    int p0, p1;
-    packet_range(ctx, &p0, &p1);
-    if (int rc = reserve(ctx, ctx->b_rowflag, 2 * (size_t)cells + (size_t)np + 64)) return rc;
-    if (int rc = reserve(ctx, ctx->b_halo_list, ((size_t)np + 4) * 4)) return rc;
-    unsigned char* cell_flag = (unsigned char*)ctx->b_rowflag.p;
-    unsigned char* pflag = cell_flag + cells;
-    if (sharded_sort) need_cell = pflag + np + 32;
-    int* list = (int*)ctx->b_halo_list.p;
+    // halo packet list for the normals pass
     CAB_CUDA(ctx, cudaMemsetAsync(cell_flag, 0, (size_t)cells, st));
-    if (need_cell) CAB_CUDA(ctx, cudaMemsetAsync(need_cell, 0, (size_t)cells, st));
-    if (p1 > p0) {
-      mark_cells_kernel<<<(p1 - p0 + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, p0, p1,
-                                                              (const int*)ctx->b_cellstart.p, cell_flag);
-      CAB_LAUNCH_CHECK(ctx);
-    }
-    flag_halo_kernel<<<(np + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, np, p0, p1,
-                                                       (const int*)ctx->b_cellstart.p, cell_flag, pflag, need_cell);
+    mark_cells_kernel<<<(np + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, info,
+                                                        (const int*)ctx->b_cellstart.p, cell_flag);
     CAB_LAUNCH_CHECK(ctx);
-    size_t tmp_sel = 0;
-    thrust::counting_iterator<int> ids(0);
-    cub::DeviceSelect::Flagged(nullptr, tmp_sel, ids, pflag, list, list + np, np, st);
-    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_sel + 16)) return rc;
-    CAB_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_cubtmp.p, tmp_sel, ids, pflag, list, list + np, np, st));
-    ctx->tm.kernel_launches += 2;
-    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, list + np, 4, cudaMemcpyDeviceToHost, st));
+    flag_halo_kernel<<<(np + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, np, info,
+                                                       (const int*)ctx->b_cellstart.p, cell_flag, pflag);
+    CAB_LAUNCH_CHECK(ctx);
+    CAB_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_cubtmp.p, tmp_all, ids, pflag, list, list + np, np, st));  // count behind the list: the normals kernel reads it there
+    ctx->tm.kernel_launches += 4;
+    if (sharded_sort) {
+      // stable selection of the indices of the points in the rank's rows (flag computed from the key)
+      if (int rc = reserve(ctx, ctx->b_vals[1], (size_t)n * 4)) return rc;
+      if (int rc = reserve(ctx, ctx->b_keys[2], (size_t)n * 8)) return rc;
+      if (int rc = reserve(ctx, ctx->b_vals[2], (size_t)n * 4 + 16)) return rc;
+      if (key32) CAB_CUDA(ctx, cub::DeviceSelect::If(ctx->b_cubtmp.p, tmp_all, ids, (int*)ctx->b_vals[2].p, &info->n_selected, n, in32, st));
+      else CAB_CUDA(ctx, cub::DeviceSelect::If(ctx->b_cubtmp.p, tmp_all, ids, (int*)ctx->b_vals[2].p, &info->n_selected, n, in64, st));
+      ctx->tm.kernel_launches += 2;
+      CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_perm.p, 0xff, (size_t)n * 4, st));  // positions outside the rows: perm = -1
+    }
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, split, tail_bytes, cudaMemcpyDeviceToHost, st));
+    CAB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->h_pin + tail_bytes, list + np, 4, cudaMemcpyDeviceToHost, st));
     CAB_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->n_halo_packets = *(const int*)ctx->h_pin;
+    const int* hs = (const int*)ctx->h_pin;
+    ctx->shard_splits.assign(hs, hs + w + 1);
+    ShardInfo hi;
+    std::memcpy(&hi, hs + split_ints, sizeof(ShardInfo));
+    std::memcpy(&ctx->n_halo_packets, (const char*)ctx->h_pin + tail_bytes, 4);
+    if (sharded_sort) {
+      n_selected = hi.n_selected;
+      sel_begin = hi.sel_begin;
+      if (n_selected != hi.sel_end - hi.sel_begin)
+        return fail(ctx, CAB_ERR_STATE, "cab_build_grid: shard selection holds %d points, its rows %d", n_selected,
+                    hi.sel_end - hi.sel_begin);
+    }
   }
 
   // ---- radix sort by (row, fine x) ----------------------------------------------------
@@ -613,36 +864,10 @@ int build_grid(cab_ctx* ctx, float cell) {
                                                     (float4*)ctx->b_pos.p);
     CAB_LAUNCH_CHECK(ctx);
   } else if (sharded_sort) {
-    const Domain& dm = ctx->domains[0];
-    if (int rc = reserve(ctx, ctx->b_vals[1], (size_t)n * 4)) return rc;
-    if (int rc = reserve(ctx, ctx->b_keys[2], (size_t)n * 8)) return rc;
-    if (int rc = reserve(ctx, ctx->b_vals[2], (size_t)n * 4 + 16)) return rc;
-    if (int rc = reserve(ctx, ctx->b_substart, ncell1 * 4 * 2)) return rc;
-    int* masked = (int*)ctx->b_substart.p;
-    int* sub_start = masked + ncell1;
-    int* d_m = (int*)((char*)ctx->b_vals[2].p + (size_t)n * 4);  // number of selected points
-    masked_count_kernel<<<(unsigned)((ncell1 + 255) / 256), 256, 0, st>>>((const int*)ctx->b_cellcnt.p, need_cell, cells, masked);
-    CAB_LAUNCH_CHECK(ctx);
-    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_bytes + 16)) return rc;
-    CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_bytes, masked, sub_start, (int)ncell1, st));
-    // stable selection of the indices of the needed points (flags computed on the fly from the keys)
-    thrust::counting_iterator<int> all_points(0);
-    size_t tmp_selk = 0;
-    NeedPoint<unsigned> need32{(const unsigned*)ctx->b_keys[0].p, need_cell, xbits, dm.xshift, dm.nx, (unsigned long long)rows};
-    NeedPoint<unsigned long long> need64{(const unsigned long long*)ctx->b_keys[0].p, need_cell, xbits, dm.xshift, dm.nx,
-                                         (unsigned long long)rows};
-    if (key32) cub::DeviceSelect::If(nullptr, tmp_selk, all_points, (int*)nullptr, d_m, n, need32, st);
-    else cub::DeviceSelect::If(nullptr, tmp_selk, all_points, (int*)nullptr, d_m, n, need64, st);
-    size_t tmp_sel2 = std::max(tmp_selk, tmp_sort);
-    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_sel2 + 16)) return rc;
-    if (key32) CAB_CUDA(ctx, cub::DeviceSelect::If(ctx->b_cubtmp.p, tmp_sel2, all_points, (int*)ctx->b_vals[2].p, d_m, n, need32, st));
-    else CAB_CUDA(ctx, cub::DeviceSelect::If(ctx->b_cubtmp.p, tmp_sel2, all_points, (int*)ctx->b_vals[2].p, d_m, n, need64, st));
-    ctx->tm.kernel_launches += 3;
-    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, d_m, 4, cudaMemcpyDeviceToHost, st));
-    CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_perm.p, 0xff, (size_t)n * 4, st));  // unneeded positions: perm = -1
-    CAB_CUDA(ctx, cudaStreamSynchronize(st));
-    const int m = *(const int*)ctx->h_pin;
+    const int m = n_selected;
+    if (ctx->n_packets == 0) CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_perm.p, 0xff, (size_t)n * 4, st));
     if (m > 0) {
+      size_t tmp_have = ctx->b_cubtmp.cap;
       if (key32)
         gather_keys_kernel<unsigned><<<(m + 255) / 256, 256, 0, st>>>((const unsigned*)ctx->b_keys[0].p, (const int*)ctx->b_vals[2].p, m,
                                                                      (unsigned*)ctx->b_keys[2].p);
@@ -651,22 +876,16 @@ int build_grid(cab_ctx* ctx, float cell) {
             (const unsigned long long*)ctx->b_keys[0].p, (const int*)ctx->b_vals[2].p, m, (unsigned long long*)ctx->b_keys[2].p);
       CAB_LAUNCH_CHECK(ctx);
       if (key32)
-        CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_sel2, (const unsigned*)ctx->b_keys[2].p,
+        CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_have, (const unsigned*)ctx->b_keys[2].p,
                                                       (unsigned*)ctx->b_keys[1].p, (const int*)ctx->b_vals[2].p,
                                                       (int*)ctx->b_vals[1].p, m, 0, end_bit, st));
       else
-        CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_sel2, (const unsigned long long*)ctx->b_keys[2].p,
+        CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_have, (const unsigned long long*)ctx->b_keys[2].p,
                                                       (unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[2].p,
                                                       (int*)ctx->b_vals[1].p, m, 0, end_bit, st));
       ctx->tm.kernel_launches += 1 + (end_bit + 7) / 8;
-      if (key32)
-        scatter_sorted_kernel<unsigned><<<(m + 255) / 256, 256, 0, st>>>(
-            ctx->xyz_in, ctx->stride, m, (const unsigned*)ctx->b_keys[1].p, (const int*)ctx->b_vals[1].p, xbits, dm.xshift, dm.nx,
-            (unsigned long long)rows, (const int*)ctx->b_cellstart.p, sub_start, (float4*)ctx->b_pos.p, (int*)ctx->b_perm.p);
-      else
-        scatter_sorted_kernel<unsigned long long><<<(m + 255) / 256, 256, 0, st>>>(
-            ctx->xyz_in, ctx->stride, m, (const unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[1].p, xbits, dm.xshift,
-            dm.nx, (unsigned long long)rows, (const int*)ctx->b_cellstart.p, sub_start, (float4*)ctx->b_pos.p, (int*)ctx->b_perm.p);
+      place_sorted_kernel<<<(m + 255) / 256, 256, 0, st>>>(ctx->xyz_in, ctx->stride, m, sel_begin, (const int*)ctx->b_vals[1].p,
+                                                          (float4*)ctx->b_pos.p, (int*)ctx->b_perm.p);
       CAB_LAUNCH_CHECK(ctx);
     }
     ctx->tm.n_sorted = m;

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) voxel_rsd_kernel(const VRsdArgs a) {
   const float4 q = a.cent[v];
   const int d = (int)(a.ukeys[v] >> 32);
   const Domain dm = g.domains[d];
-  const int cy = cell_coord(q.y, dm.oy, g.inv_cell, dm.ny), cz = cell_coord(q.z, dm.oz, g.inv_cell, dm.nz);
+  int cy, cz;
+  row_cells(dm, q.y, q.z, g.inv_cell, cy, cz);
   const int cx = xfine_coord(q.x, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift;
   const int cxlo = max(cx - 1, 0), cxhi = min(cx + 1, dm.nx - 1);
   int rb = 0, re = 0;

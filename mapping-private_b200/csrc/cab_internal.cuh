@@ -25,7 +25,8 @@ struct Domain {
   float ox, oy, oz;      // grid origin
   int nx, ny, nz;        // cells per axis
   int xshift;            // x_fine >> xshift == cell x
-  int pad;
+  int swap_yz;           // 1: the grid's y slot holds the physical z axis and its z slot the physical y axis
+                         // (the slowest-varying slot gets the longer of the two extents: thinner shard halos)
   int64_t row_base;      // first row id of this domain (row = row_base + cz*ny + cy)
   int64_t cell_base;     // first cell id (cell = cell_base + (cz*ny+cy)*nx + cx)
 };
@@ -61,6 +62,11 @@ __device__ __forceinline__ float d2_rule(float px, float py, float pz, float qx,
 __device__ __forceinline__ int cell_coord(float v, float origin, float inv_cell, int n) {
   int c = (int)floorf(__fmul_rn(__fsub_rn(v, origin), inv_cell));
   return min(max(c, 0), n - 1);
+}
+// Row coordinates (cy, cz) of a point: which physical axis fills which slot is the domain's choice.
+__device__ __forceinline__ void row_cells(const Domain& dm, float y, float z, float inv_cell, int& cy, int& cz) {
+  cy = cell_coord(dm.swap_yz ? z : y, dm.oy, inv_cell, dm.ny);
+  cz = cell_coord(dm.swap_yz ? y : z, dm.oz, inv_cell, dm.nz);
 }
 // Fine x coordinate (sub-cell resolution 2^-xshift of a cell).
 __device__ __forceinline__ int xfine_coord(float x, float ox, float inv_cell, int nx, int xshift) {

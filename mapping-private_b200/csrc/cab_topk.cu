@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(128) neighbors_debug_kernel(const DbgArgs a) {
       d = lo;
     }
     const Domain dm = a.g.domains[d];
-    const int cy = cell_coord(qy, dm.oy, a.g.inv_cell, dm.ny), cz = cell_coord(qz, dm.oz, a.g.inv_cell, dm.nz);
+    int cy, cz;
+    row_cells(dm, qy, qz, a.g.inv_cell, cy, cz);
     const int cx = xfine_coord(qx, dm.ox, a.g.inv_cell, dm.nx, dm.xshift) >> dm.xshift;
     const int cxlo = max(cx - 1, 0), cxhi = min(cx + 1, dm.nx - 1);
     float td2 = INFINITY;
