@@ -55,6 +55,7 @@ typedef struct cab_timings {
   float knn_ms;       /* last cab_knn_mean_distance / cab_statistical_outliers: all grid rounds */
   int32_t knn_rounds; /* grids built by it (the cell edge doubles until every query has its k neighbours) */
   float pfh_ms;       /* last cab_pfh: pair-feature, averaging and finishing kernels */
+  float cluster_ms;   /* last cab_euclidean_clusters: union, statistics and labelling kernels (without the grid build) */
 } cab_timings;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
@@ -207,6 +208,23 @@ int cab_svm_predict_grsd(cab_ctx* ctx, float* point_class);
 int cab_knn_mean_distance(cab_ctx* ctx, int32_t k, float cell_hint, double* avg);
 int64_t cab_statistical_outliers(cab_ctx* ctx, int32_t k, double alpha, float cell_hint, uint8_t* keep,
                                  double* avg, double* mean_out, double* stddev_out);
+
+/* ---- Euclidean clustering (next row: the segmentation step that produces GRSD's object clusters) ----
+ * Replaces cloud_geometry::nearest::extractEuclideanClusters(points, indices, tolerance, clusters, -1, -1, -1, -1,
+ * min_pts) [point_cloud_mapping, external] as called at cloud_tools/src/table_object_detector_passive.cpp:293,567
+ * and cloud_tools/src/table_object_detector_sr.cpp:370 (object_cluster_dist_tolerance 0.05, object_cluster_min_pts 30,
+ * :181-182), on the uploaded cloud (the caller uploads the `indices` subset): connected components of the graph
+ * "d2 <= tolerance^2" (the documented d2 rule), numbered in the order the reference's seed loop finds them (by
+ * smallest index); components with fewer than min_pts (or, if max_pts > 0, more than max_pts) points are dropped.
+ * The variant with a normal-angle test (nx_idx >= 0) is not implemented.  Builds its own grid (cell = tolerance),
+ * clusters the whole cloud on this GPU whatever cab_set_shard says.
+ * labels[n] (input order, may be NULL): cluster id, -1 for dropped components and non-finite points.
+ * Returns the number of clusters or < 0. */
+int64_t cab_euclidean_clusters(cab_ctx* ctx, double tolerance, int32_t min_pts, int32_t max_pts, int32_t* labels);
+/* Host helper: labels -> the reference's vector<vector<int>> as CSR.  offsets[n_clusters + 1]; indices (may be NULL)
+ * holds every cluster's point indices in ascending order, cluster after cluster -- gather the points with it and hand
+ * them, with offsets, to cab_upload_clusters / cab_grsd_batch.  Returns the number of labelled points or < 0. */
+int64_t cab_cluster_csr(const int32_t* labels, int64_t n, int32_t n_clusters, int32_t* offsets, int32_t* indices);
 
 /* ---- point feature histograms (next row: cloud_algos/PointFeatureHistogram) ----------------
  * Replaces the hot loops of PointFeatureHistogram::process (cloud_algos/src/pfh.cpp:181-350; pair features

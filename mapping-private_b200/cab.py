@@ -26,7 +26,7 @@ BUF_POS_SORTED, BUF_NRM_SORTED, BUF_RSD_SORTED, BUF_PERM = 0, 1, 2, 3
 EXPORTS = [
     "cab_create", "cab_destroy", "cab_last_error", "cab_upload_cloud", "cab_upload_clusters",
     "cab_set_cloud_device", "cab_build_grid", "cab_set_shard", "cab_shard_range", "cab_normals",
-    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd", "cab_knn_mean_distance", "cab_statistical_outliers", "cab_pfh",
+    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd", "cab_knn_mean_distance", "cab_statistical_outliers", "cab_euclidean_clusters", "cab_cluster_csr", "cab_pfh",
     "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_profile", "cab_version",
 ]
 
@@ -45,7 +45,7 @@ class Timings(C.Structure):
         ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
         ("n_points", C.c_int64), ("n_valid", C.c_int64), ("n_packets", C.c_int64), ("n_rows", C.c_int64),
         ("n_cells", C.c_int64), ("neighbour_sum", C.c_int64), ("candidate_sum", C.c_int64),
-        ("kernel_launches", C.c_int64), ("n_sorted", C.c_int64), ("knn_ms", C.c_float), ("knn_rounds", C.c_int32), ("pfh_ms", C.c_float),
+        ("kernel_launches", C.c_int64), ("n_sorted", C.c_int64), ("knn_ms", C.c_float), ("knn_rounds", C.c_int32), ("pfh_ms", C.c_float), ("cluster_ms", C.c_float),
     ]
 
     def as_dict(self):
@@ -73,6 +73,8 @@ def lib():
         L.cab_grsd_voxels.restype = C.c_int64
         L.cab_grsd_signatures.restype = C.c_int64
         L.cab_statistical_outliers.restype = C.c_int64
+        L.cab_euclidean_clusters.restype = C.c_int64
+        L.cab_cluster_csr.restype = C.c_int64
         L.cab_device_ptr.restype = C.c_void_p
         L.cab_device_ptr.argtypes = [C.c_void_p, C.c_int32]
         L.cab_stream.restype = C.c_void_p
@@ -285,6 +287,26 @@ class Context:
                                                             avg.ctypes.data_as(C.POINTER(C.c_double)), C.byref(mean), C.byref(std)),
                            "cab_statistical_outliers")
         return dict(keep=keep.astype(bool), avg=avg, mean=mean.value, stddev=std.value, kept=int(kept))
+
+    # ---- Euclidean clustering ------------------------------------------------------------
+    def euclidean_clusters(self, tolerance: float, min_pts: int = 1, max_pts: int = 0):
+        """Connected components of "d2 <= tolerance^2" on the uploaded cloud.  Returns (labels int32 (n,), n_clusters):
+        clusters numbered by their smallest index, -1 = dropped or non-finite."""
+        labels = np.full(self.n, -1, np.int32)
+        nc = self._check(self._L.cab_euclidean_clusters(self._h, C.c_double(tolerance), C.c_int32(min_pts), C.c_int32(max_pts),
+                                                        labels.ctypes.data_as(C.POINTER(C.c_int32))), "cab_euclidean_clusters")
+        return labels, int(nc)
+
+    def cluster_csr(self, labels: np.ndarray, n_clusters: int):
+        """labels -> (offsets int32 (n_clusters + 1,), indices int32): every cluster's point indices, ascending."""
+        labels = np.ascontiguousarray(labels, np.int32)
+        offsets = np.zeros(n_clusters + 1, np.int32)
+        indices = np.zeros(max(int((labels >= 0).sum()), 1), np.int32)
+        total = self._L.cab_cluster_csr(labels.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(labels.shape[0]), C.c_int32(n_clusters),
+                                        offsets.ctypes.data_as(C.POINTER(C.c_int32)), indices.ctypes.data_as(C.POINTER(C.c_int32)))
+        if total < 0:
+            raise CabError(f"cab_cluster_csr failed ({total})")
+        return offsets, indices[:total]
 
     # ---- SVM ---------------------------------------------------------------------------
     def svm_set_model(self, model, scale=None):

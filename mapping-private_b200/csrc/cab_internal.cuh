@@ -117,7 +117,7 @@ struct cab_ctx {
   // device arena (grow-only)
   cab::DevBuf b_xyz, b_domoff, b_domid, b_bounds, b_domains, b_keys[3], b_vals[3], b_cubtmp, b_pos,
       b_perm, b_cellcnt, b_cellstart, b_rowpk, b_packets, b_nrm, b_nrm_in, b_rsd, b_kcount, b_stats,
-      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost, b_halo_list, b_rowflag, b_substart, b_thr_flag, b_knn_avg, b_knn_done, b_pfh[3];
+      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost, b_halo_list, b_rowflag, b_substart, b_thr_flag, b_knn_avg, b_knn_done, b_pfh[3], b_cluster;
   // pinned staging
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;
@@ -166,6 +166,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
 int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done = nullptr);  // max_nn truncation thresholds
 int run_knn_mean(cab_ctx* ctx, int k, float cell_hint, double* avg);  // cab_knn.cu
 int run_pfh(cab_ctx* ctx, double radius, int max_nn, int quantum, int flags, float* out);  // cab_pfh.cu
+int64_t run_euclidean_clusters(cab_ctx* ctx, double tolerance, int min_pts, int max_pts, int32_t* labels);  // cab_cluster.cu
 int64_t run_neighbors_debug(cab_ctx* ctx, float r, int max_nn, int64_t q0, int64_t q1, int64_t* offsets,
                             int32_t* idx, float* d2, int64_t cap);
 int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_t* hist21);

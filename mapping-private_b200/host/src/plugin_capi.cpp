@@ -14,6 +14,7 @@
 #include <cloud_algos/noise_removal.h>
 #include <cloud_algos/pfh.h>
 #include <cloud_algos/pcd_io.h>
+#include <point_cloud_mapping/geometry/nearest.h>
 
 using namespace cloud_algos;
 
@@ -190,6 +191,35 @@ int capi_write_feature(const char* name, const float* data, int hist_num, int di
   std::vector<std::vector<float> > f(hist_num, std::vector<float>(dim));
   for (int h = 0; h < hist_num; ++h) f[h].assign(data + (size_t)h * dim, data + (size_t)(h + 1) * dim);
   return writeFeature(name, f, remove_0 != 0) ? 0 : -1;
+}
+
+// cloud_geometry::nearest::extractEuclideanClusters through its reference signature; the clusters come back as
+// cluster_of[k] for the k-th entry of indices (-1: in no cluster) plus the flattened members in cluster order.
+// Returns the number of clusters, -1 if the call reported an error.
+int capi_extract_euclidean_clusters(const float* xyz, int n, const int* indices, int n_idx, double tolerance, int nx_idx,
+                                    unsigned min_pts, int* cluster_of, int* flat_members) {
+  sensor_msgs::PointCloud cloud;
+  cloud.points.resize(n);
+  for (int i = 0; i < n; ++i) {
+    cloud.points[i].x = xyz[3 * i];
+    cloud.points[i].y = xyz[3 * i + 1];
+    cloud.points[i].z = xyz[3 * i + 2];
+  }
+  std::vector<int> idx(indices, indices + n_idx);
+  std::vector<std::vector<int> > clusters;
+  cloud_geometry::nearest::extractEuclideanClusters(cloud, idx, tolerance, clusters, nx_idx, nx_idx < 0 ? -1 : nx_idx + 1,
+                                                    nx_idx < 0 ? -1 : nx_idx + 2, 0.0, min_pts);
+  if (!cloud_geometry::nearest::lastEuclideanClusterError().empty()) return -1;
+  std::vector<int> where(n, -1);
+  for (int k = 0; k < n_idx; ++k) where[idx[k]] = k;
+  for (int k = 0; k < n_idx; ++k) cluster_of[k] = -1;
+  int w = 0;
+  for (size_t c = 0; c < clusters.size(); ++c)
+    for (int i : clusters[c]) {
+      cluster_of[where[i]] = (int)c;
+      flat_members[w++] = i;
+    }
+  return (int)clusters.size();
 }
 
 int capi_list_requires(void* hv, char* buf, int cap) {

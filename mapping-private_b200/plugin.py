@@ -53,8 +53,25 @@ def lib():
         L.capi_list_requires.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.capi_pcd_read.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.capi_write_feature.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.capi_extract_euclidean_clusters.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_uint,
+                                                      C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
+
+
+def extract_euclidean_clusters(xyz: np.ndarray, indices: np.ndarray, tolerance: float, min_pts: int = 1, nx_idx: int = -1):
+    """cloud_geometry::nearest::extractEuclideanClusters (host/include/point_cloud_mapping/geometry/nearest.h) through its
+    reference signature.  Returns the clusters as a list of index arrays, or None if the call reported an error."""
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    indices = np.ascontiguousarray(indices, np.int32)
+    cluster_of = np.full(max(len(indices), 1), -1, np.int32)
+    flat = np.zeros(max(len(indices), 1), np.int32)
+    nc = lib().capi_extract_euclidean_clusters(xyz.ctypes.data, xyz.shape[0], indices.ctypes.data, len(indices), float(tolerance),
+                                               int(nx_idx), int(min_pts), cluster_of.ctypes.data, flat.ctypes.data)
+    if nc < 0:
+        return None
+    sizes = np.bincount(cluster_of[cluster_of >= 0], minlength=nc)
+    return np.split(flat[: sizes.sum()], np.cumsum(sizes)[:-1]) if nc else []
 
 
 def pcd_read(path: str):

@@ -1123,6 +1123,38 @@ int orc_knn_mean_distance(const float* xyz, int n, int k, double* avg, int nthre
   return 0;
 }
 
+// cloud_geometry::nearest::extractEuclideanClusters [EXTERNAL] as called at
+// cloud_tools/src/table_object_detector_passive.cpp:293,567 (nx_idx = -1: no normal test).
+int orc_euclidean_clusters(const float* xyz, int n, double tolerance, int min_pts, int max_pts, int32_t* labels) {
+  const float tf = (float)tolerance, r2 = tf * tf;
+  CellGrid grid(xyz, n, tolerance);
+  std::vector<char> processed((size_t)std::max(n, 1), 0);
+  std::vector<int32_t> seed_queue;
+  std::vector<Nb> nbs;
+  for (int i = 0; i < n; ++i) labels[i] = -1;
+  int n_clusters = 0;
+  for (int i = 0; i < n; ++i) {  // seeds in index order
+    if (processed[i] || !finite3(xyz + 3 * (size_t)i)) continue;
+    seed_queue.clear();
+    seed_queue.push_back(i);
+    processed[i] = 1;
+    for (size_t sq = 0; sq < seed_queue.size(); ++sq) {
+      grid.query(xyz + 3 * (size_t)seed_queue[sq], r2, nbs);
+      for (const Nb& nb : nbs) {
+        if (processed[nb.idx]) continue;
+        processed[nb.idx] = 1;
+        seed_queue.push_back(nb.idx);
+      }
+    }
+    const int size = (int)seed_queue.size();
+    if (size >= min_pts && (max_pts <= 0 || size <= max_pts)) {
+      for (int32_t j : seed_queue) labels[j] = n_clusters;
+      ++n_clusters;
+    }
+  }
+  return n_clusters;
+}
+
 int64_t orc_noise_filter(const double* avg, int n, double alpha, uint8_t* keep, double* mean_out, double* stddev_out) {
   // noise_removal.cpp:113-121 over the finite points
   double sum = 0, sq_sum = 0;

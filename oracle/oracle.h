@@ -201,6 +201,17 @@ int orc_pfh(const float* xyz, const float* normals, int normal_stride, int n, do
 int orc_pfh_pair(const float* ps, const float* ns, const float* pt, const float* nt, float d2, double max_dist,
                  int check_flip, int abs_angles, double* f);
 
+/* ---- Euclidean clustering (the step that produces the segmented object clusters GRSD runs on) --------
+ * cloud_geometry::nearest::extractEuclideanClusters(points, indices, tolerance, clusters, -1, -1, -1, -1, min_pts)
+ * as called at cloud_tools/src/table_object_detector_passive.cpp:293,567 and table_object_detector_sr.cpp:370.
+ * The function itself lives in point_cloud_mapping [EXTERNAL, absent]; its published algorithm is restated:
+ * for i ascending over the unprocessed points: breadth-first growth from i through radiusSearch(tolerance)
+ * (neighbour <=> d2 <= tolerance^2, this repo's epsilon rule), every reached point marked processed; the
+ * region is kept iff it has >= min_pts points (and <= max_pts if max_pts > 0); kept regions are emitted in the
+ * order of their seeds (= their smallest index) with their indices sorted ascending.
+ * labels[n]: cluster id in that order, -1 for dropped regions and non-finite points.  Returns the cluster count. */
+int orc_euclidean_clusters(const float* xyz, int n, double tolerance, int min_pts, int max_pts, int32_t* labels);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -304,6 +304,17 @@ def knn_mean_distance(xyz, k, nthreads=0):
     return avg
 
 
+def euclidean_clusters(xyz, tolerance, min_pts=1, max_pts=0):
+    """extractEuclideanClusters without the normal test: (labels int32 (n,), n_clusters); clusters are numbered in
+    the order of their smallest index, -1 = dropped (too small / too large) or non-finite."""
+    L = lib()
+    p = _xyz(xyz)
+    labels = np.full(p.shape[0], -1, np.int32)
+    nc = L.orc_euclidean_clusters(_ptr(p, C.c_float), p.shape[0], C.c_double(tolerance), int(min_pts), int(max_pts),
+                                  _ptr(labels, C.c_int32))
+    return labels, int(nc)
+
+
 def noise_filter(avg, alpha):
     """Returns (keep bool (n,), mean, stddev)."""
     L = lib()
