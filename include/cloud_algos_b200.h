@@ -209,6 +209,15 @@ int cab_knn_mean_distance(cab_ctx* ctx, int32_t k, float cell_hint, double* avg)
 int64_t cab_statistical_outliers(cab_ctx* ctx, int32_t k, double alpha, float cell_hint, uint8_t* keep,
                                  double* avg, double* mean_out, double* stddev_out);
 
+/* k-nearest-neighbour normals: the other normal estimation of the reference, nearestKSearch (i, k_) +
+ * cloud_geometry::nearest::computePointNormal + flipNormalTowardsViewpoint [point_cloud_mapping, external] as in
+ * TableObjectDetector::estimatePointNormals (cloud_tools/src/table_object_detector_passive.cpp:668-714, k_ = 10 at :169)
+ * and CylinderEstimation::estimatePointNormals (cloud_algos/src/cylinder_fit_algo.cpp:138-203).  Same PCA, curvature and
+ * flip as cab_normals over the k nearest points (the query included, ties by index) instead of a radius.  cell_hint as in
+ * cab_knn_mean_distance.  nxyz_curv: n x 4 floats in input order (NaN for non-finite points), may be NULL.  Errors:
+ * k < 3, fewer than k finite points.  The result is not kept on the device: cab_set_normals feeds it to cab_rsd. */
+int cab_normals_knn(cab_ctx* ctx, int32_t k, const float vp[3], float cell_hint, float* nxyz_curv);
+
 /* ---- Euclidean clustering (next row: the segmentation step that produces GRSD's object clusters) ----
  * Replaces cloud_geometry::nearest::extractEuclideanClusters(points, indices, tolerance, clusters, -1, -1, -1, -1,
  * min_pts) [point_cloud_mapping, external] as called at cloud_tools/src/table_object_detector_passive.cpp:293,567

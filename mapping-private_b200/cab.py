@@ -26,7 +26,7 @@ BUF_POS_SORTED, BUF_NRM_SORTED, BUF_RSD_SORTED, BUF_PERM = 0, 1, 2, 3
 EXPORTS = [
     "cab_create", "cab_destroy", "cab_last_error", "cab_upload_cloud", "cab_upload_clusters",
     "cab_set_cloud_device", "cab_build_grid", "cab_set_shard", "cab_shard_range", "cab_normals",
-    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd", "cab_knn_mean_distance", "cab_statistical_outliers", "cab_euclidean_clusters", "cab_cluster_csr", "cab_pfh",
+    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd", "cab_knn_mean_distance", "cab_normals_knn", "cab_statistical_outliers", "cab_euclidean_clusters", "cab_cluster_csr", "cab_pfh",
     "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_profile", "cab_version",
 ]
 
@@ -276,6 +276,13 @@ class Context:
         self._check(self._L.cab_knn_mean_distance(self._h, C.c_int32(k), C.c_float(cell_hint),
                                                   avg.ctypes.data_as(C.POINTER(C.c_double))), "cab_knn_mean_distance")
         return avg
+
+    def normals_knn(self, k: int, vp=(0.0, 0.0, 0.0), cell_hint: float = 0.0):
+        """k-nearest-neighbour normals (n, 4) in input order: nx, ny, nz, curvature."""
+        out = np.zeros((self.n, 4), np.float32)
+        v = (C.c_float * 3)(*vp)
+        self._check(self._L.cab_normals_knn(self._h, C.c_int32(k), v, C.c_float(cell_hint), _fp(out)), "cab_normals_knn")
+        return out
 
     def statistical_outliers(self, k: int = 10, alpha: float = 3.0, cell_hint: float = 0.0):
         """Returns dict(keep bool (n,), avg float64 (n,), mean, stddev, kept)."""

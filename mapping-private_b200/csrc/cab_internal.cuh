@@ -161,10 +161,11 @@ void read_stats(cab_ctx* ctx);  // sums the kStatSlots counters staged in ctx->h
 // stage entry points (each enqueues on ctx->stream; callers synchronise)
 int compute_bounds(cab_ctx* ctx);
 int build_grid(cab_ctx* ctx, float cell);
-int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3]);
+int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsigned char* done = nullptr);
 int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, int flags);
 int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done = nullptr);  // max_nn truncation thresholds
 int run_knn_mean(cab_ctx* ctx, int k, float cell_hint, double* avg);  // cab_knn.cu
+int run_normals_knn(cab_ctx* ctx, int k, const float vp[3], float cell_hint, float* nxyz_curv);  // cab_knn.cu
 int run_pfh(cab_ctx* ctx, double radius, int max_nn, int quantum, int flags, float* out);  // cab_pfh.cu
 int64_t run_euclidean_clusters(cab_ctx* ctx, double tolerance, int min_pts, int max_pts, int32_t* labels);  // cab_cluster.cu
 int64_t run_neighbors_debug(cab_ctx* ctx, float r, int max_nn, int64_t q0, int64_t q1, int64_t* offsets,

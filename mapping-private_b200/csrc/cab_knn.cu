@@ -75,7 +75,43 @@ __global__ void knn_init_kernel(const float* __restrict__ xyz, int stride, int n
   if (!fin) atomicAdd(n_done, 1u);
 }
 
+// k-NN normals, one round: queries that found their k neighbours inside this round's cell take their result
+__global__ void __launch_bounds__(256) knn_normals_collect_kernel(const float4* __restrict__ nrm, const int* __restrict__ kcount,
+                                                                  const int* __restrict__ perm, int n_valid, int k,
+                                                                  float4* __restrict__ out, unsigned char* __restrict__ done,
+                                                                  unsigned int* __restrict__ n_done) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_valid) return;
+  const int me = perm[s];
+  if (done[me] || kcount[s] != k) return;  // (packets without open queries were skipped: their slots are stale)
+  out[me] = nrm[s];
+  done[me] = 1;
+  atomicAdd(n_done, 1u);
+}
+
 }  // namespace
+
+// Edge of the first search grid of a k-NN query: the caller's hint, or an estimate from the cloud's extent.
+static int first_knn_cell(cab_ctx* ctx, int k, float cell_hint, const char* who, float* out) {
+  float cell = cell_hint;
+  if (!(cell > 0.f)) {
+    if (int rc = compute_bounds(ctx)) return rc;
+    double ext[3] = {0, 0, 0};
+    if (ctx->dom_count.empty() || ctx->dom_count[0] == 0) return fail(ctx, CAB_ERR_ARG, "%s: no finite points", who);
+    for (int a = 0; a < 3; ++a) {
+      ext[a] = std::max(1e-6, (double)ctx->dom_bounds[3 + a] - (double)ctx->dom_bounds[a]);
+    }
+    const double nv = (double)ctx->dom_count[0];
+    // a surface sampled with nv points inside the box has a spacing of about sqrt(largest face / nv) (an
+    // under-estimate for volumetric clouds, which only costs doubling rounds); k points need a disc of
+    // about sqrt(k / pi) spacings
+    const double face = std::max(ext[0] * ext[1], std::max(ext[0] * ext[2], ext[1] * ext[2]));
+    const double spacing = std::sqrt(face / nv);
+    cell = (float)(spacing * std::sqrt((double)k / M_PI) * 1.5);
+  }
+  *out = cell;
+  return CAB_OK;
+}
 
 int run_knn_mean(cab_ctx* ctx, int k, float cell_hint, double* avg_host) {
   if (!ctx->have_cloud) return fail(ctx, CAB_ERR_STATE, "cab_knn_mean_distance: no cloud uploaded");
@@ -93,23 +129,8 @@ int run_knn_mean(cab_ctx* ctx, int k, float cell_hint, double* avg_host) {
     ~Restore() { c->shard_rank = r; c->shard_world = w; }
   } restore{ctx, saved_rank, saved_world};
 
-  // first grid: from the hint, or calibrated on a coarse grid (points per occupied cell)
-  float cell = cell_hint;
-  if (!(cell > 0.f)) {
-    if (int rc = compute_bounds(ctx)) return rc;
-    double ext[3] = {0, 0, 0};
-    if (ctx->dom_count.empty() || ctx->dom_count[0] == 0) return fail(ctx, CAB_ERR_ARG, "cab_knn_mean_distance: no finite points");
-    for (int a = 0; a < 3; ++a) {
-      ext[a] = std::max(1e-6, (double)ctx->dom_bounds[3 + a] - (double)ctx->dom_bounds[a]);
-    }
-    const double nv = (double)ctx->dom_count[0];
-    // a surface sampled with nv points inside the box has a spacing of about sqrt(largest face / nv) (an
-    // under-estimate for volumetric clouds, which only costs doubling rounds); k points need a disc of
-    // about sqrt(k / pi) spacings
-    const double face = std::max(ext[0] * ext[1], std::max(ext[0] * ext[2], ext[1] * ext[2]));
-    const double spacing = std::sqrt(face / nv);
-    cell = (float)(spacing * std::sqrt((double)k / M_PI) * 1.5);
-  }
+  float cell = 0.f;
+  if (int rc = first_knn_cell(ctx, k, cell_hint, "cab_knn_mean_distance", &cell)) return rc;
   if ((int64_t)ctx->n < k) return fail(ctx, CAB_ERR_ARG, "cab_knn_mean_distance: %d nearest neighbors requested, but only %lld points in total", k, (long long)ctx->n);
 
   if (int rc = reserve(ctx, ctx->b_knn_avg, (size_t)n * sizeof(double))) return rc;
@@ -162,6 +183,72 @@ int run_knn_mean(cab_ctx* ctx, int k, float cell_hint, double* avg_host) {
   return CAB_OK;
 }
 
+// k-nearest-neighbour normals.  The reference estimates them with nearestKSearch(i, k_) + computePointNormal +
+// flipNormalTowardsViewpoint (cloud_tools/src/table_object_detector_passive.cpp:668-714, k_ = 10 at :169;
+// cloud_algos/src/cylinder_fit_algo.cpp:138-203): the PCA of cab_normals over the k nearest points (the query
+// included, ties by index).  Same rounds as the k-NN mean distance: a query is answered on the first grid whose
+// cell holds k points within one edge of it.
+int run_normals_knn(cab_ctx* ctx, int k, const float vp[3], float cell_hint, float* out_host) {
+  if (!ctx->have_cloud) return fail(ctx, CAB_ERR_STATE, "cab_normals_knn: no cloud uploaded");
+  if (k < 3) return fail(ctx, CAB_ERR_ARG, "cab_normals_knn: a plane needs at least 3 points, k = %d", k);
+  if (ctx->n_domains != 1) return fail(ctx, CAB_ERR_ARG, "cab_normals_knn: one cloud at a time");
+  const int n = (int)ctx->n;
+  cudaStream_t st = ctx->stream;
+  if (n < k) return fail(ctx, CAB_ERR_ARG, "cab_normals_knn: %d nearest neighbors requested, but only %d points in total", k, n);
+  const int saved_rank = ctx->shard_rank, saved_world = ctx->shard_world;
+  ctx->shard_rank = 0;
+  ctx->shard_world = 1;
+  struct Restore {
+    cab_ctx* c;
+    int r, w;
+    ~Restore() { c->shard_rank = r; c->shard_world = w; }
+  } restore{ctx, saved_rank, saved_world};
+  float cell = 0.f;
+  if (int rc = first_knn_cell(ctx, k, cell_hint, "cab_normals_knn", &cell)) return rc;
+
+  if (int rc = reserve(ctx, ctx->b_knn_avg, (size_t)n * sizeof(double))) return rc;
+  if (int rc = reserve(ctx, ctx->b_knn_done, (size_t)n + 64)) return rc;
+  if (int rc = reserve(ctx, ctx->b_out4, (size_t)n * sizeof(float4))) return rc;
+  unsigned char* done = (unsigned char*)ctx->b_knn_done.p;
+  unsigned int* n_done = (unsigned int*)(done + (((size_t)n + 15) & ~(size_t)15));
+  CAB_CUDA(ctx, cudaMemsetAsync(n_done, 0, 4, st));
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_out4.p, 0xff, (size_t)n * sizeof(float4), st));  // NaN until resolved
+  knn_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, (double*)ctx->b_knn_avg.p, done, n_done);
+  CAB_LAUNCH_CHECK(ctx);
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+  int rounds = 0;
+  float kernels_ms = 0.f;
+  for (;; ++rounds) {
+    if (rounds > 60) return fail(ctx, CAB_ERR_STATE, "cab_normals_knn: did not converge");
+    int rc = build_grid(ctx, cell);
+    if (rc == CAB_ERR_OOM) {
+      cell *= 2.f;
+      continue;
+    }
+    if (rc) return rc;
+    if (ctx->n_valid < k)
+      return fail(ctx, CAB_ERR_ARG, "cab_normals_knn: %d nearest neighbors requested, but only %d finite points", k, ctx->n_valid);
+    if (int rc2 = run_normals(ctx, cell, k, vp, done)) return rc2;
+    kernels_ms += ctx->tm.normals_ms;
+    knn_normals_collect_kernel<<<(ctx->n_valid + 255) / 256, 256, 0, st>>>((const float4*)ctx->b_nrm.p, (const int*)ctx->b_kcount.p,
+                                                                         (const int*)ctx->b_perm.p, ctx->n_valid, k,
+                                                                         (float4*)ctx->b_out4.p, done, n_done);
+    CAB_LAUNCH_CHECK(ctx);
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, n_done, 4, cudaMemcpyDeviceToHost, st));
+    CAB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (*(const unsigned int*)ctx->h_pin >= (unsigned)n) break;
+    cell *= 2.f;
+  }
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+  if (out_host) CAB_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->b_out4.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.knn_ms, ctx->ev[4], ctx->ev[5]));
+  ctx->tm.normals_ms = kernels_ms;
+  ctx->tm.knn_rounds = rounds + 1;
+  ctx->have_normals = false;  // b_nrm holds the last round only; cab_set_normals puts k-NN normals in place for RSD
+  return CAB_OK;
+}
+
 }  // namespace cab
 
 using namespace cab;
@@ -172,6 +259,12 @@ int cab_knn_mean_distance(cab_ctx* ctx, int32_t k, float cell_hint, double* avg)
   if (!ctx) return CAB_ERR_ARG;
   CAB_CUDA(ctx, cudaSetDevice(ctx->device));
   return run_knn_mean(ctx, k, cell_hint, avg);
+}
+
+int cab_normals_knn(cab_ctx* ctx, int32_t k, const float vp[3], float cell_hint, float* nxyz_curv) {
+  if (!ctx) return CAB_ERR_ARG;
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return run_normals_knn(ctx, k, vp, cell_hint, nxyz_curv);
 }
 
 int64_t cab_statistical_outliers(cab_ctx* ctx, int32_t k, double alpha, float cell_hint, uint8_t* keep, double* avg,

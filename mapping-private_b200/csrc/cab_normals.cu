@@ -60,6 +60,7 @@ struct NormalsArgs {
   int* kcount;              // sorted order
   const float* thr_d2;      // optional max_nn thresholds (sorted order), may be null
   const int* thr_idx;
+  const unsigned char* done;  // optional (input order): packets whose queries are all done are skipped (k-NN rounds)
   unsigned long long* stats;  // kStatSlots x {neighbour sum, candidate sum}
 };
 
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
   const int pid = a.list ? a.list[wi] : a.p0 + wi;
   ChunkTile* tile = &tiles[warp];
   const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
+  if (a.done && !__any_sync(kFull, pc.active && !a.done[g.perm[pc.qi]])) continue;
   const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
   const float r2 = a.r2;
   using Acc = typename std::conditional<kExact, double, float>::type;
@@ -228,7 +230,7 @@ __global__ void fill_invalid_normals(float4* nrm, int* kcount, int begin, int en
 
 }  // namespace
 
-int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3]) {
+int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsigned char* done) {
   if (!ctx->have_grid) return fail(ctx, CAB_ERR_STATE, "cab_normals: build the grid first");
   if (!(r > 0.f) || r > ctx->cell * 1.0000001f)
     return fail(ctx, CAB_ERR_ARG, "cab_normals: radius %g exceeds the grid cell %g", (double)r, (double)ctx->cell);
@@ -239,10 +241,11 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3]) {
   if (int rc = reserve(ctx, ctx->b_stats, kStatBytes)) return rc;
   const bool use_thr = max_nn > 0;
   if (use_thr)
-    if (int rc = run_thresholds(ctx, r, max_nn)) return rc;
+    if (int rc = run_thresholds(ctx, r, max_nn, done)) return rc;
   CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, kStatBytes, st));
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
   NormalsArgs a{};
+  a.done = done;
   a.g = grid_view(ctx);
   packet_range(ctx, &a.p0, &a.p1);
   if (ctx->n_halo_packets >= 0) {  // multi-GPU: own packets plus the rows around them

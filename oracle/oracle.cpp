@@ -589,6 +589,31 @@ int orc_normals(const float* xyz, int n, double r, int max_nn, const float* vp, 
   return 0;
 }
 
+// k-NN normals: nearestKSearch (i, k_) + computePointNormal + flipNormalTowardsViewpoint as in
+// cloud_tools/src/table_object_detector_passive.cpp:668-714 and cloud_algos/src/cylinder_fit_algo.cpp:138-203
+// [point_cloud_mapping, EXTERNAL]: the PCA of orc_normals over the k smallest (d2, index) pairs, the query included.
+int orc_normals_knn(const float* xyz, int n, int k, const float* vp, float* out_n4, int nthreads) {
+  if (k < 3) return -1;
+  KdTree tree(xyz, n);
+  int nfinite = 0;
+  for (int i = 0; i < n; ++i) nfinite += finite3(xyz + 3 * (size_t)i) ? 1 : 0;
+  if (k > nfinite) return -2;
+  const float zero[3] = {0, 0, 0};
+  if (!vp) vp = zero;
+  nthreads = resolve_threads(nthreads);
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<Nb> nbs;
+#pragma omp for schedule(dynamic, 256)
+    for (int i = 0; i < n; ++i) {
+      const float* q = xyz + 3 * (size_t)i;
+      tree.knn(q, k, nbs);  // empty for a non-finite query: pca_normal then writes NaN
+      pca_normal(xyz, q, nbs, vp, out_n4 + 4 * (size_t)i);
+    }
+  }
+  return 0;
+}
+
 int orc_rsd(const float* xyz, const float* normals, int normal_stride, int n, double r,
             int max_nn, int ndiv, double plane_radius, int flags, float* r_min, float* r_max,
             float* r_dif, int nthreads) {

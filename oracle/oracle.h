@@ -201,6 +201,10 @@ int orc_pfh(const float* xyz, const float* normals, int normal_stride, int n, do
 int orc_pfh_pair(const float* ps, const float* ns, const float* pt, const float* nt, float d2, double max_dist,
                  int check_flip, int abs_angles, double* f);
 
+/* k-NN normals (table_object_detector_passive.cpp:668-714, cylinder_fit_algo.cpp:138-203): orc_normals' PCA over the
+ * k nearest points (query included, ties by index).  Returns -1 for k < 3, -2 for fewer than k finite points. */
+int orc_normals_knn(const float* xyz, int n, int k, const float* vp, float* out_n4, int nthreads);
+
 /* ---- Euclidean clustering (the step that produces the segmented object clusters GRSD runs on) --------
  * cloud_geometry::nearest::extractEuclideanClusters(points, indices, tolerance, clusters, -1, -1, -1, -1, min_pts)
  * as called at cloud_tools/src/table_object_detector_passive.cpp:293,567 and table_object_detector_sr.cpp:370.

@@ -304,6 +304,18 @@ def knn_mean_distance(xyz, k, nthreads=0):
     return avg
 
 
+def normals_knn(xyz, k, vp=(0.0, 0.0, 0.0), nthreads=0):
+    """k-nearest-neighbour PCA normals (n, 4): nx, ny, nz, curvature."""
+    L = lib()
+    p = _xyz(xyz)
+    out = np.zeros((p.shape[0], 4), np.float32)
+    v = np.asarray(vp, np.float32)
+    rc = L.orc_normals_knn(_ptr(p, C.c_float), p.shape[0], int(k), _ptr(v, C.c_float), _ptr(out, C.c_float), int(nthreads))
+    if rc != 0:
+        raise ValueError("k < 3" if rc == -1 else "not enough points in the cloud")
+    return out
+
+
 def euclidean_clusters(xyz, tolerance, min_pts=1, max_pts=0):
     """extractEuclideanClusters without the normal test: (labels int32 (n,), n_clusters); clusters are numbered in
     the order of their smallest index, -1 = dropped (too small / too large) or non-finite."""

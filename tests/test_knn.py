@@ -89,3 +89,85 @@ def test_gpu_knn_isolated_points_need_several_rounds(oracle):
     assert np.max(np.abs(avg - want) / want) < 1e-13
     assert ctx.profile()["knn_rounds"] > 3 and avg[-1] > 5.0
     ctx.close()
+
+
+def _angle_to(a, b):
+    """sin of the angle between two unit-vector arrays, sign-insensitive (acos of the dot product cannot resolve 1e-4 rad)."""
+    return np.linalg.norm(np.cross(a.astype(np.float64), b.astype(np.float64)), axis=1)
+
+
+def test_oracle_knn_normals_against_numpy(oracle):
+    """k-NN normals of the oracle (table_object_detector_passive.cpp:668-714) against scipy's k-d tree + numpy PCA,
+    and analytic planes."""
+    from scipy.spatial import cKDTree
+
+    pts = _cloud(n=4000, outliers=0)
+    k = 10
+    n4 = oracle.normals_knn(pts, k)
+    p64 = pts.astype(np.float64)
+    _, idx = cKDTree(p64).query(p64, k=k)
+    ref = np.zeros((len(pts), 3))
+    curv = np.zeros(len(pts))
+    for i in range(len(pts)):
+        nb = p64[idx[i]]
+        w, v = np.linalg.eigh(np.cov(nb.T, bias=True))
+        ref[i] = v[:, 0]
+        curv[i] = w[0] / w.sum()
+    good = curv < 0.05  # well-conditioned neighbourhoods (an edge point's smallest two eigenvalues can be close)
+    assert good.mean() > 0.7
+    assert np.percentile(_angle_to(n4[good, :3], ref[good]), 99) < 1e-3  # scipy breaks distance ties its own way
+    assert np.allclose(n4[good, 3], curv[good], atol=1e-4)
+    # flipped towards the viewpoint (0, 0, 0)
+    assert (np.sum(n4[:, :3].astype(np.float64) * (-p64), axis=1) >= -1e-7).all()
+    plane = synth.analytic_shape("plane", 2000)
+    np4 = oracle.normals_knn(plane, 12, vp=(0.0, 0.0, 10.0))
+    assert np.abs(np.abs(np4[:, 2]) - 1).max() < 1e-6 and np.abs(np4[:, 3]).max() < 1e-9
+    with pytest.raises(ValueError):
+        oracle.normals_knn(pts, 2)
+    with pytest.raises(ValueError):
+        oracle.normals_knn(pts[:5], 10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,hint,exact", [(10, 0.0, False), (10, 0.0, True), (30, 0.003, False), (5, 0.4, True)])
+def test_gpu_knn_normals_match_oracle(oracle, k, hint, exact):
+    ctx = cab.Context(0, exact=exact)
+    pts = _cloud(seed=k + 1)
+    pts[7] = pts[8]
+    pts[100] = np.inf
+    ctx.upload(pts)
+    vp = (0.1, -0.2, 2.0)
+    n4 = ctx.normals_knn(k, vp=vp, cell_hint=hint)
+    want = oracle.normals_knn(pts, k, vp=vp)
+    assert np.isnan(n4[100]).all() and np.isnan(want[100]).all()
+    fin = ~np.isnan(want[:, 0])
+    assert np.array_equal(~np.isnan(n4[:, 0]), fin)
+    ang = _angle_to(n4[fin, :3], want[fin, :3])
+    well = want[fin, 3] < 0.1
+    if exact:
+        assert np.percentile(ang[well], 99.9) < 1e-4
+    else:
+        assert np.mean(ang[well] > 1e-4) < 5e-3  # fp32 sums over 5..30 points: the tail is ill-conditioned neighbourhoods
+    assert np.allclose(n4[fin, 3][well], want[fin, 3][well], atol=2e-4)
+    # the flip is decided by the same viewpoint
+    d = (np.asarray(vp) - pts[fin].astype(np.float64))
+    assert (np.sum(n4[fin, :3] * d, axis=1) >= -1e-6).all()
+    assert ctx.profile()["knn_rounds"] >= 1
+
+
+@pytest.mark.gpu
+def test_gpu_knn_normals_feed_rsd_and_errors(oracle):
+    ctx = cab.Context(0)
+    pts = synth.tabletop(30_000, noise_sigma=0.0003)
+    ctx.upload(pts)
+    n4 = ctx.normals_knn(25)
+    ctx.build_grid(0.02)
+    ctx.set_normals(n4)
+    rmin, rmax = ctx.rsd(0.02)
+    omin, omax, _ = oracle.rsd(pts, n4, 0.02)
+    assert np.max(np.abs(rmin - omin) / omin) < 1e-4 and np.max(np.abs(rmax - omax) / omax) < 1e-4
+    with pytest.raises(cab.CabError):
+        ctx.normals_knn(2)
+    ctx.upload(pts[:6])
+    with pytest.raises(cab.CabError):
+        ctx.normals_knn(10)
