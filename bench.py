@@ -485,30 +485,41 @@ def main():
 
         my_lo, my_hi = shard.split_range(n, world)[rank]
         d_full = torch.empty((n, 3), dtype=torch.float32, device=dev) if world > 1 else None
+        d_slice = torch.empty((my_hi - my_lo, 3), dtype=torch.float32, device=dev) if world > 1 else None
+
+        e2e_stage = {"upload": 0.0, "build": 0.0, "normals_rsd_d2h": 0.0}
 
         def e2e_step():
+            t0 = time.perf_counter()
             if world == 1:
                 ctx._check(L.cab_upload_cloud(ctx._h, fp(h_xyz), C.c_int64(n), C.c_int32(3)), "cab_upload_cloud")
                 ctx.n = n
             else:
                 # every rank uploads 1/world of the cloud over PCIe, the slices are all-gathered over NVLink
-                d_slice = h_xyz[my_lo:my_hi].to(dev, non_blocking=True)
+                d_slice.copy_(h_xyz[my_lo:my_hi], non_blocking=True)
                 shard.gather_cloud(d_full, d_slice, rank, world)
                 torch.cuda.synchronize()
                 ctx.set_cloud_device(d_full.data_ptr(), n, 3)
+            t1 = time.perf_counter()
             ctx.build_grid(RADIUS)
+            t2 = time.perf_counter()
             # both passes in one call: the normals leave on the copy stream while the RSD kernel runs.
             # world > 1: each rank returns its own slice (sorted order) plus the input indices it belongs to
             ctx._check(L.cab_normals_rsd(ctx._h, C.c_double(RADIUS), C.c_int32(0), vp0, C.c_int32(0), C.c_int32(NDIV),
                                          C.c_double(PLANE_RADIUS), C.c_int32(0), C.c_int32(0 if world == 1 else 1), fp(h_n4),
                                          fp(h_rmin), fp(h_rmax) if world == 1 else None,
                                          C.cast(h_idx.data_ptr(), C.POINTER(C.c_int32)) if world > 1 else None), "cab_normals_rsd")
+            t3 = time.perf_counter()
+            for k, v in zip(e2e_stage, (t1 - t0, t2 - t1, t3 - t2)):
+                e2e_stage[k] += v
 
         e2e_steps = max(2, min(args.steps, 5))
         e2e_step()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        for k in e2e_stage:
+            e2e_stage[k] = 0.0
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
@@ -520,6 +531,7 @@ def main():
             dt = float(t.item())
         e2e = {"value": n / (dt / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(n * 12),  # summed over ranks
                "d2h_bytes_per_step": int(n * 24) if world == 1 else int(n * 28), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+               "stages_ms_rank0": {k: 1e3 * v / e2e_steps for k, v in e2e_stage.items()},
                "path": ("cab_upload_cloud -> cab_build_grid -> cab_normals_rsd (normals D2H overlaps the RSD kernel), pinned host buffers" if world == 1 else
                         "per rank: H2D of 1/N of the cloud + NCCL all-gather of the slices -> cab_set_cloud_device -> cab_build_grid -> "
                         "cab_normals_rsd, CAB_OUT_SHARD_SORTED (own slice + input indices), pinned host buffers; bytes summed over ranks")}

@@ -475,3 +475,55 @@ def test_spread_out_cloud_gets_coarser_cells(oracle):
     omin, omax, _ = oracle.rsd(pts, np.nan_to_num(o4[:, :3], nan=0.0), r)
     assert np.max(np.abs(rmin - omin) / omin) <= RADIUS_TOL_REL and np.max(np.abs(rmax - omax) / omax) <= RADIUS_TOL_REL
     c.close()
+
+
+@pytest.mark.parametrize("n", [5, 1001, 1002, 1003, 4096])
+def test_grid_build_layouts_agree(ctx, oracle, n):
+    """The vector key / bounds passes (packed xyz, 16-byte aligned, 4 points per thread) and the scalar passes
+    (stride 4, a device pointer that is only 4-byte aligned) build the same grid: neighbour sets bit-exact for
+    cloud sizes with every remainder mod 4, including non-finite points in the tail."""
+    import torch
+
+    full = synth.tabletop(20_000, noise_sigma=0.0004)
+    near = np.argsort(np.linalg.norm(full - full[123], axis=1), kind="stable")[:n]  # a dense patch of n points
+    pts = np.ascontiguousarray(full[np.sort(near)])
+    if n > 8:
+        pts[n - 1] = np.nan
+        pts[n - 2, 1] = np.inf
+    r = 0.02
+    ooff, oidx, _ = oracle.radius_search(pts, pts, r)
+
+    def sets():
+        off, idx, d2 = ctx.neighbors(r, 0, n)
+        return off, _canon(off, idx, d2)[0]
+
+    ctx.upload(pts)  # vector layout
+    ctx.build_grid(r)
+    off, gi = sets()
+    assert np.array_equal(off, ooff) and np.array_equal(gi, oidx)
+    p4 = np.zeros((n, 4), np.float32)
+    p4[:, :3] = pts
+    p4[:, 3] = 7.0
+    ctx.upload(p4)  # stride 4: scalar layout
+    ctx.build_grid(r)
+    off, gi = sets()
+    assert np.array_equal(off, ooff) and np.array_equal(gi, oidx)
+    dev = torch.zeros(3 * n + 1, dtype=torch.float32, device="cuda:0")
+    dev[1:] = torch.from_numpy(pts.reshape(-1)).to("cuda:0")
+    torch.cuda.synchronize()
+    ctx.set_cloud_device(dev.data_ptr() + 4, n, 3)  # packed but misaligned: scalar layout
+    ctx.build_grid(r)
+    off, gi = sets()
+    assert np.array_equal(off, ooff) and np.array_equal(gi, oidx)
+    for g in range(2):  # and as one shard of two (sharded sort over the vector passes)
+        ctx.set_shard(g, 2)
+        try:
+            ctx.upload(pts)
+            ctx.build_grid(r)
+            b, e = ctx.shard_range()
+            ctx.normals(r, download=False)
+            s4, _, sidx = ctx.download_sorted(b, e, rsd=False)
+        finally:
+            ctx.set_shard(0, 1)
+        o4, _ = oracle.normals(pts, r)
+        assert np.array_equal(np.isnan(s4[:, 0]), np.isnan(o4[sidx, 0]))
