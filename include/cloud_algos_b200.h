@@ -167,6 +167,19 @@ int64_t cab_grsd_voxels(cab_ctx* ctx, int64_t* vox_offsets, float* centroids_xyz
 int64_t cab_grsd_signatures(cab_ctx* ctx, int32_t kind, int32_t subdivision_size, int32_t off_x, int32_t off_y,
                             int32_t off_z, int64_t* hist_offsets, int32_t* subdiv_b, int32_t* hist, int64_t cap);
 
+/* The colour half of VOSCH (extractVOSCH, grsd_colorCHLAC_tools.hpp:832-843: the 20 GRSD-21 bins followed by 117 colour
+ * bins): rotation-invariant C3-HLAC (c3 = 1, pcl::C3HLAC_RI_Estimation, extractC3HLACSignature117 :787-812) or Color-CHLAC
+ * (c3 = 0, pcl::ColorCHLAC_RI_Estimation, the variant the reference's shipped *_GRSD_CCHLAC.pcd vectors were made with),
+ * color_chlac/include/color_chlac/color_chlac.hpp:1471-1528,1565-1782, from the voxels and leaf layouts the last
+ * cab_grsd_batch left on the device.  rgb: one packed 0x00RRGGBB per point of that batch (the bits of PCL's float rgb
+ * field); a voxel's colour is the truncated mean of its points' channels (pcl::VoxelGrid); thR/thG/thB binarise it
+ * (value > threshold, the reference passes 127).  Subdivisions, hist_offsets, subdiv_b and the return value as in
+ * cab_grsd_signatures.  hist: total x 117 floats, accumulated in the reference's order (the float sums of integer colour
+ * products pass 2^24, so the order is part of the result) and normalised (:1764-1782). */
+int64_t cab_color_chlac(cab_ctx* ctx, const uint32_t* rgb, int32_t c3, int32_t thR, int32_t thG, int32_t thB,
+                        int32_t subdivision_size, int32_t off_x, int32_t off_y, int32_t off_z, int64_t* hist_offsets,
+                        int32_t* subdiv_b, float* hist, int64_t cap);
+
 /* ---- SVM classification of the signatures ---------------------------------------------
  * The consumer of GRSD in the reference pipeline (table_memory_grsd.cpp:1000-1020): replaces, per
  * feature vector, scaleFeature + svm_predict of cloud_algos::SVMClassification::process

@@ -26,7 +26,7 @@ BUF_POS_SORTED, BUF_NRM_SORTED, BUF_RSD_SORTED, BUF_PERM = 0, 1, 2, 3
 EXPORTS = [
     "cab_create", "cab_destroy", "cab_last_error", "cab_upload_cloud", "cab_upload_clusters",
     "cab_set_cloud_device", "cab_build_grid", "cab_set_shard", "cab_shard_range", "cab_normals",
-    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd", "cab_knn_mean_distance", "cab_normals_knn", "cab_statistical_outliers", "cab_euclidean_clusters", "cab_cluster_csr", "cab_pfh",
+    "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_color_chlac", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd", "cab_knn_mean_distance", "cab_normals_knn", "cab_statistical_outliers", "cab_euclidean_clusters", "cab_cluster_csr", "cab_pfh",
     "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_profile", "cab_version",
 ]
 
@@ -72,6 +72,7 @@ def lib():
         L.cab_neighbors_debug.restype = C.c_int64
         L.cab_grsd_voxels.restype = C.c_int64
         L.cab_grsd_signatures.restype = C.c_int64
+        L.cab_color_chlac.restype = C.c_int64
         L.cab_statistical_outliers.restype = C.c_int64
         L.cab_euclidean_clusters.restype = C.c_int64
         L.cab_cluster_csr.restype = C.c_int64
@@ -260,6 +261,22 @@ class Context:
         hist = np.zeros((total, SIG_DIM[kind]), np.int32)
         if total:
             self._check(self._L.cab_grsd_signatures(*args, _ip(hist), C.c_int64(total)), "cab_grsd_signatures")
+        return dict(offsets=offs, subdiv_b=sb, hist=hist)
+
+    def color_chlac(self, nclusters: int, rgb: np.ndarray, c3: bool = True, thr=(127, 127, 127), subdivision_size: int = 0,
+                    off=(0, 0, 0)):
+        """Colour half of VOSCH for the clusters of the last grsd_batch (rgb: packed 0x00RRGGBB per point of that batch):
+        dict(offsets (nc+1), subdiv_b (nc,3), hist (total, 117) float32)."""
+        col = np.ascontiguousarray(rgb, np.uint32)
+        offs = np.zeros(nclusters + 1, np.int64)
+        sb = np.zeros((nclusters, 3), np.int32)
+        args = (self._h, col.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int32(1 if c3 else 0), C.c_int32(thr[0]), C.c_int32(thr[1]),
+                C.c_int32(thr[2]), C.c_int32(subdivision_size), C.c_int32(off[0]), C.c_int32(off[1]), C.c_int32(off[2]),
+                offs.ctypes.data_as(C.POINTER(C.c_int64)), _ip(sb))
+        total = self._check(self._L.cab_color_chlac(*args, None, C.c_int64(0)), "cab_color_chlac")
+        hist = np.zeros((total, 117), np.float32)
+        if total:
+            self._check(self._L.cab_color_chlac(*args, _fp(hist), C.c_int64(total)), "cab_color_chlac")
         return dict(offsets=offs, subdiv_b=sb, hist=hist)
 
     # ---- point feature histograms -----------------------------------------------------

@@ -61,7 +61,10 @@ __global__ void __launch_bounds__(256) voxel_key_kernel(const float* __restrict_
   vals[i] = i;
 }
 
-// One warp per voxel: centroid = (float)(sum_double / count); fills the leaf layout.
+// One warp per voxel: the centroid as pcl::VoxelGrid of the reference's era computes it -- an Eigen::VectorXf summed in
+// cloud order, then `/= count`, which Eigen 3.0-3.2 evaluates as a multiplication by 1.0f / count (the reference's
+// shipped feature vectors pin both: DESIGN.md section 2) -- and the leaf layout.  The lanes load 32 points at a time,
+// every lane then adds them in order (the float sum must be sequential).
 __global__ void __launch_bounds__(256) centroid_kernel(const float* __restrict__ xyz, int stride,
                                                        const unsigned long long* __restrict__ ukeys,
                                                        const int* __restrict__ ucount, const int* __restrict__ ustart,
@@ -71,22 +74,25 @@ __global__ void __launch_bounds__(256) centroid_kernel(const float* __restrict__
   const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (v >= nvox) return;
   const int b = ustart[v], c = ucount[v];
-  double sx = 0, sy = 0, sz = 0;
-  for (int s = lane; s < c; s += kWarp) {
-    const float* p = xyz + (size_t)sorted_idx[b + s] * stride;
-    sx += (double)p[0];
-    sy += (double)p[1];
-    sz += (double)p[2];
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    sx += __shfl_xor_sync(kFull, sx, o);
-    sy += __shfl_xor_sync(kFull, sy, o);
-    sz += __shfl_xor_sync(kFull, sz, o);
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int base = 0; base < c; base += kWarp) {
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (base + lane < c) {
+      const float* p = xyz + (size_t)sorted_idx[b + base + lane] * stride;
+      px = p[0];
+      py = p[1];
+      pz = p[2];
+    }
+    const int m = min(kWarp, c - base);
+    for (int j = 0; j < m; ++j) {
+      sx = __fadd_rn(sx, __shfl_sync(kFull, px, j));
+      sy = __fadd_rn(sy, __shfl_sync(kFull, py, j));
+      sz = __fadd_rn(sz, __shfl_sync(kFull, pz, j));
+    }
   }
   if (lane == 0) {
-    const double cnt = (double)c;
-    cent[v] = make_float4((float)(sx / cnt), (float)(sy / cnt), (float)(sz / cnt), 0.f);
+    const float rcp = __fdiv_rn(1.0f, (float)c);
+    cent[v] = make_float4(__fmul_rn(sx, rcp), __fmul_rn(sy, rcp), __fmul_rn(sz, rcp), 0.f);
     const unsigned long long key = ukeys[v];
     const int d = (int)(key >> 32);
     layout[vg[d].layout_base + (unsigned)(key & 0xffffffffu)] = v - vg[d].vox_first;
@@ -253,7 +259,7 @@ __constant__ int c_off26[26][3];
 // upper triangle is packed into 21 bins (grsd_colorCHLAC_tools.hpp:230-276, hist_num == 1).
 __global__ void __launch_bounds__(128) transitions_kernel(const VoxGrid* __restrict__ vg, const int* __restrict__ vox_off,
                                                           const float4* __restrict__ cent, const int* __restrict__ labels,
-                                                          const int* __restrict__ layout, float inv_leaf,
+                                                          const int* __restrict__ layout, float leaf,
                                                           int* __restrict__ hist21) {
   __shared__ int M[36];
   const int d = blockIdx.x;
@@ -265,9 +271,10 @@ __global__ void __launch_bounds__(128) transitions_kernel(const VoxGrid* __restr
   for (int w = threadIdx.x; w < work; w += blockDim.x) {
     const int v = v0 + w / 26, o = w % 26;
     const float4 c = cent[v];
-    // pcl::VoxelGrid::getNeighborCentroidIndices [EXTERNAL]: ijk = floor(ref * inverse_leaf)
-    const int i0 = (int)floorf(__fmul_rn(c.x, inv_leaf)), i1 = (int)floorf(__fmul_rn(c.y, inv_leaf)),
-              i2 = (int)floorf(__fmul_rn(c.z, inv_leaf));
+    // pcl::VoxelGrid::getNeighborCentroidIndices [EXTERNAL]: ijk = floor(ref / leaf) -- a division in the PCL of the
+    // reference's era (pinned by its shipped cube / dice feature vectors, whose centroids sit on voxel faces)
+    const int i0 = (int)floorf(__fdiv_rn(c.x, leaf)), i1 = (int)floorf(__fdiv_rn(c.y, leaf)),
+              i2 = (int)floorf(__fdiv_rn(c.z, leaf));
     const int n0 = i0 + c_off26[o][0] - g.min_b[0], n1 = i1 + c_off26[o][1] - g.min_b[1],
               n2 = i2 + c_off26[o][2] - g.min_b[2];
     int nt = 5;  // EMPTY
@@ -302,15 +309,15 @@ __global__ void __launch_bounds__(128) voxel_normals_kernel(const float4* __rest
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nvox) return;
   const int b = ustart[v], c = ucount[v];
-  double sx = 0, sy = 0, sz = 0;
+  float sx = 0.f, sy = 0.f, sz = 0.f;  // the normals are fields of the same Eigen::VectorXf as the centroid
   for (int s = 0; s < c; ++s) {
     const float4 q = nrm[inv_perm[sorted_idx[b + s]]];
-    sx += (double)q.x;
-    sy += (double)q.y;
-    sz += (double)q.z;
+    sx = __fadd_rn(sx, q.x);
+    sy = __fadd_rn(sy, q.y);
+    sz = __fadd_rn(sz, q.z);
   }
-  const double cnt = (double)c;
-  cnrm[v] = make_float4((float)(sx / cnt), (float)(sy / cnt), (float)(sz / cnt), 0.f);
+  const float rcp = __fdiv_rn(1.0f, (float)c);
+  cnrm[v] = make_float4(__fmul_rn(sx, rcp), __fmul_rn(sy, rcp), __fmul_rn(sz, rcp), 0.f);
 }
 
 struct SigDom {  // per cluster
@@ -367,9 +374,9 @@ __global__ void __launch_bounds__(128) signature_kernel(const VoxGrid* __restric
       hist_idx = ix + iy * s.sb[0] + iz * s.sb[0] * s.sb[1];
     }
     // pcl::VoxelGrid::getNeighborCentroidIndices [EXTERNAL]: ijk = floor(ref * inverse_leaf)
-    const int n0 = (int)floorf(__fmul_rn(c.x, inv_leaf)) + c_off26[o][0] - g.min_b[0],
-              n1 = (int)floorf(__fmul_rn(c.y, inv_leaf)) + c_off26[o][1] - g.min_b[1],
-              n2 = (int)floorf(__fmul_rn(c.z, inv_leaf)) + c_off26[o][2] - g.min_b[2];
+    const int n0 = (int)floorf(__fdiv_rn(c.x, leaf)) + c_off26[o][0] - g.min_b[0],
+              n1 = (int)floorf(__fdiv_rn(c.y, leaf)) + c_off26[o][1] - g.min_b[1],
+              n2 = (int)floorf(__fdiv_rn(c.z, leaf)) + c_off26[o][2] - g.min_b[2];
     int nb = -1;
     if (n0 >= 0 && n0 < g.div_b[0] && n1 >= 0 && n1 < g.div_b[1] && n2 >= 0 && n2 < g.div_b[2])
       nb = layout[g.layout_base + n0 + (long long)n1 * g.div_b[0] + (long long)n2 * g.div_b[0] * g.div_b[1]];
@@ -428,6 +435,126 @@ float d2_threshold(double radius, float r2_hi, bool (*pred)(double, double, int,
 }
 bool pred_bin(double dist, double radius, int b, int ndiv) { return (int)std::floor(ndiv * dist / radius) >= b; }
 bool pred_skip(double dist, double radius, int, int) { return dist > radius; }
+
+// ---- colour half of VOSCH: rotation-invariant Color-CHLAC / C3-HLAC, 117 bins -------------------------------------
+// color_chlac/include/color_chlac/color_chlac.hpp:1471-1528 (computeColorCHLAC), :1565-1743 (the four add functions),
+// :1745-1782 (normalisation).  The reference adds integer colour products into float bins; the sums pass 2^24, so the
+// result depends on the order of the additions.  One block per cluster, thread t owns bin t of every histogram of the
+// cluster and walks the voxels in cloud order, the 13 half-stencil neighbours in the reference's order: every bin sees
+// exactly the reference's sequence of float additions.
+
+// pcl::VoxelGrid's voxel colour [EXTERNAL]: r, g, b are fields of the same Eigen::VectorXf as the centroid (float sums in
+// cloud order, times 1.0f / count), packed back with truncation.
+__global__ void __launch_bounds__(128) voxel_color_kernel(const unsigned* __restrict__ rgb, const int* __restrict__ ucount,
+                                                          const int* __restrict__ ustart, const int* __restrict__ sorted_idx,
+                                                          int nvox, unsigned* __restrict__ vrgb) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  const int b = ustart[v], c = ucount[v];
+  float sr = 0.f, sg = 0.f, sb = 0.f;
+  for (int s = 0; s < c; ++s) {
+    const unsigned col = rgb[sorted_idx[b + s]];
+    sr = __fadd_rn(sr, (float)((col >> 16) & 0xffu));
+    sg = __fadd_rn(sg, (float)((col >> 8) & 0xffu));
+    sb = __fadd_rn(sb, (float)(col & 0xffu));
+  }
+  const float rcp = __fdiv_rn(1.0f, (float)c);
+  vrgb[v] = ((unsigned)(int)__fmul_rn(sr, rcp) << 16) | ((unsigned)(int)__fmul_rn(sg, rcp) << 8) | (unsigned)(int)__fmul_rn(sb, rcp);
+}
+
+constexpr int kChlacDim = 117;
+constexpr int kChlacSmemHists = 64;  // histograms of a cluster kept in shared memory (else accumulated in place in HBM)
+
+__global__ void __launch_bounds__(128) color_chlac_kernel(const VoxGrid* __restrict__ vg, const SigDom* __restrict__ sd,
+                                                          const int* __restrict__ vox_off, const float4* __restrict__ cent,
+                                                          const unsigned* __restrict__ vrgb, const int* __restrict__ layout,
+                                                          const int* __restrict__ lut,  // [2][256]: colour code, its complement
+                                                          float leaf, int sub, float inv_sub, int off_x, int off_y, int off_z,
+                                                          int thR, int thG, int thB, float* __restrict__ out) {
+  __shared__ float sh[kChlacSmemHists * kChlacDim];
+  const int d = blockIdx.x, t = threadIdx.x;
+  const SigDom s = sd[d];
+  if (s.hist_num == 0) return;
+  const bool use_sh = s.hist_num <= kChlacSmemHists;
+  float* H = use_sh ? sh : out + s.hist_base * kChlacDim;
+  for (int i = t; i < s.hist_num * kChlacDim; i += blockDim.x) H[i] = 0.f;  // :1822-1824
+  __syncthreads();
+  if (t < kChlacDim) {
+    // which addition of the reference feeds bin t
+    int kind, a = 0, b = 0, c = 0;
+    if (t < 6) { kind = 0; a = t; }                                             // addColorCHLAC_0: C[a]
+    else if (t < 42) { kind = 1; a = (t - 6) / 6; b = (t - 6) % 6; }            // addColorCHLAC_1: C[a] * N[b]
+    else if (t < 63) {                                                          // addColorCHLAC_0: C[a] * C[b], a <= b
+      kind = 2;
+      int k = t - 42;
+      a = 0;
+      while (k >= 6 - a) { k -= 6 - a; ++a; }
+      b = a + k;
+    } else if (t < 69) { kind = 3; a = (t - 63) / 2; b = (t - 63) & 1; }         // 0_bin: channel a set (b = 0) / clear (b = 1)
+    else if (t < 105) { kind = 4; a = (t - 69) / 12; b = ((t - 69) % 12) / 6; c = (t - 69) % 6; }  // 1_bin
+    else {                                                                      // 0_bin: pairs of channels
+      kind = 5;
+      const int k = t - 105;
+      if (k < 8) { a = k < 4 ? 0 : 1; b = (k & 3) >> 1; c = k & 1; }              // r or !r (a) with g / b (b), plain / negated (c)
+      else { a = 2 + ((k - 8) >> 1); b = 2; c = k & 1; }                          // g (2) or !g (3) with b
+    }
+    const VoxGrid g = vg[d];
+    const int v0 = vox_off[d], v1 = vox_off[d + 1];
+    for (int v = v0; v < v1; ++v) {
+      const float4 ce = cent[v];
+      int hist_idx = 0;
+      if (s.hist_num != 1) {  // :1476-1500
+        const int tx = (int)floorf(__fdiv_rn(ce.x, leaf)) - g.min_b[0] - off_x;
+        const int ty = (int)floorf(__fdiv_rn(ce.y, leaf)) - g.min_b[1] - off_y;
+        const int tz = (int)floorf(__fdiv_rn(ce.z, leaf)) - g.min_b[2] - off_z;
+        if (tx < 0 || ty < 0 || tz < 0) continue;
+        const int ix = (int)floorf(__fmul_rn((float)tx, inv_sub)), iy = (int)floorf(__fmul_rn((float)ty, inv_sub)),
+                  iz = (int)floorf(__fmul_rn((float)tz, inv_sub));
+        hist_idx = ix + iy * s.sb[0] + iz * s.sb[0] * s.sb[1];
+      }
+      float* bin = H + (size_t)hist_idx * kChlacDim + t;
+      const unsigned col = vrgb[v];
+      const int ch[3] = {(int)((col >> 16) & 0xffu), (int)((col >> 8) & 0xffu), (int)(col & 0xffu)};
+      const int bins[3] = {ch[0] > thR ? 1 : 0, ch[1] > thG ? 1 : 0, ch[2] > thB ? 1 : 0};
+      auto code = [&](const int* v3, int i) { return lut[(i & 1) * 256 + v3[i >> 1]]; };  // r, r_, g, g_, b, b_
+      if (kind == 0) *bin = __fadd_rn(*bin, (float)code(ch, a));
+      else if (kind == 2) *bin = __fadd_rn(*bin, (float)(code(ch, a) * code(ch, b)));
+      else if (kind == 3) { if (bins[a] == 1 - b) *bin = __fadd_rn(*bin, 1.f); }
+      else if (kind == 5) {
+        bool first, second;
+        if (a < 2) { first = bins[0] == 1 - a; second = bins[1 + b] == 1 - c; }
+        else { first = bins[1] == 3 - a; second = bins[2] == 1 - c; }
+        if (first && second) *bin = __fadd_rn(*bin, 1.f);
+      } else {  // the first-order terms: one addition per occupied half-stencil neighbour (:1512-1527)
+        if (kind == 4 && bins[a] != 1 - b) continue;
+        const int i0 = (int)floorf(__fdiv_rn(ce.x, leaf)), i1 = (int)floorf(__fdiv_rn(ce.y, leaf)),
+                  i2 = (int)floorf(__fdiv_rn(ce.z, leaf));
+        const int ca = kind == 1 ? code(ch, a) : 0;
+        for (int o = 0; o < 13; ++o) {
+          const int n0 = i0 + c_off26[o][0] - g.min_b[0], n1 = i1 + c_off26[o][1] - g.min_b[1], n2 = i2 + c_off26[o][2] - g.min_b[2];
+          if (n0 < 0 || n0 >= g.div_b[0] || n1 < 0 || n1 >= g.div_b[1] || n2 < 0 || n2 >= g.div_b[2]) continue;
+          const int nb = layout[g.layout_base + n0 + (long long)n1 * g.div_b[0] + (long long)n2 * g.div_b[0] * g.div_b[1]];
+          if (nb < 0) continue;
+          const unsigned nc = vrgb[v0 + nb];
+          const int nch[3] = {(int)((nc >> 16) & 0xffu), (int)((nc >> 8) & 0xffu), (int)(nc & 0xffu)};
+          if (kind == 1) *bin = __fadd_rn(*bin, (float)(ca * code(nch, b)));
+          else {
+            const int set = nch[c >> 1] > (c >> 1 == 0 ? thR : (c >> 1 == 1 ? thG : thB)) ? 1 : 0;
+            *bin = __fadd_rn(*bin, (float)((c & 1) ? 1 - set : set));
+          }
+        }
+      }
+    }
+    // normalizeColorCHLAC (:1745-1782): float constants, equal for both classes without ENABLE_THEORY_NORMALIZATION
+    const float norm = t < 6 ? (float)(1 / 255.0) : t < 42 ? (float)(1 / 845325.0) : t < 63 ? (float)(1 / 65025.0)
+                     : t < 69 ? 1.f : t < 105 ? (float)(1 / 13.0) : 1.f;
+    for (int h = 0; h < s.hist_num; ++h) H[(size_t)h * kChlacDim + t] = __fmul_rn(H[(size_t)h * kChlacDim + t], norm);
+  }
+  if (use_sh) {
+    __syncthreads();
+    for (int i = t; i < s.hist_num * kChlacDim; i += blockDim.x) out[s.hist_base * kChlacDim + i] = sh[i];
+  }
+}
 
 }  // namespace
 
@@ -590,7 +717,7 @@ int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_
     CAB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_off26, off26, sizeof(off26), 0, cudaMemcpyHostToDevice, st));
   }
   transitions_kernel<<<nd, 128, 0, st>>>((const VoxGrid*)ctx->g_vgrid.p, (const int*)ctx->g_voff.p, (const float4*)ctx->g_cent.p,
-                                         (const int*)ctx->g_vlabel.p, (const int*)ctx->g_layout.p, inv_leaf,
+                                         (const int*)ctx->g_vlabel.p, (const int*)ctx->g_layout.p, leaf,
                                          (int*)ctx->g_hist.p);
   CAB_LAUNCH_CHECK(ctx);
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
@@ -736,6 +863,92 @@ int64_t cab_grsd_signatures(cab_ctx* ctx, int32_t kind, int32_t subdivision_size
     CAB_LAUNCH_CHECK(ctx);
   }
   CAB_CUDA(ctx, cudaMemcpyAsync(hist, ctx->g_sig.p, (size_t)total * dim * 4, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  return total;
+}
+
+int64_t cab_color_chlac(cab_ctx* ctx, const uint32_t* rgb, int32_t c3, int32_t thR, int32_t thG, int32_t thB,
+                        int32_t subdivision_size, int32_t off_x, int32_t off_y, int32_t off_z, int64_t* hist_offsets,
+                        int32_t* subdiv_b, float* hist, int64_t cap) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (thR < 0 || thG < 0 || thB < 0) return fail(ctx, CAB_ERR_ARG, "cab_color_chlac: Invalid color_threshold: %d %d %d", thR, thG, thB);
+  if (subdivision_size < 0) return fail(ctx, CAB_ERR_ARG, "cab_color_chlac: Invalid subdivision size: %d", subdivision_size);
+  const int nd = (int)ctx->g_min_div.size() / 6;
+  if (nd == 0 || ctx->g_vox_offsets.size() != (size_t)nd + 1)
+    return fail(ctx, CAB_ERR_STATE, "cab_color_chlac: run cab_grsd_batch first");
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, CAB_ERR_CUDA, "cudaSetDevice failed");
+  // subdivision bookkeeping per cluster (setVoxelFilter, color_chlac.hpp:181-210), host, tiny
+  const float inv_sub = subdivision_size > 0 ? (float)(1.0 / subdivision_size) : 0.f;
+  std::vector<SigDom> sd(nd);
+  int64_t total = 0;
+  for (int d = 0; d < nd; ++d) {
+    const int32_t* div_b = ctx->g_min_div.data() + 6 * (size_t)d + 3;
+    SigDom& s = sd[d];
+    s.hist_base = total;
+    s.sb[0] = s.sb[1] = s.sb[2] = 1;
+    s.hist_num = 1;
+    if (subdivision_size > 0) {
+      if (div_b[0] <= off_x || div_b[1] <= off_y || div_b[2] <= off_z) {
+        s.sb[0] = s.sb[1] = s.sb[2] = 0;
+        s.hist_num = 0;
+      } else {
+        s.sb[0] = (int)std::ceil((div_b[0] - off_x) * inv_sub);
+        s.sb[1] = (int)std::ceil((div_b[1] - off_y) * inv_sub);
+        s.sb[2] = (int)std::ceil((div_b[2] - off_z) * inv_sub);
+        s.hist_num = s.sb[0] * s.sb[1] * s.sb[2];
+      }
+    }
+    if (hist_offsets) hist_offsets[d] = total;
+    if (subdiv_b)
+      for (int a = 0; a < 3; ++a) subdiv_b[3 * (size_t)d + a] = s.sb[a];
+    total += s.hist_num;
+  }
+  if (hist_offsets) hist_offsets[nd] = total;
+  if (!hist || total == 0) return total;
+  if (!rgb) return fail(ctx, CAB_ERR_ARG, "cab_color_chlac: no colours");
+  if (total > cap) return fail(ctx, CAB_ERR_ARG, "cab_color_chlac: %lld histograms, room for %lld", (long long)total, (long long)cap);
+  cudaStream_t st = ctx->stream;
+  const int n = (int)ctx->n;
+  const int nvox = (int)ctx->g_nvox;
+  // colour code tables (setColor, color_chlac.hpp:148-166).  C3-HLAC: 255 * sin / cos (v * angle_norm) with the float
+  // angle_norm = M_PI / 510 (color_chlac.h:9); the unqualified sin / cos of a float argument resolve to the double
+  // functions of <math.h> with the toolchain of the reference's era, the product is truncated to int.
+  int lut[512];
+  const float angle_norm = M_PI / 510;
+  for (int v = 0; v < 256; ++v) {
+    if (c3) {
+      lut[v] = 255 * ::sin((double)(v * angle_norm));
+      lut[256 + v] = 255 * ::cos((double)(v * angle_norm));
+    } else {
+      lut[v] = v;
+      lut[256 + v] = 255 - v;
+    }
+  }
+  const size_t rgb_bytes = (size_t)std::max(n, 1) * 4, vrgb_bytes = (size_t)std::max(nvox, 1) * 4;
+  if (int rc = reserve(ctx, ctx->g_color, rgb_bytes + vrgb_bytes + sizeof(lut) + 64)) return rc;
+  if (int rc = reserve(ctx, ctx->g_sig, (size_t)total * kChlacDim * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->g_sigdom, (size_t)nd * sizeof(SigDom))) return rc;
+  if (int rc = reserve_pinned(ctx, (size_t)nd * sizeof(SigDom) + sizeof(lut))) return rc;
+  unsigned* d_rgb = (unsigned*)ctx->g_color.p;
+  unsigned* d_vrgb = d_rgb + std::max(n, 1);
+  int* d_lut = (int*)(d_vrgb + std::max(nvox, 1));
+  std::memcpy(ctx->h_pin, sd.data(), (size_t)nd * sizeof(SigDom));
+  std::memcpy((char*)ctx->h_pin + (size_t)nd * sizeof(SigDom), lut, sizeof(lut));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->g_sigdom.p, ctx->h_pin, (size_t)nd * sizeof(SigDom), cudaMemcpyHostToDevice, st));
+  CAB_CUDA(ctx, cudaMemcpyAsync(d_lut, (char*)ctx->h_pin + (size_t)nd * sizeof(SigDom), sizeof(lut), cudaMemcpyHostToDevice, st));
+  if (n > 0) CAB_CUDA(ctx, cudaMemcpyAsync(d_rgb, rgb, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->g_sig.p, 0, (size_t)total * kChlacDim * 4, st));
+  if (nvox > 0) {
+    const int* ucount = (const int*)ctx->g_vcount.p;
+    const int* ustart = ucount + (std::max(n, 1) + 1);
+    voxel_color_kernel<<<(nvox + 127) / 128, 128, 0, st>>>(d_rgb, ucount, ustart, (const int*)ctx->g_vvals[1].p, nvox, d_vrgb);
+    CAB_LAUNCH_CHECK(ctx);
+    color_chlac_kernel<<<nd, 128, 0, st>>>((const VoxGrid*)ctx->g_vgrid.p, (const SigDom*)ctx->g_sigdom.p, (const int*)ctx->g_voff.p,
+                                           (const float4*)ctx->g_cent.p, d_vrgb, (const int*)ctx->g_layout.p, d_lut, ctx->g_leaf,
+                                           subdivision_size, inv_sub, off_x, off_y, off_z, thR, thG, thB, (float*)ctx->g_sig.p);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  CAB_CUDA(ctx, cudaMemcpyAsync(hist, ctx->g_sig.p, (size_t)total * kChlacDim * 4, cudaMemcpyDeviceToHost, st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   return total;
 }

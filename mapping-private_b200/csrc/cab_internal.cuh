@@ -125,7 +125,7 @@ struct cab_ctx {
   // GRSD results of the last batch
   cab::DevBuf g_vkeys[2], g_vvals[2], g_cent, g_vcount, g_vrad, g_vlabel, g_voff, g_layout, g_layoff,
       g_vgrid, g_hist, g_vfirst;
-  cab::DevBuf g_cnrm, g_invperm, g_sig, g_sigdom;
+  cab::DevBuf g_cnrm, g_invperm, g_sig, g_sigdom, g_color;
   int64_t g_nvox = 0;
   std::vector<int64_t> g_vox_offsets;
   std::vector<int32_t> g_min_div;  // host copy of the voxel grids: min_b[3], div_b[3] per cluster

@@ -470,13 +470,15 @@ void fill_offsets26(int32_t off[26][3]) {
     for (int a = 0; a < 3; ++a) off[13 + c][a] = -off[c][a];
 }
 
-// pcl::VoxelGrid::getNeighborCentroidIndices [EXTERNAL], call site
-// grsd_colorCHLAC_tools.hpp:249.
-inline int neighbor_centroid(const float* ref, float inv_leaf, const int32_t* min_b,
+// pcl::VoxelGrid::getNeighborCentroidIndices [EXTERNAL], call sites grsd_colorCHLAC_tools.hpp:249 and
+// color_chlac.hpp:1512.  ijk = floor(ref / leaf): a division in the PCL of the reference's era -- the shipped cube and
+// dice feature vectors, whose voxel centroids sit on voxel faces, give 2187 / 2809 occupied half-stencil pairs with it
+// and 2157 / 2789 with ref * (1 / leaf) (tests/test_color_chlac.py).
+inline int neighbor_centroid(const float* ref, float leaf, const int32_t* min_b,
                              const int32_t* div_b, const int32_t* layout, const int32_t* disp) {
   int ijk[3], max_b[3];
   for (int a = 0; a < 3; ++a) {
-    ijk[a] = (int)std::floor(ref[a] * inv_leaf);
+    ijk[a] = (int)std::floor(ref[a] / leaf);
     max_b[a] = min_b[a] + div_b[a] - 1;
   }
   for (int a = 0; a < 3; ++a) {
@@ -750,7 +752,11 @@ int orc_voxel_grid(const float* xyz, int n, float leaf, int32_t* min_b, int32_t*
   size_t i = 0;
   while (i < keyed.size()) {
     size_t j = i;
-    double s[3] = {0, 0, 0};
+    // Eigen::VectorXf centroid: float sums in cloud order; `centroid /= (float)nr_points` multiplies by the
+    // reciprocal in the Eigen 3.0-3.2 the reference was built with (DenseBase::operator/= for non-integer scalars).
+    // The reference's shipped feature vectors show it: a voxel of k points of colour 255 comes out as 254 for some k,
+    // and the cube's centroids on voxel faces fall into the neighbouring voxel.
+    float s[3] = {0.f, 0.f, 0.f};
     while (j < keyed.size() && keyed[j].first == keyed[i].first) {
       const float* p = xyz + 3 * (size_t)keyed[j].second;
       s[0] += p[0];
@@ -759,8 +765,8 @@ int orc_voxel_grid(const float* xyz, int n, float leaf, int32_t* min_b, int32_t*
       ++j;
     }
     if (centroids) {
-      double cnt = (double)(j - i);
-      for (int a = 0; a < 3; ++a) centroids[3 * (size_t)nvox + a] = (float)(s[a] / cnt);
+      const float rcp = 1.0f / (float)(j - i);
+      for (int a = 0; a < 3; ++a) centroids[3 * (size_t)nvox + a] = s[a] * rcp;
     }
     if (layout) layout[keyed[i].first] = nvox;
     if (counts) counts[nvox] = (int32_t)(j - i);
@@ -793,7 +799,6 @@ void orc_offsets26(int32_t* out) {
 int orc_grsd_transitions(const float* centroids, int nvox, const int32_t* types, float leaf,
                          const int32_t* min_b, const int32_t* div_b, const int32_t* layout,
                          int32_t* transition36, int32_t* hist21) {
-  const float inv = 1.0f / leaf;
   int32_t off[26][3];
   fill_offsets26(off);
   int32_t M[6][6];
@@ -801,7 +806,7 @@ int orc_grsd_transitions(const float* centroids, int nvox, const int32_t* types,
   for (int v = 0; v < nvox; ++v) {  // grsd_colorCHLAC_tools.hpp:230-260, hist_num == 1
     int src = types[v];
     for (int o = 0; o < 26; ++o) {
-      int nb = neighbor_centroid(centroids + 3 * (size_t)v, inv, min_b, div_b, layout, off[o]);
+      int nb = neighbor_centroid(centroids + 3 * (size_t)v, leaf, min_b, div_b, layout, off[o]);
       int nt = (nb == -1) ? 5 : types[nb];
       M[src][nt]++;
     }
@@ -841,7 +846,6 @@ int orc_grsd21_subdiv(const float* centroids, int nvox, const int32_t* types, fl
     subdiv_b[2] = sb[2];
   }
   if (!hist21) return hist_num;
-  const float inv = 1.0f / leaf;
   int32_t off[26][3];
   fill_offsets26(off);
   std::vector<int32_t> M((size_t)hist_num * 36, 0);
@@ -860,7 +864,7 @@ int orc_grsd21_subdiv(const float* centroids, int nvox, const int32_t* types, fl
     }
     int src = types[v];
     for (int o = 0; o < 26; ++o) {
-      int nb = neighbor_centroid(c, inv, min_b, div_b, layout, off[o]);
+      int nb = neighbor_centroid(c, leaf, min_b, div_b, layout, off[o]);
       int nt = (nb == -1) ? 5 : types[nb];
       M[(size_t)hist_idx * 36 + src * 6 + nt]++;
     }
@@ -933,7 +937,7 @@ int orc_voxel_normals(const float* xyz, const float* normals, int normal_stride,
   size_t i = 0;
   while (i < keyed.size()) {
     size_t j = i;
-    double s[3] = {0, 0, 0};
+    float s[3] = {0.f, 0.f, 0.f};  // part of the same Eigen::VectorXf as the centroid (orc_voxel_grid)
     while (j < keyed.size() && keyed[j].first == keyed[i].first) {
       const float* q = normals + (size_t)normal_stride * keyed[j].second;
       s[0] += q[0];
@@ -941,8 +945,8 @@ int orc_voxel_normals(const float* xyz, const float* normals, int normal_stride,
       s[2] += q[2];
       ++j;
     }
-    const double cnt = (double)(j - i);
-    for (int a = 0; a < 3; ++a) out[3 * (size_t)v + a] = (float)(s[a] / cnt);
+    const float rcp = 1.0f / (float)(j - i);
+    for (int a = 0; a < 3; ++a) out[3 * (size_t)v + a] = s[a] * rcp;
     ++v;
     i = j;
   }
@@ -978,7 +982,6 @@ int orc_grsd_signature(int kind, const float* centroids, const float* cent_norma
   }
   if (!hist) return hist_num;
   const int dim = kind == ORC_SIG_GRSD21 ? 21 : (kind == ORC_SIG_GRSD325 ? 325 : 110);
-  const float inv = 1.0f / leaf;
   int32_t off[26][3];
   fill_offsets26(off);
   const int NRDIV = 7, NRCLASS = 5;  // grsd_colorCHLAC_tools.h:9,18
@@ -1013,13 +1016,13 @@ int orc_grsd_signature(int kind, const float* centroids, const float* cent_norma
     const int src = types[v];
     if (kind == ORC_SIG_GRSD21) {
       for (int o = 0; o < 26; ++o) {
-        int nb = neighbor_centroid(c, inv, min_b, div_b, layout, off[o]);
+        int nb = neighbor_centroid(c, leaf, min_b, div_b, layout, off[o]);
         int nt = (nb == -1) ? 5 : types[nb];
         H[src * 6 + nt]++;
       }
     } else if (kind == ORC_SIG_GRSD325) {
       for (int o = 0; o < 13; ++o) {  // :415-429: the 13 half offsets only
-        int nb = neighbor_centroid(c, inv, min_b, div_b, layout, off[o]);
+        int nb = neighbor_centroid(c, leaf, min_b, div_b, layout, off[o]);
         if (nb == -1) continue;  // "ignore EMPTY"
         H[src + types[nb] * 5 + o * 25]++;
       }
@@ -1027,7 +1030,7 @@ int orc_grsd_signature(int kind, const float* centroids, const float* cent_norma
       const float* sn = nn.data() + 3 * (size_t)v;
       if (!(std::isfinite(sn[0]) && std::isfinite(sn[1]) && std::isfinite(sn[2]))) continue;  // :583
       for (int o = 0; o < 26; ++o) {
-        int nb = neighbor_centroid(c, inv, min_b, div_b, layout, off[o]);
+        int nb = neighbor_centroid(c, leaf, min_b, div_b, layout, off[o]);
         if (nb == -1) {
           H[NRDIV * 25 + src]++;  // transitions_to_empty (:595-596)
           continue;
@@ -1146,6 +1149,176 @@ int orc_knn_mean_distance(const float* xyz, int n, int k, double* avg, int nthre
     }
   }
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Colour half of VOSCH: rotation-invariant Color-CHLAC / C3-HLAC, 117 bins
+// (color_chlac/include/color_chlac/color_chlac.hpp; called from extractC3HLACSignature117 and extractVOSCH,
+// grsd_colorCHLAC_tools.hpp:787-843).  Integer colour arithmetic accumulated into float bins in the
+// reference's order (voxels in cloud order, per voxel: 0th-order binary, 0th-order, then per valid
+// half-stencil neighbour 1st-order binary, 1st-order) -- the float sums pass 2^24, so the order matters.
+// ---------------------------------------------------------------------------------------------------
+
+// pcl::VoxelGrid's colour of a voxel [EXTERNAL]: r, g, b unpacked, summed as floats, times 1 / count, truncated.
+int orc_voxel_colors(const float* xyz, const uint32_t* rgb, int n, float leaf, uint32_t* out_rgb) {
+  const float inv = 1.0f / leaf;
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int nf = 0;
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * (size_t)i;
+    if (!finite3(p)) continue;
+    ++nf;
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = std::min(mn[a], p[a]);
+      mx[a] = std::max(mx[a], p[a]);
+    }
+  }
+  if (nf == 0) return 0;
+  int32_t min_b[3], div_b[3];
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = (int32_t)std::floor(mn[a] * inv);
+    div_b[a] = (int32_t)std::floor(mx[a] * inv) - min_b[a] + 1;
+  }
+  std::vector<std::pair<int64_t, int32_t>> keyed;
+  keyed.reserve(nf);
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * (size_t)i;
+    if (!finite3(p)) continue;
+    const int i0 = (int)(std::floor(p[0] * inv) - min_b[0]), i1 = (int)(std::floor(p[1] * inv) - min_b[1]),
+              i2 = (int)(std::floor(p[2] * inv) - min_b[2]);
+    keyed.emplace_back((int64_t)i0 + (int64_t)i1 * div_b[0] + (int64_t)i2 * div_b[0] * div_b[1], i);
+  }
+  std::sort(keyed.begin(), keyed.end());
+  int nvox = 0;
+  for (size_t i = 0; i < keyed.size();) {
+    size_t j = i;
+    float sr = 0.f, sg = 0.f, sb = 0.f;
+    for (; j < keyed.size() && keyed[j].first == keyed[i].first; ++j) {
+      const uint32_t c = rgb[keyed[j].second];
+      sr += (float)((c >> 16) & 0xff);
+      sg += (float)((c >> 8) & 0xff);
+      sb += (float)(c & 0xff);
+    }
+    const float rcp = 1.0f / (float)(j - i);  // Eigen 3.0-3.2 `/=`: times the reciprocal (see orc_voxel_grid)
+    out_rgb[nvox++] = ((uint32_t)(int)(sr * rcp) << 16) | ((uint32_t)(int)(sg * rcp) << 8) | (uint32_t)(int)(sb * rcp);
+    i = j;
+  }
+  return nvox;
+}
+
+int orc_color_chlac117(int c3, const float* centroids, const uint32_t* rgb, int nvox, float leaf, const int32_t* min_b,
+                       const int32_t* div_b, const int32_t* layout, int thR, int thG, int thB, int subdivision_size,
+                       int off_x, int off_y, int off_z, int32_t* subdiv_b, float* hist) {
+  if (thR < 0 || thG < 0 || thB < 0) return -2;  // color_chlac.hpp:1812-1815
+  if (subdivision_size < 0) return -1;           // :203-206
+  int hist_num = 1;
+  float inverse_subdivision_size = 0.f;
+  int sb[3] = {1, 1, 1};
+  if (subdivision_size > 0) {  // setVoxelFilter, :185-201
+    inverse_subdivision_size = 1.0 / subdivision_size;
+    if (div_b[0] <= off_x || div_b[1] <= off_y || div_b[2] <= off_z) {
+      if (subdiv_b) subdiv_b[0] = subdiv_b[1] = subdiv_b[2] = 0;
+      return 0;
+    }
+    sb[0] = (int)std::ceil((div_b[0] - off_x) * inverse_subdivision_size);
+    sb[1] = (int)std::ceil((div_b[1] - off_y) * inverse_subdivision_size);
+    sb[2] = (int)std::ceil((div_b[2] - off_z) * inverse_subdivision_size);
+    hist_num = sb[0] * sb[1] * sb[2];
+  }
+  if (subdiv_b) {
+    subdiv_b[0] = sb[0];
+    subdiv_b[1] = sb[1];
+    subdiv_b[2] = sb[2];
+  }
+  if (!hist) return hist_num;
+  const int DIM = 117;
+  for (size_t i = 0; i < (size_t)hist_num * DIM; ++i) hist[i] = 0.f;  // :1822-1824
+  int32_t off[26][3];
+  fill_offsets26(off);  // the first 13 are color_chlac.h:92-113's relative_coordinates
+  const float angle_norm = M_PI / 510;  // color_chlac.h:9
+  // setColor (:148-166).  C3-HLAC: `255 * sin( val1 * angle_norm )` -- int * float -> float argument; the unqualified sin /
+  // cos inside namespace pcl resolve to <math.h>'s double functions with the toolchain of the reference's era (GCC 4.x:
+  // the float overloads live in std:: only), 255 * double -> double, truncated to int.  Only v = 255 depends on the choice
+  // (254 here, 255 with sinf); the shipped feature vectors were made with the other colour coding and cannot tell.
+  auto code = [&](int v, int& pos, int& neg) {
+    if (c3) {
+      pos = 255 * ::sin((double)(v * angle_norm));
+      neg = 255 * ::cos((double)(v * angle_norm));
+    } else {
+      pos = v;
+      neg = 255 - v;
+    }
+  };
+  for (int v = 0; v < nvox; ++v) {
+    int hist_idx = 0;
+    const float* c = centroids + 3 * (size_t)v;
+    if (hist_num != 1) {  // :1476-1500
+      const int tmp_x = std::floor(c[0] / leaf) - min_b[0] - off_x;
+      const int tmp_y = std::floor(c[1] / leaf) - min_b[1] - off_y;
+      const int tmp_z = std::floor(c[2] / leaf) - min_b[2] - off_z;
+      if (tmp_x < 0 || tmp_y < 0 || tmp_z < 0) continue;
+      const int ix = (int)std::floor(tmp_x * inverse_subdivision_size), iy = (int)std::floor(tmp_y * inverse_subdivision_size),
+                iz = (int)std::floor(tmp_z * inverse_subdivision_size);
+      hist_idx = ix + iy * sb[0] + iz * sb[0] * sb[1];
+    }
+    float* H = hist + (size_t)hist_idx * DIM;
+    const uint32_t color = rgb[v];
+    const int cr0 = (color >> 16) & 0xff, cg0 = (color >> 8) & 0xff, cb0 = color & 0xff;  // :1502-1505
+    const int br = cr0 > thR ? 1 : 0, bg = cg0 > thG ? 1 : 0, bb = cb0 > thB ? 1 : 0;     // :129-146
+    // addColorCHLAC_0_bin (:1597-1645)
+    H[br ? 63 : 64]++;
+    H[bg ? 65 : 66]++;
+    H[bb ? 67 : 68]++;
+    if (br) {
+      H[bg ? 105 : 106]++;
+      H[bb ? 107 : 108]++;
+    } else {
+      H[bg ? 109 : 110]++;
+      H[bb ? 111 : 112]++;
+    }
+    if (bg) H[bb ? 113 : 114]++;
+    else H[bb ? 115 : 116]++;
+    // addColorCHLAC_0 (:1565-1595)
+    int C[6];  // r, r_, g, g_, b, b_
+    code(cr0, C[0], C[1]);
+    code(cg0, C[2], C[3]);
+    code(cb0, C[4], C[5]);
+    for (int i = 0; i < 6; ++i) H[i] += C[i];
+    for (int i = 0, t = 42; i < 6; ++i)
+      for (int j = i; j < 6; ++j, ++t) H[t] += C[i] * C[j];
+    // 13 half-stencil neighbours (:1512-1527)
+    for (int o = 0; o < 13; ++o) {
+      const int nb = neighbor_centroid(c, leaf, min_b, div_b, layout, off[o]);
+      if (nb == -1) continue;
+      const uint32_t nc = rgb[nb];
+      const int r = (nc >> 16) & 0xff, g = (nc >> 8) & 0xff, b = nc & 0xff;
+      // addColorCHLAC_1_bin (:1688-1743)
+      const int nbr = r > thR ? 1 : 0, nbg = g > thG ? 1 : 0, nbb = b > thB ? 1 : 0;
+      const int B6[6] = {nbr, 1 - nbr, nbg, 1 - nbg, nbb, 1 - nbb};
+      for (int i = 0; i < 6; ++i) H[(br ? 69 : 75) + i] += B6[i];
+      for (int i = 0; i < 6; ++i) H[(bg ? 81 : 87) + i] += B6[i];
+      for (int i = 0; i < 6; ++i) H[(bb ? 93 : 99) + i] += B6[i];
+      // addColorCHLAC_1 (:1647-1686)
+      int N[6];
+      code(r, N[0], N[1]);
+      code(g, N[2], N[3]);
+      code(b, N[4], N[5]);
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) H[6 + 6 * i + j] += C[i] * N[j];
+    }
+  }
+  // normalizeColorCHLAC (:1745-1782; the constants of the two classes are equal without ENABLE_THEORY_NORMALIZATION)
+  const float n_ri_0 = 1 / 255.0, n_ri_1 = 1 / 845325.0, n_1 = 1 / 65025.0, n_ri_0_bin = 1, n_ri_1_bin = 1 / 13.0, n_1_bin = 1;
+  for (int h = 0; h < hist_num; ++h) {
+    float* H = hist + (size_t)h * DIM;
+    for (int i = 0; i < 6; ++i) H[i] *= n_ri_0;
+    for (int i = 6; i < 42; ++i) H[i] *= n_ri_1;
+    for (int i = 42; i < 63; ++i) H[i] *= n_1;
+    for (int i = 63; i < 69; ++i) H[i] *= n_ri_0_bin;
+    for (int i = 69; i < 105; ++i) H[i] *= n_ri_1_bin;
+    for (int i = 105; i < DIM; ++i) H[i] *= n_1_bin;
+  }
+  return hist_num;
 }
 
 // cloud_geometry::nearest::extractEuclideanClusters [EXTERNAL] as called at

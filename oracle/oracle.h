@@ -201,6 +201,21 @@ int orc_pfh(const float* xyz, const float* normals, int normal_stride, int n, do
 int orc_pfh_pair(const float* ps, const float* ns, const float* pt, const float* nt, float d2, double max_dist,
                  int check_flip, int abs_angles, double* f);
 
+/* ---- colour half of VOSCH: rotation-invariant Color-CHLAC / C3-HLAC, 117 bins ---------------------------
+ * color_chlac/include/color_chlac/color_chlac.hpp:1471-1528 (computeColorCHLAC), :1565-1743 (the four add functions),
+ * :1745-1782 (normalisation), setColor :148-166, setVoxelFilter :181-210; called by extractC3HLACSignature117 and
+ * extractVOSCH (grsd_colorCHLAC_tools.hpp:787-843; VOSCH = the 20 GRSD bins followed by these 117).
+ * c3 = 1: C3HLAC_RI_Estimation (sin / cos colour coding), 0: ColorCHLAC_RI_Estimation (v, 255 - v).
+ * rgb: one packed 0x00RRGGBB per voxel (orc_voxel_colors).  Call with hist == NULL for subdiv_b / hist_num; returns
+ * hist_num (0: offsets exceed the grid, -1: invalid subdivision size, -2: negative colour threshold).
+ * hist: hist_num x 117 floats, accumulated and normalised exactly in the reference's order. */
+int orc_color_chlac117(int c3, const float* centroids, const uint32_t* rgb, int nvox, float leaf, const int32_t* min_b,
+                       const int32_t* div_b, const int32_t* layout, int thR, int thG, int thB, int subdivision_size,
+                       int off_x, int off_y, int off_z, int32_t* subdiv_b, float* hist);
+/* pcl::VoxelGrid's voxel colour [EXTERNAL]: r, g, b summed and divided as floats, truncated; voxel order as
+ * orc_voxel_grid.  Returns V. */
+int orc_voxel_colors(const float* xyz, const uint32_t* rgb, int n, float leaf, uint32_t* out_rgb);
+
 /* k-NN normals (table_object_detector_passive.cpp:668-714, cylinder_fit_algo.cpp:138-203): orc_normals' PCA over the
  * k nearest points (query included, ties by index).  Returns -1 for k < 3, -2 for fewer than k finite points. */
 int orc_normals_knn(const float* xyz, int n, int k, const float* vp, float* out_n4, int nthreads);

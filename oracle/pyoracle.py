@@ -246,6 +246,34 @@ def grsd_signature(kind, grid, types, cent_normals=None, subdivision_size=0, off
     return hn, sb, h
 
 
+def voxel_colors(xyz, rgb, leaf):
+    """pcl::VoxelGrid's colour of every voxel (packed 0x00RRGGBB, voxel order as voxel_grid)."""
+    L = lib()
+    p = _xyz(xyz)
+    c = np.ascontiguousarray(rgb, np.uint32)
+    out = np.zeros(max(p.shape[0], 1), np.uint32)
+    nv = L.orc_voxel_colors(_ptr(p, C.c_float), _ptr(c, C.c_uint32), p.shape[0], C.c_float(leaf), _ptr(out, C.c_uint32))
+    return out[:nv]
+
+
+def color_chlac117(grid, voxel_rgb, thr=(127, 127, 127), c3=True, subdivision_size=0, off=(0, 0, 0)):
+    """Rotation-invariant C3-HLAC (c3=True) / Color-CHLAC, 117 bins.  grid: voxel_grid(...) + "leaf";
+    returns (hist_num, subdiv_b (3,), hist (hist_num, 117) float32)."""
+    L = lib()
+    cent = np.ascontiguousarray(grid["centroids"], np.float32)
+    col = np.ascontiguousarray(voxel_rgb, np.uint32)
+    sb = np.zeros(3, np.int32)
+    args = (1 if c3 else 0, _ptr(cent, C.c_float), _ptr(col, C.c_uint32), int(grid["nvox"]), C.c_float(grid["leaf"]),
+            _ptr(grid["min_b"], C.c_int32), _ptr(grid["div_b"], C.c_int32), _ptr(grid["layout"], C.c_int32),
+            int(thr[0]), int(thr[1]), int(thr[2]), int(subdivision_size), int(off[0]), int(off[1]), int(off[2]), _ptr(sb, C.c_int32))
+    hn = L.orc_color_chlac117(*args, None)
+    if hn <= 0:
+        return hn, sb, np.zeros((0, 117), np.float32)
+    h = np.zeros((hn, 117), np.float32)
+    assert L.orc_color_chlac117(*args, _ptr(h, C.c_float)) == hn
+    return hn, sb, h
+
+
 def grsd_cluster(xyz, leaf, kind=SIG_GRSD21, subdivision_size=0, off=(0, 0, 0), r_normals=0.02, rsd_radius_min=0.01,
                  rsd_flags=0, normals_in=None, vp=(0.0, 0.0, 0.0), nthreads=0):
     """Whole recipe for one cluster and any signature: normals -> voxel grid -> voxel RSD -> labels ->

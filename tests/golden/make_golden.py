@@ -54,8 +54,36 @@ def svm_fixture():
     print("svm_grsd_ijrr:", m.nr_class, "classes,", m.total_sv, "SVs, dim", m.dim)
 
 
+def vosch_fixture():
+    """The reference's own VOSCH outputs (20 GRSD + 117 C3-HLAC values per file, exampleVOSCH.cpp: leaf 0.01, colour
+    thresholds 127) for ten of its fourteen shape geometries in all seven colours.  Every file is uniformly coloured and
+    the seven colours of a shape share one geometry, so the fixture holds each geometry once."""
+    geoms = ["noiseless_" + s for s in ("plane", "sphere", "cylinder", "torus", "cone", "cube", "dice")] + \
+            ["noisy_" + s for s in ("torus", "cone", "sphere")]
+    colors = ["black", "blue", "green", "orange", "purple", "red", "yellow"]
+    data = {"geoms": np.array(geoms), "colors": np.array(colors)}
+    for g in geoms:
+        xyz0 = None
+        for c in colors:
+            raw = (REF / f"{g}_{c}.pcd").read_bytes()
+            head = raw[:4096].decode("ascii", errors="ignore")
+            n = int(re.search(r"POINTS (\d+)", head).group(1))
+            a = np.frombuffer(raw, dtype="<f4", count=n * 4, offset=4096).reshape(n, 4)
+            xyz, rgb = np.ascontiguousarray(a[:, :3]), np.ascontiguousarray(a[:, 3]).view(np.uint32)
+            assert len(np.unique(rgb)) == 1
+            if xyz0 is None:
+                xyz0 = xyz
+                data[f"{g}_xyz"] = xyz.astype(np.float32)
+            assert np.array_equal(xyz0, xyz)
+            data[f"{g}_{c}_rgb"] = np.uint32(rgb[0])
+            data[f"{g}_{c}_vosch137"] = np.loadtxt(REF / f"{g}_{c}_GRSD_CCHLAC.pcd", skiprows=9).astype(np.float32)
+    np.savez_compressed(OUT / "shape_data_vosch.npz", **data)
+    print("shape_data_vosch:", len(geoms), "geometries x", len(colors), "colours")
+
+
 def main():
     svm_fixture()
+    vosch_fixture()
     data = {}
     for s in SHAPES:
         xyz = read_pcd_xyz(REF / f"noiseless_{s}_blue.pcd")
