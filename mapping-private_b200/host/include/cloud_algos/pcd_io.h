@@ -1,6 +1,7 @@
 // pcd_io.h -- the little PCD I/O the GRSD tools need (color_chlac/include/color_chlac/grsd_colorCHLAC_tools.hpp:12-58):
 //   readPCDXYZ    stands in for readPoints() -> pcl::io::loadPCDFile for the fields this path reads: x, y, z and, when
-//                 present, normal_x, normal_y, normal_z.  Reads `DATA ascii` and `DATA binary` (v.7: the payload follows
+//                 present, normal_x, normal_y, normal_z and rgb (PCL's packed colour: the bits of a float / uint32 field,
+//                 returned as 0x00RRGGBB).  Reads `DATA ascii` and `DATA binary` (v.7: the payload follows
 //                 the DATA line; v.5/.6 files whose header is padded to a 4096-byte page, as the reference's
 //                 color_chlac/demos/shape_data/*.pcd are: the payload then starts at byte 4096).
 //   writeFeature  the reference's histogram writer: `FIELDS vfh`, COUNT = dimension, one ASCII line per histogram,
@@ -8,6 +9,8 @@
 // Unlike the reference's readPoints, which returns bool(-1) == true on failure (:16-19), a failed read returns false.
 #ifndef CLOUD_ALGOS_PCD_IO_H
 #define CLOUD_ALGOS_PCD_IO_H
+#include <stdint.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,10 +22,12 @@
 namespace cloud_algos
 {
 
-inline bool readPCDXYZ (const char* name, std::vector<float>& xyz, std::vector<float>* normals = 0, std::string* error = 0)
+inline bool readPCDXYZ (const char* name, std::vector<float>& xyz, std::vector<float>* normals = 0, std::string* error = 0,
+                        std::vector<uint32_t>* rgb = 0)
 {
   xyz.clear ();
   if (normals) normals->clear ();
+  if (rgb) rgb->clear ();
   std::ifstream fs (name, std::ios::binary);
   if (!fs.is_open ()) { if (error) *error = std::string ("Couldn't read file ") + name; return false; }
   std::vector<std::string> fields;
@@ -57,9 +62,12 @@ inline bool readPCDXYZ (const char* name, std::vector<float>& xyz, std::vector<f
   int col[6] = {-1, -1, -1, -1, -1, -1};   // column (in scalar elements) of x y z normal_x normal_y normal_z
   int off[6] = {-1, -1, -1, -1, -1, -1};   // byte offset inside a binary record
   int ncols = 0, rec = 0;
+  int rgb_col = -1, rgb_off = -1;
+  char rgb_type = 'F';
   static const char* want[6] = {"x", "y", "z", "normal_x", "normal_y", "normal_z"};
   for (size_t f = 0; f < fields.size (); ++f)
   {
+    if ((fields[f] == "rgb" || fields[f] == "rgba") && size[f] == 4) { rgb_col = ncols; rgb_off = rec; rgb_type = type[f]; }
     for (int w = 0; w < 6; ++w)
       if (fields[f] == want[w] && size[f] == 4 && type[f] == 'F') { col[w] = ncols; off[w] = rec; }
     ncols += count[f];
@@ -67,8 +75,10 @@ inline bool readPCDXYZ (const char* name, std::vector<float>& xyz, std::vector<f
   }
   if (col[0] < 0 || col[1] < 0 || col[2] < 0) { if (error) *error = "PCD file without float x, y, z fields"; return false; }
   const bool have_n = normals && col[3] >= 0 && col[4] >= 0 && col[5] >= 0;
+  const bool have_rgb = rgb && rgb_col >= 0;
   xyz.resize ((size_t) points * 3);
   if (have_n) normals->resize ((size_t) points * 3);
+  if (have_rgb) rgb->resize ((size_t) points);
   if (data_mode == "ascii")
   {
     std::vector<double> row (ncols);
@@ -84,6 +94,13 @@ inline bool readPCDXYZ (const char* name, std::vector<float>& xyz, std::vector<f
       }
       for (int a = 0; a < 3; ++a) xyz[3 * (size_t) p + a] = (float) row[col[a]];
       if (have_n) for (int a = 0; a < 3; ++a) (*normals)[3 * (size_t) p + a] = (float) row[col[3 + a]];
+      if (have_rgb)
+      {
+        uint32_t bits;
+        if (rgb_type == 'F') { const float f = (float) row[rgb_col]; std::memcpy (&bits, &f, 4); }   // PCL prints the float whose bits are the colour
+        else bits = (uint32_t) row[rgb_col];
+        (*rgb)[(size_t) p] = bits & 0x00ffffffu;
+      }
     }
     return true;
   }
@@ -102,6 +119,7 @@ inline bool readPCDXYZ (const char* name, std::vector<float>& xyz, std::vector<f
     const char* r = buf.data () + (size_t) p * rec;
     for (int a = 0; a < 3; ++a) std::memcpy (&xyz[3 * (size_t) p + a], r + off[a], 4);
     if (have_n) for (int a = 0; a < 3; ++a) std::memcpy (&(*normals)[3 * (size_t) p + a], r + off[3 + a], 4);
+    if (have_rgb) { uint32_t bits; std::memcpy (&bits, r + rgb_off, 4); (*rgb)[(size_t) p] = bits & 0x00ffffffu; }
   }
   return true;
 }

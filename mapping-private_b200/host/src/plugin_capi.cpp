@@ -187,6 +187,14 @@ int capi_pcd_read(const char* name, float* xyz, float* nrm, int cap, int* has_no
     }
   return n;
 }
+// packed colours of a PCD file (0x00RRGGBB per point): returns the number of points, 0 if the file has no rgb field, -1 on failure
+int capi_pcd_read_rgb(const char* name, unsigned* rgb, int cap) {
+  std::vector<float> p;
+  std::vector<uint32_t> c;
+  if (!readPCDXYZ(name, p, 0, 0, &c)) return -1;
+  for (size_t i = 0; i < c.size() && (int)i < cap; ++i) rgb[i] = c[i];
+  return (int)c.size();
+}
 int capi_write_feature(const char* name, const float* data, int hist_num, int dim, int remove_0) {
   std::vector<std::vector<float> > f(hist_num, std::vector<float>(dim));
   for (int h = 0; h < hist_num; ++h) f[h].assign(data + (size_t)h * dim, data + (size_t)(h + 1) * dim);

@@ -52,6 +52,7 @@ def lib():
         L.capi_out_points.argtypes = [C.c_void_p, C.c_int]
         L.capi_list_requires.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.capi_pcd_read.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.capi_pcd_read_rgb.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
         L.capi_write_feature.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.capi_extract_euclidean_clusters.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_uint,
                                                       C.c_void_p, C.c_void_p]
@@ -85,6 +86,19 @@ def pcd_read(path: str):
     nrm = np.zeros((max(n, 1), 3), np.float32)
     L.capi_pcd_read(str(path).encode(), xyz.ctypes.data_as(C.POINTER(C.c_float)), nrm.ctypes.data_as(C.POINTER(C.c_float)), n, C.byref(has))
     return xyz[:n], (nrm[:n] if has.value else None)
+
+
+def pcd_read_rgb(path: str):
+    """Packed 0x00RRGGBB colours of a PCD file with an rgb field (uint32 (n,)), None if it has none."""
+    L = lib()
+    n = L.capi_pcd_read_rgb(str(path).encode(), None, 0)
+    if n < 0:
+        raise IOError(f"cannot read {path}")
+    if n == 0:
+        return None
+    rgb = np.zeros(n, np.uint32)
+    L.capi_pcd_read_rgb(str(path).encode(), rgb.ctypes.data, n)
+    return rgb
 
 
 def write_feature(path: str, feature: np.ndarray, remove_0: bool = True):

@@ -22,9 +22,11 @@ def built():
     return plugin.LIB_PATH
 
 
-def _write_pcd(path, xyz, normals=None, mode="binary", padded=False, extra_int=False):
+def _write_pcd(path, xyz, normals=None, mode="binary", padded=False, extra_int=False, rgb=None):
     n = len(xyz)
     fields, size, typ, cols = ["x", "y", "z"], ["4"] * 3, ["F"] * 3, [xyz.astype("<f4")]
+    if rgb is not None:  # PCL's packed colour: a float field whose bits are 0x00RRGGBB (the shipped shape_data layout: x y z rgb)
+        fields.append("rgb"); size.append("4"); typ.append("F"); cols.append(np.asarray(rgb, "<u4")[:, None].view("<f4"))
     if extra_int:  # an unrelated int32 column between the coordinates and the normals
         fields.append("idx"); size.append("4"); typ.append("I"); cols.append(np.arange(n, dtype="<i4")[:, None].view("<f4"))
     if normals is not None:
@@ -107,3 +109,48 @@ def test_compute_grsd_tool_against_oracle(built, oracle, kat, tmp_path):
         assert np.array_equal(vals.astype(np.int64), np.array(rows))
     r = subprocess.run([str(TOOL), str(tmp_path / "nope.pcd"), "0.01", str(tmp_path / "x.pcd")], capture_output=True, text=True)
     assert r.returncode != 0 and "Couldn't read file" in r.stderr
+
+
+def test_pcd_reader_rgb(built, tmp_path):
+    rng = np.random.default_rng(1)
+    xyz = rng.normal(size=(100, 3)).astype(np.float32)
+    rgb = (rng.integers(1, 256, 100).astype(np.uint32) << 16) | (rng.integers(0, 256, 100).astype(np.uint32) << 8) | 7
+    for mode, padded in (("binary", True), ("binary", False), ("ascii", False)):
+        p = tmp_path / f"rgb_{mode}_{padded}.pcd"
+        _write_pcd(p, xyz, None, mode, padded, rgb=rgb)
+        assert np.array_equal(plugin.pcd_read(p)[0].view(np.uint32), xyz.view(np.uint32))
+        assert np.array_equal(plugin.pcd_read_rgb(p), rgb), mode
+    _write_pcd(tmp_path / "plain.pcd", xyz)
+    assert plugin.pcd_read_rgb(tmp_path / "plain.pcd") is None
+
+
+@pytest.mark.gpu
+def test_compute_grsd_tool_colour_modes(built, oracle, tmp_path):
+    """exampleVOSCH.cpp / example_GRSD_CCHLAC.cpp on the reference's shipped cube and sphere clouds (x y z rgb, page-padded
+    binary): the colour part against the reference's own *_GRSD_CCHLAC.pcd values, the VOSCH vector against the oracle."""
+    d = np.load(ROOT / "tests" / "golden" / "shape_data_vosch.npz")
+    for shape, color in (("cube", "purple"), ("sphere", "orange")):
+        xyz = d[f"noiseless_{shape}_xyz"]
+        rgb = np.full(len(xyz), d[f"noiseless_{shape}_{color}_rgb"], np.uint32)
+        src = tmp_path / f"{shape}_{color}.pcd"
+        _write_pcd(src, xyz, None, "binary", padded=True, rgb=rgb)
+        out = tmp_path / "out.pcd"
+        r = subprocess.run([str(TOOL), str(src), "0.01", str(out), "-kind", "cchlac"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        vals = np.loadtxt(out, skiprows=9).reshape(-1, 117)[0]
+        gold = d[f"noiseless_{shape}_{color}_vosch137"][20:].astype(np.float64)
+        vals[:6] *= 0.5  # the shipped files' revision halved the 0th-order bins
+        vals[63:69] *= 0.5
+        assert np.all(np.abs(vals - gold) <= 1.1e-6 * np.maximum(1.0, np.abs(gold)))  # both sides printed with %f
+        r = subprocess.run([str(TOOL), str(src), "0.01", str(out), "-kind", "vosch"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        vosch = np.loadtxt(out, skiprows=9).reshape(-1, 137)[0]
+        want = oracle.grsd_cluster(xyz, 0.01, oracle.SIG_GRSD21)
+        assert np.array_equal(vosch[:20].astype(np.int64), want["hist"][0][:20])
+        grid = oracle.voxel_grid(xyz, 0.01)
+        grid["leaf"] = 0.01
+        _, _, h = oracle.color_chlac117(grid, oracle.voxel_colors(xyz, rgb, 0.01), c3=True)
+        assert np.all(np.abs(vosch[20:] - h[0].astype(np.float64)) <= 5.1e-7 * np.maximum(1.0, np.abs(h[0])))
+    _write_pcd(tmp_path / "nocolor.pcd", d["noiseless_sphere_xyz"])
+    r = subprocess.run([str(TOOL), str(tmp_path / "nocolor.pcd"), "0.01", str(tmp_path / "x.pcd"), "-kind", "vosch"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no rgb field" in r.stderr
