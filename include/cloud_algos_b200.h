@@ -50,8 +50,8 @@ typedef struct cab_timings {
   int64_t neighbour_sum; /* sum over queries of in-radius neighbours of the last normals/rsd pass */
   int64_t candidate_sum; /* sum over queries of candidates tested in that pass */
   int64_t kernel_launches; /* kernels launched by this library since cab_create (own + CUB) */
-  int64_t n_sorted; /* points radix-sorted by the last cab_build_grid: n_valid, or only the shard's own cells
-                       plus the cells its halo needs when the context is one shard of several (cab_set_shard) */
+  int64_t n_sorted; /* points radix-sorted by the last cab_build_grid: n_valid, or only the rows the shard, its halo
+                       and their candidates lie in when the context is one shard of several (cab_set_shard) */
   float knn_ms;       /* last cab_knn_mean_distance / cab_statistical_outliers: all grid rounds */
   int32_t knn_rounds; /* grids built by it (the cell edge doubles until every query has its k neighbours) */
   float pfh_ms;       /* last cab_pfh: pair-feature, averaging and finishing kernels */
@@ -85,10 +85,11 @@ int cab_set_cloud_device(cab_ctx* ctx, const float* d_xyz, int64_t n, int32_t st
 int cab_build_grid(cab_ctx* ctx, float cell);
 
 /* Query sharding for multi-GPU runs: this context only computes a contiguous range of the packets of
- * the sorted order (cost-balanced split, identical on every rank).  Default (0,1).  With world > 1 the
- * next cab_build_grid still builds the full cell table and packet list (they follow from the cell
- * histogram) but sorts only the points of the cells this shard reads; cab_download then returns this
- * shard's rows only -- use cab_download_sorted / CAB_OUT_SHARD_SORTED. */
+ * the sorted order (split by cost -- a rank's own packets in both passes plus the normals of the halo rows
+ * around them -- identical on every rank).  Default (0,1).  With world > 1 the next cab_build_grid still
+ * builds the full cell table and packet list (they follow from the cell histogram) but sorts only the
+ * points of the rows this shard reads; cab_download then returns this shard's rows only -- use
+ * cab_download_sorted / CAB_OUT_SHARD_SORTED. */
 int cab_set_shard(cab_ctx* ctx, int32_t rank, int32_t world);
 /* Sorted-order element range [begin, end) covered by this context's shard. */
 int cab_shard_range(const cab_ctx* ctx, int64_t* begin, int64_t* end);

@@ -259,7 +259,7 @@ void cab_destroy(cab_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->b_xyz, &ctx->b_domoff, &ctx->b_domid, &ctx->b_bounds, &ctx->b_domains, &ctx->b_keys[0],
-                    &ctx->b_keys[1], &ctx->b_keys[2], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_vals[2], &ctx->b_substart, &ctx->b_thr_flag, &ctx->b_knn_avg, &ctx->b_knn_done, &ctx->b_pfh[0], &ctx->b_pfh[1], &ctx->b_pfh[2], &ctx->b_cluster, &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
+                    &ctx->b_keys[1], &ctx->b_keys[2], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_vals[2], &ctx->b_thr_flag, &ctx->b_knn_avg, &ctx->b_knn_done, &ctx->b_pfh[0], &ctx->b_pfh[1], &ctx->b_pfh[2], &ctx->b_cluster, &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
                     &ctx->b_cellcnt, &ctx->b_cellstart, &ctx->b_rowpk, &ctx->b_packets, &ctx->b_nrm, &ctx->b_nrm_in,
                     &ctx->b_rsd, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
                     &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_halo_list, &ctx->b_rowflag, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
