@@ -182,10 +182,33 @@ def cpu_points_per_s(pts, nthreads=0):
 
     pyoracle.build()
     t0 = time.perf_counter()
-    n4, _ = pyoracle.normals(pts, RADIUS, nthreads=nthreads)
-    pyoracle.rsd(pts, n4, RADIUS, ndiv=NDIV, plane_radius=PLANE_RADIUS, nthreads=nthreads)
+    n4, k = pyoracle.normals(pts, RADIUS, nthreads=nthreads)
+    rmin, rmax, _ = pyoracle.rsd(pts, n4, RADIUS, ndiv=NDIV, plane_radius=PLANE_RADIUS, nthreads=nthreads)
     dt = time.perf_counter() - t0
+    cpu_points_per_s.last = (n4, k, rmin, rmax)  # kept for the parity gate of the same run
     return pts.shape[0] / dt, dt, pyoracle.num_threads() if nthreads <= 0 else nthreads
+
+
+def parity_gate(ctx, sample):
+    """the parity gates that go with every benchmark line.  The CUDA path on the slab the CPU baseline just
+    processed, against that run's oracle results: neighbour counts bit-exact, normals within 1e-4 rad (sign-insensitive),
+    radii within 1e-4 relative given the same normals.  The oracle is the checker here, nothing of it is timed."""
+    import numpy as np
+
+    o4, ok, omin, omax = cpu_points_per_s.last
+    ctx.upload(sample)
+    ctx.build_grid(RADIUS)
+    g4 = ctx.normals(RADIUS)
+    same_counts = int(ctx.profile()["neighbour_sum"]) == int(ok.sum())
+    good = ~np.isnan(o4[:, 0]) & ~np.isnan(g4[:, 0])
+    sin_angle = np.linalg.norm(np.cross(g4[good, :3].astype(np.float64), o4[good, :3].astype(np.float64)), axis=1)
+    ctx.set_normals(o4)
+    gmin, gmax = ctx.rsd(RADIUS, ndiv=NDIV, plane_radius=PLANE_RADIUS)
+    rel = np.maximum(np.abs(gmin - omin) / omin, np.abs(gmax - omax) / omax)
+    return {"sample_points": int(sample.shape[0]), "neighbour_counts_equal": bool(same_counts),
+            "nan_normals_equal": bool(np.array_equal(np.isnan(o4[:, 0]), np.isnan(g4[:, 0]))),
+            "normals_fraction_over_1e-4_rad": float(np.mean(sin_angle > 1e-4)), "normals_p99.9_rad": float(np.percentile(sin_angle, 99.9)),
+            "radii_max_rel_err_given_same_normals": float(np.nanmax(rel)), "mode": "fast-fp32 kernels vs fp64 oracle"}
 
 
 def run_reference(args, rank):
@@ -607,11 +630,16 @@ def main():
 
     # ---- CPU baseline (oracle port) on rank 0 at N = 1 ---------------------------------------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = slab_sample(pts, args.cpu_sample)
         rate, dt, cores = cpu_points_per_s(sample)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
                "sample": f"x-slab of the room cloud, {sample.shape[0]} points (same density), oracle normals+RSD streaming mode"}
+        try:
+            parity = parity_gate(ctx, sample)
+        except Exception as e:  # a failed gate must show up in the line, not kill the measurement
+            parity = {"error": repr(e)}
 
     if rank == 0:
         out = {
@@ -626,7 +654,7 @@ def main():
                        "host_affinity": (f"rank 0 bound to the {numa_cores} cores of its GPU's NUMA node" if numa_cores else "not bound")},
             "phases_ms": {"build": build_ms, "normals": nrm_ms, "rsd": rsd_ms},
             "per_rank_stage_ms": per_rank,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(json.dumps(out))
     if world > 1:
