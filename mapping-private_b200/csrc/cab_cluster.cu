@@ -92,10 +92,13 @@ __global__ void iota_kernel(int* __restrict__ v, int n) {
   if (i < n) v[i] = i;
 }
 
-// root of every point (written back: the forest becomes flat), size and smallest input index of every tree.
+// Root of every point, size and smallest input index of every tree.  The roots go to their own array: a root written
+// back into parent[s] could be overwritten by the path halving of a thread that walks through s at the same time (with
+// an ancestor it read earlier, not the root), and the kernels after this one need the root itself.
 // Lanes of a warp that share a root (the usual case: neighbours in the sorted order) combine before the atomics.
 __global__ void __launch_bounds__(256) cluster_stats_kernel(int* __restrict__ parent, const int* __restrict__ perm, int n_valid,
-                                                            int* __restrict__ size, int* __restrict__ min_idx) {
+                                                            int* __restrict__ root_of, int* __restrict__ size,
+                                                            int* __restrict__ min_idx) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = s < n_valid;
   const int root = in ? uf_find(parent, s) : -1 - (int)(threadIdx.x & 31);
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(256) cluster_stats_kernel(int* __restrict__ pa
   const unsigned peers = __match_any_sync(kFull, root);
   const int lo = __reduce_min_sync(peers, idx);
   if (in) {
-    parent[s] = root;
+    root_of[s] = root;
     if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
       atomicAdd(size + root, __popc(peers));
       atomicMin(min_idx + root, lo);
@@ -113,22 +116,22 @@ __global__ void __launch_bounds__(256) cluster_stats_kernel(int* __restrict__ pa
 
 // a kept tree marks its smallest input index: the exclusive prefix of the marks numbers the clusters in
 // the order the reference's seed loop would have found them
-__global__ void __launch_bounds__(256) cluster_seed_kernel(const int* __restrict__ parent, const int* __restrict__ size,
+__global__ void __launch_bounds__(256) cluster_seed_kernel(const int* __restrict__ root_of, const int* __restrict__ size,
                                                            const int* __restrict__ min_idx, int n_valid, int min_pts, int max_pts,
                                                            int* __restrict__ seed_flag) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_valid || parent[s] != s) return;
+  if (s >= n_valid || root_of[s] != s) return;
   const int sz = size[s];
   if (sz >= min_pts && (max_pts <= 0 || sz <= max_pts)) seed_flag[min_idx[s]] = 1;
 }
 
-__global__ void __launch_bounds__(256) cluster_label_kernel(const int* __restrict__ parent, const int* __restrict__ perm,
+__global__ void __launch_bounds__(256) cluster_label_kernel(const int* __restrict__ root_of, const int* __restrict__ perm,
                                                             const int* __restrict__ size, const int* __restrict__ min_idx,
                                                             const int* __restrict__ seed_rank, int n_valid, int min_pts,
                                                             int max_pts, int* __restrict__ labels) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_valid) return;
-  const int root = parent[s];
+  const int root = root_of[s];
   const int sz = size[root];
   labels[perm[s]] = (sz >= min_pts && (max_pts <= 0 || sz <= max_pts)) ? seed_rank[min_idx[root]] : -1;
 }
@@ -155,12 +158,13 @@ int64_t run_euclidean_clusters(cab_ctx* ctx, double tolerance, int min_pts, int 
   if (int rc = build_grid(ctx, tol)) return rc;
   const int nv = ctx->n_valid;
 
-  // parent | size | min_idx (sorted order), seed_flag | seed_rank (input order, n + 1), labels (input order)
+  // parent | root_of | size | min_idx (sorted order), seed_flag | seed_rank (input order, n + 1), labels (input order)
   const size_t n1 = (size_t)n + 1;
-  if (int rc = reserve(ctx, ctx->b_cluster, (3 * (size_t)std::max(nv, 1) + 2 * n1 + (size_t)n) * sizeof(int))) return rc;
+  if (int rc = reserve(ctx, ctx->b_cluster, (4 * (size_t)std::max(nv, 1) + 2 * n1 + (size_t)n) * sizeof(int))) return rc;
   if (int rc = reserve(ctx, ctx->b_stats, kStatBytes)) return rc;
   int* parent = (int*)ctx->b_cluster.p;
-  int* size = parent + std::max(nv, 1);
+  int* root_of = parent + std::max(nv, 1);
+  int* size = root_of + std::max(nv, 1);
   int* min_idx = size + std::max(nv, 1);
   int* seed_flag = min_idx + std::max(nv, 1);
   int* seed_rank = seed_flag + n1;
@@ -196,13 +200,13 @@ int64_t run_euclidean_clusters(cab_ctx* ctx, double tolerance, int min_pts, int 
       CAB_LAUNCH_CHECK(ctx);
     }
     const unsigned gv = (unsigned)((nv + 255) / 256);
-    cluster_stats_kernel<<<gv, 256, 0, st>>>(parent, (const int*)ctx->b_perm.p, nv, size, min_idx);
+    cluster_stats_kernel<<<gv, 256, 0, st>>>(parent, (const int*)ctx->b_perm.p, nv, root_of, size, min_idx);
     CAB_LAUNCH_CHECK(ctx);
-    cluster_seed_kernel<<<gv, 256, 0, st>>>(parent, size, min_idx, nv, min_pts, max_pts, seed_flag);
+    cluster_seed_kernel<<<gv, 256, 0, st>>>(root_of, size, min_idx, nv, min_pts, max_pts, seed_flag);
     CAB_LAUNCH_CHECK(ctx);
     CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_scan, seed_flag, seed_rank, (int)n1, st));
     ctx->tm.kernel_launches += 2;
-    cluster_label_kernel<<<gv, 256, 0, st>>>(parent, (const int*)ctx->b_perm.p, size, min_idx, seed_rank, nv, min_pts, max_pts, labels);
+    cluster_label_kernel<<<gv, 256, 0, st>>>(root_of, (const int*)ctx->b_perm.p, size, min_idx, seed_rank, nv, min_pts, max_pts, labels);
     CAB_LAUNCH_CHECK(ctx);
   } else {
     CAB_CUDA(ctx, cudaMemsetAsync(seed_rank, 0, n1 * sizeof(int), st));
