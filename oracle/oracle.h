@@ -86,7 +86,8 @@ int orc_rsd_ref_faithful(const float* xyz, const float* normals, int normal_stri
 /* pcl::VoxelGrid with setSaveLeafLayout(true) [EXTERNAL], as used at
  * grsd_colorCHLAC_tools.hpp:94-100.  Call with centroids == NULL to get sizes.
  *   min_b[3], div_b[3]; returns number of occupied voxels V.
- *   centroids: V x 3 (mean xyz, voxels ordered by linear index x-fastest)
+ *   centroids: V x 3 (mean xyz = fp32 sum in cloud order times 1.0f / count, the Eigen 3.0-3.2 `/=` of the
+ *              reference's era, pinned by its shipped feature vectors; voxels ordered by linear index x-fastest)
  *   layout: div_b[0]*div_b[1]*div_b[2] ints, voxel -> centroid index or -1
  *   counts: V point counts (optional) */
 int orc_voxel_grid(const float* xyz, int n, float leaf, int32_t* min_b, int32_t* div_b,
@@ -127,8 +128,8 @@ int orc_grsd21_subdiv(const float* centroids, int nvox, const int32_t* types, fl
 
 /* Mean normal of every voxel.  pcl::VoxelGrid with downsample_all_data averages every field of
  * the point type, the normals included, and does not re-normalise them (comment at
- * grsd_colorCHLAC_tools.hpp:558) [EXTERNAL].  out: V x 3 = (float)(sum_double / count), summed in
- * (voxel, input index) order; voxel order as orc_voxel_grid.  Returns V. */
+ * grsd_colorCHLAC_tools.hpp:558) [EXTERNAL].  out: V x 3 = fp32 sum in (voxel, input index) order times
+ * 1.0f / count (the arithmetic of orc_voxel_grid's centroids); voxel order as orc_voxel_grid.  Returns V. */
 int orc_voxel_normals(const float* xyz, const float* normals, int normal_stride, int n, float leaf,
                       float* out);
 
