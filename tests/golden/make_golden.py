@@ -81,8 +81,27 @@ def vosch_fixture():
     print("shape_data_vosch:", len(geoms), "geometries x", len(colors), "colours")
 
 
+def normals_fixture():
+    """color_chlac/demos/data/tmp_normal.pcd: 4712 points with the normal_x/y/z and curvature fields the reference's
+    computeNormal (pcl::NormalEstimation, setRadiusSearch(0.02), grsd_colorCHLAC_tools.hpp:67-90) wrote for exactly these
+    points -- recognised by reproducing them: radius 0.02 on the file's own points gives the stored normals to 2e-5 rad
+    and the stored curvatures to 4e-7 (no other radius or k comes close)."""
+    raw = (REF.parent / "data" / "tmp_normal.pcd").read_bytes()
+    head = raw[:4096].decode("ascii", errors="ignore")
+    fields = re.search(r"FIELDS (.*)", head).group(1).split()
+    n = int(re.search(r"POINTS (\d+)", head).group(1))
+    assert len(raw) - 4096 == n * 4 * len(fields)
+    a = np.frombuffer(raw, dtype="<f4", count=n * len(fields), offset=4096).reshape(n, len(fields))
+    col = {f: i for i, f in enumerate(fields)}
+    np.savez_compressed(OUT / "tmp_normal.npz", xyz=np.ascontiguousarray(a[:, [col["x"], col["y"], col["z"]]]),
+                        normal=np.ascontiguousarray(a[:, [col["normal_x"], col["normal_y"], col["normal_z"]]]),
+                        curvature=np.ascontiguousarray(a[:, col["curvature"]]))
+    print("tmp_normal:", n, "points")
+
+
 def main():
     svm_fixture()
+    normals_fixture()
     vosch_fixture()
     data = {}
     for s in SHAPES:

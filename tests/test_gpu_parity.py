@@ -527,3 +527,22 @@ def test_grid_build_layouts_agree(ctx, oracle, n):
             ctx.set_shard(0, 1)
         o4, _ = oracle.normals(pts, r)
         assert np.array_equal(np.isnan(s4[:, 0]), np.isnan(o4[sidx, 0]))
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_normals_against_the_references_own_output(ctx, ctx_exact, exact):
+    """The device normals against the normals and curvatures the reference itself wrote into
+    color_chlac/demos/data/tmp_normal.pcd (computeNormal, radius 0.02, viewpoint 0; tests/golden/tmp_normal.npz)."""
+    import pathlib
+
+    g = np.load(pathlib.Path(__file__).resolve().parent / "golden" / "tmp_normal.npz")
+    xyz, ref_n, ref_c = g["xyz"], g["normal"], g["curvature"]
+    c = ctx_exact if exact else ctx
+    c.set_shard(0, 1)
+    c.upload(xyz)
+    c.build_grid(0.02)
+    n4 = c.normals(0.02)
+    assert (np.sum(n4[:, :3].astype(np.float64) * ref_n, axis=1) > 0).all()  # same side of the surface everywhere
+    ang = _angle(n4[:, :3], ref_n)
+    assert np.sum(ang > 1e-4) <= 2 and np.percentile(ang, 99.9) < 5e-5
+    assert np.abs(n4[:, 3] - ref_c).max() < (1e-6 if exact else 2e-5)

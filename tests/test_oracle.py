@@ -2,11 +2,15 @@
 known answers for normals and RSD radii, the get_type truth table, hand-built voxel blocks,
 subdivision cases and the known answers decoded from the reference's shape_data goldens
 (tests/golden/make_golden.py)."""
+import pathlib
+
 import numpy as np
 import pytest
 from scipy.spatial import cKDTree
 
 from mapping_private_b200 import synth
+
+GOLDEN = pathlib.Path(__file__).resolve().parent / "golden"
 
 
 def _sets(off, idx):
@@ -457,3 +461,22 @@ def test_grsd_cluster_recipe_all_kinds(oracle):
     occupied = r21["hist"][0].sum() - r21["hist"][0][[5, 10, 14, 17, 19]].sum()
     assert r325["hist"].sum() * 2 >= occupied  # 21 drops the below-diagonal ordered pairs
     assert r110["hist_num"] == int(np.prod(r110["subdiv_b"])) and r110["hist"].shape[1] == 110
+
+
+def test_normals_against_the_references_own_output(oracle):
+    """color_chlac/demos/data/tmp_normal.pcd carries the normals and curvatures the reference's computeNormal
+    (pcl::NormalEstimation, radius 0.02, viewpoint 0) wrote for its 4712 points (mean 273 neighbours each): the oracle
+    reproduces them -- direction AND sign -- which pins the neighbour rule, the PCA, curvature = l0 / (l0 + l1 + l2) and
+    the flip towards the viewpoint against the reference itself."""
+    g = np.load(GOLDEN / "tmp_normal.npz")
+    xyz, ref_n, ref_c = g["xyz"], g["normal"], g["curvature"]
+    n4, k = oracle.normals(xyz, 0.02)
+    assert k.min() >= 3 and 250 < k.mean() < 300
+    sin_angle = np.linalg.norm(np.cross(n4[:, :3].astype(np.float64), ref_n.astype(np.float64)), axis=1)
+    assert (np.sum(n4[:, :3].astype(np.float64) * ref_n, axis=1) > 0).all()  # flipNormalTowardsViewpoint agrees everywhere
+    assert np.sum(sin_angle > 1e-4) <= 1 and sin_angle.max() < 2e-4  # one point of curvature 0.18 (lambda0 close to lambda1)
+    assert np.percentile(sin_angle, 99.9) < 3e-5
+    assert np.abs(n4[:, 3] - ref_c).max() < 1e-6
+    # and it is this recipe, not a neighbouring one
+    for other in (oracle.normals(xyz, 0.03)[0], oracle.normals_knn(xyz, 30)):
+        assert np.median(np.linalg.norm(np.cross(other[:, :3].astype(np.float64), ref_n.astype(np.float64)), axis=1)) > 1e-2
