@@ -189,6 +189,39 @@ def cpu_points_per_s(pts, nthreads=0):
     return pts.shape[0] / dt, dt, pyoracle.num_threads() if nthreads <= 0 else nthreads
 
 
+def c1_reference_faithful(ctx):
+    """BASELINE config C1 (the reference's own CPU-runnable case: sample_pipeline's RSD on a 100 k-point tabletop cloud,
+    r = 2 cm, the plugin's default max_nn = 150) the way the reference runs it -- kd-tree, materialised neighbour lists,
+    estimation loop, ONE thread, the three phases timed where radius_estimation.cpp:108,125,216 log them -- next to the
+    same call through the C ABI (upload + grid + thresholds + RSD + download, host buffers).  A reported baseline."""
+    import numpy as np
+
+    import pyoracle
+    from mapping_private_b200 import synth
+
+    pts = synth.tabletop(100_000)
+    n4, _ = pyoracle.normals(pts, RADIUS)
+    nrm = np.ascontiguousarray(n4[:, :3])
+    t0 = time.perf_counter()
+    omin, omax, phases = pyoracle.rsd_ref_faithful(pts, nrm, RADIUS, max_nn=150, ndiv=NDIV, plane_radius=PLANE_RADIUS)
+    cpu_s = time.perf_counter() - t0
+    ctx.upload(pts)  # warm-up of this size
+    ctx.build_grid(RADIUS)
+    ctx.set_normals(n4)
+    ctx.rsd(RADIUS, max_nn=150, ndiv=NDIV, plane_radius=PLANE_RADIUS)
+    t0 = time.perf_counter()
+    ctx.upload(pts)
+    ctx.build_grid(RADIUS)
+    ctx.set_normals(n4)
+    gmin, gmax = ctx.rsd(RADIUS, max_nn=150, ndiv=NDIV, plane_radius=PLANE_RADIUS)
+    gpu_s = time.perf_counter() - t0
+    rel = float(np.nanmax(np.maximum(np.abs(gmin - omin) / omin, np.abs(gmax - omax) / omax)))
+    return {"workload": "C1 100k-point synthetic tabletop, RSD r=2cm, max_nn=150 (plugin default), normals given",
+            "cpu_points_per_s": pts.shape[0] / cpu_s, "cpu_cores": 1, "cpu_kind": "port, reference-faithful organisation",
+            "cpu_phases_s": {"kdtree_build": float(phases[0]), "neighbour_search": float(phases[1]), "estimation": float(phases[2])},
+            "b200_points_per_s_e2e": pts.shape[0] / gpu_s, "b200_ms_e2e": 1e3 * gpu_s, "radii_max_rel_err": rel}
+
+
 def parity_gate(ctx, sample):
     """the parity gates that go with every benchmark line.  The CUDA path on the slab the CPU baseline just
     processed, against that run's oracle results: neighbour counts bit-exact, normals within 1e-4 rad (sign-insensitive),
@@ -640,6 +673,10 @@ def main():
             parity = parity_gate(ctx, sample)
         except Exception as e:  # a failed gate must show up in the line, not kill the measurement
             parity = {"error": repr(e)}
+        try:
+            cpu["c1_reference_faithful"] = c1_reference_faithful(ctx)
+        except Exception as e:
+            cpu["c1_reference_faithful"] = {"error": repr(e)}
 
     if rank == 0:
         out = {
