@@ -146,7 +146,10 @@ int cab_grsd_batch(cab_ctx* ctx, const float* xyz, int32_t stride, const int32_t
                    int32_t rsd_flags, const float vp[3], const float* nx, const float* ny,
                    const float* nz, int32_t* hist21);
 /* Per-voxel results of the last cab_grsd_batch (voxels ordered by cluster, then linear voxel
- * index).  vox_offsets: nclusters+1. Any pointer may be NULL. Returns total voxels. */
+ * index).  vox_offsets: nclusters+1. Any pointer may be NULL. Returns total voxels.
+ * Centroids follow pcl::VoxelGrid of the reference's era: fp32 sums in cloud order times 1.0f / count (Eigen 3.0-3.2's
+ * `/=`), and getNeighborCentroidIndices looks a centroid's voxel up by floor(c / leaf) -- both pinned by the reference's
+ * shipped color_chlac/demos/shape_data vectors. */
 int64_t cab_grsd_voxels(cab_ctx* ctx, int64_t* vox_offsets, float* centroids_xyz, float* r_min,
                         float* r_max, int32_t* labels, int64_t cap);
 
