@@ -56,6 +56,8 @@ typedef struct cab_timings {
   int32_t knn_rounds; /* grids built by it (the cell edge doubles until every query has its k neighbours) */
   float pfh_ms;       /* last cab_pfh: pair-feature, averaging and finishing kernels */
   float cluster_ms;   /* last cab_euclidean_clusters: union, statistics and labelling kernels (without the grid build) */
+  float exchange_ms;  /* last cab_step_normals_rsd of a group: end of the RSD kernel -> every rank's results have arrived */
+  float step_ms;      /* last cab_step_normals_rsd: first kernel of the build -> end of the step, on the device */
 } cab_timings;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
@@ -84,15 +86,17 @@ int cab_set_cloud_device(cab_ctx* ctx, const float* d_xyz, int64_t n, int32_t st
  * indexed with coarser cells -- same results, more candidates tested per query. */
 int cab_build_grid(cab_ctx* ctx, float cell);
 
-/* Query sharding for multi-GPU runs: this context only computes a contiguous range of the packets of
- * the sorted order (split by cost -- a rank's own packets in both passes plus the normals of the halo rows
- * around them -- identical on every rank).  Default (0,1).  With world > 1 the next cab_build_grid still
- * builds the full cell table and packet list (they follow from the cell histogram) but sorts only the
- * points of the rows this shard reads; cab_download then returns this shard's rows only -- use
- * cab_download_sorted / CAB_OUT_SHARD_SORTED. */
+/* Query sharding for multi-GPU runs (the reference is single-threaded, radius_estimation.cpp:139): this
+ * context answers the queries of one slab of the cloud -- whole rows of the grid, cut so that every rank's cost (its
+ * own rows in both passes plus the normals of one layer of halo rows around them) is the same; the cuts follow from a
+ * fixed sample of the cloud and are identical on every rank.  Default (0,1).  With world > 1 the next cab_build_grid
+ * keys, sorts and tabulates only the rows this rank reads (own + halo + the halo's candidates): the device arrays
+ * (CAB_BUF_*) are then local to the slab, cab_download returns this shard's rows only -- use cab_download_sorted /
+ * CAB_OUT_SHARD_SORTED, or the cab_comm_* calls below, which concatenate the ranks' results.  Every shard's results
+ * equal the unsharded ones bit for bit.  One cloud only: a batch of clusters (cab_upload_clusters) shards by cluster. */
 int cab_set_shard(cab_ctx* ctx, int32_t rank, int32_t world);
-/* Sorted-order element range [begin, end) covered by this context's shard. */
-int cab_shard_range(const cab_ctx* ctx, int64_t* begin, int64_t* end);
+/* Element range [begin, end) of this context's own queries in its (local) sorted arrays. */
+int cab_shard_range(cab_ctx* ctx, int64_t* begin, int64_t* end);
 
 /* ---- normals -------------------------------------------------------------------------
  * Replaces pcl::NormalEstimation::compute with setRadiusSearch(r)
@@ -281,11 +285,63 @@ void* cab_stream(cab_ctx* ctx); /* cudaStream_t all work of this context is enqu
 /* Copy device results (sorted order) to host arrays in input order. Any pointer may be NULL. */
 int cab_download(cab_ctx* ctx, float* nxyz_curv, float* r_min, float* r_max);
 
+/* r_dif of the last cab_rsd in input order: (float)(max_radius - min_radius) with the subtraction in double, before the
+ * radii are rounded to float -- the value LocalRadiusEstimation stores in its r_dif channel (radius_estimation.cpp:206);
+ * r_max - r_min of the rounded outputs can differ from it in the last bit. */
+int cab_download_rdif(cab_ctx* ctx, float* r_dif);
+
 /* Copy the sorted-order slice [begin, end) of the results to host: normals (4 floats per point),
  * radii (2 floats: r_min, r_max) and the sorted-position -> input-index map.  Any pointer may be
  * NULL.  A rank of a sharded run downloads its own cab_shard_range this way. */
 int cab_download_sorted(cab_ctx* ctx, int64_t begin, int64_t end, float* nxyz_curv, float* rmin_rmax,
                         int32_t* input_index);
+
+/* ---- one step, one call ------------------------------------------------------------------
+ * cab_build_grid(cell) + cab_normals((float)r) + cab_rsd(r) on the cloud last given to cab_upload_cloud /
+ * cab_set_cloud_device / cab_comm_upload_cloud, enqueued back to back with one host synchronisation at the end instead
+ * of one per stage (the NormalEstimation -> LocalRadiusEstimation chain of cloud_algos/sample_pipeline.yaml as a frame
+ * loop would run it).  Results stay on the device (cab_download*, CAB_BUF_*).  When the context belongs to a group
+ * (cab_comm_init*), the step also concatenates the ranks' results: the RSD kernel stores every packet's normals, radii
+ * and input indices into every rank's copy of the concatenated arrays (peer memory over NVLink), so that when the call
+ * returns EVERY rank holds the results of ALL queries (cab_comm_device_ptr, cab_comm_download_range). */
+int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_normals, const float vp[3], int32_t max_nn_rsd,
+                         int32_t ndiv, double plane_radius, int32_t flags);
+
+/* ---- multi-GPU groups ---------------------------------------------------------------------
+ * One cab_ctx per GPU; the contexts of a group run the same calls in the same order (SPMD), each from its own host
+ * thread or process.  Joining a group also sets the shard (cab_set_shard(rank, world)).
+ *   cab_comm_init_local   contexts of ONE process (e.g. a plugin host with one worker thread per GPU): peer access
+ *                         between the devices, nothing else needed.
+ *   cab_comm_init         one process per GPU (the torchrun / MPI layout): rank 0 obtains an id with cab_comm_get_id
+ *                         (ncclGetUniqueId; libnccl.so.2 is loaded on first use), the application hands it to every
+ *                         rank, every rank calls cab_comm_init.  NCCL carries the bootstrap (CUDA IPC handles of the
+ *                         exchange buffers) and cab_comm_allreduce_i32; the data path uses peer memory directly.
+ *   cab_comm_reserve / cab_comm_connect   the same without NCCL: every rank reserves buffers for clouds of up to
+ *                         max_points points and gets a blob of CAB_COMM_BLOB_BYTES; the application gathers the blobs
+ *                         of all ranks (rank order) by whatever means it has and gives them to cab_comm_connect. */
+#define CAB_COMM_ID_BYTES 128
+#define CAB_COMM_BLOB_BYTES 512
+int cab_comm_get_id(char id[CAB_COMM_ID_BYTES]);
+int cab_comm_init(cab_ctx* ctx, const char id[CAB_COMM_ID_BYTES], int32_t rank, int32_t world);
+int cab_comm_init_local(cab_ctx** ctxs, int32_t world);
+int cab_comm_reserve(cab_ctx* ctx, int32_t rank, int32_t world, int64_t max_points, void* blob);
+int cab_comm_connect(cab_ctx* ctx, const void* blobs);
+int cab_comm_free(cab_ctx* ctx);
+/* Replicates a host cloud on every rank of the group: xyz points at the WHOLE cloud (n points, packed xyz) on every rank;
+ * a rank uploads rows [n*rank/world, n*(rank+1)/world) over its own PCIe link and copies them into the peers' buffers
+ * over NVLink (copy engines), then waits for the other slices.  Without a group: cab_upload_cloud. */
+int cab_comm_upload_cloud(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride);
+/* Results of the last cab_step_normals_rsd of the group for the input-order range [j0, j1) -- any range, on any rank:
+ * nxyz_curv (j1-j0) x 4, r_min / r_max (j1-j0) floats; any pointer may be NULL.  With j0 = n*rank/world, j1 =
+ * n*(rank+1)/world and pointers into ONE host array shared by the ranks, the ranks together leave the channels
+ * LocalRadiusEstimation appends (radius_estimation.cpp:204-214) in input order, each paying 1/world of the copy. */
+int cab_comm_download_range(cab_ctx* ctx, int64_t j0, int64_t j1, float* nxyz_curv, float* r_min, float* r_max);
+/* The concatenated arrays of the last exchanged step on this rank: CAB_BUF_NRM_SORTED / _RSD_SORTED / _PERM, *count
+ * entries (all finite points of the cloud, slab after slab). */
+void* cab_comm_device_ptr(cab_ctx* ctx, int32_t which, int64_t* count);
+/* In-place sum over the group of `count` int32 values in host memory: the integer histograms of GRSD batches sharded by
+ * cluster, or of one large cloud sharded by voxels (one small ncclAllReduce; bit-exact in any order). */
+int cab_comm_allreduce_i32(cab_ctx* ctx, int32_t* values, int64_t count);
 
 int cab_profile(const cab_ctx* ctx, cab_timings* out);
 int cab_version(void);

@@ -27,8 +27,11 @@ EXPORTS = [
     "cab_create", "cab_destroy", "cab_last_error", "cab_upload_cloud", "cab_upload_clusters",
     "cab_set_cloud_device", "cab_build_grid", "cab_set_shard", "cab_shard_range", "cab_normals",
     "cab_set_normals", "cab_rsd", "cab_normals_rsd", "cab_neighbors_debug", "cab_grsd_batch", "cab_grsd_voxels", "cab_grsd_signatures", "cab_color_chlac", "cab_svm_set_model", "cab_svm_set_scaling", "cab_svm_predict", "cab_svm_predict_grsd", "cab_knn_mean_distance", "cab_normals_knn", "cab_statistical_outliers", "cab_euclidean_clusters", "cab_cluster_csr", "cab_pfh",
-    "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_profile", "cab_version",
+    "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_download_rdif", "cab_profile", "cab_version",
+    "cab_step_normals_rsd", "cab_comm_get_id", "cab_comm_init", "cab_comm_init_local", "cab_comm_reserve", "cab_comm_connect",
+    "cab_comm_free", "cab_comm_upload_cloud", "cab_comm_download_range", "cab_comm_device_ptr", "cab_comm_allreduce_i32",
 ]
+COMM_ID_BYTES, COMM_BLOB_BYTES = 128, 512
 
 
 class CabError(RuntimeError):
@@ -46,6 +49,7 @@ class Timings(C.Structure):
         ("n_points", C.c_int64), ("n_valid", C.c_int64), ("n_packets", C.c_int64), ("n_rows", C.c_int64),
         ("n_cells", C.c_int64), ("neighbour_sum", C.c_int64), ("candidate_sum", C.c_int64),
         ("kernel_launches", C.c_int64), ("n_sorted", C.c_int64), ("knn_ms", C.c_float), ("knn_rounds", C.c_int32), ("pfh_ms", C.c_float), ("cluster_ms", C.c_float),
+        ("exchange_ms", C.c_float), ("step_ms", C.c_float),
     ]
 
     def as_dict(self):
@@ -81,6 +85,8 @@ def lib():
         L.cab_stream.restype = C.c_void_p
         L.cab_stream.argtypes = [C.c_void_p]
         L.cab_destroy.argtypes = [C.c_void_p]
+        L.cab_comm_device_ptr.restype = C.c_void_p
+        L.cab_comm_device_ptr.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]
         _LIB = L
     return _LIB
 
@@ -368,6 +374,61 @@ class Context:
         self._check(self._L.cab_svm_predict_grsd(self._h, _fp(out)), "cab_svm_predict_grsd")
         return out
 
+    # ---- one step, one call / multi-GPU groups ------------------------------------------
+    def step_normals_rsd(self, cell: float, r: float, max_nn_normals: int = 0, vp=(0.0, 0.0, 0.0), max_nn_rsd: int = 0,
+                         ndiv: int = 10, plane_radius: float = 0.1, flags: int = 0):
+        """Grid build + normals + RSD with one host synchronisation; in a group also the concatenation of the results."""
+        v = (C.c_float * 3)(*vp)
+        self._check(self._L.cab_step_normals_rsd(self._h, C.c_float(cell), C.c_double(r), C.c_int32(max_nn_normals), v,
+                                                 C.c_int32(max_nn_rsd), C.c_int32(ndiv), C.c_double(plane_radius), C.c_int32(flags)),
+                    "cab_step_normals_rsd")
+
+    def download_rdif(self):
+        out = np.empty(self.n, np.float32)
+        self._check(self._L.cab_download_rdif(self._h, _fp(out)), "cab_download_rdif")
+        return out
+
+    def comm_init(self, comm_id: bytes, rank: int, world: int):
+        assert len(comm_id) == COMM_ID_BYTES
+        self._check(self._L.cab_comm_init(self._h, C.c_char_p(comm_id), C.c_int32(rank), C.c_int32(world)), "cab_comm_init")
+
+    def comm_reserve(self, rank: int, world: int, max_points: int) -> bytes:
+        blob = C.create_string_buffer(COMM_BLOB_BYTES)
+        self._check(self._L.cab_comm_reserve(self._h, C.c_int32(rank), C.c_int32(world), C.c_int64(max_points), blob), "cab_comm_reserve")
+        return blob.raw
+
+    def comm_connect(self, blobs):
+        raw = b"".join(blobs)
+        self._check(self._L.cab_comm_connect(self._h, C.c_char_p(raw)), "cab_comm_connect")
+
+    def comm_free(self):
+        self._check(self._L.cab_comm_free(self._h), "cab_comm_free")
+
+    def comm_upload_cloud(self, xyz: np.ndarray):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        self._keep = xyz
+        self.n = xyz.shape[0]
+        self._check(self._L.cab_comm_upload_cloud(self._h, _fp(xyz), C.c_int64(self.n), C.c_int32(xyz.shape[1])), "cab_comm_upload_cloud")
+
+    def comm_download_range(self, j0: int, j1: int, normals: bool = True, rsd: bool = True):
+        m = j1 - j0
+        n4 = np.empty((m, 4), np.float32) if normals else None
+        rmin = np.empty(m, np.float32) if rsd else None
+        rmax = np.empty(m, np.float32) if rsd else None
+        self._check(self._L.cab_comm_download_range(self._h, C.c_int64(j0), C.c_int64(j1), _fp(n4), _fp(rmin), _fp(rmax)),
+                    "cab_comm_download_range")
+        return n4, rmin, rmax
+
+    def comm_device_ptr(self, which: int):
+        cnt = C.c_int64()
+        p = self._L.cab_comm_device_ptr(self._h, which, C.byref(cnt)) or 0
+        return p, cnt.value
+
+    def comm_allreduce_i32(self, values: np.ndarray):
+        assert values.dtype == np.int32 and values.flags.c_contiguous
+        self._check(self._L.cab_comm_allreduce_i32(self._h, _ip(values), C.c_int64(values.size)), "cab_comm_allreduce_i32")
+        return values
+
     # ---- plumbing --------------------------------------------------------------------
     def device_ptr(self, which: int) -> int:
         return self._L.cab_device_ptr(self._h, which) or 0
@@ -379,3 +440,20 @@ class Context:
         t = Timings()
         self._check(self._L.cab_profile(self._h, C.byref(t)), "cab_profile")
         return t.as_dict()
+
+
+def comm_get_id() -> bytes:
+    """ncclGetUniqueId through the C ABI: rank 0 calls it, the application hands the 128 bytes to every rank."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = lib().cab_comm_get_id(buf)
+    if rc != 0:
+        raise CabError(f"cab_comm_get_id failed ({rc}): {lib().cab_last_error(None).decode()}")
+    return buf.raw
+
+
+def comm_init_local(contexts):
+    """Links the contexts of this process into one group (rank = position in the list)."""
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    rc = lib().cab_comm_init_local(arr, C.c_int32(len(contexts)))
+    if rc != 0:
+        raise CabError(f"cab_comm_init_local failed ({rc})")

@@ -60,8 +60,8 @@ int reserve_pinned(cab_ctx* ctx, size_t bytes) {
   return CAB_OK;
 }
 
-void read_stats(cab_ctx* ctx) {
-  const unsigned long long* h = (const unsigned long long*)ctx->h_pin;
+void read_stats(cab_ctx* ctx, const void* staged) {
+  const unsigned long long* h = (const unsigned long long*)(staged ? staged : ctx->h_pin);
   unsigned long long ks = 0, cs = 0;
   for (int i = 0; i < kStatSlots; ++i) {
     ks += h[2 * i];
@@ -97,6 +97,14 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const int* __restrict__ 
     out_a[j] = v.x;
     out_b[j] = v.y;
   }
+}
+
+__global__ void __launch_bounds__(256) unpermute_scalar_kernel(const int* __restrict__ perm, int count,
+                                                               const float* __restrict__ in, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int j = perm[i];
+  if (j >= 0) out[j] = in[i];
 }
 
 int set_domains(cab_ctx* ctx, int64_t n, const int32_t* offsets, int nclusters) {
@@ -161,9 +169,12 @@ int permute_normals_in(cab_ctx* ctx, const float* nx, const float* ny, const flo
     CAB_CUDA(ctx, cudaMemcpyAsync(d, nx, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CAB_CUDA(ctx, cudaMemcpyAsync(d + n, ny, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CAB_CUDA(ctx, cudaMemcpyAsync(d + 2 * (size_t)n, nz, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    gather_normals_kernel<<<(n + 255) / 256, 256, 0, st>>>(d, d + n, d + 2 * (size_t)n, (const int*)ctx->b_perm.p, n,
-                                                           (float4*)ctx->b_nrm.p);
-    CAB_LAUNCH_CHECK(ctx);
+    const int ns = (int)ctx->n_sorted;
+    if (ns > 0) {
+      gather_normals_kernel<<<(ns + 255) / 256, 256, 0, st>>>(d, d + n, d + 2 * (size_t)n, (const int*)ctx->b_perm.p, ns,
+                                                              (float4*)ctx->b_nrm.p);
+      CAB_LAUNCH_CHECK(ctx);
+    }
   }
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->have_normals = true;
@@ -172,6 +183,7 @@ int permute_normals_in(cab_ctx* ctx, const float* nx, const float* ny, const flo
 
 int download_results(cab_ctx* ctx, float* n4, float* rmin, float* rmax) {
   const int n = (int)ctx->n;
+  const int ns = (int)ctx->n_sorted;  // entries of the sorted arrays (a slab holds fewer than n)
   cudaStream_t st = ctx->stream;
   if ((rmin == nullptr) != (rmax == nullptr)) return fail(ctx, CAB_ERR_ARG, "r_min and r_max must be given together");
   if (n4 && !ctx->have_normals) return fail(ctx, CAB_ERR_STATE, "no normals to download");
@@ -184,11 +196,20 @@ int download_results(cab_ctx* ctx, float* n4, float* rmin, float* rmax) {
     if (int rc = reserve(ctx, ctx->b_out1b, (size_t)n * sizeof(float))) return rc;
   }
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
-  unpermute_kernel<<<(n + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, 0, n, (const float4*)ctx->b_nrm.p,
-                                                    (const float2*)ctx->b_rsd.p, n4 ? (float4*)ctx->b_out4.p : nullptr,
-                                                    rmin ? (float*)ctx->b_out1a.p : nullptr,
-                                                    rmin ? (float*)ctx->b_out1b.p : nullptr);
-  CAB_LAUNCH_CHECK(ctx);
+  if (ctx->slab) {  // rows of other shards: untouched device memory must not reach the caller
+    if (n4) CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_out4.p, 0, (size_t)n * sizeof(float4), st));
+    if (rmin) {
+      CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_out1a.p, 0, (size_t)n * sizeof(float), st));
+      CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_out1b.p, 0, (size_t)n * sizeof(float), st));
+    }
+  }
+  if (ns > 0) {
+    unpermute_kernel<<<(ns + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, 0, ns, (const float4*)ctx->b_nrm.p,
+                                                     (const float2*)ctx->b_rsd.p, n4 ? (float4*)ctx->b_out4.p : nullptr,
+                                                     rmin ? (float*)ctx->b_out1a.p : nullptr,
+                                                     rmin ? (float*)ctx->b_out1b.p : nullptr);
+    CAB_LAUNCH_CHECK(ctx);
+  }
   if (n4) CAB_CUDA(ctx, cudaMemcpyAsync(n4, ctx->b_out4.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, st));
   if (rmin) {
     CAB_CUDA(ctx, cudaMemcpyAsync(rmin, ctx->b_out1a.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -244,6 +265,12 @@ int cab_create(const cab_config* cfg, cab_ctx** out) {
   }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming);
+  if (cudaMallocHost((void**)&ctx->h_step, kStepBytes) != cudaSuccess) {
+    cudaGetLastError();
+    g_create_err = "cudaMallocHost failed";
+    cab_destroy(ctx);
+    return CAB_ERR_OOM;
+  }
   if (reserve_pinned(ctx, 1 << 16) != CAB_OK) {
     g_create_err = ctx->err;
     cab_destroy(ctx);
@@ -261,14 +288,16 @@ void cab_destroy(cab_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->b_xyz, &ctx->b_domoff, &ctx->b_domid, &ctx->b_bounds, &ctx->b_domains, &ctx->b_keys[0],
                     &ctx->b_keys[1], &ctx->b_keys[2], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_vals[2], &ctx->b_thr_flag, &ctx->b_knn_avg, &ctx->b_knn_done, &ctx->b_pfh[0], &ctx->b_pfh[1], &ctx->b_pfh[2], &ctx->b_cluster, &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
                     &ctx->b_cellcnt, &ctx->b_cellstart, &ctx->b_rowpk, &ctx->b_packets, &ctx->b_nrm, &ctx->b_nrm_in,
-                    &ctx->b_rsd, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
-                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_halo_list, &ctx->b_rowflag, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
+                    &ctx->b_rsd, &ctx->b_rdif, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
+                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_slab, &ctx->b_sel, &ctx->b_stats2, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
                     &ctx->g_vvals[1], &ctx->g_cent, &ctx->g_vcount, &ctx->g_vrad, &ctx->g_vlabel, &ctx->g_voff,
                     &ctx->g_layout, &ctx->g_layoff, &ctx->g_vgrid, &ctx->g_hist, &ctx->g_vfirst, &ctx->g_cnrm, &ctx->g_invperm, &ctx->g_sig, &ctx->g_sigdom, &ctx->g_color};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   svm_free(ctx);
+  comm_free(ctx);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->h_step) cudaFreeHost(ctx->h_step);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
@@ -303,26 +332,25 @@ int cab_build_grid(cab_ctx* ctx, float cell) {
 int cab_set_shard(cab_ctx* ctx, int32_t rank, int32_t world) {
   if (!ctx) return CAB_ERR_ARG;
   if (world < 1 || rank < 0 || rank >= world) return fail(ctx, CAB_ERR_ARG, "bad shard %d/%d", rank, world);
-  if (ctx->shard_world != world) ctx->shard_splits.clear();
   ctx->shard_rank = rank;
   ctx->shard_world = world;
   return CAB_OK;
 }
 
-int cab_shard_range(const cab_ctx* ctx, int64_t* begin, int64_t* end) {
+int cab_shard_range(cab_ctx* ctx, int64_t* begin, int64_t* end) {
   if (!ctx || !begin || !end) return CAB_ERR_ARG;
-  if (!ctx->have_grid) return CAB_ERR_STATE;
-  // packets are ordered by their start; the shard covers [start of packet p0, start of packet p1)
-  int p0, p1;
-  packet_range(ctx, &p0, &p1);
-  auto start_of = [&](int p) -> int64_t {
-    if (p >= ctx->n_packets) return ctx->n_valid;
-    Packet pk;
-    cudaMemcpy(&pk, (const Packet*)ctx->b_packets.p + p, sizeof(Packet), cudaMemcpyDeviceToHost);
-    return pk.start;
-  };
-  *begin = start_of(p0);
-  *end = start_of(p1);
+  if (!ctx->have_grid) return fail(ctx, CAB_ERR_STATE, "cab_shard_range: no grid");
+  if (!ctx->slab) {
+    *begin = 0;
+    *end = ctx->n_valid;
+    return CAB_OK;
+  }
+  if (!ctx->slab_info_valid) {
+    CAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (int rc = finish_slab(ctx)) return rc;
+  }
+  *begin = ctx->slab_info.q0;
+  *end = ctx->slab_info.q1;
   return CAB_OK;
 }
 
@@ -378,10 +406,29 @@ int cab_download(cab_ctx* ctx, float* nxyz_curv, float* r_min, float* r_max) {
   return download_results(ctx, nxyz_curv, r_min, r_max);
 }
 
+int cab_download_rdif(cab_ctx* ctx, float* r_dif) {
+  if (!ctx || !r_dif) return CAB_ERR_ARG;
+  if (!ctx->have_rsd) return fail(ctx, CAB_ERR_STATE, "cab_download_rdif: no RSD results");
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int n = (int)ctx->n, ns = (int)ctx->n_sorted;
+  if (n == 0) return CAB_OK;
+  cudaStream_t st = ctx->stream;
+  if (int rc = reserve(ctx, ctx->b_out1a, (size_t)n * sizeof(float))) return rc;
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_out1a.p, 0, (size_t)n * sizeof(float), st));
+  if (ns > 0) {
+    unpermute_scalar_kernel<<<(ns + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, ns, (const float*)ctx->b_rdif.p,
+                                                            (float*)ctx->b_out1a.p);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  CAB_CUDA(ctx, cudaMemcpyAsync(r_dif, ctx->b_out1a.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  return CAB_OK;
+}
+
 int cab_download_sorted(cab_ctx* ctx, int64_t begin, int64_t end, float* nxyz_curv, float* rmin_rmax, int32_t* input_index) {
   if (!ctx) return CAB_ERR_ARG;
   if (!ctx->have_grid) return fail(ctx, CAB_ERR_STATE, "cab_download_sorted: no grid");
-  if (begin < 0 || end < begin || end > ctx->n) return fail(ctx, CAB_ERR_ARG, "cab_download_sorted: bad range");
+  if (begin < 0 || end < begin || end > ctx->n_sorted) return fail(ctx, CAB_ERR_ARG, "cab_download_sorted: bad range");
   if (nxyz_curv && !ctx->have_normals) return fail(ctx, CAB_ERR_STATE, "no normals to download");
   if (rmin_rmax && !ctx->have_rsd) return fail(ctx, CAB_ERR_STATE, "no RSD results to download");
   CAB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -410,59 +457,115 @@ int cab_normals_rsd(cab_ctx* ctx, double r, int32_t max_nn_normals, const float 
   if (layout == CAB_OUT_INPUT_ORDER && (out_a == nullptr) != (out_b == nullptr))
     return fail(ctx, CAB_ERR_ARG, "cab_normals_rsd: r_min and r_max must be given together");
   const int n = (int)ctx->n;
+  const int ns = (int)ctx->n_sorted;
   cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+  if (layout == CAB_OUT_INPUT_ORDER && ctx->slab)
+    return fail(ctx, CAB_ERR_STATE, "cab_normals_rsd: a shard returns its own slice (CAB_OUT_SHARD_SORTED); the concatenated "
+                                     "results of a group come from cab_step_normals_rsd + cab_comm_download_range");
   // pass 1 on the compute stream
   if (int rc = run_normals(ctx, (float)r, max_nn_normals, vp)) return rc;
   int64_t b = 0, e = 0;
   if (layout == CAB_OUT_SHARD_SORTED)
     if (int rc = cab_shard_range(ctx, &b, &e)) return rc;
   const size_t m = (size_t)(e - b);
+  if (nxyz_curv && n > 0 && layout == CAB_OUT_INPUT_ORDER)
+    if (int rc = reserve(ctx, ctx->b_out4, (size_t)n * sizeof(float4))) return rc;
+  // From here on the copy stream may be writing into the caller's buffers: every exit goes through the epilogue below,
+  // which drains both streams; the first error (a failing call, or a CUDA error of any enqueue) is the result.
+  int rc = CAB_OK;
+  cudaError_t ce = cudaSuccess;
+  auto cuda = [&](cudaError_t x) {
+    if (ce == cudaSuccess && x != cudaSuccess) ce = x;
+    return x == cudaSuccess;
+  };
   // the normals leave on the copy stream while pass 2 runs
-  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+  cuda(cudaEventRecord(ctx->ev[6], st));
   if (nxyz_curv && n > 0) {
     if (layout == CAB_OUT_INPUT_ORDER) {
-      if (int rc = reserve(ctx, ctx->b_out4, (size_t)n * sizeof(float4))) return rc;
-      unpermute_kernel<<<(n + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, 0, n, (const float4*)ctx->b_nrm.p, nullptr,
-                                                        (float4*)ctx->b_out4.p, nullptr, nullptr);
-      CAB_LAUNCH_CHECK(ctx);
-      CAB_CUDA(ctx, cudaEventRecord(ctx->ev_ready, st));
-      CAB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_ready, 0));
-      CAB_CUDA(ctx, cudaMemcpyAsync(nxyz_curv, ctx->b_out4.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, cs));
+      if (ns > 0) {
+        unpermute_kernel<<<(ns + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, 0, ns, (const float4*)ctx->b_nrm.p, nullptr,
+                                                           (float4*)ctx->b_out4.p, nullptr, nullptr);
+        ctx->tm.kernel_launches++;
+        cuda(cudaGetLastError());
+      }
+      if (cuda(cudaEventRecord(ctx->ev_ready, st)) && cuda(cudaStreamWaitEvent(cs, ctx->ev_ready, 0)))
+        cuda(cudaMemcpyAsync(nxyz_curv, ctx->b_out4.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, cs));
     } else if (m) {
-      CAB_CUDA(ctx, cudaEventRecord(ctx->ev_ready, st));
-      CAB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_ready, 0));
-      CAB_CUDA(ctx, cudaMemcpyAsync(nxyz_curv, (const float4*)ctx->b_nrm.p + b, m * sizeof(float4), cudaMemcpyDeviceToHost, cs));
+      if (cuda(cudaEventRecord(ctx->ev_ready, st)) && cuda(cudaStreamWaitEvent(cs, ctx->ev_ready, 0)))
+        cuda(cudaMemcpyAsync(nxyz_curv, (const float4*)ctx->b_nrm.p + b, m * sizeof(float4), cudaMemcpyDeviceToHost, cs));
     }
   }
-  if (layout == CAB_OUT_SHARD_SORTED && input_index && m)
-    CAB_CUDA(ctx, cudaMemcpyAsync(input_index, (const int*)ctx->b_perm.p + b, m * sizeof(int), cudaMemcpyDeviceToHost, cs));
+  if (ce == cudaSuccess && layout == CAB_OUT_SHARD_SORTED && input_index && m)
+    cuda(cudaMemcpyAsync(input_index, (const int*)ctx->b_perm.p + b, m * sizeof(int), cudaMemcpyDeviceToHost, cs));
   // pass 2 (run_rsd synchronises the compute stream only)
-  int rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags);
-  if (rc == CAB_OK && out_a && n > 0) {
+  if (ce == cudaSuccess) rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags);
+  if (rc == CAB_OK && ce == cudaSuccess && out_a && n > 0) {
     if (layout == CAB_OUT_INPUT_ORDER) {
       rc = reserve(ctx, ctx->b_out1a, (size_t)n * sizeof(float));
       if (rc == CAB_OK) rc = reserve(ctx, ctx->b_out1b, (size_t)n * sizeof(float));
       if (rc == CAB_OK) {
-        unpermute_kernel<<<(n + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, 0, n, nullptr, (const float2*)ctx->b_rsd.p,
-                                                          nullptr, (float*)ctx->b_out1a.p, (float*)ctx->b_out1b.p);
-        ctx->tm.kernel_launches++;
-        cudaMemcpyAsync(out_a, ctx->b_out1a.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(out_b, ctx->b_out1b.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (ns > 0) {
+          unpermute_kernel<<<(ns + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, 0, ns, nullptr, (const float2*)ctx->b_rsd.p,
+                                                             nullptr, (float*)ctx->b_out1a.p, (float*)ctx->b_out1b.p);
+          ctx->tm.kernel_launches++;
+          cuda(cudaGetLastError());
+        }
+        cuda(cudaMemcpyAsync(out_a, ctx->b_out1a.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        cuda(cudaMemcpyAsync(out_b, ctx->b_out1b.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
       }
     } else if (m) {
-      cudaMemcpyAsync(out_a, (const float2*)ctx->b_rsd.p + b, m * sizeof(float2), cudaMemcpyDeviceToHost, st);
+      cuda(cudaMemcpyAsync(out_a, (const float2*)ctx->b_rsd.p + b, m * sizeof(float2), cudaMemcpyDeviceToHost, st));
     }
   }
-  cudaEventRecord(ctx->ev[7], st);
-  // both streams must drain before the host buffers are valid (also on the error path: the copy
-  // stream may still be writing nxyz_curv)
-  cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(st), e3 = cudaGetLastError();
+  cuda(cudaEventRecord(ctx->ev[7], st));
+  // epilogue: both streams drain before the host buffers are valid or reusable, on every path
+  cuda(cudaStreamSynchronize(cs));
+  cuda(cudaStreamSynchronize(st));
+  cuda(cudaGetLastError());
   if (rc != CAB_OK) return rc;
-  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
-    return fail(ctx, CAB_ERR_CUDA, "cab_normals_rsd: %s",
-                cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+  if (ce != cudaSuccess) return fail(ctx, CAB_ERR_CUDA, "cab_normals_rsd: %s", cudaGetErrorString(ce));
   CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[6], ctx->ev[7]));
   ctx->tm.d2h_ms -= ctx->tm.rsd_ms;  // copy time left exposed around pass 2
+  return CAB_OK;
+}
+
+int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_normals, const float vp[3], int32_t max_nn_rsd,
+                         int32_t ndiv, double plane_radius, int32_t flags) {
+  if (!ctx) return CAB_ERR_ARG;
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const bool exchange = comm_active(ctx);
+  struct Deferred {  // the stages leave the stream running; whatever happens, the flag goes back
+    cab_ctx* c;
+    explicit Deferred(cab_ctx* x) : c(x) { c->defer_sync = true; }
+    ~Deferred() { c->defer_sync = false; }
+  } deferred(ctx);
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[8], st));
+  int rc = build_grid(ctx, cell);
+  const bool push = rc == CAB_OK && exchange && ctx->slab;
+  if (rc == CAB_OK && exchange && !ctx->slab && ctx->n_valid > 0)
+    rc = fail(ctx, CAB_ERR_STATE, "cab_step_normals_rsd: the group's shard was reset (cab_set_shard) behind its back");
+  if (rc == CAB_OK && push) rc = comm_step_begin(ctx);
+  if (rc == CAB_OK) rc = run_normals(ctx, (float)r, max_nn_normals, vp);
+  if (rc == CAB_OK && push) rc = comm_step_before_push(ctx);
+  if (rc == CAB_OK) rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags);
+  if (rc == CAB_OK) rc = cudaEventRecord(ctx->ev[9], st) == cudaSuccess ? CAB_OK : fail(ctx, CAB_ERR_CUDA, "cudaEventRecord failed");
+  if (rc == CAB_OK && push) rc = comm_step_end(ctx, plane_radius);
+  if (rc == CAB_OK) rc = cudaEventRecord(ctx->ev[10], st) == cudaSuccess ? CAB_OK : fail(ctx, CAB_ERR_CUDA, "cudaEventRecord failed");
+  // one synchronisation per step (also on the error path: nothing may be left running on the caller's buffers)
+  const cudaError_t e = cudaStreamSynchronize(st);
+  if (rc != CAB_OK) return rc;
+  if (e != cudaSuccess) return fail(ctx, CAB_ERR_CUDA, "cab_step_normals_rsd: %s", cudaGetErrorString(e));
+  if (ctx->slab)
+    if (int rc2 = finish_slab(ctx)) return rc2;
+  if (int rc2 = finish_pass_stats(ctx, 0)) return rc2;
+  const int64_t k_normals = ctx->tm.neighbour_sum, c_normals = ctx->tm.candidate_sum;
+  (void)k_normals;
+  (void)c_normals;
+  if (int rc2 = finish_pass_stats(ctx, 1)) return rc2;
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.exchange_ms, ctx->ev[9], ctx->ev[10]));
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.step_ms, ctx->ev[8], ctx->ev[10]));
+  if (push) return comm_step_finish(ctx);
   return CAB_OK;
 }
 

@@ -1,0 +1,697 @@
+// cab_comm.cu -- the multi-GPU data plane behind the C ABI: one cab_ctx per GPU, one host thread or process per context.
+//
+// The reference runs its plugins single-threaded on one CPU (cloud_algos/src/radius_estimation.cpp:139 "TODO
+// parallelize!"); sharding is this implementation's own: queries shard as slabs of rows (cab_grid.cu), the
+// cloud is replicated, the results are concatenated.  Nothing here is a library collective on the data path:
+//   * the cloud is replicated by copy engines: every rank uploads 1/world of it over its own PCIe link and copies that
+//     slice into the peers' buffers over NVLink (cab_comm_upload_cloud);
+//   * the concatenation of the results is fused into the RSD kernel: a warp stores its packet's normals, radii and
+//     input indices straight into every rank's copy of the concatenated arrays (peer memory, cab_rsd.cu push_results);
+//     all that is left of the collective are two tiny flag kernels per step (slice offsets before, completion after).
+// Peer memory is plain cudaMalloc memory reached through cudaDeviceEnablePeerAccess (contexts of one process) or CUDA IPC
+// handles (one process per GPU, the torchrun layout).  NCCL is used for what it is good at -- the bootstrap (moving the
+// IPC handles) and the small integer all-reduce of GRSD histograms (grsd_colorCHLAC_tools.hpp:230-260 accumulates one
+// 6x6 matrix per histogram; its integer sums are order independent) -- and is loaded with dlopen so that a single-GPU
+// user of the library does not need it.
+#include <dlfcn.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "cab_internal.cuh"
+
+namespace cab {
+
+struct Id128 {  // ncclUniqueId
+  char b[CAB_COMM_ID_BYTES];
+};
+
+namespace {
+
+// ---- NCCL through dlopen (the subset used; declarations follow nccl.h 2.x, whose ABI for these calls is stable) ----
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128 /* ncclUniqueId by value */, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclInt8 = 0, kNcclInt32 = 2, kNcclSum = 0;
+
+NcclApi* nccl_api(std::string* why) {
+  static NcclApi api;
+  static std::once_flag once;
+  static std::string err;
+  std::call_once(once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (!api.lib) {
+      err = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : "?");
+      return;
+    }
+    auto sym = [&](const char* n) {
+      void* p = dlsym(api.lib, n);
+      if (!p && err.empty()) err = std::string("symbol missing in libnccl: ") + n;
+      return p;
+    };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  });
+  if (!err.empty()) {
+    if (why) *why = err;
+    return nullptr;
+  }
+  return &api;
+}
+
+// What a rank tells the others about its exchange buffers.
+constexpr int kBufNrm = 0, kBufRsd = 1, kBufPerm = 2, kBufCloud = 3, kBufSync = 4, kNumBufs = 5;
+struct CommBlob {
+  int64_t pid;
+  int32_t device;
+  int32_t rank;
+  int64_t cap_points;
+  uint64_t raw[kNumBufs];                 // device pointers (meaningful inside process `pid`)
+  cudaIpcMemHandle_t handle[kNumBufs];    // the same allocations for other processes
+};
+static_assert(sizeof(CommBlob) <= CAB_COMM_BLOB_BYTES, "CAB_COMM_BLOB_BYTES too small");
+
+// Contexts of one process (one host thread each): the blob table and a host barrier.
+struct LocalGroup {
+  std::mutex m;
+  std::condition_variable cv;
+  int world = 0, arrived = 0;
+  unsigned gen = 0;
+  std::vector<CommBlob> blobs;
+  void barrier() {
+    std::unique_lock<std::mutex> lk(m);
+    const unsigned g = gen;
+    if (++arrived == world) {
+      arrived = 0;
+      ++gen;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return gen != g; });
+    }
+  }
+};
+
+// Sync block of a rank (ints / 64-bit words in its own memory, written by the peers).
+struct SyncBlock {
+  unsigned long long mail[kMaxPeers];   // (seq << 32) | own query count of rank p
+  unsigned done[kMaxPeers];             // seq once rank p's pushes of this step are complete
+  unsigned cloud[kMaxPeers];            // cloud_seq once rank p's slice of the cloud has arrived
+  unsigned long long total;             // sum of the ranks' counts of the last step (host reads it back)
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+struct PeerSync {
+  SyncBlock* block[kMaxPeers];
+};
+
+// after the slab build: tell every rank how many queries this rank answers
+__global__ void post_count_kernel(const SlabInfo* __restrict__ info, PeerSync peers, int rank, int world, unsigned seq) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  const unsigned long long count = (unsigned long long)(unsigned)(info->q1 - info->q0);
+  st_release_sys(&peers.block[p]->mail[rank], ((unsigned long long)seq << 32) | count);
+}
+
+// before the pushes: wait for every rank's count, place this rank's slice in the concatenation
+__global__ void wait_counts_kernel(SlabInfo* __restrict__ info, SyncBlock* __restrict__ mine, int rank, int world, unsigned seq,
+                                   unsigned long long timeout_ns) {
+  __shared__ unsigned long long counts[kMaxPeers];
+  __shared__ int failed;
+  const int p = threadIdx.x;
+  if (p == 0) failed = 0;
+  __syncthreads();
+  if (p < world) {
+    const unsigned long long t0 = global_timer_ns();
+    unsigned long long v;
+    for (;;) {
+      v = ld_acquire_sys(&mine->mail[p]);
+      if ((unsigned)(v >> 32) == seq) break;
+      if (global_timer_ns() - t0 > timeout_ns) {
+        failed = 1;
+        v = 0;
+        break;
+      }
+      __nanosleep(200);
+    }
+    counts[p] = v & 0xffffffffull;
+  }
+  __syncthreads();
+  if (p == 0) {
+    unsigned long long base = 0, total = 0;
+    for (int q = 0; q < world; ++q) {
+      if (q < rank) base += counts[q];
+      total += counts[q];
+    }
+    info->gbase = (int)base;
+    if (failed) info->error = 1;
+    mine->total = total;
+  }
+}
+
+// after the RSD kernel (whose stores to peer memory are complete at the kernel boundary): tell every rank
+__global__ void post_flag_kernel(PeerSync peers, int rank, int world, unsigned seq, int which) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  __threadfence_system();
+  unsigned* f = which == 0 ? &peers.block[p]->done[rank] : &peers.block[p]->cloud[rank];
+  st_release_sys(f, seq);
+}
+
+__global__ void wait_flag_kernel(SlabInfo* __restrict__ info, int* __restrict__ error_out, SyncBlock* __restrict__ mine, int world,
+                                 unsigned seq, int which, unsigned long long timeout_ns) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  const unsigned* f = which == 0 ? &mine->done[p] : &mine->cloud[p];
+  const unsigned long long t0 = global_timer_ns();
+  while (ld_acquire_sys(f) != seq) {
+    if (global_timer_ns() - t0 > timeout_ns) {
+      if (info) info->error = 1;
+      if (error_out) *error_out = 1;
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
+// concatenated (sorted-order) results -> one range [j0, j1) of the input order
+__global__ void __launch_bounds__(256) range_unpermute_kernel(const int* __restrict__ perm, long long total, int j0, int j1,
+                                                              const float4* __restrict__ nrm, const float2* __restrict__ rsd,
+                                                              float4* __restrict__ out4, float* __restrict__ out_a,
+                                                              float* __restrict__ out_b) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= total) return;
+  const int j = perm[s];
+  if (j < j0 || j >= j1) return;
+  if (out4) out4[j - j0] = nrm[s];
+  if (out_a) {
+    const float2 v = rsd[s];
+    out_a[j - j0] = v.x;
+    out_b[j - j0] = v.y;
+  }
+}
+
+__global__ void __launch_bounds__(256) fill_defaults_kernel(float4* __restrict__ out4, float* __restrict__ out_a,
+                                                            float* __restrict__ out_b, int m, float radius) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float nan = __int_as_float(0x7fc00000);
+  if (out4) out4[i] = make_float4(nan, nan, nan, nan);
+  if (out_a) {
+    out_a[i] = radius;
+    out_b[i] = radius;
+  }
+}
+
+}  // namespace
+
+struct CommState {
+  int rank = 0, world = 1;
+  std::shared_ptr<LocalGroup> local;  // contexts of this process linked by cab_comm_init_local
+  void* nccl = nullptr;               // ncclComm_t (bootstrap + integer all-reduce)
+  DevBuf own[kNumBufs];
+  int64_t cap_points = 0;
+  bool connected = false;
+  void* peer[kMaxPeers][kNumBufs] = {};
+  bool peer_is_ipc[kMaxPeers] = {};
+  unsigned seq = 0, cloud_seq = 0;
+  bool armed = false;                 // this step's RSD kernel pushes its results
+  int64_t last_total = 0;             // entries of the concatenated arrays after the last step
+  double last_plane_radius = 0.1;
+  DevBuf stage;                       // device staging for the blob all-gather / integer all-reduce
+  unsigned long long timeout_ns = 5ull * 1000 * 1000 * 1000;
+};
+
+namespace {
+
+int nccl_fail(cab_ctx* ctx, const char* what, int code) {
+  NcclApi* api = nccl_api(nullptr);
+  return fail(ctx, CAB_ERR_CUDA, "%s failed: %s", what, api && api->GetErrorString ? api->GetErrorString(code) : "?");
+}
+
+void close_peers(cab_ctx* ctx) {
+  CommState* cs = ctx->comm;
+  for (int p = 0; p < kMaxPeers; ++p) {
+    if (cs->peer_is_ipc[p])
+      for (int b = 0; b < kNumBufs; ++b)
+        if (cs->peer[p][b]) cudaIpcCloseMemHandle(cs->peer[p][b]);
+    for (int b = 0; b < kNumBufs; ++b) cs->peer[p][b] = nullptr;
+    cs->peer_is_ipc[p] = false;
+  }
+  cs->connected = false;
+}
+
+// (Re)allocates this rank's exchange buffers for clouds of up to n points and describes them.
+int make_blob(cab_ctx* ctx, int64_t n, CommBlob* blob) {
+  CommState* cs = ctx->comm;
+  cudaStreamSynchronize(ctx->stream);
+  close_peers(ctx);
+  const size_t np = (size_t)std::max<int64_t>(n, 1);
+  const size_t bytes[kNumBufs] = {np * sizeof(float4), np * sizeof(float2), np * sizeof(int), np * 3 * sizeof(float) + 64,
+                                  sizeof(SyncBlock)};
+  for (int b = 0; b < kNumBufs; ++b) {
+    if (cs->own[b].p && cs->own[b].cap >= bytes[b]) continue;
+    if (cs->own[b].p) cudaFree(cs->own[b].p);
+    cs->own[b] = DevBuf{};
+    // plain cudaMalloc, one allocation per buffer: that is what cudaIpcGetMemHandle can export
+    const size_t want = b == kBufSync ? bytes[b] : bytes[b] + bytes[b] / 16;
+    cudaError_t e = cudaMalloc(&cs->own[b].p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      cs->own[b].p = nullptr;
+      return fail(ctx, CAB_ERR_OOM, "cab_comm: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    cs->own[b].cap = want;
+    if (b == kBufSync) {
+      CAB_CUDA(ctx, cudaMemset(cs->own[b].p, 0xff, want));  // no flag equals a sequence number yet
+      cs->seq = cs->cloud_seq = 0;
+    }
+  }
+  cs->cap_points = (int64_t)np;
+  std::memset(blob, 0, sizeof(*blob));
+  blob->pid = (int64_t)getpid();
+  blob->device = ctx->device;
+  blob->rank = cs->rank;
+  blob->cap_points = cs->cap_points;
+  for (int b = 0; b < kNumBufs; ++b) {
+    blob->raw[b] = (uint64_t)(uintptr_t)cs->own[b].p;
+    cudaError_t e = cudaIpcGetMemHandle(&blob->handle[b], cs->own[b].p);
+    if (e != cudaSuccess) {
+      cudaGetLastError();  // contexts of one process do not need the handles
+      std::memset(&blob->handle[b], 0, sizeof(blob->handle[b]));
+    }
+  }
+  return CAB_OK;
+}
+
+int connect_blobs(cab_ctx* ctx, const CommBlob* blobs) {
+  CommState* cs = ctx->comm;
+  const int64_t me = (int64_t)getpid();
+  for (int p = 0; p < cs->world; ++p) {
+    const CommBlob& b = blobs[p];
+    if (b.rank != p) return fail(ctx, CAB_ERR_ARG, "cab_comm: blob %d describes rank %d", p, b.rank);
+    if (b.cap_points != cs->cap_points)
+      return fail(ctx, CAB_ERR_ARG, "cab_comm: rank %d reserved %lld points, this rank %lld", p, (long long)b.cap_points,
+                  (long long)cs->cap_points);
+    if (p == cs->rank) {
+      for (int k = 0; k < kNumBufs; ++k) cs->peer[p][k] = cs->own[k].p;
+    } else if (b.pid == me) {
+      if (b.device != ctx->device) {
+        int can = 0;
+        CAB_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, b.device));
+        if (!can) return fail(ctx, CAB_ERR_CUDA, "cab_comm: device %d cannot access device %d", ctx->device, b.device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(ctx, CAB_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", b.device, cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      for (int k = 0; k < kNumBufs; ++k) cs->peer[p][k] = (void*)(uintptr_t)b.raw[k];
+    } else {
+      for (int k = 0; k < kNumBufs; ++k) {
+        cudaError_t e = cudaIpcOpenMemHandle(&cs->peer[p][k], b.handle[k], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+          cudaGetLastError();
+          return fail(ctx, CAB_ERR_CUDA, "cudaIpcOpenMemHandle (rank %d, buffer %d): %s", p, k, cudaGetErrorString(e));
+        }
+      }
+      cs->peer_is_ipc[p] = true;
+    }
+  }
+  cs->connected = true;
+  return CAB_OK;
+}
+
+PeerSync peer_sync(const CommState* cs) {
+  PeerSync ps{};
+  for (int p = 0; p < cs->world; ++p) ps.block[p] = (SyncBlock*)cs->peer[p][kBufSync];
+  return ps;
+}
+
+}  // namespace
+
+// Collective: makes sure every rank's exchange buffers hold n points and are mapped on every rank.  A no-op once they
+// do (every rank takes the same decision: n is the same everywhere).
+int comm_prepare(cab_ctx* ctx, int64_t n) {
+  CommState* cs = ctx->comm;
+  if (!cs) return fail(ctx, CAB_ERR_STATE, "cab_comm: this context belongs to no group (cab_comm_init / cab_comm_init_local)");
+  if (cs->connected && n <= cs->cap_points) return CAB_OK;
+  if (!cs->local && !cs->nccl)
+    return fail(ctx, CAB_ERR_STATE, "cab_comm: buffers for %lld points are not connected (cab_comm_reserve / _export / _connect)", (long long)n);
+  CommBlob mine;
+  if (int rc = make_blob(ctx, n + n / 8, &mine)) return rc;
+  std::vector<CommBlob> all(cs->world);
+  if (cs->local) {
+    {
+      std::lock_guard<std::mutex> lk(cs->local->m);
+      cs->local->blobs.resize(cs->world);
+      cs->local->blobs[cs->rank] = mine;
+    }
+    cs->local->barrier();
+    {
+      std::lock_guard<std::mutex> lk(cs->local->m);
+      all = cs->local->blobs;
+    }
+    cs->local->barrier();  // nobody overwrites the table before everybody has read it
+  } else {
+    NcclApi* api = nccl_api(nullptr);
+    const size_t sz = sizeof(CommBlob);
+    if (int rc = reserve(ctx, cs->stage, sz * (cs->world + 1))) return rc;
+    char* d = (char*)cs->stage.p;
+    CAB_CUDA(ctx, cudaMemcpyAsync(d, &mine, sz, cudaMemcpyHostToDevice, ctx->stream));
+    int e = api->AllGather(d, d + sz, sz, kNcclInt8, cs->nccl, ctx->stream);
+    if (e) return nccl_fail(ctx, "ncclAllGather", e);
+    CAB_CUDA(ctx, cudaMemcpyAsync(all.data(), d + sz, sz * cs->world, cudaMemcpyDeviceToHost, ctx->stream));
+    CAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return connect_blobs(ctx, all.data());
+}
+
+void comm_push_targets(const cab_ctx* ctx, PushTargets* out) {
+  out->world = 0;
+  const CommState* cs = ctx->comm;
+  if (!cs || !cs->armed || !cs->connected) return;
+  out->world = cs->world;
+  for (int p = 0; p < cs->world; ++p) {
+    out->nrm[p] = (float4*)cs->peer[p][kBufNrm];
+    out->rsd[p] = (float2*)cs->peer[p][kBufRsd];
+    out->perm[p] = (int*)cs->peer[p][kBufPerm];
+  }
+}
+
+void comm_free(cab_ctx* ctx) {
+  CommState* cs = ctx->comm;
+  if (!cs) return;
+  cudaStreamSynchronize(ctx->stream);
+  close_peers(ctx);
+  for (auto& b : cs->own)
+    if (b.p) cudaFree(b.p);
+  if (cs->stage.p) cudaFree(cs->stage.p);
+  if (cs->nccl) {
+    NcclApi* api = nccl_api(nullptr);
+    if (api) api->CommDestroy(cs->nccl);
+  }
+  delete cs;
+  ctx->comm = nullptr;
+}
+
+// ---- the pieces of one exchanged step, called by cab_step_normals_rsd (cab_api.cu) ---------------------------------
+bool comm_active(const cab_ctx* ctx) { return ctx->comm && ctx->comm->world > 1; }
+
+int comm_step_begin(cab_ctx* ctx) {  // after the slab build
+  CommState* cs = ctx->comm;
+  if (int rc = comm_prepare(ctx, ctx->n)) return rc;
+  cs->seq++;
+  cs->armed = true;
+  post_count_kernel<<<1, kMaxPeers, 0, ctx->stream>>>(slab_info_device(ctx), peer_sync(cs), cs->rank, cs->world, cs->seq);
+  CAB_LAUNCH_CHECK(ctx);
+  return CAB_OK;
+}
+
+int comm_step_before_push(cab_ctx* ctx) {  // after the normals pass
+  CommState* cs = ctx->comm;
+  wait_counts_kernel<<<1, kMaxPeers, 0, ctx->stream>>>((SlabInfo*)slab_info_device(ctx), (SyncBlock*)cs->own[kBufSync].p, cs->rank,
+                                                     cs->world, cs->seq, cs->timeout_ns);
+  CAB_LAUNCH_CHECK(ctx);
+  return CAB_OK;
+}
+
+int comm_step_end(cab_ctx* ctx, double plane_radius) {  // after the RSD kernel
+  CommState* cs = ctx->comm;
+  cs->armed = false;
+  cs->last_plane_radius = plane_radius;
+  post_flag_kernel<<<1, kMaxPeers, 0, ctx->stream>>>(peer_sync(cs), cs->rank, cs->world, cs->seq, 0);
+  CAB_LAUNCH_CHECK(ctx);
+  wait_flag_kernel<<<1, kMaxPeers, 0, ctx->stream>>>((SlabInfo*)slab_info_device(ctx), nullptr, (SyncBlock*)cs->own[kBufSync].p,
+                                                   cs->world, cs->seq, 0, cs->timeout_ns);
+  CAB_LAUNCH_CHECK(ctx);
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepComm, &((SyncBlock*)cs->own[kBufSync].p)->total, 8, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  return CAB_OK;
+}
+
+int comm_step_finish(cab_ctx* ctx) {  // after the step's synchronisation
+  CommState* cs = ctx->comm;
+  unsigned long long total;
+  std::memcpy(&total, ctx->h_step + kStepComm, 8);
+  cs->last_total = (int64_t)total;
+  if (ctx->slab_info.error) return fail(ctx, CAB_ERR_STATE, "cab_comm: a peer did not answer within %.1f s", cs->timeout_ns * 1e-9);
+  return CAB_OK;
+}
+
+}  // namespace cab
+
+using namespace cab;
+
+extern "C" {
+
+int cab_comm_get_id(char id[CAB_COMM_ID_BYTES]) {
+  std::string why;
+  NcclApi* api = nccl_api(&why);
+  if (!api) return fail(nullptr, CAB_ERR_CUDA, "cab_comm_get_id: %s", why.c_str());
+  std::memset(id, 0, CAB_COMM_ID_BYTES);
+  int e = api->GetUniqueId(id);
+  if (e) return fail(nullptr, CAB_ERR_CUDA, "ncclGetUniqueId failed: %s", api->GetErrorString(e));
+  return CAB_OK;
+}
+
+int cab_comm_init(cab_ctx* ctx, const char id[CAB_COMM_ID_BYTES], int32_t rank, int32_t world) {
+  if (!ctx || !id) return CAB_ERR_ARG;
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(ctx, CAB_ERR_ARG, "cab_comm_init: bad rank %d / world %d (at most %d ranks)", rank, world, kMaxPeers);
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::string why;
+  NcclApi* api = nccl_api(&why);
+  if (!api) return fail(ctx, CAB_ERR_CUDA, "cab_comm_init: %s", why.c_str());
+  comm_free(ctx);
+  Id128 uid;
+  std::memcpy(uid.b, id, CAB_COMM_ID_BYTES);
+  void* comm = nullptr;
+  int e = api->CommInitRank(&comm, world, uid, rank);
+  if (e) return nccl_fail(ctx, "ncclCommInitRank", e);
+  ctx->comm = new CommState();
+  ctx->comm->rank = rank;
+  ctx->comm->world = world;
+  ctx->comm->nccl = comm;
+  return cab_set_shard(ctx, rank, world);
+}
+
+int cab_comm_init_local(cab_ctx** ctxs, int32_t world) {
+  if (!ctxs || world < 1 || world > kMaxPeers) return CAB_ERR_ARG;
+  auto group = std::make_shared<LocalGroup>();
+  group->world = world;
+  for (int r = 0; r < world; ++r) {
+    cab_ctx* ctx = ctxs[r];
+    if (!ctx) return CAB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    comm_free(ctx);
+    ctx->comm = new CommState();
+    ctx->comm->rank = r;
+    ctx->comm->world = world;
+    ctx->comm->local = group;
+    if (int rc = cab_set_shard(ctx, r, world)) return rc;
+  }
+  return CAB_OK;
+}
+
+int cab_comm_reserve(cab_ctx* ctx, int32_t rank, int32_t world, int64_t max_points, void* blob) {
+  if (!ctx || !blob) return CAB_ERR_ARG;
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(ctx, CAB_ERR_ARG, "cab_comm_reserve: bad rank %d / world %d (at most %d ranks)", rank, world, kMaxPeers);
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->comm) ctx->comm = new CommState();
+  ctx->comm->rank = rank;
+  ctx->comm->world = world;
+  if (int rc = cab_set_shard(ctx, rank, world)) return rc;
+  std::memset(blob, 0, CAB_COMM_BLOB_BYTES);
+  return make_blob(ctx, max_points, (CommBlob*)blob);
+}
+
+int cab_comm_connect(cab_ctx* ctx, const void* blobs) {
+  if (!ctx || !blobs) return CAB_ERR_ARG;
+  if (!ctx->comm) return fail(ctx, CAB_ERR_STATE, "cab_comm_connect: call cab_comm_reserve first");
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<CommBlob> all(ctx->comm->world);
+  for (int p = 0; p < ctx->comm->world; ++p)
+    std::memcpy(&all[p], (const char*)blobs + (size_t)p * CAB_COMM_BLOB_BYTES, sizeof(CommBlob));
+  return connect_blobs(ctx, all.data());
+}
+
+int cab_comm_free(cab_ctx* ctx) {
+  if (!ctx) return CAB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  comm_free(ctx);
+  return cab_set_shard(ctx, 0, 1);
+}
+
+int cab_comm_upload_cloud(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (!comm_active(ctx)) return cab_upload_cloud(ctx, xyz, n, stride);
+  if (stride != 3) return fail(ctx, CAB_ERR_ARG, "cab_comm_upload_cloud: packed xyz (stride 3) only");
+  if (n < 0 || (n > 0 && !xyz)) return fail(ctx, CAB_ERR_ARG, "cab_comm_upload_cloud: bad cloud");
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (int rc = comm_prepare(ctx, n)) return rc;
+  CommState* cs = ctx->comm;
+  cudaStream_t st = ctx->stream;
+  const int64_t lo = n * cs->rank / cs->world, hi = n * (cs->rank + 1) / cs->world;
+  const size_t off = (size_t)lo * 3, bytes = (size_t)(hi - lo) * 3 * sizeof(float);
+  float* mine = (float*)cs->own[kBufCloud].p;
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+  if (bytes) {
+    CAB_CUDA(ctx, cudaMemcpyAsync(mine + off, xyz + off, bytes, cudaMemcpyHostToDevice, st));
+    for (int k = 1; k < cs->world; ++k) {  // start with the right-hand neighbour: the ranks' copies do not collide
+      const int p = (cs->rank + k) % cs->world;
+      CAB_CUDA(ctx, cudaMemcpyAsync((float*)cs->peer[p][kBufCloud] + off, mine + off, bytes, cudaMemcpyDefault, st));
+    }
+  }
+  cs->cloud_seq++;
+  if (int rc = reserve(ctx, ctx->b_misc, 64)) return rc;
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_misc.p, 0, 4, st));
+  post_flag_kernel<<<1, kMaxPeers, 0, st>>>(peer_sync(cs), cs->rank, cs->world, cs->cloud_seq, 1);
+  CAB_LAUNCH_CHECK(ctx);
+  wait_flag_kernel<<<1, kMaxPeers, 0, st>>>(nullptr, (int*)ctx->b_misc.p, (SyncBlock*)cs->own[kBufSync].p, cs->world, cs->cloud_seq, 1,
+                                          cs->timeout_ns);
+  CAB_LAUNCH_CHECK(ctx);
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepComm + 16, ctx->b_misc.p, 4, cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[6], ctx->ev[7]));
+  int err;
+  std::memcpy(&err, ctx->h_step + kStepComm + 16, 4);
+  if (err) return fail(ctx, CAB_ERR_STATE, "cab_comm_upload_cloud: a peer's slice did not arrive within %.1f s", cs->timeout_ns * 1e-9);
+  return cab_set_cloud_device(ctx, mine, n, 3);
+}
+
+int cab_comm_download_range(cab_ctx* ctx, int64_t j0, int64_t j1, float* nxyz_curv, float* r_min, float* r_max) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (!comm_active(ctx) || !ctx->comm->connected)
+    return fail(ctx, CAB_ERR_STATE, "cab_comm_download_range: no exchanged step has run on this context");
+  if (j0 < 0 || j1 < j0 || j1 > ctx->n) return fail(ctx, CAB_ERR_ARG, "cab_comm_download_range: bad range");
+  if ((r_min == nullptr) != (r_max == nullptr)) return fail(ctx, CAB_ERR_ARG, "r_min and r_max must be given together");
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  CommState* cs = ctx->comm;
+  const int m = (int)(j1 - j0);
+  if (m == 0 || (!nxyz_curv && !r_min)) return CAB_OK;
+  cudaStream_t st = ctx->stream;
+  if (nxyz_curv)
+    if (int rc = reserve(ctx, ctx->b_out4, (size_t)m * sizeof(float4))) return rc;
+  if (r_min) {
+    if (int rc = reserve(ctx, ctx->b_out1a, (size_t)m * sizeof(float))) return rc;
+    if (int rc = reserve(ctx, ctx->b_out1b, (size_t)m * sizeof(float))) return rc;
+  }
+  float4* o4 = nxyz_curv ? (float4*)ctx->b_out4.p : nullptr;
+  float* oa = r_min ? (float*)ctx->b_out1a.p : nullptr;
+  float* ob = r_min ? (float*)ctx->b_out1b.p : nullptr;
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+  // points that are nobody's query (non-finite) keep the values the single-GPU path gives them
+  fill_defaults_kernel<<<(m + 255) / 256, 256, 0, st>>>(o4, oa, ob, m, (float)cs->last_plane_radius);
+  CAB_LAUNCH_CHECK(ctx);
+  const long long total = cs->last_total;
+  if (total > 0) {
+    range_unpermute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const int*)cs->own[kBufPerm].p, total, (int)j0, (int)j1,
+                                                                          (const float4*)cs->own[kBufNrm].p,
+                                                                          (const float2*)cs->own[kBufRsd].p, o4, oa, ob);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  if (nxyz_curv) CAB_CUDA(ctx, cudaMemcpyAsync(nxyz_curv, o4, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  if (r_min) {
+    CAB_CUDA(ctx, cudaMemcpyAsync(r_min, oa, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CAB_CUDA(ctx, cudaMemcpyAsync(r_max, ob, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[6], ctx->ev[7]));
+  return CAB_OK;
+}
+
+void* cab_comm_device_ptr(cab_ctx* ctx, int32_t which, int64_t* count) {
+  if (!ctx || !ctx->comm || !ctx->comm->connected) return nullptr;
+  if (count) *count = ctx->comm->last_total;
+  switch (which) {
+    case CAB_BUF_NRM_SORTED: return ctx->comm->own[kBufNrm].p;
+    case CAB_BUF_RSD_SORTED: return ctx->comm->own[kBufRsd].p;
+    case CAB_BUF_PERM: return ctx->comm->own[kBufPerm].p;
+    default: return nullptr;
+  }
+}
+
+int cab_comm_allreduce_i32(cab_ctx* ctx, int32_t* values, int64_t count) {
+  if (!ctx || (count > 0 && !values)) return CAB_ERR_ARG;
+  if (!ctx->comm || ctx->comm->world <= 1 || count == 0) return CAB_OK;
+  CAB_CUDA(ctx, cudaSetDevice(ctx->device));
+  CommState* cs = ctx->comm;
+  cudaStream_t st = ctx->stream;
+  const size_t bytes = (size_t)count * 4;
+  if (cs->nccl) {
+    NcclApi* api = nccl_api(nullptr);
+    if (int rc = reserve(ctx, cs->stage, bytes)) return rc;
+    CAB_CUDA(ctx, cudaMemcpyAsync(cs->stage.p, values, bytes, cudaMemcpyHostToDevice, st));
+    int e = api->AllReduce(cs->stage.p, cs->stage.p, (size_t)count, kNcclInt32, kNcclSum, cs->nccl, st);
+    if (e) return nccl_fail(ctx, "ncclAllReduce", e);
+    CAB_CUDA(ctx, cudaMemcpyAsync(values, cs->stage.p, bytes, cudaMemcpyDeviceToHost, st));
+    CAB_CUDA(ctx, cudaStreamSynchronize(st));
+    return CAB_OK;
+  }
+  if (cs->local) {  // contexts of one process: sum on the host, integers are order independent
+    static std::mutex m;
+    static std::vector<int64_t> acc;
+    {
+      std::lock_guard<std::mutex> lk(m);
+      if ((int64_t)acc.size() != count) acc.assign((size_t)count, 0);
+      for (int64_t i = 0; i < count; ++i) acc[(size_t)i] += values[i];
+    }
+    cs->local->barrier();
+    {
+      std::lock_guard<std::mutex> lk(m);
+      for (int64_t i = 0; i < count; ++i) values[i] = (int32_t)acc[(size_t)i];
+    }
+    cs->local->barrier();
+    if (cs->rank == 0) {
+      std::lock_guard<std::mutex> lk(m);
+      acc.clear();
+    }
+    cs->local->barrier();
+    return CAB_OK;
+  }
+  return fail(ctx, CAB_ERR_STATE, "cab_comm_allreduce_i32: needs cab_comm_init (NCCL) or cab_comm_init_local");
+}
+
+}  // extern "C"

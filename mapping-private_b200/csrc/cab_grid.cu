@@ -12,6 +12,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
 #include <cmath>
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(const Domain* __restr
                                                            const int* __restrict__ seglen, int n_packets,
                                                            Packet* __restrict__ packets) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_packets < 0) n_packets = packet_base[n_cells];  // slab build: the host launches before it knows the count
   if (p >= n_packets) return;
   long long lo = 0, hi = n_cells;  // largest cell with packet_base[cell] <= p: the segment's first cell
   while (hi - lo > 1) {
@@ -289,144 +291,70 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(const Domain* __restr
   packets[p] = Packet{a, b - a, (int)((c0 - dm.cell_base) / dm.nx), d};
 }
 
-// Cells of a row covered by the sorted positions [s0, s1] (both inside the row): the cell holding s is the
-// last one whose start is <= s.  Needs only the cell table, not the sorted points.
-__device__ __forceinline__ int cell_of_position(const int* __restrict__ row_start, int nx, int s) {
-  int lo = 0, hi = nx;  // largest c in [0, nx) with row_start[c] <= s
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (row_start[mid] <= s) lo = mid; else hi = mid;
+// ---- slab build (multi-GPU, one cloud): a rank indexes only the rows it reads ---------------------------------
+// Every rank holds the whole cloud, but keys, sorts and tabulates only its slab: the rows whose queries it answers
+// (own), one layer of rows around them whose normals it recomputes instead of receiving them (halo), and one more
+// layer, the halo's candidates (window).  The cuts between the ranks must be the same on every rank and balance the
+// ranks' work, so they are taken from a statistic every rank computes identically and cheaply: the cell histogram of
+// a fixed 1-in-S sample of the points, turned into a cost per row (candidates tested ~ points of a cell times points
+// of the 27 cells around it).  Whatever the sample says, the cuts are consistent and complete; balance only needs it
+// to be representative.  Inside the window the sort, cell table, segments and packets are the unsharded ones (same
+// keys, stable selection, stable sort), so a rank's results equal the single-GPU results bit for bit.
+
+// cell histogram of every S-th group of four points
+__global__ void __launch_bounds__(256) sample_hist_kernel(const float* __restrict__ xyz, int stride, int n, int sample,
+                                                          const Domain* __restrict__ domains, float inv_cell,
+                                                          int* __restrict__ cellcnt) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long first = t * 4 * sample;
+  if (first >= n) return;
+  const Domain dm = domains[0];
+  const int last = (int)min((long long)n, first + 4);
+  for (int i = (int)first; i < last; ++i) {
+    const float* p = xyz + (size_t)i * stride;
+    const float x = p[0], y = p[1], z = p[2];
+    if (!finite3(x, y, z)) continue;
+    int cy, cz;
+    row_cells(dm, y, z, inv_cell, cy, cz);
+    const int cx = xfine_coord(x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift;
+    atomicAdd(cellcnt + ((long long)cz * dm.ny + cy) * dm.nx + cx, 1);
   }
-  return lo;
 }
 
-// cost model of a packet for the multi-GPU split: the candidates its queries will be tested against
-__global__ void __launch_bounds__(256) packet_cost_kernel(const Domain* __restrict__ domains, const Packet* __restrict__ packets,
-                                                          int n_packets, const int* __restrict__ cell_start,
-                                                          long long* __restrict__ cost) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_packets) return;
-  const Packet pk = packets[p];
-  const Domain dm = domains[pk.domain];
-  const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
-  const int* row = cell_start + dm.cell_base + (long long)pk.row_local * dm.nx;
-  const int cxlo = max(cell_of_position(row, dm.nx, pk.start) - 1, 0);
-  const int cxhi = min(cell_of_position(row, dm.nx, pk.start + pk.count - 1) + 1, dm.nx - 1);
-  long long c = 0;
-  for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1); ++z)
-    for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1); ++y) {
-      const long long b = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
-      c += cell_start[b + cxhi + 1] - cell_start[b + cxlo];
+// cost of a row = sum over its cells of (sampled points) x (estimated candidates per point + a constant per point);
+// one warp per row
+__global__ void __launch_bounds__(256) row_cost_kernel(const Domain* __restrict__ domains, const int* __restrict__ cnt,
+                                                       int sample, long long* __restrict__ rowcost) {
+  const Domain dm = domains[0];
+  const int n_rows = dm.ny * dm.nz;
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * (blockDim.x >> 5)) {
+    const int cy = row % dm.ny, cz = row / dm.ny;
+    const int* mine = cnt + (long long)row * dm.nx;
+    long long acc = 0;
+    for (int cx = lane; cx < dm.nx; cx += kWarp) {
+      const int c = mine[cx];
+      if (c == 0) continue;
+      int s = 0;
+      for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1); ++z)
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1); ++y) {
+          const int* r = cnt + ((long long)z * dm.ny + y) * dm.nx;
+          for (int x = max(cx - 1, 0); x <= min(cx + 1, dm.nx - 1); ++x) s += r[x];
+        }
+      acc += (long long)c * ((long long)s * sample + 2);
     }
-  cost[p] = c + 64;  // + a constant per packet (setup, fit, eigen-solve)
-}
-
-// What a rank needs to know about its shard; written by split_kernel, read by the kernels that follow it in
-// the stream (so the host does not have to wait for the split before it launches them).
-struct ShardInfo {
-  int p0, p1;              // own packets
-  int row_lo, row_hi;      // rows (inclusive) whose points this rank sorts: own rows, halo rows and their candidates
-  int sel_begin, sel_end;  // the same as a range of the global sorted order
-  int unused;
-  int n_selected;          // points selected for the sort (= sel_end - sel_begin)
-};
-
-// cells touched by the shard's own packets
-__global__ void __launch_bounds__(256) mark_cells_kernel(const Domain* __restrict__ domains, const Packet* __restrict__ packets,
-                                                         const ShardInfo* __restrict__ info, const int* __restrict__ cell_start,
-                                                         unsigned char* __restrict__ cell_flag) {
-  const int p = info->p0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= info->p1) return;
-  const Packet pk = packets[p];
-  const Domain dm = domains[pk.domain];
-  const long long base = dm.cell_base + (long long)pk.row_local * dm.nx;
-  const int c0 = cell_of_position(cell_start + base, dm.nx, pk.start);
-  const int c1 = cell_of_position(cell_start + base, dm.nx, pk.start + pk.count - 1);
-  for (int c = c0; c <= c1; ++c) cell_flag[base + c] = 1;
-}
-
-// A packet needs normals on this rank if it is the shard's own or touches a cell adjacent (3x3x3) to
-// a cell of the shard: every candidate of the shard's RSD pass then has a locally computed normal
-// and no exchange between the two passes is needed.
-__global__ void __launch_bounds__(256) flag_halo_kernel(const Domain* __restrict__ domains, const Packet* __restrict__ packets,
-                                                        int n_packets, const ShardInfo* __restrict__ info,
-                                                        const int* __restrict__ cell_start,
-                                                        const unsigned char* __restrict__ cell_flag,
-                                                        unsigned char* __restrict__ flag) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_packets) return;
-  unsigned char f = (p >= info->p0 && p < info->p1) ? 1 : 0;
-  if (!f && info->p1 > info->p0) {
-    const Packet pk = packets[p];
-    const Domain dm = domains[pk.domain];
-    const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
-    const int* row = cell_start + dm.cell_base + (long long)pk.row_local * dm.nx;
-    const int c0 = max(cell_of_position(row, dm.nx, pk.start) - 1, 0);
-    const int c1 = min(cell_of_position(row, dm.nx, pk.start + pk.count - 1) + 1, dm.nx - 1);
-    for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1) && !f; ++z)
-      for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1) && !f; ++y) {
-        const long long base = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
-        for (int c = c0; c <= c1; ++c)
-          if (cell_flag[base + c]) { f = 1; break; }
-      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    if (lane == 0) rowcost[row] = acc;
   }
-  flag[p] = f;
 }
-
-// ---- sharded sort (multi-GPU, one domain): only the rows the rank reads are sorted on this rank ----
-// Own packets are a contiguous range of the sorted order, hence of rows; halo packets lie within one layer
-// (ny + 1 rows) of them and their candidates within two.  Whole rows [row_lo, row_hi] are taken: the
-// selected points are then exactly the range [sel_begin, sel_end) of the global sorted order, and sorting
-// them alone reproduces that range of the full sort (the radix sort is stable and so is the selection).
-template <typename KeyT>
-struct RowRangePoint {
-  const KeyT* keys;
-  const ShardInfo* info;
-  int xbits;
-  __device__ __forceinline__ bool operator()(int i) const {
-    const long long row = (long long)((unsigned long long)keys[i] >> xbits);
-    return row >= info->row_lo && row <= info->row_hi;  // the sentinel row of non-finite points lies above every row
-  }
-};
-
-template <typename KeyT>
-__global__ void __launch_bounds__(256) gather_keys_kernel(const KeyT* __restrict__ keys, const int* __restrict__ idx, int m,
-                                                          KeyT* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < m) out[j] = keys[idx[j]];
-}
-
-// j-th element of the sorted subset -> position sel_begin + j of the full sorted order
-__global__ void __launch_bounds__(256) place_sorted_kernel(const float* __restrict__ xyz, int stride, int m, int sel_begin,
-                                                           const int* __restrict__ svals, float4* __restrict__ pos,
-                                                           int* __restrict__ perm) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m) return;
-  const int i = svals[j];
-  const float* p = xyz + (size_t)i * stride;
-  pos[sel_begin + j] = make_float4(p[0], p[1], p[2], 0.f);
-  perm[sel_begin + j] = i;
-}
-
-// Shard boundaries.  A rank's work is its own packets (both passes) plus the normals of its halo: the
-// packets up to one layer of rows before its first and after its last packet.  One block, thread g owns
-// cut g; a few fixed-point rounds move the cuts until own cost + kHaloWeight * halo cost is the same for
-// every rank (interior ranks have two halos, the first and last rank one).
-//   cum         inclusive prefix of the packet costs
-//   packet_base per cell: packets before the cell's segment; at a row's first cell: packets of the rows before
-constexpr int kHaloPermille = 380;  // share of the normals pass in a packet's cost (9.05 of 23.6 ms on the 20 M-point room)
 
 __device__ __forceinline__ long long cum_before(const long long* __restrict__ cum, int p) { return p > 0 ? cum[p - 1] : 0; }
-__device__ __forceinline__ int first_packet_of_row(const Domain& dm, const int* __restrict__ packet_base, long long row) {
-  const long long rows = (long long)dm.ny * dm.nz;
-  row = row < 0 ? 0 : (row > rows ? rows : row);
-  return packet_base[dm.cell_base + row * dm.nx];
-}
 
-// first packet whose inclusive cost prefix reaches t, found by one warp: 32 probes per step instead of a
-// chain of dependent loads (the cuts are on the critical path of every sharded build)
-__device__ __forceinline__ int cut_at(const long long* __restrict__ cum, int n_packets, long long t, int lane) {
-  int lo = 0, hi = n_packets;  // the answer lies in [lo, hi]
+// first index whose inclusive cost prefix reaches t, found by one warp: 32 probes per step instead of a chain of
+// dependent loads (the cuts are on the critical path of every sharded build)
+__device__ __forceinline__ int cut_at(const long long* __restrict__ cum, int n_items, long long t, int lane) {
+  int lo = 0, hi = n_items;  // the answer lies in [lo, hi]
   while (hi - lo > 32) {
     const int step = (hi - lo + 31) / 32;
     const long long idx = (long long)lo + (long long)lane * step;
@@ -444,40 +372,36 @@ __device__ __forceinline__ int cut_at(const long long* __restrict__ cum, int n_p
   return m ? min(lo + __ffs(m) - 1, hi) : hi;
 }
 
-__global__ void __launch_bounds__(1024) split_kernel(const long long* __restrict__ cum, int n_packets, int world, int rank,
-                                                     const Packet* __restrict__ packets, const Domain* __restrict__ domains,
-                                                     int n_domains, const int* __restrict__ packet_base,
-                                                     const int* __restrict__ cell_start, int* __restrict__ split,
-                                                     ShardInfo* __restrict__ info) {
+// Row cuts.  A rank's work is its own rows (both passes) plus the normals of its halo rows (one layer = ny + 1 rows on
+// either side; the first and last rank have one halo).  One block, one warp per cut; a few fixed-point rounds move the
+// cuts until own cost + halo_permille/1000 * halo cost is the same for every rank.  Leaves the rank's row ranges in
+// `info` and turns domains[0] into the slab's table geometry.
+__global__ void __launch_bounds__(1024) slab_split_kernel(const long long* __restrict__ cum, int world, int rank,
+                                                          int halo_permille, Domain* __restrict__ domains,
+                                                          int* __restrict__ cuts, SlabInfo* __restrict__ info) {
   __shared__ int s[65];
   __shared__ long long halo[64];
   __shared__ long long target[65];
+  const Domain dm = domains[0];
+  const int n_rows = dm.ny * dm.nz, layer = dm.ny + 1;
   const int g = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-  const long long total = cum[n_packets - 1];
+  const long long total = cum[n_rows - 1];
   if (g == 0) {
     s[0] = 0;
-    s[world] = n_packets;
+    s[world] = n_rows;
   }
   for (int c = 1 + warp; c < world; c += n_warps) {  // one warp per cut
-    const int v = cut_at(cum, n_packets, total / world * c, lane);
+    const int v = cut_at(cum, n_rows, total / world * c, lane);
     if (lane == 0) s[c] = v;
   }
   __syncthreads();
-  for (int round = 0; round < 3; ++round) {
+  for (int round = 0; round < 4; ++round) {
     if (g < world) {
       long long h = 0;
       const int a = s[g], b = s[g + 1];
-      if (g > 0 && a > 0 && a < n_packets) {  // rows below the first own packet
-        const Packet pk = packets[a];
-        const Domain dm = domains[pk.domain];
-        h += cum_before(cum, a) - cum_before(cum, first_packet_of_row(dm, packet_base, (long long)pk.row_local - dm.ny - 1));
-      }
-      if (g < world - 1 && b > 0 && b < n_packets) {  // rows above the last own packet
-        const Packet pk = packets[b - 1];
-        const Domain dm = domains[pk.domain];
-        h += cum_before(cum, first_packet_of_row(dm, packet_base, (long long)pk.row_local + dm.ny + 2)) - cum_before(cum, b);
-      }
-      halo[g] = h < 0 ? 0 : h * kHaloPermille / 1000;
+      if (g > 0) h += cum_before(cum, a) - cum_before(cum, max(a - layer, 0));
+      if (g < world - 1) h += cum_before(cum, min(b + layer, n_rows)) - cum_before(cum, b);
+      halo[g] = h * halo_permille / 1000;
     }
     __syncthreads();
     if (g == 0) {
@@ -496,30 +420,105 @@ __global__ void __launch_bounds__(1024) split_kernel(const long long* __restrict
     }
     __syncthreads();
     for (int c = 1 + warp; c < world; c += n_warps) {
-      const int v = cut_at(cum, n_packets, target[c], lane);
+      const int v = cut_at(cum, n_rows, target[c], lane);
       if (lane == 0) s[c] = v;
     }
     __syncthreads();
   }
-  if (g <= world) split[g] = s[g];
+  if (g == 0)
+    for (int c = 1; c <= world; ++c) s[c] = max(s[c], s[c - 1]);  // monotone whatever the rounds did
+  __syncthreads();
+  if (g <= world) cuts[g] = s[g];
   if (g == 0) {
-    ShardInfo si{};
-    si.p0 = s[rank];
-    si.p1 = s[rank + 1];
-    si.row_lo = 0;
-    si.row_hi = -1;
-    if (n_domains == 1 && si.p1 > si.p0) {
-      const Domain dm = domains[0];
-      const long long rows = (long long)dm.ny * dm.nz;
-      const long long lo = (long long)packets[si.p0].row_local - 2 * dm.ny - 2;
-      const long long hi = (long long)packets[si.p1 - 1].row_local + 2 * dm.ny + 2;
-      si.row_lo = (int)(lo < 0 ? 0 : lo);
-      si.row_hi = (int)(hi > rows - 1 ? rows - 1 : hi);
-      si.sel_begin = cell_start[(long long)si.row_lo * dm.nx];
-      si.sel_end = cell_start[((long long)si.row_hi + 1) * dm.nx];
+    SlabInfo si{};
+    si.own_lo = s[rank];
+    si.own_hi = s[rank + 1];
+    if (si.own_hi > si.own_lo) {
+      si.halo_lo = max(si.own_lo - layer, 0);
+      si.halo_hi = min(si.own_hi + layer, n_rows);
+      si.win_lo = max(si.own_lo - 2 * layer, 0);
+      si.win_hi = min(si.own_hi + 2 * layer, n_rows);
+    } else {
+      si.halo_lo = si.halo_hi = si.win_lo = si.win_hi = si.own_lo;
     }
     *info = si;
+    domains[0].row_lo = si.win_lo;
+    domains[0].row_hi = si.win_hi;
+    domains[0].cell_base = -(long long)si.win_lo * dm.nx;
   }
+}
+
+// stable selection of the window's points, read once from the caller's cloud and kept as {x, y, z, input index}
+struct SelPoint {
+  float x, y, z;
+  int idx;
+};
+struct LoadPoint {
+  const float* xyz;
+  int stride;
+  __device__ __forceinline__ SelPoint operator()(int i) const {
+    const float* p = xyz + (size_t)i * stride;
+    return SelPoint{p[0], p[1], p[2], i};
+  }
+};
+struct InWindow {
+  const Domain* domains;
+  float inv_cell;
+  __device__ __forceinline__ bool operator()(const SelPoint& p) const {
+    if (!finite3(p.x, p.y, p.z)) return false;
+    const Domain& dm = domains[0];
+    int cy, cz;
+    row_cells(dm, p.y, p.z, inv_cell, cy, cz);
+    const int row = cz * dm.ny + cy;
+    return row >= dm.row_lo && row < dm.row_hi;
+  }
+};
+
+// keys + the window's cell histogram
+template <typename KeyT>
+__global__ void __launch_bounds__(256) slab_key_kernel(const SelPoint* __restrict__ sel, const SlabInfo* __restrict__ info,
+                                                       const Domain* __restrict__ domains, float inv_cell, int xbits,
+                                                       KeyT* __restrict__ keys, int* __restrict__ vals,
+                                                       int* __restrict__ cellcnt) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= info->n_selected) return;
+  const Domain dm = domains[0];
+  const SelPoint p = sel[j];
+  int cy, cz;
+  row_cells(dm, p.y, p.z, inv_cell, cy, cz);
+  const int xf = xfine_coord(p.x, dm.ox, inv_cell, dm.nx, dm.xshift);
+  const long long lrow = (long long)cz * dm.ny + cy - dm.row_lo;
+  atomicAdd(cellcnt + lrow * dm.nx + (xf >> dm.xshift), 1);
+  keys[j] = (KeyT)(((unsigned long long)lrow << xbits) | (unsigned)xf);
+  vals[j] = j;
+}
+
+// packet and query ranges of the rank's own and halo rows (packet_base / cell_start at a row's first cell = packets /
+// points of the rows before it)
+__global__ void slab_ranges_kernel(const Domain* __restrict__ domains, const int* __restrict__ cell_start,
+                                   const int* __restrict__ packet_base, SlabInfo* __restrict__ info) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const Domain dm = domains[0];
+  SlabInfo si = *info;
+  auto first_cell = [&](int row) { return (long long)(row - si.win_lo) * dm.nx; };
+  si.n_packets = packet_base[first_cell(si.win_hi)];
+  si.p0 = packet_base[first_cell(si.own_lo)];
+  si.p1 = packet_base[first_cell(si.own_hi)];
+  si.ph0 = packet_base[first_cell(si.halo_lo)];
+  si.ph1 = packet_base[first_cell(si.halo_hi)];
+  si.q0 = cell_start[first_cell(si.own_lo)];
+  si.q1 = cell_start[first_cell(si.own_hi)];
+  *info = si;
+}
+
+// sorted position -> position, input index
+__global__ void __launch_bounds__(256) slab_place_kernel(const SelPoint* __restrict__ sel, const int* __restrict__ svals, int m,
+                                                         float4* __restrict__ pos, int* __restrict__ perm) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= m) return;
+  const SelPoint p = sel[svals[s]];
+  pos[s] = make_float4(p.x, p.y, p.z, 0.f);
+  perm[s] = p.idx;
 }
 
 }  // namespace
@@ -692,12 +691,21 @@ int build_grid(cab_ctx* ctx, float cell) {
     Domain& dm = ctx->domains[d];
     dm.xshift = 0;
     while (dm.xshift < 8 && ((int64_t)dm.nx << (dm.xshift + 1)) <= ((int64_t)1 << xbits)) dm.xshift++;
+    dm.row_lo = 0;
+    dm.row_hi = dm.ny * dm.nz;
   }
 
   if (int rc = reserve(ctx, ctx->b_domains, nd * sizeof(Domain))) return rc;
-  if (int rc = reserve_pinned(ctx, nd * sizeof(Domain))) return rc;
+  if (int rc = reserve_pinned(ctx, nd * sizeof(Domain) + sizeof(SlabInfo) + 64)) return rc;
   std::memcpy(ctx->h_pin, ctx->domains.data(), nd * sizeof(Domain));
   CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_domains.p, ctx->h_pin, nd * sizeof(Domain), cudaMemcpyHostToDevice, st));
+
+  ctx->slab = false;
+  ctx->slab_info_valid = false;
+  if (ctx->shard_world > 1 && nd > 1)
+    return fail(ctx, CAB_ERR_STATE, "cab_build_grid: query shards apply to one cloud; a batch of clusters shards by cluster "
+                                     "(one context per rank, each with its own clusters)");
+  if (ctx->shard_world > 1 && n_valid > 0) return build_slab(ctx, key32, xbits);
 
   // ---- keys + cell histogram ----------------------------------------------------------
   const size_t ncell1 = (size_t)cells + 1;
@@ -709,9 +717,7 @@ int build_grid(cab_ctx* ctx, float cell) {
   if (int rc = reserve(ctx, ctx->b_cellstart, ncell1 * 4)) return rc;
   if (int rc = reserve(ctx, ctx->b_pos, (size_t)std::max(n, 1) * sizeof(float4))) return rc;
   CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_cellcnt.p, 0, ncell1 * 4, st));
-  // the sharded sort of one domain selects point indices itself: no identity payload to write
-  const bool sharded_sort = ctx->shard_world > 1 && nd == 1 && n > 0;
-  int* ident = sharded_sort ? nullptr : (int*)ctx->b_vals[0].p;
+  int* ident = (int*)ctx->b_vals[0].p;
   if (n > 0 && vector_layout(ctx)) {
     const unsigned blocks = (unsigned)(((n >> 2) + 1 + 255) / 256);
     if (key32)
@@ -770,87 +776,9 @@ int build_grid(cab_ctx* ctx, float cell) {
         (Packet*)ctx->b_packets.p);
     CAB_LAUNCH_CHECK(ctx);
   }
-  // ---- cost-balanced shard boundaries, the halo and the selection for the sharded sort (multi-GPU only) ----
-  // Everything between the packet count and the sort size runs without a host round trip: the kernels read
-  // the rank's packet range and row range from the ShardInfo the split kernel leaves on the device.
-  ctx->shard_splits.clear();
-  ctx->n_halo_packets = -1;
-  int n_selected = 0, sel_begin = 0;
-  if (ctx->shard_world > 1 && ctx->n_packets > 0) {
-    const int np = ctx->n_packets, w = ctx->shard_world;
-    if (w + 1 > 64) return fail(ctx, CAB_ERR_ARG, "cab_set_shard: world > 63 not supported");
-    const int split_ints = (w + 1 + 3) & ~3;  // keeps the ShardInfo behind the splits 16-byte aligned
-    const size_t tail_bytes = (size_t)split_ints * 4 + sizeof(ShardInfo);
-    if (int rc = reserve(ctx, ctx->b_pcost, (size_t)np * 16 + tail_bytes + 64)) return rc;
-    long long* cost = (long long*)ctx->b_pcost.p;
-    long long* cum = cost + np;
-    int* split = (int*)(cum + np);
-    ShardInfo* info = (ShardInfo*)(split + split_ints);
-    size_t tmp_cost = 0, tmp_sel = 0, tmp_selk = 0;
-    thrust::counting_iterator<int> ids(0);
-    cub::DeviceScan::InclusiveSum(nullptr, tmp_cost, (const long long*)nullptr, (long long*)nullptr, np, st);
-    cub::DeviceSelect::Flagged(nullptr, tmp_sel, ids, (const unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, np, st);
-    RowRangePoint<unsigned> in32{(const unsigned*)ctx->b_keys[0].p, info, xbits};
-    RowRangePoint<unsigned long long> in64{(const unsigned long long*)ctx->b_keys[0].p, info, xbits};
-    if (sharded_sort) {
-      if (key32) cub::DeviceSelect::If(nullptr, tmp_selk, ids, (int*)nullptr, (int*)nullptr, n, in32, st);
-      else cub::DeviceSelect::If(nullptr, tmp_selk, ids, (int*)nullptr, (int*)nullptr, n, in64, st);
-    }
-    size_t tmp_all = std::max(std::max(tmp_cost, tmp_sel), std::max(tmp_selk, tmp_sort));
-    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_all + 16)) return rc;
-    if (int rc = reserve(ctx, ctx->b_rowflag, (size_t)cells + (size_t)np + 64)) return rc;
-    if (int rc = reserve(ctx, ctx->b_halo_list, ((size_t)np + 4) * 4)) return rc;
-    if (int rc = reserve_pinned(ctx, tail_bytes + 64)) return rc;
-    unsigned char* cell_flag = (unsigned char*)ctx->b_rowflag.p;
-    unsigned char* pflag = cell_flag + cells;
-    int* list = (int*)ctx->b_halo_list.p;
-    packet_cost_kernel<<<(np + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, np,
-                                                         (const int*)ctx->b_cellstart.p, cost);
-    CAB_LAUNCH_CHECK(ctx);
-    CAB_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->b_cubtmp.p, tmp_all, cost, cum, np, st));
-    split_kernel<<<1, 32 * std::min(32, std::max(2, w)), 0, st>>>(cum, np, w, ctx->shard_rank, (const Packet*)ctx->b_packets.p, (const Domain*)ctx->b_domains.p, nd,
-                                   packet_base, (const int*)ctx->b_cellstart.p, split, info);
-    CAB_LAUNCH_CHECK(ctx);
-    // halo packet list for the normals pass
-    CAB_CUDA(ctx, cudaMemsetAsync(cell_flag, 0, (size_t)cells, st));
-    mark_cells_kernel<<<(np + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, info,
-                                                        (const int*)ctx->b_cellstart.p, cell_flag);
-    CAB_LAUNCH_CHECK(ctx);
-    flag_halo_kernel<<<(np + 255) / 256, 256, 0, st>>>((const Domain*)ctx->b_domains.p, (const Packet*)ctx->b_packets.p, np, info,
-                                                       (const int*)ctx->b_cellstart.p, cell_flag, pflag);
-    CAB_LAUNCH_CHECK(ctx);
-    CAB_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_cubtmp.p, tmp_all, ids, pflag, list, list + np, np, st));  // count behind the list: the normals kernel reads it there
-    ctx->tm.kernel_launches += 4;
-    if (sharded_sort) {
-      // stable selection of the indices of the points in the rank's rows (flag computed from the key)
-      if (int rc = reserve(ctx, ctx->b_vals[1], (size_t)n * 4)) return rc;
-      if (int rc = reserve(ctx, ctx->b_keys[2], (size_t)n * 8)) return rc;
-      if (int rc = reserve(ctx, ctx->b_vals[2], (size_t)n * 4 + 16)) return rc;
-      if (key32) CAB_CUDA(ctx, cub::DeviceSelect::If(ctx->b_cubtmp.p, tmp_all, ids, (int*)ctx->b_vals[2].p, &info->n_selected, n, in32, st));
-      else CAB_CUDA(ctx, cub::DeviceSelect::If(ctx->b_cubtmp.p, tmp_all, ids, (int*)ctx->b_vals[2].p, &info->n_selected, n, in64, st));
-      ctx->tm.kernel_launches += 2;
-      CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_perm.p, 0xff, (size_t)n * 4, st));  // positions outside the rows: perm = -1
-    }
-    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, split, tail_bytes, cudaMemcpyDeviceToHost, st));
-    CAB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->h_pin + tail_bytes, list + np, 4, cudaMemcpyDeviceToHost, st));
-    CAB_CUDA(ctx, cudaStreamSynchronize(st));
-    const int* hs = (const int*)ctx->h_pin;
-    ctx->shard_splits.assign(hs, hs + w + 1);
-    ShardInfo hi;
-    std::memcpy(&hi, hs + split_ints, sizeof(ShardInfo));
-    std::memcpy(&ctx->n_halo_packets, (const char*)ctx->h_pin + tail_bytes, 4);
-    if (sharded_sort) {
-      n_selected = hi.n_selected;
-      sel_begin = hi.sel_begin;
-      if (n_selected != hi.sel_end - hi.sel_begin)
-        return fail(ctx, CAB_ERR_STATE, "cab_build_grid: shard selection holds %d points, its rows %d", n_selected,
-                    hi.sel_end - hi.sel_begin);
-    }
-  }
 
   // ---- radix sort by (row, fine x) ----------------------------------------------------
-  if (n > 0 && !sharded_sort) {
-    if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_sort + 16)) return rc;
+  if (n > 0) {
     if (key32)
       CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_sort, (const unsigned*)ctx->b_keys[0].p,
                                                     (unsigned*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
@@ -863,34 +791,9 @@ int build_grid(cab_ctx* ctx, float cell) {
     reorder_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, (const int*)ctx->b_perm.p,
                                                     (float4*)ctx->b_pos.p);
     CAB_LAUNCH_CHECK(ctx);
-  } else if (sharded_sort) {
-    const int m = n_selected;
-    if (ctx->n_packets == 0) CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_perm.p, 0xff, (size_t)n * 4, st));
-    if (m > 0) {
-      size_t tmp_have = ctx->b_cubtmp.cap;
-      if (key32)
-        gather_keys_kernel<unsigned><<<(m + 255) / 256, 256, 0, st>>>((const unsigned*)ctx->b_keys[0].p, (const int*)ctx->b_vals[2].p, m,
-                                                                     (unsigned*)ctx->b_keys[2].p);
-      else
-        gather_keys_kernel<unsigned long long><<<(m + 255) / 256, 256, 0, st>>>(
-            (const unsigned long long*)ctx->b_keys[0].p, (const int*)ctx->b_vals[2].p, m, (unsigned long long*)ctx->b_keys[2].p);
-      CAB_LAUNCH_CHECK(ctx);
-      if (key32)
-        CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_have, (const unsigned*)ctx->b_keys[2].p,
-                                                      (unsigned*)ctx->b_keys[1].p, (const int*)ctx->b_vals[2].p,
-                                                      (int*)ctx->b_vals[1].p, m, 0, end_bit, st));
-      else
-        CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_have, (const unsigned long long*)ctx->b_keys[2].p,
-                                                      (unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[2].p,
-                                                      (int*)ctx->b_vals[1].p, m, 0, end_bit, st));
-      ctx->tm.kernel_launches += 1 + (end_bit + 7) / 8;
-      place_sorted_kernel<<<(m + 255) / 256, 256, 0, st>>>(ctx->xyz_in, ctx->stride, m, sel_begin, (const int*)ctx->b_vals[1].p,
-                                                          (float4*)ctx->b_pos.p, (int*)ctx->b_perm.p);
-      CAB_LAUNCH_CHECK(ctx);
-    }
-    ctx->tm.n_sorted = m;
   }
-  if (!sharded_sort) ctx->tm.n_sorted = ctx->n_valid;
+  ctx->n_sorted = n;
+  ctx->tm.n_sorted = ctx->n_valid;
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.build_ms, ctx->ev[0], ctx->ev[1]));
@@ -900,6 +803,159 @@ int build_grid(cab_ctx* ctx, float cell) {
   ctx->tm.n_rows = rows;
   ctx->tm.n_cells = cells;
   ctx->have_grid = true;
+  return CAB_OK;
+}
+
+// The slab build of one rank (see the kernels above).  Two host round trips: the bounds (before this function) and the
+// number of points selected for the sort; everything after the second one only enqueues work.  With ctx->defer_sync the
+// function returns with the stream still running (cab_step_*): ctx->slab_info and the timings are then filled in by
+// finish_slab() after the step's final synchronisation.
+int build_slab(cab_ctx* ctx, bool key32, int xbits) {
+  const int n = (int)ctx->n;
+  cudaStream_t st = ctx->stream;
+  const Domain dm = ctx->domains[0];
+  const int64_t rows = ctx->n_rows, cells = ctx->n_cells;
+  const int w = ctx->shard_world;
+  if (w + 1 > 64) return fail(ctx, CAB_ERR_ARG, "cab_set_shard: world > 63 not supported");
+  if (rows >= (int64_t)1 << 31) return fail(ctx, CAB_ERR_OOM, "cab_build_grid: too many rows for a sharded build");
+  // ---- cuts from the sampled cell histogram ------------------------------------------------------------
+  const int sample = n >= (1 << 22) ? 8 : n >= (1 << 20) ? 4 : n >= (1 << 18) ? 2 : 1;
+  const size_t split_ints = (size_t)((w + 1 + 3) & ~3);
+  if (int rc = reserve(ctx, ctx->b_cellcnt, ((size_t)cells + 1) * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->b_pcost, (size_t)rows * 16 + 64)) return rc;
+  if (int rc = reserve(ctx, ctx->b_slab, split_ints * 4 + sizeof(SlabInfo) + 64)) return rc;
+  if (int rc = reserve(ctx, ctx->b_sel, (size_t)n * sizeof(SelPoint) + 64)) return rc;
+  long long* rowcost = (long long*)ctx->b_pcost.p;
+  long long* cum = rowcost + rows;
+  int* cuts = (int*)ctx->b_slab.p;
+  SlabInfo* info = (SlabInfo*)(cuts + split_ints);
+  Domain* d_dom = (Domain*)ctx->b_domains.p;
+  size_t tmp_cost = 0, tmp_sel = 0;
+  thrust::counting_iterator<int> ids(0);
+  auto points = thrust::make_transform_iterator(ids, LoadPoint{ctx->xyz_in, ctx->stride});
+  InWindow in_window{d_dom, ctx->inv_cell};
+  cub::DeviceScan::InclusiveSum(nullptr, tmp_cost, (const long long*)nullptr, (long long*)nullptr, (int)rows, st);
+  cub::DeviceSelect::If(nullptr, tmp_sel, points, (SelPoint*)nullptr, (int*)nullptr, n, in_window, st);
+  if (int rc = reserve(ctx, ctx->b_cubtmp, std::max(tmp_cost, tmp_sel) + 16)) return rc;
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_cellcnt.p, 0, ((size_t)cells + 1) * 4, st));
+  {
+    const long long threads = ((long long)n + 4 * sample - 1) / (4 * sample);
+    sample_hist_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, sample, d_dom,
+                                                                        ctx->inv_cell, (int*)ctx->b_cellcnt.p);
+    CAB_LAUNCH_CHECK(ctx);
+    const unsigned blocks = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->sm_count * 16);
+    row_cost_kernel<<<blocks, 256, 0, st>>>(d_dom, (const int*)ctx->b_cellcnt.p, sample, rowcost);
+    CAB_LAUNCH_CHECK(ctx);
+    CAB_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->b_cubtmp.p, tmp_cost, rowcost, cum, (int)rows, st));
+    slab_split_kernel<<<1, 32 * std::min(32, std::max(2, w)), 0, st>>>(cum, w, ctx->shard_rank, ctx->halo_permille, d_dom, cuts, info);
+    CAB_LAUNCH_CHECK(ctx);
+    // stable selection of the window's points
+    CAB_CUDA(ctx, cub::DeviceSelect::If(ctx->b_cubtmp.p, tmp_sel, points, (SelPoint*)ctx->b_sel.p, &info->n_selected, n,
+                                        in_window, st));
+    ctx->tm.kernel_launches += 4;
+  }
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, info, sizeof(SlabInfo), cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  SlabInfo si;
+  std::memcpy(&si, ctx->h_pin, sizeof(SlabInfo));
+  const int m = si.n_selected;
+  const int64_t lrows = (int64_t)si.win_hi - si.win_lo;
+  const int64_t lcells = lrows * dm.nx;
+  const size_t ncell1 = (size_t)lcells + 1;
+  // host copy of the table geometry the split kernel left on the device
+  ctx->domains[0].row_lo = si.win_lo;
+  ctx->domains[0].row_hi = si.win_hi;
+  ctx->domains[0].cell_base = -(int64_t)si.win_lo * dm.nx;
+  // ---- keys + the window's cell table, segments, packets ------------------------------------------------------
+  int lrow_bits = 1;
+  while (((int64_t)1 << lrow_bits) < std::max<int64_t>(lrows, 1)) ++lrow_bits;
+  const int end_bit = std::min(key32 ? 32 : 64, xbits + lrow_bits);
+  size_t tmp_sort = 0, tmp_scan = 0;
+  if (key32)
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr,
+                                    (int*)nullptr, m, 0, end_bit, st);
+  else
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (const int*)nullptr, (int*)nullptr, m, 0, end_bit, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (const int*)nullptr, (int*)nullptr, (int)ncell1, st);
+  size_t tmp_bytes = std::max(tmp_sort, tmp_scan);
+  const size_t mm = (size_t)std::max(m, 1);
+  const size_t max_packets = std::min<size_t>(mm, mm / kWarp + (size_t)lcells + 1);
+  if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_bytes + 16)) return rc;
+  if (int rc = reserve(ctx, ctx->b_keys[0], mm * 8)) return rc;
+  if (int rc = reserve(ctx, ctx->b_keys[1], mm * 8)) return rc;
+  if (int rc = reserve(ctx, ctx->b_vals[0], mm * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->b_vals[1], mm * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->b_perm, mm * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->b_pos, mm * sizeof(float4))) return rc;
+  if (int rc = reserve(ctx, ctx->b_cellstart, ncell1 * 4)) return rc;
+  if (int rc = reserve(ctx, ctx->b_rowpk, ncell1 * 4 * 3)) return rc;
+  if (int rc = reserve(ctx, ctx->b_packets, max_packets * sizeof(Packet))) return rc;
+  int* cellcnt = (int*)ctx->b_cellcnt.p;  // the sample histogram is no longer needed
+  int* segpk = (int*)ctx->b_rowpk.p;
+  int* packet_base = segpk + ncell1;
+  int* seglen = packet_base + ncell1;
+  CAB_CUDA(ctx, cudaMemsetAsync(cellcnt, 0, ncell1 * 4, st));
+  if (m > 0) {
+    if (key32)
+      slab_key_kernel<unsigned><<<(m + 255) / 256, 256, 0, st>>>((const SelPoint*)ctx->b_sel.p, info, d_dom, ctx->inv_cell, xbits,
+                                                                (unsigned*)ctx->b_keys[0].p, (int*)ctx->b_vals[0].p, cellcnt);
+    else
+      slab_key_kernel<unsigned long long><<<(m + 255) / 256, 256, 0, st>>>((const SelPoint*)ctx->b_sel.p, info, d_dom, ctx->inv_cell,
+                                                                          xbits, (unsigned long long*)ctx->b_keys[0].p,
+                                                                          (int*)ctx->b_vals[0].p, cellcnt);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_bytes, (const int*)cellcnt, (int*)ctx->b_cellstart.p,
+                                              (int)ncell1, st));
+  segment_kernel<<<(unsigned)((ncell1 + 255) / 256), 256, 0, st>>>(d_dom, 1, lcells, (const int*)ctx->b_cellstart.p, segpk, seglen);
+  CAB_LAUNCH_CHECK(ctx);
+  CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_bytes, segpk, packet_base, (int)ncell1, st));
+  ctx->tm.kernel_launches += 4;
+  fill_packets_kernel<<<(unsigned)((max_packets + 255) / 256), 256, 0, st>>>(d_dom, 1, lcells, (const int*)ctx->b_cellstart.p,
+                                                                            packet_base, seglen, -1, (Packet*)ctx->b_packets.p);
+  CAB_LAUNCH_CHECK(ctx);
+  slab_ranges_kernel<<<1, 32, 0, st>>>(d_dom, (const int*)ctx->b_cellstart.p, packet_base, info);
+  CAB_LAUNCH_CHECK(ctx);
+  // ---- radix sort of the window by (row, fine x) --------------------------------------------------------------
+  if (m > 0) {
+    if (key32)
+      CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_sort, (const unsigned*)ctx->b_keys[0].p,
+                                                    (unsigned*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
+                                                    (int*)ctx->b_vals[1].p, m, 0, end_bit, st));
+    else
+      CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_sort, (const unsigned long long*)ctx->b_keys[0].p,
+                                                    (unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
+                                                    (int*)ctx->b_vals[1].p, m, 0, end_bit, st));
+    ctx->tm.kernel_launches += 1 + (end_bit + 7) / 8;
+    slab_place_kernel<<<(m + 255) / 256, 256, 0, st>>>((const SelPoint*)ctx->b_sel.p, (const int*)ctx->b_vals[1].p, m,
+                                                      (float4*)ctx->b_pos.p, (int*)ctx->b_perm.p);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepSlab, info, sizeof(SlabInfo), cudaMemcpyDeviceToHost, st));
+  ctx->slab = true;
+  ctx->n_sorted = m;
+  ctx->n_valid = m;  // finite points of the local sorted arrays
+  ctx->n_cells = lcells;
+  ctx->tm.n_sorted = m;
+  ctx->tm.n_points = ctx->n;
+  ctx->tm.n_valid = m;
+  ctx->tm.n_rows = lrows;
+  ctx->tm.n_cells = lcells;
+  ctx->have_grid = true;
+  if (ctx->defer_sync) return CAB_OK;
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  return finish_slab(ctx);
+}
+
+// After the stream has drained: the host copy of the slab's ranges and the build time.
+int finish_slab(cab_ctx* ctx) {
+  std::memcpy(&ctx->slab_info, ctx->h_step + kStepSlab, sizeof(SlabInfo));
+  ctx->slab_info_valid = true;
+  ctx->n_packets = ctx->slab_info.n_packets;
+  ctx->tm.n_packets = ctx->n_packets;
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.build_ms, ctx->ev[0], ctx->ev[1]));
   return CAB_OK;
 }
 
@@ -917,14 +973,26 @@ GridView grid_view(const cab_ctx* ctx) {
 }
 
 void packet_range(const cab_ctx* ctx, int* p0, int* p1) {
-  if ((int)ctx->shard_splits.size() == ctx->shard_world + 1) {
-    *p0 = ctx->shard_splits[ctx->shard_rank];
-    *p1 = ctx->shard_splits[ctx->shard_rank + 1];
+  if (ctx->slab && ctx->slab_info_valid) {
+    *p0 = ctx->slab_info.p0;
+    *p1 = ctx->slab_info.p1;
     return;
   }
-  int64_t P = ctx->n_packets;
-  *p0 = (int)(P * ctx->shard_rank / ctx->shard_world);
-  *p1 = (int)(P * (ctx->shard_rank + 1) / ctx->shard_world);
+  *p0 = 0;
+  *p1 = ctx->n_packets;
+}
+
+// device-side {p0, p1} of the rank's own (halo = false) or own + halo packets; null when the grid is not a slab
+const int* slab_packet_range(const cab_ctx* ctx, bool halo) {
+  if (!ctx->slab) return nullptr;
+  const size_t split_ints = (size_t)((ctx->shard_world + 1 + 3) & ~3);
+  const SlabInfo* info = (const SlabInfo*)((const int*)ctx->b_slab.p + split_ints);
+  return halo ? &info->ph0 : &info->p0;
+}
+const SlabInfo* slab_info_device(const cab_ctx* ctx) {
+  if (!ctx->slab) return nullptr;
+  const size_t split_ints = (size_t)((ctx->shard_world + 1 + 3) & ~3);
+  return (const SlabInfo*)((const int*)ctx->b_slab.p + split_ints);
 }
 
 }  // namespace cab

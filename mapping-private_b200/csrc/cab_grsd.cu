@@ -371,6 +371,10 @@ __global__ void __launch_bounds__(128) signature_kernel(const VoxGrid* __restric
       if (tx < 0 || ty < 0 || tz < 0) continue;
       const int ix = (int)floorf(__fmul_rn((float)tx, inv_sub)), iy = (int)floorf(__fmul_rn((float)ty, inv_sub)),
                 iz = (int)floorf(__fmul_rn((float)tz, inv_sub));
+      // A centroid on a voxel face can land one voxel beyond the grid here (the division above against the multiply
+      // that built the grid): the reference then indexes past its histogram vector (:246-258, undefined behaviour on
+      // the host); here the voxel is left out instead of writing into a neighbouring cluster's histograms.
+      if (ix >= s.sb[0] || iy >= s.sb[1] || iz >= s.sb[2]) continue;
       hist_idx = ix + iy * s.sb[0] + iz * s.sb[0] * s.sb[1];
     }
     // pcl::VoxelGrid::getNeighborCentroidIndices [EXTERNAL]: ijk = floor(ref * inverse_leaf)
@@ -510,6 +514,7 @@ __global__ void __launch_bounds__(128) color_chlac_kernel(const VoxGrid* __restr
         if (tx < 0 || ty < 0 || tz < 0) continue;
         const int ix = (int)floorf(__fmul_rn((float)tx, inv_sub)), iy = (int)floorf(__fmul_rn((float)ty, inv_sub)),
                   iz = (int)floorf(__fmul_rn((float)tz, inv_sub));
+        if (ix >= s.sb[0] || iy >= s.sb[1] || iz >= s.sb[2]) continue;  // see signature_kernel
         hist_idx = ix + iy * s.sb[0] + iz * s.sb[0] * s.sb[1];
       }
       float* bin = H + (size_t)hist_idx * kChlacDim + t;
@@ -742,6 +747,14 @@ int cab_grsd_batch(cab_ctx* ctx, const float* xyz, int32_t stride, const int32_t
   const bool have_n = nx && ny && nz;
   if (!have_n && (nx || ny || nz)) return fail(ctx, CAB_ERR_ARG, "cab_grsd_batch: give all of nx, ny, nz or none");
   const int64_t n = offsets[nclusters];
+  // A batch shards by cluster (each rank of a group gets its own clusters), never by rows: every cluster of this call
+  // is processed here, whatever cab_set_shard says.
+  struct WholeBatch {
+    cab_ctx* c;
+    int r, w;
+    explicit WholeBatch(cab_ctx* x) : c(x), r(x->shard_rank), w(x->shard_world) { c->shard_rank = 0; c->shard_world = 1; }
+    ~WholeBatch() { c->shard_rank = r; c->shard_world = w; }
+  } whole(ctx);
   if (int rc = cab_upload_clusters(ctx, xyz, n, stride, offsets, nclusters)) return rc;
   // grsd_colorCHLAC_tools.hpp:172: std::max(rsd_radius_search, voxel_size/2 * sqrt(3)); float/2 * double
   const double r_rsd = std::max(rsd_radius_min, (double)(leaf / 2) * std::sqrt(3.0));

@@ -28,7 +28,28 @@ struct Domain {
   int swap_yz;           // 1: the grid's y slot holds the physical z axis and its z slot the physical y axis
                          // (the slowest-varying slot gets the longer of the two extents: thinner shard halos)
   int64_t row_base;      // first row id of this domain (row = row_base + cz*ny + cy)
-  int64_t cell_base;     // first cell id (cell = cell_base + (cz*ny+cy)*nx + cx)
+  int64_t cell_base;     // first cell id (cell = cell_base + (cz*ny+cy)*nx + cx); negative for a slab table, whose
+                         // first cell is the first cell of row row_lo
+  int row_lo, row_hi;    // rows [row_lo, row_hi) of this domain (row = cz*ny + cy) are present in the cell table:
+                         // all of them, or the window one rank of a multi-GPU run sorts (cab_set_shard)
+};
+
+// What one rank of a sharded run (cab_set_shard, one cloud) knows about its slab.  Rows are (cz, cy) tubes, row id =
+// cz*ny + cy; a rank answers the queries of whole rows [own_lo, own_hi), computes normals for one more layer of rows on
+// either side (halo: every candidate of its RSD pass then has a locally computed normal) and sorts two layers on either
+// side (window: the candidates of the halo rows).  Written on the device by the slab build, read there by the kernels
+// that follow it in the stream; the host copy is valid after the next synchronisation.
+struct SlabInfo {
+  int own_lo, own_hi;    // rows
+  int halo_lo, halo_hi;
+  int win_lo, win_hi;
+  int n_selected;        // points of the window = entries of the local sorted arrays
+  int n_packets;         // packets of the window
+  int p0, p1;            // own packets
+  int ph0, ph1;          // own + halo packets
+  int q0, q1;            // own queries: positions in the local sorted arrays
+  int gbase;             // position of q0 in the concatenation of all ranks' own slices (result exchange)
+  int error;             // != 0: a peer did not answer in time (result exchange)
 };
 
 // 32-query work unit: consecutive sorted points of one row.
@@ -68,6 +89,12 @@ __device__ __forceinline__ void row_cells(const Domain& dm, float y, float z, fl
   cy = cell_coord(dm.swap_yz ? z : y, dm.oy, inv_cell, dm.ny);
   cz = cell_coord(dm.swap_yz ? y : z, dm.oz, inv_cell, dm.nz);
 }
+// Is row (y, z) of the domain inside the grid and present in the cell table?
+__device__ __forceinline__ bool row_in_table(const Domain& dm, int y, int z) {
+  if (y < 0 || y >= dm.ny || z < 0 || z >= dm.nz) return false;
+  const int row = z * dm.ny + y;
+  return row >= dm.row_lo && row < dm.row_hi;
+}
 // Fine x coordinate (sub-cell resolution 2^-xshift of a cell).
 __device__ __forceinline__ int xfine_coord(float x, float ox, float inv_cell, int nx, int xshift) {
   float s = __fmul_rn(__fsub_rn(x, ox), __fmul_rn(inv_cell, (float)(1 << xshift)));
@@ -75,12 +102,26 @@ __device__ __forceinline__ int xfine_coord(float x, float ox, float inv_cell, in
   return min(max(c, 0), (nx << xshift) - 1);
 }
 
+// slots of cab_ctx::h_step
+constexpr size_t kStepSlab = 0, kStepThr = 512, kStepStats0 = 1024, kStepStats1 = 3072, kStepComm = 5120, kStepBytes = 8192;
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
 };
 
-struct SvmState;  // cab_svm.cu
+// Result exchange of a multi-GPU run (cab_comm.cu): every rank's copy of the concatenated result arrays, as pointers
+// valid on this rank (own memory, a peer device of the same process, or CUDA IPC mappings of the other processes).
+constexpr int kMaxPeers = 16;
+struct PushTargets {
+  int world;  // 0: no exchange
+  float4* nrm[kMaxPeers];
+  float2* rsd[kMaxPeers];
+  int* perm[kMaxPeers];
+};
+
+struct SvmState;   // cab_svm.cu
+struct CommState;  // cab_comm.cu
 
 }  // namespace cab
 
@@ -90,7 +131,7 @@ struct cab_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // device->host copies that overlap the next kernel (cab_normals_rsd)
-  cudaEvent_t ev[8]{};
+  cudaEvent_t ev[12]{};
   cudaEvent_t ev_ready = nullptr;      // results staged for the copy stream
   std::string err;
   cab_timings tm{};
@@ -111,16 +152,21 @@ struct cab_ctx {
   int64_t n_rows = 0, n_cells = 0;
   int n_packets = 0;
   int shard_rank = 0, shard_world = 1;
-  int n_halo_packets = -1;          // >= 0: normals run over b_halo_list (own + halo packets)
-  std::vector<int> shard_splits;   // world + 1 packet indices, cost balanced (empty: equal counts)
+  bool slab = false;               // the grid is this rank's slab of a sharded run (local sorted arrays)
+  cab::SlabInfo slab_info{};       // host copy (valid when slab_info_valid)
+  bool slab_info_valid = false;
+  int64_t n_sorted = 0;            // entries of the sorted arrays: n, or the slab window's points
+  int halo_permille = 420;         // share of the normals pass in a packet's cost (shard balance)
+  bool defer_sync = false;         // run_normals / run_rsd leave the stream running (cab_step_*: one sync per step)
 
   // device arena (grow-only)
   cab::DevBuf b_xyz, b_domoff, b_domid, b_bounds, b_domains, b_keys[3], b_vals[3], b_cubtmp, b_pos,
-      b_perm, b_cellcnt, b_cellstart, b_rowpk, b_packets, b_nrm, b_nrm_in, b_rsd, b_kcount, b_stats,
-      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost, b_halo_list, b_rowflag, b_thr_flag, b_knn_avg, b_knn_done, b_pfh[3], b_cluster;
+      b_perm, b_cellcnt, b_cellstart, b_rowpk, b_packets, b_nrm, b_nrm_in, b_rsd, b_rdif, b_kcount, b_stats,
+      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost, b_slab, b_sel, b_stats2, b_thr_flag, b_knn_avg, b_knn_done, b_pfh[3], b_cluster;
   // pinned staging
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;
+  unsigned char* h_step = nullptr;  // fixed pinned slots read back once per step (cab::kStep*)
 
   // GRSD results of the last batch
   cab::DevBuf g_vkeys[2], g_vvals[2], g_cent, g_vcount, g_vrad, g_vlabel, g_voff, g_layout, g_layoff,
@@ -133,6 +179,7 @@ struct cab_ctx {
   bool g_have_cnrm = false;        // voxel mean normals computed for the last batch
 
   cab::SvmState* svm = nullptr;    // SVM model + scaling (cab_svm.cu)
+  cab::CommState* comm = nullptr;  // multi-GPU group this context belongs to (cab_comm.cu)
 };
 
 namespace cab {
@@ -142,7 +189,12 @@ int reserve(cab_ctx* ctx, DevBuf& b, size_t bytes);
 int reserve_pinned(cab_ctx* ctx, size_t bytes);
 GridView grid_view(const cab_ctx* ctx);
 void packet_range(const cab_ctx* ctx, int* p0, int* p1);
-void read_stats(cab_ctx* ctx);  // sums the kStatSlots counters staged in ctx->h_pin into ctx->tm
+int build_slab(cab_ctx* ctx, bool key32, int xbits);          // cab_grid.cu: one rank's slab of a sharded run
+int finish_slab(cab_ctx* ctx);                                 // host copy of the slab ranges once the stream has drained
+const int* slab_packet_range(const cab_ctx* ctx, bool halo);   // device {p0, p1}; null unless the grid is a slab
+const SlabInfo* slab_info_device(const cab_ctx* ctx);
+int finish_pass_stats(cab_ctx* ctx, int pass);                 // deferred mode: timings + counters of pass 0 (normals) / 1 (RSD)
+void read_stats(cab_ctx* ctx, const void* staged = nullptr);  // sums the kStatSlots counters staged in ctx->h_pin (or `staged`) into ctx->tm
 
 #define CAB_CUDA(ctx, call)                                                                  \
   do {                                                                                       \
@@ -163,7 +215,7 @@ int compute_bounds(cab_ctx* ctx);
 int build_grid(cab_ctx* ctx, float cell);
 int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsigned char* done = nullptr);
 int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, int flags);
-int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done = nullptr);  // max_nn truncation thresholds
+int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done = nullptr, bool halo = false);  // max_nn truncation thresholds (halo: also for a slab's halo packets)
 int run_knn_mean(cab_ctx* ctx, int k, float cell_hint, double* avg);  // cab_knn.cu
 int run_normals_knn(cab_ctx* ctx, int k, const float vp[3], float cell_hint, float* nxyz_curv);  // cab_knn.cu
 int run_pfh(cab_ctx* ctx, double radius, int max_nn, int quantum, int flags, float* out);  // cab_pfh.cu
@@ -174,5 +226,12 @@ int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_
 int permute_normals_in(cab_ctx* ctx, const float* nx, const float* ny, const float* nz);
 int download_results(cab_ctx* ctx, float* n4, float* rmin, float* rmax);
 void svm_free(cab_ctx* ctx);
+void comm_free(cab_ctx* ctx);                                  // cab_comm.cu
+bool comm_active(const cab_ctx* ctx);                          // the context belongs to a group of more than one rank
+int comm_step_begin(cab_ctx* ctx);                             // after the slab build: publish this rank's query count
+int comm_step_before_push(cab_ctx* ctx);                       // before the RSD kernel: place the slice in the concatenation
+int comm_step_end(cab_ctx* ctx, double plane_radius);          // after the RSD kernel: completion flags
+int comm_step_finish(cab_ctx* ctx);                            // after the step's synchronisation
+void comm_push_targets(const cab_ctx* ctx, PushTargets* out);  // world = 0 unless a result exchange is armed for this step
 
 }  // namespace cab

@@ -5,6 +5,7 @@
 // (self included), covariance about the centroid, eigenvector of the smallest eigenvalue,
 // curvature = l0 / (l0+l1+l2), flipped towards the viewpoint; fewer than 3 neighbours -> NaN.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 
 #include "cab_internal.cuh"
@@ -52,8 +53,7 @@ __device__ __forceinline__ void smallest_eigen(T a00, T a01, T a02, T a11, T a12
 struct NormalsArgs {
   GridView g;
   int p0, p1;
-  const int* list;        // optional packet list (own + halo packets of a shard); null: [p0, p1)
-  const int* list_count;
+  const int* range;       // optional device-side {p0, p1} (own + halo packets of a slab); null: the values above
   float r, r2;
   float vpx, vpy, vpz;
   float4* nrm;              // sorted order
@@ -90,10 +90,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
   __shared__ ChunkTile tiles[kWarpsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GridView& g = a.g;
+  const int p0 = a.range ? a.range[0] : a.p0, p1 = a.range ? a.range[1] : a.p1;
   for (;;) {
-  const int wi = next_packet(a.stats, lane);
-  if (wi >= (a.list ? *a.list_count : a.p1 - a.p0)) break;
-  const int pid = a.list ? a.list[wi] : a.p0 + wi;
+  const int pid = p0 + next_packet(a.stats, lane);
+  if (pid >= p1) break;
   ChunkTile* tile = &tiles[warp];
   const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
   if (a.done && !__any_sync(kFull, pc.active && !a.done[g.perm[pc.qi]])) continue;
@@ -241,17 +241,14 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsi
   if (int rc = reserve(ctx, ctx->b_stats, kStatBytes)) return rc;
   const bool use_thr = max_nn > 0;
   if (use_thr)
-    if (int rc = run_thresholds(ctx, r, max_nn, done)) return rc;
+    if (int rc = run_thresholds(ctx, r, max_nn, done, true)) return rc;
   CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, kStatBytes, st));
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
   NormalsArgs a{};
   a.done = done;
   a.g = grid_view(ctx);
   packet_range(ctx, &a.p0, &a.p1);
-  if (ctx->n_halo_packets >= 0) {  // multi-GPU: own packets plus the rows around them
-    a.list = (const int*)ctx->b_halo_list.p;
-    a.list_count = a.list + ctx->n_packets;
-  }
+  a.range = slab_packet_range(ctx, true);  // multi-GPU: own packets plus the rows around them, read on the device
   a.r = r;
   a.r2 = r * r;
   a.vpx = vp ? vp[0] : 0.f;
@@ -262,8 +259,9 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsi
   a.thr_d2 = use_thr ? (const float*)ctx->b_thr_d2.p : nullptr;
   a.thr_idx = use_thr ? (const int*)ctx->b_thr_idx.p : nullptr;
   a.stats = (unsigned long long*)ctx->b_stats.p;
-  const int np = ctx->n_halo_packets >= 0 ? ctx->n_halo_packets : a.p1 - a.p0;
-  if (np > 0) {
+  // a slab's packet range lives on the device: launch the full persistent grid, surplus warps leave at once
+  const int np = a.range ? std::max(1, (int)std::min<int64_t>(ctx->n_sorted, INT_MAX)) : a.p1 - a.p0;
+  if (np > 0 && ctx->n_sorted > 0) {
     const dim3 blk(kWarpsPerBlock * kWarp);
     auto grid_for = [&](const void* fn) {
       int per_sm = 1;
@@ -276,17 +274,23 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsi
     else normals_kernel<false, false><<<grid_for((const void*)normals_kernel<false, false>), blk, 0, st>>>(a);
     CAB_LAUNCH_CHECK(ctx);
   }
-  if (n > ctx->n_valid) {
+  if (!ctx->slab && n > ctx->n_valid) {  // non-finite points sit behind the sorted finite ones (a slab holds none)
     fill_invalid_normals<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((float4*)ctx->b_nrm.p, (int*)ctx->b_kcount.p,
                                                                         ctx->n_valid, n);
     CAB_LAUNCH_CHECK(ctx);
   }
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->b_stats.p, kStatBytes, cudaMemcpyDeviceToHost, st));
-  CAB_CUDA(ctx, cudaStreamSynchronize(st));
-  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.normals_ms, ctx->ev[2], ctx->ev[3]));
-  read_stats(ctx);
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepStats0, ctx->b_stats.p, kStatBytes, cudaMemcpyDeviceToHost, st));
   ctx->have_normals = true;
+  if (ctx->defer_sync) return CAB_OK;
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  return finish_pass_stats(ctx, 0);
+}
+
+int finish_pass_stats(cab_ctx* ctx, int pass) {
+  if (pass == 0) CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.normals_ms, ctx->ev[2], ctx->ev[3]));
+  else CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.rsd_ms, ctx->ev[4], ctx->ev[5]));
+  read_stats(ctx, ctx->h_step + (pass == 0 ? kStepStats0 : kStepStats1));
   return CAB_OK;
 }
 

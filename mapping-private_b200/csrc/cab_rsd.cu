@@ -23,6 +23,7 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "cab_internal.cuh"
@@ -38,9 +39,13 @@ constexpr float kBinBias = 1.0f / 1024.0f;  // >> error of the rsqrt bin estimat
 struct RsdArgs {
   GridView g;
   int p0, p1;
+  const int* range;        // optional device-side {p0, p1} (own packets of a slab); null: the values above
+  const SlabInfo* slab;    // with push.world > 0: where the rank's slice sits in the concatenated results
+  PushTargets push;        // result exchange: every rank's copy of the concatenated arrays (peer memory)
   float r, r2;
   const float4* nrm;       // sorted order
   float2* out;             // sorted order (r_min, r_max)
+  float* rdif;             // sorted order: (float)(max_radius - min_radius), the subtraction in double (:206)
   const float* thr_d2;     // optional max_nn thresholds
   const int* thr_idx;
   const float* bin_thr;    // ndiv + 1 fp32 d2 thresholds, bin_thr[0] = -inf, bin_thr[ndiv] = +inf
@@ -83,6 +88,20 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
   return y;
 }
 
+// Result exchange fused into the kernel: the packet's normals, radii and input indices go straight into every rank's
+// copy of the concatenated (sorted-order) result arrays -- 32 consecutive entries per store, over NVLink for the peers.
+__device__ __forceinline__ void push_results(const PushTargets& push, const SlabInfo* slab, const GridView& g,
+                                             const PacketCtx& pc, const float4& nq, const float2 radii) {
+  if (push.world <= 0 || !pc.active) return;
+  const int gpos = slab->gbase + (pc.qi - slab->q0);
+  const int input_index = g.perm[pc.qi];
+  for (int p = 0; p < push.world; ++p) {
+    push.nrm[p][gpos] = nq;
+    push.rsd[p][gpos] = radii;
+    push.perm[p][gpos] = input_index;
+  }
+}
+
 template <bool kExact, bool kUseThr>
 __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -101,9 +120,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
   const float r2 = a.r2;
   const float bscale = a.bin_scale;
   const int last_bin = ndiv - 1;
+  const int p0 = a.range ? a.range[0] : a.p0, p1 = a.range ? a.range[1] : a.p1;
   for (;;) {
-    const int pid = a.p0 + next_packet(a.stats, lane);
-    if (pid >= a.p1) break;
+    const int pid = p0 + next_packet(a.stats, lane);
+    if (pid >= p1) break;
     const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
     const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
     const float4 nq = a.nrm[pc.qi];
@@ -197,12 +217,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
     const double max_radius = (Amint_Amin == 0) ? a.plane_radius : fmin(Amint_d / Amint_Amin, a.plane_radius);
     const double min_radius = (Amaxt_Amax == 0) ? a.plane_radius : fmin(Amaxt_d / Amaxt_Amax, a.plane_radius);
     float rmin = (float)min_radius, rmax = (float)max_radius;
+    if (pc.active) a.rdif[pc.qi] = (float)(max_radius - min_radius);
     if (a.flags & CAB_RSD_SCALE_SORT) {
       const float x = rmax * 1.1f, y = rmin * 0.9f;
       rmin = fminf(x, y);
       rmax = fmaxf(x, y);
     }
     if (pc.active) a.out[pc.qi] = make_float2(rmin, rmax);
+    push_results(a.push, a.slab, g, pc, nq, make_float2(rmin, rmax));
     unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
 #pragma unroll
     for (int o = 16; o; o >>= 1) ks += __shfl_xor_sync(kFull, ks, o);
@@ -215,9 +237,275 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
   }
 }
 
-__global__ void fill_invalid_rsd(float2* out, int begin, int end, float v) {
+// ---- the fast-mode kernel (fp32, no max_nn): every staged candidate is processed under a predicate -------------------
+// About 2 candidates in 5 are hits, and visiting only the hits (rsd_kernel above) pays for the compaction with a loop
+// whose trip count is the largest hit count of the warp, six shuffles and a recomputed d2 per hit: ~36 issue slots per
+// candidate tested.  Here the chunk's positions AND normals are staged in shared memory, and each candidate costs the
+// distance test, the cosine, a three-instruction bin estimate (sqrt.approx, FFMA, F2I) and, under the hit predicate, one
+// threshold load and two shared-memory reductions: ~22 slots, no divergence.  Differences from rsd_kernel, none in the
+// results: chunks are consecutive stream positions (coalesced loads; the packet's own queries then sit in at most two
+// chunks, and only those run the variant of the loop that knows the self bit); candidates whose normal is not finite
+// are staged far away (they never contribute, :158-172) and counted in a rare side path; the bins are two arrays
+// [bin][lane] (min |cos|, max |cos|), so that a warp's reductions never meet in a bank whatever bins its lanes hit.
+struct alignas(16) FastTile {
+  float x[kWarp], y[kWarp], z[kWarp];
+  float nx[kWarp], ny[kWarp], nz[kWarp];
+  int self_slot[kWarp];
+  int run_begin[12];
+  int run_cum[12];
+};
+
+template <bool kSelf>
+__device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float qy, float qz, float nqx, float nqy, float nqz,
+                                          float r2, float bscale, unsigned thr_addr, unsigned min_addr, unsigned max_addr, int sb) {
+  const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
+  const float4* tx = reinterpret_cast<const float4*>(tile->x);
+  const float4* ty = reinterpret_cast<const float4*>(tile->y);
+  const float4* tz = reinterpret_cast<const float4*>(tile->z);
+  const float4* tnx = reinterpret_cast<const float4*>(tile->nx);
+  const float4* tny = reinterpret_cast<const float4*>(tile->ny);
+  const float4* tnz = reinterpret_cast<const float4*>(tile->nz);
+  int k = 0;
+  auto one = [&](int m, float d2, float cnx, float cny, float cnz) {
+    // radius_estimation.cpp:153-155, the fp32 expression as written (no contraction)
+    const float cs = __fadd_rn(__fadd_rn(__fmul_rn(nqx, cnx), __fmul_rn(nqy, cny)), __fmul_rn(nqz, cnz));
+    // bin estimate biased low by kBinBias: the bin is the estimate or the next one, the exact fp32 d2 threshold decides
+    float root;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(root) : "f"(d2));
+    const int be = __float2int_rz(fmaf(root, bscale, -kBinBias));
+    const unsigned ua = __float_as_uint(fabsf(cs));
+    const unsigned ta = thr_addr + 4u + 4u * (unsigned)be;
+    if (kSelf) {
+      asm volatile(
+          "{\n\t.reg .pred p, q, s;\n\t.reg .f32 t;\n\t.reg .u32 a, b;\n\t"
+          "setp.ne.s32 s, %7, %8;\n\t"
+          "setp.le.and.f32 p, %1, %2, s;\n\t"
+          "@p ld.shared.f32 t, [%3];\n\t"
+          "setp.ge.and.f32 q, %1, t, p;\n\t"
+          "selp.u32 b, 128, 0, q;\n\t"
+          "@p add.s32 %0, %0, 1;\n\t"
+          "add.u32 a, %4, b;\n\t"
+          "@p red.shared.min.u32 [a], %6;\n\t"
+          "add.u32 a, %5, b;\n\t"
+          "@p red.shared.max.u32 [a], %6;\n\t}"
+          : "+r"(k)
+          : "f"(d2), "f"(r2), "r"(ta), "r"(min_addr + 128u * (unsigned)be), "r"(max_addr + 128u * (unsigned)be), "r"(ua), "r"(m), "r"(sb)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p, q;\n\t.reg .f32 t;\n\t.reg .u32 a, b;\n\t"
+          "setp.le.f32 p, %1, %2;\n\t"
+          "@p ld.shared.f32 t, [%3];\n\t"
+          "setp.ge.and.f32 q, %1, t, p;\n\t"
+          "selp.u32 b, 128, 0, q;\n\t"
+          "@p add.s32 %0, %0, 1;\n\t"
+          "add.u32 a, %4, b;\n\t"
+          "@p red.shared.min.u32 [a], %6;\n\t"
+          "add.u32 a, %5, b;\n\t"
+          "@p red.shared.max.u32 [a], %6;\n\t}"
+          : "+r"(k)
+          : "f"(d2), "f"(r2), "r"(ta), "r"(min_addr + 128u * (unsigned)be), "r"(max_addr + 128u * (unsigned)be), "r"(ua)
+          : "memory");
+    }
+  };
+#pragma unroll
+  for (int g4 = 0; g4 < kWarp / 4; ++g4) {
+    const float4 X = tx[g4], Y = ty[g4], Z = tz[g4];
+    const float4 NX = tnx[g4], NY = tny[g4], NZ = tnz[g4];
+    float a, b;
+    {
+      const f32x2 dx = sub2(pack2(X.x, X.y), qx2), dy = sub2(pack2(Y.x, Y.y), qy2), dz = sub2(pack2(Z.x, Z.y), qz2);
+      unpack2(add2(add2(sq2(dx), sq2(dy)), sq2(dz)), a, b);
+      one(4 * g4, a, NX.x, NY.x, NZ.x);
+      one(4 * g4 + 1, b, NX.y, NY.y, NZ.y);
+    }
+    {
+      const f32x2 dx = sub2(pack2(X.z, X.w), qx2), dy = sub2(pack2(Y.z, Y.w), qy2), dz = sub2(pack2(Z.z, Z.w), qz2);
+      unpack2(add2(add2(sq2(dx), sq2(dy)), sq2(dz)), a, b);
+      one(4 * g4 + 2, a, NX.z, NY.z, NZ.z);
+      one(4 * g4 + 3, b, NX.w, NY.w, NZ.w);
+    }
+  }
+  return k;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const RsdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FastTile* tiles = reinterpret_cast<FastTile*>(smem_raw);                          // [W]
+  unsigned* bins = reinterpret_cast<unsigned*>(tiles + kWarpsPerBlock);             // [W][2][ndiv][32]
+  float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * 2 * a.ndiv * kWarp);  // [ndiv + 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ndiv = a.ndiv;
+  for (int i = threadIdx.x; i <= ndiv; i += blockDim.x) thr[i] = a.bin_thr[i];
+  __syncthreads();
+  const GridView& g = a.g;
+  FastTile* tile = &tiles[warp];
+  unsigned* my_min = bins + (size_t)warp * 2 * ndiv * kWarp + lane;  // bin b at my_min[b * 32]
+  unsigned* my_max = my_min + ndiv * kWarp;
+  const unsigned min_addr = smem_u32(my_min), max_addr = smem_u32(my_max), thr_addr = smem_u32(thr);
+  const float r2 = a.r2, bscale = a.bin_scale;
+  const int p0 = a.range ? a.range[0] : a.p0, p1 = a.range ? a.range[1] : a.p1;
+  for (;;) {
+    const int pid = p0 + next_packet(a.stats, lane);
+    if (pid >= p1) break;
+    // the packet and its candidate runs (load_packet works on a ChunkTile; the run tables sit at the same place here)
+    PacketCtx pc;
+    {
+      const Packet pk = g.packets[pid];
+      const Domain dm = g.domains[pk.domain];
+      pc.start = pk.start;
+      pc.count = pk.count;
+      pc.active = lane < pk.count;
+      pc.qi = pk.start + min(lane, pk.count - 1);
+      pc.q = g.pos[pc.qi];
+      const float xmin = warp_min(pc.q.x), xmax = warp_max(pc.q.x);
+      const float rc = a.r * 1.00001f;
+      const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
+      const int cxlo = max((xfine_coord(xmin, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift) - 1, 0);
+      const int cxhi = min((xfine_coord(xmax, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift) + 1, dm.nx - 1);
+      const int xf_lo = xfine_coord(xmin - rc, dm.ox, g.inv_cell, dm.nx, dm.xshift);
+      const int xf_hi = xfine_coord(xmax + rc, dm.ox, g.inv_cell, dm.nx, dm.xshift);
+      const int t = lane & 15;
+      int lo = 0, hi = 0;
+      if (t < 9) {
+        const int y = cy + t % 3 - 1, z = cz + t / 3 - 1;
+        if (row_in_table(dm, y, z)) {
+          const long long c = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
+          lo = g.cell_start[c + cxlo];
+          hi = g.cell_start[c + cxhi + 1];
+        }
+      }
+      const int key = lane < 16 ? xf_lo : xf_hi + 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int xf = xfine_coord(g.pos[mid].x, dm.ox, g.inv_cell, dm.nx, dm.xshift);
+        if (xf < key) lo = mid + 1; else hi = mid;
+      }
+      const int end = __shfl_sync(kFull, lo, (lane + 16) & 31);
+      const int len = (lane < 9) ? max(end - lo, 0) : 0;
+      int cum = len;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, cum, o);
+        if (lane >= o) cum += v;
+      }
+      __syncwarp();
+      if (lane < 9) {
+        tile->run_begin[lane] = lo;
+        tile->run_cum[lane] = cum - len;
+      }
+      pc.total = __shfl_sync(kFull, cum, 8);
+      if (lane == 9) tile->run_cum[9] = pc.total;
+      __syncwarp();
+    }
+    const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
+    const float4 nq = a.nrm[pc.qi];
+    const bool q_ok = isfinite(nq.x) && isfinite(nq.y) && isfinite(nq.z);
+    for (int b = 0; b < ndiv; ++b) {
+      my_min[b * kWarp] = 0x7f800000u;  // +inf: empty
+      my_max[b * kWarp] = 0u;
+    }
+    if (a.flags & CAB_RSD_SEED_BIN0) {
+      my_min[0] = 0x3f800000u;
+      my_max[0] = 0x3f800000u;
+    }
+    int k = 0;
+    const int nchunks = (pc.total + kWarp - 1) / kWarp;
+#pragma unroll 1
+    for (int c0 = 0; c0 < nchunks; ++c0) {
+      const int p = c0 * kWarp + lane;
+      const bool valid = p < pc.total;
+      int t = (p >= tile->run_cum[4]) ? 4 : 0;
+      t += (p >= tile->run_cum[t + 2]) ? 2 : 0;
+      t += (p >= tile->run_cum[t + 1]) ? 1 : 0;
+      t += (t == 7 && p >= tile->run_cum[8]) ? 1 : 0;
+      const int j = valid ? tile->run_begin[t] + (p - tile->run_cum[t]) : -1;
+      float4 c = make_float4(3.0e30f, 3.0e30f, 3.0e30f, 0.f), cn = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        c = g.pos[j];
+        cn = a.nrm[j];
+      }
+      const bool finite_n = isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z);
+      const int own = j - pc.start;
+      const bool is_own = valid && own >= 0 && own < pc.count;
+      __syncwarp();
+      tile->x[lane] = (valid && finite_n) ? c.x : 3.0e30f;  // a candidate without a normal never contributes
+      tile->y[lane] = c.y;
+      tile->z[lane] = c.z;
+      tile->nx[lane] = cn.x;
+      tile->ny[lane] = cn.y;
+      tile->nz[lane] = cn.z;
+      const unsigned own_mask = __ballot_sync(kFull, is_own);
+      const unsigned odd_mask = __ballot_sync(kFull, valid && !finite_n);
+      if (own_mask) {
+        tile->self_slot[lane] = -1;
+        __syncwarp();
+        if (is_own) tile->self_slot[own] = lane;
+      }
+      __syncwarp();
+      if (own_mask) {
+        k += fast_chunk<true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, min_addr, max_addr, tile->self_slot[lane]);
+        k += tile->self_slot[lane] >= 0 ? 1 : 0;  // the query itself is a neighbour of the radius search (:120), just not a pair (:150)
+      } else {
+        k += fast_chunk<false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, min_addr, max_addr, -1);
+      }
+      if (odd_mask) {  // rare: neighbours without a normal still count as neighbours
+        unsigned mm = odd_mask;
+        while (mm) {
+          const int m = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const float cx = __shfl_sync(kFull, c.x, m), cy = __shfl_sync(kFull, c.y, m), cz = __shfl_sync(kFull, c.z, m);
+          const int cj = __shfl_sync(kFull, j, m);
+          if (d2_rule(cx, cy, cz, qx, qy, qz) <= r2 && cj != pc.qi) k += 1;  // the query itself is counted above
+        }
+      }
+    }
+
+    // ---- least-squares fit of the min / max angle lines, radius_estimation.cpp:175-202 ----
+    double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;
+    if (q_ok) {
+      for (int di = 0; di < ndiv; ++di) {
+        const float lo = __uint_as_float(my_min[di * kWarp]), hi = __uint_as_float(my_max[di * kWarp]);
+        if (lo != INFINITY) {  // bin not empty (:181)
+          const double p_min = fold_angle<false>(fminf(hi, 1.f));
+          const double p_max = fold_angle<false>(fminf(lo, 1.f));
+          const double f = (di + 0.5) * a.radius / ndiv;
+          Amint_Amin = __dadd_rn(Amint_Amin, __dmul_rn(p_min, p_min));
+          Amint_d = __dadd_rn(Amint_d, __dmul_rn(p_min, f));
+          Amaxt_Amax = __dadd_rn(Amaxt_Amax, __dmul_rn(p_max, p_max));
+          Amaxt_d = __dadd_rn(Amaxt_d, __dmul_rn(p_max, f));
+        }
+      }
+    }
+    const double max_radius = (Amint_Amin == 0) ? a.plane_radius : fmin(Amint_d / Amint_Amin, a.plane_radius);
+    const double min_radius = (Amaxt_Amax == 0) ? a.plane_radius : fmin(Amaxt_d / Amaxt_Amax, a.plane_radius);
+    float rmin = (float)min_radius, rmax = (float)max_radius;
+    if (pc.active) a.rdif[pc.qi] = (float)(max_radius - min_radius);
+    if (a.flags & CAB_RSD_SCALE_SORT) {
+      const float x = rmax * 1.1f, y = rmin * 0.9f;
+      rmin = fminf(x, y);
+      rmax = fmaxf(x, y);
+    }
+    if (pc.active) a.out[pc.qi] = make_float2(rmin, rmax);
+    push_results(a.push, a.slab, g, pc, nq, make_float2(rmin, rmax));
+    unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ks += __shfl_xor_sync(kFull, ks, o);
+    if (lane == 0) {
+      unsigned long long* slot = a.stats + 2 * (pid & (kStatSlots - 1));
+      atomicAdd(slot, ks);
+      atomicAdd(slot + 1, (unsigned long long)pc.total * (unsigned)pc.count);
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void fill_invalid_rsd(float2* out, float* rdif, int begin, int end, float v) {
   int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < end) out[i] = make_float2(v, v);
+  if (i < end) {
+    out[i] = make_float2(v, v);
+    rdif[i] = 0.f;
+  }
 }
 
 // Smallest fp32 d2 whose reference bin floor(ndiv*(double)sqrtf(d2)/radius) is >= b.
@@ -261,6 +549,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   const int n = (int)ctx->n;
   cudaStream_t st = ctx->stream;
   if (int rc = reserve(ctx, ctx->b_rsd, (size_t)std::max(n, 1) * sizeof(float2))) return rc;
+  if (int rc = reserve(ctx, ctx->b_rdif, (size_t)std::max(n, 1) * sizeof(float))) return rc;
   if (int rc = reserve(ctx, ctx->b_stats, kStatBytes)) return rc;
   const bool use_thr = max_nn > 0;
   if (use_thr)
@@ -271,22 +560,26 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   thr[0] = -INFINITY;
   for (int b = 1; b < ndiv; ++b) thr[b] = bin_threshold(b, ndiv, r, r2);
   thr[ndiv] = INFINITY;
-  if (int rc = reserve(ctx, ctx->b_misc, sizeof(thr))) return rc;
-  if (int rc = reserve_pinned(ctx, sizeof(thr) + kStatBytes)) return rc;
-  std::memcpy(ctx->h_pin, thr, sizeof(float) * (ndiv + 1));
-  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_misc.p, ctx->h_pin, sizeof(float) * (ndiv + 1), cudaMemcpyHostToDevice, st));
+  // staged through its own device / pinned slots: in a deferred step nothing before it in the stream has been waited for
+  if (int rc = reserve(ctx, ctx->b_stats2, sizeof(thr))) return rc;
+  std::memcpy(ctx->h_step + kStepThr, thr, sizeof(float) * (ndiv + 1));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_stats2.p, ctx->h_step + kStepThr, sizeof(float) * (ndiv + 1), cudaMemcpyHostToDevice, st));
   CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, kStatBytes, st));
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
   RsdArgs a{};
   a.g = grid_view(ctx);
   packet_range(ctx, &a.p0, &a.p1);
+  a.range = slab_packet_range(ctx, false);
+  a.slab = slab_info_device(ctx);
+  comm_push_targets(ctx, &a.push);
   a.r = rf;
   a.r2 = r2;
   a.nrm = (const float4*)ctx->b_nrm.p;
   a.out = (float2*)ctx->b_rsd.p;
+  a.rdif = (float*)ctx->b_rdif.p;
   a.thr_d2 = use_thr ? (const float*)ctx->b_thr_d2.p : nullptr;
   a.thr_idx = use_thr ? (const int*)ctx->b_thr_idx.p : nullptr;
-  a.bin_thr = (const float*)ctx->b_misc.p;
+  a.bin_thr = (const float*)ctx->b_stats2.p;
   a.ndiv = ndiv;
   a.flags = flags;
   a.bin_scale = (float)(ndiv / r);
@@ -295,26 +588,36 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   a.stats = (unsigned long long*)ctx->b_stats.p;
   const size_t smem = (size_t)kWarpsPerBlock * sizeof(ChunkTile) + (size_t)kWarpsPerBlock * ndiv * kWarp * sizeof(float2) +
                       (size_t)((ndiv + 4) & ~3) * sizeof(float) + (size_t)kWarpsPerBlock * kWarp * sizeof(int);
-  const int np = a.p1 - a.p0;
-  if (np > 0) {
+  const int np = a.range ? std::max(1, (int)std::min<int64_t>(ctx->n_sorted, INT_MAX)) : a.p1 - a.p0;
+  if (np > 0 && ctx->n_sorted > 0) {
     const unsigned blocks = (np + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int rc;
-    if (ctx->cfg.exact) rc = use_thr ? launch_rsd<true, true>(ctx, a, blocks, smem) : launch_rsd<true, false>(ctx, a, blocks, smem);
+    static const bool legacy = std::getenv("CAB_RSD_LEGACY") != nullptr;  // A/B switch for profiling
+    if (!ctx->cfg.exact && !use_thr && !legacy) {
+      const size_t fsmem = (size_t)kWarpsPerBlock * sizeof(FastTile) + (size_t)kWarpsPerBlock * 2 * ndiv * kWarp * sizeof(unsigned) +
+                           (size_t)((ndiv + 4) & ~3) * sizeof(float) + 256;
+      CAB_CUDA(ctx, cudaFuncSetAttribute(rsd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      int per_sm = 1;
+      CAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rsd_fast_kernel, kWarpsPerBlock * kWarp, fsmem));
+      const unsigned grid = std::min<unsigned>(blocks, (unsigned)std::max(per_sm, 1) * ctx->sm_count);
+      rsd_fast_kernel<<<grid, kWarpsPerBlock * kWarp, fsmem, ctx->stream>>>(a);
+      CAB_LAUNCH_CHECK(ctx);
+      rc = CAB_OK;
+    } else if (ctx->cfg.exact) rc = use_thr ? launch_rsd<true, true>(ctx, a, blocks, smem) : launch_rsd<true, false>(ctx, a, blocks, smem);
     else rc = use_thr ? launch_rsd<false, true>(ctx, a, blocks, smem) : launch_rsd<false, false>(ctx, a, blocks, smem);
     if (rc) return rc;
   }
-  if (n > ctx->n_valid) {
-    fill_invalid_rsd<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((float2*)ctx->b_rsd.p, ctx->n_valid, n,
+  if (!ctx->slab && n > ctx->n_valid) {
+    fill_invalid_rsd<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((float2*)ctx->b_rsd.p, (float*)ctx->b_rdif.p, ctx->n_valid, n,
                                                                     (float)plane_radius);
     CAB_LAUNCH_CHECK(ctx);
   }
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
-  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->b_stats.p, kStatBytes, cudaMemcpyDeviceToHost, st));
-  CAB_CUDA(ctx, cudaStreamSynchronize(st));
-  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.rsd_ms, ctx->ev[4], ctx->ev[5]));
-  read_stats(ctx);
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepStats1, ctx->b_stats.p, kStatBytes, cudaMemcpyDeviceToHost, st));
   ctx->have_rsd = true;
-  return CAB_OK;
+  if (ctx->defer_sync) return CAB_OK;
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  return finish_pass_stats(ctx, 1);
 }
 
 }  // namespace cab

@@ -278,8 +278,9 @@ __global__ void __launch_bounds__(128) neighbors_debug_kernel(const DbgArgs a) {
       tidx = a.thr_idx[s];
     }
     const long long off = a.offsets ? a.offsets[t] : 0;
-    for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1); ++z)
-      for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1); ++y) {
+    for (int z = cz - 1; z <= cz + 1; ++z)
+      for (int y = cy - 1; y <= cy + 1; ++y) {
+        if (!row_in_table(dm, y, z)) continue;
         const long long c = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
         const int b = a.g.cell_start[c + cxlo], e = a.g.cell_start[c + cxhi + 1];
         for (int j = b; j < e; ++j) {
@@ -303,14 +304,22 @@ __global__ void __launch_bounds__(128) neighbors_debug_kernel(const DbgArgs a) {
 
 }  // namespace
 
-int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done) {
+int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done, bool halo) {
   const int n = (int)ctx->n;
   cudaStream_t st = ctx->stream;
+  if (ctx->slab && !ctx->slab_info_valid) {  // the launch dimensions below need the slab's packet ranges on the host
+    CAB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (int rc = finish_slab(ctx)) return rc;
+  }
   if (int rc = reserve(ctx, ctx->b_thr_d2, (size_t)std::max(n, 1) * sizeof(float))) return rc;
   if (int rc = reserve(ctx, ctx->b_thr_idx, (size_t)std::max(n, 1) * sizeof(int))) return rc;
   ThrArgs a{};
   a.g = grid_view(ctx);
   packet_range(ctx, &a.p0, &a.p1);
+  if (ctx->slab && halo) {
+    a.p0 = ctx->slab_info.ph0;
+    a.p1 = ctx->slab_info.ph1;
+  }
   a.r = r;
   a.r2 = r * r;
   a.max_nn = max_nn;
@@ -337,6 +346,7 @@ int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done)
 int64_t run_neighbors_debug(cab_ctx* ctx, float r, int max_nn, int64_t q0, int64_t q1, int64_t* offsets, int32_t* idx,
                             float* d2, int64_t cap) {
   if (!ctx->have_grid) return fail(ctx, CAB_ERR_STATE, "cab_neighbors_debug: build the grid first");
+  if (ctx->slab) return fail(ctx, CAB_ERR_STATE, "cab_neighbors_debug: needs the whole grid, this context holds one shard's slab");
   if (q0 < 0 || q1 < q0 || q1 > ctx->n) return fail(ctx, CAB_ERR_ARG, "cab_neighbors_debug: bad query range");
   if (!offsets) return fail(ctx, CAB_ERR_ARG, "cab_neighbors_debug: offsets is NULL");
   if (!(r > 0.f) || r > ctx->cell * 1.0000001f)
@@ -361,13 +371,7 @@ int64_t run_neighbors_debug(cab_ctx* ctx, float r, int max_nn, int64_t q0, int64
   long long* d_off = (long long*)scratch.p;
   int* d_cnt = (int*)((char*)scratch.p + off_bytes);
   if (max_nn > 0) {
-    int save_r = ctx->shard_rank, save_w = ctx->shard_world;
-    ctx->shard_rank = 0;
-    ctx->shard_world = 1;  // thresholds for every query
-    int rc = run_thresholds(ctx, r, max_nn);
-    ctx->shard_rank = save_r;
-    ctx->shard_world = save_w;
-    if (rc) return rc;
+    if (int rc = run_thresholds(ctx, r, max_nn)) return rc;
     if (int rc2 = reserve(ctx, ctx->b_out1a, (size_t)n * 4)) return rc2;
     inverse_perm_kernel<<<(n + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, n, (int*)ctx->b_out1a.p);
     CAB_LAUNCH_CHECK(ctx);

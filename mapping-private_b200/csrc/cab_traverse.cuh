@@ -107,7 +107,7 @@ __device__ __forceinline__ PacketCtx load_packet(const GridView& g, int pid, int
   int lo = 0, hi = 0;
   if (t < 9) {
     const int y = cy + t % 3 - 1, z = cz + t / 3 - 1;
-    if (y >= 0 && y < dm.ny && z >= 0 && z < dm.nz) {
+    if (row_in_table(dm, y, z)) {
       const long long c = dm.cell_base + ((long long)z * dm.ny + y) * dm.nx;
       lo = g.cell_start[c + cxlo];
       hi = g.cell_start[c + cxhi + 1];

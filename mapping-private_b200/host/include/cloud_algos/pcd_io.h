@@ -53,12 +53,22 @@ inline bool readPCDXYZ (const char* name, std::vector<float>& xyz, std::vector<f
     else if (key == "DATA") { is >> data_mode; payload = fs.tellg (); break; }
   }
   if (fields.empty () || data_mode.empty ()) { if (error) *error = "not a PCD file"; return false; }
-  if (points < 0) points = width * height;
+  // the header of an untrusted file decides every allocation below: check it first
+  if (points < 0)
+  {
+    if (width < 0 || height < 0 || (height > 0 && width > (1L << 31) / height))
+      { if (error) *error = "PCD header without a usable POINTS / WIDTH x HEIGHT"; return false; }
+    points = width * height;
+  }
+  if (points > (1L << 31) - 16) { if (error) *error = "PCD header declares too many points"; return false; }
   if (size.empty ()) size.assign (fields.size (), 4);   // old headers without SIZE / TYPE: float32 columns
   if (type.empty ()) type.assign (fields.size (), 'F');
   if (count.empty ()) count.assign (fields.size (), 1);
   if (size.size () != fields.size () || type.size () != fields.size () || count.size () != fields.size ())
     { if (error) *error = "inconsistent PCD header"; return false; }
+  for (size_t f = 0; f < fields.size (); ++f)
+    if ((size[f] != 1 && size[f] != 2 && size[f] != 4 && size[f] != 8) || count[f] < 1 || count[f] > 65536)
+      { if (error) *error = "PCD header with an invalid SIZE or COUNT"; return false; }
   int col[6] = {-1, -1, -1, -1, -1, -1};   // column (in scalar elements) of x y z normal_x normal_y normal_z
   int off[6] = {-1, -1, -1, -1, -1, -1};   // byte offset inside a binary record
   int ncols = 0, rec = 0;
@@ -76,6 +86,14 @@ inline bool readPCDXYZ (const char* name, std::vector<float>& xyz, std::vector<f
   if (col[0] < 0 || col[1] < 0 || col[2] < 0) { if (error) *error = "PCD file without float x, y, z fields"; return false; }
   const bool have_n = normals && col[3] >= 0 && col[4] >= 0 && col[5] >= 0;
   const bool have_rgb = rgb && rgb_col >= 0;
+  {  // the payload must be there before anything of its declared size is allocated (an ASCII row has >= 2 bytes)
+    const std::streampos here = fs.tellg ();
+    fs.seekg (0, std::ios::end);
+    const std::streamoff have = fs.tellg ();
+    fs.seekg (here);
+    const std::streamoff per_point = data_mode == "binary" ? (std::streamoff) rec : 2;
+    if (per_point <= 0 || (std::streamoff) points > have / per_point) { if (error) *error = "truncated PCD file"; return false; }
+  }
   xyz.resize ((size_t) points * 3);
   if (have_n) normals->resize ((size_t) points * 3);
   if (have_rgb) rgb->resize ((size_t) points);
@@ -107,6 +125,7 @@ inline bool readPCDXYZ (const char* name, std::vector<float>& xyz, std::vector<f
   if (data_mode != "binary") { if (error) *error = "unsupported PCD DATA mode " + data_mode; return false; }
   fs.seekg (0, std::ios::end);
   const std::streamoff file_size = fs.tellg ();
+  if (rec <= 0) { if (error) *error = "PCD header with empty records"; return false; }
   const std::streamoff need = (std::streamoff) points * rec;
   // page-padded header of the older writers: exactly one 4096-byte page before the records
   if (file_size - 4096 == need && (std::streamoff) payload <= 4096) payload = 4096;

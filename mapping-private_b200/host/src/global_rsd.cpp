@@ -113,6 +113,13 @@ std::string GlobalRSD::process (const boost::shared_ptr<const GlobalRSD::InputTy
   {
     int64_t voff[2] = {0, 0};
     const int64_t nv = cab_grsd_voxels (ctx, voff, 0, 0, 0, 0, 0);
+    if (nv < 0)
+    {
+      output_valid_ = false;
+      err = std::string ("GRSD voxel download failed: ") + cab_last_error (ctx);
+      ROS_ERROR ("[GlobalRSD] %s", err.c_str ());
+      return err;
+    }
     std::vector<float> c (3 * (size_t) nv), rmin ((size_t) nv), rmax ((size_t) nv);
     std::vector<int32_t> lab ((size_t) nv);
     if (nv > 0) cab_grsd_voxels (ctx, voff, &c[0], &rmin[0], &rmax[0], &lab[0], nv);

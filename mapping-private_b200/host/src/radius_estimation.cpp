@@ -86,6 +86,8 @@ std::string LocalRadiusEstimation::process (const boost::shared_ptr<const LocalR
   if (rc == CAB_OK) rc = cab_build_grid (ctx, (float) radius_);
   if (rc == CAB_OK) rc = cab_set_normals (ctx, nx, ny, nz);
   if (rc == CAB_OK) rc = cab_rsd (ctx, radius_, max_nn_, distance_div_, plane_radius_, 0, rmin, rmax);
+  // r_dif is rounded from the double difference (radius_estimation.cpp:206), not from the rounded radii
+  if (rc == CAB_OK && n) rc = cab_download_rdif (ctx, &cloud_radius_->channels[rIdx + 2].values[0]);
   if (rc != CAB_OK)
   {
     output_valid_ = false;
@@ -95,7 +97,6 @@ std::string LocalRadiusEstimation::process (const boost::shared_ptr<const LocalR
   }
   for (size_t cp = 0; cp < n; ++cp)
   {
-    cloud_radius_->channels[rIdx + 2].values[cp] = rmax[cp] - rmin[cp];
     if (rmin2curvature_ && cIdx != -1) cloud_radius_->channels[cIdx].values[cp] = rmin[cp];
     if (point_label_ != -1) cloud_radius_->channels[labelIdx].values[cp] = point_label_;
   }

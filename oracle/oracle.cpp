@@ -197,11 +197,12 @@ void eig3_jacobi(const double a[6], double w[3], double v[3][3]) {
 // call site grsd_colorCHLAC_tools.hpp:76-81).  Coordinates are taken relative to
 // the query so the double sums are exact for lattice inputs.
 void pca_normal(const float* xyz, const float* q, const std::vector<Nb>& nbs, const float* vp,
-                float out[4]) {
+                float out[4], float* gap = nullptr) {
   const float nan = std::numeric_limits<float>::quiet_NaN();
   size_t k = nbs.size();
   if (k < 3) {
     out[0] = out[1] = out[2] = out[3] = nan;
+    if (gap) *gap = nan;
     return;
   }
   double s1[3] = {0, 0, 0}, s2[6] = {0, 0, 0, 0, 0, 0};
@@ -238,6 +239,8 @@ void pca_normal(const float* xyz, const float* q, const std::vector<Nb>& nbs, co
     nz = -nz;
   }
   double tr = w[0] + w[1] + w[2];
+  // conditioning of the normal: a perturbation e of the covariance turns it by about e / (l1 - l0)
+  if (gap) *gap = (tr != 0.0) ? (float)((w[1] - w[0]) / tr) : 0.0f;
   out[0] = (float)nx;
   out[1] = (float)ny;
   out[2] = (float)nz;
@@ -591,6 +594,29 @@ int orc_normals(const float* xyz, int n, double r, int max_nn, const float* vp, 
   return 0;
 }
 
+// The normals of orc_normals plus their conditioning (l1 - l0) / (l0 + l1 + l2): the parity gates list the points whose
+// own decision margin is below the noise of any fp32 implementation instead of dropping them.
+int orc_normals_gap(const float* xyz, int n, double r, int max_nn, const float* vp, float* out_n4, float* out_gap,
+                    int nthreads) {
+  CellGrid grid(xyz, n, r);
+  const float r2 = r2_of(r);
+  const float zero[3] = {0, 0, 0};
+  if (!vp) vp = zero;
+  nthreads = resolve_threads(nthreads);
+#pragma omp parallel num_threads(nthreads)
+  {
+    std::vector<Nb> nbs;
+#pragma omp for schedule(dynamic, 512)
+    for (int i = 0; i < n; ++i) {
+      const float* q = xyz + 3 * (size_t)i;
+      grid.query(q, r2, nbs);
+      if (max_nn > 0 && (int)nbs.size() > max_nn) sort_truncate(nbs, max_nn);
+      pca_normal(xyz, q, nbs, vp, out_n4 + 4 * (size_t)i, out_gap + i);
+    }
+  }
+  return 0;
+}
+
 // k-NN normals: nearestKSearch (i, k_) + computePointNormal + flipNormalTowardsViewpoint as in
 // cloud_tools/src/table_object_detector_passive.cpp:668-714 and cloud_algos/src/cylinder_fit_algo.cpp:138-203
 // [point_cloud_mapping, EXTERNAL]: the PCA of orc_normals over the k smallest (d2, index) pairs, the query included.
@@ -860,6 +886,7 @@ int orc_grsd21_subdiv(const float* centroids, int nvox, const int32_t* types, fl
       int ix = (int)std::floor(tmp_x * inverse_subdivision_size);
       int iy = (int)std::floor(tmp_y * inverse_subdivision_size);
       int iz = (int)std::floor(tmp_z * inverse_subdivision_size);
+      if (ix >= sb[0] || iy >= sb[1] || iz >= sb[2]) continue;  // the reference indexes past its vector here (UB): voxel left out
       hist_idx = ix + iy * sb[0] + iz * sb[0] * sb[1];
     }
     int src = types[v];
@@ -1010,6 +1037,7 @@ int orc_grsd_signature(int kind, const float* centroids, const float* cent_norma
       int ix = (int)std::floor(tmp_x * inverse_subdivision_size);
       int iy = (int)std::floor(tmp_y * inverse_subdivision_size);
       int iz = (int)std::floor(tmp_z * inverse_subdivision_size);
+      if (ix >= sb[0] || iy >= sb[1] || iz >= sb[2]) continue;  // see orc_grsd21: out of range in the reference
       hist_idx = ix + iy * sb[0] + iz * sb[0] * sb[1];
     }
     int32_t* H = R.data() + (size_t)hist_idx * raw;
@@ -1259,6 +1287,7 @@ int orc_color_chlac117(int c3, const float* centroids, const uint32_t* rgb, int 
       if (tmp_x < 0 || tmp_y < 0 || tmp_z < 0) continue;
       const int ix = (int)std::floor(tmp_x * inverse_subdivision_size), iy = (int)std::floor(tmp_y * inverse_subdivision_size),
                 iz = (int)std::floor(tmp_z * inverse_subdivision_size);
+      if (ix >= sb[0] || iy >= sb[1] || iz >= sb[2]) continue;  // see orc_grsd21: out of range in the reference
       hist_idx = ix + iy * sb[0] + iz * sb[0] * sb[1];
     }
     float* H = hist + (size_t)hist_idx * DIM;

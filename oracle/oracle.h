@@ -61,6 +61,9 @@ int64_t orc_radius_search_brute(const float* surface_xyz, int n, const float* qu
  * out_n4: n x {nx,ny,nz,curvature}; out_k (optional): neighbour counts. */
 int orc_normals(const float* xyz, int n, double r, int max_nn, const float* vp,
                 float* out_n4, int32_t* out_k, int nthreads);
+/* Same normals plus the eigenvalue gap (l1 - l0) / trace of every point (NaN where the normal is NaN). */
+int orc_normals_gap(const float* xyz, int n, double r, int max_nn, const float* vp, float* out_n4, float* out_gap,
+                    int nthreads);
 
 /* RSD for every point of a cloud with per-point normals (stride floats apart).
  * Restates radius_estimation.cpp:140-215.  Outputs are fp32 like the reference's

@@ -90,6 +90,18 @@ def normals(xyz, r, max_nn=0, vp=(0.0, 0.0, 0.0), nthreads=0):
     return out, k
 
 
+def normals_gap(xyz, r, max_nn=0, vp=(0.0, 0.0, 0.0), nthreads=0):
+    """Returns (n4 (n,4), gap (n,)): the normals of normals() and their conditioning (l1 - l0) / trace."""
+    L = lib()
+    p = _xyz(xyz)
+    out = np.empty((p.shape[0], 4), dtype=np.float32)
+    gap = np.empty(p.shape[0], dtype=np.float32)
+    v = np.asarray(vp, dtype=np.float32)
+    L.orc_normals_gap(_ptr(p, C.c_float), p.shape[0], C.c_double(r), int(max_nn), _ptr(v, C.c_float),
+                      _ptr(out, C.c_float), _ptr(gap, C.c_float), int(nthreads))
+    return out, gap
+
+
 def rsd(xyz, nrm, r, max_nn=0, ndiv=10, plane_radius=0.1, flags=0, nthreads=0):
     """In-tree LocalRadiusEstimation arithmetic. nrm: (n,3) or (n,4). Returns r_min, r_max, r_dif."""
     L = lib()

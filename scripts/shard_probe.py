@@ -1,5 +1,7 @@
 """Runs the W shards of the 20M-point room one after the other on ONE GPU and prints per-shard
-kernel times and work statistics (used to tune the multi-GPU split without an 8-GPU box)."""
+kernel times and work statistics (used to tune the multi-GPU split without an 8-GPU box): each shard's
+cab_step_normals_rsd (slab build + normals of own and halo rows + RSD of own rows), without the result exchange.
+usage: python scripts/shard_probe.py [W] [points] [halo_permille]"""
 import sys, pathlib
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -14,17 +16,19 @@ ctx.upload(pts)
 rows = []
 for g in range(W):
     ctx.set_shard(g, W)
-    ctx.build_grid(0.02)
-    ctx.build_grid(0.02)
-    pb = ctx.profile()
+    best = None
+    for _ in range(4):
+        ctx.step_normals_rsd(0.02, 0.02)
+        p = ctx.profile()
+        if best is None or p['step_ms'] < best['step_ms']:
+            best = p
     b, e = ctx.shard_range()
-    for _ in range(2):
-        ctx.normals(0.02, download=False)
-        p1 = ctx.profile()
-        ctx.rsd(0.02, download=False)
-        p2 = ctx.profile()
     q = max(e - b, 1)
-    rows.append((g, b, e, p1['normals_ms'], p2['rsd_ms'], p2['neighbour_sum'] / q, p2['candidate_sum'] / q, pb['build_ms'], pb['n_sorted']))
-for g, b, e, tn, tr, k, c, tb, ns in rows:
+    rows.append((g, b, e, best))
+tot = 0.0
+for g, b, e, p in rows:
     q = max(e - b, 1)
-    print(f"shard {g:3d}: [{b:9d},{e:9d}) q {q:8d} normals {tn:6.3f} ms rsd {tr:6.3f} ms k/q {k:6.1f} cand/q {c:7.1f} ns/q n {1e6*tn/q:6.2f} r {1e6*tr/q:6.2f} build {tb:6.3f} ms sorted {ns:9d} total {tb+tn+tr:6.3f} ms")
+    print(f"shard {g:3d}: q {q:8d} sorted {p['n_sorted']:9d} packets {p['n_packets']:7d} build {p['build_ms']:6.3f} normals {p['normals_ms']:6.3f} "
+          f"rsd {p['rsd_ms']:6.3f} step {p['step_ms']:6.3f} ms  k/q {p['neighbour_sum'] / q:6.1f} cand/q {p['candidate_sum'] / q:7.1f}")
+    tot = max(tot, p['step_ms'])
+print(f"W {W}: slowest shard step {tot:.3f} ms")

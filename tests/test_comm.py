@@ -1,0 +1,210 @@
+"""Multi-GPU data plane behind the C ABI (csrc/cab_comm.cu, cab_step_normals_rsd): slab-sharded ranks whose RSD kernel
+stores its results straight into every rank's copy of the concatenated arrays.  The single-GPU result is the checker:
+every rank of a group must end up with exactly those bits.
+
+* contexts of one process (cab_comm_init_local), three ranks on cuda:0, one host thread each;
+* one process per rank, CUDA IPC (cab_comm_reserve / cab_comm_connect), two ranks on cuda:0;
+* NCCL bootstrap (cab_comm_get_id / cab_comm_init) + the integer all-reduce, two ranks on two GPUs (skipped on one).
+"""
+import multiprocessing as mp
+import threading
+
+import numpy as np
+import pytest
+
+from mapping_private_b200 import cab, synth
+
+import comm_workers  # tests/comm_workers.py: the rank processes (importable without conftest)
+
+pytestmark = pytest.mark.gpu
+
+R = 0.02
+
+
+def _single_gpu(pts, exact=False, max_nn=0):
+    c = cab.Context(0, exact=exact)
+    c.upload(pts)
+    c.build_grid(R)
+    n4 = c.normals(R, max_nn=max_nn)
+    rmin, rmax = c.rsd(R, max_nn=max_nn)
+    k = c.profile()["neighbour_sum"]
+    c.close()
+    return n4, rmin, rmax, k
+
+
+def _same(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
+
+
+def test_step_equals_the_three_stages():
+    """cab_step_normals_rsd (one synchronisation per step) leaves the bits of build + normals + RSD."""
+    pts = synth.tabletop(40_000, noise_sigma=0.0003)
+    pts[11] = np.nan
+    n4, rmin, rmax, k = _single_gpu(pts)
+    c = cab.Context(0)
+    c.upload(pts)
+    for _ in range(2):
+        c.step_normals_rsd(R, R)
+        s4, smin, smax = c.download()
+        assert _same(s4, n4) and _same(smin, rmin) and _same(smax, rmax)
+        p = c.profile()
+        assert p["neighbour_sum"] == k and p["step_ms"] > 0
+    dif = c.download_rdif()
+    assert np.abs(dif - (rmax - rmin)).max() <= np.spacing(np.float32(0.1))
+    c.close()
+
+
+@pytest.mark.parametrize("world,max_nn", [(3, 0), (2, 60)])
+def test_local_group_every_rank_holds_all_results(world, max_nn):
+    """Three contexts of this process on one GPU: after the step EVERY rank's concatenated arrays hold the single-GPU
+    results of all points (input order through cab_comm_download_range), pushed there by the ranks' RSD kernels."""
+    pts = synth.tabletop(90_000, noise_sigma=0.0002)
+    pts[5] = np.nan  # nobody's query
+    n = pts.shape[0]
+    n4, rmin, rmax, k = _single_gpu(pts, max_nn=max_nn)
+    ctxs = [cab.Context(0) for _ in range(world)]
+    cab.comm_init_local(ctxs)
+    out, errs = [None] * world, []
+
+    def work(r):
+        try:
+            c = ctxs[r]
+            for it in range(2):  # the second step reuses the connected buffers
+                c.comm_upload_cloud(pts)
+                c.step_normals_rsd(R, R, max_nn_normals=max_nn, max_nn_rsd=max_nn)
+            full = c.comm_download_range(0, n)
+            lo, hi = n * r // world, n * (r + 1) // world
+            part = c.comm_download_range(lo, hi)
+            out[r] = (full, part, c.profile(), c.shard_range())
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not errs, errs
+    total_k = 0
+    for r in range(world):
+        (f4, fmin, fmax), (p4, pmin, pmax), prof, (b, e) = out[r]
+        assert _same(f4, n4) and _same(fmin, rmin) and _same(fmax, rmax), f"rank {r}"
+        lo, hi = n * r // world, n * (r + 1) // world
+        assert _same(p4, n4[lo:hi]) and _same(pmin, rmin[lo:hi]) and _same(pmax, rmax[lo:hi])
+        total_k += prof["neighbour_sum"]
+        assert e > b
+    if max_nn == 0:
+        assert total_k == k  # every query answered by exactly one rank
+    for c in ctxs:
+        c.close()
+
+
+def test_local_group_grsd_allreduce():
+    """Cluster-per-rank GRSD: the ranks' integer histograms summed through cab_comm_allreduce_i32."""
+    xyz, off = synth.clusters(6, 1300, 2500)
+    one = cab.Context(0, exact=True)
+    want = one.grsd_batch(xyz, off, 0.025)
+    one.close()
+    world = 2
+    ctxs = [cab.Context(0, exact=True) for _ in range(world)]
+    cab.comm_init_local(ctxs)
+    got, errs = [None] * world, []
+
+    def work(r):
+        try:
+            mine = [c for c in range(6) if c % world == r]
+            sub = np.concatenate([xyz[off[c]:off[c + 1]] for c in mine])
+            soff = np.concatenate([[0], np.cumsum([off[c + 1] - off[c] for c in mine])]).astype(np.int32)
+            hist = np.zeros((6, 21), np.int32)
+            hist[mine] = ctxs[r].grsd_batch(sub, soff, 0.025)
+            got[r] = ctxs[r].comm_allreduce_i32(hist)
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not errs, errs
+    for r in range(world):
+        assert np.array_equal(got[r], want)
+    for c in ctxs:
+        c.close()
+
+
+def _run_processes(world, devices, pts):
+    ctx = mp.get_context("spawn")
+    pipes, procs = [], []
+    for r in range(world):
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=comm_workers.ipc_worker, args=(r, world, devices[r], pts, b), daemon=True)
+        p.start()
+        pipes.append(a)
+        procs.append(p)
+    try:
+        blobs = []
+        for a in pipes:
+            assert a.poll(180), "worker did not report its buffers"
+            blobs.append(a.recv())
+        for a in pipes:
+            a.send(blobs)
+        res = []
+        for a in pipes:
+            assert a.poll(300), "worker did not finish"
+            res.append(a.recv())
+        for a in pipes:
+            a.send("bye")
+        return res
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+
+
+def test_ipc_group_two_processes_one_gpu():
+    """One process per rank, buffers shared through CUDA IPC handles the application moved (no NCCL)."""
+    pts = synth.tabletop(60_000, noise_sigma=0.0002)
+    n = pts.shape[0]
+    n4, rmin, rmax, _ = _single_gpu(pts)
+    res = _run_processes(2, [0, 0], pts)
+    for r, (status, part, full) in enumerate(res):
+        assert status == "ok", part
+        lo, hi = n * r // 2, n * (r + 1) // 2
+        p4, pmin, pmax = part
+        assert _same(p4, n4[lo:hi]) and _same(pmin, rmin[lo:hi]) and _same(pmax, rmax[lo:hi])
+        assert _same(full[1], rmin) and _same(full[2], rmax)
+
+
+def test_nccl_group_two_gpus():
+    """cab_comm_get_id / cab_comm_init: NCCL moves the IPC handles, the pushes cross NVLink, the all-reduce is NCCL's."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    pts = synth.tabletop(80_000, noise_sigma=0.0002)
+    n4, rmin, rmax, _ = _single_gpu(pts)
+    comm_id = cab.comm_get_id()
+    ctx = mp.get_context("spawn")
+    pipes, procs = [], []
+    for r in range(2):
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=comm_workers.nccl_worker, args=(r, 2, comm_id, pts, b), daemon=True)
+        p.start()
+        pipes.append(a)
+        procs.append(p)
+    try:
+        for a in pipes:
+            assert a.poll(300), "worker did not finish"
+            status, full, h = a.recv()
+            assert status == "ok", full
+            assert _same(full[0], n4) and _same(full[1], rmin) and _same(full[2], rmax)
+            assert (h == 3).all()
+        for a in pipes:
+            a.send("bye")
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
