@@ -301,12 +301,12 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(const Domain* __restr
 // to be representative.  Inside the window the sort, cell table, segments and packets are the unsharded ones (same
 // keys, stable selection, stable sort), so a rank's results equal the single-GPU results bit for bit.
 
-// cell histogram of every S-th group of four points
+// cell histogram of every S-th run of 256 consecutive points (3 KB: whole DRAM bursts, unlike a stride of single points)
 __global__ void __launch_bounds__(256) sample_hist_kernel(const float* __restrict__ xyz, int stride, int n, int sample,
                                                           const Domain* __restrict__ domains, float inv_cell,
                                                           int* __restrict__ cellcnt) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long first = t * 4 * sample;
+  const long long first = ((t >> 6) * sample * 64 + (t & 63)) * 4;
   if (first >= n) return;
   const Domain dm = domains[0];
   const int last = (int)min((long long)n, first + 4);
@@ -448,49 +448,103 @@ __global__ void __launch_bounds__(1024) slab_split_kernel(const long long* __res
   }
 }
 
-// stable selection of the window's points, read once from the caller's cloud and kept as {x, y, z, input index}
+// Stable selection of the window's points, read once from the caller's cloud and kept as {x, y, z, input index}.
+// Two small kernels instead of a library select (whose look-back pass over 20 M twelve-byte items took 220 us): each
+// block compacts its own 2048 consecutive points, in order, into its own stretch of the staging array and leaves its
+// count; after a scan of the ~10 k counts the key kernel walks the blocks' stretches and numbers the points
+// consecutively -- input order is preserved (the radix sort is stable, so equal keys keep the unsharded order).
 struct SelPoint {
   float x, y, z;
   int idx;
 };
-struct LoadPoint {
-  const float* xyz;
-  int stride;
-  __device__ __forceinline__ SelPoint operator()(int i) const {
-    const float* p = xyz + (size_t)i * stride;
-    return SelPoint{p[0], p[1], p[2], i};
-  }
-};
-struct InWindow {
-  const Domain* domains;
-  float inv_cell;
-  __device__ __forceinline__ bool operator()(const SelPoint& p) const {
-    if (!finite3(p.x, p.y, p.z)) return false;
-    const Domain& dm = domains[0];
-    int cy, cz;
-    row_cells(dm, p.y, p.z, inv_cell, cy, cz);
-    const int row = cz * dm.ny + cy;
-    return row >= dm.row_lo && row < dm.row_hi;
-  }
-};
+constexpr int kSelChunk = 2048;  // points per selection block (256 threads x 8 consecutive points)
 
-// keys + the window's cell histogram
+__device__ __forceinline__ bool in_window(const Domain& dm, float inv_cell, float x, float y, float z) {
+  if (!finite3(x, y, z)) return false;
+  int cy, cz;
+  row_cells(dm, y, z, inv_cell, cy, cz);
+  const int row = cz * dm.ny + cy;
+  return row >= dm.row_lo && row < dm.row_hi;
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(256) slab_select_kernel(const float* __restrict__ xyz, int stride, int n,
+                                                          const Domain* __restrict__ domains, float inv_cell,
+                                                          SelPoint* __restrict__ stage, int* __restrict__ counts) {
+  __shared__ int warp_sum[8];
+  const Domain dm = domains[0];
+  const int base = blockIdx.x * kSelChunk + threadIdx.x * 8;  // this thread's 8 consecutive points
+  float px[8], py[8], pz[8];
+  unsigned keep = 0;
+  if (kVec && base + 8 <= n) {
+    const float4* v = reinterpret_cast<const float4*>(xyz);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const Pts4 p = load_pts4(v, (base >> 2) + h);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        px[4 * h + k] = p.x[k];
+        py[4 * h + k] = p.y[k];
+        pz[4 * h + k] = p.z[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) keep |= in_window(dm, inv_cell, px[k], py[k], pz[k]) ? 1u << k : 0u;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (base + k < n) {
+        const float* p = xyz + (size_t)(base + k) * stride;
+        px[k] = p[0];
+        py[k] = p[1];
+        pz[k] = p[2];
+        keep |= in_window(dm, inv_cell, px[k], py[k], pz[k]) ? 1u << k : 0u;
+      }
+    }
+  }
+  const int mine = __popc(keep), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  int before = incl - mine;
+  for (int w = 0; w < warp; ++w) before += warp_sum[w];
+  SelPoint* out = stage + (size_t)blockIdx.x * kSelChunk + before;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (keep & (1u << k)) *out++ = SelPoint{px[k], py[k], pz[k], base + k};
+  if (threadIdx.x == 255) counts[blockIdx.x] = before + mine;
+}
+
+// keys + the window's cell histogram; one block per selection block, numbering the points consecutively
 template <typename KeyT>
-__global__ void __launch_bounds__(256) slab_key_kernel(const SelPoint* __restrict__ sel, const SlabInfo* __restrict__ info,
+__global__ void __launch_bounds__(256) slab_key_kernel(const SelPoint* __restrict__ stage, const int* __restrict__ sel_off,
                                                        const Domain* __restrict__ domains, float inv_cell, int xbits,
                                                        KeyT* __restrict__ keys, int* __restrict__ vals,
-                                                       int* __restrict__ cellcnt) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= info->n_selected) return;
+                                                       int* __restrict__ cellcnt, SelPoint* __restrict__ compact) {
+  const int first = sel_off[blockIdx.x], count = sel_off[blockIdx.x + 1] - first;
   const Domain dm = domains[0];
-  const SelPoint p = sel[j];
-  int cy, cz;
-  row_cells(dm, p.y, p.z, inv_cell, cy, cz);
-  const int xf = xfine_coord(p.x, dm.ox, inv_cell, dm.nx, dm.xshift);
-  const long long lrow = (long long)cz * dm.ny + cy - dm.row_lo;
-  atomicAdd(cellcnt + lrow * dm.nx + (xf >> dm.xshift), 1);
-  keys[j] = (KeyT)(((unsigned long long)lrow << xbits) | (unsigned)xf);
-  vals[j] = j;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const int src = blockIdx.x * kSelChunk + i;
+    const SelPoint p = stage[src];
+    int cy, cz;
+    row_cells(dm, p.y, p.z, inv_cell, cy, cz);
+    const int xf = xfine_coord(p.x, dm.ox, inv_cell, dm.nx, dm.xshift);
+    const long long lrow = (long long)cz * dm.ny + cy - dm.row_lo;
+    atomicAdd(cellcnt + lrow * dm.nx + (xf >> dm.xshift), 1);
+    keys[first + i] = (KeyT)(((unsigned long long)lrow << xbits) | (unsigned)xf);
+    vals[first + i] = first + i;
+    compact[first + i] = p;  // the staging array is sparse (one stretch per block): the gather after the sort reads this copy
+  }
+}
+
+// the number of selected points joins the rank's SlabInfo
+__global__ void slab_count_kernel(const int* __restrict__ sel_off, int n_blocks, SlabInfo* __restrict__ info) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) info->n_selected = sel_off[n_blocks];
 }
 
 // packet and query ranges of the rank's own and halo rows (packet_base / cell_start at a row's first cell = packets /
@@ -824,22 +878,23 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
   if (int rc = reserve(ctx, ctx->b_cellcnt, ((size_t)cells + 1) * 4)) return rc;
   if (int rc = reserve(ctx, ctx->b_pcost, (size_t)rows * 16 + 64)) return rc;
   if (int rc = reserve(ctx, ctx->b_slab, split_ints * 4 + sizeof(SlabInfo) + 64)) return rc;
-  if (int rc = reserve(ctx, ctx->b_sel, (size_t)n * sizeof(SelPoint) + 64)) return rc;
+  if (int rc = reserve(ctx, ctx->b_sel, ((size_t)n + kSelChunk) * sizeof(SelPoint) + 64)) return rc;
   long long* rowcost = (long long*)ctx->b_pcost.p;
   long long* cum = rowcost + rows;
   int* cuts = (int*)ctx->b_slab.p;
   SlabInfo* info = (SlabInfo*)(cuts + split_ints);
   Domain* d_dom = (Domain*)ctx->b_domains.p;
-  size_t tmp_cost = 0, tmp_sel = 0;
-  thrust::counting_iterator<int> ids(0);
-  auto points = thrust::make_transform_iterator(ids, LoadPoint{ctx->xyz_in, ctx->stride});
-  InWindow in_window{d_dom, ctx->inv_cell};
+  size_t tmp_cost = 0, tmp_selscan = 0;
+  const int sel_blocks = (n + kSelChunk - 1) / kSelChunk;
   cub::DeviceScan::InclusiveSum(nullptr, tmp_cost, (const long long*)nullptr, (long long*)nullptr, (int)rows, st);
-  cub::DeviceSelect::If(nullptr, tmp_sel, points, (SelPoint*)nullptr, (int*)nullptr, n, in_window, st);
-  if (int rc = reserve(ctx, ctx->b_cubtmp, std::max(tmp_cost, tmp_sel) + 16)) return rc;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_selscan, (const int*)nullptr, (int*)nullptr, sel_blocks + 1, st);
+  if (int rc = reserve(ctx, ctx->b_cubtmp, std::max(tmp_cost, tmp_selscan) + 16)) return rc;
+  if (int rc = reserve(ctx, ctx->b_vals[2], ((size_t)sel_blocks + 2) * 8)) return rc;
+  int* sel_cnt = (int*)ctx->b_vals[2].p;
+  int* sel_off = sel_cnt + sel_blocks + 1;
   CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_cellcnt.p, 0, ((size_t)cells + 1) * 4, st));
   {
-    const long long threads = ((long long)n + 4 * sample - 1) / (4 * sample);
+    const long long threads = (((long long)n + 256LL * sample - 1) / (256LL * sample)) * 64;
     sample_hist_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, sample, d_dom,
                                                                         ctx->inv_cell, (int*)ctx->b_cellcnt.p);
     CAB_LAUNCH_CHECK(ctx);
@@ -849,9 +904,16 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
     CAB_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->b_cubtmp.p, tmp_cost, rowcost, cum, (int)rows, st));
     slab_split_kernel<<<1, 32 * std::min(32, std::max(2, w)), 0, st>>>(cum, w, ctx->shard_rank, ctx->halo_permille, d_dom, cuts, info);
     CAB_LAUNCH_CHECK(ctx);
-    // stable selection of the window's points
-    CAB_CUDA(ctx, cub::DeviceSelect::If(ctx->b_cubtmp.p, tmp_sel, points, (SelPoint*)ctx->b_sel.p, &info->n_selected, n,
-                                        in_window, st));
+    // stable selection of the window's points: per-block compaction, then a scan of the blocks' counts
+    CAB_CUDA(ctx, cudaMemsetAsync(sel_cnt + sel_blocks, 0, 4, st));
+    if (vector_layout(ctx))
+      slab_select_kernel<true><<<sel_blocks, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, d_dom, ctx->inv_cell, (SelPoint*)ctx->b_sel.p, sel_cnt);
+    else
+      slab_select_kernel<false><<<sel_blocks, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, d_dom, ctx->inv_cell, (SelPoint*)ctx->b_sel.p, sel_cnt);
+    CAB_LAUNCH_CHECK(ctx);
+    CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_selscan, sel_cnt, sel_off, sel_blocks + 1, st));
+    slab_count_kernel<<<1, 32, 0, st>>>(sel_off, sel_blocks, info);
+    CAB_LAUNCH_CHECK(ctx);
     ctx->tm.kernel_launches += 4;
   }
   CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, info, sizeof(SlabInfo), cudaMemcpyDeviceToHost, st));
@@ -884,6 +946,7 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
   if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_bytes + 16)) return rc;
   if (int rc = reserve(ctx, ctx->b_keys[0], mm * 8)) return rc;
   if (int rc = reserve(ctx, ctx->b_keys[1], mm * 8)) return rc;
+  if (int rc = reserve(ctx, ctx->b_keys[2], mm * sizeof(SelPoint))) return rc;
   if (int rc = reserve(ctx, ctx->b_vals[0], mm * 4)) return rc;
   if (int rc = reserve(ctx, ctx->b_vals[1], mm * 4)) return rc;
   if (int rc = reserve(ctx, ctx->b_perm, mm * 4)) return rc;
@@ -898,12 +961,13 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
   CAB_CUDA(ctx, cudaMemsetAsync(cellcnt, 0, ncell1 * 4, st));
   if (m > 0) {
     if (key32)
-      slab_key_kernel<unsigned><<<(m + 255) / 256, 256, 0, st>>>((const SelPoint*)ctx->b_sel.p, info, d_dom, ctx->inv_cell, xbits,
-                                                                (unsigned*)ctx->b_keys[0].p, (int*)ctx->b_vals[0].p, cellcnt);
+      slab_key_kernel<unsigned><<<sel_blocks, 256, 0, st>>>((const SelPoint*)ctx->b_sel.p, sel_off, d_dom, ctx->inv_cell, xbits,
+                                                           (unsigned*)ctx->b_keys[0].p, (int*)ctx->b_vals[0].p, cellcnt,
+                                                           (SelPoint*)ctx->b_keys[2].p);
     else
-      slab_key_kernel<unsigned long long><<<(m + 255) / 256, 256, 0, st>>>((const SelPoint*)ctx->b_sel.p, info, d_dom, ctx->inv_cell,
-                                                                          xbits, (unsigned long long*)ctx->b_keys[0].p,
-                                                                          (int*)ctx->b_vals[0].p, cellcnt);
+      slab_key_kernel<unsigned long long><<<sel_blocks, 256, 0, st>>>((const SelPoint*)ctx->b_sel.p, sel_off, d_dom, ctx->inv_cell,
+                                                                     xbits, (unsigned long long*)ctx->b_keys[0].p,
+                                                                     (int*)ctx->b_vals[0].p, cellcnt, (SelPoint*)ctx->b_keys[2].p);
     CAB_LAUNCH_CHECK(ctx);
   }
   CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_bytes, (const int*)cellcnt, (int*)ctx->b_cellstart.p,
@@ -928,7 +992,7 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
                                                     (unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
                                                     (int*)ctx->b_vals[1].p, m, 0, end_bit, st));
     ctx->tm.kernel_launches += 1 + (end_bit + 7) / 8;
-    slab_place_kernel<<<(m + 255) / 256, 256, 0, st>>>((const SelPoint*)ctx->b_sel.p, (const int*)ctx->b_vals[1].p, m,
+    slab_place_kernel<<<(m + 255) / 256, 256, 0, st>>>((const SelPoint*)ctx->b_keys[2].p, (const int*)ctx->b_vals[1].p, m,
                                                       (float4*)ctx->b_pos.p, (int*)ctx->b_perm.p);
     CAB_LAUNCH_CHECK(ctx);
   }

@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
 // chunks, and only those run the variant of the loop that knows the self bit); candidates whose normal is not finite
 // are staged far away (they never contribute, :158-172) and counted in a rare side path; the bins are two arrays
 // [bin][lane] (min |cos|, max |cos|), so that a warp's reductions never meet in a bank whatever bins its lanes hit.
+constexpr int kFastThr = 260;  // entries of the fast kernel's threshold table (257 used)
 struct alignas(16) FastTile {
   float x[kWarp], y[kWarp], z[kWarp];
   float nx[kWarp], ny[kWarp], nz[kWarp];
@@ -257,7 +258,8 @@ struct alignas(16) FastTile {
 
 template <bool kSelf>
 __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float qy, float qz, float nqx, float nqy, float nqz,
-                                          float r2, float bscale, unsigned thr_addr, unsigned min_addr, unsigned max_addr, int sb) {
+                                          float r2, float bscale, unsigned thr_addr, unsigned spare_off, unsigned bins_addr,
+                                          int sb) {
   const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
   const float4* tx = reinterpret_cast<const float4*>(tile->x);
   const float4* ty = reinterpret_cast<const float4*>(tile->y);
@@ -266,64 +268,76 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
   const float4* tny = reinterpret_cast<const float4*>(tile->ny);
   const float4* tnz = reinterpret_cast<const float4*>(tile->nz);
   int k = 0;
-  auto one = [&](int m, float d2, float cnx, float cny, float cnz) {
-    // radius_estimation.cpp:153-155, the fp32 expression as written (no contraction)
-    const float cs = __fadd_rn(__fadd_rn(__fmul_rn(nqx, cnx), __fmul_rn(nqy, cny)), __fmul_rn(nqz, cnz));
-    // bin estimate biased low by kBinBias: the bin is the estimate or the next one, the exact fp32 d2 threshold decides
-    float root;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(root) : "f"(d2));
-    const int be = __float2int_rz(fmaf(root, bscale, -kBinBias));
-    const unsigned ua = __float_as_uint(fabsf(cs));
-    const unsigned ta = thr_addr + 4u + 4u * (unsigned)be;
-    if (kSelf) {
-      asm volatile(
-          "{\n\t.reg .pred p, q, s;\n\t.reg .f32 t;\n\t.reg .u32 a, b;\n\t"
-          "setp.ne.s32 s, %7, %8;\n\t"
-          "setp.le.and.f32 p, %1, %2, s;\n\t"
-          "@p ld.shared.f32 t, [%3];\n\t"
-          "setp.ge.and.f32 q, %1, t, p;\n\t"
-          "selp.u32 b, 128, 0, q;\n\t"
-          "@p add.s32 %0, %0, 1;\n\t"
-          "add.u32 a, %4, b;\n\t"
-          "@p red.shared.min.u32 [a], %6;\n\t"
-          "add.u32 a, %5, b;\n\t"
-          "@p red.shared.max.u32 [a], %6;\n\t}"
-          : "+r"(k)
-          : "f"(d2), "f"(r2), "r"(ta), "r"(min_addr + 128u * (unsigned)be), "r"(max_addr + 128u * (unsigned)be), "r"(ua), "r"(m), "r"(sb)
-          : "memory");
-    } else {
-      asm volatile(
-          "{\n\t.reg .pred p, q;\n\t.reg .f32 t;\n\t.reg .u32 a, b;\n\t"
-          "setp.le.f32 p, %1, %2;\n\t"
-          "@p ld.shared.f32 t, [%3];\n\t"
-          "setp.ge.and.f32 q, %1, t, p;\n\t"
-          "selp.u32 b, 128, 0, q;\n\t"
-          "@p add.s32 %0, %0, 1;\n\t"
-          "add.u32 a, %4, b;\n\t"
-          "@p red.shared.min.u32 [a], %6;\n\t"
-          "add.u32 a, %5, b;\n\t"
-          "@p red.shared.max.u32 [a], %6;\n\t}"
-          : "+r"(k)
-          : "f"(d2), "f"(r2), "r"(ta), "r"(min_addr + 128u * (unsigned)be), "r"(max_addr + 128u * (unsigned)be), "r"(ua)
-          : "memory");
-    }
-  };
+  // One group of four candidates: everything up to the bin address is plain arithmetic on independent chains (the
+  // compiler interleaves them); only the two reductions and the count sit under the hit predicate.  No "memory" clobber
+  // on the reductions: the warp barriers around the chunk order them against the plain accesses of the bins.
 #pragma unroll
   for (int g4 = 0; g4 < kWarp / 4; ++g4) {
     const float4 X = tx[g4], Y = ty[g4], Z = tz[g4];
     const float4 NX = tnx[g4], NY = tny[g4], NZ = tnz[g4];
-    float a, b;
+    float d2[4];
     {
       const f32x2 dx = sub2(pack2(X.x, X.y), qx2), dy = sub2(pack2(Y.x, Y.y), qy2), dz = sub2(pack2(Z.x, Z.y), qz2);
-      unpack2(add2(add2(sq2(dx), sq2(dy)), sq2(dz)), a, b);
-      one(4 * g4, a, NX.x, NY.x, NZ.x);
-      one(4 * g4 + 1, b, NX.y, NY.y, NZ.y);
+      unpack2(add2(add2(sq2(dx), sq2(dy)), sq2(dz)), d2[0], d2[1]);
     }
     {
       const f32x2 dx = sub2(pack2(X.z, X.w), qx2), dy = sub2(pack2(Y.z, Y.w), qy2), dz = sub2(pack2(Z.z, Z.w), qz2);
-      unpack2(add2(add2(sq2(dx), sq2(dy)), sq2(dz)), a, b);
-      one(4 * g4 + 2, a, NX.z, NY.z, NZ.z);
-      one(4 * g4 + 3, b, NX.w, NY.w, NZ.w);
+      unpack2(add2(add2(sq2(dx), sq2(dy)), sq2(dz)), d2[2], d2[3]);
+    }
+    const float cnx[4] = {NX.x, NX.y, NX.z, NX.w}, cny[4] = {NY.x, NY.y, NY.z, NY.w}, cnz[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
+    unsigned ua[4], addr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // radius_estimation.cpp:153-155, the fp32 expression as written (no contraction)
+      const float cs = __fadd_rn(__fadd_rn(__fmul_rn(nqx, cnx[i]), __fmul_rn(nqy, cny[i])), __fmul_rn(nqz, cnz[i]));
+      ua[i] = __float_as_uint(fabsf(cs));
+      // Bin estimate biased low by kBinBias: the bin is the estimate or the next one, the exact fp32 d2 threshold decides.
+      // The conversion saturates at 255 (misses may lie anywhere; thr[] has 257 entries, +inf from ndiv on).
+      float root;
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(root) : "f"(d2[i]));
+      const float est = fmaf(root, bscale, -kBinBias);
+      // The integer tail, spelled out so that it costs what it has to: threshold load, two compares, the row of the
+      // lane's column (hit: estimate, + 1 row if d2 reached the threshold; miss: the spare row and nothing else -- a
+      // staged-away candidate has d2 = inf, which "reaches" the +inf threshold), the neighbour count.
+      // (ptxas turns a predicated shared-memory reduction into a branch around it, so the reductions below are
+      // unconditional and the misses go to the spare row.)
+      if (kSelf) {
+        asm("{\n\t.reg .pred p, g, s;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
+            "cvt.rzi.u8.f32 be, %2;\n\t"
+            "mad.lo.u32 ta, be, 4, %5;\n\t"
+            "ld.shared.f32 t, [ta+4];\n\t"
+            "setp.ne.s32 s, %8, %9;\n\t"
+            "setp.le.and.f32 p, %3, %4, s;\n\t"
+            "setp.ge.and.f32 g, %3, t, p;\n\t"
+            "shl.b32 rb, be, 8;\n\t"
+            "selp.u32 rb, rb, %6, p;\n\t"
+            "selp.u32 go, 256, 0, g;\n\t"
+            "add.u32 rb, rb, go;\n\t"
+            "add.u32 %0, rb, %7;\n\t"
+            "@p add.s32 %1, %1, 1;\n\t}"
+            : "=r"(addr[i]), "+r"(k)
+            : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr), "r"(4 * g4 + i), "r"(sb));
+      } else {
+        asm("{\n\t.reg .pred p, g;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
+            "cvt.rzi.u8.f32 be, %2;\n\t"
+            "mad.lo.u32 ta, be, 4, %5;\n\t"
+            "ld.shared.f32 t, [ta+4];\n\t"
+            "setp.le.f32 p, %3, %4;\n\t"
+            "setp.ge.and.f32 g, %3, t, p;\n\t"
+            "shl.b32 rb, be, 8;\n\t"
+            "selp.u32 rb, rb, %6, p;\n\t"
+            "selp.u32 go, 256, 0, g;\n\t"
+            "add.u32 rb, rb, go;\n\t"
+            "add.u32 %0, rb, %7;\n\t"
+            "@p add.s32 %1, %1, 1;\n\t}"
+            : "=r"(addr[i]), "+r"(k)
+            : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(addr[i]), "r"(ua[i]));
+      asm volatile("red.shared.max.u32 [%0+128], %1;" ::"r"(addr[i]), "r"(ua[i]));
     }
   }
   return k;
@@ -332,17 +346,17 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
 __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const RsdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastTile* tiles = reinterpret_cast<FastTile*>(smem_raw);                          // [W]
-  unsigned* bins = reinterpret_cast<unsigned*>(tiles + kWarpsPerBlock);             // [W][2][ndiv][32]
-  float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * 2 * a.ndiv * kWarp);  // [ndiv + 1]
+  unsigned* bins = reinterpret_cast<unsigned*>(tiles + kWarpsPerBlock);                    // [W][ndiv + 1][2][32], row ndiv: the misses
+  float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * 2 * (a.ndiv + 1) * kWarp);  // [257], +inf from ndiv on
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ndiv = a.ndiv;
-  for (int i = threadIdx.x; i <= ndiv; i += blockDim.x) thr[i] = a.bin_thr[i];
+  for (int i = threadIdx.x; i < kFastThr; i += blockDim.x) thr[i] = i <= ndiv ? a.bin_thr[i] : INFINITY;
   __syncthreads();
   const GridView& g = a.g;
   FastTile* tile = &tiles[warp];
-  unsigned* my_min = bins + (size_t)warp * 2 * ndiv * kWarp + lane;  // bin b at my_min[b * 32]
-  unsigned* my_max = my_min + ndiv * kWarp;
-  const unsigned min_addr = smem_u32(my_min), max_addr = smem_u32(my_max), thr_addr = smem_u32(thr);
+  unsigned* my_min = bins + (size_t)warp * 2 * (ndiv + 1) * kWarp + lane;  // bin b: min |cos| at my_min[b * 64], max at my_max[b * 64]
+  unsigned* my_max = my_min + kWarp;
+  const unsigned bins_addr = smem_u32(my_min), thr_addr = smem_u32(thr);
   const float r2 = a.r2, bscale = a.bin_scale;
   const int p0 = a.range ? a.range[0] : a.p0, p1 = a.range ? a.range[1] : a.p1;
   for (;;) {
@@ -402,8 +416,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
     const float4 nq = a.nrm[pc.qi];
     const bool q_ok = isfinite(nq.x) && isfinite(nq.y) && isfinite(nq.z);
     for (int b = 0; b < ndiv; ++b) {
-      my_min[b * kWarp] = 0x7f800000u;  // +inf: empty
-      my_max[b * kWarp] = 0u;
+      my_min[b * 2 * kWarp] = 0x7f800000u;  // +inf: empty
+      my_max[b * 2 * kWarp] = 0u;
     }
     if (a.flags & CAB_RSD_SEED_BIN0) {
       my_min[0] = 0x3f800000u;
@@ -444,10 +458,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       }
       __syncwarp();
       if (own_mask) {
-        k += fast_chunk<true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, min_addr, max_addr, tile->self_slot[lane]);
+        k += fast_chunk<true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, tile->self_slot[lane]);
         k += tile->self_slot[lane] >= 0 ? 1 : 0;  // the query itself is a neighbour of the radius search (:120), just not a pair (:150)
       } else {
-        k += fast_chunk<false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, min_addr, max_addr, -1);
+        k += fast_chunk<false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, -1);
       }
       if (odd_mask) {  // rare: neighbours without a normal still count as neighbours
         unsigned mm = odd_mask;
@@ -461,11 +475,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       }
     }
 
+    __syncwarp();  // the reductions above are complete before the bins are read back
     // ---- least-squares fit of the min / max angle lines, radius_estimation.cpp:175-202 ----
     double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;
     if (q_ok) {
       for (int di = 0; di < ndiv; ++di) {
-        const float lo = __uint_as_float(my_min[di * kWarp]), hi = __uint_as_float(my_max[di * kWarp]);
+        const float lo = __uint_as_float(my_min[di * 2 * kWarp]), hi = __uint_as_float(my_max[di * 2 * kWarp]);
         if (lo != INFINITY) {  // bin not empty (:181)
           const double p_min = fold_angle<false>(fminf(hi, 1.f));
           const double p_max = fold_angle<false>(fminf(lo, 1.f));
@@ -594,8 +609,8 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
     int rc;
     static const bool legacy = std::getenv("CAB_RSD_LEGACY") != nullptr;  // A/B switch for profiling
     if (!ctx->cfg.exact && !use_thr && !legacy) {
-      const size_t fsmem = (size_t)kWarpsPerBlock * sizeof(FastTile) + (size_t)kWarpsPerBlock * 2 * ndiv * kWarp * sizeof(unsigned) +
-                           (size_t)((ndiv + 4) & ~3) * sizeof(float) + 256;
+      const size_t fsmem = (size_t)kWarpsPerBlock * sizeof(FastTile) + (size_t)kWarpsPerBlock * 2 * (ndiv + 1) * kWarp * sizeof(unsigned) +
+                           (size_t)kFastThr * sizeof(float) + 256;
       CAB_CUDA(ctx, cudaFuncSetAttribute(rsd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       int per_sm = 1;
       CAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rsd_fast_kernel, kWarpsPerBlock * kWarp, fsmem));

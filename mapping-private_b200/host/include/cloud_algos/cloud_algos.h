@@ -72,7 +72,19 @@ template <class algo>
  public:
   CloudAlgoNode (ros::NodeHandle& nh, algo &alg) : nh_ (nh), a (alg)
   {
+    // check if the input topic is advertised (cloud_algos.h:53-66)
+    std::vector<ros::master::TopicInfo> t_list;
+    bool topic_found = false;
+    ros::master::getTopics (t_list);
+    for (std::vector<ros::master::TopicInfo>::iterator it = t_list.begin (); it != t_list.end (); it++)
+      if (it->name == a.default_input_topic ()) { topic_found = true; break; }
+    if (!topic_found)
+      ROS_WARN ("Trying to subscribe to %s, but the topic doesn't exist!", a.default_input_topic ().c_str ());
+
     pub_ = nh_.advertise <typename algo::OutputType> (a.default_output_topic (), 5);
+    sub_ = nh_.subscribe (a.default_input_topic (), 1, &CloudAlgoNode<algo>::input_cb, this);
+    ROS_INFO ("CloudAlgoNode (%s) created. SUB [%s], PUB[%s]", ros::this_node::getName ().c_str (),
+              a.default_input_topic ().c_str (), a.default_output_topic ().c_str ());
     a.init (nh_);
   }
 
@@ -93,6 +105,18 @@ template <class algo>
   ros::Subscriber sub_;
   algo& a;
 };
+
+// main() of the <algo>_node executables (cloud_algos.h:106-117; built with -DCREATE_NODE, CMakeLists.txt:42-57)
+template <class algo>
+  int standalone_node (int argc, char* argv[])
+{
+  ros::init (argc, argv, algo::default_node_name ());
+  algo a;
+  ros::NodeHandle nh ("~");
+  CloudAlgoNode<algo> c (nh, a);
+  ros::spin ();
+  return (0);
+}
 
 }
 #endif

@@ -1,7 +1,9 @@
 #pragma once
 // Stand-in for ros/ros.h: a NodeHandle whose parameter server is an in-process map, publishers
-// that count what they are given, and the logging macros.
+// that count what they are given, an in-process topic table (subscribe / inject / spin) and the logging macros.
 #include <chrono>
+#include <deque>
+#include <functional>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -49,6 +51,52 @@ class Publisher {
 
 class Subscriber {};
 
+// In-process stand-in of the master: topics that have a subscriber and the messages waiting for them.  A test (or
+// the node mains built with -DCREATE_NODE) injects a message, ros::spin() delivers what is queued and returns.
+namespace master {
+struct TopicInfo {
+  std::string name, datatype;
+};
+struct Table {
+  std::map<std::string, std::function<void(const boost::shared_ptr<const void>&)>> subscribers;
+  std::deque<std::pair<std::string, boost::shared_ptr<const void>>> queue;
+  std::vector<TopicInfo> advertised;
+};
+inline Table& table() {
+  static Table t;
+  return t;
+}
+inline bool getTopics(std::vector<TopicInfo>& out) {
+  out = table().advertised;
+  return true;
+}
+}  // namespace master
+
+namespace this_node {
+inline std::string& name_ref() {
+  static std::string n = "node";
+  return n;
+}
+inline const std::string& getName() { return name_ref(); }
+}  // namespace this_node
+
+inline void init(int&, char**, const std::string& name) { this_node::name_ref() = name; }
+template <class M>
+inline void inject(const std::string& topic, const boost::shared_ptr<const M>& msg) {
+  master::table().advertised.push_back(master::TopicInfo{topic, ""});
+  master::table().queue.emplace_back(topic, boost::shared_ptr<const void>(msg));
+}
+// delivers the queued messages to their subscribers, then returns (a real ros::spin() blocks until shutdown)
+inline void spin() {
+  master::Table& t = master::table();
+  while (!t.queue.empty()) {
+    auto item = t.queue.front();
+    t.queue.pop_front();
+    auto it = t.subscribers.find(item.first);
+    if (it != t.subscribers.end()) it->second(item.second);
+  }
+}
+
 class NodeHandle {
  public:
   explicit NodeHandle(const std::string& ns = "")
@@ -66,6 +114,13 @@ class NodeHandle {
   void deleteParam(const std::string& key) { params_->erase(key); }
   bool hasParam(const std::string& key) const { return has(key); }
   template <class M> Publisher advertise(const std::string& topic, int /*queue*/) { return Publisher(topic); }
+  template <class M, class T>
+  Subscriber subscribe(const std::string& topic, int /*queue*/, void (T::*cb)(const boost::shared_ptr<const M>&), T* obj) {
+    master::table().subscribers[topic] = [cb, obj](const boost::shared_ptr<const void>& m) {
+      (obj->*cb)(boost::static_pointer_cast<const M>(m));
+    };
+    return Subscriber();
+  }
  private:
   bool has(const std::string& key) const { return params_->count(key) != 0; }
   std::string ns_;

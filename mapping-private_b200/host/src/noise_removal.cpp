@@ -120,3 +120,11 @@ std::string StatisticalNoiseRemoval::process (const boost::shared_ptr<const Stat
 
 boost::shared_ptr<const StatisticalNoiseRemoval::OutputType> StatisticalNoiseRemoval::output ()
   {return cloud_denoise_;}
+
+#ifdef CREATE_NODE
+// the <algo>_node executable of the reference's CMakeLists.txt:42-57 (cloud_algos.h:106-117)
+int main (int argc, char* argv[])
+{
+  return cloud_algos::standalone_node <cloud_algos::StatisticalNoiseRemoval> (argc, argv);
+}
+#endif

@@ -83,3 +83,11 @@ std::string NormalEstimation::process (const boost::shared_ptr<const NormalEstim
 
 boost::shared_ptr<const NormalEstimation::OutputType> NormalEstimation::output ()
   {return cloud_normals_;}
+
+#ifdef CREATE_NODE
+// the <algo>_node executable of the reference's CMakeLists.txt:42-57 (cloud_algos.h:106-117)
+int main (int argc, char* argv[])
+{
+  return cloud_algos::standalone_node <cloud_algos::NormalEstimation> (argc, argv);
+}
+#endif

@@ -139,3 +139,11 @@ std::string PointFeatureHistogram::process (const boost::shared_ptr<const PointF
 
 PointFeatureHistogram::OutputType PointFeatureHistogram::output ()
   {return *(cloud_pfh_.get ());}
+
+#ifdef CREATE_NODE
+// the <algo>_node executable of the reference's CMakeLists.txt:42-57 (cloud_algos.h:106-117)
+int main (int argc, char* argv[])
+{
+  return cloud_algos::standalone_node <cloud_algos::PointFeatureHistogram> (argc, argv);
+}
+#endif

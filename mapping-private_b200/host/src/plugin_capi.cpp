@@ -162,6 +162,34 @@ const char* capi_process(void* hv, const float* xyz, int n, int nchan, const cha
   return h->result.c_str();
 }
 
+// The reference's stand-alone node path (cloud_algos.h:46-117): a CloudAlgoNode subscribes the algorithm to its default
+// input topic, a message on that topic runs pre / process / publish(output) / post.  Returns the messages published.
+int capi_radius_node_roundtrip(const float* xyz, const float* nx, const float* ny, const float* nz, int n, double radius) {
+  boost::shared_ptr<sensor_msgs::PointCloud> cloud(new sensor_msgs::PointCloud());
+  cloud->points.resize((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    cloud->points[i].x = xyz[3 * i];
+    cloud->points[i].y = xyz[3 * i + 1];
+    cloud->points[i].z = xyz[3 * i + 2];
+  }
+  if (nx) {
+    cloud->channels.resize(3);
+    const char* names[3] = {"nx", "ny", "nz"};
+    const float* src[3] = {nx, ny, nz};
+    for (int c = 0; c < 3; ++c) {
+      cloud->channels[c].name = names[c];
+      cloud->channels[c].values.assign(src[c], src[c] + n);
+    }
+  }
+  ros::inject<sensor_msgs::PointCloud>(LocalRadiusEstimation::default_input_topic(), cloud);
+  LocalRadiusEstimation a;
+  ros::NodeHandle nh("~");
+  nh.setParam("radius", radius);
+  CloudAlgoNode<LocalRadiusEstimation> node(nh, a);
+  ros::spin();
+  return node.pub_.getNumPublished();
+}
+
 int capi_output_valid(void* hv) { return ((Handle*)hv)->algo->output_valid_ ? 1 : 0; }
 int capi_num_published(void* hv) { return ((Handle*)hv)->pub.getNumPublished(); }
 const char* capi_topic(void* hv) { return ((Handle*)hv)->pub.getTopic().c_str(); }

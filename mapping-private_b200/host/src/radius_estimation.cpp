@@ -109,3 +109,11 @@ std::string LocalRadiusEstimation::process (const boost::shared_ptr<const LocalR
 
 boost::shared_ptr<const LocalRadiusEstimation::OutputType> LocalRadiusEstimation::output ()
   {return cloud_radius_;}
+
+#ifdef CREATE_NODE
+// the <algo>_node executable of the reference's CMakeLists.txt:42-57 (cloud_algos.h:106-117)
+int main (int argc, char* argv[])
+{
+  return cloud_algos::standalone_node <cloud_algos::LocalRadiusEstimation> (argc, argv);
+}
+#endif

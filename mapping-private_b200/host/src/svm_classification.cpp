@@ -254,3 +254,11 @@ std::string SVMClassification::process (const boost::shared_ptr<const SVMClassif
 
 boost::shared_ptr<const SVMClassification::OutputType> SVMClassification::output ()
   {return cloud_svm_;}
+
+#ifdef CREATE_NODE
+// the <algo>_node executable of the reference's CMakeLists.txt:42-57 (cloud_algos.h:106-117)
+int main (int argc, char* argv[])
+{
+  return cloud_algos::standalone_node <cloud_algos::SVMClassification> (argc, argv);
+}
+#endif

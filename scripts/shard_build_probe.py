@@ -1,4 +1,4 @@
-"""One shard's build under ncu: which kernels make up the replicated part of a sharded cab_build_grid.
+"""One shard's step under ncu: which kernels make up a sharded cab_step_normals_rsd (slab build + normals + RSD).
 usage: ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python scripts/shard_build_probe.py [rank] [world]"""
 import sys, pathlib
 ROOT = pathlib.Path(__file__).resolve().parent.parent
@@ -13,5 +13,5 @@ ctx = cab.Context(0)
 ctx.upload(pts)
 ctx.set_shard(rank, world)
 for _ in range(3):
-    ctx.build_grid(0.02)
+    ctx.step_normals_rsd(0.02, 0.02)
 print(ctx.profile())
