@@ -557,14 +557,14 @@ _REAL_STDOUT = 1
 def main():
     global _REAL_STDOUT
     args = parse_args()
+    if args.gpus > 1 and "RANK" not in os.environ:  # before stdout is redirected: the workers inherit the real one
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", "29517", str(ROOT / "bench.py")] + sys.argv[1:])
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.gpus > 1 and "RANK" not in os.environ:
-        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-                                   "--master-addr", "127.0.0.1", "--master-port", "29517", str(ROOT / "bench.py")] + sys.argv[1:])
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -1,6 +1,7 @@
 // cab_api.cu -- C ABI of libcloudalgos_b200.so (see include/cloud_algos_b200.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <algorithm>
@@ -135,7 +136,7 @@ int upload_impl(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride, const
   if (stride < 3) return fail(ctx, CAB_ERR_ARG, "stride must be >= 3 floats");
   if (n > 0 && !xyz) return fail(ctx, CAB_ERR_ARG, "xyz is NULL");
   CAB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ctx->have_cloud = ctx->have_grid = ctx->have_normals = ctx->have_rsd = false;
+  ctx->have_cloud = ctx->have_grid = ctx->have_normals = ctx->have_rsd = ctx->kcount_valid = false;
   ctx->g_min_div.clear();  // voxel state of the last cab_grsd_batch belongs to the previous cloud
   if (int rc = set_domains(ctx, n, offsets, nclusters)) return rc;
   if (device_ptr) {
@@ -254,6 +255,10 @@ int cab_create(const cab_config* cfg, cab_ctx** out) {
   ctx->cfg = c;
   ctx->device = c.device;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* hp = std::getenv("CAB_HALO_PERMILLE")) {  // shard balance knob (tuning runs only)
+    const int v = std::atoi(hp);
+    if (v >= 0 && v <= 2000) ctx->halo_permille = v;
+  }
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete ctx;
     return fail(nullptr, CAB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));

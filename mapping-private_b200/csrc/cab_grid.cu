@@ -335,13 +335,18 @@ __global__ void __launch_bounds__(256) row_cost_kernel(const Domain* __restrict_
     for (int cx = lane; cx < dm.nx; cx += kWarp) {
       const int c = mine[cx];
       if (c == 0) continue;
-      int s = 0;
+      // candidates ~ the 3 x 3 rows around the cell, along x the cell itself plus 0.7 of either neighbour: a packet's x
+      // window is its own extent + 2 r, about 2.4 cells (a full 3-cell stencil overrates surfaces that run along x,
+      // e.g. the walls an end slab consists of, by a quarter against surfaces across x)
+      int s10 = 0;
       for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1); ++z)
         for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1); ++y) {
           const int* r = cnt + ((long long)z * dm.ny + y) * dm.nx;
-          for (int x = max(cx - 1, 0); x <= min(cx + 1, dm.nx - 1); ++x) s += r[x];
+          s10 += 10 * r[cx] + 7 * ((cx > 0 ? r[cx - 1] : 0) + (cx + 1 < dm.nx ? r[cx + 1] : 0));
         }
-      acc += (long long)c * ((long long)s * sample + 2);
+      // + a constant per point (fit, eigen-solve: 2 candidates' worth) and per occupied cell (sparse rows make many short
+      // packets, each with its own run table and chunk overhead: 16 candidates' worth per cell)
+      acc += (long long)c * ((long long)s10 * sample + 20) + 160;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
@@ -655,7 +660,7 @@ int build_grid(cab_ctx* ctx, float cell) {
   const int n = (int)ctx->n;
   const int nd = ctx->n_domains;
   cudaStream_t st = ctx->stream;
-  ctx->have_grid = ctx->have_normals = ctx->have_rsd = false;
+  ctx->have_grid = ctx->have_normals = ctx->have_rsd = ctx->kcount_valid = false;
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
 
   if (int rc = compute_bounds(ctx)) return rc;

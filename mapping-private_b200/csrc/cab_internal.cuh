@@ -17,6 +17,8 @@ namespace cab {
 constexpr int kWarp = 32;
 constexpr int kXBits = 20;            // sub-cell x field of the sort key
 constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kTruncBins = 64;          // d2 histogram bins of the max_nn selection
+constexpr int kTruncCap = 16;           // candidates of the target bin the truncated fast RSD pass settles from a list
 constexpr int kStatSlots = 64;         // spread counters (avoids same-address atomic serialisation)
 constexpr size_t kStatBytes = (kStatSlots * 2 + 2) * sizeof(unsigned long long);  // + the packet work counter
 
@@ -141,6 +143,8 @@ struct cab_ctx {
   int n_valid = 0;
   int n_domains = 0;
   bool have_cloud = false, have_grid = false, have_normals = false, have_rsd = false;
+  bool kcount_valid = false;  // b_kcount holds the untruncated in-radius neighbour counts (self included) of radius kcount_r
+  float kcount_r = 0.f;
   bool cloud_external = false;
   const float* xyz_in = nullptr;  // device, stride floats
   int stride = 3;
@@ -156,7 +160,7 @@ struct cab_ctx {
   cab::SlabInfo slab_info{};       // host copy (valid when slab_info_valid)
   bool slab_info_valid = false;
   int64_t n_sorted = 0;            // entries of the sorted arrays: n, or the slab window's points
-  int halo_permille = 420;         // share of the normals pass in a packet's cost (shard balance)
+  int halo_permille = 470;         // share of the normals pass in a packet's cost (shard balance)
   bool defer_sync = false;         // run_normals / run_rsd leave the stream running (cab_step_*: one sync per step)
 
   // device arena (grow-only)
@@ -216,6 +220,7 @@ int build_grid(cab_ctx* ctx, float cell);
 int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsigned char* done = nullptr);
 int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, int flags);
 int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done = nullptr, bool halo = false);  // max_nn truncation thresholds (halo: also for a slab's halo packets)
+int run_nn_hist(cab_ctx* ctx, float r, int max_nn);  // cab_topk.cu: histogram half of the truncated fast RSD pass
 int run_knn_mean(cab_ctx* ctx, int k, float cell_hint, double* avg);  // cab_knn.cu
 int run_normals_knn(cab_ctx* ctx, int k, const float vp[3], float cell_hint, float* nxyz_curv);  // cab_knn.cu
 int run_pfh(cab_ctx* ctx, double radius, int max_nn, int quantum, int flags, float* out);  // cab_pfh.cu

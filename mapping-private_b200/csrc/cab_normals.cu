@@ -282,6 +282,8 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsi
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
   CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepStats0, ctx->b_stats.p, kStatBytes, cudaMemcpyDeviceToHost, st));
   ctx->have_normals = true;
+  ctx->kcount_valid = !use_thr && done == nullptr;  // every query of this context's range counted, nothing truncated
+  ctx->kcount_r = r;
   if (ctx->defer_sync) return CAB_OK;
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   return finish_pass_stats(ctx, 0);

@@ -48,6 +48,11 @@ struct RsdArgs {
   float* rdif;             // sorted order: (float)(max_radius - min_radius), the subtraction in double (:206)
   const float* thr_d2;     // optional max_nn thresholds
   const int* thr_idx;
+  const unsigned char* only;   // legacy kernel: optional per-packet flags (relative to p0), unflagged packets are skipped
+  const unsigned char* skip;   // fast kernel: optional per-packet flags, flagged packets are left to the legacy kernel
+  const int* trunc_code;       // truncated fast pass: per query target bin | kept << 8 (cab_topk.cu nn_hist_kernel)
+  float trunc_scale;           // kTruncBins / r2
+  const int* kcount;       // optional: in-radius neighbour counts of the normals pass at this radius (the statistics then need no count)
   const float* bin_thr;    // ndiv + 1 fp32 d2 thresholds, bin_thr[0] = -inf, bin_thr[ndiv] = +inf
   int ndiv;
   int flags;
@@ -124,6 +129,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
   for (;;) {
     const int pid = p0 + next_packet(a.stats, lane);
     if (pid >= p1) break;
+    if (a.only && !a.only[pid - p0]) continue;
     const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
     const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
     const float4 nq = a.nrm[pc.qi];
@@ -251,16 +257,23 @@ constexpr int kFastThr = 260;  // entries of the fast kernel's threshold table (
 struct alignas(16) FastTile {
   float x[kWarp], y[kWarp], z[kWarp];
   float nx[kWarp], ny[kWarp], nz[kWarp];
+  int idx[kWarp];  // sorted index of the staged candidate (truncated pass: the target bin's candidates are listed by it)
   int self_slot[kWarp];
   int run_begin[12];
   int run_cum[12];
 };
 
-template <bool kSelf>
+// Truncated pass (kTrunc): v = d2 * trunc_scale is the candidate's place in the 64-bin histogram of nn_hist_kernel (same
+// expression, same bits).  Below the query's target bin (v < t1f) a neighbour is kept outright; inside it (t1f <= v <
+// t1hi) it goes to the lane's list `lst` (entry e: d2 at lst[2e * 32], sorted index at lst[(2e + 1) * 32]) and is settled
+// after the traversal; beyond it it is dropped.  A query that keeps everything has t1f = +inf.
+template <bool kSelf, bool kCount, bool kTrunc>
 __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float qy, float qz, float nqx, float nqy, float nqz,
                                           float r2, float bscale, unsigned thr_addr, unsigned spare_off, unsigned bins_addr,
-                                          int sb) {
+                                          int sb, float tscale = 0.f, float t1f = 0.f, float t1hi = 0.f, float* lst = nullptr,
+                                          int* lcnt = nullptr) {
   const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
+  const f32x2 nqx2 = pack2(nqx, nqx), nqy2 = pack2(nqy, nqy), nqz2 = pack2(nqz, nqz);
   const float4* tx = reinterpret_cast<const float4*>(tile->x);
   const float4* ty = reinterpret_cast<const float4*>(tile->y);
   const float4* tz = reinterpret_cast<const float4*>(tile->z);
@@ -284,13 +297,21 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
       const f32x2 dx = sub2(pack2(X.z, X.w), qx2), dy = sub2(pack2(Y.z, Y.w), qy2), dz = sub2(pack2(Z.z, Z.w), qz2);
       unpack2(add2(add2(sq2(dx), sq2(dy)), sq2(dz)), d2[2], d2[3]);
     }
-    const float cnx[4] = {NX.x, NX.y, NX.z, NX.w}, cny[4] = {NY.x, NY.y, NY.z, NY.w}, cnz[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
+    // radius_estimation.cpp:153-155, the fp32 expression as written (products and sums rounded separately), two
+    // candidates per packed instruction
+    float cs[4];
+    {
+      const f32x2 a = mul2(nqx2, pack2(NX.x, NX.y)), b = mul2(nqy2, pack2(NY.x, NY.y)), c = mul2(nqz2, pack2(NZ.x, NZ.y));
+      unpack2(add2(add2(a, b), c), cs[0], cs[1]);
+    }
+    {
+      const f32x2 a = mul2(nqx2, pack2(NX.z, NX.w)), b = mul2(nqy2, pack2(NY.z, NY.w)), c = mul2(nqz2, pack2(NZ.z, NZ.w));
+      unpack2(add2(add2(a, b), c), cs[2], cs[3]);
+    }
     unsigned ua[4], addr[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      // radius_estimation.cpp:153-155, the fp32 expression as written (no contraction)
-      const float cs = __fadd_rn(__fadd_rn(__fmul_rn(nqx, cnx[i]), __fmul_rn(nqy, cny[i])), __fmul_rn(nqz, cnz[i]));
-      ua[i] = __float_as_uint(fabsf(cs));
+      ua[i] = __float_as_uint(fabsf(cs[i]));
       // Bin estimate biased low by kBinBias: the bin is the estimate or the next one, the exact fp32 d2 threshold decides.
       // The conversion saturates at 255 (misses may lie anywhere; thr[] has 257 entries, +inf from ndiv on).
       float root;
@@ -301,7 +322,33 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
       // staged-away candidate has d2 = inf, which "reaches" the +inf threshold), the neighbour count.
       // (ptxas turns a predicated shared-memory reduction into a branch around it, so the reductions below are
       // unconditional and the misses go to the spare row.)
-      if (kSelf) {
+      if (kTrunc) {
+        const float v = d2[i] * tscale;
+        if (d2[i] <= r2 && !(v < t1f) && v < t1hi) {  // the target bin: listed, the query itself included (it is one of the max_nn)
+          const int c = *lcnt;
+          if (c < kTruncCap) {
+            lst[(2 * c) * kWarp] = d2[i];
+            reinterpret_cast<int*>(lst)[(2 * c + 1) * kWarp] = tile->idx[4 * g4 + i];
+          }
+          *lcnt = c + 1;
+        }
+        asm("{\n\t.reg .pred p, g, s;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
+            "cvt.rzi.u8.f32 be, %2;\n\t"
+            "mad.lo.u32 ta, be, 4, %5;\n\t"
+            "ld.shared.f32 t, [ta+4];\n\t"
+            "setp.ne.s32 s, %8, %9;\n\t"
+            "setp.le.and.f32 p, %3, %4, s;\n\t"
+            "setp.lt.and.f32 p, %10, %11, p;\n\t"
+            "setp.ge.and.f32 g, %3, t, p;\n\t"
+            "shl.b32 rb, be, 8;\n\t"
+            "selp.u32 rb, rb, %6, p;\n\t"
+            "selp.u32 go, 256, 0, g;\n\t"
+            "add.u32 rb, rb, go;\n\t"
+            "add.u32 %0, rb, %7;\n\t"
+            "@p add.s32 %1, %1, 1;\n\t}"
+            : "=r"(addr[i]), "+r"(k)
+            : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr), "r"(4 * g4 + i), "r"(sb), "f"(v), "f"(t1f));
+      } else if (kSelf) {
         asm("{\n\t.reg .pred p, g, s;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
             "cvt.rzi.u8.f32 be, %2;\n\t"
             "mad.lo.u32 ta, be, 4, %5;\n\t"
@@ -317,7 +364,7 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
             "@p add.s32 %1, %1, 1;\n\t}"
             : "=r"(addr[i]), "+r"(k)
             : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr), "r"(4 * g4 + i), "r"(sb));
-      } else {
+      } else if (kCount) {
         asm("{\n\t.reg .pred p, g;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
             "cvt.rzi.u8.f32 be, %2;\n\t"
             "mad.lo.u32 ta, be, 4, %5;\n\t"
@@ -332,6 +379,20 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
             "@p add.s32 %1, %1, 1;\n\t}"
             : "=r"(addr[i]), "+r"(k)
             : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr));
+      } else {  // the neighbour counts of this radius are known from the normals pass
+        asm("{\n\t.reg .pred p, g;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
+            "cvt.rzi.u8.f32 be, %2;\n\t"
+            "mad.lo.u32 ta, be, 4, %5;\n\t"
+            "ld.shared.f32 t, [ta+4];\n\t"
+            "setp.le.f32 p, %3, %4;\n\t"
+            "setp.ge.and.f32 g, %3, t, p;\n\t"
+            "shl.b32 rb, be, 8;\n\t"
+            "selp.u32 rb, rb, %6, p;\n\t"
+            "selp.u32 go, 256, 0, g;\n\t"
+            "add.u32 rb, rb, go;\n\t"
+            "add.u32 %0, rb, %7;\n\t}"
+            : "=r"(addr[i]), "+r"(k)
+            : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr));
       }
     }
 #pragma unroll
@@ -343,6 +404,7 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
   return k;
 }
 
+template <bool kCount, bool kTrunc>
 __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const RsdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastTile* tiles = reinterpret_cast<FastTile*>(smem_raw);                          // [W]
@@ -350,10 +412,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
   float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * 2 * (a.ndiv + 1) * kWarp);  // [257], +inf from ndiv on
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ndiv = a.ndiv;
+  float* lists = thr + kFastThr;  // kTrunc: [W][2 * kTruncCap][32], a lane's list of its target bin's candidates
   for (int i = threadIdx.x; i < kFastThr; i += blockDim.x) thr[i] = i <= ndiv ? a.bin_thr[i] : INFINITY;
   __syncthreads();
   const GridView& g = a.g;
   FastTile* tile = &tiles[warp];
+  float* lst = lists + (size_t)warp * 2 * kTruncCap * kWarp + lane;
   unsigned* my_min = bins + (size_t)warp * 2 * (ndiv + 1) * kWarp + lane;  // bin b: min |cos| at my_min[b * 64], max at my_max[b * 64]
   unsigned* my_max = my_min + kWarp;
   const unsigned bins_addr = smem_u32(my_min), thr_addr = smem_u32(thr);
@@ -362,6 +426,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
   for (;;) {
     const int pid = p0 + next_packet(a.stats, lane);
     if (pid >= p1) break;
+    if (kTrunc && a.skip && a.skip[pid - p0]) continue;  // left to the exact-threshold path
     // the packet and its candidate runs (load_packet works on a ChunkTile; the run tables sit at the same place here)
     PacketCtx pc;
     {
@@ -424,6 +489,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       my_max[0] = 0x3f800000u;
     }
     int k = 0;
+    // truncated pass: the query's target bin of the d2 histogram and how many of that bin's candidates are kept
+    int lcnt = 0, need = 0;
+    float t1f = INFINITY, t1hi = INFINITY;
+    if (kTrunc) {
+      const int code = a.trunc_code[pc.qi];
+      const int t1 = code & 255;
+      need = code >> 8;
+      if (t1 != 255) {
+        t1f = (float)t1;
+        t1hi = t1 == kTruncBins - 1 ? INFINITY : t1f + 1.f;
+      }
+    }
     const int nchunks = (pc.total + kWarp - 1) / kWarp;
 #pragma unroll 1
     for (int c0 = 0; c0 < nchunks; ++c0) {
@@ -449,6 +526,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       tile->nx[lane] = cn.x;
       tile->ny[lane] = cn.y;
       tile->nz[lane] = cn.z;
+      if (kTrunc) tile->idx[lane] = j;
       const unsigned own_mask = __ballot_sync(kFull, is_own);
       const unsigned odd_mask = __ballot_sync(kFull, valid && !finite_n);
       if (own_mask) {
@@ -457,11 +535,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
         if (is_own) tile->self_slot[own] = lane;
       }
       __syncwarp();
-      if (own_mask) {
-        k += fast_chunk<true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, tile->self_slot[lane]);
+      if (kTrunc) {
+        const int sb = own_mask ? tile->self_slot[lane] : -1;
+        k += fast_chunk<true, true, true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, sb,
+                                          a.trunc_scale, t1f, t1hi, lst, &lcnt);
+        k += (sb >= 0 && t1f > 0.f) ? 1 : 0;  // the query itself, unless it sits in the target bin (then the list has it)
+      } else if (own_mask) {
+        k += fast_chunk<true, true, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, tile->self_slot[lane]);
         k += tile->self_slot[lane] >= 0 ? 1 : 0;  // the query itself is a neighbour of the radius search (:120), just not a pair (:150)
       } else {
-        k += fast_chunk<false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, -1);
+        k += fast_chunk<false, kCount, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, -1);
       }
       if (odd_mask) {  // rare: neighbours without a normal still count as neighbours
         unsigned mm = odd_mask;
@@ -476,6 +559,32 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
     }
 
     __syncwarp();  // the reductions above are complete before the bins are read back
+    if (kTrunc && lcnt > 0) {
+      // The target bin: keep the `need` smallest (d2, input index) of its candidates (the rule of the radius search with
+      // max_nn, radius_estimation.cpp:120); the query itself counts among them but forms no pair (:150).
+      const int L = min(lcnt, kTruncCap);
+      const int* lj = reinterpret_cast<const int*>(lst);
+      for (int e = 0; e < L; ++e) {
+        const float de = lst[(2 * e) * kWarp];
+        const int je = lj[(2 * e + 1) * kWarp];
+        int rank = 0;
+        for (int f = 0; f < L; ++f) {
+          const float df = lst[(2 * f) * kWarp];
+          if (df < de) ++rank;
+          else if (df == de && f != e && g.perm[lj[(2 * f + 1) * kWarp]] < g.perm[je]) ++rank;
+        }
+        if (rank >= need) continue;
+        ++k;
+        if (je == pc.qi) continue;
+        const float4 cn = a.nrm[je];  // finite: packets with a candidate lacking a normal never take this path
+        const float cs = __fadd_rn(__fadd_rn(__fmul_rn(nq.x, cn.x), __fmul_rn(nq.y, cn.y)), __fmul_rn(nq.z, cn.z));
+        const unsigned ua = __float_as_uint(fabsf(cs));
+        int b = 0;
+        while (b < ndiv - 1 && de >= thr[b + 1]) ++b;
+        my_min[b * 2 * kWarp] = min(my_min[b * 2 * kWarp], ua);
+        my_max[b * 2 * kWarp] = max(my_max[b * 2 * kWarp], ua);
+      }
+    }
     // ---- least-squares fit of the min / max angle lines, radius_estimation.cpp:175-202 ----
     double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;
     if (q_ok) {
@@ -503,6 +612,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
     }
     if (pc.active) a.out[pc.qi] = make_float2(rmin, rmax);
     push_results(a.push, a.slab, g, pc, nq, make_float2(rmin, rmax));
+    if (!kCount) k = a.kcount[pc.qi];  // same radius, same rule, no truncation: the normals pass counted these neighbours
     unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
 #pragma unroll
     for (int o = 16; o; o >>= 1) ks += __shfl_xor_sync(kFull, ks, o);
@@ -567,8 +677,14 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   if (int rc = reserve(ctx, ctx->b_rdif, (size_t)std::max(n, 1) * sizeof(float))) return rc;
   if (int rc = reserve(ctx, ctx->b_stats, kStatBytes)) return rc;
   const bool use_thr = max_nn > 0;
-  if (use_thr)
+  static const bool legacy = std::getenv("CAB_RSD_LEGACY") != nullptr;  // A/B switch for profiling
+  // fast mode with max_nn: one histogram traversal, then the RSD traversal settles the truncation itself
+  const bool trunc_fast = use_thr && !ctx->cfg.exact && !legacy;
+  if (trunc_fast) {
+    if (int rc = run_nn_hist(ctx, rf, max_nn)) return rc;
+  } else if (use_thr) {
     if (int rc = run_thresholds(ctx, rf, max_nn)) return rc;
+  }
   // bin thresholds
   float thr[kMaxDiv + 1];
   const float r2 = rf * rf;
@@ -607,17 +723,32 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   if (np > 0 && ctx->n_sorted > 0) {
     const unsigned blocks = (np + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int rc;
-    static const bool legacy = std::getenv("CAB_RSD_LEGACY") != nullptr;  // A/B switch for profiling
-    if (!ctx->cfg.exact && !use_thr && !legacy) {
+    if (!ctx->cfg.exact && (!use_thr || trunc_fast) && !legacy) {
       const size_t fsmem = (size_t)kWarpsPerBlock * sizeof(FastTile) + (size_t)kWarpsPerBlock * 2 * (ndiv + 1) * kWarp * sizeof(unsigned) +
-                           (size_t)kFastThr * sizeof(float) + 256;
-      CAB_CUDA(ctx, cudaFuncSetAttribute(rsd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                           (size_t)kFastThr * sizeof(float) + 256 +
+                           (trunc_fast ? (size_t)kWarpsPerBlock * 2 * kTruncCap * kWarp * sizeof(float) : 0);
+      // neighbour counts kept by the last normals pass are this pass's counts if radius and rule were the same
+      const bool counted = !trunc_fast && ctx->kcount_r == rf && ctx->kcount_valid;
+      a.kcount = counted ? (const int*)ctx->b_kcount.p : nullptr;
+      if (trunc_fast) {
+        a.trunc_code = (const int*)ctx->b_thr_idx.p;
+        a.trunc_scale = (float)kTruncBins / r2;
+        a.skip = (const unsigned char*)ctx->b_thr_flag.p;
+      }
+      auto kernel = trunc_fast ? rsd_fast_kernel<true, true> : counted ? rsd_fast_kernel<false, false> : rsd_fast_kernel<true, false>;
+      CAB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       int per_sm = 1;
-      CAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rsd_fast_kernel, kWarpsPerBlock * kWarp, fsmem));
+      CAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * kWarp, fsmem));
       const unsigned grid = std::min<unsigned>(blocks, (unsigned)std::max(per_sm, 1) * ctx->sm_count);
-      rsd_fast_kernel<<<grid, kWarpsPerBlock * kWarp, fsmem, ctx->stream>>>(a);
+      kernel<<<grid, kWarpsPerBlock * kWarp, fsmem, ctx->stream>>>(a);
       CAB_LAUNCH_CHECK(ctx);
       rc = CAB_OK;
+      if (trunc_fast) {  // the flagged packets: exact thresholds (computed by run_nn_hist for them) and the hit-compacting kernel
+        CAB_CUDA(ctx, cudaMemsetAsync((unsigned long long*)ctx->b_stats.p + 2 * kStatSlots, 0, 8, st));  // packet work counter
+        a.skip = nullptr;
+        a.only = (const unsigned char*)ctx->b_thr_flag.p;
+        rc = launch_rsd<false, true>(ctx, a, blocks, smem);
+      }
     } else if (ctx->cfg.exact) rc = use_thr ? launch_rsd<true, true>(ctx, a, blocks, smem) : launch_rsd<true, false>(ctx, a, blocks, smem);
     else rc = use_thr ? launch_rsd<false, true>(ctx, a, blocks, smem) : launch_rsd<false, false>(ctx, a, blocks, smem);
     if (rc) return rc;

@@ -24,7 +24,7 @@ namespace cab {
 namespace {
 
 constexpr int kSelWarps = 4;
-constexpr int kSelBins = 64;
+constexpr int kSelBins = kTruncBins;
 
 struct ThrArgs {
   GridView g;
@@ -37,6 +37,10 @@ struct ThrArgs {
   const unsigned char* done;  // optional, indexed by input index: queries that need no threshold any more
   unsigned char* fallback;    // per packet (relative to p0): value_select_kernel sets it, threshold_kernel honours it
   int use_fallback;           // threshold_kernel: only the flagged packets
+  const unsigned char* only;  // optional, per packet (relative to p0): value_select_kernel works on the flagged packets only
+  int* code;                  // nn_hist_kernel: per query (sorted order) target bin | rank inside it << 8
+  const float4* nrm;          // nn_hist_kernel: normals (sorted order); packets with a candidate without one are flagged
+  unsigned long long* stats;  // nn_hist_kernel: packet work counter
 };
 
 __global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrArgs a) {
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) value_select_kernel(const T
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pid = a.p0 + blockIdx.x * kSelWarps + warp;
   if (pid >= a.p1) return;
+  if (a.only && !a.only[pid - a.p0]) return;
   const GridView& g = a.g;
   ChunkTile* tile = &tiles[warp];
   const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
@@ -223,6 +228,57 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) value_select_kernel(const T
   if (pc.active && wanted && !need) {
     a.thr_d2[pc.qi] = INFINITY;
     a.thr_idx[pc.qi] = INT_MAX;
+  }
+}
+
+// First half of the truncated fast RSD pass (cab_rsd.cu, rsd_fast_kernel<., true>): the 64-bin histogram of d2 alone.
+// Per query it leaves the bin that holds the max_nn-th neighbour and how many of that bin's candidates are still kept
+// (code = bin | kept << 8; bin 255: the query has at most max_nn neighbours, all are kept).  The RSD traversal then
+// accepts every candidate below the bin outright and settles the bin's few candidates from a short list, so the
+// truncation costs one extra traversal instead of two plus a slower RSD kernel.  Packets in which some query's bin
+// holds more candidates than the list takes are flagged and go through the exact-threshold path.
+__global__ void __launch_bounds__(kSelWarps * kWarp) nn_hist_kernel(const ThrArgs a) {
+  __shared__ ChunkTile tiles[kSelWarps];
+  __shared__ unsigned hist[kSelWarps][kSelBins + 1][kWarp];  // row kSelBins: everything beyond the radius
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GridView& g = a.g;
+  ChunkTile* tile = &tiles[warp];
+  const float r2 = a.r2;
+  const float scale1 = (float)kSelBins / r2;
+  const unsigned col = (unsigned)__cvta_generic_to_shared(&hist[warp][0][lane]);
+  for (;;) {
+    const int pid = a.p0 + next_packet(a.stats, lane);
+    if (pid >= a.p1) break;
+    const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
+    const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
+    for (int b = 0; b <= kSelBins; ++b) hist[warp][b][lane] = 0;
+    bool odd = false;  // a candidate without a finite normal: it takes part in the truncation but the fast RSD pass never sees it
+    for_each_chunk(g, pc, lane, tile, [&](int cnt, const float4&, int j, bool valid) {
+      if (valid) {
+        const float4 cn = a.nrm[j];
+        odd = odd || !(isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z));
+      }
+      for_each_staged_d2(tile, cnt, qx, qy, qz, [&](int, float d2) {
+        const int row = d2 <= r2 ? min(__float2int_rz(d2 * scale1), kSelBins - 1) : kSelBins;
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(col + 128u * (unsigned)row) : "memory");
+      });
+    });
+    __syncwarp();
+    int k = 0, bin = 255, before = 0, in_bin = 0;
+    for (int b = 0; b < kSelBins; ++b) {
+      const int c = hist[warp][b][lane];
+      if (bin == 255 && k + c >= a.max_nn + 1) {  // the (max_nn + 1)-th neighbour would be the first one dropped
+        bin = b;
+        before = k;
+        in_bin = c;
+      }
+      k += c;
+    }
+    // bin: holds neighbour number max_nn + 1, so at least one of its candidates is dropped; kept = max_nn - before of them
+    const bool over = odd || (pc.active && bin != 255 && in_bin > kTruncCap);
+    if (pc.active) a.code[pc.qi] = bin == 255 ? 255 : (bin | ((a.max_nn - before) << 8));
+    if (__any_sync(kFull, over) && lane == 0) a.fallback[pid - a.p0] = 1;
+    __syncwarp();
   }
 }
 
@@ -340,6 +396,56 @@ int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done,
     threshold_kernel<<<(np + kSelWarps - 1) / kSelWarps, kSelWarps * kWarp, 0, st>>>(a);
     CAB_LAUNCH_CHECK(ctx);
   }
+  return CAB_OK;
+}
+
+// Histogram half of the truncated fast RSD pass: per-query codes in b_thr_idx, flags of the packets that need the exact
+// thresholds in b_thr_flag, and for those packets the thresholds themselves (b_thr_d2 / b_thr_idx hold either kind).
+int run_nn_hist(cab_ctx* ctx, float r, int max_nn) {
+  const int n = (int)ctx->n;
+  cudaStream_t st = ctx->stream;
+  if (ctx->slab && !ctx->slab_info_valid) {
+    CAB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (int rc = finish_slab(ctx)) return rc;
+  }
+  if (int rc = reserve(ctx, ctx->b_thr_d2, (size_t)std::max(n, 1) * sizeof(float))) return rc;
+  if (int rc = reserve(ctx, ctx->b_thr_idx, (size_t)std::max(n, 1) * sizeof(int))) return rc;
+  if (int rc = reserve(ctx, ctx->b_stats, kStatBytes)) return rc;
+  ThrArgs a{};
+  a.g = grid_view(ctx);
+  packet_range(ctx, &a.p0, &a.p1);
+  a.r = r;
+  a.r2 = r * r;
+  a.max_nn = max_nn;
+  uint32_t bits;
+  std::memcpy(&bits, &a.r2, 4);
+  a.first_shift = (bits >> 30) ? 30 : 24;
+  a.thr_d2 = (float*)ctx->b_thr_d2.p;
+  a.thr_idx = (int*)ctx->b_thr_idx.p;
+  a.code = (int*)ctx->b_thr_idx.p;
+  a.nrm = (const float4*)ctx->b_nrm.p;
+  a.stats = (unsigned long long*)ctx->b_stats.p;
+  const int np = a.p1 - a.p0;
+  if (np <= 0) return CAB_OK;
+  if (int rc = reserve(ctx, ctx->b_thr_flag, 2 * (size_t)np + 32)) return rc;
+  unsigned char* flag_a = (unsigned char*)ctx->b_thr_flag.p;  // packets that leave the fast path
+  unsigned char* flag_b = flag_a + np;                        // of those: packets that need the radix select
+  CAB_CUDA(ctx, cudaMemsetAsync(flag_a, 0, 2 * (size_t)np, st));
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, kStatBytes, st));
+  a.fallback = flag_a;
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn_hist_kernel, kSelWarps * kWarp, 0);
+  const unsigned grid = (unsigned)std::min<long long>((long long)std::max(per_sm, 1) * ctx->sm_count, (np + kSelWarps - 1) / kSelWarps);
+  nn_hist_kernel<<<grid, kSelWarps * kWarp, 0, st>>>(a);
+  CAB_LAUNCH_CHECK(ctx);
+  // exact (d2, index) thresholds for the flagged packets only
+  a.only = flag_a;
+  a.fallback = flag_b;
+  value_select_kernel<<<(np + kSelWarps - 1) / kSelWarps, kSelWarps * kWarp, 0, st>>>(a);
+  CAB_LAUNCH_CHECK(ctx);
+  a.use_fallback = 1;
+  threshold_kernel<<<(np + kSelWarps - 1) / kSelWarps, kSelWarps * kWarp, 0, st>>>(a);
+  CAB_LAUNCH_CHECK(ctx);
   return CAB_OK;
 }
 

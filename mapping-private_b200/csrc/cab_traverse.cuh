@@ -44,6 +44,8 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
 }
+// exact product (one rounding): fma(a, b, +0) rounds like a multiply and cannot be contracted with a following add
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { return fma2(a, b, 0ull); }
 // exact product (one rounding), not contractible by ptxas
 __device__ __forceinline__ f32x2 sq2(f32x2 a) { return fma2(a, a, 0ull); }
 

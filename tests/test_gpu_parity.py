@@ -107,7 +107,8 @@ def test_normals_parity_c1(ctx, ctx_exact, oracle, c1, exact):
 
 
 @pytest.mark.parametrize("exact", [False, True])
-@pytest.mark.parametrize("max_nn,ndiv,plane,flags", [(0, 10, 0.1, 0), (75, 10, 0.1, 0), (0, 5, 0.2, 2 | 4), (0, 7, 0.15, 4)])
+@pytest.mark.parametrize("max_nn,ndiv,plane,flags", [(0, 10, 0.1, 0), (75, 10, 0.1, 0), (150, 10, 0.1, 0), (12, 10, 0.1, 2), (0, 5, 0.2, 2 | 4),
+                                                     (0, 7, 0.15, 4)])
 def test_rsd_parity_given_normals(ctx, ctx_exact, oracle, exact, max_nn, ndiv, plane, flags):
     c = ctx_exact if exact else ctx
     pts = synth.tabletop(40_000, noise_sigma=0.0004)
@@ -125,8 +126,34 @@ def test_rsd_parity_given_normals(ctx, ctx_exact, oracle, exact, max_nn, ndiv, p
         assert np.mean(rmin == omin) > 0.999 and np.mean(rmax == omax) > 0.999
 
 
+def test_rsd_truncation_with_ties_and_missing_normals(ctx, oracle):
+    """The max_nn paths of the fast mode: a lattice (every distance occurs many times: the target bin of the d2 histogram
+    overflows its list and the packet takes the exact-threshold path) and a cloud with NaN normals (such neighbours count
+    for the truncation but form no pair), against the oracle's (d2, index) rule."""
+    g = np.arange(0, 0.12, 0.004, dtype=np.float32)
+    lattice = np.stack(np.meshgrid(g, g, g[:6], indexing="ij"), axis=-1).reshape(-1, 3)
+    noisy = synth.tabletop(20_000, noise_sigma=0.0004)
+    for pts, max_nn in ((lattice, 40), (noisy, 60), (noisy, 200)):
+        r = 0.02
+        o4, _ = oracle.normals(pts, r)
+        o4[::37, :3] = np.nan
+        ctx.upload(pts)
+        ctx.build_grid(r)
+        ctx.set_normals(o4)
+        rmin, rmax = ctx.rsd(r, max_nn=max_nn)
+        k_gpu = ctx.profile()["neighbour_sum"]
+        omin, omax, _ = oracle.rsd(pts, o4, r, max_nn=max_nn)
+        assert np.max(np.abs(rmin - omin) / omin) <= RADIUS_TOL_REL and np.max(np.abs(rmax - omax) / omax) <= RADIUS_TOL_REL
+        off, _, _ = oracle.radius_search(pts, pts, r, max_nn=max_nn)
+        assert k_gpu == int(off[-1])  # sum over queries of min(k, max_nn)
+
+
 def test_pipeline_c1(ctx, oracle, c1):
-    """normals -> RSD entirely on the GPU (fast mode) against the oracle pipeline."""
+    """normals -> RSD entirely on the GPU (fast mode) against the oracle pipeline.  Normals meet 1e-4 rad everywhere.
+    The radii cannot meet 1e-4 relative everywhere END TO END in any arithmetic that is not the reference's bit for bit:
+    its cosine is an fp32 expression (radius_estimation.cpp:153-155), and near |cos| = 1 one ulp of a normal moves the
+    angle by up to 3.5e-4 rad.  The bound is therefore the oracle's own: the spread of its radii when its normals are
+    moved by ONE ulp; the device path (normals within ~1e-6 rad of the oracle's) must stay well inside it."""
     r = 0.02
     ctx.upload(c1)
     ctx.build_grid(r)
@@ -134,13 +161,24 @@ def test_pipeline_c1(ctx, oracle, c1):
     rmin, rmax = ctx.rsd(r)
     o4, _ = oracle.normals(c1, r)
     omin, omax, _ = oracle.rsd(c1, o4, r)
-    emin = np.abs(rmin - omin) / omin
-    emax = np.abs(rmax - omax) / omax
-    print(f"pipeline: max rel err r_min {emin.max():.3e} r_max {emax.max():.3e}; "
-          f">1e-4: {(emin > 1e-4).sum()} / {(emax > 1e-4).sum()}")
-    # fp32 normals feed an ill-conditioned 1/angle^2 fit on near-planar points: bound the tail
-    assert np.mean(emin > RADIUS_TOL_REL) < 2e-3 and np.mean(emax > RADIUS_TOL_REL) < 2e-3
-    assert np.median(emin) < 1e-6 and np.median(emax) < 1e-6
+    good = ~np.isnan(o4[:, 0])
+    assert _angle(n4[good, :3], o4[good, :3]).max() <= NORMAL_TOL_RAD
+    rel = np.maximum(np.abs(rmin - omin) / omin, np.abs(rmax - omax) / omax)
+    rng = np.random.default_rng(7)
+    bumped = o4.copy()
+    sign = rng.integers(0, 2, size=(c1.shape[0], 3)).astype(np.float32) * 2 - 1
+    bumped[:, :3] = np.nextafter(o4[:, :3], o4[:, :3] + sign)
+    bmin, bmax, _ = oracle.rsd(c1, bumped, r)
+    self_rel = np.maximum(np.abs(bmin - omin) / omin, np.abs(bmax - omax) / omax)
+    print(f"pipeline: device vs oracle: {(rel > 1e-4).sum()} points over 1e-4 (max {rel.max():.3e}); "
+          f"oracle vs oracle with normals 1 ulp off: {(self_rel > 1e-4).sum()} (max {self_rel.max():.3e})")
+    # well inside the reference's own conditioning margin (measured: 0.14 % of the points against 1.6 %)
+    assert np.mean(rel > RADIUS_TOL_REL) <= 0.5 * np.mean(self_rel > RADIUS_TOL_REL)
+    assert np.median(rel) < 1e-6
+    # and with identical normals the radii agree everywhere
+    ctx.set_normals(o4)
+    smin, smax = ctx.rsd(r)
+    assert np.max(np.abs(smin - omin) / omin) <= RADIUS_TOL_REL and np.max(np.abs(smax - omax) / omax) <= RADIUS_TOL_REL
 
 
 def test_pipeline_exact_mode(ctx_exact, oracle):
