@@ -58,6 +58,8 @@ typedef struct cab_timings {
   float cluster_ms;   /* last cab_euclidean_clusters: union, statistics and labelling kernels (without the grid build) */
   float exchange_ms;  /* last cab_step_normals_rsd of a group: end of the RSD kernel -> every rank's results have arrived */
   float step_ms;      /* last cab_step_normals_rsd: first kernel of the build -> end of the step, on the device */
+  int32_t shard_mode; /* last cab_build_grid: 0 whole cloud; 1 slab, halo normals recomputed; 2 slab, halo normals exchanged
+                         with the neighbouring ranks (cab_step_normals_rsd of a group whose slabs are two layers thick) */
 } cab_timings;
 
 /* ---- lifetime ------------------------------------------------------------------------ */

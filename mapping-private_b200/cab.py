@@ -49,7 +49,7 @@ class Timings(C.Structure):
         ("n_points", C.c_int64), ("n_valid", C.c_int64), ("n_packets", C.c_int64), ("n_rows", C.c_int64),
         ("n_cells", C.c_int64), ("neighbour_sum", C.c_int64), ("candidate_sum", C.c_int64),
         ("kernel_launches", C.c_int64), ("n_sorted", C.c_int64), ("knn_ms", C.c_float), ("knn_rounds", C.c_int32), ("pfh_ms", C.c_float), ("cluster_ms", C.c_float),
-        ("exchange_ms", C.c_float), ("step_ms", C.c_float),
+        ("exchange_ms", C.c_float), ("step_ms", C.c_float), ("shard_mode", C.c_int32),
     ]
 
     def as_dict(self):

@@ -290,6 +290,7 @@ void cab_destroy(cab_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  comm_free(ctx);  // first: while the context belongs to a group its working normals live in a buffer the group owns
   DevBuf* bufs[] = {&ctx->b_xyz, &ctx->b_domoff, &ctx->b_domid, &ctx->b_bounds, &ctx->b_domains, &ctx->b_keys[0],
                     &ctx->b_keys[1], &ctx->b_keys[2], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_vals[2], &ctx->b_thr_flag, &ctx->b_knn_avg, &ctx->b_knn_done, &ctx->b_pfh[0], &ctx->b_pfh[1], &ctx->b_pfh[2], &ctx->b_cluster, &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
                     &ctx->b_cellcnt, &ctx->b_cellstart, &ctx->b_rowpk, &ctx->b_packets, &ctx->b_nrm, &ctx->b_nrm_in,
@@ -300,7 +301,6 @@ void cab_destroy(cab_ctx* ctx) {
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   svm_free(ctx);
-  comm_free(ctx);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->h_step) cudaFreeHost(ctx->h_step);
   for (auto& ev : ctx->ev)
@@ -546,14 +546,27 @@ int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_norm
     ~Deferred() { c->defer_sync = false; }
   } deferred(ctx);
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[8], st));
-  int rc = build_grid(ctx, cell);
+  int rc = CAB_OK;
+  if (exchange) rc = comm_prepare(ctx, ctx->n);  // before the build: the working normals move into the exported buffer
+  ctx->want_halo_exchange = exchange && rc == CAB_OK;
+  if (rc == CAB_OK) rc = build_grid(ctx, cell);
+  ctx->want_halo_exchange = false;
   const bool push = rc == CAB_OK && exchange && ctx->slab;
+  const bool halo = push && ctx->slab_info.exchange != 0;  // known since the build's second host round trip
   if (rc == CAB_OK && exchange && !ctx->slab && ctx->n_valid > 0)
     rc = fail(ctx, CAB_ERR_STATE, "cab_step_normals_rsd: the group's shard was reset (cab_set_shard) behind its back");
   if (rc == CAB_OK && push) rc = comm_step_begin(ctx);
   if (rc == CAB_OK) rc = run_normals(ctx, (float)r, max_nn_normals, vp);
+  if (rc == CAB_OK && halo) rc = comm_halo_send(ctx);
   if (rc == CAB_OK && push) rc = comm_step_before_push(ctx);
-  if (rc == CAB_OK) rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags);
+  if (halo) {
+    // the halo rows' normals travel while the packets that do not read them run
+    if (rc == CAB_OK) rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags, 1);
+    if (rc == CAB_OK) rc = comm_halo_receive(ctx);
+    if (rc == CAB_OK) rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags, 2);
+  } else if (rc == CAB_OK) {
+    rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags);
+  }
   if (rc == CAB_OK) rc = cudaEventRecord(ctx->ev[9], st) == cudaSuccess ? CAB_OK : fail(ctx, CAB_ERR_CUDA, "cudaEventRecord failed");
   if (rc == CAB_OK && push) rc = comm_step_end(ctx, plane_radius);
   if (rc == CAB_OK) rc = cudaEventRecord(ctx->ev[10], st) == cudaSuccess ? CAB_OK : fail(ctx, CAB_ERR_CUDA, "cudaEventRecord failed");

@@ -79,7 +79,9 @@ NcclApi* nccl_api(std::string* why) {
 }
 
 // What a rank tells the others about its exchange buffers.
-constexpr int kBufNrm = 0, kBufRsd = 1, kBufPerm = 2, kBufCloud = 3, kBufSync = 4, kNumBufs = 5;
+// kBufWork: the rank's WORKING normals (local sorted order, what its kernels read and write: ctx->b_nrm is pointed at
+// it while the context belongs to a group), reachable by the neighbours for the halo exchange
+constexpr int kBufNrm = 0, kBufRsd = 1, kBufPerm = 2, kBufCloud = 3, kBufSync = 4, kBufWork = 5, kNumBufs = 6;
 struct CommBlob {
   int64_t pid;
   int32_t device;
@@ -115,6 +117,7 @@ struct SyncBlock {
   unsigned long long mail[kMaxPeers];   // (seq << 32) | own query count of rank p
   unsigned done[kMaxPeers];             // seq once rank p's pushes of this step are complete
   unsigned cloud[kMaxPeers];            // cloud_seq once rank p's slice of the cloud has arrived
+  unsigned normals[kMaxPeers];          // seq once rank p's normals pass is complete and its top layer has been stored into the rank above
   unsigned long long total;             // sum of the ranks' counts of the last step (host reads it back)
 };
 
@@ -193,15 +196,16 @@ __global__ void post_flag_kernel(PeerSync peers, int rank, int world, unsigned s
   const int p = threadIdx.x;
   if (p >= world) return;
   __threadfence_system();
-  unsigned* f = which == 0 ? &peers.block[p]->done[rank] : &peers.block[p]->cloud[rank];
+  unsigned* f = which == 0 ? &peers.block[p]->done[rank] : which == 1 ? &peers.block[p]->cloud[rank] : &peers.block[p]->normals[rank];
   st_release_sys(f, seq);
 }
 
+// waits for the flag of every rank (from < 0) or of rank `from` alone
 __global__ void wait_flag_kernel(SlabInfo* __restrict__ info, int* __restrict__ error_out, SyncBlock* __restrict__ mine, int world,
-                                 unsigned seq, int which, unsigned long long timeout_ns) {
+                                 unsigned seq, int which, unsigned long long timeout_ns, int from = -1) {
   const int p = threadIdx.x;
-  if (p >= world) return;
-  const unsigned* f = which == 0 ? &mine->done[p] : &mine->cloud[p];
+  if (p >= world || (from >= 0 && p != from)) return;
+  const unsigned* f = which == 0 ? &mine->done[p] : which == 1 ? &mine->cloud[p] : &mine->normals[p];
   const unsigned long long t0 = global_timer_ns();
   while (ld_acquire_sys(f) != seq) {
     if (global_timer_ns() - t0 > timeout_ns) {
@@ -211,6 +215,22 @@ __global__ void wait_flag_kernel(SlabInfo* __restrict__ info, int* __restrict__ 
     }
     __nanosleep(200);
   }
+}
+
+// Halo exchange, both directions driven by the LOWER rank of a pair (it knows every offset involved: its top layer is
+// the upper rank's first rows, and the upper rank's bottom layer starts where that rank's lower halo ends, i.e. after
+// as many points as the lower rank's top layer holds).
+//   send: my top layer of own rows  -> positions [0, count) of the rank above
+__global__ void __launch_bounds__(256) halo_send_kernel(const SlabInfo* __restrict__ info, const float4* __restrict__ mine,
+                                                        float4* __restrict__ above) {
+  const int first = info->top_src, count = info->q1 - first;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) above[i] = mine[first + i];
+}
+//   fetch: the bottom layer of the rank above -> my upper halo, positions [q1, n_selected)
+__global__ void __launch_bounds__(256) halo_fetch_kernel(const SlabInfo* __restrict__ info, float4* __restrict__ mine,
+                                                         const float4* __restrict__ above) {
+  const int src = info->q1 - info->top_src, dst = info->q1, count = info->n_selected - info->q1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) mine[dst + i] = above[src + i];
 }
 
 // concatenated (sorted-order) results -> one range [j0, j1) of the input order
@@ -287,7 +307,8 @@ int make_blob(cab_ctx* ctx, int64_t n, CommBlob* blob) {
   close_peers(ctx);
   const size_t np = (size_t)std::max<int64_t>(n, 1);
   const size_t bytes[kNumBufs] = {np * sizeof(float4), np * sizeof(float2), np * sizeof(int), np * 3 * sizeof(float) + 64,
-                                  sizeof(SyncBlock)};
+                                  sizeof(SyncBlock), np * sizeof(float4)};
+  if (ctx->b_nrm.p == cs->own[kBufWork].p) ctx->b_nrm = DevBuf{};  // the working normals move with their buffer
   for (int b = 0; b < kNumBufs; ++b) {
     if (cs->own[b].p && cs->own[b].cap >= bytes[b]) continue;
     if (cs->own[b].p) cudaFree(cs->own[b].p);
@@ -307,6 +328,10 @@ int make_blob(cab_ctx* ctx, int64_t n, CommBlob* blob) {
     }
   }
   cs->cap_points = (int64_t)np;
+  // the context's normals live in the exported buffer from now on
+  if (ctx->b_nrm.p && ctx->b_nrm.p != cs->own[kBufWork].p) cudaFree(ctx->b_nrm.p);
+  ctx->b_nrm = cs->own[kBufWork];
+  ctx->have_normals = false;
   std::memset(blob, 0, sizeof(*blob));
   blob->pid = (int64_t)getpid();
   blob->device = ctx->device;
@@ -422,6 +447,10 @@ void comm_free(cab_ctx* ctx) {
   if (!cs) return;
   cudaStreamSynchronize(ctx->stream);
   close_peers(ctx);
+  if (ctx->b_nrm.p == cs->own[kBufWork].p) {  // the arena gets its own normals buffer back on the next pass
+    ctx->b_nrm = DevBuf{};
+    ctx->have_normals = false;
+  }
   for (auto& b : cs->own)
     if (b.p) cudaFree(b.p);
   if (cs->stage.p) cudaFree(cs->stage.p);
@@ -451,6 +480,37 @@ int comm_step_before_push(cab_ctx* ctx) {  // after the normals pass
   wait_counts_kernel<<<1, kMaxPeers, 0, ctx->stream>>>((SlabInfo*)slab_info_device(ctx), (SyncBlock*)cs->own[kBufSync].p, cs->rank,
                                                      cs->world, cs->seq, cs->timeout_ns);
   CAB_LAUNCH_CHECK(ctx);
+  return CAB_OK;
+}
+
+int comm_halo_send(cab_ctx* ctx) {  // after the normals pass
+  CommState* cs = ctx->comm;
+  cudaStream_t st = ctx->stream;
+  if (cs->rank + 1 < cs->world) {
+    halo_send_kernel<<<128, 256, 0, st>>>(slab_info_device(ctx), (const float4*)cs->own[kBufWork].p,
+                                          (float4*)cs->peer[cs->rank + 1][kBufWork]);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  post_flag_kernel<<<1, kMaxPeers, 0, st>>>(peer_sync(cs), cs->rank, cs->world, cs->seq, 2);
+  CAB_LAUNCH_CHECK(ctx);
+  return CAB_OK;
+}
+
+int comm_halo_receive(cab_ctx* ctx) {  // before the boundary packets of the RSD pass
+  CommState* cs = ctx->comm;
+  cudaStream_t st = ctx->stream;
+  SlabInfo* info = (SlabInfo*)slab_info_device(ctx);
+  SyncBlock* mine = (SyncBlock*)cs->own[kBufSync].p;
+  if (cs->rank + 1 < cs->world) {  // the rank above has finished its normals: fetch its bottom layer
+    wait_flag_kernel<<<1, kMaxPeers, 0, st>>>(info, nullptr, mine, cs->world, cs->seq, 2, cs->timeout_ns, cs->rank + 1);
+    CAB_LAUNCH_CHECK(ctx);
+    halo_fetch_kernel<<<128, 256, 0, st>>>(info, (float4*)cs->own[kBufWork].p, (const float4*)cs->peer[cs->rank + 1][kBufWork]);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  if (cs->rank > 0) {  // the rank below has stored its top layer into my lower halo
+    wait_flag_kernel<<<1, kMaxPeers, 0, st>>>(info, nullptr, mine, cs->world, cs->seq, 2, cs->timeout_ns, cs->rank - 1);
+    CAB_LAUNCH_CHECK(ctx);
+  }
   return CAB_OK;
 }
 

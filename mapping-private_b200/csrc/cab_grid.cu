@@ -321,37 +321,53 @@ __global__ void __launch_bounds__(256) sample_hist_kernel(const float* __restric
   }
 }
 
-// cost of a row = sum over its cells of (sampled points) x (estimated candidates per point + a constant per point);
-// one warp per row
-__global__ void __launch_bounds__(256) row_cost_kernel(const Domain* __restrict__ domains, const int* __restrict__ cnt,
-                                                       int sample, long long* __restrict__ rowcost) {
+// cost of a row = sum over its cells of (sampled points) x (estimated candidates per point + constants).  One block
+// per strip of kCostRows rows of one z layer: the 3 x (kCostRows + 2) rows it reads are staged in shared memory chunk by
+// chunk along x (coalesced loads, every table row read ~4 times instead of 9, no divergent gathers); one warp per row.
+constexpr int kCostRows = 6, kCostChunk = 256;
+__global__ void __launch_bounds__(kCostRows * 32) row_cost_kernel(const Domain* __restrict__ domains, const int* __restrict__ cnt,
+                                                                  int sample, long long* __restrict__ rowcost) {
+  __shared__ int tile[3][kCostRows + 2][kCostChunk + 2];
   const Domain dm = domains[0];
-  const int n_rows = dm.ny * dm.nz;
-  const int lane = threadIdx.x & 31;
-  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * (blockDim.x >> 5)) {
-    const int cy = row % dm.ny, cz = row / dm.ny;
-    const int* mine = cnt + (long long)row * dm.nx;
-    long long acc = 0;
-    for (int cx = lane; cx < dm.nx; cx += kWarp) {
-      const int c = mine[cx];
-      if (c == 0) continue;
-      // candidates ~ the 3 x 3 rows around the cell, along x the cell itself plus 0.7 of either neighbour: a packet's x
-      // window is its own extent + 2 r, about 2.4 cells (a full 3-cell stencil overrates surfaces that run along x,
-      // e.g. the walls an end slab consists of, by a quarter against surfaces across x)
-      int s10 = 0;
-      for (int z = max(cz - 1, 0); z <= min(cz + 1, dm.nz - 1); ++z)
-        for (int y = max(cy - 1, 0); y <= min(cy + 1, dm.ny - 1); ++y) {
-          const int* r = cnt + ((long long)z * dm.ny + y) * dm.nx;
-          s10 += 10 * r[cx] + 7 * ((cx > 0 ? r[cx - 1] : 0) + (cx + 1 < dm.nx ? r[cx + 1] : 0));
-        }
-      // + a constant per point (fit, eigen-solve: 2 candidates' worth) and per occupied cell (sparse rows make many short
-      // packets, each with its own run table and chunk overhead: 16 candidates' worth per cell)
-      acc += (long long)c * ((long long)s10 * sample + 20) + 160;
+  const int strips = (dm.ny + kCostRows - 1) / kCostRows;
+  const int cz = blockIdx.x / strips, cy0 = (blockIdx.x % strips) * kCostRows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cy = cy0 + warp;
+  long long acc = 0;
+  for (int x0 = 0; x0 < dm.nx; x0 += kCostChunk) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * (kCostRows + 2) * (kCostChunk + 2); i += blockDim.x) {
+      const int xx = i % (kCostChunk + 2), rr = (i / (kCostChunk + 2)) % (kCostRows + 2), zz = i / ((kCostChunk + 2) * (kCostRows + 2));
+      const int x = x0 + xx - 1, y = cy0 + rr - 1, z = cz + zz - 1;
+      int v = 0;
+      if (x >= 0 && x < dm.nx && y >= 0 && y < dm.ny && z >= 0 && z < dm.nz) v = cnt[((long long)z * dm.ny + y) * dm.nx + x];
+      tile[zz][rr][xx] = v;
     }
+    __syncthreads();
+    if (cy < dm.ny) {
+      for (int xx = lane; xx < kCostChunk && x0 + xx < dm.nx; xx += kWarp) {
+        const int c = tile[1][warp + 1][xx + 1];
+        if (c == 0) continue;
+        // candidates ~ the 3 x 3 rows around the cell, along x the cell itself plus 0.7 of either neighbour: a packet's x
+        // window is its own extent + 2 r, about 2.4 cells (a full 3-cell stencil overrates surfaces that run along x,
+        // e.g. the walls an end slab consists of, by a quarter against surfaces across x)
+        int s10 = 0;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
-    if (lane == 0) rowcost[row] = acc;
+        for (int zz = 0; zz < 3; ++zz)
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr) {
+            const int* r = &tile[zz][warp + rr][xx];
+            s10 += 10 * r[1] + 7 * (r[0] + r[2]);
+          }
+        // + a constant per point (fit, eigen-solve: 2 candidates' worth) and per occupied cell (sparse rows make many
+        // short packets, each with its own run table and chunk overhead: 16 candidates' worth per cell)
+        acc += (long long)c * ((long long)s10 * sample + 20) + 160;
+      }
+    }
   }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  if (lane == 0 && cy < dm.ny) rowcost[(long long)cz * dm.ny + cy] = acc;
 }
 
 __device__ __forceinline__ long long cum_before(const long long* __restrict__ cum, int p) { return p > 0 ? cum[p - 1] : 0; }
@@ -382,7 +398,7 @@ __device__ __forceinline__ int cut_at(const long long* __restrict__ cum, int n_i
 // cuts until own cost + halo_permille/1000 * halo cost is the same for every rank.  Leaves the rank's row ranges in
 // `info` and turns domains[0] into the slab's table geometry.
 __global__ void __launch_bounds__(1024) slab_split_kernel(const long long* __restrict__ cum, int world, int rank,
-                                                          int halo_permille, Domain* __restrict__ domains,
+                                                          int halo_permille, int want_exchange, Domain* __restrict__ domains,
                                                           int* __restrict__ cuts, SlabInfo* __restrict__ info) {
   __shared__ int s[65];
   __shared__ long long halo[64];
@@ -406,7 +422,7 @@ __global__ void __launch_bounds__(1024) slab_split_kernel(const long long* __res
       const int a = s[g], b = s[g + 1];
       if (g > 0) h += cum_before(cum, a) - cum_before(cum, max(a - layer, 0));
       if (g < world - 1) h += cum_before(cum, min(b + layer, n_rows)) - cum_before(cum, b);
-      halo[g] = h * halo_permille / 1000;
+      halo[g] = want_exchange ? 0 : h * halo_permille / 1000;  // exchanged halos cost (almost) nothing
     }
     __syncthreads();
     if (g == 0) {
@@ -438,7 +454,17 @@ __global__ void __launch_bounds__(1024) slab_split_kernel(const long long* __res
     SlabInfo si{};
     si.own_lo = s[rank];
     si.own_hi = s[rank + 1];
-    if (si.own_hi > si.own_lo) {
+    // the exchange needs every rank to be two layers thick: a halo then comes from the immediate neighbour alone and
+    // there are packets to run while it travels
+    bool thick = want_exchange != 0;
+    for (int c = 0; c < world; ++c) thick = thick && s[c + 1] - s[c] >= 2 * layer;
+    si.exchange = thick ? 1 : 0;
+    if (thick) {
+      si.halo_lo = si.own_lo;
+      si.halo_hi = si.own_hi;
+      si.win_lo = max(si.own_lo - layer, 0);
+      si.win_hi = min(si.own_hi + layer, n_rows);
+    } else if (si.own_hi > si.own_lo) {
       si.halo_lo = max(si.own_lo - layer, 0);
       si.halo_hi = min(si.own_hi + layer, n_rows);
       si.win_lo = max(si.own_lo - 2 * layer, 0);
@@ -567,6 +593,13 @@ __global__ void slab_ranges_kernel(const Domain* __restrict__ domains, const int
   si.ph1 = packet_base[first_cell(si.halo_hi)];
   si.q0 = cell_start[first_cell(si.own_lo)];
   si.q1 = cell_start[first_cell(si.own_hi)];
+  const int layer = dm.ny + 1;
+  const int lo_end = min(si.own_lo + layer, si.own_hi), hi_begin = max(si.own_hi - layer, lo_end);
+  si.r_blo[0] = si.p0;
+  si.r_blo[1] = si.r_int[0] = packet_base[first_cell(lo_end)];
+  si.r_int[1] = si.r_bhi[0] = packet_base[first_cell(hi_begin)];
+  si.r_bhi[1] = si.p1;
+  si.top_src = cell_start[first_cell(max(si.own_hi - layer, si.own_lo))];
   *info = si;
 }
 
@@ -852,6 +885,7 @@ int build_grid(cab_ctx* ctx, float cell) {
     CAB_LAUNCH_CHECK(ctx);
   }
   ctx->n_sorted = n;
+  ctx->tm.shard_mode = 0;
   ctx->tm.n_sorted = ctx->n_valid;
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -903,11 +937,12 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
     sample_hist_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, sample, d_dom,
                                                                         ctx->inv_cell, (int*)ctx->b_cellcnt.p);
     CAB_LAUNCH_CHECK(ctx);
-    const unsigned blocks = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->sm_count * 16);
-    row_cost_kernel<<<blocks, 256, 0, st>>>(d_dom, (const int*)ctx->b_cellcnt.p, sample, rowcost);
+    const unsigned blocks = (unsigned)(((int64_t)dm.ny + kCostRows - 1) / kCostRows * dm.nz);
+    row_cost_kernel<<<blocks, kCostRows * 32, 0, st>>>(d_dom, (const int*)ctx->b_cellcnt.p, sample, rowcost);
     CAB_LAUNCH_CHECK(ctx);
     CAB_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->b_cubtmp.p, tmp_cost, rowcost, cum, (int)rows, st));
-    slab_split_kernel<<<1, 32 * std::min(32, std::max(2, w)), 0, st>>>(cum, w, ctx->shard_rank, ctx->halo_permille, d_dom, cuts, info);
+    slab_split_kernel<<<1, 32 * std::min(32, std::max(2, w)), 0, st>>>(cum, w, ctx->shard_rank, ctx->halo_permille,
+                                                                       ctx->want_halo_exchange ? 1 : 0, d_dom, cuts, info);
     CAB_LAUNCH_CHECK(ctx);
     // stable selection of the window's points: per-block compaction, then a scan of the blocks' counts
     CAB_CUDA(ctx, cudaMemsetAsync(sel_cnt + sel_blocks, 0, 4, st));
@@ -925,6 +960,7 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   SlabInfo si;
   std::memcpy(&si, ctx->h_pin, sizeof(SlabInfo));
+  ctx->slab_info = si;  // rows and mode are final; the packet / query ranges follow with finish_slab()
   const int m = si.n_selected;
   const int64_t lrows = (int64_t)si.win_hi - si.win_lo;
   const int64_t lcells = lrows * dm.nx;
@@ -1024,6 +1060,7 @@ int finish_slab(cab_ctx* ctx) {
   ctx->slab_info_valid = true;
   ctx->n_packets = ctx->slab_info.n_packets;
   ctx->tm.n_packets = ctx->n_packets;
+  ctx->tm.shard_mode = ctx->slab_info.exchange ? 2 : 1;
   CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.build_ms, ctx->ev[0], ctx->ev[1]));
   return CAB_OK;
 }

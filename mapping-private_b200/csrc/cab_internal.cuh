@@ -52,6 +52,14 @@ struct SlabInfo {
   int q0, q1;            // own queries: positions in the local sorted arrays
   int gbase;             // position of q0 in the concatenation of all ranks' own slices (result exchange)
   int error;             // != 0: a peer did not answer in time (result exchange)
+  // Halo exchange (cab_step_normals_rsd of a group, every rank at least two layers thick): the halo rows' normals are
+  // not recomputed but received -- the window is own +- ONE layer, halo = own, and the RSD pass runs in two launches:
+  // the packets that read no halo row first (r_int), the two boundary layers (r_blo, r_bhi) once the neighbours'
+  // normals have arrived.
+  int exchange;          // 1: the mode above
+  int top_src;           // local position of the first point of the top layer of own rows (sent to the rank above)
+  int r_int[2];          // packets of own rows at least one layer away from either end
+  int r_blo[2], r_bhi[2];  // packets of the bottom / top layer of own rows
 };
 
 // 32-query work unit: consecutive sorted points of one row.
@@ -161,6 +169,7 @@ struct cab_ctx {
   bool slab_info_valid = false;
   int64_t n_sorted = 0;            // entries of the sorted arrays: n, or the slab window's points
   int halo_permille = 470;         // share of the normals pass in a packet's cost (shard balance)
+  bool want_halo_exchange = false; // set by cab_step_normals_rsd of a group: build_slab may choose the exchange mode
   bool defer_sync = false;         // run_normals / run_rsd leave the stream running (cab_step_*: one sync per step)
 
   // device arena (grow-only)
@@ -218,7 +227,8 @@ void read_stats(cab_ctx* ctx, const void* staged = nullptr);  // sums the kStatS
 int compute_bounds(cab_ctx* ctx);
 int build_grid(cab_ctx* ctx, float cell);
 int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsigned char* done = nullptr);
-int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, int flags);
+// phase 0: the whole pass; 1: prologue + the packets that read no halo row; 2: the boundary packets + epilogue
+int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, int flags, int phase = 0);
 int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done = nullptr, bool halo = false);  // max_nn truncation thresholds (halo: also for a slab's halo packets)
 int run_nn_hist(cab_ctx* ctx, float r, int max_nn);  // cab_topk.cu: histogram half of the truncated fast RSD pass
 int run_knn_mean(cab_ctx* ctx, int k, float cell_hint, double* avg);  // cab_knn.cu
@@ -232,9 +242,12 @@ int permute_normals_in(cab_ctx* ctx, const float* nx, const float* ny, const flo
 int download_results(cab_ctx* ctx, float* n4, float* rmin, float* rmax);
 void svm_free(cab_ctx* ctx);
 void comm_free(cab_ctx* ctx);                                  // cab_comm.cu
+int comm_prepare(cab_ctx* ctx, int64_t n);                     // collective: exchange buffers for n points, mapped on every rank
 bool comm_active(const cab_ctx* ctx);                          // the context belongs to a group of more than one rank
 int comm_step_begin(cab_ctx* ctx);                             // after the slab build: publish this rank's query count
 int comm_step_before_push(cab_ctx* ctx);                       // before the RSD kernel: place the slice in the concatenation
+int comm_halo_send(cab_ctx* ctx);                              // after the normals pass: top layer to the rank above, "normals done" to all
+int comm_halo_receive(cab_ctx* ctx);                           // before the boundary packets: fetch the layer above, wait for the layer below
 int comm_step_end(cab_ctx* ctx, double plane_radius);          // after the RSD kernel: completion flags
 int comm_step_finish(cab_ctx* ctx);                            // after the step's synchronisation
 void comm_push_targets(const cab_ctx* ctx, PushTargets* out);  // world = 0 unless a result exchange is armed for this step

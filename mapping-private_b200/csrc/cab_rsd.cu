@@ -40,6 +40,7 @@ struct RsdArgs {
   GridView g;
   int p0, p1;
   const int* range;        // optional device-side {p0, p1} (own packets of a slab); null: the values above
+  const int* range_b;      // optional second device-side range, processed after the first (the two boundary layers)
   const SlabInfo* slab;    // with push.world > 0: where the rank's slice sits in the concatenated results
   PushTargets push;        // result exchange: every rank's copy of the concatenated arrays (peer memory)
   float r, r2;
@@ -125,11 +126,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
   const float r2 = a.r2;
   const float bscale = a.bin_scale;
   const int last_bin = ndiv - 1;
-  const int p0 = a.range ? a.range[0] : a.p0, p1 = a.range ? a.range[1] : a.p1;
+  const int p0 = a.range ? a.range[0] : a.p0, n1 = (a.range ? a.range[1] : a.p1) - p0;
+  const int pb = a.range_b ? a.range_b[0] : 0, n2 = a.range_b ? a.range_b[1] - pb : 0;
   for (;;) {
-    const int pid = p0 + next_packet(a.stats, lane);
-    if (pid >= p1) break;
-    if (a.only && !a.only[pid - p0]) continue;
+    const int w = next_packet(a.stats, lane);
+    if (w >= n1 + n2) break;
+    const int pid = w < n1 ? p0 + w : pb + (w - n1);
+    if (a.only && !a.only[pid - a.p0]) continue;
     const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
     const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
     const float4 nq = a.nrm[pc.qi];
@@ -422,11 +425,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
   unsigned* my_max = my_min + kWarp;
   const unsigned bins_addr = smem_u32(my_min), thr_addr = smem_u32(thr);
   const float r2 = a.r2, bscale = a.bin_scale;
-  const int p0 = a.range ? a.range[0] : a.p0, p1 = a.range ? a.range[1] : a.p1;
+  const int p0 = a.range ? a.range[0] : a.p0, n1 = (a.range ? a.range[1] : a.p1) - p0;
+  const int pb = a.range_b ? a.range_b[0] : 0, n2 = a.range_b ? a.range_b[1] - pb : 0;
   for (;;) {
-    const int pid = p0 + next_packet(a.stats, lane);
-    if (pid >= p1) break;
-    if (kTrunc && a.skip && a.skip[pid - p0]) continue;  // left to the exact-threshold path
+    const int w = next_packet(a.stats, lane);
+    if (w >= n1 + n2) break;
+    const int pid = w < n1 ? p0 + w : pb + (w - n1);
+    if (kTrunc && a.skip && a.skip[pid - a.p0]) continue;  // left to the exact-threshold path
     // the packet and its candidate runs (load_packet works on a ChunkTile; the run tables sit at the same place here)
     PacketCtx pc;
     {
@@ -664,7 +669,7 @@ int launch_rsd(cab_ctx* ctx, const RsdArgs& a, unsigned blocks, size_t smem) {
 
 }  // namespace
 
-int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, int flags) {
+int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, int flags, int phase) {
   if (!ctx->have_grid) return fail(ctx, CAB_ERR_STATE, "cab_rsd: build the grid first");
   if (!ctx->have_normals) return fail(ctx, CAB_ERR_STATE, "cab_rsd: missing normals");
   const float rf = (float)r;
@@ -680,7 +685,10 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   static const bool legacy = std::getenv("CAB_RSD_LEGACY") != nullptr;  // A/B switch for profiling
   // fast mode with max_nn: one histogram traversal, then the RSD traversal settles the truncation itself
   const bool trunc_fast = use_thr && !ctx->cfg.exact && !legacy;
-  if (trunc_fast) {
+  if (phase == 2) {
+    // second launch of a split pass: only the work counter starts over, everything else was set up by phase 1
+    CAB_CUDA(ctx, cudaMemsetAsync((unsigned long long*)ctx->b_stats.p + 2 * kStatSlots, 0, 8, st));
+  } else if (trunc_fast) {
     if (int rc = run_nn_hist(ctx, rf, max_nn)) return rc;
   } else if (use_thr) {
     if (int rc = run_thresholds(ctx, rf, max_nn)) return rc;
@@ -693,15 +701,23 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   thr[ndiv] = INFINITY;
   // staged through its own device / pinned slots: in a deferred step nothing before it in the stream has been waited for
   if (int rc = reserve(ctx, ctx->b_stats2, sizeof(thr))) return rc;
-  std::memcpy(ctx->h_step + kStepThr, thr, sizeof(float) * (ndiv + 1));
-  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_stats2.p, ctx->h_step + kStepThr, sizeof(float) * (ndiv + 1), cudaMemcpyHostToDevice, st));
-  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, kStatBytes, st));
-  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+  if (phase != 2) {
+    std::memcpy(ctx->h_step + kStepThr, thr, sizeof(float) * (ndiv + 1));
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_stats2.p, ctx->h_step + kStepThr, sizeof(float) * (ndiv + 1), cudaMemcpyHostToDevice, st));
+    CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, kStatBytes, st));
+    CAB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+  }
   RsdArgs a{};
   a.g = grid_view(ctx);
   packet_range(ctx, &a.p0, &a.p1);
   a.range = slab_packet_range(ctx, false);
   a.slab = slab_info_device(ctx);
+  if (phase == 1) {
+    a.range = a.slab->r_int;  // device addresses of the SlabInfo's ranges
+  } else if (phase == 2) {
+    a.range = a.slab->r_blo;
+    a.range_b = a.slab->r_bhi;
+  }
   comm_push_targets(ctx, &a.push);
   a.r = rf;
   a.r2 = r2;
@@ -753,6 +769,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
     else rc = use_thr ? launch_rsd<false, true>(ctx, a, blocks, smem) : launch_rsd<false, false>(ctx, a, blocks, smem);
     if (rc) return rc;
   }
+  if (phase == 1) return CAB_OK;  // the boundary packets and the epilogue follow in phase 2
   if (!ctx->slab && n > ctx->n_valid) {
     fill_invalid_rsd<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((float2*)ctx->b_rsd.p, (float*)ctx->b_rdif.p, ctx->n_valid, n,
                                                                     (float)plane_radius);

@@ -93,8 +93,44 @@ def test_local_group_every_rank_holds_all_results(world, max_nn):
         assert _same(p4, n4[lo:hi]) and _same(pmin, rmin[lo:hi]) and _same(pmax, rmax[lo:hi])
         total_k += prof["neighbour_sum"]
         assert e > b
+        assert prof["shard_mode"] == 2  # thick slabs: the halo rows' normals were exchanged, not recomputed
     if max_nn == 0:
         assert total_k == k  # every query answered by exactly one rank
+    for c in ctxs:
+        c.close()
+
+
+def test_local_group_thin_slabs_recompute_their_halos():
+    """Eight ranks on a small flat cloud: the slabs are thinner than two layers of rows, so the halo exchange is off and
+    every rank recomputes the normals of the rows around its own (shard_mode 1); same results."""
+    pts = synth.analytic_shape("plane", 6_000, side=0.3)
+    n = pts.shape[0]
+    n4, rmin, rmax, k = _single_gpu(pts)
+    world = 8
+    ctxs = [cab.Context(0) for _ in range(world)]
+    cab.comm_init_local(ctxs)
+    out, errs = [None] * world, []
+
+    def work(r):
+        try:
+            c = ctxs[r]
+            c.comm_upload_cloud(pts)
+            c.step_normals_rsd(R, R)
+            out[r] = (c.comm_download_range(0, n), c.profile())
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not errs, errs
+    for r in range(world):
+        (f4, fmin, fmax), prof = out[r]
+        assert _same(f4, n4) and _same(fmin, rmin) and _same(fmax, rmax), f"rank {r}"
+        assert prof["shard_mode"] == 1
+    assert sum(o[1]["neighbour_sum"] for o in out) == k
     for c in ctxs:
         c.close()
 
