@@ -592,6 +592,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         # the group behind the C ABI: NCCL carries the bootstrap, the data plane is peer memory (csrc/cab_comm.cu)
         ctx.comm_init(broadcast_comm_id(rank, cab), rank, world)
+        # every result crosses NVLink once, to the rank that owns the point's input index: after a step rank g holds the
+        # channels of input indices [n g / N, n (g + 1) / N) in input order
+        ctx.comm_set_layout(cab.COMM_LAYOUT_INPUT_RANGES)
     n = args.points
     pts = synth.room(n)
     d_xyz = torch.from_numpy(pts).to(dev)  # resident in HBM before the timed region
@@ -601,7 +604,7 @@ def main():
 
     def step(c=ctx, max_nn_rsd=0):
         """One pass of the hot path over the cloud in ONE C call: grid build + normals + RSD and, in a group, the
-        concatenation of the ranks' results (every rank ends up holding all of them)."""
+        concatenation of the ranks' results (input order, rank g holding the g-th N-th of the input indices)."""
         c.set_cloud_device(d_xyz.data_ptr(), n, 3)
         c.step_normals_rsd(RADIUS, RADIUS, max_nn_rsd=max_nn_rsd, ndiv=NDIV, plane_radius=PLANE_RADIUS)
 
@@ -651,12 +654,24 @@ def main():
 
     concatenated = None
     if world > 1:
-        # the concatenation is part of the timed step: check that THIS rank really holds every point's results
-        ptr, total = ctx.comm_device_ptr(cab.BUF_PERM)
-        perm_all = torch.as_tensor(_DevArray(ptr, (total,), "<i4"), device=dev)
-        seen = torch.zeros(n, dtype=torch.bool, device=dev)
-        seen[perm_all.long()] = True
-        concatenated = {"entries_on_this_rank": int(total), "distinct_points": int(seen.sum().item()), "points": n}
+        # the concatenation is part of the timed step: poison every rank's range, run one more step, and count the
+        # entries the ranks' RSD kernels (and, for non-finite points, the owner's selection pass) have written
+        p4, cnt = ctx.comm_device_ptr(cab.BUF_NRM_INPUT_RANGE)
+        p2, _ = ctx.comm_device_ptr(cab.BUF_RSD_INPUT_RANGE)
+        own4 = torch.as_tensor(_DevArray(p4, (cnt * 4,), "<i4"), device=dev)
+        own2 = torch.as_tensor(_DevArray(p2, (cnt * 2,), "<i4"), device=dev)
+        own4.fill_(-1)
+        own2.fill_(-1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        written = torch.tensor([int(((own4.view(-1, 4) != -1).any(dim=1) & (own2.view(-1, 2) != -1).any(dim=1)).sum().item()), cnt],
+                               device=dev, dtype=torch.int64)
+        dist.all_reduce(written, op=dist.ReduceOp.SUM)
+        concatenated = {"layout": "input ranges: rank g holds input indices [n g / N, n (g + 1) / N) in input order",
+                        "entries_written_by_one_step": int(written[0].item()), "entries": int(written[1].item()), "points": n}
 
     # ---- roofline of the dominant kernel (rsd_kernel), SURVEY section 8(d) accounting -------
     peak, peak_src = hbm_peak()
@@ -752,7 +767,7 @@ def main():
                     e2e_stage[k] += v
 
             path = ("per rank: cab_comm_upload_cloud (H2D of 1/N of the cloud + copy-engine replication over NVLink) -> cab_step_normals_rsd "
-                    "(slab build + normals + RSD, results pushed into every rank's concatenated arrays by the RSD kernel) -> "
+                    "(slab build + normals + RSD, every result pushed by the RSD kernel to the rank that owns its input index) -> "
                     "cab_comm_download_range: each rank copies ITS input-order range into ONE shared page-locked host array; bytes summed over ranks")
             d2h_bytes = n * 24
 
@@ -778,15 +793,21 @@ def main():
                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
                "stages_ms_rank0": {k: 1e3 * v / e2e_steps for k, v in e2e_stage.items()}, "path": path}
         if world > 1:
-            if rank == 0:  # the shared array against this rank's own copy of the concatenated results
+            # the shared array against the OTHER layout: one step that leaves every rank's results on every rank
+            ctx.comm_set_layout(cab.COMM_LAYOUT_REPLICATED)
+            dist.barrier()
+            step()
+            dist.barrier()
+            if rank == 0:
                 f4, fmin, fmax = ctx.comm_download_range(0, n)
                 sh = np.asarray(shared)
                 e2e["shared_host_array"] = {
                     "page_locked": registered,
-                    "equals_rank0_concatenation": bool(np.array_equal(sh[:4 * n].view(np.uint32), f4.reshape(-1).view(np.uint32)) and
-                                                       np.array_equal(sh[4 * n:5 * n].view(np.uint32), fmin.view(np.uint32)) and
-                                                       np.array_equal(sh[5 * n:].view(np.uint32), fmax.view(np.uint32)))}
+                    "equals_replicated_layout_on_rank0": bool(np.array_equal(sh[:4 * n].view(np.uint32), f4.reshape(-1).view(np.uint32)) and
+                                                              np.array_equal(sh[4 * n:5 * n].view(np.uint32), fmin.view(np.uint32)) and
+                                                              np.array_equal(sh[5 * n:].view(np.uint32), fmax.view(np.uint32)))}
             dist.barrier()
+            ctx.comm_set_layout(cab.COMM_LAYOUT_INPUT_RANGES)
             torch.cuda.cudart().cudaHostUnregister(h_all.data_ptr())
             del h_all, shared
             if rank == 0:
@@ -926,9 +947,10 @@ def main():
     if rank == 0:
         par = "single GPU"
         if world > 1:
-            par = (f"query-shard x{world}: cloud replicated, every rank keys / sorts / tabulates only its slab of rows (+ 2 layers), halo normals "
-                   "recomputed locally, results CONCATENATED inside the timed step: the RSD kernel stores normals, radii and input indices "
-                   "into every rank's copy of the result arrays over NVLink peer memory; one C call per step per rank")
+            par = (f"query-shard x{world}: cloud replicated, every rank keys / sorts / tabulates only its slab of rows (+ 1 layer), the halo rows' "
+                   "normals exchanged between neighbouring ranks over NVLink peer memory, results CONCATENATED inside the timed step: the RSD "
+                   "kernel stores every point's normal and radii into the arrays of the rank that owns its input index (input order; rank g "
+                   "holds input indices [n g / N, n (g + 1) / N)); cuts from a cost model + measured-time feedback; one C call per step per rank")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

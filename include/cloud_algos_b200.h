@@ -303,9 +303,10 @@ int cab_download_sorted(cab_ctx* ctx, int64_t begin, int64_t end, float* nxyz_cu
  * cab_set_cloud_device / cab_comm_upload_cloud, enqueued back to back with one host synchronisation at the end instead
  * of one per stage (the NormalEstimation -> LocalRadiusEstimation chain of cloud_algos/sample_pipeline.yaml as a frame
  * loop would run it).  Results stay on the device (cab_download*, CAB_BUF_*).  When the context belongs to a group
- * (cab_comm_init*), the step also concatenates the ranks' results: the RSD kernel stores every packet's normals, radii
- * and input indices into every rank's copy of the concatenated arrays (peer memory over NVLink), so that when the call
- * returns EVERY rank holds the results of ALL queries (cab_comm_device_ptr, cab_comm_download_range). */
+ * (cab_comm_init*), the step also concatenates the ranks' results: the RSD kernel stores every packet's normals and
+ * radii into peer memory over NVLink -- into every rank's copy of the concatenated arrays (replicated layout: when the
+ * call returns EVERY rank holds the results of ALL queries) or into the arrays of the rank that owns the point's input
+ * index (input-range layout, cab_comm_set_layout); see cab_comm_device_ptr, cab_comm_download_range. */
 int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_normals, const float vp[3], int32_t max_nn_rsd,
                          int32_t ndiv, double plane_radius, int32_t flags);
 
@@ -329,11 +330,32 @@ int cab_comm_init_local(cab_ctx** ctxs, int32_t world);
 int cab_comm_reserve(cab_ctx* ctx, int32_t rank, int32_t world, int64_t max_points, void* blob);
 int cab_comm_connect(cab_ctx* ctx, const void* blobs);
 int cab_comm_free(cab_ctx* ctx);
+/* Where the step's concatenated results live (the same choice on every rank; default REPLICATED):
+ *   CAB_COMM_LAYOUT_REPLICATED    every rank ends up holding the results of ALL queries, slab after slab in sorted order
+ *                                 plus the input index of every entry (cab_comm_device_ptr CAB_BUF_*_SORTED / _PERM);
+ *                                 cab_comm_download_range serves any input range on any rank.  world x the traffic.
+ *   CAB_COMM_LAYOUT_INPUT_RANGES  rank g ends up holding the results of input indices [n g / world, n (g + 1) / world) in
+ *                                 INPUT order (the ranks' arrays, rank after rank, are the channels radius_estimation.cpp:
+ *                                 204-214 appends): every result crosses NVLink once, to its owner;
+ *                                 cab_comm_download_range serves ranges inside the rank's own range
+ *                                 (cab_comm_device_ptr CAB_BUF_NRM_INPUT_RANGE / CAB_BUF_RSD_INPUT_RANGE). */
+#define CAB_COMM_LAYOUT_REPLICATED 0
+#define CAB_COMM_LAYOUT_INPUT_RANGES 1
+#define CAB_BUF_NRM_INPUT_RANGE 4 /* float4[hi-lo] nx,ny,nz,curvature of this rank's input range, input order */
+#define CAB_BUF_RSD_INPUT_RANGE 5 /* float2[hi-lo] r_min,r_max of this rank's input range, input order */
+int cab_comm_set_layout(cab_ctx* ctx, int32_t layout);
+/* Shard balance of a group.  The rows are cut by a cost model (sampled cell histogram -> candidates per row); with the
+ * feedback on (default) every step also leaves each rank's measured normals + RSD time with every rank, and the next
+ * step's cuts give a rank that took longer than the mean a smaller share.  Results never depend on the cuts; all ranks
+ * must use the same setting (a step fails with CAB_ERR_STATE if the ranks' cuts disagree).  Setting it resets the
+ * shares to equal. */
+int cab_comm_set_feedback(cab_ctx* ctx, int32_t on);
 /* Replicates a host cloud on every rank of the group: xyz points at the WHOLE cloud (n points, packed xyz) on every rank;
  * a rank uploads rows [n*rank/world, n*(rank+1)/world) over its own PCIe link and copies them into the peers' buffers
  * over NVLink (copy engines), then waits for the other slices.  Without a group: cab_upload_cloud. */
 int cab_comm_upload_cloud(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride);
-/* Results of the last cab_step_normals_rsd of the group for the input-order range [j0, j1) -- any range, on any rank:
+/* Results of the last cab_step_normals_rsd of the group for the input-order range [j0, j1) -- any range, on any rank
+ * (replicated layout), or any range inside [n rank / world, n (rank + 1) / world) (input-range layout):
  * nxyz_curv (j1-j0) x 4, r_min / r_max (j1-j0) floats; any pointer may be NULL.  With j0 = n*rank/world, j1 =
  * n*(rank+1)/world and pointers into ONE host array shared by the ranks, the ranks together leave the channels
  * LocalRadiusEstimation appends (radius_estimation.cpp:204-214) in input order, each paying 1/world of the copy. */

@@ -22,6 +22,8 @@ RSD_SCALE_SORT = 4
 SIG_GRSD21, SIG_GRSD325, SIG_PLUSGRSD110 = 0, 1, 2
 SIG_DIM = {0: 21, 1: 325, 2: 110}
 BUF_POS_SORTED, BUF_NRM_SORTED, BUF_RSD_SORTED, BUF_PERM = 0, 1, 2, 3
+BUF_NRM_INPUT_RANGE, BUF_RSD_INPUT_RANGE = 4, 5
+COMM_LAYOUT_REPLICATED, COMM_LAYOUT_INPUT_RANGES = 0, 1
 
 EXPORTS = [
     "cab_create", "cab_destroy", "cab_last_error", "cab_upload_cloud", "cab_upload_clusters",
@@ -30,6 +32,7 @@ EXPORTS = [
     "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_download_rdif", "cab_profile", "cab_version",
     "cab_step_normals_rsd", "cab_comm_get_id", "cab_comm_init", "cab_comm_init_local", "cab_comm_reserve", "cab_comm_connect",
     "cab_comm_free", "cab_comm_upload_cloud", "cab_comm_download_range", "cab_comm_device_ptr", "cab_comm_allreduce_i32",
+    "cab_comm_set_layout", "cab_comm_set_feedback",
 ]
 COMM_ID_BYTES, COMM_BLOB_BYTES = 128, 512
 
@@ -403,6 +406,12 @@ class Context:
 
     def comm_free(self):
         self._check(self._L.cab_comm_free(self._h), "cab_comm_free")
+
+    def comm_set_feedback(self, on: bool):
+        self._check(self._L.cab_comm_set_feedback(self._h, C.c_int32(1 if on else 0)), "cab_comm_set_feedback")
+
+    def comm_set_layout(self, layout: int):
+        self._check(self._L.cab_comm_set_layout(self._h, C.c_int32(layout)), "cab_comm_set_layout")
 
     def comm_upload_cloud(self, xyz: np.ndarray):
         xyz = np.ascontiguousarray(xyz, dtype=np.float32)

@@ -270,6 +270,8 @@ int cab_create(const cab_config* cfg, cab_ctx** out) {
   }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (cudaMallocHost((void**)&ctx->h_step, kStepBytes) != cudaSuccess) {
     cudaGetLastError();
     g_create_err = "cudaMallocHost failed";
@@ -295,7 +297,7 @@ void cab_destroy(cab_ctx* ctx) {
                     &ctx->b_keys[1], &ctx->b_keys[2], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_vals[2], &ctx->b_thr_flag, &ctx->b_knn_avg, &ctx->b_knn_done, &ctx->b_pfh[0], &ctx->b_pfh[1], &ctx->b_pfh[2], &ctx->b_cluster, &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
                     &ctx->b_cellcnt, &ctx->b_cellstart, &ctx->b_rowpk, &ctx->b_packets, &ctx->b_nrm, &ctx->b_nrm_in,
                     &ctx->b_rsd, &ctx->b_rdif, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
-                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_slab, &ctx->b_sel, &ctx->b_stats2, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
+                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_slab, &ctx->b_sel, &ctx->b_stats2, &ctx->b_sorttmp, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
                     &ctx->g_vvals[1], &ctx->g_cent, &ctx->g_vcount, &ctx->g_vrad, &ctx->g_vlabel, &ctx->g_voff,
                     &ctx->g_layout, &ctx->g_layoff, &ctx->g_vgrid, &ctx->g_hist, &ctx->g_vfirst, &ctx->g_cnrm, &ctx->g_invperm, &ctx->g_sig, &ctx->g_sigdom, &ctx->g_color};
   for (DevBuf* b : bufs)
@@ -306,6 +308,8 @@ void cab_destroy(cab_ctx* ctx) {
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -549,8 +553,14 @@ int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_norm
   int rc = CAB_OK;
   if (exchange) rc = comm_prepare(ctx, ctx->n);  // before the build: the working normals move into the exported buffer
   ctx->want_halo_exchange = exchange && rc == CAB_OK;
+  if (ctx->want_halo_exchange) {
+    comm_range_defaults(ctx, plane_radius);
+    comm_shares(ctx);
+  }
   if (rc == CAB_OK) rc = build_grid(ctx, cell);
   ctx->want_halo_exchange = false;
+  ctx->range_defaults = RangeDefaults{};
+  ctx->shard_cum.clear();
   const bool push = rc == CAB_OK && exchange && ctx->slab;
   const bool halo = push && ctx->slab_info.exchange != 0;  // known since the build's second host round trip
   if (rc == CAB_OK && exchange && !ctx->slab && ctx->n_valid > 0)
@@ -561,8 +571,12 @@ int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_norm
   if (rc == CAB_OK && push) rc = comm_step_before_push(ctx);
   if (halo) {
     // the halo rows' normals travel while the packets that do not read them run
+    // (phase 1 runs on the compute stream; the halo's arrival and the boundary packets of phase 2 follow on the copy
+    // stream, so that the boundary packets fill the SMs the interior kernel's last packets leave idle)
     if (rc == CAB_OK) rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags, 1);
-    if (rc == CAB_OK) rc = comm_halo_receive(ctx);
+    if (rc == CAB_OK && cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0) != cudaSuccess)
+      rc = fail(ctx, CAB_ERR_CUDA, "cudaStreamWaitEvent failed");
+    if (rc == CAB_OK) rc = comm_halo_receive(ctx, ctx->copy_stream);
     if (rc == CAB_OK) rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags, 2);
   } else if (rc == CAB_OK) {
     rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags);
@@ -571,6 +585,7 @@ int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_norm
   if (rc == CAB_OK && push) rc = comm_step_end(ctx, plane_radius);
   if (rc == CAB_OK) rc = cudaEventRecord(ctx->ev[10], st) == cudaSuccess ? CAB_OK : fail(ctx, CAB_ERR_CUDA, "cudaEventRecord failed");
   // one synchronisation per step (also on the error path: nothing may be left running on the caller's buffers)
+  if (rc != CAB_OK) cudaStreamSynchronize(ctx->copy_stream);  // a failed step may have left forked work unjoined
   const cudaError_t e = cudaStreamSynchronize(st);
   if (rc != CAB_OK) return rc;
   if (e != cudaSuccess) return fail(ctx, CAB_ERR_CUDA, "cab_step_normals_rsd: %s", cudaGetErrorString(e));

@@ -17,6 +17,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstring>
 #include <memory>
@@ -119,6 +121,12 @@ struct SyncBlock {
   unsigned cloud[kMaxPeers];            // cloud_seq once rank p's slice of the cloud has arrived
   unsigned normals[kMaxPeers];          // seq once rank p's normals pass is complete and its top layer has been stored into the rank above
   unsigned long long total;             // sum of the ranks' counts of the last step (host reads it back)
+  // measured-time feedback of the shard balance + the consistency check of the cuts: with its completion flag every rank
+  // leaves how long its normals + RSD passes took (device clock, from the end of its build) and how many queries it
+  // answered.  Contiguous: the host reads busy[] and count[] back in one copy.
+  unsigned long long busy[kMaxPeers];
+  unsigned long long count[kMaxPeers];
+  unsigned long long t_begin;           // %globaltimer at the end of this rank's build
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -189,6 +197,23 @@ __global__ void wait_counts_kernel(SlabInfo* __restrict__ info, SyncBlock* __res
     if (failed) info->error = 1;
     mine->total = total;
   }
+}
+
+__global__ void stamp_kernel(SyncBlock* __restrict__ mine) {
+  if (threadIdx.x == 0) mine->t_begin = global_timer_ns();
+}
+
+// after the RSD kernel (whose stores to peer memory are complete at the kernel boundary): completion flag, busy time and
+// query count to every rank
+__global__ void post_done_kernel(PeerSync peers, const SyncBlock* __restrict__ mine, const SlabInfo* __restrict__ info, int rank,
+                                 int world, unsigned seq) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  const unsigned long long busy = global_timer_ns() - mine->t_begin;
+  peers.block[p]->busy[rank] = busy;
+  peers.block[p]->count[rank] = (unsigned long long)(unsigned)(info->q1 - info->q0);
+  __threadfence_system();
+  st_release_sys(&peers.block[p]->done[rank], seq);
 }
 
 // after the RSD kernel (whose stores to peer memory are complete at the kernel boundary): tell every rank
@@ -262,6 +287,16 @@ __global__ void __launch_bounds__(256) fill_defaults_kernel(float4* __restrict__
   }
 }
 
+// input-range layout: the rank's own range is already in input order; only the radii pairs are split for the caller
+__global__ void __launch_bounds__(256) split_radii_kernel(const float2* __restrict__ rsd, int m, float* __restrict__ out_a,
+                                                          float* __restrict__ out_b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float2 v = rsd[i];
+  out_a[i] = v.x;
+  out_b[i] = v.y;
+}
+
 }  // namespace
 
 struct CommState {
@@ -275,6 +310,10 @@ struct CommState {
   bool peer_is_ipc[kMaxPeers] = {};
   unsigned seq = 0, cloud_seq = 0;
   bool armed = false;                 // this step's RSD kernel pushes its results
+  bool feedback = true;               // measured-time correction of the ranks' shares (cab_comm_set_feedback)
+  double share[kMaxPeers];            // the ranks' shares of the modelled cost; the same numbers on every rank
+  int layout = CAB_COMM_LAYOUT_REPLICATED;  // where the concatenated results live (cab_comm_set_layout)
+  int64_t last_n = 0;                 // points of the cloud of the last step
   int64_t last_total = 0;             // entries of the concatenated arrays after the last step
   double last_plane_radius = 0.1;
   DevBuf stage;                       // device staging for the blob all-gather / integer all-reduce
@@ -282,6 +321,15 @@ struct CommState {
 };
 
 namespace {
+
+CommState* new_comm_state(int rank, int world) {
+  CommState* cs = new CommState();
+  cs->rank = rank;
+  cs->world = world;
+  for (int p = 0; p < kMaxPeers; ++p) cs->share[p] = 1.0 / world;
+  if (std::getenv("CAB_NO_FEEDBACK")) cs->feedback = false;  // A/B switch for tuning runs
+  return cs;
+}
 
 int nccl_fail(cab_ctx* ctx, const char* what, int code) {
   NcclApi* api = nccl_api(nullptr);
@@ -435,6 +483,9 @@ void comm_push_targets(const cab_ctx* ctx, PushTargets* out) {
   const CommState* cs = ctx->comm;
   if (!cs || !cs->armed || !cs->connected) return;
   out->world = cs->world;
+  out->layout = cs->layout;
+  out->n = ctx->n;
+  for (int p = 0; p <= cs->world; ++p) out->lo[p] = (int)(ctx->n * p / cs->world);
   for (int p = 0; p < cs->world; ++p) {
     out->nrm[p] = (float4*)cs->peer[p][kBufNrm];
     out->rsd[p] = (float2*)cs->peer[p][kBufRsd];
@@ -470,13 +521,30 @@ int comm_step_begin(cab_ctx* ctx) {  // after the slab build
   if (int rc = comm_prepare(ctx, ctx->n)) return rc;
   cs->seq++;
   cs->armed = true;
+  cs->last_n = ctx->n;
+  stamp_kernel<<<1, 32, 0, ctx->stream>>>((SyncBlock*)cs->own[kBufSync].p);
+  CAB_LAUNCH_CHECK(ctx);
+  if (cs->layout == CAB_COMM_LAYOUT_INPUT_RANGES) return CAB_OK;  // a result's place follows from its input index alone
   post_count_kernel<<<1, kMaxPeers, 0, ctx->stream>>>(slab_info_device(ctx), peer_sync(cs), cs->rank, cs->world, cs->seq);
   CAB_LAUNCH_CHECK(ctx);
   return CAB_OK;
 }
 
+// Input-range layout, before the slab build: where the selection pass leaves the defaults of this rank's non-finite points
+void comm_range_defaults(cab_ctx* ctx, double plane_radius) {
+  ctx->range_defaults = RangeDefaults{};
+  CommState* cs = ctx->comm;
+  if (!cs || cs->world <= 1 || cs->layout != CAB_COMM_LAYOUT_INPUT_RANGES || !cs->connected) return;
+  ctx->range_defaults.nrm = (float4*)cs->own[kBufNrm].p;
+  ctx->range_defaults.rsd = (float2*)cs->own[kBufRsd].p;
+  ctx->range_defaults.lo = (int)(ctx->n * cs->rank / cs->world);
+  ctx->range_defaults.hi = (int)(ctx->n * (cs->rank + 1) / cs->world);
+  ctx->range_defaults.radius = (float)plane_radius;
+}
+
 int comm_step_before_push(cab_ctx* ctx) {  // after the normals pass
   CommState* cs = ctx->comm;
+  if (cs->layout == CAB_COMM_LAYOUT_INPUT_RANGES) return CAB_OK;
   wait_counts_kernel<<<1, kMaxPeers, 0, ctx->stream>>>((SlabInfo*)slab_info_device(ctx), (SyncBlock*)cs->own[kBufSync].p, cs->rank,
                                                      cs->world, cs->seq, cs->timeout_ns);
   CAB_LAUNCH_CHECK(ctx);
@@ -496,9 +564,8 @@ int comm_halo_send(cab_ctx* ctx) {  // after the normals pass
   return CAB_OK;
 }
 
-int comm_halo_receive(cab_ctx* ctx) {  // before the boundary packets of the RSD pass
+int comm_halo_receive(cab_ctx* ctx, cudaStream_t st) {  // before the boundary packets of the RSD pass
   CommState* cs = ctx->comm;
-  cudaStream_t st = ctx->stream;
   SlabInfo* info = (SlabInfo*)slab_info_device(ctx);
   SyncBlock* mine = (SyncBlock*)cs->own[kBufSync].p;
   if (cs->rank + 1 < cs->world) {  // the rank above has finished its normals: fetch its bottom layer
@@ -518,23 +585,78 @@ int comm_step_end(cab_ctx* ctx, double plane_radius) {  // after the RSD kernel
   CommState* cs = ctx->comm;
   cs->armed = false;
   cs->last_plane_radius = plane_radius;
-  post_flag_kernel<<<1, kMaxPeers, 0, ctx->stream>>>(peer_sync(cs), cs->rank, cs->world, cs->seq, 0);
+  SyncBlock* mine = (SyncBlock*)cs->own[kBufSync].p;
+  post_done_kernel<<<1, kMaxPeers, 0, ctx->stream>>>(peer_sync(cs), mine, slab_info_device(ctx), cs->rank, cs->world, cs->seq);
   CAB_LAUNCH_CHECK(ctx);
-  wait_flag_kernel<<<1, kMaxPeers, 0, ctx->stream>>>((SlabInfo*)slab_info_device(ctx), nullptr, (SyncBlock*)cs->own[kBufSync].p,
-                                                   cs->world, cs->seq, 0, cs->timeout_ns);
+  wait_flag_kernel<<<1, kMaxPeers, 0, ctx->stream>>>((SlabInfo*)slab_info_device(ctx), nullptr, mine, cs->world, cs->seq, 0,
+                                                   cs->timeout_ns);
   CAB_LAUNCH_CHECK(ctx);
-  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepComm, &((SyncBlock*)cs->own[kBufSync].p)->total, 8, cudaMemcpyDeviceToHost,
-                                ctx->stream));
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepComm + 64, mine->busy, 2 * kMaxPeers * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  if (cs->layout == CAB_COMM_LAYOUT_REPLICATED)
+    CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepComm, &((SyncBlock*)cs->own[kBufSync].p)->total, 8, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
   return CAB_OK;
 }
 
 int comm_step_finish(cab_ctx* ctx) {  // after the step's synchronisation
   CommState* cs = ctx->comm;
-  unsigned long long total;
-  std::memcpy(&total, ctx->h_step + kStepComm, 8);
-  cs->last_total = (int64_t)total;
+  if (cs->layout == CAB_COMM_LAYOUT_REPLICATED) {
+    unsigned long long total;
+    std::memcpy(&total, ctx->h_step + kStepComm, 8);
+    cs->last_total = (int64_t)total;
+  } else {
+    cs->last_total = ctx->n * (cs->rank + 1) / cs->world - ctx->n * cs->rank / cs->world;
+  }
   if (ctx->slab_info.error) return fail(ctx, CAB_ERR_STATE, "cab_comm: a peer did not answer within %.1f s", cs->timeout_ns * 1e-9);
+  unsigned long long fb[2 * kMaxPeers];
+  std::memcpy(fb, ctx->h_step + kStepComm + 64, sizeof(fb));
+  const unsigned long long* busy = fb;
+  const unsigned long long* count = fb + kMaxPeers;
+  // every finite point is exactly one rank's query -- unless the ranks cut the rows differently
+  unsigned long long answered = 0;
+  for (int p = 0; p < cs->world; ++p) answered += count[p];
+  const unsigned long long finite = ctx->dom_count.empty() ? 0ull : (unsigned long long)ctx->dom_count[0];
+  if (answered != finite)
+    return fail(ctx, CAB_ERR_STATE, "cab_comm: the ranks answered %llu queries of %llu finite points -- they did not cut the "
+                                    "rows alike (different cab_comm_set_feedback / clouds / parameters on the ranks?)",
+                answered, finite);
+  if (cs->feedback) {
+    // measured-time feedback: a rank that took longer than the mean gets a smaller share of the modelled cost next
+    // time.  Every rank reads the same numbers and does the same arithmetic, so the cuts stay consistent.
+    double mean = 0;
+    bool ok = true;
+    for (int p = 0; p < cs->world; ++p) {
+      mean += (double)busy[p];
+      ok = ok && busy[p] > 0 && busy[p] < (1ull << 40);
+    }
+    mean /= cs->world;
+    if (ok && mean > 0) {
+      double sum = 0;
+      for (int p = 0; p < cs->world; ++p) {
+        double s = cs->share[p] * std::pow(mean / (double)busy[p], 0.75);
+        s = std::min(std::max(s, 0.25 / cs->world), 4.0 / cs->world);
+        cs->share[p] = s;
+        sum += s;
+      }
+      for (int p = 0; p < cs->world; ++p) cs->share[p] /= sum;
+    }
+  }
   return CAB_OK;
+}
+
+// before the slab build: the ranks' shares of the modelled cost
+void comm_shares(cab_ctx* ctx) {
+  ctx->shard_cum.clear();
+  CommState* cs = ctx->comm;
+  if (!cs || cs->world <= 1 || !cs->feedback) return;
+  ctx->shard_cum.assign((size_t)cs->world + 1, 0.0);
+  double acc = 0;
+  for (int p = 0; p < cs->world; ++p) {
+    acc += cs->share[p];
+    ctx->shard_cum[(size_t)p + 1] = acc;
+  }
+  ctx->shard_cum[(size_t)cs->world] = 1.0;
 }
 
 }  // namespace cab
@@ -567,9 +689,7 @@ int cab_comm_init(cab_ctx* ctx, const char id[CAB_COMM_ID_BYTES], int32_t rank, 
   void* comm = nullptr;
   int e = api->CommInitRank(&comm, world, uid, rank);
   if (e) return nccl_fail(ctx, "ncclCommInitRank", e);
-  ctx->comm = new CommState();
-  ctx->comm->rank = rank;
-  ctx->comm->world = world;
+  ctx->comm = new_comm_state(rank, world);
   ctx->comm->nccl = comm;
   return cab_set_shard(ctx, rank, world);
 }
@@ -583,9 +703,7 @@ int cab_comm_init_local(cab_ctx** ctxs, int32_t world) {
     if (!ctx) return CAB_ERR_ARG;
     cudaSetDevice(ctx->device);
     comm_free(ctx);
-    ctx->comm = new CommState();
-    ctx->comm->rank = r;
-    ctx->comm->world = world;
+    ctx->comm = new_comm_state(r, world);
     ctx->comm->local = group;
     if (int rc = cab_set_shard(ctx, r, world)) return rc;
   }
@@ -597,9 +715,10 @@ int cab_comm_reserve(cab_ctx* ctx, int32_t rank, int32_t world, int64_t max_poin
   if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
     return fail(ctx, CAB_ERR_ARG, "cab_comm_reserve: bad rank %d / world %d (at most %d ranks)", rank, world, kMaxPeers);
   CAB_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (!ctx->comm) ctx->comm = new CommState();
-  ctx->comm->rank = rank;
-  ctx->comm->world = world;
+  if (!ctx->comm || ctx->comm->world != world || ctx->comm->rank != rank) {
+    comm_free(ctx);
+    ctx->comm = new_comm_state(rank, world);
+  }
   if (int rc = cab_set_shard(ctx, rank, world)) return rc;
   std::memset(blob, 0, CAB_COMM_BLOB_BYTES);
   return make_blob(ctx, max_points, (CommBlob*)blob);
@@ -613,6 +732,24 @@ int cab_comm_connect(cab_ctx* ctx, const void* blobs) {
   for (int p = 0; p < ctx->comm->world; ++p)
     std::memcpy(&all[p], (const char*)blobs + (size_t)p * CAB_COMM_BLOB_BYTES, sizeof(CommBlob));
   return connect_blobs(ctx, all.data());
+}
+
+int cab_comm_set_layout(cab_ctx* ctx, int32_t layout) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (layout != CAB_COMM_LAYOUT_REPLICATED && layout != CAB_COMM_LAYOUT_INPUT_RANGES)
+    return fail(ctx, CAB_ERR_ARG, "cab_comm_set_layout: unknown layout %d", layout);
+  if (!ctx->comm) return fail(ctx, CAB_ERR_STATE, "cab_comm_set_layout: this context belongs to no group");
+  ctx->comm->layout = layout;
+  ctx->comm->last_total = 0;
+  return CAB_OK;
+}
+
+int cab_comm_set_feedback(cab_ctx* ctx, int32_t on) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (!ctx->comm) return fail(ctx, CAB_ERR_STATE, "cab_comm_set_feedback: this context belongs to no group");
+  ctx->comm->feedback = on != 0;
+  for (int p = 0; p < kMaxPeers; ++p) ctx->comm->share[p] = 1.0 / ctx->comm->world;
+  return CAB_OK;
 }
 
 int cab_comm_free(cab_ctx* ctx) {
@@ -671,6 +808,50 @@ int cab_comm_download_range(cab_ctx* ctx, int64_t j0, int64_t j1, float* nxyz_cu
   const int m = (int)(j1 - j0);
   if (m == 0 || (!nxyz_curv && !r_min)) return CAB_OK;
   cudaStream_t st = ctx->stream;
+  if (cs->layout == CAB_COMM_LAYOUT_INPUT_RANGES) {
+    const int64_t lo = ctx->n * cs->rank / cs->world, hi = ctx->n * (cs->rank + 1) / cs->world;
+    if (j0 < lo || j1 > hi)
+      return fail(ctx, CAB_ERR_ARG, "cab_comm_download_range: [%lld, %lld) is not inside this rank's input range [%lld, %lld) "
+                                    "(input-range layout)", (long long)j0, (long long)j1, (long long)lo, (long long)hi);
+    if (cs->last_n != ctx->n) return fail(ctx, CAB_ERR_STATE, "cab_comm_download_range: no exchanged step has run on this cloud");
+    const float4* nrm = (const float4*)cs->own[kBufNrm].p + (j0 - lo);
+    const float2* rsd = (const float2*)cs->own[kBufRsd].p + (j0 - lo);
+    CAB_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+    if (!ctx->slab) {  // no finite point anywhere: nothing was selected, nothing pushed
+      if (nxyz_curv)
+        if (int rc = reserve(ctx, ctx->b_out4, (size_t)m * sizeof(float4))) return rc;
+      if (r_min) {
+        if (int rc = reserve(ctx, ctx->b_out1a, (size_t)m * sizeof(float))) return rc;
+        if (int rc = reserve(ctx, ctx->b_out1b, (size_t)m * sizeof(float))) return rc;
+      }
+      fill_defaults_kernel<<<(m + 255) / 256, 256, 0, st>>>(nxyz_curv ? (float4*)ctx->b_out4.p : nullptr,
+                                                            r_min ? (float*)ctx->b_out1a.p : nullptr,
+                                                            r_min ? (float*)ctx->b_out1b.p : nullptr, m, (float)cs->last_plane_radius);
+      CAB_LAUNCH_CHECK(ctx);
+      if (nxyz_curv) CAB_CUDA(ctx, cudaMemcpyAsync(nxyz_curv, ctx->b_out4.p, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, st));
+      if (r_min) {
+        CAB_CUDA(ctx, cudaMemcpyAsync(r_min, ctx->b_out1a.p, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CAB_CUDA(ctx, cudaMemcpyAsync(r_max, ctx->b_out1b.p, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, st));
+      }
+    } else {
+      // the normals leave as they are; the radii pairs are split while the normals travel
+      if (r_min) {
+        if (int rc = reserve(ctx, ctx->b_out1a, (size_t)m * sizeof(float))) return rc;
+        if (int rc = reserve(ctx, ctx->b_out1b, (size_t)m * sizeof(float))) return rc;
+        split_radii_kernel<<<(m + 255) / 256, 256, 0, st>>>(rsd, m, (float*)ctx->b_out1a.p, (float*)ctx->b_out1b.p);
+        CAB_LAUNCH_CHECK(ctx);
+      }
+      if (nxyz_curv) CAB_CUDA(ctx, cudaMemcpyAsync(nxyz_curv, nrm, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, st));
+      if (r_min) {
+        CAB_CUDA(ctx, cudaMemcpyAsync(r_min, ctx->b_out1a.p, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CAB_CUDA(ctx, cudaMemcpyAsync(r_max, ctx->b_out1b.p, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, st));
+      }
+    }
+    CAB_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+    CAB_CUDA(ctx, cudaStreamSynchronize(st));
+    CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.d2h_ms, ctx->ev[6], ctx->ev[7]));
+    return CAB_OK;
+  }
   if (nxyz_curv)
     if (int rc = reserve(ctx, ctx->b_out4, (size_t)m * sizeof(float4))) return rc;
   if (r_min) {
@@ -705,10 +886,13 @@ int cab_comm_download_range(cab_ctx* ctx, int64_t j0, int64_t j1, float* nxyz_cu
 void* cab_comm_device_ptr(cab_ctx* ctx, int32_t which, int64_t* count) {
   if (!ctx || !ctx->comm || !ctx->comm->connected) return nullptr;
   if (count) *count = ctx->comm->last_total;
+  const bool ranges = ctx->comm->layout == CAB_COMM_LAYOUT_INPUT_RANGES;
   switch (which) {
-    case CAB_BUF_NRM_SORTED: return ctx->comm->own[kBufNrm].p;
-    case CAB_BUF_RSD_SORTED: return ctx->comm->own[kBufRsd].p;
-    case CAB_BUF_PERM: return ctx->comm->own[kBufPerm].p;
+    case CAB_BUF_NRM_SORTED: return ranges ? nullptr : ctx->comm->own[kBufNrm].p;
+    case CAB_BUF_RSD_SORTED: return ranges ? nullptr : ctx->comm->own[kBufRsd].p;
+    case CAB_BUF_PERM: return ranges ? nullptr : ctx->comm->own[kBufPerm].p;
+    case CAB_BUF_NRM_INPUT_RANGE: return ranges ? ctx->comm->own[kBufNrm].p : nullptr;
+    case CAB_BUF_RSD_INPUT_RANGE: return ranges ? ctx->comm->own[kBufRsd].p : nullptr;
     default: return nullptr;
   }
 }

@@ -397,9 +397,13 @@ __device__ __forceinline__ int cut_at(const long long* __restrict__ cum, int n_i
 // either side; the first and last rank have one halo).  One block, one warp per cut; a few fixed-point rounds move the
 // cuts until own cost + halo_permille/1000 * halo cost is the same for every rank.  Leaves the rank's row ranges in
 // `info` and turns domains[0] into the slab's table geometry.
+struct SplitShares {
+  double cum[65];  // cumulative share of the total cost the ranks before rank c get; cum[0] = 0, cum[world] = 1
+};
 __global__ void __launch_bounds__(1024) slab_split_kernel(const long long* __restrict__ cum, int world, int rank,
-                                                          int halo_permille, int want_exchange, Domain* __restrict__ domains,
-                                                          int* __restrict__ cuts, SlabInfo* __restrict__ info) {
+                                                          int halo_permille, int want_exchange, const SplitShares sh,
+                                                          Domain* __restrict__ domains, int* __restrict__ cuts,
+                                                          SlabInfo* __restrict__ info) {
   __shared__ int s[65];
   __shared__ long long halo[64];
   __shared__ long long target[65];
@@ -412,26 +416,28 @@ __global__ void __launch_bounds__(1024) slab_split_kernel(const long long* __res
     s[world] = n_rows;
   }
   for (int c = 1 + warp; c < world; c += n_warps) {  // one warp per cut
-    const int v = cut_at(cum, n_rows, total / world * c, lane);
+    const int v = cut_at(cum, n_rows, (long long)((double)total * sh.cum[c]), lane);
     if (lane == 0) s[c] = v;
   }
   __syncthreads();
-  for (int round = 0; round < 4; ++round) {
+  // exchanged halos cost (almost) nothing: the first cuts stand
+  for (int round = 0; round < (want_exchange ? 0 : 4); ++round) {
     if (g < world) {
       long long h = 0;
       const int a = s[g], b = s[g + 1];
       if (g > 0) h += cum_before(cum, a) - cum_before(cum, max(a - layer, 0));
       if (g < world - 1) h += cum_before(cum, min(b + layer, n_rows)) - cum_before(cum, b);
-      halo[g] = want_exchange ? 0 : h * halo_permille / 1000;  // exchanged halos cost (almost) nothing
+      halo[g] = h * halo_permille / 1000;
     }
     __syncthreads();
     if (g == 0) {
       long long sum = total;
       for (int j = 0; j < world; ++j) sum += halo[j];
-      const long long each = sum / world, floor_own = total / (8 * (long long)world) + 1;
+      const long long floor_own = total / (8 * (long long)world) + 1;
       double acc = 0;
       target[0] = 0;
       for (int j = 0; j < world; ++j) {
+        const long long each = (long long)((double)sum * (sh.cum[j + 1] - sh.cum[j]));
         const long long own = each - halo[j] > floor_own ? each - halo[j] : floor_own;
         acc += (double)own;
         target[j + 1] = (long long)acc;
@@ -501,7 +507,8 @@ __device__ __forceinline__ bool in_window(const Domain& dm, float inv_cell, floa
 template <bool kVec>
 __global__ void __launch_bounds__(256) slab_select_kernel(const float* __restrict__ xyz, int stride, int n,
                                                           const Domain* __restrict__ domains, float inv_cell,
-                                                          SelPoint* __restrict__ stage, int* __restrict__ counts) {
+                                                          SelPoint* __restrict__ stage, int* __restrict__ counts,
+                                                          const RangeDefaults rd) {
   __shared__ int warp_sum[8];
   const Domain dm = domains[0];
   const int base = blockIdx.x * kSelChunk + threadIdx.x * 8;  // this thread's 8 consecutive points
@@ -530,6 +537,19 @@ __global__ void __launch_bounds__(256) slab_select_kernel(const float* __restric
         py[k] = p[1];
         pz[k] = p[2];
         keep |= in_window(dm, inv_cell, px[k], py[k], pz[k]) ? 1u << k : 0u;
+      }
+    }
+  }
+  if (rd.nrm && base < rd.hi && base + 8 > rd.lo) {
+    // input-range layout of a group: this rank owns the results of input indices [lo, hi); the points among them that are
+    // nobody's query get the single-GPU path's values here (nobody else ever writes those entries)
+    const float nan = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = base + k;
+      if (j < n && j >= rd.lo && j < rd.hi && !finite3(px[k], py[k], pz[k])) {
+        rd.nrm[j - rd.lo] = make_float4(nan, nan, nan, nan);
+        rd.rsd[j - rd.lo] = make_float2(rd.radius, rd.radius);
       }
     }
   }
@@ -941,15 +961,18 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
     row_cost_kernel<<<blocks, kCostRows * 32, 0, st>>>(d_dom, (const int*)ctx->b_cellcnt.p, sample, rowcost);
     CAB_LAUNCH_CHECK(ctx);
     CAB_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->b_cubtmp.p, tmp_cost, rowcost, cum, (int)rows, st));
+    SplitShares sh{};
+    for (int c = 0; c <= w; ++c)
+      sh.cum[c] = (int)ctx->shard_cum.size() == w + 1 ? ctx->shard_cum[(size_t)c] : (double)c / (double)w;
     slab_split_kernel<<<1, 32 * std::min(32, std::max(2, w)), 0, st>>>(cum, w, ctx->shard_rank, ctx->halo_permille,
-                                                                       ctx->want_halo_exchange ? 1 : 0, d_dom, cuts, info);
+                                                                       ctx->want_halo_exchange ? 1 : 0, sh, d_dom, cuts, info);
     CAB_LAUNCH_CHECK(ctx);
     // stable selection of the window's points: per-block compaction, then a scan of the blocks' counts
     CAB_CUDA(ctx, cudaMemsetAsync(sel_cnt + sel_blocks, 0, 4, st));
     if (vector_layout(ctx))
-      slab_select_kernel<true><<<sel_blocks, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, d_dom, ctx->inv_cell, (SelPoint*)ctx->b_sel.p, sel_cnt);
+      slab_select_kernel<true><<<sel_blocks, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, d_dom, ctx->inv_cell, (SelPoint*)ctx->b_sel.p, sel_cnt, ctx->range_defaults);
     else
-      slab_select_kernel<false><<<sel_blocks, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, d_dom, ctx->inv_cell, (SelPoint*)ctx->b_sel.p, sel_cnt);
+      slab_select_kernel<false><<<sel_blocks, 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, d_dom, ctx->inv_cell, (SelPoint*)ctx->b_sel.p, sel_cnt, ctx->range_defaults);
     CAB_LAUNCH_CHECK(ctx);
     CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_selscan, sel_cnt, sel_off, sel_blocks + 1, st));
     slab_count_kernel<<<1, 32, 0, st>>>(sel_off, sel_blocks, info);
@@ -981,10 +1004,11 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
                                     (const int*)nullptr, (int*)nullptr, m, 0, end_bit, st);
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (const int*)nullptr, (int*)nullptr, (int)ncell1, st);
-  size_t tmp_bytes = std::max(tmp_sort, tmp_scan);
+  size_t tmp_bytes = tmp_scan;
   const size_t mm = (size_t)std::max(m, 1);
   const size_t max_packets = std::min<size_t>(mm, mm / kWarp + (size_t)lcells + 1);
   if (int rc = reserve(ctx, ctx->b_cubtmp, tmp_bytes + 16)) return rc;
+  if (int rc = reserve(ctx, ctx->b_sorttmp, tmp_sort + 16)) return rc;  // the sort runs beside the scans: its own scratch
   if (int rc = reserve(ctx, ctx->b_keys[0], mm * 8)) return rc;
   if (int rc = reserve(ctx, ctx->b_keys[1], mm * 8)) return rc;
   if (int rc = reserve(ctx, ctx->b_keys[2], mm * sizeof(SelPoint))) return rc;
@@ -1011,6 +1035,26 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
                                                                      (int*)ctx->b_vals[0].p, cellcnt, (SelPoint*)ctx->b_keys[2].p);
     CAB_LAUNCH_CHECK(ctx);
   }
+  // ---- radix sort of the window by (row, fine x), on the copy stream: the four latency-bound passes over a few million
+  // keys run beside the cell table, segment and packet kernels below, which need the cell histogram only
+  cudaStream_t ss = ctx->copy_stream;
+  if (m > 0) {
+    CAB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    CAB_CUDA(ctx, cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
+    if (key32)
+      CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sorttmp.p, tmp_sort, (const unsigned*)ctx->b_keys[0].p,
+                                                    (unsigned*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
+                                                    (int*)ctx->b_vals[1].p, m, 0, end_bit, ss));
+    else
+      CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sorttmp.p, tmp_sort, (const unsigned long long*)ctx->b_keys[0].p,
+                                                    (unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
+                                                    (int*)ctx->b_vals[1].p, m, 0, end_bit, ss));
+    ctx->tm.kernel_launches += 1 + (end_bit + 7) / 8;
+    slab_place_kernel<<<(m + 255) / 256, 256, 0, ss>>>((const SelPoint*)ctx->b_keys[2].p, (const int*)ctx->b_vals[1].p, m,
+                                                      (float4*)ctx->b_pos.p, (int*)ctx->b_perm.p);
+    CAB_LAUNCH_CHECK(ctx);
+    CAB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ss));
+  }
   CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp_bytes, (const int*)cellcnt, (int*)ctx->b_cellstart.p,
                                               (int)ncell1, st));
   segment_kernel<<<(unsigned)((ncell1 + 255) / 256), 256, 0, st>>>(d_dom, 1, lcells, (const int*)ctx->b_cellstart.p, segpk, seglen);
@@ -1022,21 +1066,7 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
   CAB_LAUNCH_CHECK(ctx);
   slab_ranges_kernel<<<1, 32, 0, st>>>(d_dom, (const int*)ctx->b_cellstart.p, packet_base, info);
   CAB_LAUNCH_CHECK(ctx);
-  // ---- radix sort of the window by (row, fine x) --------------------------------------------------------------
-  if (m > 0) {
-    if (key32)
-      CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_sort, (const unsigned*)ctx->b_keys[0].p,
-                                                    (unsigned*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
-                                                    (int*)ctx->b_vals[1].p, m, 0, end_bit, st));
-    else
-      CAB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_cubtmp.p, tmp_sort, (const unsigned long long*)ctx->b_keys[0].p,
-                                                    (unsigned long long*)ctx->b_keys[1].p, (const int*)ctx->b_vals[0].p,
-                                                    (int*)ctx->b_vals[1].p, m, 0, end_bit, st));
-    ctx->tm.kernel_launches += 1 + (end_bit + 7) / 8;
-    slab_place_kernel<<<(m + 255) / 256, 256, 0, st>>>((const SelPoint*)ctx->b_keys[2].p, (const int*)ctx->b_vals[1].p, m,
-                                                      (float4*)ctx->b_pos.p, (int*)ctx->b_perm.p);
-    CAB_LAUNCH_CHECK(ctx);
-  }
+  if (m > 0) CAB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));  // the sorted window joins the tables
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
   CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepSlab, info, sizeof(SlabInfo), cudaMemcpyDeviceToHost, st));
   ctx->slab = true;

@@ -124,10 +124,22 @@ struct DevBuf {
 // valid on this rank (own memory, a peer device of the same process, or CUDA IPC mappings of the other processes).
 constexpr int kMaxPeers = 16;
 struct PushTargets {
-  int world;  // 0: no exchange
+  int world;   // 0: no exchange
+  int layout;  // CAB_COMM_LAYOUT_*: replicated sorted-order arrays on every rank, or input-order ranges (one owner per point)
+  long long n; // points of the cloud (input-range layout: rank p owns input indices [lo[p], lo[p + 1]))
+  int lo[kMaxPeers + 1];
   float4* nrm[kMaxPeers];
   float2* rsd[kMaxPeers];
   int* perm[kMaxPeers];
+};
+
+// Input-range layout: what the slab selection writes for the points of this rank's input range that are nobody's query
+// (non-finite coordinates): the values the single-GPU path gives them.
+struct RangeDefaults {
+  float4* nrm = nullptr;
+  float2* rsd = nullptr;
+  int lo = 0, hi = 0;
+  float radius = 0.f;
 };
 
 struct SvmState;   // cab_svm.cu
@@ -143,6 +155,7 @@ struct cab_ctx {
   cudaStream_t copy_stream = nullptr;  // device->host copies that overlap the next kernel (cab_normals_rsd)
   cudaEvent_t ev[12]{};
   cudaEvent_t ev_ready = nullptr;      // results staged for the copy stream
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // work forked onto copy_stream inside a step and joined again
   std::string err;
   cab_timings tm{};
 
@@ -171,11 +184,14 @@ struct cab_ctx {
   int halo_permille = 470;         // share of the normals pass in a packet's cost (shard balance)
   bool want_halo_exchange = false; // set by cab_step_normals_rsd of a group: build_slab may choose the exchange mode
   bool defer_sync = false;         // run_normals / run_rsd leave the stream running (cab_step_*: one sync per step)
+  std::vector<double> shard_cum;   // empty: equal shares; else world + 1 cumulative shares of the modelled cost (0 ... 1), the
+                                   // group's measured-time feedback (cab_comm.cu) -- identical on every rank by construction
+  cab::RangeDefaults range_defaults{};  // set by cab_step_normals_rsd of a group in the input-range layout (slab selection)
 
   // device arena (grow-only)
   cab::DevBuf b_xyz, b_domoff, b_domid, b_bounds, b_domains, b_keys[3], b_vals[3], b_cubtmp, b_pos,
       b_perm, b_cellcnt, b_cellstart, b_rowpk, b_packets, b_nrm, b_nrm_in, b_rsd, b_rdif, b_kcount, b_stats,
-      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost, b_slab, b_sel, b_stats2, b_thr_flag, b_knn_avg, b_knn_done, b_pfh[3], b_cluster;
+      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost, b_slab, b_sel, b_stats2, b_sorttmp, b_thr_flag, b_knn_avg, b_knn_done, b_pfh[3], b_cluster;
   // pinned staging
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;
@@ -247,9 +263,11 @@ bool comm_active(const cab_ctx* ctx);                          // the context be
 int comm_step_begin(cab_ctx* ctx);                             // after the slab build: publish this rank's query count
 int comm_step_before_push(cab_ctx* ctx);                       // before the RSD kernel: place the slice in the concatenation
 int comm_halo_send(cab_ctx* ctx);                              // after the normals pass: top layer to the rank above, "normals done" to all
-int comm_halo_receive(cab_ctx* ctx);                           // before the boundary packets: fetch the layer above, wait for the layer below
+int comm_halo_receive(cab_ctx* ctx, cudaStream_t st);          // before the boundary packets: fetch the layer above, wait for the layer below
 int comm_step_end(cab_ctx* ctx, double plane_radius);          // after the RSD kernel: completion flags
 int comm_step_finish(cab_ctx* ctx);                            // after the step's synchronisation
+void comm_shares(cab_ctx* ctx);                                // before the slab build: the ranks' shares (measured-time feedback) -> ctx->shard_cum
+void comm_range_defaults(cab_ctx* ctx, double plane_radius);   // input-range layout: arms ctx->range_defaults for the slab selection
 void comm_push_targets(const cab_ctx* ctx, PushTargets* out);  // world = 0 unless a result exchange is armed for this step
 
 }  // namespace cab

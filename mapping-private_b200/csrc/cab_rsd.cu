@@ -60,6 +60,7 @@ struct RsdArgs {
   float bin_scale;         // ndiv / radius
   double radius, plane_radius;
   unsigned long long* stats;
+  int work_slot;           // which packet work counter this launch pulls from (next_packet)
 };
 
 // angle between the two lines, radius_estimation.cpp:158-161
@@ -94,13 +95,24 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
   return y;
 }
 
-// Result exchange fused into the kernel: the packet's normals, radii and input indices go straight into every rank's
-// copy of the concatenated (sorted-order) result arrays -- 32 consecutive entries per store, over NVLink for the peers.
+// Result exchange fused into the kernel.  Replicated layout: the packet's normals, radii and input indices go straight
+// into every rank's copy of the concatenated (sorted-order) result arrays -- 32 consecutive entries per store, over NVLink
+// for the peers.  Input-range layout: every point's results go to ONE rank, the owner of its input index, already in
+// input order (1/world of the traffic, no permutation left to undo).
 __device__ __forceinline__ void push_results(const PushTargets& push, const SlabInfo* slab, const GridView& g,
                                              const PacketCtx& pc, const float4& nq, const float2 radii) {
   if (push.world <= 0 || !pc.active) return;
-  const int gpos = slab->gbase + (pc.qi - slab->q0);
   const int input_index = g.perm[pc.qi];
+  if (push.layout == CAB_COMM_LAYOUT_INPUT_RANGES) {
+    // one owner per point: the rank whose input range holds it gets the results at the point's place in that range
+    int p = (int)(((long long)input_index * push.world) / push.n);
+    if (input_index >= push.lo[p + 1]) ++p;
+    const int o = input_index - push.lo[p];
+    push.nrm[p][o] = nq;
+    push.rsd[p][o] = radii;
+    return;
+  }
+  const int gpos = slab->gbase + (pc.qi - slab->q0);
   for (int p = 0; p < push.world; ++p) {
     push.nrm[p][gpos] = nq;
     push.rsd[p][gpos] = radii;
@@ -129,7 +141,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
   const int p0 = a.range ? a.range[0] : a.p0, n1 = (a.range ? a.range[1] : a.p1) - p0;
   const int pb = a.range_b ? a.range_b[0] : 0, n2 = a.range_b ? a.range_b[1] - pb : 0;
   for (;;) {
-    const int w = next_packet(a.stats, lane);
+    const int w = next_packet(a.stats, lane, a.work_slot);
     if (w >= n1 + n2) break;
     const int pid = w < n1 ? p0 + w : pb + (w - n1);
     if (a.only && !a.only[pid - a.p0]) continue;
@@ -428,7 +440,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
   const int p0 = a.range ? a.range[0] : a.p0, n1 = (a.range ? a.range[1] : a.p1) - p0;
   const int pb = a.range_b ? a.range_b[0] : 0, n2 = a.range_b ? a.range_b[1] - pb : 0;
   for (;;) {
-    const int w = next_packet(a.stats, lane);
+    const int w = next_packet(a.stats, lane, a.work_slot);
     if (w >= n1 + n2) break;
     const int pid = w < n1 ? p0 + w : pb + (w - n1);
     if (kTrunc && a.skip && a.skip[pid - a.p0]) continue;  // left to the exact-threshold path
@@ -657,12 +669,12 @@ float bin_threshold(int b, int ndiv, double radius, float r2) {
 }
 
 template <bool kExact, bool kUseThr>
-int launch_rsd(cab_ctx* ctx, const RsdArgs& a, unsigned blocks, size_t smem) {
+int launch_rsd(cab_ctx* ctx, const RsdArgs& a, unsigned blocks, size_t smem, cudaStream_t ks) {
   CAB_CUDA(ctx, cudaFuncSetAttribute(rsd_kernel<kExact, kUseThr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   CAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rsd_kernel<kExact, kUseThr>, kWarpsPerBlock * kWarp, smem));
   blocks = std::min<unsigned>(blocks, (unsigned)std::max(per_sm, 1) * ctx->sm_count);  // persistent warps
-  rsd_kernel<kExact, kUseThr><<<blocks, kWarpsPerBlock * kWarp, smem, ctx->stream>>>(a);
+  rsd_kernel<kExact, kUseThr><<<blocks, kWarpsPerBlock * kWarp, smem, ks>>>(a);
   CAB_LAUNCH_CHECK(ctx);
   return CAB_OK;
 }
@@ -677,7 +689,11 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
     return fail(ctx, CAB_ERR_ARG, "cab_rsd: radius %g exceeds the grid cell %g", r, (double)ctx->cell);
   if (ndiv < 1 || ndiv > kMaxDiv) return fail(ctx, CAB_ERR_ARG, "cab_rsd: distance_div must be in [1, %d]", kMaxDiv);
   const int n = (int)ctx->n;
+  // phase 2 (the boundary packets of a split pass) is launched on the copy stream with its own work counter: it runs
+  // beside the tail of phase 1 instead of after it
   cudaStream_t st = ctx->stream;
+  cudaStream_t ks = phase == 2 ? ctx->copy_stream : ctx->stream;
+  const int slot = phase == 2 ? 1 : 0;
   if (int rc = reserve(ctx, ctx->b_rsd, (size_t)std::max(n, 1) * sizeof(float2))) return rc;
   if (int rc = reserve(ctx, ctx->b_rdif, (size_t)std::max(n, 1) * sizeof(float))) return rc;
   if (int rc = reserve(ctx, ctx->b_stats, kStatBytes)) return rc;
@@ -686,8 +702,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   // fast mode with max_nn: one histogram traversal, then the RSD traversal settles the truncation itself
   const bool trunc_fast = use_thr && !ctx->cfg.exact && !legacy;
   if (phase == 2) {
-    // second launch of a split pass: only the work counter starts over, everything else was set up by phase 1
-    CAB_CUDA(ctx, cudaMemsetAsync((unsigned long long*)ctx->b_stats.p + 2 * kStatSlots, 0, 8, st));
+    // second launch of a split pass: everything was set up by phase 1 (both work counters included)
   } else if (trunc_fast) {
     if (int rc = run_nn_hist(ctx, rf, max_nn)) return rc;
   } else if (use_thr) {
@@ -706,6 +721,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
     CAB_CUDA(ctx, cudaMemcpyAsync(ctx->b_stats2.p, ctx->h_step + kStepThr, sizeof(float) * (ndiv + 1), cudaMemcpyHostToDevice, st));
     CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, kStatBytes, st));
     CAB_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+    if (phase == 1) CAB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));  // phase 2 may start once the prologue is in place
   }
   RsdArgs a{};
   a.g = grid_view(ctx);
@@ -733,6 +749,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   a.radius = r;
   a.plane_radius = plane_radius;
   a.stats = (unsigned long long*)ctx->b_stats.p;
+  a.work_slot = slot;
   const size_t smem = (size_t)kWarpsPerBlock * sizeof(ChunkTile) + (size_t)kWarpsPerBlock * ndiv * kWarp * sizeof(float2) +
                       (size_t)((ndiv + 4) & ~3) * sizeof(float) + (size_t)kWarpsPerBlock * kWarp * sizeof(int);
   const int np = a.range ? std::max(1, (int)std::min<int64_t>(ctx->n_sorted, INT_MAX)) : a.p1 - a.p0;
@@ -756,20 +773,24 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
       int per_sm = 1;
       CAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * kWarp, fsmem));
       const unsigned grid = std::min<unsigned>(blocks, (unsigned)std::max(per_sm, 1) * ctx->sm_count);
-      kernel<<<grid, kWarpsPerBlock * kWarp, fsmem, ctx->stream>>>(a);
+      kernel<<<grid, kWarpsPerBlock * kWarp, fsmem, ks>>>(a);
       CAB_LAUNCH_CHECK(ctx);
       rc = CAB_OK;
       if (trunc_fast) {  // the flagged packets: exact thresholds (computed by run_nn_hist for them) and the hit-compacting kernel
-        CAB_CUDA(ctx, cudaMemsetAsync((unsigned long long*)ctx->b_stats.p + 2 * kStatSlots, 0, 8, st));  // packet work counter
+        CAB_CUDA(ctx, cudaMemsetAsync((unsigned long long*)ctx->b_stats.p + 2 * kStatSlots + slot, 0, 8, ks));  // packet work counter
         a.skip = nullptr;
         a.only = (const unsigned char*)ctx->b_thr_flag.p;
-        rc = launch_rsd<false, true>(ctx, a, blocks, smem);
+        rc = launch_rsd<false, true>(ctx, a, blocks, smem, ks);
       }
-    } else if (ctx->cfg.exact) rc = use_thr ? launch_rsd<true, true>(ctx, a, blocks, smem) : launch_rsd<true, false>(ctx, a, blocks, smem);
-    else rc = use_thr ? launch_rsd<false, true>(ctx, a, blocks, smem) : launch_rsd<false, false>(ctx, a, blocks, smem);
+    } else if (ctx->cfg.exact) rc = use_thr ? launch_rsd<true, true>(ctx, a, blocks, smem, ks) : launch_rsd<true, false>(ctx, a, blocks, smem, ks);
+    else rc = use_thr ? launch_rsd<false, true>(ctx, a, blocks, smem, ks) : launch_rsd<false, false>(ctx, a, blocks, smem, ks);
     if (rc) return rc;
   }
   if (phase == 1) return CAB_OK;  // the boundary packets and the epilogue follow in phase 2
+  if (phase == 2) {               // join: the epilogue waits for both launches
+    CAB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ks));
+    CAB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+  }
   if (!ctx->slab && n > ctx->n_valid) {
     fill_invalid_rsd<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((float2*)ctx->b_rsd.p, (float*)ctx->b_rdif.p, ctx->n_valid, n,
                                                                     (float)plane_radius);

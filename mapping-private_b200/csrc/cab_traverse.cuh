@@ -49,11 +49,12 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { return fma2(a, b, 0ull
 // exact product (one rounding), not contractible by ptxas
 __device__ __forceinline__ f32x2 sq2(f32x2 a) { return fma2(a, a, 0ull); }
 
-// Persistent warps pull packets from a global counter (stats[2*kStatSlots]): blocks never idle on
+// Persistent warps pull packets from a global counter (stats[2*kStatSlots + slot]; two launches that run side by side
+// use one slot each): blocks never idle on
 // their slowest warp and concurrently running warps work on neighbouring packets (L2 locality).
-__device__ __forceinline__ int next_packet(unsigned long long* stats, int lane) {
+__device__ __forceinline__ int next_packet(unsigned long long* stats, int lane, int slot = 0) {
   int v = 0;
-  if (lane == 0) v = (int)atomicAdd(reinterpret_cast<unsigned int*>(stats + 2 * kStatSlots), 1u);
+  if (lane == 0) v = (int)atomicAdd(reinterpret_cast<unsigned int*>(stats + 2 * kStatSlots + slot), 1u);
   return __shfl_sync(kFull, v, 0);
 }
 

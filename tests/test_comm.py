@@ -100,6 +100,57 @@ def test_local_group_every_rank_holds_all_results(world, max_nn):
         c.close()
 
 
+@pytest.mark.parametrize("world,max_nn", [(3, 0), (4, 60)])
+def test_local_group_input_range_layout(world, max_nn):
+    """CAB_COMM_LAYOUT_INPUT_RANGES: every result crosses to ONE rank, the owner of the point's input index; after the
+    step rank g holds input indices [n g / world, n (g + 1) / world) in input order -- the ranks' ranges, rank after rank,
+    are the single-GPU channels bit for bit, non-finite points included."""
+    pts = synth.tabletop(90_000, noise_sigma=0.0002)
+    n = pts.shape[0]
+    for j in (5, n // world, n // 2 + 1, n - 1):  # nobody's query: their owners fill in the defaults
+        pts[j] = np.nan
+    n4, rmin, rmax, k = _single_gpu(pts, max_nn=max_nn)
+    ctxs = [cab.Context(0) for _ in range(world)]
+    cab.comm_init_local(ctxs)
+    out, errs = [None] * world, []
+
+    def work(r):
+        try:
+            c = ctxs[r]
+            c.comm_set_layout(cab.COMM_LAYOUT_INPUT_RANGES)
+            for it in range(2):
+                c.comm_upload_cloud(pts)
+                c.step_normals_rsd(R, R, max_nn_normals=max_nn, max_nn_rsd=max_nn)
+            lo, hi = n * r // world, n * (r + 1) // world
+            part = c.comm_download_range(lo, hi)
+            inner = c.comm_download_range(lo + 7, hi - 3, normals=False)
+            ptr, cnt = c.comm_device_ptr(cab.BUF_NRM_INPUT_RANGE)
+            assert ptr and cnt == hi - lo and c.comm_device_ptr(cab.BUF_PERM)[0] == 0
+            with pytest.raises(cab.CabError, match="input range"):
+                c.comm_download_range(max(lo - 1, 0), hi) if r > 0 else c.comm_download_range(lo, hi + 1)
+            out[r] = (part, inner, c.profile())
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not errs, errs
+    g4 = np.concatenate([o[0][0] for o in out])
+    gmin = np.concatenate([o[0][1] for o in out])
+    gmax = np.concatenate([o[0][2] for o in out])
+    assert _same(g4, n4) and _same(gmin, rmin) and _same(gmax, rmax)
+    for r in range(world):
+        lo, hi = n * r // world, n * (r + 1) // world
+        assert _same(out[r][1][1], rmin[lo + 7:hi - 3]) and _same(out[r][1][2], rmax[lo + 7:hi - 3])
+    if max_nn == 0:
+        assert sum(o[2]["neighbour_sum"] for o in out) == k
+    for c in ctxs:
+        c.close()
+
+
 def test_local_group_thin_slabs_recompute_their_halos():
     """Eight ranks on a small flat cloud: the slabs are thinner than two layers of rows, so the halo exchange is off and
     every rank recomputes the normals of the rows around its own (shard_mode 1); same results."""
