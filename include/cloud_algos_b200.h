@@ -313,6 +313,11 @@ int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_norm
 /* ---- multi-GPU groups ---------------------------------------------------------------------
  * One cab_ctx per GPU; the contexts of a group run the same calls in the same order (SPMD), each from its own host
  * thread or process.  Joining a group also sets the shard (cab_set_shard(rank, world)).
+ * One GPU per rank is the intended layout.  Ranks that share a GPU (tests) need CUDA_MODULE_LOADING=EAGER and
+ * CUDA_DEVICE_MAX_CONNECTIONS >= 2 x (ranks on the GPU) in the environment before CUDA is initialised: a step's kernels
+ * wait for the peers' flags, and a lazily loaded kernel's first launch, or a kernel queued behind a waiting kernel in a
+ * shared hardware queue, would stall the step until the timeout; connecting such a group without them fails with
+ * CAB_ERR_STATE.
  *   cab_comm_init_local   contexts of ONE process (e.g. a plugin host with one worker thread per GPU): peer access
  *                         between the devices, nothing else needed.
  *   cab_comm_init         one process per GPU (the torchrun / MPI layout): rank 0 obtains an id with cab_comm_get_id

@@ -27,10 +27,21 @@ int fail(cab_ctx* ctx, int code, const char* fmt, ...) {
 int reserve(cab_ctx* ctx, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return CAB_OK;
   if (b.p) {
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(b.p);
+    // The outgrown buffer is not freed here: cudaFree synchronises the whole device, and in a group whose ranks share a
+    // GPU (several contexts of one process, the tests) a peer's kernel may be spinning on a flag this rank has yet to
+    // post -- the free would wait for the peer and the peer for this rank.  Work still in flight may also go on using
+    // the old buffer.  The graveyard is emptied when the context is destroyed, or here once it holds more than a GiB.
+    ctx->graveyard.push_back(b);
+    ctx->graveyard_bytes += b.cap;
     b.p = nullptr;
     b.cap = 0;
+    if (ctx->graveyard_bytes > ((size_t)1 << 30)) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaStreamSynchronize(ctx->copy_stream);
+      for (DevBuf& g : ctx->graveyard) cudaFree(g.p);
+      ctx->graveyard.clear();
+      ctx->graveyard_bytes = 0;
+    }
   }
   size_t want = bytes + bytes / 8 + 256;  // grow-only arena with a little headroom
   cudaError_t e = cudaMalloc(&b.p, want);
@@ -297,11 +308,12 @@ void cab_destroy(cab_ctx* ctx) {
                     &ctx->b_keys[1], &ctx->b_keys[2], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_vals[2], &ctx->b_thr_flag, &ctx->b_knn_avg, &ctx->b_knn_done, &ctx->b_pfh[0], &ctx->b_pfh[1], &ctx->b_pfh[2], &ctx->b_cluster, &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
                     &ctx->b_cellcnt, &ctx->b_cellstart, &ctx->b_rowpk, &ctx->b_packets, &ctx->b_nrm, &ctx->b_nrm_in,
                     &ctx->b_rsd, &ctx->b_rdif, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
-                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_slab, &ctx->b_sel, &ctx->b_stats2, &ctx->b_sorttmp, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
+                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_slab, &ctx->b_sel, &ctx->b_stats2, &ctx->b_sorttmp, &ctx->b_occ, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
                     &ctx->g_vvals[1], &ctx->g_cent, &ctx->g_vcount, &ctx->g_vrad, &ctx->g_vlabel, &ctx->g_voff,
                     &ctx->g_layout, &ctx->g_layoff, &ctx->g_vgrid, &ctx->g_hist, &ctx->g_vfirst, &ctx->g_cnrm, &ctx->g_invperm, &ctx->g_sig, &ctx->g_sigdom, &ctx->g_color};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
+  for (DevBuf& g : ctx->graveyard) cudaFree(g.p);
   svm_free(ctx);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->h_step) cudaFreeHost(ctx->h_step);
@@ -565,6 +577,17 @@ int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_norm
   const bool halo = push && ctx->slab_info.exchange != 0;  // known since the build's second host round trip
   if (rc == CAB_OK && exchange && !ctx->slab && ctx->n_valid > 0)
     rc = fail(ctx, CAB_ERR_STATE, "cab_step_normals_rsd: the group's shard was reset (cab_set_shard) behind its back");
+  if (rc == CAB_OK && push) {
+    // every buffer the two passes need, before the first kernel that waits for a peer is enqueued: an allocation behind
+    // such a kernel may have to wait for it (ranks sharing one GPU), and the peer for this rank
+    const size_t np = (size_t)std::max<int64_t>(ctx->n, 1);
+    DevBuf* four[] = {&ctx->b_kcount, &ctx->b_rdif, &ctx->b_thr_d2, &ctx->b_thr_idx};
+    for (DevBuf* b : four)
+      if (rc == CAB_OK && (b == &ctx->b_kcount || b == &ctx->b_rdif || max_nn_rsd > 0 || max_nn_normals > 0)) rc = reserve(ctx, *b, np * 4);
+    if (rc == CAB_OK) rc = reserve(ctx, ctx->b_rsd, np * sizeof(float2));
+    if (rc == CAB_OK) rc = reserve(ctx, ctx->b_stats, kStatBytes);
+    if (rc == CAB_OK) rc = reserve(ctx, ctx->b_stats2, 65 * sizeof(float));
+  }
   if (rc == CAB_OK && push) rc = comm_step_begin(ctx);
   if (rc == CAB_OK) rc = run_normals(ctx, (float)r, max_nn_normals, vp);
   if (rc == CAB_OK && halo) rc = comm_halo_send(ctx);
@@ -576,7 +599,8 @@ int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_norm
     if (rc == CAB_OK) rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags, 1);
     if (rc == CAB_OK && cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0) != cudaSuccess)
       rc = fail(ctx, CAB_ERR_CUDA, "cudaStreamWaitEvent failed");
-    if (rc == CAB_OK) rc = comm_halo_receive(ctx, ctx->copy_stream);
+    static const bool serial_phases = std::getenv("CAB_SERIAL_PHASES") != nullptr;  // A/B switch
+    if (rc == CAB_OK) rc = comm_halo_receive(ctx, serial_phases ? ctx->stream : ctx->copy_stream);
     if (rc == CAB_OK) rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags, 2);
   } else if (rc == CAB_OK) {
     rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags);

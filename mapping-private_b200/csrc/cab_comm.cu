@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <condition_variable>
@@ -89,6 +90,7 @@ struct CommBlob {
   int32_t device;
   int32_t rank;
   int64_t cap_points;
+  char uuid[16];                          // of the device: two ranks on one GPU are told apart from two GPUs
   uint64_t raw[kNumBufs];                 // device pointers (meaningful inside process `pid`)
   cudaIpcMemHandle_t handle[kNumBufs];    // the same allocations for other processes
 };
@@ -207,9 +209,12 @@ __global__ void stamp_kernel(SyncBlock* __restrict__ mine) {
 // query count to every rank
 __global__ void post_done_kernel(PeerSync peers, const SyncBlock* __restrict__ mine, const SlabInfo* __restrict__ info, int rank,
                                  int world, unsigned seq) {
+  __shared__ unsigned long long busy_shared;  // ONE reading of the clock: every rank must receive the same number
   const int p = threadIdx.x;
+  if (p == 0) busy_shared = global_timer_ns() - mine->t_begin;
+  __syncthreads();
   if (p >= world) return;
-  const unsigned long long busy = global_timer_ns() - mine->t_begin;
+  const unsigned long long busy = busy_shared;
   peers.block[p]->busy[rank] = busy;
   peers.block[p]->count[rank] = (unsigned long long)(unsigned)(info->q1 - info->q0);
   __threadfence_system();
@@ -371,7 +376,8 @@ int make_blob(cab_ctx* ctx, int64_t n, CommBlob* blob) {
     }
     cs->own[b].cap = want;
     if (b == kBufSync) {
-      CAB_CUDA(ctx, cudaMemset(cs->own[b].p, 0xff, want));  // no flag equals a sequence number yet
+      CAB_CUDA(ctx, cudaMemsetAsync(cs->own[b].p, 0xff, want, ctx->stream));  // no flag equals a sequence number yet
+      CAB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       cs->seq = cs->cloud_seq = 0;
     }
   }
@@ -385,6 +391,11 @@ int make_blob(cab_ctx* ctx, int64_t n, CommBlob* blob) {
   blob->device = ctx->device;
   blob->rank = cs->rank;
   blob->cap_points = cs->cap_points;
+  {
+    cudaDeviceProp prop;
+    CAB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    std::memcpy(blob->uuid, &prop.uuid, 16);
+  }
   for (int b = 0; b < kNumBufs; ++b) {
     blob->raw[b] = (uint64_t)(uintptr_t)cs->own[b].p;
     cudaError_t e = cudaIpcGetMemHandle(&blob->handle[b], cs->own[b].p);
@@ -399,6 +410,27 @@ int make_blob(cab_ctx* ctx, int64_t n, CommBlob* blob) {
 int connect_blobs(cab_ctx* ctx, const CommBlob* blobs) {
   CommState* cs = ctx->comm;
   const int64_t me = (int64_t)getpid();
+  // Ranks that share a GPU run their kernels side by side, and a step's kernels wait for the peers' flags.  With CUDA's
+  // lazy module loading the FIRST launch of a kernel may have to wait until the device is idle -- i.e. for a peer's
+  // kernel that is itself waiting for this rank: the first step would stall until the timeout.  Eager loading (set
+  // before CUDA is initialised) is the documented remedy; one GPU per rank, the production layout, is not affected.
+  // Likewise the ranks' streams (two per rank) must not share a hardware queue, where a waiting kernel of one rank
+  // would hold back the kernels of another: CUDA_DEVICE_MAX_CONNECTIONS (default 8) >= 2 x the ranks on the GPU.
+  for (int p = 0; p < cs->world; ++p) {
+    int sharing = 0;
+    for (int q = 0; q < cs->world; ++q) sharing += std::memcmp(blobs[p].uuid, blobs[q].uuid, 16) == 0 ? 1 : 0;
+    if (sharing < 2) continue;
+    const char* mode = std::getenv("CUDA_MODULE_LOADING");
+    if (!mode || std::strcmp(mode, "EAGER") != 0)
+      return fail(ctx, CAB_ERR_STATE, "cab_comm: %d ranks share the GPU of rank %d; set CUDA_MODULE_LOADING=EAGER before CUDA is "
+                                      "initialised (lazy kernel loading can stall a step whose kernels wait for each other)", sharing, p);
+    const char* conn = std::getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+    const int have = conn ? std::atoi(conn) : 8;
+    if (have < 2 * sharing)
+      return fail(ctx, CAB_ERR_STATE, "cab_comm: %d ranks share the GPU of rank %d; set CUDA_DEVICE_MAX_CONNECTIONS >= %d before "
+                                      "CUDA is initialised (streams sharing a hardware queue serialise behind a waiting kernel)",
+                  sharing, p, 2 * sharing);
+  }
   for (int p = 0; p < cs->world; ++p) {
     const CommBlob& b = blobs[p];
     if (b.rank != p) return fail(ctx, CAB_ERR_ARG, "cab_comm: blob %d describes rank %d", p, b.rank);
@@ -593,6 +625,9 @@ int comm_step_end(cab_ctx* ctx, double plane_radius) {  // after the RSD kernel
   CAB_LAUNCH_CHECK(ctx);
   CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepComm + 64, mine->busy, 2 * kMaxPeers * sizeof(unsigned long long),
                                 cudaMemcpyDeviceToHost, ctx->stream));
+  // the waits of this step report a peer that did not answer in SlabInfo::error: read it after the last of them
+  CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepComm + 8, &slab_info_device(ctx)->error, sizeof(int), cudaMemcpyDeviceToHost,
+                                ctx->stream));
   if (cs->layout == CAB_COMM_LAYOUT_REPLICATED)
     CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepComm, &((SyncBlock*)cs->own[kBufSync].p)->total, 8, cudaMemcpyDeviceToHost,
                                   ctx->stream));
@@ -608,6 +643,11 @@ int comm_step_finish(cab_ctx* ctx) {  // after the step's synchronisation
   } else {
     cs->last_total = ctx->n * (cs->rank + 1) / cs->world - ctx->n * cs->rank / cs->world;
   }
+  std::memcpy(&ctx->slab_info.error, ctx->h_step + kStepComm + 8, sizeof(int));
+  if (std::getenv("CAB_COMM_DEBUG"))
+    fprintf(stderr, "[cab_comm] rank %d seq %u q0 %d q1 %d gbase %d total %lld n_selected %d exchange %d error %d\n", cs->rank, cs->seq,
+            ctx->slab_info.q0, ctx->slab_info.q1, ctx->slab_info.gbase, (long long)cs->last_total, ctx->slab_info.n_selected,
+            ctx->slab_info.exchange, ctx->slab_info.error);
   if (ctx->slab_info.error) return fail(ctx, CAB_ERR_STATE, "cab_comm: a peer did not answer within %.1f s", cs->timeout_ns * 1e-9);
   unsigned long long fb[2 * kMaxPeers];
   std::memcpy(fb, ctx->h_step + kStepComm + 64, sizeof(fb));

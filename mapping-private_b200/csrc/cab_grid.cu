@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(const Domain* __restr
 // cell histogram of every S-th run of 256 consecutive points (3 KB: whole DRAM bursts, unlike a stride of single points)
 __global__ void __launch_bounds__(256) sample_hist_kernel(const float* __restrict__ xyz, int stride, int n, int sample,
                                                           const Domain* __restrict__ domains, float inv_cell,
-                                                          int* __restrict__ cellcnt) {
+                                                          int* __restrict__ cellcnt, int* __restrict__ occ_count,
+                                                          int* __restrict__ occ_list) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long first = ((t >> 6) * sample * 64 + (t & 63)) * 4;
   if (first >= n) return;
@@ -317,57 +318,58 @@ __global__ void __launch_bounds__(256) sample_hist_kernel(const float* __restric
     int cy, cz;
     row_cells(dm, y, z, inv_cell, cy, cz);
     const int cx = xfine_coord(x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift;
-    atomicAdd(cellcnt + ((long long)cz * dm.ny + cy) * dm.nx + cx, 1);
+    const long long cell = ((long long)cz * dm.ny + cy) * dm.nx + cx;
+    // the first sampled point of a cell lists it: the cost kernel then visits the occupied cells only (a few per cent of
+    // the table of a cloud of surfaces)
+    if (atomicAdd(cellcnt + cell, 1) == 0) occ_list[atomicAdd(occ_count, 1)] = (int)cell;
   }
 }
 
-// cost of a row = sum over its cells of (sampled points) x (estimated candidates per point + constants).  One block
-// per strip of kCostRows rows of one z layer: the 3 x (kCostRows + 2) rows it reads are staged in shared memory chunk by
-// chunk along x (coalesced loads, every table row read ~4 times instead of 9, no divergent gathers); one warp per row.
-constexpr int kCostRows = 6, kCostChunk = 256;
-__global__ void __launch_bounds__(kCostRows * 32) row_cost_kernel(const Domain* __restrict__ domains, const int* __restrict__ cnt,
-                                                                  int sample, long long* __restrict__ rowcost) {
-  __shared__ int tile[3][kCostRows + 2][kCostChunk + 2];
+// cost of a row = sum over its occupied cells of (sampled points) x (estimated candidates per point + constants).  One
+// warp per listed cell, four cells in flight per warp: 27 lanes read the 3 x 3 x 3 cells around it (nine short runs of the
+// table, L2 hits), the warp sums them, lane 0 adds the cell's cost to its row.  Integer sums: the order does not matter.
+__global__ void __launch_bounds__(256) cell_cost_kernel(const Domain* __restrict__ domains, const int* __restrict__ cnt,
+                                                        const int* __restrict__ occ_count, const int* __restrict__ occ_list,
+                                                        int sample, unsigned long long* __restrict__ rowcost) {
   const Domain dm = domains[0];
-  const int strips = (dm.ny + kCostRows - 1) / kCostRows;
-  const int cz = blockIdx.x / strips, cy0 = (blockIdx.x % strips) * kCostRows;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cy = cy0 + warp;
-  long long acc = 0;
-  for (int x0 = 0; x0 < dm.nx; x0 += kCostChunk) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * (kCostRows + 2) * (kCostChunk + 2); i += blockDim.x) {
-      const int xx = i % (kCostChunk + 2), rr = (i / (kCostChunk + 2)) % (kCostRows + 2), zz = i / ((kCostChunk + 2) * (kCostRows + 2));
-      const int x = x0 + xx - 1, y = cy0 + rr - 1, z = cz + zz - 1;
-      int v = 0;
-      if (x >= 0 && x < dm.nx && y >= 0 && y < dm.ny && z >= 0 && z < dm.nz) v = cnt[((long long)z * dm.ny + y) * dm.nx + x];
-      tile[zz][rr][xx] = v;
-    }
-    __syncthreads();
-    if (cy < dm.ny) {
-      for (int xx = lane; xx < kCostChunk && x0 + xx < dm.nx; xx += kWarp) {
-        const int c = tile[1][warp + 1][xx + 1];
-        if (c == 0) continue;
-        // candidates ~ the 3 x 3 rows around the cell, along x the cell itself plus 0.7 of either neighbour: a packet's x
-        // window is its own extent + 2 r, about 2.4 cells (a full 3-cell stencil overrates surfaces that run along x,
-        // e.g. the walls an end slab consists of, by a quarter against surfaces across x)
-        int s10 = 0;
+  const int n_occ = *occ_count;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  // lane -> offset in the stencil; candidates ~ the 3 x 3 rows around the cell, along x the cell itself plus 0.7 of
+  // either neighbour: a packet's x window is its own extent + 2 r, about 2.4 cells (a full 3-cell stencil overrates
+  // surfaces that run along x, e.g. the walls an end slab consists of, by a quarter against surfaces across x)
+  const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+  const int weight = lane >= 27 ? 0 : dx == 0 ? 10 : 7;
+  for (int base = warp * 4; base < n_occ; base += n_warps * 4) {
+    int v[4], row[4], c[4];
 #pragma unroll
-        for (int zz = 0; zz < 3; ++zz)
-#pragma unroll
-          for (int rr = 0; rr < 3; ++rr) {
-            const int* r = &tile[zz][warp + rr][xx];
-            s10 += 10 * r[1] + 7 * (r[0] + r[2]);
-          }
-        // + a constant per point (fit, eigen-solve: 2 candidates' worth) and per occupied cell (sparse rows make many
-        // short packets, each with its own run table and chunk overhead: 16 candidates' worth per cell)
-        acc += (long long)c * ((long long)s10 * sample + 20) + 160;
+    for (int u = 0; u < 4; ++u) {
+      v[u] = 0;
+      row[u] = -1;
+      c[u] = 0;
+      if (base + u < n_occ) {
+        const int cell = occ_list[base + u];
+        const int cx = cell % dm.nx;
+        row[u] = cell / dm.nx;
+        const int cy = row[u] % dm.ny, cz = row[u] / dm.ny;
+        const int x = cx + dx, y = cy + dy, z = cz + dz;
+        if (lane < 27 && x >= 0 && x < dm.nx && y >= 0 && y < dm.ny && z >= 0 && z < dm.nz)
+          v[u] = cnt[((long long)z * dm.ny + y) * dm.nx + x];
+        c[u] = __shfl_sync(kFull, v[u], 13);  // the cell itself (dx = dy = dz = 0)
+        v[u] *= weight;
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
-  if (lane == 0 && cy < dm.ny) rowcost[(long long)cz * dm.ny + cy] = acc;
+    for (int u = 0; u < 4; ++u) {
+      int s10 = v[u];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s10 += __shfl_xor_sync(kFull, s10, o);
+      // + a constant per point (fit, eigen-solve: 2 candidates' worth) and per occupied cell (sparse rows make many
+      // short packets, each with its own run table and chunk overhead: 16 candidates' worth per cell)
+      if (lane == 0 && row[u] >= 0)
+        atomicAdd(rowcost + row[u], (unsigned long long)((long long)c[u] * ((long long)s10 * sample + 20) + 160));
+    }
+  }
 }
 
 __device__ __forceinline__ long long cum_before(const long long* __restrict__ cum, int p) { return p > 0 ? cum[p - 1] : 0; }
@@ -952,13 +954,18 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
   int* sel_cnt = (int*)ctx->b_vals[2].p;
   int* sel_off = sel_cnt + sel_blocks + 1;
   CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_cellcnt.p, 0, ((size_t)cells + 1) * 4, st));
+  CAB_CUDA(ctx, cudaMemsetAsync(rowcost, 0, (size_t)rows * 8, st));
+  if (int rc = reserve(ctx, ctx->b_occ, ((size_t)n / sample + 1024 + 4 * 256) * 4)) return rc;  // at most one entry per sampled point
   {
     const long long threads = (((long long)n + 256LL * sample - 1) / (256LL * sample)) * 64;
+    // the table's spare last entry (zeroed with it) counts the occupied cells the histogram kernel lists
+    int* occ_count = (int*)ctx->b_cellcnt.p + cells;
     sample_hist_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, sample, d_dom,
-                                                                        ctx->inv_cell, (int*)ctx->b_cellcnt.p);
+                                                                        ctx->inv_cell, (int*)ctx->b_cellcnt.p, occ_count,
+                                                                        (int*)ctx->b_occ.p);
     CAB_LAUNCH_CHECK(ctx);
-    const unsigned blocks = (unsigned)(((int64_t)dm.ny + kCostRows - 1) / kCostRows * dm.nz);
-    row_cost_kernel<<<blocks, kCostRows * 32, 0, st>>>(d_dom, (const int*)ctx->b_cellcnt.p, sample, rowcost);
+    cell_cost_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_dom, (const int*)ctx->b_cellcnt.p, occ_count, (const int*)ctx->b_occ.p,
+                                                        sample, (unsigned long long*)rowcost);
     CAB_LAUNCH_CHECK(ctx);
     CAB_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->b_cubtmp.p, tmp_cost, rowcost, cum, (int)rows, st));
     SplitShares sh{};
@@ -1037,7 +1044,8 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
   }
   // ---- radix sort of the window by (row, fine x), on the copy stream: the four latency-bound passes over a few million
   // keys run beside the cell table, segment and packet kernels below, which need the cell histogram only
-  cudaStream_t ss = ctx->copy_stream;
+  static const bool serial_sort = std::getenv("CAB_SERIAL_SORT") != nullptr;  // A/B switch
+  cudaStream_t ss = serial_sort ? st : ctx->copy_stream;
   if (m > 0) {
     CAB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
     CAB_CUDA(ctx, cudaStreamWaitEvent(ss, ctx->ev_fork, 0));

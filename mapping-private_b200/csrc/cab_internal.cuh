@@ -191,7 +191,9 @@ struct cab_ctx {
   // device arena (grow-only)
   cab::DevBuf b_xyz, b_domoff, b_domid, b_bounds, b_domains, b_keys[3], b_vals[3], b_cubtmp, b_pos,
       b_perm, b_cellcnt, b_cellstart, b_rowpk, b_packets, b_nrm, b_nrm_in, b_rsd, b_rdif, b_kcount, b_stats,
-      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost, b_slab, b_sel, b_stats2, b_sorttmp, b_thr_flag, b_knn_avg, b_knn_done, b_pfh[3], b_cluster;
+      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost, b_slab, b_sel, b_stats2, b_sorttmp, b_occ, b_thr_flag, b_knn_avg, b_knn_done, b_pfh[3], b_cluster;
+  std::vector<cab::DevBuf> graveyard;  // outgrown arena buffers (see reserve())
+  size_t graveyard_bytes = 0;
   // pinned staging
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;

@@ -692,7 +692,8 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   // phase 2 (the boundary packets of a split pass) is launched on the copy stream with its own work counter: it runs
   // beside the tail of phase 1 instead of after it
   cudaStream_t st = ctx->stream;
-  cudaStream_t ks = phase == 2 ? ctx->copy_stream : ctx->stream;
+  static const bool serial_phases = std::getenv("CAB_SERIAL_PHASES") != nullptr;  // A/B switch
+  cudaStream_t ks = phase == 2 && !serial_phases ? ctx->copy_stream : ctx->stream;
   const int slot = phase == 2 ? 1 : 0;
   if (int rc = reserve(ctx, ctx->b_rsd, (size_t)std::max(n, 1) * sizeof(float2))) return rc;
   if (int rc = reserve(ctx, ctx->b_rdif, (size_t)std::max(n, 1) * sizeof(float))) return rc;

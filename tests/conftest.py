@@ -1,5 +1,12 @@
+import os
 import pathlib
 import sys
+
+# Several ranks of a group share the one GPU of the test box (tests/test_comm.py): their kernels wait for each other's
+# flags, and CUDA's lazy module loading can stall the first launch of a kernel behind such a waiting kernel.  Must be set
+# before CUDA is initialised (csrc/cab_comm.cu connect_blobs refuses such a group otherwise).
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # two streams per rank, up to eight ranks on the GPU
 
 import pytest
 

@@ -65,13 +65,17 @@ def test_local_group_every_rank_holds_all_results(world, max_nn):
     ctxs = [cab.Context(0) for _ in range(world)]
     cab.comm_init_local(ctxs)
     out, errs = [None] * world, []
+    gate = threading.Barrier(world)
 
     def work(r):
         try:
             c = ctxs[r]
-            for it in range(2):  # the second step reuses the connected buffers
+            for it in range(3):  # the later steps reuse the connected buffers, with cuts moved by the measured-time feedback
                 c.comm_upload_cloud(pts)
                 c.step_normals_rsd(R, R, max_nn_normals=max_nn, max_nn_rsd=max_nn)
+                f4, fmin, fmax = c.comm_download_range(0, n)  # the very first step of a fresh group included
+                assert _same(f4, n4) and _same(fmin, rmin) and _same(fmax, rmax), f"rank {r}, step {it}"
+                gate.wait(timeout=60)  # nobody starts pushing the next step's results into arrays still being read
             full = c.comm_download_range(0, n)
             lo, hi = n * r // world, n * (r + 1) // world
             part = c.comm_download_range(lo, hi)
@@ -113,15 +117,19 @@ def test_local_group_input_range_layout(world, max_nn):
     ctxs = [cab.Context(0) for _ in range(world)]
     cab.comm_init_local(ctxs)
     out, errs = [None] * world, []
+    gate = threading.Barrier(world)
 
     def work(r):
         try:
             c = ctxs[r]
             c.comm_set_layout(cab.COMM_LAYOUT_INPUT_RANGES)
-            for it in range(2):
+            lo, hi = n * r // world, n * (r + 1) // world
+            for it in range(3):
                 c.comm_upload_cloud(pts)
                 c.step_normals_rsd(R, R, max_nn_normals=max_nn, max_nn_rsd=max_nn)
-            lo, hi = n * r // world, n * (r + 1) // world
+                p4, pmin, pmax = c.comm_download_range(lo, hi)
+                assert _same(p4, n4[lo:hi]) and _same(pmin, rmin[lo:hi]) and _same(pmax, rmax[lo:hi]), f"rank {r}, step {it}"
+                gate.wait(timeout=60)
             part = c.comm_download_range(lo, hi)
             inner = c.comm_download_range(lo + 7, hi - 3, normals=False)
             ptr, cnt = c.comm_device_ptr(cab.BUF_NRM_INPUT_RANGE)
