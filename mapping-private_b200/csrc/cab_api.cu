@@ -147,7 +147,7 @@ int upload_impl(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride, const
   if (stride < 3) return fail(ctx, CAB_ERR_ARG, "stride must be >= 3 floats");
   if (n > 0 && !xyz) return fail(ctx, CAB_ERR_ARG, "xyz is NULL");
   CAB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ctx->have_cloud = ctx->have_grid = ctx->have_normals = ctx->have_rsd = ctx->kcount_valid = false;
+  ctx->have_cloud = ctx->have_grid = ctx->have_normals = ctx->have_rsd = ctx->kcount_valid = ctx->trunc_hist_valid = false;
   ctx->g_min_div.clear();  // voxel state of the last cab_grsd_batch belongs to the previous cloud
   if (int rc = set_domains(ctx, n, offsets, nclusters)) return rc;
   if (device_ptr) {
@@ -484,7 +484,8 @@ int cab_normals_rsd(cab_ctx* ctx, double r, int32_t max_nn_normals, const float 
     return fail(ctx, CAB_ERR_STATE, "cab_normals_rsd: a shard returns its own slice (CAB_OUT_SHARD_SORTED); the concatenated "
                                      "results of a group come from cab_step_normals_rsd + cab_comm_download_range");
   // pass 1 on the compute stream
-  if (int rc = run_normals(ctx, (float)r, max_nn_normals, vp)) return rc;
+  // (an RSD pass truncated at max_nn_rsd follows at the same radius: the normals traversal takes its d2 histogram along)
+  if (int rc = run_normals(ctx, (float)r, max_nn_normals, vp, nullptr, max_nn_normals == 0 ? max_nn_rsd : 0)) return rc;
   int64_t b = 0, e = 0;
   if (layout == CAB_OUT_SHARD_SORTED)
     if (int rc = cab_shard_range(ctx, &b, &e)) return rc;
@@ -589,7 +590,7 @@ int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_norm
     if (rc == CAB_OK) rc = reserve(ctx, ctx->b_stats2, 65 * sizeof(float));
   }
   if (rc == CAB_OK && push) rc = comm_step_begin(ctx);
-  if (rc == CAB_OK) rc = run_normals(ctx, (float)r, max_nn_normals, vp);
+  if (rc == CAB_OK) rc = run_normals(ctx, (float)r, max_nn_normals, vp, nullptr, max_nn_normals == 0 ? max_nn_rsd : 0);
   if (rc == CAB_OK && halo) rc = comm_halo_send(ctx);
   if (rc == CAB_OK && push) rc = comm_step_before_push(ctx);
   if (halo) {

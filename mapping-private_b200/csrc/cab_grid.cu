@@ -304,8 +304,7 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(const Domain* __restr
 // cell histogram of every S-th run of 256 consecutive points (3 KB: whole DRAM bursts, unlike a stride of single points)
 __global__ void __launch_bounds__(256) sample_hist_kernel(const float* __restrict__ xyz, int stride, int n, int sample,
                                                           const Domain* __restrict__ domains, float inv_cell,
-                                                          int* __restrict__ cellcnt, int* __restrict__ occ_count,
-                                                          int* __restrict__ occ_list) {
+                                                          int* __restrict__ cellcnt) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long first = ((t >> 6) * sample * 64 + (t & 63)) * 4;
   if (first >= n) return;
@@ -318,57 +317,56 @@ __global__ void __launch_bounds__(256) sample_hist_kernel(const float* __restric
     int cy, cz;
     row_cells(dm, y, z, inv_cell, cy, cz);
     const int cx = xfine_coord(x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift;
-    const long long cell = ((long long)cz * dm.ny + cy) * dm.nx + cx;
-    // the first sampled point of a cell lists it: the cost kernel then visits the occupied cells only (a few per cent of
-    // the table of a cloud of surfaces)
-    if (atomicAdd(cellcnt + cell, 1) == 0) occ_list[atomicAdd(occ_count, 1)] = (int)cell;
+    atomicAdd(cellcnt + ((long long)cz * dm.ny + cy) * dm.nx + cx, 1);  // no return value: a fire-and-forget reduction
   }
 }
 
 // cost of a row = sum over its occupied cells of (sampled points) x (estimated candidates per point + constants).  One
-// warp per listed cell, four cells in flight per warp: 27 lanes read the 3 x 3 x 3 cells around it (nine short runs of the
-// table, L2 hits), the warp sums them, lane 0 adds the cell's cost to its row.  Integer sums: the order does not matter.
+// thread per cell of the table, streamed (L2 hits right after the histogram kernel); only the occupied cells -- a few per
+// cent of the table of a cloud of surfaces, in runs along x -- read the 3 x 3 x 3 cells around them, and the lanes of a
+// run read neighbouring words.  A warp's cells lie in one or two rows: one 64-bit atomic per row and warp.  Integer sums:
+// the order does not matter.
 __global__ void __launch_bounds__(256) cell_cost_kernel(const Domain* __restrict__ domains, const int* __restrict__ cnt,
-                                                        const int* __restrict__ occ_count, const int* __restrict__ occ_list,
-                                                        int sample, unsigned long long* __restrict__ rowcost) {
+                                                        long long n_cells, int sample, unsigned long long* __restrict__ rowcost) {
   const Domain dm = domains[0];
-  const int n_occ = *occ_count;
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  // lane -> offset in the stencil; candidates ~ the 3 x 3 rows around the cell, along x the cell itself plus 0.7 of
-  // either neighbour: a packet's x window is its own extent + 2 r, about 2.4 cells (a full 3-cell stencil overrates
-  // surfaces that run along x, e.g. the walls an end slab consists of, by a quarter against surfaces across x)
-  const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
-  const int weight = lane >= 27 ? 0 : dx == 0 ? 10 : 7;
-  for (int base = warp * 4; base < n_occ; base += n_warps * 4) {
-    int v[4], row[4], c[4];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n_cells; base += stride) {
+    const long long cell = base + lane;
+    const int c = cell < n_cells ? cnt[cell] : 0;
+    const int row = (int)(min(cell, n_cells - 1) / dm.nx);
+    unsigned long long cost = 0;
+    if (c != 0) {
+      const int cx = (int)(cell - (long long)row * dm.nx), cy = row % dm.ny, cz = row / dm.ny;
+      // candidates ~ the 3 x 3 rows around the cell, along x the cell itself plus 0.7 of either neighbour: a packet's x
+      // window is its own extent + 2 r, about 2.4 cells (a full 3-cell stencil overrates surfaces that run along x,
+      // e.g. the walls an end slab consists of, by a quarter against surfaces across x)
+      int s10 = 0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      v[u] = 0;
-      row[u] = -1;
-      c[u] = 0;
-      if (base + u < n_occ) {
-        const int cell = occ_list[base + u];
-        const int cx = cell % dm.nx;
-        row[u] = cell / dm.nx;
-        const int cy = row[u] % dm.ny, cz = row[u] / dm.ny;
-        const int x = cx + dx, y = cy + dy, z = cz + dz;
-        if (lane < 27 && x >= 0 && x < dm.nx && y >= 0 && y < dm.ny && z >= 0 && z < dm.nz)
-          v[u] = cnt[((long long)z * dm.ny + y) * dm.nx + x];
-        c[u] = __shfl_sync(kFull, v[u], 13);  // the cell itself (dx = dy = dz = 0)
-        v[u] *= weight;
-      }
-    }
+      for (int dz = -1; dz <= 1; ++dz)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int s10 = v[u];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) s10 += __shfl_xor_sync(kFull, s10, o);
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int y = cy + dy, z = cz + dz;
+          if (y < 0 || y >= dm.ny || z < 0 || z >= dm.nz) continue;
+          const int* r = cnt + ((long long)z * dm.ny + y) * dm.nx + cx;
+          s10 += 10 * r[0] + 7 * ((cx > 0 ? r[-1] : 0) + (cx + 1 < dm.nx ? r[1] : 0));
+        }
       // + a constant per point (fit, eigen-solve: 2 candidates' worth) and per occupied cell (sparse rows make many
       // short packets, each with its own run table and chunk overhead: 16 candidates' worth per cell)
-      if (lane == 0 && row[u] >= 0)
-        atomicAdd(rowcost + row[u], (unsigned long long)((long long)c[u] * ((long long)s10 * sample + 20) + 160));
+      cost = (unsigned long long)((long long)c * ((long long)s10 * sample + 20) + 160);
     }
+    if (__ballot_sync(kFull, c != 0) == 0) continue;
+    // the warp's cells are consecutive: lanes of the first row, lanes of the last row, (nx < 16: rows in between)
+    const int row_a = __shfl_sync(kFull, row, 0), row_b = __shfl_sync(kFull, row, 31);
+    unsigned long long sa = row == row_a ? cost : 0ull, sb = (row == row_b && row_b != row_a) ? cost : 0ull;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      sa += __shfl_xor_sync(kFull, sa, o);
+      sb += __shfl_xor_sync(kFull, sb, o);
+    }
+    if (lane == 0 && sa) atomicAdd(rowcost + row_a, sa);
+    if (lane == 31 && sb) atomicAdd(rowcost + row_b, sb);
+    if (row != row_a && row != row_b && cost) atomicAdd(rowcost + row, cost);
   }
 }
 
@@ -715,7 +713,7 @@ int build_grid(cab_ctx* ctx, float cell) {
   const int n = (int)ctx->n;
   const int nd = ctx->n_domains;
   cudaStream_t st = ctx->stream;
-  ctx->have_grid = ctx->have_normals = ctx->have_rsd = ctx->kcount_valid = false;
+  ctx->have_grid = ctx->have_normals = ctx->have_rsd = ctx->kcount_valid = ctx->trunc_hist_valid = false;
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
 
   if (int rc = compute_bounds(ctx)) return rc;
@@ -955,17 +953,13 @@ int build_slab(cab_ctx* ctx, bool key32, int xbits) {
   int* sel_off = sel_cnt + sel_blocks + 1;
   CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_cellcnt.p, 0, ((size_t)cells + 1) * 4, st));
   CAB_CUDA(ctx, cudaMemsetAsync(rowcost, 0, (size_t)rows * 8, st));
-  if (int rc = reserve(ctx, ctx->b_occ, ((size_t)n / sample + 1024 + 4 * 256) * 4)) return rc;  // at most one entry per sampled point
   {
     const long long threads = (((long long)n + 256LL * sample - 1) / (256LL * sample)) * 64;
-    // the table's spare last entry (zeroed with it) counts the occupied cells the histogram kernel lists
-    int* occ_count = (int*)ctx->b_cellcnt.p + cells;
     sample_hist_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ctx->xyz_in, ctx->stride, n, sample, d_dom,
-                                                                        ctx->inv_cell, (int*)ctx->b_cellcnt.p, occ_count,
-                                                                        (int*)ctx->b_occ.p);
+                                                                        ctx->inv_cell, (int*)ctx->b_cellcnt.p);
     CAB_LAUNCH_CHECK(ctx);
-    cell_cost_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_dom, (const int*)ctx->b_cellcnt.p, occ_count, (const int*)ctx->b_occ.p,
-                                                        sample, (unsigned long long*)rowcost);
+    cell_cost_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_dom, (const int*)ctx->b_cellcnt.p, (long long)cells, sample,
+                                                        (unsigned long long*)rowcost);
     CAB_LAUNCH_CHECK(ctx);
     CAB_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->b_cubtmp.p, tmp_cost, rowcost, cum, (int)rows, st));
     SplitShares sh{};

@@ -166,6 +166,8 @@ struct cab_ctx {
   bool have_cloud = false, have_grid = false, have_normals = false, have_rsd = false;
   bool kcount_valid = false;  // b_kcount holds the untruncated in-radius neighbour counts (self included) of radius kcount_r
   float kcount_r = 0.f;
+  bool trunc_hist_valid = false;  // b_thr_idx / b_thr_flag hold the d2-histogram codes of radius kcount_r, max_nn trunc_hist_max_nn
+  int trunc_hist_max_nn = 0;      // (taken along by the last normals pass for the truncated fast RSD pass)
   bool cloud_external = false;
   const float* xyz_in = nullptr;  // device, stride floats
   int stride = 3;
@@ -244,7 +246,7 @@ void read_stats(cab_ctx* ctx, const void* staged = nullptr);  // sums the kStatS
 // stage entry points (each enqueues on ctx->stream; callers synchronise)
 int compute_bounds(cab_ctx* ctx);
 int build_grid(cab_ctx* ctx, float cell);
-int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsigned char* done = nullptr);
+int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsigned char* done = nullptr, int hist_max_nn = 0);
 // phase 0: the whole pass; 1: prologue + the packets that read no halo row; 2: the boundary packets + epilogue
 int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, int flags, int phase = 0);
 int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done = nullptr, bool halo = false);  // max_nn truncation thresholds (halo: also for a slab's halo packets)

@@ -62,6 +62,13 @@ struct NormalsArgs {
   const int* thr_idx;
   const unsigned char* done;  // optional (input order): packets whose queries are all done are skipped (k-NN rounds)
   unsigned long long* stats;  // kStatSlots x {neighbour sum, candidate sum}
+  // kHist: the d2 histogram of the truncated fast RSD pass that follows at the same radius (cab_topk.cu nn_hist_kernel
+  // does the same in a traversal of its own): per query the bin of neighbour max_nn + 1 and how many of that bin's
+  // candidates are kept, per packet whether some query's bin holds more candidates than the RSD pass can list
+  int* code;
+  unsigned char* flag;      // indexed by packet - p0
+  int hist_max_nn;
+  float hist_scale;         // kTruncBins / r2
 };
 
 // fp32 accumulate of one candidate, predicated on d2 <= r2 (explicit predication: the compiler's
@@ -85,10 +92,22 @@ __device__ __forceinline__ void accum_pred(float d2, float r2, float dx, float d
       : "f"(d2), "f"(r2), "f"(dx), "f"(dy), "f"(dz));
 }
 
-template <bool kExact, bool kUseThr>
+// one candidate of the kHist variant: bin of the 64-bin d2 histogram (the expression of nn_hist_kernel, same bits), misses
+// to the spare row (an unconditional reduction: ptxas would turn a predicated one into a branch)
+__device__ __forceinline__ void hist_add(float d2, float r2, float scale, unsigned col) {
+  const int b = d2 <= r2 ? min(__float2int_rz(d2 * scale), kTruncBins - 1) : kTruncBins;
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(col + 128u * (unsigned)b));
+}
+
+template <bool kExact, bool kUseThr, bool kHist = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const NormalsArgs a) {
   __shared__ ChunkTile tiles[kWarpsPerBlock];
+  extern __shared__ unsigned hist_dyn[];  // kHist: [warps][kTruncBins + 1][32], row kTruncBins: the misses (dynamic: 66.5 KB)
+  typedef unsigned HistRows[kTruncBins + 1][kWarp];
+  HistRows* hist = reinterpret_cast<HistRows*>(hist_dyn);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned hcol = kHist ? (unsigned)__cvta_generic_to_shared(&hist[warp][0][lane]) : 0u;
+  const float hscale = a.hist_scale;
   const GridView& g = a.g;
   const int p0 = a.range ? a.range[0] : a.p0, p1 = a.range ? a.range[1] : a.p1;
   for (;;) {
@@ -106,6 +125,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
   if constexpr (!kExact && !kUseThr) {
     // fast path: packed fp32x2 distance test, predicated fp32 accumulation
     const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
+    if constexpr (kHist) {
+      for (int b = 0; b <= kTruncBins; ++b) hist[warp][b][lane] = 0;
+      __syncwarp();
+    }
     tested = for_each_chunk(g, pc, lane, tile, [&](int cnt, const float4&, int, bool) {
       const float4* tx = reinterpret_cast<const float4*>(tile->x);
       const float4* ty = reinterpret_cast<const float4*>(tile->y);
@@ -120,13 +143,40 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
         unpack2(d2, d2a, d2b); unpack2(dx, xa, xb); unpack2(dy, ya, yb); unpack2(dz, za, zb);
         accum_pred(d2a, r2, xa, ya, za, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, k);
         accum_pred(d2b, r2, xb, yb, zb, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, k);
+        if constexpr (kHist) {
+          hist_add(d2a, r2, hscale, hcol);
+          hist_add(d2b, r2, hscale, hcol);
+        }
         dx = sub2(pack2(X.z, X.w), qx2); dy = sub2(pack2(Y.z, Y.w), qy2); dz = sub2(pack2(Z.z, Z.w), qz2);
         d2 = add2(add2(sq2(dx), sq2(dy)), sq2(dz));
         unpack2(d2, d2a, d2b); unpack2(dx, xa, xb); unpack2(dy, ya, yb); unpack2(dz, za, zb);
         accum_pred(d2a, r2, xa, ya, za, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, k);
         accum_pred(d2b, r2, xb, yb, zb, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, k);
+        if constexpr (kHist) {
+          hist_add(d2a, r2, hscale, hcol);
+          hist_add(d2b, r2, hscale, hcol);
+        }
       }
     });
+    if constexpr (kHist) {
+      // the bin that holds neighbour number max_nn + 1 (the first one dropped), as nn_hist_kernel finds it
+      __syncwarp();
+      asm volatile("" ::: "memory");
+      int kk = 0, bin = 255, before = 0, in_bin = 0;
+      for (int b = 0; b < kTruncBins; ++b) {
+        const int c = (int)hist[warp][b][lane];
+        if (bin == 255 && kk + c >= a.hist_max_nn + 1) {
+          bin = b;
+          before = kk;
+          in_bin = c;
+        }
+        kk += c;
+      }
+      const bool over = pc.active && bin != 255 && in_bin > kTruncCap;
+      if (pc.active) a.code[pc.qi] = bin == 255 ? 255 : (bin | ((a.hist_max_nn - before) << 8));
+      if (__any_sync(kFull, over) && lane == 0) a.flag[pid - a.p0] = 1;
+      __syncwarp();
+    }
   } else {
     // exact / truncated path: hit mask per chunk, then only the hits are visited; the candidate is
     // fetched from the lane that staged it (warp shuffle, no shared-memory bank conflicts)
@@ -230,7 +280,7 @@ __global__ void fill_invalid_normals(float4* nrm, int* kcount, int begin, int en
 
 }  // namespace
 
-int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsigned char* done) {
+int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsigned char* done, int hist_max_nn) {
   if (!ctx->have_grid) return fail(ctx, CAB_ERR_STATE, "cab_normals: build the grid first");
   if (!(r > 0.f) || r > ctx->cell * 1.0000001f)
     return fail(ctx, CAB_ERR_ARG, "cab_normals: radius %g exceeds the grid cell %g", (double)r, (double)ctx->cell);
@@ -261,6 +311,20 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsi
   a.stats = (unsigned long long*)ctx->b_stats.p;
   // a slab's packet range lives on the device: launch the full persistent grid, surplus warps leave at once
   const int np = a.range ? std::max(1, (int)std::min<int64_t>(ctx->n_sorted, INT_MAX)) : a.p1 - a.p0;
+  // The truncated fast RSD pass of the same call (cab_step_normals_rsd, cab_normals_rsd: one radius, normals untruncated,
+  // RSD with max_nn) needs the d2 histogram of exactly these neighbourhoods: this traversal takes it along instead of a
+  // traversal of its own (cab_topk.cu run_nn_hist then only settles the flagged packets).
+  const bool with_hist = hist_max_nn > 0 && !use_thr && !ctx->cfg.exact && !ctx->slab && done == nullptr && np > 0;
+  ctx->trunc_hist_valid = false;
+  if (with_hist) {
+    if (int rc = reserve(ctx, ctx->b_thr_idx, (size_t)std::max(n, 1) * sizeof(int))) return rc;
+    if (int rc = reserve(ctx, ctx->b_thr_flag, 2 * (size_t)np + 32)) return rc;
+    CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_thr_flag.p, 0, 2 * (size_t)np, st));
+    a.code = (int*)ctx->b_thr_idx.p;
+    a.flag = (unsigned char*)ctx->b_thr_flag.p;
+    a.hist_max_nn = hist_max_nn;
+    a.hist_scale = (float)kTruncBins / a.r2;
+  }
   if (np > 0 && ctx->n_sorted > 0) {
     const dim3 blk(kWarpsPerBlock * kWarp);
     auto grid_for = [&](const void* fn) {
@@ -271,6 +335,14 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsi
     if (ctx->cfg.exact && use_thr) normals_kernel<true, true><<<grid_for((const void*)normals_kernel<true, true>), blk, 0, st>>>(a);
     else if (ctx->cfg.exact) normals_kernel<true, false><<<grid_for((const void*)normals_kernel<true, false>), blk, 0, st>>>(a);
     else if (use_thr) normals_kernel<false, true><<<grid_for((const void*)normals_kernel<false, true>), blk, 0, st>>>(a);
+    else if (with_hist) {
+      const size_t hsmem = (size_t)kWarpsPerBlock * (kTruncBins + 1) * kWarp * sizeof(unsigned);
+      CAB_CUDA(ctx, cudaFuncSetAttribute(normals_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+      int per_sm = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, normals_kernel<false, false, true>, kWarpsPerBlock * kWarp, hsmem);
+      const unsigned grid = (unsigned)std::min<long long>((long long)std::max(per_sm, 1) * ctx->sm_count, (np + kWarpsPerBlock - 1) / kWarpsPerBlock);
+      normals_kernel<false, false, true><<<grid, blk, hsmem, st>>>(a);
+    }
     else normals_kernel<false, false><<<grid_for((const void*)normals_kernel<false, false>), blk, 0, st>>>(a);
     CAB_LAUNCH_CHECK(ctx);
   }
@@ -284,6 +356,8 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsi
   ctx->have_normals = true;
   ctx->kcount_valid = !use_thr && done == nullptr;  // every query of this context's range counted, nothing truncated
   ctx->kcount_r = r;
+  ctx->trunc_hist_valid = with_hist;
+  ctx->trunc_hist_max_nn = hist_max_nn;
   if (ctx->defer_sync) return CAB_OK;
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
   return finish_pass_stats(ctx, 0);

@@ -278,15 +278,17 @@ struct alignas(16) FastTile {
   int run_cum[12];
 };
 
-// Truncated pass (kTrunc): v = d2 * trunc_scale is the candidate's place in the 64-bin histogram of nn_hist_kernel (same
-// expression, same bits).  Below the query's target bin (v < t1f) a neighbour is kept outright; inside it (t1f <= v <
-// t1hi) it goes to the lane's list `lst` (entry e: d2 at lst[2e * 32], sorted index at lst[(2e + 1) * 32]) and is settled
-// after the traversal; beyond it it is dropped.  A query that keeps everything has t1f = +inf.
+// Truncated pass (kTrunc).  A candidate's place in the 64-bin histogram of nn_hist_kernel is min(int(d2 * trunc_scale), 63);
+// the query's target bin t1 holds neighbour number max_nn + 1.  Both edges of that bin are turned into exact fp32 d2
+// cut-offs once per query (bin_edge below: the smallest d2 whose product reaches the bin -- the comparison against it
+// decides exactly what the product would), so that the loop is the untruncated loop with the radius test d2 <= r2 replaced
+// by d2 < cut (a neighbour below the target bin is kept outright), plus one bit per candidate of the target bin
+// (cut <= d2 < hi) in `tmask`: the caller lists those few candidates after the chunk and settles them after the
+// traversal.  Beyond the bin a candidate is dropped.  A query that keeps everything has cut = hi = nextafter(r2).
 template <bool kSelf, bool kCount, bool kTrunc>
 __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float qy, float qz, float nqx, float nqy, float nqz,
                                           float r2, float bscale, unsigned thr_addr, unsigned spare_off, unsigned bins_addr,
-                                          int sb, float tscale = 0.f, float t1f = 0.f, float t1hi = 0.f, float* lst = nullptr,
-                                          int* lcnt = nullptr) {
+                                          int sb, float hi, unsigned& tmask) {
   const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
   const f32x2 nqx2 = pack2(nqx, nqx), nqy2 = pack2(nqy, nqy), nqz2 = pack2(nqz, nqz);
   const float4* tx = reinterpret_cast<const float4*>(tile->x);
@@ -296,10 +298,13 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
   const float4* tny = reinterpret_cast<const float4*>(tile->ny);
   const float4* tnz = reinterpret_cast<const float4*>(tile->nz);
   int k = 0;
+  unsigned tm = 0;  // kTrunc: this chunk's candidates of the target bin
   // One group of four candidates: everything up to the bin address is plain arithmetic on independent chains (the
   // compiler interleaves them); only the two reductions and the count sit under the hit predicate.  No "memory" clobber
   // on the reductions: the warp barriers around the chunk order them against the plain accesses of the bins.
-#pragma unroll
+  // (the truncated variant is unrolled half as far: its body is longer, and fully unrolled the kernel's hot code no longer
+  // fits the instruction cache -- ncu showed 3 issue slots in 10 waiting for instructions)
+#pragma unroll(kTrunc ? 4 : 8)
   for (int g4 = 0; g4 < kWarp / 4; ++g4) {
     const float4 X = tx[g4], Y = ty[g4], Z = tz[g4];
     const float4 NX = tnx[g4], NY = tny[g4], NZ = tnz[g4];
@@ -338,31 +343,45 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
       // (ptxas turns a predicated shared-memory reduction into a branch around it, so the reductions below are
       // unconditional and the misses go to the spare row.)
       if (kTrunc) {
-        const float v = d2[i] * tscale;
-        if (d2[i] <= r2 && !(v < t1f) && v < t1hi) {  // the target bin: listed, the query itself included (it is one of the max_nn)
-          const int c = *lcnt;
-          if (c < kTruncCap) {
-            lst[(2 * c) * kWarp] = d2[i];
-            reinterpret_cast<int*>(lst)[(2 * c + 1) * kWarp] = tile->idx[4 * g4 + i];
-          }
-          *lcnt = c + 1;
+        // r2 holds the query's cut: "d2 < cut" keeps the candidate; cut <= d2 < hi marks it in the chunk's target mask
+        asm("{\n\t.reg .pred q;\n\t"
+            "setp.ge.f32 q, %1, %2;\n\t"
+            "setp.lt.and.f32 q, %1, %3, q;\n\t"
+            "@q or.b32 %0, %0, %4;\n\t}"
+            : "+r"(tm)
+            : "f"(d2[i]), "f"(r2), "f"(hi), "r"(1u << (4 * g4 + i)));
+        if (kSelf) {
+          asm("{\n\t.reg .pred p, g, s;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
+              "cvt.rzi.u8.f32 be, %2;\n\t"
+              "mad.lo.u32 ta, be, 4, %5;\n\t"
+              "ld.shared.f32 t, [ta+4];\n\t"
+              "setp.ne.s32 s, %8, %9;\n\t"
+              "setp.lt.and.f32 p, %3, %4, s;\n\t"
+              "setp.ge.and.f32 g, %3, t, p;\n\t"
+              "shl.b32 rb, be, 8;\n\t"
+              "selp.u32 rb, rb, %6, p;\n\t"
+              "selp.u32 go, 256, 0, g;\n\t"
+              "add.u32 rb, rb, go;\n\t"
+              "add.u32 %0, rb, %7;\n\t"
+              "@p add.s32 %1, %1, 1;\n\t}"
+              : "=r"(addr[i]), "+r"(k)
+              : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr), "r"(4 * g4 + i), "r"(sb));
+        } else {  // no query of the packet among this chunk's candidates
+          asm("{\n\t.reg .pred p, g;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
+              "cvt.rzi.u8.f32 be, %2;\n\t"
+              "mad.lo.u32 ta, be, 4, %5;\n\t"
+              "ld.shared.f32 t, [ta+4];\n\t"
+              "setp.lt.f32 p, %3, %4;\n\t"
+              "setp.ge.and.f32 g, %3, t, p;\n\t"
+              "shl.b32 rb, be, 8;\n\t"
+              "selp.u32 rb, rb, %6, p;\n\t"
+              "selp.u32 go, 256, 0, g;\n\t"
+              "add.u32 rb, rb, go;\n\t"
+              "add.u32 %0, rb, %7;\n\t"
+              "@p add.s32 %1, %1, 1;\n\t}"
+              : "=r"(addr[i]), "+r"(k)
+              : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr));
         }
-        asm("{\n\t.reg .pred p, g, s;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
-            "cvt.rzi.u8.f32 be, %2;\n\t"
-            "mad.lo.u32 ta, be, 4, %5;\n\t"
-            "ld.shared.f32 t, [ta+4];\n\t"
-            "setp.ne.s32 s, %8, %9;\n\t"
-            "setp.le.and.f32 p, %3, %4, s;\n\t"
-            "setp.lt.and.f32 p, %10, %11, p;\n\t"
-            "setp.ge.and.f32 g, %3, t, p;\n\t"
-            "shl.b32 rb, be, 8;\n\t"
-            "selp.u32 rb, rb, %6, p;\n\t"
-            "selp.u32 go, 256, 0, g;\n\t"
-            "add.u32 rb, rb, go;\n\t"
-            "add.u32 %0, rb, %7;\n\t"
-            "@p add.s32 %1, %1, 1;\n\t}"
-            : "=r"(addr[i]), "+r"(k)
-            : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr), "r"(4 * g4 + i), "r"(sb), "f"(v), "f"(t1f));
       } else if (kSelf) {
         asm("{\n\t.reg .pred p, g, s;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
             "cvt.rzi.u8.f32 be, %2;\n\t"
@@ -416,7 +435,47 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
       asm volatile("red.shared.max.u32 [%0+128], %1;" ::"r"(addr[i]), "r"(ua[i]));
     }
   }
+  if (kTrunc) tmask = tm;
   return k;
+}
+
+// Truncated pass, a chunk that holds a candidate without a finite normal (rare: a point with fewer than three
+// neighbours).  Such a candidate is a neighbour like any other -- it counts towards max_nn and may sit in the target bin
+// -- but forms no pair (radius_estimation.cpp:158-172 never sees a normal it could use).  The predicated loop above has no
+// room for that rule, so the chunk is walked candidate by candidate with the rules spelled out; same bins, same list.
+__device__ __forceinline__ int trunc_slow_chunk(const FastTile* tile, float qx, float qy, float qz, float nqx, float nqy, float nqz,
+                                                 float cut, float hi, const float* thr, int ndiv, unsigned* my_min, unsigned* my_max,
+                                                 int sb, unsigned& tmask) {
+  int k = 0;
+  unsigned tm = 0;
+  for (int m = 0; m < kWarp; ++m) {
+    const float d2 = d2_rule(tile->x[m], tile->y[m], tile->z[m], qx, qy, qz);
+    if (!(d2 < cut)) {
+      if (d2 < hi) tm |= 1u << m;  // the target bin: listed by the caller, the query itself included
+      continue;
+    }
+    if (m == sb) continue;  // the query itself: counted by the caller
+    ++k;
+    const float nx = tile->nx[m], ny = tile->ny[m], nz = tile->nz[m];
+    if (!(isfinite(nx) && isfinite(ny) && isfinite(nz))) continue;
+    const float cs = __fadd_rn(__fadd_rn(__fmul_rn(nqx, nx), __fmul_rn(nqy, ny)), __fmul_rn(nqz, nz));
+    const unsigned ua = __float_as_uint(fabsf(cs));
+    int b = 0;
+    while (b < ndiv - 1 && d2 >= thr[b + 1]) ++b;
+    my_min[b * 2 * kWarp] = min(my_min[b * 2 * kWarp], ua);
+    my_max[b * 2 * kWarp] = max(my_max[b * 2 * kWarp], ua);
+  }
+  tmask = tm;
+  return k;
+}
+
+// smallest fp32 d2 >= 0 whose product with `scale` (rounded to nearest, as the histogram computes it) reaches t
+__device__ __forceinline__ float bin_edge(float t, float scale) {
+  if (!(t > 0.f)) return 0.f;
+  float x = __fdiv_rn(t, scale);
+  while (x > 0.f && __fmul_rn(x, scale) >= t) x = __uint_as_float(__float_as_uint(x) - 1u);
+  while (__fmul_rn(x, scale) < t) x = __uint_as_float(__float_as_uint(x) + 1u);
+  return x;
 }
 
 template <bool kCount, bool kTrunc>
@@ -427,12 +486,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
   float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * 2 * (a.ndiv + 1) * kWarp);  // [257], +inf from ndiv on
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ndiv = a.ndiv;
-  float* lists = thr + kFastThr;  // kTrunc: [W][2 * kTruncCap][32], a lane's list of its target bin's candidates
+  int* lists = reinterpret_cast<int*>(thr + kFastThr);  // kTrunc: [W][kTruncCap][32], a lane's list of its target bin's candidates (sorted indices)
   for (int i = threadIdx.x; i < kFastThr; i += blockDim.x) thr[i] = i <= ndiv ? a.bin_thr[i] : INFINITY;
   __syncthreads();
   const GridView& g = a.g;
   FastTile* tile = &tiles[warp];
-  float* lst = lists + (size_t)warp * 2 * kTruncCap * kWarp + lane;
+  int* lst = lists + (size_t)warp * kTruncCap * kWarp + lane;
   unsigned* my_min = bins + (size_t)warp * 2 * (ndiv + 1) * kWarp + lane;  // bin b: min |cos| at my_min[b * 64], max at my_max[b * 64]
   unsigned* my_max = my_min + kWarp;
   const unsigned bins_addr = smem_u32(my_min), thr_addr = smem_u32(thr);
@@ -446,6 +505,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
     if (kTrunc && a.skip && a.skip[pid - a.p0]) continue;  // left to the exact-threshold path
     // the packet and its candidate runs (load_packet works on a ChunkTile; the run tables sit at the same place here)
     PacketCtx pc;
+    float cut = 0.f, hi = 0.f;  // kTrunc
+    int need = 0;
     {
       const Packet pk = g.packets[pid];
       const Domain dm = g.domains[pk.domain];
@@ -455,7 +516,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       pc.qi = pk.start + min(lane, pk.count - 1);
       pc.q = g.pos[pc.qi];
       const float xmin = warp_min(pc.q.x), xmax = warp_max(pc.q.x);
-      const float rc = a.r * 1.00001f;
+      float rc = a.r * 1.00001f;
+      if (kTrunc) {
+        // the query's target bin of the d2 histogram as two exact d2 cut-offs (see fast_chunk), and how many of that
+        // bin's candidates are kept
+        const int code = a.trunc_code[pc.qi];
+        const int t1 = code & 255;
+        need = code >> 8;
+        const float r2n = __uint_as_float(__float_as_uint(a.r2) + 1u);  // d2 < r2n is d2 <= r2
+        if (t1 == 255) {
+          cut = hi = r2n;
+        } else {
+          cut = bin_edge((float)t1, a.trunc_scale);
+          hi = t1 == kTruncBins - 1 ? r2n : fminf(bin_edge((float)(t1 + 1), a.trunc_scale), r2n);
+        }
+        // no query of the packet keeps a neighbour at or beyond `hi`: the candidate runs are trimmed to the largest such
+        // distance instead of the radius
+        rc = fminf(rc, sqrtf(warp_max(hi)) * 1.00001f);
+      }
       const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
       const int cxlo = max((xfine_coord(xmin, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift) - 1, 0);
       const int cxhi = min((xfine_coord(xmax, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift) + 1, dm.nx - 1);
@@ -506,18 +584,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       my_max[0] = 0x3f800000u;
     }
     int k = 0;
-    // truncated pass: the query's target bin of the d2 histogram and how many of that bin's candidates are kept
-    int lcnt = 0, need = 0;
-    float t1f = INFINITY, t1hi = INFINITY;
-    if (kTrunc) {
-      const int code = a.trunc_code[pc.qi];
-      const int t1 = code & 255;
-      need = code >> 8;
-      if (t1 != 255) {
-        t1f = (float)t1;
-        t1hi = t1 == kTruncBins - 1 ? INFINITY : t1f + 1.f;
-      }
-    }
+    int lcnt = 0;  // truncated pass: candidates of the target bin listed so far
     const int nchunks = (pc.total + kWarp - 1) / kWarp;
 #pragma unroll 1
     for (int c0 = 0; c0 < nchunks; ++c0) {
@@ -537,7 +604,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       const int own = j - pc.start;
       const bool is_own = valid && own >= 0 && own < pc.count;
       __syncwarp();
-      tile->x[lane] = (valid && finite_n) ? c.x : 3.0e30f;  // a candidate without a normal never contributes
+      // a candidate without a normal never contributes: staged far away -- except in the truncated pass, where it still
+      // counts towards max_nn (its chunk takes the spelled-out path below)
+      tile->x[lane] = (valid && (finite_n || kTrunc)) ? c.x : 3.0e30f;
       tile->y[lane] = c.y;
       tile->z[lane] = c.z;
       tile->nx[lane] = cn.x;
@@ -554,16 +623,27 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       __syncwarp();
       if (kTrunc) {
         const int sb = own_mask ? tile->self_slot[lane] : -1;
-        k += fast_chunk<true, true, true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, sb,
-                                          a.trunc_scale, t1f, t1hi, lst, &lcnt);
-        k += (sb >= 0 && t1f > 0.f) ? 1 : 0;  // the query itself, unless it sits in the target bin (then the list has it)
+        unsigned tmask = 0;
+        if (odd_mask)
+          k += trunc_slow_chunk(tile, qx, qy, qz, nq.x, nq.y, nq.z, cut, hi, thr, ndiv, my_min, my_max, sb, tmask);
+        else  // one body for chunks with and without queries of the packet (sb = -1 matches no slot): half the code
+          k += fast_chunk<true, true, true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, cut, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, sb, hi, tmask);
+        k += (sb >= 0 && cut > 0.f) ? 1 : 0;  // the query itself, unless it sits in the target bin (then the list has it)
+        while (tmask) {  // the chunk's candidates of the target bin (a handful per query and traversal): listed for the settlement
+          const int m = __ffs(tmask) - 1;
+          tmask &= tmask - 1;
+          if (lcnt < kTruncCap) lst[lcnt * kWarp] = tile->idx[m];
+          ++lcnt;
+        }
       } else if (own_mask) {
-        k += fast_chunk<true, true, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, tile->self_slot[lane]);
+        unsigned dummy_mask;
+        k += fast_chunk<true, true, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, tile->self_slot[lane], 0.f, dummy_mask);
         k += tile->self_slot[lane] >= 0 ? 1 : 0;  // the query itself is a neighbour of the radius search (:120), just not a pair (:150)
       } else {
-        k += fast_chunk<false, kCount, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, -1);
+        unsigned dummy_mask;
+        k += fast_chunk<false, kCount, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, -1, 0.f, dummy_mask);
       }
-      if (odd_mask) {  // rare: neighbours without a normal still count as neighbours
+      if (!kTrunc && odd_mask) {  // rare: neighbours without a normal still count as neighbours
         unsigned mm = odd_mask;
         while (mm) {
           const int m = __ffs(mm) - 1;
@@ -580,20 +660,32 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       // The target bin: keep the `need` smallest (d2, input index) of its candidates (the rule of the radius search with
       // max_nn, radius_estimation.cpp:120); the query itself counts among them but forms no pair (:150).
       const int L = min(lcnt, kTruncCap);
-      const int* lj = reinterpret_cast<const int*>(lst);
+      // the candidates' d2 (the bits the traversal saw): recomputed once each into the warp's tile, whose eight rows the
+      // traversal no longer needs; entries beyond the eighth (rare) are recomputed where they are used
+      float* scratch = reinterpret_cast<float*>(tile) + lane;
+      auto d2_of = [&](int e) {
+        if (e < 8) return scratch[e * kWarp];
+        const float4 pe = g.pos[lst[e * kWarp]];
+        return d2_rule(pe.x, pe.y, pe.z, qx, qy, qz);
+      };
+      for (int e = 0; e < min(L, 8); ++e) {
+        const float4 pe = g.pos[lst[e * kWarp]];
+        scratch[e * kWarp] = d2_rule(pe.x, pe.y, pe.z, qx, qy, qz);
+      }
       for (int e = 0; e < L; ++e) {
-        const float de = lst[(2 * e) * kWarp];
-        const int je = lj[(2 * e + 1) * kWarp];
+        const int je = lst[e * kWarp];
+        const float de = d2_of(e);
         int rank = 0;
         for (int f = 0; f < L; ++f) {
-          const float df = lst[(2 * f) * kWarp];
+          const float df = d2_of(f);
           if (df < de) ++rank;
-          else if (df == de && f != e && g.perm[lj[(2 * f + 1) * kWarp]] < g.perm[je]) ++rank;
+          else if (df == de && f != e && g.perm[lst[f * kWarp]] < g.perm[je]) ++rank;
         }
         if (rank >= need) continue;
         ++k;
         if (je == pc.qi) continue;
-        const float4 cn = a.nrm[je];  // finite: packets with a candidate lacking a normal never take this path
+        const float4 cn = a.nrm[je];
+        if (!(isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z))) continue;  // a neighbour, but no pair
         const float cs = __fadd_rn(__fadd_rn(__fmul_rn(nq.x, cn.x), __fmul_rn(nq.y, cn.y)), __fmul_rn(nq.z, cn.z));
         const unsigned ua = __float_as_uint(fabsf(cs));
         int b = 0;
@@ -760,7 +852,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
     if (!ctx->cfg.exact && (!use_thr || trunc_fast) && !legacy) {
       const size_t fsmem = (size_t)kWarpsPerBlock * sizeof(FastTile) + (size_t)kWarpsPerBlock * 2 * (ndiv + 1) * kWarp * sizeof(unsigned) +
                            (size_t)kFastThr * sizeof(float) + 256 +
-                           (trunc_fast ? (size_t)kWarpsPerBlock * 2 * kTruncCap * kWarp * sizeof(float) : 0);
+                           (trunc_fast ? (size_t)kWarpsPerBlock * kTruncCap * kWarp * sizeof(int) : 0);
       // neighbour counts kept by the last normals pass are this pass's counts if radius and rule were the same
       const bool counted = !trunc_fast && ctx->kcount_r == rf && ctx->kcount_valid;
       a.kcount = counted ? (const int*)ctx->b_kcount.p : nullptr;
@@ -773,6 +865,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
       CAB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       int per_sm = 1;
       CAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * kWarp, fsmem));
+      if (const char* g3 = std::getenv("CAB_FAST_PER_SM")) per_sm = std::min(per_sm, std::atoi(g3));
       const unsigned grid = std::min<unsigned>(blocks, (unsigned)std::max(per_sm, 1) * ctx->sm_count);
       kernel<<<grid, kWarpsPerBlock * kWarp, fsmem, ks>>>(a);
       CAB_LAUNCH_CHECK(ctx);

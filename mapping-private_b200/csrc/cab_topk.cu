@@ -235,8 +235,9 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) value_select_kernel(const T
 // Per query it leaves the bin that holds the max_nn-th neighbour and how many of that bin's candidates are still kept
 // (code = bin | kept << 8; bin 255: the query has at most max_nn neighbours, all are kept).  The RSD traversal then
 // accepts every candidate below the bin outright and settles the bin's few candidates from a short list, so the
-// truncation costs one extra traversal instead of two plus a slower RSD kernel.  Packets in which some query's bin
-// holds more candidates than the list takes are flagged and go through the exact-threshold path.
+// truncation costs one extra traversal instead of two plus a slower RSD kernel -- or none at all when the normals pass of
+// the same call took the histogram along (cab_normals.cu, kHist).  Packets in which some query's bin holds more
+// candidates than the list takes are flagged and go through the exact-threshold path.
 __global__ void __launch_bounds__(kSelWarps * kWarp) nn_hist_kernel(const ThrArgs a) {
   __shared__ ChunkTile tiles[kSelWarps];
   __shared__ unsigned hist[kSelWarps][kSelBins + 1][kWarp];  // row kSelBins: everything beyond the radius
@@ -252,12 +253,7 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) nn_hist_kernel(const ThrArg
     const PacketCtx pc = load_packet(g, pid, lane, a.r, tile);
     const float qx = pc.q.x, qy = pc.q.y, qz = pc.q.z;
     for (int b = 0; b <= kSelBins; ++b) hist[warp][b][lane] = 0;
-    bool odd = false;  // a candidate without a finite normal: it takes part in the truncation but the fast RSD pass never sees it
-    for_each_chunk(g, pc, lane, tile, [&](int cnt, const float4&, int j, bool valid) {
-      if (valid) {
-        const float4 cn = a.nrm[j];
-        odd = odd || !(isfinite(cn.x) && isfinite(cn.y) && isfinite(cn.z));
-      }
+    for_each_chunk(g, pc, lane, tile, [&](int cnt, const float4&, int, bool) {
       for_each_staged_d2(tile, cnt, qx, qy, qz, [&](int, float d2) {
         const int row = d2 <= r2 ? min(__float2int_rz(d2 * scale1), kSelBins - 1) : kSelBins;
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(col + 128u * (unsigned)row) : "memory");
@@ -275,7 +271,7 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) nn_hist_kernel(const ThrArg
       k += c;
     }
     // bin: holds neighbour number max_nn + 1, so at least one of its candidates is dropped; kept = max_nn - before of them
-    const bool over = odd || (pc.active && bin != 255 && in_bin > kTruncCap);
+    const bool over = pc.active && bin != 255 && in_bin > kTruncCap;
     if (pc.active) a.code[pc.qi] = bin == 255 ? 255 : (bin | ((a.max_nn - before) << 8));
     if (__any_sync(kFull, over) && lane == 0) a.fallback[pid - a.p0] = 1;
     __syncwarp();
@@ -430,14 +426,19 @@ int run_nn_hist(cab_ctx* ctx, float r, int max_nn) {
   if (int rc = reserve(ctx, ctx->b_thr_flag, 2 * (size_t)np + 32)) return rc;
   unsigned char* flag_a = (unsigned char*)ctx->b_thr_flag.p;  // packets that leave the fast path
   unsigned char* flag_b = flag_a + np;                        // of those: packets that need the radix select
-  CAB_CUDA(ctx, cudaMemsetAsync(flag_a, 0, 2 * (size_t)np, st));
-  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, kStatBytes, st));
-  a.fallback = flag_a;
-  int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn_hist_kernel, kSelWarps * kWarp, 0);
-  const unsigned grid = (unsigned)std::min<long long>((long long)std::max(per_sm, 1) * ctx->sm_count, (np + kSelWarps - 1) / kSelWarps);
-  nn_hist_kernel<<<grid, kSelWarps * kWarp, 0, st>>>(a);
-  CAB_LAUNCH_CHECK(ctx);
+  // the normals pass of this call may have taken the histogram along (same grid, radius and max_nn): codes and flags are in place
+  const bool have = ctx->trunc_hist_valid && !ctx->slab && ctx->kcount_r == r && ctx->trunc_hist_max_nn == max_nn;
+  if (!have) {
+    CAB_CUDA(ctx, cudaMemsetAsync(flag_a, 0, 2 * (size_t)np, st));
+    CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_stats.p, 0, kStatBytes, st));
+    a.fallback = flag_a;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn_hist_kernel, kSelWarps * kWarp, 0);
+    const unsigned grid = (unsigned)std::min<long long>((long long)std::max(per_sm, 1) * ctx->sm_count, (np + kSelWarps - 1) / kSelWarps);
+    nn_hist_kernel<<<grid, kSelWarps * kWarp, 0, st>>>(a);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  ctx->trunc_hist_valid = false;  // the thresholds of the flagged packets are about to overwrite their codes
   // exact (d2, index) thresholds for the flagged packets only
   a.only = flag_a;
   a.fallback = flag_b;

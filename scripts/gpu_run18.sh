@@ -1,0 +1,19 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 400 python bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r18_bench_n8.json 2> gpurun_out/r18_bench_n8.err; echo "rc $?" >> gpurun_out/r18_bench_n8.err
+CAB_NO_FEEDBACK=1 timeout 400 python bench.py --gpus 8 --steps 20 --warmup 5 --no-e2e > gpurun_out/r18_bench_n8_nofb.json 2> gpurun_out/r18_bench_n8_nofb.err; echo "rc $?" >> gpurun_out/r18_bench_n8_nofb.err
+timeout 400 python bench.py --gpus 4 --steps 20 --warmup 5 --no-e2e > gpurun_out/r18_bench_n4.json 2> gpurun_out/r18_bench_n4.err; echo "rc $?" >> gpurun_out/r18_bench_n4.err
+timeout 400 python bench.py --gpus 2 --steps 20 --warmup 5 --no-e2e > gpurun_out/r18_bench_n2.json 2> gpurun_out/r18_bench_n2.err; echo "rc $?" >> gpurun_out/r18_bench_n2.err
+timeout 300 python -m pytest tests/test_comm.py -x -q -m gpu > gpurun_out/r18_pytest_comm.log 2>&1; tail -3 gpurun_out/r18_pytest_comm.log
+tail -3 gpurun_out/r18_bench_n8.err; for f in gpurun_out/r18_bench_n8.json gpurun_out/r18_bench_n8_nofb.json gpurun_out/r18_bench_n4.json gpurun_out/r18_bench_n2.json; do python - "$f" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], d['n_gpus'], 'ms/step', round(d['ms_per_step'],3), 'value', d['value'])
+    for r in d['per_rank_phase_ms']: print('   ', {k:(round(v,3) if isinstance(v,float) else v) for k,v in r.items()})
+    if d.get('e2e'): print('   e2e', d['e2e']['ms_per_step'], d['e2e']['stages_ms_rank0'], d['e2e'].get('shared_host_array'))
+    print('   concat', d.get('results_concatenated'))
+except Exception as e: print(sys.argv[1], 'ERR', e)
+PY
+done

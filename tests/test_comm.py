@@ -54,6 +54,33 @@ def test_step_equals_the_three_stages():
     c.close()
 
 
+@pytest.mark.parametrize("max_nn", [60, 150])
+def test_step_with_truncated_rsd(max_nn):
+    """Normals unlimited, RSD truncated at max_nn (the plugin defaults, radius_estimation.h:82): in one call the normals
+    traversal takes the d2 histogram of the truncation along; same bits as the three stages, whose RSD pass builds the
+    histogram in a traversal of its own.  Pairs of stray points (two neighbours: no normal) sit next to the table: they
+    count towards max_nn but form no pair."""
+    pts = synth.analytic_shape("plane", 8_000, side=0.2)  # ~250 neighbours per query: the truncation is active everywhere
+    rng = np.random.default_rng(5)
+    # a stray point 19.99 mm off the plane sees the point below it and hardly anything else (0.6 mm around its foot)
+    stray = pts[rng.choice(pts.shape[0], 40, replace=False)] + np.float32([0.0, 0.0, 0.01999])
+    pts = np.concatenate([pts, stray]).astype(np.float32)
+    pts[11] = np.nan
+    c = cab.Context(0)
+    c.upload(pts)
+    c.build_grid(R)
+    n4 = c.normals(R)
+    rmin, rmax = c.rsd(R, max_nn=max_nn)
+    k = c.profile()["neighbour_sum"]
+    assert np.isnan(n4[-40:, 0]).sum() > 0  # some stray pairs really have no normal
+    for _ in range(2):
+        c.step_normals_rsd(R, R, max_nn_rsd=max_nn)
+        s4, smin, smax = c.download()
+        assert _same(s4, n4) and _same(smin, rmin) and _same(smax, rmax)
+        assert c.profile()["neighbour_sum"] == k
+    c.close()
+
+
 @pytest.mark.parametrize("world,max_nn", [(3, 0), (2, 60)])
 def test_local_group_every_rank_holds_all_results(world, max_nn):
     """Three contexts of this process on one GPU: after the step EVERY rank's concatenated arrays hold the single-GPU
