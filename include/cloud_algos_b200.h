@@ -177,6 +177,27 @@ int64_t cab_grsd_voxels(cab_ctx* ctx, int64_t* vox_offsets, float* centroids_xyz
 int64_t cab_grsd_signatures(cab_ctx* ctx, int32_t kind, int32_t subdivision_size, int32_t off_x, int32_t off_y,
                             int32_t off_z, int64_t* hist_offsets, int32_t* subdiv_b, int32_t* hist, int64_t cap);
 
+/* GRSD of ONE large cloud -- the cloud of cab_upload_cloud / cab_set_cloud_device / cab_comm_upload_cloud --, the
+ * getVoxelGrid + computeGRSD + extractGRSDSignature21 chain of grsd_colorCHLAC_tools.hpp:64-294 on a single cluster, and
+ * its multi-GPU form: on a sharded context (cab_set_shard / a group) every rank voxelises the whole cloud
+ * (cheap, replicated) but computes normals for its slab of rows and the RSD radii + surface-type labels of the voxels
+ * whose centroid lies in its own rows; the ranks' labels are merged (every voxel has exactly one owner: the sum of
+ * label + 1 | 0), every rank counts the neighbour transitions of its own voxels, and one small int32 all-reduce sums the
+ * 6 x 6 transition matrices (their integer sums are order independent: bit-exact against one GPU).
+ *   cab_grsd_cloud             all of it in a group (cab_comm_init*: the two merges are cab_comm_allreduce_i32) or on an
+ *                              unsharded context; hist21 = the whole cloud's GRSD-21 on every rank.  Afterwards
+ *                              cab_grsd_signatures (GRSD-21 with subdivisions, GRSD-325) works the same way: own voxels,
+ *                              then the all-reduce of the hist_num x dim counts.  PlusGRSD is not available on a
+ *                              sharded cloud (it needs the normals of every point of a voxel).
+ *   cab_grsd_cloud_labels      step 1 alone: returns the number of voxels; labels_plus1[v] = label + 1 for this rank's
+ *   cab_grsd_cloud_set_labels  voxels, 0 otherwise.  The application merges (sums) the ranks' arrays by its own means,
+ *                              gives the merged labels back, and sums the partial histograms of cab_grsd_signatures. */
+int64_t cab_grsd_cloud_labels(cab_ctx* ctx, float leaf, float r_normals, double rsd_radius_min, int32_t rsd_flags,
+                              const float vp[3], int32_t* labels_plus1, int64_t cap);
+int cab_grsd_cloud_set_labels(cab_ctx* ctx, const int32_t* labels_plus1, int64_t count);
+int cab_grsd_cloud(cab_ctx* ctx, float leaf, float r_normals, double rsd_radius_min, int32_t rsd_flags, const float vp[3],
+                   int32_t* hist21);
+
 /* The colour half of VOSCH (extractVOSCH, grsd_colorCHLAC_tools.hpp:832-843: the 20 GRSD-21 bins followed by 117 colour
  * bins): rotation-invariant C3-HLAC (c3 = 1, pcl::C3HLAC_RI_Estimation, extractC3HLACSignature117 :787-812) or Color-CHLAC
  * (c3 = 0, pcl::ColorCHLAC_RI_Estimation, the variant the reference's shipped *_GRSD_CCHLAC.pcd vectors were made with),

@@ -32,7 +32,7 @@ EXPORTS = [
     "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_download_rdif", "cab_profile", "cab_version",
     "cab_step_normals_rsd", "cab_comm_get_id", "cab_comm_init", "cab_comm_init_local", "cab_comm_reserve", "cab_comm_connect",
     "cab_comm_free", "cab_comm_upload_cloud", "cab_comm_download_range", "cab_comm_device_ptr", "cab_comm_allreduce_i32",
-    "cab_comm_set_layout", "cab_comm_set_feedback",
+    "cab_comm_set_layout", "cab_comm_set_feedback", "cab_grsd_cloud", "cab_grsd_cloud_labels", "cab_grsd_cloud_set_labels",
 ]
 COMM_ID_BYTES, COMM_BLOB_BYTES = 128, 512
 
@@ -79,6 +79,7 @@ def lib():
         L.cab_neighbors_debug.restype = C.c_int64
         L.cab_grsd_voxels.restype = C.c_int64
         L.cab_grsd_signatures.restype = C.c_int64
+        L.cab_grsd_cloud_labels.restype = C.c_int64
         L.cab_color_chlac.restype = C.c_int64
         L.cab_statistical_outliers.restype = C.c_int64
         L.cab_euclidean_clusters.restype = C.c_int64
@@ -247,6 +248,26 @@ class Context:
                                            C.c_float(leaf), C.c_float(r_normals), C.c_double(rsd_radius_min),
                                            C.c_int32(rsd_flags), _fp(v), _fp(nx), _fp(ny), _fp(nz), _ip(hist)), "cab_grsd_batch")
         return hist
+
+    def grsd_cloud(self, leaf: float, r_normals: float = 0.02, rsd_radius_min: float = 0.01, rsd_flags: int = 0, vp=(0.0, 0.0, 0.0)):
+        """GRSD-21 of the one cloud this context holds; in a group: sharded by rows, labels and histogram merged (21 int32)."""
+        hist = np.zeros(21, np.int32)
+        v = np.asarray(vp, dtype=np.float32)
+        self._check(self._L.cab_grsd_cloud(self._h, C.c_float(leaf), C.c_float(r_normals), C.c_double(rsd_radius_min),
+                                           C.c_int32(rsd_flags), _fp(v), _ip(hist)), "cab_grsd_cloud")
+        return hist
+
+    def grsd_cloud_labels(self, leaf: float, r_normals: float = 0.02, rsd_radius_min: float = 0.01, rsd_flags: int = 0,
+                          vp=(0.0, 0.0, 0.0)):
+        """Step 1 of grsd_cloud alone: label + 1 of this rank's voxels, 0 for the others."""
+        v = np.asarray(vp, dtype=np.float32)
+        args = (self._h, C.c_float(leaf), C.c_float(r_normals), C.c_double(rsd_radius_min), C.c_int32(rsd_flags), _fp(v))
+        self._check(self._L.cab_grsd_cloud_labels(*args, None, C.c_int64(0)), "cab_grsd_cloud_labels")
+        return self.grsd_voxels(1)["labels"] + 1  # the voxels of the other ranks carry label -1
+
+    def grsd_cloud_set_labels(self, labels_plus1: np.ndarray):
+        lab = np.ascontiguousarray(labels_plus1, np.int32)
+        self._check(self._L.cab_grsd_cloud_set_labels(self._h, _ip(lab), C.c_int64(lab.size)), "cab_grsd_cloud_set_labels")
 
     def grsd_voxels(self, nclusters: int):
         off = np.zeros(nclusters + 1, np.int64)

@@ -310,7 +310,7 @@ void cab_destroy(cab_ctx* ctx) {
                     &ctx->b_rsd, &ctx->b_rdif, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
                     &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_slab, &ctx->b_sel, &ctx->b_stats2, &ctx->b_sorttmp, &ctx->b_occ, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
                     &ctx->g_vvals[1], &ctx->g_cent, &ctx->g_vcount, &ctx->g_vrad, &ctx->g_vlabel, &ctx->g_voff,
-                    &ctx->g_layout, &ctx->g_layoff, &ctx->g_vgrid, &ctx->g_hist, &ctx->g_vfirst, &ctx->g_cnrm, &ctx->g_invperm, &ctx->g_sig, &ctx->g_sigdom, &ctx->g_color};
+                    &ctx->g_layout, &ctx->g_layoff, &ctx->g_vgrid, &ctx->g_hist, &ctx->g_vfirst, &ctx->g_cnrm, &ctx->g_invperm, &ctx->g_sig, &ctx->g_sigdom, &ctx->g_color, &ctx->g_vown};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (DevBuf& g : ctx->graveyard) cudaFree(g.p);

@@ -112,6 +112,11 @@ struct VRsdArgs {
   float bin_thr[9];      // ndiv + 1 entries
   float2* radii;         // out r_min, r_max
   int* labels;
+  // one large cloud sharded over the ranks of a group (cab_grsd_cloud): a rank labels the voxels whose centroid lies in
+  // one of its own rows (every centroid lies in exactly one rank's rows: the cuts are the same on every rank); `own`
+  // remembers which, the other voxels get label -1 until the ranks' labels are merged
+  const SlabInfo* slab;
+  unsigned char* own;
 };
 
 // grsd_colorCHLAC_tools.hpp:104-116: fp32 radii compared against double literals
@@ -138,6 +143,21 @@ __global__ void __launch_bounds__(256) voxel_rsd_kernel(const VRsdArgs a) {
   const Domain dm = g.domains[d];
   int cy, cz;
   row_cells(dm, q.y, q.z, g.inv_cell, cy, cz);
+  if (a.own) {
+    bool mine = true;
+    if (a.slab) {
+      const int row = cz * dm.ny + cy;
+      mine = row >= a.slab->own_lo && row < a.slab->own_hi;
+    }
+    if (lane == 0) a.own[v] = mine ? 1 : 0;
+    if (!mine) {
+      if (lane == 0) {
+        a.radii[v] = make_float2(0.f, 0.f);
+        a.labels[v] = -1;
+      }
+      return;
+    }
+  }
   const int cx = xfine_coord(q.x, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift;
   const int cxlo = max(cx - 1, 0), cxhi = min(cx + 1, dm.nx - 1);
   int rb = 0, re = 0;
@@ -344,7 +364,7 @@ __global__ void __launch_bounds__(128) signature_kernel(const VoxGrid* __restric
                                                         const float4* __restrict__ cnrm, const int* __restrict__ labels,
                                                         const int* __restrict__ layout, float leaf, float inv_leaf,
                                                         int sub, float inv_sub, int off_x, int off_y, int off_z,
-                                                        int* __restrict__ out) {
+                                                        int* __restrict__ out, const unsigned char* __restrict__ own) {
   constexpr int kDim = kKind == 0 ? 21 : (kKind == 1 ? 325 : 110);
   constexpr int kOff = kKind == 1 ? 13 : 26;
   __shared__ int sh[kSigSmemInts];
@@ -362,6 +382,7 @@ __global__ void __launch_bounds__(128) signature_kernel(const VoxGrid* __restric
   const long long work = (long long)(v1 - v0) * kOff;
   for (long long w = (long long)blockIdx.y * blockDim.x + threadIdx.x; w < work; w += (long long)gridDim.y * blockDim.x) {
     const int v = v0 + (int)(w / kOff), o = (int)(w % kOff);
+    if (own && !own[v]) continue;  // a sharded cloud: the source voxels of this rank only (integer sums: the ranks' parts add up)
     const float4 c = cent[v];
     int hist_idx = 0;
     if (sub > 0) {  // :233-246: floor(x / voxel_size) - min_b - offset, fp32 division
@@ -563,7 +584,7 @@ __global__ void __launch_bounds__(128) color_chlac_kernel(const VoxGrid* __restr
 
 }  // namespace
 
-int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_t* hist21) {
+int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_t* hist21, bool labels_only) {
   const int n = (int)ctx->n, nd = ctx->n_domains;
   cudaStream_t st = ctx->stream;
   if (!(leaf > 0.f)) return fail(ctx, CAB_ERR_ARG, "cab_grsd_batch: leaf must be > 0");
@@ -677,6 +698,9 @@ int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_
     }
   ctx->g_leaf = leaf;
   ctx->g_have_cnrm = false;
+  ctx->g_own_valid = false;
+  if (labels_only)
+    if (int rc = reserve(ctx, ctx->g_vown, (size_t)std::max(nvox, 1))) return rc;
   if (int rc = reserve(ctx, ctx->g_cent, (size_t)std::max(nvox, 1) * sizeof(float4))) return rc;
   if (int rc = reserve(ctx, ctx->g_vrad, (size_t)std::max(nvox, 1) * sizeof(float2))) return rc;
   if (int rc = reserve(ctx, ctx->g_vlabel, (size_t)std::max(nvox, 1) * sizeof(int))) return rc;
@@ -707,6 +731,8 @@ int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_
     for (int b = ndiv; b < 9; ++b) a.bin_thr[b] = INFINITY;
     a.radii = (float2*)ctx->g_vrad.p;
     a.labels = (int*)ctx->g_vlabel.p;
+    a.slab = labels_only ? slab_info_device(ctx) : nullptr;  // null unless the grid is one rank's slab
+    a.own = labels_only ? (unsigned char*)ctx->g_vown.p : nullptr;
     voxel_rsd_kernel<<<blocks, 256, 0, st>>>(a);
     CAB_LAUNCH_CHECK(ctx);
   }
@@ -720,6 +746,13 @@ int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_
         off26[13 + c][k] = -off13[c][k];
       }
     CAB_CUDA(ctx, cudaMemcpyToSymbolAsync(c_off26, off26, sizeof(off26), 0, cudaMemcpyHostToDevice, st));
+  }
+  if (labels_only) {  // the transitions wait for the other ranks' labels (cab_grsd_cloud)
+    CAB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    CAB_CUDA(ctx, cudaStreamSynchronize(st));
+    CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.grsd_ms, ctx->ev[4], ctx->ev[5]));
+    ctx->g_own_valid = ctx->slab;
+    return CAB_OK;
   }
   transitions_kernel<<<nd, 128, 0, st>>>((const VoxGrid*)ctx->g_vgrid.p, (const int*)ctx->g_voff.p, (const float4*)ctx->g_cent.p,
                                          (const int*)ctx->g_vlabel.p, (const int*)ctx->g_layout.p, leaf,
@@ -768,6 +801,71 @@ int cab_grsd_batch(cab_ctx* ctx, const float* xyz, int32_t stride, const int32_t
     if (int rc = cab_normals(ctx, r_normals, 0, vp, nullptr)) return rc;
   }
   return run_grsd_batch(ctx, leaf, r_rsd, rsd_flags, hist21);
+}
+
+int64_t cab_grsd_cloud_labels(cab_ctx* ctx, float leaf, float r_normals, double rsd_radius_min, int32_t rsd_flags,
+                              const float vp[3], int32_t* labels_plus1, int64_t cap) {
+  if (!ctx) return CAB_ERR_ARG;
+  if (!ctx->have_cloud) return fail(ctx, CAB_ERR_STATE, "cab_grsd_cloud: no cloud uploaded");
+  if (ctx->n_domains != 1) return fail(ctx, CAB_ERR_STATE, "cab_grsd_cloud: works on one cloud (a batch of clusters: cab_grsd_batch)");
+  if (!(leaf > 0.f)) return fail(ctx, CAB_ERR_ARG, "cab_grsd_cloud: leaf must be > 0");
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, CAB_ERR_CUDA, "cudaSetDevice failed");
+  // grsd_colorCHLAC_tools.hpp:172: std::max(rsd_radius_search, voxel_size/2 * sqrt(3)); float/2 * double
+  const double r_rsd = std::max(rsd_radius_min, (double)(leaf / 2) * std::sqrt(3.0));
+  float cell = (float)r_rsd;
+  if ((double)cell < r_rsd) cell = std::nextafter(cell, INFINITY);
+  cell = std::max(cell, r_normals);
+  // a rank of a sharded context builds its slab of rows (own rows, one layer of halo rows whose normals it computes
+  // itself, one more layer of candidates): the points within r_rsd <= cell of a centroid in an own row all have normals
+  ctx->want_halo_exchange = false;
+  if (int rc = build_grid(ctx, cell)) return rc;
+  if (int rc = run_normals(ctx, r_normals, 0, vp)) return rc;
+  if (int rc = run_grsd_batch(ctx, leaf, r_rsd, rsd_flags, nullptr, true)) return rc;
+  const int64_t nv = ctx->g_nvox;
+  if (!labels_plus1 || nv == 0 || nv > cap) return nv;
+  std::vector<int32_t> lab((size_t)nv);
+  CAB_CUDA(ctx, cudaMemcpy(lab.data(), ctx->g_vlabel.p, (size_t)nv * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int64_t v = 0; v < nv; ++v) labels_plus1[v] = lab[(size_t)v] + 1;  // 0: not this rank's voxel
+  return nv;
+}
+
+int cab_grsd_cloud_set_labels(cab_ctx* ctx, const int32_t* labels_plus1, int64_t count) {
+  if (!ctx || !labels_plus1) return CAB_ERR_ARG;
+  if (count != ctx->g_nvox) return fail(ctx, CAB_ERR_ARG, "cab_grsd_cloud_set_labels: %lld labels for %lld voxels", (long long)count, (long long)ctx->g_nvox);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, CAB_ERR_CUDA, "cudaSetDevice failed");
+  std::vector<int32_t> lab((size_t)count);
+  for (int64_t v = 0; v < count; ++v) {
+    if (labels_plus1[v] < 1 || labels_plus1[v] > 5)
+      return fail(ctx, CAB_ERR_ARG, "cab_grsd_cloud_set_labels: voxel %lld has no label (the ranks' labels were not merged?)", (long long)v);
+    lab[(size_t)v] = labels_plus1[v] - 1;
+  }
+  if (count) CAB_CUDA(ctx, cudaMemcpy(ctx->g_vlabel.p, lab.data(), (size_t)count * sizeof(int), cudaMemcpyHostToDevice));
+  return CAB_OK;
+}
+
+int cab_grsd_cloud(cab_ctx* ctx, float leaf, float r_normals, double rsd_radius_min, int32_t rsd_flags, const float vp[3],
+                   int32_t* hist21) {
+  if (!ctx || !hist21) return CAB_ERR_ARG;
+  if (ctx->shard_world > 1 && !comm_active(ctx))
+    return fail(ctx, CAB_ERR_STATE, "cab_grsd_cloud: a sharded context outside a group -- merge the ranks' labels and histograms "
+                                    "yourself (cab_grsd_cloud_labels, cab_grsd_cloud_set_labels, cab_grsd_signatures) or join a group");
+  const int64_t nv = cab_grsd_cloud_labels(ctx, leaf, r_normals, rsd_radius_min, rsd_flags, vp, nullptr, 0);
+  if (nv < 0) return (int)nv;
+  std::memset(hist21, 0, 21 * sizeof(int32_t));
+  std::vector<int32_t> lab((size_t)nv);
+  if (nv > 0) {
+    CAB_CUDA(ctx, cudaMemcpy(lab.data(), ctx->g_vlabel.p, (size_t)nv * sizeof(int), cudaMemcpyDeviceToHost));
+    for (auto& l : lab) l += 1;
+    // every voxel was labelled by exactly one rank: the sum of the ranks' (label + 1 | 0) arrays is the cloud's labelling
+    if (comm_active(ctx))
+      if (int rc = cab_comm_allreduce_i32(ctx, lab.data(), nv)) return rc;
+    if (int rc = cab_grsd_cloud_set_labels(ctx, lab.data(), nv)) return rc;
+  } else if (comm_active(ctx)) {
+    if (int rc = cab_comm_allreduce_i32(ctx, lab.data(), 0)) return rc;
+  }
+  // GRSD-21 of the whole cloud: this rank's source voxels, then the integer all-reduce inside cab_grsd_signatures
+  const int64_t got = cab_grsd_signatures(ctx, CAB_SIG_GRSD21, 0, 0, 0, 0, nullptr, nullptr, hist21, 1);
+  return got < 0 ? (int)got : CAB_OK;
 }
 
 int64_t cab_grsd_voxels(cab_ctx* ctx, int64_t* vox_offsets, float* centroids_xyz, float* r_min, float* r_max,
@@ -839,6 +937,9 @@ int64_t cab_grsd_signatures(cab_ctx* ctx, int32_t kind, int32_t subdivision_size
   cudaStream_t st = ctx->stream;
   const int n = (int)ctx->n;
   const int nvox = (int)ctx->g_nvox;
+  if (kind == CAB_SIG_PLUSGRSD110 && ctx->g_own_valid)
+    return fail(ctx, CAB_ERR_STATE, "cab_grsd_signatures: PlusGRSD needs the normals of every point of a voxel; a sharded cloud "
+                                    "(cab_grsd_cloud on a group) holds those of its own rows only");
   if (kind == CAB_SIG_PLUSGRSD110 && !ctx->g_have_cnrm && nvox > 0) {
     if (!ctx->have_normals) return fail(ctx, CAB_ERR_STATE, "cab_grsd_signatures: no normals");
     if (int rc = reserve(ctx, ctx->g_invperm, (size_t)std::max(n, 1) * 4)) return rc;
@@ -863,12 +964,13 @@ int64_t cab_grsd_signatures(cab_ctx* ctx, int32_t kind, int32_t subdivision_size
     const unsigned slices = (unsigned)std::min<long long>(std::max<long long>(((long long)max_vox * noff + 2047) / 2048, 1), 1024);
     const dim3 grid((unsigned)nd, slices);
     const float leaf = ctx->g_leaf, inv_leaf = 1.0f / leaf;
+    const unsigned char* own_mask = ctx->g_own_valid ? (const unsigned char*)ctx->g_vown.p : nullptr;
 #define CAB_SIG_LAUNCH(K)                                                                                                  \
   signature_kernel<K><<<grid, 128, 0, st>>>((const VoxGrid*)ctx->g_vgrid.p, (const SigDom*)ctx->g_sigdom.p,                \
                                             (const int*)ctx->g_voff.p, (const float4*)ctx->g_cent.p,                      \
                                             (const float4*)ctx->g_cnrm.p, (const int*)ctx->g_vlabel.p,                    \
                                             (const int*)ctx->g_layout.p, leaf, inv_leaf, subdivision_size, inv_sub, off_x, \
-                                            off_y, off_z, (int*)ctx->g_sig.p)
+                                            off_y, off_z, (int*)ctx->g_sig.p, own_mask)
     if (kind == CAB_SIG_GRSD21) CAB_SIG_LAUNCH(0);
     else if (kind == CAB_SIG_GRSD325) CAB_SIG_LAUNCH(1);
     else CAB_SIG_LAUNCH(2);
@@ -877,6 +979,10 @@ int64_t cab_grsd_signatures(cab_ctx* ctx, int32_t kind, int32_t subdivision_size
   }
   CAB_CUDA(ctx, cudaMemcpyAsync(hist, ctx->g_sig.p, (size_t)total * dim * 4, cudaMemcpyDeviceToHost, st));
   CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  // one large cloud sharded over a group (cab_grsd_cloud): this rank counted the transitions of its own voxels; one small
+  // integer all-reduce makes every rank's copy the whole cloud's (grsd_colorCHLAC_tools.hpp:230-260 sums the same integers)
+  if (ctx->g_own_valid && comm_active(ctx))
+    if (int rc = cab_comm_allreduce_i32(ctx, hist, total * dim)) return rc;
   return total;
 }
 

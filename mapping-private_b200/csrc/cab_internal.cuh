@@ -204,7 +204,8 @@ struct cab_ctx {
   // GRSD results of the last batch
   cab::DevBuf g_vkeys[2], g_vvals[2], g_cent, g_vcount, g_vrad, g_vlabel, g_voff, g_layout, g_layoff,
       g_vgrid, g_hist, g_vfirst;
-  cab::DevBuf g_cnrm, g_invperm, g_sig, g_sigdom, g_color;
+  cab::DevBuf g_cnrm, g_invperm, g_sig, g_sigdom, g_color, g_vown;
+  bool g_own_valid = false;        // g_vown marks the voxels this rank labelled (cab_grsd_cloud on a sharded context)
   int64_t g_nvox = 0;
   std::vector<int64_t> g_vox_offsets;
   std::vector<int32_t> g_min_div;  // host copy of the voxel grids: min_b[3], div_b[3] per cluster
@@ -257,7 +258,7 @@ int run_pfh(cab_ctx* ctx, double radius, int max_nn, int quantum, int flags, flo
 int64_t run_euclidean_clusters(cab_ctx* ctx, double tolerance, int min_pts, int max_pts, int32_t* labels);  // cab_cluster.cu
 int64_t run_neighbors_debug(cab_ctx* ctx, float r, int max_nn, int64_t q0, int64_t q1, int64_t* offsets,
                             int32_t* idx, float* d2, int64_t cap);
-int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_t* hist21);
+int run_grsd_batch(cab_ctx* ctx, float leaf, double r_rsd, int rsd_flags, int32_t* hist21, bool labels_only = false);
 int permute_normals_in(cab_ctx* ctx, const float* nx, const float* ny, const float* nz);
 int download_results(cab_ctx* ctx, float* n4, float* rmin, float* rmax);
 void svm_free(cab_ctx* ctx);
