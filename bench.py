@@ -30,7 +30,7 @@ RADIUS = 0.02
 NDIV = 10
 PLANE_RADIUS = 0.1
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
-KERNELS_VERSION = "r02-v1"  # bumped with every kernel change: profiles/traffic.json is only quoted for the kernels it measured
+KERNELS_VERSION = "r02-v2"  # bumped with every kernel change: profiles/traffic.json is only quoted for the kernels it measured
 
 
 def parse_args():
@@ -867,6 +867,49 @@ def main():
     extras = {}
     cpu = None
     parity = None
+    # GRSD of the ONE large cloud across the ranks (last stage): slab normals, own voxels' labels, labels merged,
+    # one int32 all-reduce of the transition counts -- all behind the C ABI (cab_grsd_cloud); every N
+    if not args.no_extras or world > 1:
+        try:
+            ctx.set_cloud_device(d_xyz.data_ptr(), n, 3)
+            h = ctx.grsd_cloud(0.025)  # warm-up (allocations)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                h = ctx.grsd_cloud(0.025)
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+                hh = torch.from_numpy(h.astype(np.int64)).to(dev)
+                lo_, hi_ = hh.clone(), hh.clone()
+                dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+                same_everywhere = bool(torch.equal(lo_, hi_))
+            else:
+                same_everywhere = True
+            g = {"workload": "GRSD-21 of the whole C4 cloud as one cluster, leaf 2.5 cm, normals r = 2 cm, device-resident cloud",
+                 "ms_per_cloud": 1e3 * dt / reps, "voxels": int(ctx.grsd_voxels(1)["labels"].shape[0]),
+                 "hist21": [int(x) for x in h], "same_histogram_on_every_rank": same_everywhere,
+                 "path": "cab_grsd_cloud: slab grid + normals per rank, own voxels' radii and labels, label merge and int32 all-reduce "
+                         "of the transition counts through cab_comm_allreduce_i32 (NCCL)" if world > 1 else "cab_grsd_cloud, one GPU"}
+            if world > 1 and rank == 0:  # the unsharded result on this rank's GPU, same mode
+                c1 = cab.Context(local_rank, exact=args.exact)
+                c1.set_cloud_device(d_xyz.data_ptr(), n, 3)
+                c1.n = n
+                t0 = time.perf_counter()
+                h1 = c1.grsd_cloud(0.025)
+                g["single_gpu_ms_first_call"] = 1e3 * (time.perf_counter() - t0)
+                g["equals_single_gpu"] = bool(np.array_equal(h1, h))
+                c1.close()
+            extras["grsd_one_cloud"] = g
+        except Exception as e:
+            extras["grsd_one_cloud"] = {"error": repr(e)}
+        ctx.set_cloud_device(d_xyz.data_ptr(), n, 3)
     if rank == 0 and world == 1 and not args.no_extras:
         def timed_steps(fn, reps):
             fn()
