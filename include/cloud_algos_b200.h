@@ -279,6 +279,26 @@ int64_t cab_euclidean_clusters(cab_ctx* ctx, double tolerance, int32_t min_pts, 
  * them, with offsets, to cab_upload_clusters / cab_grsd_batch.  Returns the number of labelled points or < 0. */
 int64_t cab_cluster_csr(const int32_t* labels, int64_t n, int32_t n_clusters, int32_t* offsets, int32_t* indices);
 
+/* The table-plane step in front of the object clustering: fitSACPlane (cloud_tools/src/table_object_detector_passive.cpp:
+ * 621-659, table_object_detector_sr.cpp): sample_consensus::MSAC over SACModelPlane (setMaxIterations(500),
+ * setProbability(0.99)) [point_cloud_mapping, external], computeCoefficients, refineCoefficients (least squares over the
+ * inliers), selectWithinDistance(coeff, threshold) and projectPointsInPlace.
+ * xyz: n host points (stride floats each); indices: optional list of n_idx point indices the model is fitted to (the
+ * detector passes one cluster of Z-parallel points), NULL = all points.  triples: n_triples x 3 POSITIONS into that list
+ * (or into the cloud), the sample sequence -- the caller's, because the reference's rand() stream is not reproducible;
+ * a hypothesis is the plane through the next triple; a degenerate triple (repeated or collinear points) is skipped, as
+ * upstream getSamples draws again.  The loop runs while iterations < k (k = log(1 - probability) / log(1 - w^3) after
+ * every improvement, w = inlier ratio of the best model), for at most max_iterations + 1 hypotheses and n_triples
+ * samples, exactly as the sequential loop would -- the device scores 32 hypotheses per launch.
+ * coeff: a, b, c, d of the refined plane (unit normal on the sampled model's side).  inliers: the indices within
+ * `threshold` of the refined plane, in list order; projected_xyz: their projections (3 floats each); both optional, room
+ * for `cap` entries.  iterations_run / best_iteration (optional): hypotheses scored, position of the winning triple in
+ * the sample sequence (-1: none valid).  Returns the number of inliers (0 with coeff = 0 if no model was found) or < 0. */
+int64_t cab_fit_plane_msac(cab_ctx* ctx, const float* xyz, int64_t n, int32_t stride, const int32_t* indices, int64_t n_idx,
+                           double threshold, int32_t max_iterations, double probability, const int32_t* triples,
+                           int64_t n_triples, double coeff[4], int32_t* inliers, float* projected_xyz, int64_t cap,
+                           int32_t* iterations_run, int32_t* best_iteration);
+
 /* ---- point feature histograms (next row: cloud_algos/PointFeatureHistogram) ----------------
  * Replaces the hot loops of PointFeatureHistogram::process (cloud_algos/src/pfh.cpp:181-350; pair features
  * cloud_algos/include/cloud_algos/pfh.h:102-238) on the uploaded cloud with its normals (cab_set_normals or

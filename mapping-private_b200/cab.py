@@ -33,6 +33,7 @@ EXPORTS = [
     "cab_step_normals_rsd", "cab_comm_get_id", "cab_comm_init", "cab_comm_init_local", "cab_comm_reserve", "cab_comm_connect",
     "cab_comm_free", "cab_comm_upload_cloud", "cab_comm_download_range", "cab_comm_device_ptr", "cab_comm_allreduce_i32",
     "cab_comm_set_layout", "cab_comm_set_feedback", "cab_grsd_cloud", "cab_grsd_cloud_labels", "cab_grsd_cloud_set_labels",
+    "cab_fit_plane_msac",
 ]
 COMM_ID_BYTES, COMM_BLOB_BYTES = 128, 512
 
@@ -80,6 +81,7 @@ def lib():
         L.cab_grsd_voxels.restype = C.c_int64
         L.cab_grsd_signatures.restype = C.c_int64
         L.cab_grsd_cloud_labels.restype = C.c_int64
+        L.cab_fit_plane_msac.restype = C.c_int64
         L.cab_color_chlac.restype = C.c_int64
         L.cab_statistical_outliers.restype = C.c_int64
         L.cab_euclidean_clusters.restype = C.c_int64
@@ -248,6 +250,23 @@ class Context:
                                            C.c_float(leaf), C.c_float(r_normals), C.c_double(rsd_radius_min),
                                            C.c_int32(rsd_flags), _fp(v), _fp(nx), _fp(ny), _fp(nz), _ip(hist)), "cab_grsd_batch")
         return hist
+
+    def fit_plane_msac(self, xyz: np.ndarray, triples: np.ndarray, indices: np.ndarray | None = None, threshold: float = 0.03,
+                       max_iterations: int = 500, probability: float = 0.99):
+        """fitSACPlane: dict(coeff (4,) float64, inliers int32, projected (m,3) float32, iterations, best_iteration)."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        tri = np.ascontiguousarray(triples, dtype=np.int32).reshape(-1, 3)
+        idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
+        m = xyz.shape[0] if idx is None else idx.shape[0]
+        coeff = np.zeros(4, np.float64)
+        inl = np.zeros(max(m, 1), np.int32)
+        proj = np.zeros((max(m, 1), 3), np.float32)
+        it, best = C.c_int32(), C.c_int32()
+        nin = self._check(self._L.cab_fit_plane_msac(
+            self._h, _fp(xyz), C.c_int64(xyz.shape[0]), C.c_int32(xyz.shape[1]), _ip(idx), C.c_int64(0 if idx is None else idx.shape[0]),
+            C.c_double(threshold), C.c_int32(max_iterations), C.c_double(probability), _ip(tri), C.c_int64(tri.shape[0]),
+            coeff.ctypes.data_as(C.POINTER(C.c_double)), _ip(inl), _fp(proj), C.c_int64(m), C.byref(it), C.byref(best)), "cab_fit_plane_msac")
+        return dict(coeff=coeff, inliers=inl[:nin], projected=proj[:nin], iterations=it.value, best_iteration=best.value)
 
     def grsd_cloud(self, leaf: float, r_normals: float = 0.02, rsd_radius_min: float = 0.01, rsd_flags: int = 0, vp=(0.0, 0.0, 0.0)):
         """GRSD-21 of the one cloud this context holds; in a group: sharded by rows, labels and histogram merged (21 int32)."""

@@ -15,6 +15,7 @@
 #include <cloud_algos/pfh.h>
 #include <cloud_algos/pcd_io.h>
 #include <point_cloud_mapping/geometry/nearest.h>
+#include <cloud_tools/fit_sac_plane.h>
 
 using namespace cloud_algos;
 
@@ -256,6 +257,32 @@ int capi_extract_euclidean_clusters(const float* xyz, int n, const int* indices,
       flat_members[w++] = i;
     }
   return (int)clusters.size();
+}
+
+// cloud_tools::fitSACPlane through the member's signature: xyz is updated in place with the projected inliers.
+// Returns the number of inliers (coeff filled), 0 if no model, -1 if there were too few indices, -2 on a library error.
+int capi_fit_sac_plane(float* xyz, int n, const int* indices, int n_idx, double threshold, int min_pts, unsigned seed,
+                       int* inliers, double* coeff) {
+  sensor_msgs::PointCloud cloud;
+  cloud.points.resize(n);
+  for (int i = 0; i < n; ++i) {
+    cloud.points[i].x = xyz[3 * i];
+    cloud.points[i].y = xyz[3 * i + 1];
+    cloud.points[i].z = xyz[3 * i + 2];
+  }
+  std::vector<int> idx(indices, indices + n_idx), in;
+  std::vector<double> c;
+  const int rc = cloud_tools::fitSACPlane(&cloud, &idx, in, c, threshold, min_pts, seed);
+  if (!cloud_tools::lastFitSACPlaneError().empty()) return -2;
+  if (rc < 0) return -1;
+  for (size_t i = 0; i < in.size(); ++i) inliers[i] = in[i];
+  for (size_t k = 0; k < c.size(); ++k) coeff[k] = c[k];
+  for (int i = 0; i < n; ++i) {
+    xyz[3 * i] = cloud.points[i].x;
+    xyz[3 * i + 1] = cloud.points[i].y;
+    xyz[3 * i + 2] = cloud.points[i].z;
+  }
+  return (int)in.size();
 }
 
 int capi_list_requires(void* hv, char* buf, int cap) {

@@ -56,8 +56,22 @@ def lib():
         L.capi_write_feature.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.capi_extract_euclidean_clusters.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_uint,
                                                       C.c_void_p, C.c_void_p]
+        L.capi_fit_sac_plane.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
+
+
+def fit_sac_plane(xyz: np.ndarray, indices: np.ndarray, threshold: float = 0.03, min_pts: int = 10, seed: int = 1):
+    """cloud_tools::fitSACPlane (host/include/cloud_tools/fit_sac_plane.h) through the member's signature.  Returns
+    (rc, inliers, coeff (4,), xyz with the inliers projected in place); rc = number of inliers, 0, -1 (too few indices)
+    or -2 (library error)."""
+    pts = np.array(xyz, np.float32, copy=True, order="C")
+    indices = np.ascontiguousarray(indices, np.int32)
+    inl = np.zeros(max(len(indices), 1), np.int32)
+    coeff = np.zeros(4, np.float64)
+    rc = lib().capi_fit_sac_plane(pts.ctypes.data, pts.shape[0], indices.ctypes.data, len(indices), float(threshold), int(min_pts),
+                                  int(seed), inl.ctypes.data, coeff.ctypes.data)
+    return rc, inl[:max(rc, 0)], coeff, pts
 
 
 def extract_euclidean_clusters(xyz: np.ndarray, indices: np.ndarray, tolerance: float, min_pts: int = 1, nx_idx: int = -1):

@@ -1532,4 +1532,137 @@ int orc_pfh(const float* xyz, const float* normals, int normal_stride, int n, do
   return nr_bins;
 }
 
+
+// fitSACPlane, cloud_tools/src/table_object_detector_passive.cpp:621-659: sample_consensus::MSAC over SACModelPlane
+// [point_cloud_mapping, EXTERNAL: not in /root/reference -- parity unpinned; the published algorithm restated:
+// MSAC::computeModel's loop (penalty = sum min(distance, threshold); k = log(1 - p) / log(1 - w^3) after every
+// improvement; iterations_ > max_iterations_ ends it), SACModelPlane::computeModelCoefficients (plane through three
+// points), getDistancesToModel (|a x + b y + c z + d| in double), refineCoefficients (computePointNormal: centroid,
+// covariance, eigenvector of the smallest eigenvalue), selectWithinDistance, projectPointsInPlace].  The sample sequence
+// is given (triples: positions into the index list); a degenerate triple is skipped, as getSamples draws again.
+int64_t orc_fit_plane_msac(const float* xyz, int64_t n, const int32_t* indices, int64_t n_idx, double threshold,
+                           int32_t max_iterations, double probability, const int32_t* triples, int64_t n_triples,
+                           double coeff[4], int32_t* inliers, float* projected_xyz, int32_t* iterations_run,
+                           int32_t* best_iteration) {
+  const int64_t m = indices ? n_idx : n;
+  auto point = [&](int64_t pos) { return xyz + 3 * (size_t)(indices ? indices[pos] : pos); };
+  for (int k = 0; k < 4; ++k) coeff[k] = 0.0;
+  *iterations_run = 0;
+  *best_iteration = -1;
+  if (m < 3) return 0;
+  double best_penalty = DBL_MAX, k = 1.0, best[4] = {0, 0, 0, 0};
+  int iterations = 0;
+  for (int64_t smp = 0; iterations < k && smp < n_triples; ++smp) {
+    const int32_t* t = triples + 3 * (size_t)smp;
+    double mdl[4];
+    bool ok = t[0] != t[1] && t[0] != t[2] && t[1] != t[2];
+    if (ok) {
+      const float *p0 = point(t[0]), *p1 = point(t[1]), *p2 = point(t[2]);
+      const double ux = (double)p1[0] - p0[0], uy = (double)p1[1] - p0[1], uz = (double)p1[2] - p0[2];
+      const double vx = (double)p2[0] - p0[0], vy = (double)p2[1] - p0[1], vz = (double)p2[2] - p0[2];
+      double a = uy * vz - uz * vy, b = uz * vx - ux * vz, c = ux * vy - uy * vx;
+      const double len = std::sqrt(a * a + b * b + c * c);
+      ok = len > 0.0 && std::isfinite(len);
+      if (ok) {
+        a /= len;
+        b /= len;
+        c /= len;
+        mdl[0] = a;
+        mdl[1] = b;
+        mdl[2] = c;
+        mdl[3] = -(a * (double)p0[0] + b * (double)p0[1] + c * (double)p0[2]);
+      }
+    }
+    if (!ok) continue;  // getSamples draws again: a degenerate triple is not an iteration
+    {
+      double penalty = 0;
+      int64_t count = 0;
+      for (int64_t i = 0; i < m; ++i) {
+        const float* p = point(i);
+        const double d = std::fabs(mdl[0] * (double)p[0] + mdl[1] * (double)p[1] + mdl[2] * (double)p[2] + mdl[3]);
+        penalty += std::min(d, threshold);
+        count += d <= threshold ? 1 : 0;
+      }
+      if (penalty < best_penalty) {
+        best_penalty = penalty;
+        std::memcpy(best, mdl, sizeof(best));
+        *best_iteration = (int32_t)smp;
+        const double w = (double)count / (double)m;
+        double p_no_outliers = 1.0 - std::pow(w, 3.0);
+        p_no_outliers = std::max(std::numeric_limits<double>::epsilon(), p_no_outliers);
+        p_no_outliers = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no_outliers);
+        k = std::log(1.0 - probability) / std::log(p_no_outliers);
+      }
+    }
+    iterations += 1;
+    if (iterations > max_iterations) break;
+  }
+  *iterations_run = iterations;
+  if (*best_iteration < 0) return 0;
+  // refineCoefficients over the best model's inliers
+  double sx = 0, sy = 0, sz = 0, cnt = 0;
+  std::vector<char> in((size_t)m, 0);
+  for (int64_t i = 0; i < m; ++i) {
+    const float* p = point(i);
+    const double d = std::fabs(best[0] * (double)p[0] + best[1] * (double)p[1] + best[2] * (double)p[2] + best[3]);
+    if (d <= threshold) {
+      in[(size_t)i] = 1;
+      sx += p[0];
+      sy += p[1];
+      sz += p[2];
+      cnt += 1;
+    }
+  }
+  double ref[4] = {best[0], best[1], best[2], best[3]};
+  if (cnt >= 3) {
+    const double cx = sx / cnt, cy = sy / cnt, cz = sz / cnt;
+    double cov[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t i = 0; i < m; ++i) {
+      if (!in[(size_t)i]) continue;
+      const float* p = point(i);
+      const double dx = (double)p[0] - cx, dy = (double)p[1] - cy, dz = (double)p[2] - cz;
+      cov[0] += dx * dx;
+      cov[1] += dx * dy;
+      cov[2] += dx * dz;
+      cov[3] += dy * dy;
+      cov[4] += dy * dz;
+      cov[5] += dz * dz;
+    }
+    double w[3], v[3][3];
+    eig3_jacobi(cov, w, v);
+    double nx = v[0][0], ny = v[1][0], nz = v[2][0];
+    const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+    nx /= len;
+    ny /= len;
+    nz /= len;
+    if (std::isfinite(nx) && std::isfinite(ny) && std::isfinite(nz)) {
+      if (nx * best[0] + ny * best[1] + nz * best[2] < 0) {  // the sign is arbitrary upstream: the sampled model's side
+        nx = -nx;
+        ny = -ny;
+        nz = -nz;
+      }
+      ref[0] = nx;
+      ref[1] = ny;
+      ref[2] = nz;
+      ref[3] = -(nx * cx + ny * cy + nz * cz);
+    }
+  }
+  std::memcpy(coeff, ref, sizeof(ref));
+  int64_t n_in = 0;
+  for (int64_t i = 0; i < m; ++i) {
+    const float* p = point(i);
+    const double dist = ref[0] * (double)p[0] + ref[1] * (double)p[1] + ref[2] * (double)p[2] + ref[3];
+    if (std::fabs(dist) <= threshold) {
+      if (inliers) inliers[n_in] = (int32_t)(indices ? indices[i] : i);
+      if (projected_xyz) {
+        projected_xyz[3 * n_in] = (float)((double)p[0] - dist * ref[0]);
+        projected_xyz[3 * n_in + 1] = (float)((double)p[1] - dist * ref[1]);
+        projected_xyz[3 * n_in + 2] = (float)((double)p[2] - dist * ref[2]);
+      }
+      ++n_in;
+    }
+  }
+  return n_in;
+}
+
 }  // extern "C"

@@ -234,6 +234,13 @@ int orc_normals_knn(const float* xyz, int n, int k, const float* vp, float* out_
  * order of their seeds (= their smallest index) with their indices sorted ascending.
  * labels[n]: cluster id in that order, -1 for dropped regions and non-finite points.  Returns the cluster count. */
 int orc_euclidean_clusters(const float* xyz, int n, double tolerance, int min_pts, int max_pts, int32_t* labels);
+/* fitSACPlane (cloud_tools/src/table_object_detector_passive.cpp:621-659): MSAC plane through a given sample sequence,
+ * refined by least squares, inliers within the threshold and their projections.  [parity unpinned: point_cloud_mapping's
+ * sample_consensus is not in the tree and draws its samples with rand()] */
+int64_t orc_fit_plane_msac(const float* xyz, int64_t n, const int32_t* indices, int64_t n_idx, double threshold,
+                           int32_t max_iterations, double probability, const int32_t* triples, int64_t n_triples,
+                           double coeff[4], int32_t* inliers, float* projected_xyz, int32_t* iterations_run,
+                           int32_t* best_iteration);
 
 int orc_num_threads(void);
 

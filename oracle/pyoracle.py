@@ -367,6 +367,26 @@ def euclidean_clusters(xyz, tolerance, min_pts=1, max_pts=0):
     return labels, int(nc)
 
 
+def fit_plane_msac(xyz, triples, indices=None, threshold=0.03, max_iterations=500, probability=0.99):
+    """fitSACPlane on a given sample sequence: dict(coeff, inliers, projected, iterations, best_iteration)."""
+    L = lib()
+    L.orc_fit_plane_msac.restype = C.c_int64
+    p = _xyz(xyz)
+    tri = np.ascontiguousarray(triples, np.int32).reshape(-1, 3)
+    idx = None if indices is None else np.ascontiguousarray(indices, np.int32)
+    m = p.shape[0] if idx is None else idx.shape[0]
+    coeff = np.zeros(4, np.float64)
+    inl = np.zeros(max(m, 1), np.int32)
+    proj = np.zeros((max(m, 1), 3), np.float32)
+    it, best = C.c_int32(), C.c_int32()
+    nin = L.orc_fit_plane_msac(_ptr(p, C.c_float), C.c_int64(p.shape[0]), None if idx is None else _ptr(idx, C.c_int32),
+                               C.c_int64(0 if idx is None else idx.shape[0]), C.c_double(threshold), C.c_int32(max_iterations),
+                               C.c_double(probability), _ptr(tri, C.c_int32), C.c_int64(tri.shape[0]),
+                               coeff.ctypes.data_as(C.POINTER(C.c_double)), _ptr(inl, C.c_int32), _ptr(proj, C.c_float),
+                               C.byref(it), C.byref(best))
+    return dict(coeff=coeff, inliers=inl[:nin], projected=proj[:nin], iterations=it.value, best_iteration=best.value)
+
+
 def noise_filter(avg, alpha):
     """Returns (keep bool (n,), mean, stddev)."""
     L = lib()
