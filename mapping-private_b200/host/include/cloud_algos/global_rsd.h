@@ -38,6 +38,12 @@ class GlobalRSD : public CloudAlgo
   std::vector<std::string> provides ();
   std::string process (const boost::shared_ptr<const InputType>&);
   boost::shared_ptr<const OutputType> output ();
+  /** Not in the reference (whose caller loops over the object clusters and calls process () once per cluster,
+    * dyn_obj_store/src/table_memory_grsd.cpp:913-997): all clusters of a frame in ONE device call (cab_grsd_batch), which
+    * is where the GPU's batched rate comes from.  outputs[i] is what process (clusters[i]) + output () would have
+    * produced; returns "ok" or the first error. */
+  std::string process_batch (const std::vector<boost::shared_ptr<const InputType> >& clusters,
+                             std::vector<boost::shared_ptr<const OutputType> >& outputs);
   boost::shared_ptr<const sensor_msgs::PointCloud> getCentroids () {return cloud_centroids_;}
   boost::shared_ptr<const sensor_msgs::PointCloud> getVRSD () {return cloud_vrsd_;}
 

@@ -142,3 +142,86 @@ std::string GlobalRSD::process (const boost::shared_ptr<const GlobalRSD::InputTy
 
 boost::shared_ptr<const GlobalRSD::OutputType> GlobalRSD::output ()
   {return cloud_grsd_;}
+
+std::string GlobalRSD::process_batch (const std::vector<boost::shared_ptr<const GlobalRSD::InputType> >& clusters,
+                                      std::vector<boost::shared_ptr<const GlobalRSD::OutputType> >& outputs)
+{
+  outputs.clear ();
+  output_valid_ = true;
+  if (step_ != 0 || min_voxel_pts_ > 1)
+  {
+    output_valid_ = false;
+    return std::string ("unsupported options: only step = 0 and min_voxel_pts <= 1 are implemented");
+  }
+  const size_t nc = clusters.size ();
+  if (nc == 0) return std::string ("ok");
+  std::vector<int32_t> offsets (nc + 1, 0);
+  for (size_t c = 0; c < nc; ++c)
+  {
+    const int nxIdx = getChannelIndex (clusters[c], "nx");
+    if (nxIdx == -1 || nxIdx + 2 >= (int) clusters[c]->channels.size ())
+    {
+      ROS_ERROR ("[GlobalRSD] Provided point cloud does not have normals. Use the normal_estimation or mls_fit first!");
+      output_valid_ = false;
+      return std::string ("missing normals");
+    }
+    offsets[c + 1] = offsets[c] + (int32_t) clusters[c]->points.size ();
+  }
+  const size_t n = (size_t) offsets[nc];
+  std::vector<float> xyz (3 * n), nx (n), ny (n), nz (n);
+  for (size_t c = 0; c < nc; ++c)
+  {
+    const InputType& cl = *clusters[c];
+    const int nxIdx = getChannelIndex (clusters[c], "nx");
+    for (size_t i = 0; i < cl.points.size (); ++i)
+    {
+      const size_t j = (size_t) offsets[c] + i;
+      xyz[3 * j] = cl.points[i].x; xyz[3 * j + 1] = cl.points[i].y; xyz[3 * j + 2] = cl.points[i].z;
+      nx[j] = cl.channels[nxIdx].values[i]; ny[j] = cl.channels[nxIdx + 1].values[i]; nz[j] = cl.channels[nxIdx + 2].values[i];
+    }
+  }
+  std::string err;
+  cab_ctx* ctx = gpu_.get (err, true);
+  if (!ctx) { output_valid_ = false; ROS_ERROR ("[GlobalRSD] %s", err.c_str ()); return err; }
+  std::vector<int32_t> hist (21 * nc, 0);
+  const float vp[3] = {0, 0, 0};
+  if (n)
+  {
+    const int rc = cab_grsd_batch (ctx, &xyz[0], 3, &offsets[0], (int32_t) nc, (float) width_, 0.f, rsd_radius_min_, 0, vp, &nx[0], &ny[0],
+                                   &nz[0], &hist[0]);
+    if (rc != CAB_OK)
+    {
+      output_valid_ = false;
+      err = std::string ("GRSD failed: ") + cab_last_error (ctx);
+      ROS_ERROR ("[GlobalRSD] %s", err.c_str ());
+      return err;
+    }
+  }
+  outputs.resize (nc);
+  for (size_t c = 0; c < nc; ++c)
+  {
+    const InputType& cl = *clusters[c];
+    boost::shared_ptr<sensor_msgs::PointCloud> o (new sensor_msgs::PointCloud ());
+    o->header = cl.header;
+    o->points.resize (1);
+    double cx = 0, cy = 0, cz = 0;
+    const size_t m = cl.points.size ();
+    for (size_t i = 0; i < m; ++i) { cx += cl.points[i].x; cy += cl.points[i].y; cz += cl.points[i].z; }
+    if (m) { o->points[0].x = (float) (cx / m); o->points[0].y = (float) (cy / m); o->points[0].z = (float) (cz / m); }
+    o->channels.resize (label_ != -1 ? 22 : 21);
+    for (int i = 0; i < 21; ++i)
+    {
+      char name[8];
+      std::snprintf (name, sizeof (name), "f%d", i + 1);
+      o->channels[i].name = name;
+      o->channels[i].values.assign (1, (float) hist[21 * c + i]);
+    }
+    if (label_ != -1)
+    {
+      o->channels[21].name = "point_label";
+      o->channels[21].values.assign (1, (float) label_);
+    }
+    outputs[c] = o;
+  }
+  return std::string ("ok");
+}

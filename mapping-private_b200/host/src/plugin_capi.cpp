@@ -259,6 +259,35 @@ int capi_extract_euclidean_clusters(const float* xyz, int n, const int* indices,
   return (int)clusters.size();
 }
 
+// GlobalRSD::process_batch: clusters given as one concatenated cloud + offsets, nx/ny/nz per point; out: nc x 21 floats.
+// Returns 0, or -1 with the error string in the handle's result.
+int capi_grsd_process_batch(void* hv, const float* xyz, const float* nxyz, const int* offsets, int nc, float* out) {
+  Handle* h = (Handle*)hv;
+  GlobalRSD* a = dynamic_cast<GlobalRSD*>(h->algo);
+  if (!a) { h->result = "not a GlobalRSD"; return -1; }
+  std::vector<boost::shared_ptr<const sensor_msgs::PointCloud> > clusters(nc), outs;
+  for (int c = 0; c < nc; ++c) {
+    boost::shared_ptr<sensor_msgs::PointCloud> in(new sensor_msgs::PointCloud());
+    const int b = offsets[c], m = offsets[c + 1] - offsets[c];
+    in->points.resize(m);
+    in->channels.resize(3);
+    in->channels[0].name = "nx"; in->channels[1].name = "ny"; in->channels[2].name = "nz";
+    for (int k = 0; k < 3; ++k) in->channels[k].values.resize(m);
+    for (int i = 0; i < m; ++i) {
+      in->points[i].x = xyz[3 * (size_t)(b + i)];
+      in->points[i].y = xyz[3 * (size_t)(b + i) + 1];
+      in->points[i].z = xyz[3 * (size_t)(b + i) + 2];
+      for (int k = 0; k < 3; ++k) in->channels[k].values[i] = nxyz[3 * (size_t)(b + i) + k];
+    }
+    clusters[c] = in;
+  }
+  h->result = a->process_batch(clusters, outs);
+  if (h->result != "ok") return -1;
+  for (int c = 0; c < nc; ++c)
+    for (int i = 0; i < 21; ++i) out[21 * (size_t)c + i] = outs[c]->channels[i].values.at(0);
+  return 0;
+}
+
 // cloud_tools::fitSACPlane through the member's signature: xyz is updated in place with the projected inliers.
 // Returns the number of inliers (coeff filled), 0 if no model, -1 if there were too few indices, -2 on a library error.
 int capi_fit_sac_plane(float* xyz, int n, const int* indices, int n_idx, double threshold, int min_pts, unsigned seed,

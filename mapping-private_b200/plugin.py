@@ -155,6 +155,17 @@ class Plugin:
         if rc != 0:
             raise AttributeError(field)
 
+    def grsd_process_batch(self, xyz: np.ndarray, normals: np.ndarray, offsets: np.ndarray):
+        """GlobalRSD::process_batch: all clusters of a frame in one device call.  Returns (result string, hist (nc, 21))."""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        nrm = np.ascontiguousarray(normals, np.float32)
+        off = np.ascontiguousarray(offsets, np.int32)
+        nc = len(off) - 1
+        out = np.zeros((max(nc, 1), 21), np.float32)
+        self._L.capi_grsd_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        rc = self._L.capi_grsd_process_batch(self._h, xyz.ctypes.data, nrm.ctypes.data, off.ctypes.data, nc, out.ctypes.data)
+        return ("ok" if rc == 0 else "error"), out[:nc]
+
     def requires_provides(self):
         buf = C.create_string_buffer(1024)
         self._L.capi_list_requires(self._h, buf, 1024)

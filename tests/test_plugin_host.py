@@ -198,6 +198,30 @@ def test_global_rsd_plugin_against_oracle(built, oracle):
 
 
 @pytest.mark.gpu
+def test_global_rsd_process_batch_equals_per_cluster_calls(built, oracle):
+    """GlobalRSD::process_batch (all clusters of a frame in one device call) against process () cluster by cluster, the
+    loop of table_memory_grsd.cpp:913-997."""
+    xyz, off = synth.clusters(6, 1500, 3000, seed_extra=7)
+    nrm = np.zeros_like(xyz)
+    for c in range(6):
+        o4, _ = oracle.normals(xyz[off[c]:off[c + 1]], 0.02)
+        nrm[off[c]:off[c + 1]] = np.nan_to_num(o4[:, :3], nan=0.0)
+    g = plugin.Plugin("cloud_algos/GlobalRSD")
+    g.set_param("width", 0.03)
+    g._L.capi_pre(g._h)
+    g.set_field("min_voxel_pts_", 0)
+    res, hist = g.grsd_process_batch(xyz, nrm, off)
+    assert res == "ok" and hist.shape == (6, 21)
+    for c in range(6):
+        pts = xyz[off[c]:off[c + 1]]
+        n3 = nrm[off[c]:off[c + 1]]
+        r1, out = g.run(pts, {"nx": n3[:, 0], "ny": n3[:, 1], "nz": n3[:, 2]}, fields={"min_voxel_pts_": 0})
+        assert r1 == "ok"
+        one = np.array([out["channels"][f"f{i}"][0] for i in range(1, 22)])
+        assert np.array_equal(one, hist[c]), c
+
+
+@pytest.mark.gpu
 def test_svm_plugin_against_oracle(built, oracle, tmp_path):
     """GlobalRSD -> SVMClassification the way table_memory_grsd.cpp:974-1018 chains them, with the
     reference's grsd_ijrr model and scale ranges written back to files in libsvm's formats."""
