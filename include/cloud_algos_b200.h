@@ -392,10 +392,14 @@ int cab_comm_free(cab_ctx* ctx);
 int cab_comm_set_layout(cab_ctx* ctx, int32_t layout);
 /* Shard balance of a group.  The rows are cut by a cost model (sampled cell histogram -> candidates per row); with the
  * feedback on (default) every step also leaves each rank's measured normals + RSD time with every rank, and the next
- * step's cuts give a rank that took longer than the mean a smaller share.  Results never depend on the cuts; all ranks
+ * step's cuts give a rank that took longer than the mean a smaller share (steps whose passes take less than half a
+ * millisecond leave the shares alone: that is latency, not work).  Results never depend on the cuts; all ranks
  * must use the same setting (a step fails with CAB_ERR_STATE if the ranks' cuts disagree).  Setting it resets the
  * shares to equal. */
 int cab_comm_set_feedback(cab_ctx* ctx, int32_t on);
+/* The ranks' shares of the modelled cost, set by hand (unequal GPUs, or a test that wants the cuts elsewhere): `count` =
+ * world positive numbers, normalised to sum 1; the same numbers on every rank.  The feedback, if on, continues from them. */
+int cab_comm_set_shares(cab_ctx* ctx, const double* shares, int32_t count);
 /* Replicates a host cloud on every rank of the group: xyz points at the WHOLE cloud (n points, packed xyz) on every rank;
  * a rank uploads rows [n*rank/world, n*(rank+1)/world) over its own PCIe link and copies them into the peers' buffers
  * over NVLink (copy engines), then waits for the other slices.  Without a group: cab_upload_cloud. */

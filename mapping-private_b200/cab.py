@@ -32,7 +32,7 @@ EXPORTS = [
     "cab_device_ptr", "cab_stream", "cab_download", "cab_download_sorted", "cab_download_rdif", "cab_profile", "cab_version",
     "cab_step_normals_rsd", "cab_comm_get_id", "cab_comm_init", "cab_comm_init_local", "cab_comm_reserve", "cab_comm_connect",
     "cab_comm_free", "cab_comm_upload_cloud", "cab_comm_download_range", "cab_comm_device_ptr", "cab_comm_allreduce_i32",
-    "cab_comm_set_layout", "cab_comm_set_feedback", "cab_grsd_cloud", "cab_grsd_cloud_labels", "cab_grsd_cloud_set_labels",
+    "cab_comm_set_layout", "cab_comm_set_feedback", "cab_comm_set_shares", "cab_grsd_cloud", "cab_grsd_cloud_labels", "cab_grsd_cloud_set_labels",
     "cab_fit_plane_msac",
 ]
 COMM_ID_BYTES, COMM_BLOB_BYTES = 128, 512
@@ -449,6 +449,10 @@ class Context:
 
     def comm_set_feedback(self, on: bool):
         self._check(self._L.cab_comm_set_feedback(self._h, C.c_int32(1 if on else 0)), "cab_comm_set_feedback")
+
+    def comm_set_shares(self, shares):
+        a = np.ascontiguousarray(shares, np.float64)
+        self._check(self._L.cab_comm_set_shares(self._h, a.ctypes.data_as(C.POINTER(C.c_double)), C.c_int32(a.size)), "cab_comm_set_shares")
 
     def comm_set_layout(self, layout: int):
         self._check(self._L.cab_comm_set_layout(self._h, C.c_int32(layout)), "cab_comm_set_layout")

@@ -671,7 +671,8 @@ int comm_step_finish(cab_ctx* ctx) {  // after the step's synchronisation
       ok = ok && busy[p] > 0 && busy[p] < (1ull << 40);
     }
     mean /= cs->world;
-    if (ok && mean > 0) {
+    // (steps of less than half a millisecond are launch latency, not work: their times say nothing about the cuts)
+    if (ok && mean > 5e5) {
       double sum = 0;
       for (int p = 0; p < cs->world; ++p) {
         double s = cs->share[p] * std::pow(mean / (double)busy[p], 0.75);
@@ -689,7 +690,7 @@ int comm_step_finish(cab_ctx* ctx) {  // after the step's synchronisation
 void comm_shares(cab_ctx* ctx) {
   ctx->shard_cum.clear();
   CommState* cs = ctx->comm;
-  if (!cs || cs->world <= 1 || !cs->feedback) return;
+  if (!cs || cs->world <= 1) return;
   ctx->shard_cum.assign((size_t)cs->world + 1, 0.0);
   double acc = 0;
   for (int p = 0; p < cs->world; ++p) {
@@ -789,6 +790,19 @@ int cab_comm_set_feedback(cab_ctx* ctx, int32_t on) {
   if (!ctx->comm) return fail(ctx, CAB_ERR_STATE, "cab_comm_set_feedback: this context belongs to no group");
   ctx->comm->feedback = on != 0;
   for (int p = 0; p < kMaxPeers; ++p) ctx->comm->share[p] = 1.0 / ctx->comm->world;
+  return CAB_OK;
+}
+
+int cab_comm_set_shares(cab_ctx* ctx, const double* shares, int32_t count) {
+  if (!ctx || !shares) return CAB_ERR_ARG;
+  if (!ctx->comm) return fail(ctx, CAB_ERR_STATE, "cab_comm_set_shares: this context belongs to no group");
+  if (count != ctx->comm->world) return fail(ctx, CAB_ERR_ARG, "cab_comm_set_shares: %d shares for %d ranks", count, ctx->comm->world);
+  double sum = 0;
+  for (int p = 0; p < count; ++p) {
+    if (!(shares[p] > 0) || !std::isfinite(shares[p])) return fail(ctx, CAB_ERR_ARG, "cab_comm_set_shares: shares must be positive");
+    sum += shares[p];
+  }
+  for (int p = 0; p < count; ++p) ctx->comm->share[p] = shares[p] / sum;
   return CAB_OK;
 }
 

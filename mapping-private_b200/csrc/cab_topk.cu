@@ -43,11 +43,12 @@ struct ThrArgs {
   unsigned long long* stats;  // nn_hist_kernel: packet work counter
 };
 
-__global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrArgs a) {
+// (one packet; the kernels below walk the packets with a grid-stride loop: in the truncated fast RSD pass only a few
+// packets are flagged, and a grid of one block per four packets costs 0.8 ms on 660 k packets just to be scheduled)
+__device__ __forceinline__ void threshold_packet(const ThrArgs& a, int pid) {
   __shared__ ChunkTile tiles[kSelWarps];
   __shared__ unsigned hist[kSelWarps][kSelBins][kWarp];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pid = a.p0 + blockIdx.x * kSelWarps + warp;
   if (pid >= a.p1) return;
   if (a.use_fallback && !a.fallback[pid - a.p0]) return;
   const GridView& g = a.g;
@@ -123,11 +124,18 @@ constexpr int kListCap = kSelBins / 2;  // (d2, index) pairs that fit into a lan
 // Selection by value histograms (see the file comment).  hist[warp][.][lane] is the lane's private column: first
 // the 64 counters, then the list of the target bin's candidates.  A second histogram level subdivides the
 // target bin when it is too full for the list (k-NN queries: k << candidates in the radius).
-__global__ void __launch_bounds__(kSelWarps * kWarp) value_select_kernel(const ThrArgs a) {
+__global__ void __launch_bounds__(kSelWarps * kWarp) threshold_kernel(const ThrArgs a) {
+  const int warp = threadIdx.x >> 5;
+  for (int pid = a.p0 + blockIdx.x * kSelWarps + warp; pid < a.p1; pid += gridDim.x * kSelWarps) {
+    threshold_packet(a, pid);
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void value_select_packet(const ThrArgs& a, int pid) {
   __shared__ ChunkTile tiles[kSelWarps];
   __shared__ unsigned hist[kSelWarps][kSelBins + 1][kWarp];  // row kSelBins: everything beyond the radius
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pid = a.p0 + blockIdx.x * kSelWarps + warp;
   if (pid >= a.p1) return;
   if (a.only && !a.only[pid - a.p0]) return;
   const GridView& g = a.g;
@@ -228,6 +236,14 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) value_select_kernel(const T
   if (pc.active && wanted && !need) {
     a.thr_d2[pc.qi] = INFINITY;
     a.thr_idx[pc.qi] = INT_MAX;
+  }
+}
+
+__global__ void __launch_bounds__(kSelWarps * kWarp) value_select_kernel(const ThrArgs a) {
+  const int warp = threadIdx.x >> 5;
+  for (int pid = a.p0 + blockIdx.x * kSelWarps + warp; pid < a.p1; pid += gridDim.x * kSelWarps) {
+    value_select_packet(a, pid);
+    __syncwarp();
   }
 }
 
@@ -356,6 +372,11 @@ __global__ void __launch_bounds__(128) neighbors_debug_kernel(const DbgArgs a) {
 
 }  // namespace
 
+// grid of the selection kernels: enough blocks to fill the GPU several times over, each walking the packets with a stride
+static unsigned sel_grid(const cab_ctx* ctx, int np) {
+  return (unsigned)std::max(1, std::min((np + kSelWarps - 1) / kSelWarps, ctx->sm_count * 32));
+}
+
 int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done, bool halo) {
   const int n = (int)ctx->n;
   cudaStream_t st = ctx->stream;
@@ -386,10 +407,10 @@ int run_thresholds(cab_ctx* ctx, float r, int max_nn, const unsigned char* done,
     if (int rc = reserve(ctx, ctx->b_thr_flag, (size_t)np + 16)) return rc;
     a.fallback = (unsigned char*)ctx->b_thr_flag.p;
     CAB_CUDA(ctx, cudaMemsetAsync(a.fallback, 0, (size_t)np, st));
-    value_select_kernel<<<(np + kSelWarps - 1) / kSelWarps, kSelWarps * kWarp, 0, st>>>(a);
+    value_select_kernel<<<sel_grid(ctx, np), kSelWarps * kWarp, 0, st>>>(a);
     CAB_LAUNCH_CHECK(ctx);
     a.use_fallback = 1;  // packets whose target bin did not fit the list (flag read on the device: no host sync)
-    threshold_kernel<<<(np + kSelWarps - 1) / kSelWarps, kSelWarps * kWarp, 0, st>>>(a);
+    threshold_kernel<<<sel_grid(ctx, np), kSelWarps * kWarp, 0, st>>>(a);
     CAB_LAUNCH_CHECK(ctx);
   }
   return CAB_OK;
@@ -442,10 +463,10 @@ int run_nn_hist(cab_ctx* ctx, float r, int max_nn) {
   // exact (d2, index) thresholds for the flagged packets only
   a.only = flag_a;
   a.fallback = flag_b;
-  value_select_kernel<<<(np + kSelWarps - 1) / kSelWarps, kSelWarps * kWarp, 0, st>>>(a);
+  value_select_kernel<<<sel_grid(ctx, np), kSelWarps * kWarp, 0, st>>>(a);
   CAB_LAUNCH_CHECK(ctx);
   a.use_fallback = 1;
-  threshold_kernel<<<(np + kSelWarps - 1) / kSelWarps, kSelWarps * kWarp, 0, st>>>(a);
+  threshold_kernel<<<sel_grid(ctx, np), kSelWarps * kWarp, 0, st>>>(a);
   CAB_LAUNCH_CHECK(ctx);
   return CAB_OK;
 }

@@ -186,6 +186,49 @@ def test_local_group_input_range_layout(world, max_nn):
         c.close()
 
 
+def test_results_do_not_depend_on_the_cuts():
+    """cab_comm_set_shares moves the cuts (what the measured-time feedback does on clouds large enough to be measured):
+    the ranks answer different numbers of queries, the results keep their bits."""
+    pts = synth.tabletop(90_000, noise_sigma=0.0002)
+    n = pts.shape[0]
+    n4, rmin, rmax, k = _single_gpu(pts)
+    world = 3
+    ctxs = [cab.Context(0) for _ in range(world)]
+    cab.comm_init_local(ctxs)
+    gate = threading.Barrier(world)
+    counts, errs = {}, []
+
+    def work(r):
+        try:
+            c = ctxs[r]
+            c.comm_set_layout(cab.COMM_LAYOUT_INPUT_RANGES)
+            lo, hi = n * r // world, n * (r + 1) // world
+            for shares in ((1, 1, 1), (0.5, 0.2, 0.3), (0.15, 0.7, 0.15)):
+                c.comm_set_shares(shares)
+                c.comm_upload_cloud(pts)
+                c.step_normals_rsd(R, R)
+                p4, pmin, pmax = c.comm_download_range(lo, hi)
+                assert _same(p4, n4[lo:hi]) and _same(pmin, rmin[lo:hi]) and _same(pmax, rmax[lo:hi]), f"rank {r}, shares {shares}"
+                b, e = c.shard_range()
+                counts[(r, shares)] = e - b
+                gate.wait(timeout=60)
+            with pytest.raises(cab.CabError):
+                c.comm_set_shares((1, 2))
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not errs, errs
+    assert counts[(0, (0.5, 0.2, 0.3))] > 1.5 * counts[(1, (0.5, 0.2, 0.3))]
+    assert counts[(1, (0.15, 0.7, 0.15))] > 2 * counts[(0, (0.15, 0.7, 0.15))]
+    for c in ctxs:
+        c.close()
+
+
 def test_local_group_thin_slabs_recompute_their_halos():
     """Eight ranks on a small flat cloud: the slabs are thinner than two layers of rows, so the halo exchange is off and
     every rank recomputes the normals of the rows around its own (shard_mode 1); same results."""
