@@ -308,14 +308,18 @@ int64_t cab_fit_plane_msac(cab_ctx* ctx, const float* xyz, int64_t n, int32_t st
  *   CAB_PFH_AVERAGE       1/d2-weighted average of the neighbours' histograms = FPFH (average_, :303-333)
  *   CAB_PFH_DIFFERENTIAL  bin-to-bin differences (differential_, :337-350)
  *   CAB_PFH_CHECK_FLIP / CAB_PFH_ABS_ANGLES / CAB_PFH_USE_DIST  check_flip_, abs_angles_, use_dist_
- * The plugin's defaults (pfh.h:83-93) are radius 0.03, max_nn 100, quantum 9, CHECK_FLIP | AVERAGE.  The
- * combined n-D histogram (combine_) is not implemented.  hist: n x quantum * (3 or 4) floats, point-major,
- * input order (channel f<b+1> of point i is hist[i * nbins + b]). */
+ *   CAB_PFH_COMBINE       combine_: ONE histogram of quantum ^ (3 or 4) bins per point, the feature indices being the
+ *                         digits of the bin number in the reference's order (:113-121, 239-258); an invalid pair adds
+ *                         100 / k / nbins to every bin (:279-281); no differences (:345).  At most 4096 bins.
+ * The plugin's defaults (pfh.h:83-93) are radius 0.03, max_nn 100, quantum 9, CHECK_FLIP | AVERAGE.  hist: n x nbins
+ * floats, nbins = quantum * (3 or 4), or quantum ^ (3 or 4) with COMBINE, point-major, input order (channel f<b+1> of
+ * point i is hist[i * nbins + b]). */
 #define CAB_PFH_USE_DIST 1
 #define CAB_PFH_DIFFERENTIAL 2
 #define CAB_PFH_CHECK_FLIP 4
 #define CAB_PFH_ABS_ANGLES 8
 #define CAB_PFH_AVERAGE 16
+#define CAB_PFH_COMBINE 32 /* combine_: one n-D histogram of quantum ^ (3 or 4) bins per point (pfh.cpp:47-57, 239-258) */
 int cab_pfh(cab_ctx* ctx, double radius, int32_t max_nn, int32_t quantum, int32_t flags, float* hist);
 
 /* ---- device plumbing (bench / multi-GPU) ---------------------------------------------- */

@@ -15,7 +15,7 @@ _DIR = pathlib.Path(__file__).resolve().parent
 LIB_PATH = _DIR / "csrc" / "libcloudalgos_b200.so"
 _LIB = None
 
-PFH_USE_DIST, PFH_DIFFERENTIAL, PFH_CHECK_FLIP, PFH_ABS_ANGLES, PFH_AVERAGE = 1, 2, 4, 8, 16
+PFH_USE_DIST, PFH_DIFFERENTIAL, PFH_CHECK_FLIP, PFH_ABS_ANGLES, PFH_AVERAGE, PFH_COMBINE = 1, 2, 4, 8, 16, 32
 PFH_DEFAULT = PFH_CHECK_FLIP | PFH_AVERAGE
 RSD_SEED_BIN0 = 2
 RSD_SCALE_SORT = 4
@@ -330,7 +330,8 @@ class Context:
 
     # ---- point feature histograms -----------------------------------------------------
     def pfh(self, radius: float = 0.03, max_nn: int = 100, quantum: int = 9, flags: int = PFH_DEFAULT):
-        nb = quantum * (4 if flags & PFH_USE_DIST else 3)
+        nf = 4 if flags & PFH_USE_DIST else 3
+        nb = quantum ** nf if flags & PFH_COMBINE else quantum * nf
         out = np.zeros((self.n, nb), np.float32)
         self._check(self._L.cab_pfh(self._h, C.c_double(radius), C.c_int32(max_nn), C.c_int32(quantum), C.c_int32(flags), _fp(out)),
                     "cab_pfh")

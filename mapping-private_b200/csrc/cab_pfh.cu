@@ -17,6 +17,8 @@
 #include <cstring>
 
 #include "cab_internal.cuh"
+#include <cub/device/device_scan.cuh>
+
 #include "cab_traverse.cuh"
 
 namespace cab {
@@ -236,7 +238,212 @@ __global__ void __launch_bounds__(256) pfh_finish_kernel(const float* __restrict
   }
 }
 
+// ---- combine_ = true: one n-D histogram of quantum ^ features bins per point (pfh.cpp:47-57, 239-258, 279-281) --------
+// The bins no longer fit lane-private shared memory (9^3 = 729, 5^4 = 625 ...): a lane counts its query's pairs in the
+// query's own row of a global int array (no other lane touches that row), a second kernel turns counts into the
+// reference's floats, and the FPFH average runs warp per query over materialised neighbour lists so that the neighbours'
+// long rows are read coalesced.
+struct PfhCombineArgs {
+  int* cnt;              // sorted order, n x nbins pair counts
+  int* ninv;             // sorted order: invalid pairs per query
+  const int* list_off;   // sorted order: first list entry of the query (exclusive scan of kcount)
+  int2* list;            // (sorted index, d2 bits) of every kept neighbour but the query itself
+  int slot[4];           // digit of feature f (alpha, beta, gamma, delta) in the bin index (:113-121)
+};
+
+template <bool kUseThr, bool kLists>
+__global__ void __launch_bounds__(kWarpsPerBlock * kWarp) pfh_combine_kernel(const PfhArgs a, const PfhCombineArgs ca) {
+  __shared__ ChunkTile tiles[kWarpsPerBlock];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pid = a.p0 + blockIdx.x * kWarpsPerBlock + warp;
+  if (pid >= a.p1) return;
+  ChunkTile* tile = &tiles[warp];
+  const PacketCtx pc = load_packet(a.g, pid, lane, a.r, tile);
+  const float4 nq = a.nrm[pc.qi];
+  const bool check_flip = a.flags & CAB_PFH_CHECK_FLIP, abs_angles = a.flags & CAB_PFH_ABS_ANGLES;
+  int* row = ca.cnt + (size_t)pc.qi * a.nbins;
+  int ninv = 0, filled = 0;
+  const int base = kLists ? ca.list_off[pc.qi] : 0;
+  const int k = visit_neighbours<kUseThr>(a, pc, lane, tile, [&](int m, float d2, float cx, float cy, float cz, float nx, float ny, float nz) {
+    if (!pc.active) return;
+    if (kLists) {
+      ca.list[base + filled] = make_int2(tile->idx[m], __float_as_int(d2));
+      ++filled;
+      return;
+    }
+    double f[4];
+    if (pair_features(pc.q.x, pc.q.y, pc.q.z, nq.x, nq.y, nq.z, cx, cy, cz, nx, ny, nz, d2, a.max_dist, check_flip, abs_angles, f)) {
+      int index = 0, fi[4] = {0, 0, 0, 0};
+      for (int ft = 0; ft < a.nfeat; ++ft)
+        fi[ca.slot[ft]] = max(0, min(a.quantum - 1, __double2int_rd(__dmul_rn((double)a.quantum, f[ft]))));
+      int power = 1;
+      for (int d = 0; d < a.nfeat; ++d) {
+        index += power * fi[d];
+        power *= a.quantum;
+      }
+      row[index] += 1;
+    } else {
+      ++ninv;
+    }
+  });
+  if (pc.active && !kLists) {
+    ca.ninv[pc.qi] = ninv;
+    a.kcount[pc.qi] = k;
+  }
+}
+
+// counts -> the reference's floats: every valid pair added npsqr = 100 / k to its bin, every invalid one npsqr / nr_bins
+// to all bins (pfh.cpp:212, 251-258, 279-281); histograms are floats, the increment a double
+__global__ void __launch_bounds__(256) pfh_combine_fill_kernel(const int* __restrict__ cnt, const int* __restrict__ ninv,
+                                                               const int* __restrict__ kcount, int n_valid, int nbins, int stride,
+                                                               float* __restrict__ spfh) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_valid * stride) return;
+  const int i = (int)(t / stride), b = (int)(t % stride);
+  float h = 0.f;
+  if (b < nbins) {
+    const double npsqr = 100.0 / (double)kcount[i], spread = npsqr / (double)nbins;
+    for (int c = cnt[(size_t)i * nbins + b]; c > 0; --c) h = (float)((double)h + npsqr);
+    for (int c = ninv[i]; c > 0; --c) h = (float)((double)h + spread);
+  }
+  spfh[t] = h;
+}
+
+// FPFH step (pfh.cpp:303-333) for long rows: one warp per query, lanes across the bins
+__global__ void __launch_bounds__(256) pfh_combine_average_kernel(const float* __restrict__ spfh, const int* __restrict__ list_off,
+                                                                  const int2* __restrict__ list, const int* __restrict__ kcount,
+                                                                  int n_valid, int nbins, int stride, float* __restrict__ out) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (q >= n_valid) return;
+  const int first = list_off[q], count = max(kcount[q] - 1, 0);  // the query itself is not listed (:317)
+  double sum_weight = 0.0;
+  for (int e = 0; e < count; ++e) sum_weight += 1.0 / (double)__int_as_float(list[first + e].y);
+  for (int b0 = 0; b0 < stride; b0 += 8 * kWarp) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int e = 0; e < count; ++e) {
+      const int2 en = list[first + e];
+      const double weight = 1.0 / (double)__int_as_float(en.y);
+      const float* hn = spfh + (size_t)en.x * stride;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int b = b0 + j * kWarp + lane;
+        if (b < nbins) acc[j] = (float)((double)acc[j] + (double)hn[b] * weight);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j * kWarp + lane;
+      if (b < stride) out[(size_t)q * stride + b] = b < nbins ? (float)((double)acc[j] / sum_weight) : 0.f;  // 0 / 0 = NaN without neighbours (:330)
+    }
+  }
+}
+
+// the way back to input order, point-major rows of nbins floats (no differences in the combined mode, :345)
+__global__ void __launch_bounds__(256) pfh_combine_finish_kernel(const float* __restrict__ rows, int stride, int nbins,
+                                                                 const int* __restrict__ perm, int n_valid, float* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_valid * nbins) return;
+  const int i = (int)(t / nbins), b = (int)(t % nbins);
+  const int dst = perm[i];
+  if (dst >= 0) out[(size_t)dst * nbins + b] = rows[(size_t)i * stride + b];
+}
+
 }  // namespace
+
+static int run_pfh_combined(cab_ctx* ctx, double radius, int max_nn, int quantum, int flags, float* out_host) {
+  const float rf = (float)radius;
+  const int nfeat = (flags & CAB_PFH_USE_DIST) ? 4 : 3;
+  long long nb = 1;
+  for (int f = 0; f < nfeat; ++f) nb *= quantum;  // (int) ceil (pow (quantum_, nr_features_)), pfh.cpp:51
+  if (nb > 4096) return fail(ctx, CAB_ERR_ARG, "cab_pfh: quantum ^ features = %lld bins, at most 4096", nb);
+  const int nbins = (int)nb, stride = (nbins + 3) & ~3;
+  const int n = (int)ctx->n, nv = ctx->n_valid;
+  cudaStream_t st = ctx->stream;
+  const size_t rows = (size_t)std::max(n, 1);
+  if (rows * (size_t)stride > ((size_t)1 << 31)) return fail(ctx, CAB_ERR_OOM, "cab_pfh: %d points x %d bins is more than the combined mode handles", n, nbins);
+  if (int rc = reserve(ctx, ctx->b_pfh[0], rows * stride * sizeof(float))) return rc;
+  if (int rc = reserve(ctx, ctx->b_pfh[1], rows * stride * sizeof(float))) return rc;
+  if (int rc = reserve(ctx, ctx->b_pfh[2], rows * nbins * sizeof(float))) return rc;
+  if (int rc = reserve(ctx, ctx->b_out4, rows * nbins * sizeof(int))) return rc;          // pair counts
+  if (int rc = reserve(ctx, ctx->b_out1a, rows * sizeof(int))) return rc;                  // invalid pairs
+  if (int rc = reserve(ctx, ctx->b_out1b, (rows + 1) * sizeof(int))) return rc;            // list offsets
+  if (int rc = reserve(ctx, ctx->b_kcount, rows * sizeof(int))) return rc;
+  const bool use_thr = max_nn > 0;
+  if (use_thr)
+    if (int rc = run_thresholds(ctx, rf, max_nn)) return rc;
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+  PfhArgs a{};
+  a.g = grid_view(ctx);
+  packet_range(ctx, &a.p0, &a.p1);
+  a.r = rf;
+  a.r2 = rf * rf;
+  a.nrm = (const float4*)ctx->b_nrm.p;
+  a.thr_d2 = use_thr ? (const float*)ctx->b_thr_d2.p : nullptr;
+  a.thr_idx = use_thr ? (const int*)ctx->b_thr_idx.p : nullptr;
+  a.quantum = quantum;
+  a.nfeat = nfeat;
+  a.nbins = nbins;
+  a.stride = stride;
+  a.flags = flags;
+  a.max_dist = 2 * radius;
+  a.spfh = (float*)ctx->b_pfh[0].p;
+  a.out = (float*)ctx->b_pfh[1].p;
+  a.kcount = (int*)ctx->b_kcount.p;
+  PfhCombineArgs ca{};
+  ca.cnt = (int*)ctx->b_out4.p;
+  ca.ninv = (int*)ctx->b_out1a.p;
+  ca.list_off = (const int*)ctx->b_out1b.p;
+  // The order of the features in the histogram binning (:113-121): a_, b_, c_, d_ = 3, 0, 2, 1 with the distance, 2, 0, 1 without
+  const int slot4[4] = {3, 0, 2, 1}, slot3[4] = {2, 0, 1, 3};
+  for (int f = 0; f < 4; ++f) ca.slot[f] = nfeat == 4 ? slot4[f] : slot3[f];
+  const int np = a.p1 - a.p0;
+  const float* result = a.spfh;
+  CAB_CUDA(ctx, cudaMemsetAsync(ca.cnt, 0, rows * nbins * sizeof(int), st));
+  CAB_CUDA(ctx, cudaMemsetAsync(ca.ninv, 0, rows * sizeof(int), st));
+  CAB_CUDA(ctx, cudaMemsetAsync(a.kcount, 0, rows * sizeof(int), st));
+  if (np > 0 && nv > 0) {
+    const unsigned blocks = (np + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (use_thr) pfh_combine_kernel<true, false><<<blocks, kWarpsPerBlock * kWarp, 0, st>>>(a, ca);
+    else pfh_combine_kernel<false, false><<<blocks, kWarpsPerBlock * kWarp, 0, st>>>(a, ca);
+    CAB_LAUNCH_CHECK(ctx);
+    const long long elems = (long long)nv * stride;
+    pfh_combine_fill_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(ca.cnt, ca.ninv, a.kcount, nv, nbins, stride, a.spfh);
+    CAB_LAUNCH_CHECK(ctx);
+    if (flags & CAB_PFH_AVERAGE) {
+      size_t tmp = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int*)nullptr, (int*)nullptr, nv + 1, st);
+      if (int rc = reserve(ctx, ctx->b_cubtmp, tmp + 16)) return rc;
+      CAB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_cubtmp.p, tmp, (const int*)a.kcount, (int*)ctx->b_out1b.p, nv + 1, st));
+      int total = 0;
+      CAB_CUDA(ctx, cudaMemcpyAsync(&total, (const int*)ctx->b_out1b.p + nv, 4, cudaMemcpyDeviceToHost, st));
+      CAB_CUDA(ctx, cudaStreamSynchronize(st));
+      if (int rc = reserve(ctx, ctx->b_keys[2], (size_t)std::max(total, 1) * sizeof(int2))) return rc;
+      ca.list = (int2*)ctx->b_keys[2].p;
+      if (use_thr) pfh_combine_kernel<true, true><<<blocks, kWarpsPerBlock * kWarp, 0, st>>>(a, ca);
+      else pfh_combine_kernel<false, true><<<blocks, kWarpsPerBlock * kWarp, 0, st>>>(a, ca);
+      CAB_LAUNCH_CHECK(ctx);
+      pfh_combine_average_kernel<<<(unsigned)(((long long)nv * kWarp + 255) / 256), 256, 0, st>>>(a.spfh, ca.list_off, ca.list, a.kcount, nv,
+                                                                                                  nbins, stride, a.out);
+      CAB_LAUNCH_CHECK(ctx);
+      result = a.out;
+    }
+  }
+  CAB_CUDA(ctx, cudaMemsetAsync(ctx->b_pfh[2].p, 0, rows * nbins * sizeof(float), st));
+  if (nv > 0) {
+    const long long elems = (long long)nv * nbins;
+    pfh_combine_finish_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(result, stride, nbins, (const int*)ctx->b_perm.p, nv,
+                                                                              (float*)ctx->b_pfh[2].p);
+    CAB_LAUNCH_CHECK(ctx);
+  }
+  CAB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+  if (out_host && n > 0)
+    CAB_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->b_pfh[2].p, (size_t)n * nbins * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CAB_CUDA(ctx, cudaStreamSynchronize(st));
+  CAB_CUDA(ctx, cudaEventElapsedTime(&ctx->tm.pfh_ms, ctx->ev[2], ctx->ev[3]));
+  return CAB_OK;
+}
 
 int run_pfh(cab_ctx* ctx, double radius, int max_nn, int quantum, int flags, float* out_host) {
   if (!ctx->have_grid) return fail(ctx, CAB_ERR_STATE, "cab_pfh: build the grid first");
@@ -246,8 +453,11 @@ int run_pfh(cab_ctx* ctx, double radius, int max_nn, int quantum, int flags, flo
   if (!(rf > 0.f) || rf > ctx->cell * 1.0000001f)
     return fail(ctx, CAB_ERR_ARG, "cab_pfh: radius %g exceeds the grid cell %g", radius, (double)ctx->cell);
   const int nfeat = (flags & CAB_PFH_USE_DIST) ? 4 : 3;
+  const bool combine = (flags & CAB_PFH_COMBINE) != 0;
+  if (quantum < 1) return fail(ctx, CAB_ERR_ARG, "cab_pfh: quantum must be >= 1");
+  if (combine) return run_pfh_combined(ctx, radius, max_nn, quantum, flags, out_host);
   const int nbins = quantum * nfeat;
-  if (quantum < 1 || nbins > kPfhMaxBins) return fail(ctx, CAB_ERR_ARG, "cab_pfh: quantum * features must be in [1, %d]", kPfhMaxBins);
+  if (nbins > kPfhMaxBins) return fail(ctx, CAB_ERR_ARG, "cab_pfh: quantum * features must be in [1, %d]", kPfhMaxBins);
   const int n = (int)ctx->n;
   const int stride = (nbins + 3) & ~3;
   cudaStream_t st = ctx->stream;

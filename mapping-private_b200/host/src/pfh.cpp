@@ -2,8 +2,7 @@
 // Contract of cloud_algos/src/pfh.cpp of the reference: rosparams read in pre() (:12-24), requires x, y, z, nx,
 // ny, nz (:31-43), provides f1..f<nr_bins> (+ point_label) with nr_bins = quantum * (3 or 4) (:45-76); process()
 // returns "missing normals" without the nx channel (:81-95), copies the cloud, appends the feature channels
-// (:127-163) and fills them (:205-350).  The combined n-D histogram (combine_, :251-265) is not implemented: such a
-// request fails loudly instead of silently computing something else.
+// (:127-163) and fills them (:205-350), the combined n-D histogram (combine_, :251-265) included.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -75,13 +74,7 @@ std::string PointFeatureHistogram::process (const boost::shared_ptr<const PointF
     return std::string ("missing normals");
   }
   nr_features_ = use_dist_ ? 4 : 3;
-  if (combine_)
-  {
-    output_valid_ = false;
-    ROS_ERROR ("[PointFeatureHistogram] combined (n-D) histograms are not implemented on the GPU path");
-    return std::string ("unsupported options: combine is not implemented");
-  }
-  nr_bins_ = quantum_ * nr_features_;
+  nr_bins_ = combine_ ? (int) ceil (pow (quantum_, nr_features_)) : quantum_ * nr_features_;  // :98-108
   std::string err;
   cab_ctx* ctx = gpu_.get (err);
   if (!ctx) { output_valid_ = false; ROS_ERROR ("[PointFeatureHistogram] %s", err.c_str ()); return err; }
@@ -109,7 +102,7 @@ std::string PointFeatureHistogram::process (const boost::shared_ptr<const PointF
 
   const int flags = (use_dist_ ? CAB_PFH_USE_DIST : 0) | (differential_ ? CAB_PFH_DIFFERENTIAL : 0) |
                     (check_flip_ ? CAB_PFH_CHECK_FLIP : 0) | (abs_angles_ ? CAB_PFH_ABS_ANGLES : 0) |
-                    (average_ ? CAB_PFH_AVERAGE : 0);
+                    (average_ ? CAB_PFH_AVERAGE : 0) | (combine_ ? CAB_PFH_COMBINE : 0);
   std::vector<float> hist (n * (size_t) nr_bins_);
   int rc = CAB_OK;
   if (n)

@@ -1475,7 +1475,12 @@ int orc_pfh(const float* xyz, const float* normals, int normal_stride, int n, do
   if (quantum < 1) return -1;
   const bool use_dist = flags & ORC_PFH_USE_DIST, differential = flags & ORC_PFH_DIFFERENTIAL;
   const bool check_flip = flags & ORC_PFH_CHECK_FLIP, abs_angles = flags & ORC_PFH_ABS_ANGLES, average = flags & ORC_PFH_AVERAGE;
-  const int nr_features = use_dist ? 4 : 3, nr_bins = quantum * nr_features;
+  const bool combine = flags & ORC_PFH_COMBINE;
+  const int nr_features = use_dist ? 4 : 3;
+  const int nr_bins = combine ? (int)std::ceil(std::pow((double)quantum, (double)nr_features)) : quantum * nr_features;  // :47-57
+  // the order of the features in the n-D histogram (:113-121): fi[slot[f]] = index of feature f (alpha, beta, gamma, delta)
+  const int slot4[4] = {3, 0, 2, 1}, slot3[4] = {2, 0, 1, 3};
+  const int* slot = use_dist ? slot4 : slot3;
   CellGrid grid(xyz, n, radius);
   const float r2 = r2_of(radius);
   nthreads = resolve_threads(nthreads);
@@ -1495,10 +1500,24 @@ int orc_pfh(const float* xyz, const float* normals, int normal_stride, int n, do
         double f[4];
         if (orc_pfh_pair(xyz + 3 * (size_t)cp, normals + (size_t)normal_stride * cp, xyz + 3 * (size_t)j,
                          normals + (size_t)normal_stride * j, nbs[ni].d2, 2 * radius, check_flip, abs_angles, f)) {
-          for (int ft = 0; ft < nr_features; ++ft) {  // :224-228, :267-271 with a_, b_, c_, d_ = 0, 1, 2, 3
-            const int fi = std::max(0, std::min(quantum - 1, (int)std::floor(quantum * f[ft])));
-            h[ft * quantum + fi] += npsqr;  // float += double
+          if (combine) {  // :239-258: the feature indices as the digits of a number in base quantum
+            int fi[4] = {0, 0, 0, 0};
+            for (int ft = 0; ft < nr_features; ++ft)
+              fi[slot[ft]] = std::max(0, std::min(quantum - 1, (int)std::floor(quantum * f[ft])));
+            int index = 0, power = 1;
+            for (int d = 0; d < nr_features; ++d) {
+              index += power * fi[d];
+              power *= quantum;
+            }
+            h[index] += npsqr;
+          } else {
+            for (int ft = 0; ft < nr_features; ++ft) {  // :224-228, :267-271 with a_, b_, c_, d_ = 0, 1, 2, 3
+              const int fi = std::max(0, std::min(quantum - 1, (int)std::floor(quantum * f[ft])));
+              h[ft * quantum + fi] += npsqr;  // float += double
+            }
           }
+        } else if (combine) {
+          for (int i = 0; i < nr_bins; i++) h[i] += npsqr / nr_bins;  // :279-281
         } else {
           for (int i = 0; i < nr_bins; i++) h[i] += npsqr / quantum;  // :284-286
         }
@@ -1525,7 +1544,7 @@ int orc_pfh(const float* xyz, const float* normals, int normal_stride, int n, do
         for (int b = 0; b < nr_bins; ++b) o[b] /= sum_weight;  // :330-331
       }
     }
-    if (differential)  // :337-350
+    if (differential && !combine)  // :337-350 (:345 !combine_ && differential_)
       for (int ft = 0; ft < nr_features; ++ft)
         for (int b = quantum - 1; b > 0; b--) o[ft * quantum + b] -= o[ft * quantum + b - 1];
   }

@@ -188,8 +188,8 @@ int64_t orc_noise_filter(const double* avg, int n, double alpha, uint8_t* keep, 
  * neighbours within `radius` (<= max_nn nearest, self first and skipped), one 1-D histogram of `quantum`
  * bins per feature (alpha, beta, gamma [, delta]) with increments of 100 / k, then -- with
  * ORC_PFH_AVERAGE, the FPFH step -- the 1/d2-weighted average of the neighbours' histograms (:303-333) and,
- * with ORC_PFH_DIFFERENTIAL, bin-to-bin differences (:337-350).  The combined n-D histogram mode
- * (combine_ = true) is not restated.  out: n x nr_bins floats, point-major, nr_bins = quantum * (3 or 4).
+ * with ORC_PFH_DIFFERENTIAL, bin-to-bin differences (:337-350).  ORC_PFH_COMBINE: the combined n-D histogram mode
+ * (combine_ = true).  out: n x nr_bins floats, point-major, nr_bins = quantum * (3 or 4), or quantum ^ (3 or 4).
  * Quirks kept: a point whose only neighbour is itself gets 0/0 = NaN with ORC_PFH_AVERAGE; a duplicate
  * neighbour (d2 == 0) yields an invalid pair (increment spread over all bins, :277-287) and an infinite
  * weight. */
@@ -198,6 +198,7 @@ int64_t orc_noise_filter(const double* avg, int n, double alpha, uint8_t* keep, 
 #define ORC_PFH_CHECK_FLIP 4
 #define ORC_PFH_ABS_ANGLES 8
 #define ORC_PFH_AVERAGE 16
+#define ORC_PFH_COMBINE 32 /* combine_: one n-D histogram of quantum^features bins (pfh.cpp:47-57, 239-258, 279-281) */
 int orc_pfh(const float* xyz, const float* normals, int normal_stride, int n, double radius, int max_nn,
             int quantum, int flags, float* out, int nthreads);
 /* One pair (pfh.h:102-238): returns 0 if the pair is invalid, else 1 and alpha, beta, gamma, delta in f[4]

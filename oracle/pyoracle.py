@@ -399,7 +399,7 @@ def noise_filter(avg, alpha):
     return keep.astype(bool), mean.value, std.value
 
 
-PFH_USE_DIST, PFH_DIFFERENTIAL, PFH_CHECK_FLIP, PFH_ABS_ANGLES, PFH_AVERAGE = 1, 2, 4, 8, 16
+PFH_USE_DIST, PFH_DIFFERENTIAL, PFH_CHECK_FLIP, PFH_ABS_ANGLES, PFH_AVERAGE, PFH_COMBINE = 1, 2, 4, 8, 16, 32
 PFH_DEFAULT = PFH_CHECK_FLIP | PFH_AVERAGE  # the plugin's defaults produce FPFHs (pfh.h:83-93)
 
 
@@ -408,7 +408,8 @@ def pfh(xyz, nrm, radius=0.03, max_nn=100, quantum=9, flags=PFH_DEFAULT, nthread
     L = lib()
     p = _xyz(xyz)
     nn = np.ascontiguousarray(nrm, dtype=np.float32)
-    nb = quantum * (4 if flags & PFH_USE_DIST else 3)
+    nf = 4 if flags & PFH_USE_DIST else 3
+    nb = quantum ** nf if flags & PFH_COMBINE else quantum * nf
     out = np.zeros((p.shape[0], nb), np.float32)
     rc = L.orc_pfh(_ptr(p, C.c_float), _ptr(nn, C.c_float), int(nn.shape[1]), p.shape[0], C.c_double(radius), int(max_nn),
                    int(quantum), int(flags), _ptr(out, C.c_float), int(nthreads))

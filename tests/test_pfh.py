@@ -77,6 +77,46 @@ def test_histogram_invariants(oracle):
     assert np.all((m > 85) & (m < 100.001))
 
 
+def test_combined_histogram_invariants(oracle):
+    """combine_ = true (pfh.cpp:47-57, 239-258): one n-D histogram; its marginals are the 1-D histograms."""
+    pts = synth.tabletop(4000, noise_sigma=0.0003)
+    nrm = np.nan_to_num(oracle.normals(pts, 0.02)[0][:, :3], nan=0.0)
+    q = 5
+    sep = oracle.pfh(pts, nrm, quantum=q, flags=oracle.PFH_CHECK_FLIP)
+    com = oracle.pfh(pts, nrm, quantum=q, flags=oracle.PFH_CHECK_FLIP | oracle.PFH_COMBINE)
+    assert com.shape == (pts.shape[0], q ** 3)
+    cube = com.reshape(-1, q, q, q)  # index = fi[0] + q fi[1] + q^2 fi[2]: axes (fi[2], fi[1], fi[0]) = (alpha, gamma, beta)
+    assert np.allclose(cube.sum((2, 3)), sep[:, 0:q], atol=2e-3)        # alpha
+    assert np.allclose(cube.sum((1, 2)), sep[:, q:2 * q], atol=2e-3)    # beta
+    assert np.allclose(cube.sum((1, 3)), sep[:, 2 * q:3 * q], atol=2e-3)  # gamma
+    com4 = oracle.pfh(pts, nrm, quantum=3, flags=oracle.PFH_CHECK_FLIP | oracle.PFH_COMBINE | oracle.PFH_USE_DIST)
+    assert com4.shape[1] == 81
+    # the differential option is ignored in the combined mode (:345)
+    assert np.array_equal(com, oracle.pfh(pts, nrm, quantum=q, flags=oracle.PFH_CHECK_FLIP | oracle.PFH_COMBINE | oracle.PFH_DIFFERENTIAL))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags,max_nn,quantum", [(4 | 32, 100, 9), (4 | 16 | 32, 100, 5), (4 | 16 | 1 | 32, 0, 4), (8 | 32 | 2, 60, 6)])
+def test_gpu_combined_pfh_matches_oracle(oracle, flags, max_nn, quantum):
+    ctx = cab.Context(0)
+    pts = synth.tabletop(9_000, noise_sigma=0.0003, seed_extra=flags)
+    nrm = np.nan_to_num(oracle.normals(pts, 0.02)[0][:, :3], nan=0.0)
+    ctx.upload(pts)
+    ctx.build_grid(0.03)
+    ctx.set_normals(nrm)
+    got = ctx.pfh(0.03, max_nn, quantum, flags)
+    want = oracle.pfh(pts, nrm, 0.03, max_nn, quantum, flags)
+    assert got.shape == want.shape == (pts.shape[0], quantum ** (4 if flags & 1 else 3))
+    if not flags & 16:
+        assert np.mean(np.any(got != want, axis=1)) < 3e-3  # a feature within an ulp of a bin edge moves one count
+        assert np.allclose(got.sum(1), want.sum(1), rtol=1e-5)
+    else:
+        assert np.allclose(got, want, rtol=2e-4, atol=2e-3)
+    with pytest.raises(cab.CabError, match="at most 4096"):
+        ctx.pfh(0.03, max_nn, 17, 4 | 32)
+    ctx.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("flags,max_nn,quantum", [(4, 100, 9), (4 | 16, 100, 9), (4 | 16 | 1, 0, 7), (8 | 16 | 2, 60, 5), (16, 100, 9)])
 def test_gpu_pfh_matches_oracle(oracle, flags, max_nn, quantum):

@@ -110,9 +110,11 @@ def test_pfh_plugin_surface_and_errors(built):
     res, out = pf.run(pts, {"intensity": np.zeros(50, np.float32)})
     assert res == "missing normals" and out is None
     nrm = {"nx": np.zeros(50, np.float32), "ny": np.zeros(50, np.float32), "nz": np.ones(50, np.float32)}
-    res, out = pf.run(pts, nrm, fields={"combine_": 1})
-    assert res.startswith("unsupported options") and out is None and not pf.output_valid()
+    pf.set_field("combine_", 1)
+    pf.set_field("quantum_", 4)
+    assert pf.requires_provides()[1] == [f"f{i}" for i in range(1, 4 ** 3 + 1)]  # pfh.cpp:49-52: quantum ^ features bins
     pf.set_field("combine_", 0)
+    pf.set_field("quantum_", 9)
     pf.set_field("use_dist_", 1)
     pf.set_field("point_label_", 3)
     assert pf.requires_provides()[1] == [f"f{i}" for i in range(1, 37)] + ["point_label"]
