@@ -606,7 +606,10 @@ def main():
         """One pass of the hot path over the cloud in ONE C call: grid build + normals + RSD and, in a group, the
         concatenation of the ranks' results (input order, rank g holding the g-th N-th of the input indices)."""
         c.set_cloud_device(d_xyz.data_ptr(), n, 3)
-        c.step_normals_rsd(RADIUS, RADIUS, max_nn_rsd=max_nn_rsd, ndiv=NDIV, plane_radius=PLANE_RADIUS)
+        # at every N the step leaves the channels of radius_estimation.cpp:204-214 in INPUT order on the device: a group's
+        # ranks hold one input range each, a single context all of it (CAB_STEP_INPUT_ORDER: scattered by the RSD kernel)
+        c.step_normals_rsd(RADIUS, RADIUS, max_nn_rsd=max_nn_rsd, ndiv=NDIV, plane_radius=PLANE_RADIUS,
+                           flags=cab.STEP_INPUT_ORDER if world == 1 else 0)
 
     for _ in range(warmup):
         step()
@@ -653,6 +656,17 @@ def main():
     kbar = neighbour_sum / n
 
     concatenated = None
+    if world == 1:
+        # the input-order arrays the timed step left on the device against the sorted arrays + permutation (cab_download)
+        p4 = ctx.device_ptr(cab.BUF_NRM_INPUT_RANGE)
+        p2 = ctx.device_ptr(cab.BUF_RSD_INPUT_RANGE)
+        in4 = torch.as_tensor(_DevArray(p4, (n, 4), "<i4"), device=dev)
+        in2 = torch.as_tensor(_DevArray(p2, (n, 2), "<i4"), device=dev)
+        f4, fmin, fmax = ctx.download()
+        same = bool(np.array_equal(in4.cpu().numpy(), f4.view(np.int32)) and np.array_equal(in2[:, 0].cpu().numpy(), fmin.view(np.int32))
+                    and np.array_equal(in2[:, 1].cpu().numpy(), fmax.view(np.int32)))
+        concatenated = {"layout": "input order on the device (one context holds all points)", "equals_cab_download": same, "points": n}
+        del in4, in2, f4, fmin, fmax
     if world > 1:
         # the concatenation is part of the timed step: poison every rank's range, run one more step, and count the
         # entries the ranks' RSD kernels (and, for non-finite points, the owner's selection pass) have written

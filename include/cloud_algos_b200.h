@@ -31,6 +31,10 @@ extern "C" {
  * (cloud_algos/src/radius_estimation.cpp:140-215). */
 #define CAB_RSD_SEED_BIN0 2  /* bin 0 starts at angle 0 (newer pcl::computeRSD) */
 #define CAB_RSD_SCALE_SORT 4 /* r_min*=1.1, r_max*=0.9, then ordered (newer pcl::computeRSD) */
+#define CAB_STEP_INPUT_ORDER 0x100 /* cab_step_normals_rsd on a context outside a group: the RSD kernel also leaves normals +
+                                      curvature (float4) and r_min, r_max (float2) of every point in INPUT order on the device
+                                      (cab_device_ptr CAB_BUF_NRM_INPUT_RANGE / CAB_BUF_RSD_INPUT_RANGE: the channels
+                                      radius_estimation.cpp:204-214 appends) -- what a group's step leaves rank by rank */
 
 typedef struct cab_ctx cab_ctx;
 

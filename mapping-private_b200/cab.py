@@ -19,6 +19,7 @@ PFH_USE_DIST, PFH_DIFFERENTIAL, PFH_CHECK_FLIP, PFH_ABS_ANGLES, PFH_AVERAGE, PFH
 PFH_DEFAULT = PFH_CHECK_FLIP | PFH_AVERAGE
 RSD_SEED_BIN0 = 2
 RSD_SCALE_SORT = 4
+STEP_INPUT_ORDER = 0x100
 SIG_GRSD21, SIG_GRSD325, SIG_PLUSGRSD110 = 0, 1, 2
 SIG_DIM = {0: 21, 1: 325, 2: 110}
 BUF_POS_SORTED, BUF_NRM_SORTED, BUF_RSD_SORTED, BUF_PERM = 0, 1, 2, 3

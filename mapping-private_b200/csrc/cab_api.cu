@@ -308,7 +308,7 @@ void cab_destroy(cab_ctx* ctx) {
                     &ctx->b_keys[1], &ctx->b_keys[2], &ctx->b_vals[0], &ctx->b_vals[1], &ctx->b_vals[2], &ctx->b_thr_flag, &ctx->b_knn_avg, &ctx->b_knn_done, &ctx->b_pfh[0], &ctx->b_pfh[1], &ctx->b_pfh[2], &ctx->b_cluster, &ctx->b_cubtmp, &ctx->b_pos, &ctx->b_perm,
                     &ctx->b_cellcnt, &ctx->b_cellstart, &ctx->b_rowpk, &ctx->b_packets, &ctx->b_nrm, &ctx->b_nrm_in,
                     &ctx->b_rsd, &ctx->b_rdif, &ctx->b_kcount, &ctx->b_stats, &ctx->b_out4, &ctx->b_out1a, &ctx->b_out1b,
-                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_slab, &ctx->b_sel, &ctx->b_stats2, &ctx->b_sorttmp, &ctx->b_occ, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
+                    &ctx->b_thr_d2, &ctx->b_thr_idx, &ctx->b_misc, &ctx->b_pcost, &ctx->b_slab, &ctx->b_sel, &ctx->b_stats2, &ctx->b_sorttmp, &ctx->b_occ, &ctx->b_in_nrm, &ctx->b_in_rsd, &ctx->g_vkeys[0], &ctx->g_vkeys[1], &ctx->g_vvals[0],
                     &ctx->g_vvals[1], &ctx->g_cent, &ctx->g_vcount, &ctx->g_vrad, &ctx->g_vlabel, &ctx->g_voff,
                     &ctx->g_layout, &ctx->g_layoff, &ctx->g_vgrid, &ctx->g_hist, &ctx->g_vfirst, &ctx->g_cnrm, &ctx->g_invperm, &ctx->g_sig, &ctx->g_sigdom, &ctx->g_color, &ctx->g_vown};
   for (DevBuf* b : bufs)
@@ -415,6 +415,8 @@ void* cab_device_ptr(cab_ctx* ctx, int32_t which) {
     case CAB_BUF_NRM_SORTED: return ctx->b_nrm.p;
     case CAB_BUF_RSD_SORTED: return ctx->b_rsd.p;
     case CAB_BUF_PERM: return ctx->b_perm.p;
+    case CAB_BUF_NRM_INPUT_RANGE: return ctx->have_input_order ? ctx->b_in_nrm.p : nullptr;  // CAB_STEP_INPUT_ORDER
+    case CAB_BUF_RSD_INPUT_RANGE: return ctx->have_input_order ? ctx->b_in_rsd.p : nullptr;
     default: return nullptr;
   }
 }
@@ -564,6 +566,13 @@ int cab_step_normals_rsd(cab_ctx* ctx, float cell, double r, int32_t max_nn_norm
   } deferred(ctx);
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[8], st));
   int rc = CAB_OK;
+  ctx->have_input_order = false;
+  struct InputOrder {  // the RSD pass of this call scatters its results into input-order arrays (outside a group)
+    cab_ctx* c;
+    InputOrder(cab_ctx* x, bool on) : c(x) { c->step_input_order = on; }
+    ~InputOrder() { c->step_input_order = false; }
+  } input_order(ctx, (flags & CAB_STEP_INPUT_ORDER) != 0 && !exchange && ctx->shard_world == 1);
+  flags &= ~CAB_STEP_INPUT_ORDER;
   if (exchange) rc = comm_prepare(ctx, ctx->n);  // before the build: the working normals move into the exported buffer
   ctx->want_halo_exchange = exchange && rc == CAB_OK;
   if (ctx->want_halo_exchange) {

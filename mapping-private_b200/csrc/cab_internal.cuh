@@ -185,6 +185,8 @@ struct cab_ctx {
   int64_t n_sorted = 0;            // entries of the sorted arrays: n, or the slab window's points
   int halo_permille = 470;         // share of the normals pass in a packet's cost (shard balance)
   bool want_halo_exchange = false; // set by cab_step_normals_rsd of a group: build_slab may choose the exchange mode
+  bool step_input_order = false;   // CAB_STEP_INPUT_ORDER: the RSD kernel of this step also scatters the results into b_in_nrm / b_in_rsd
+  bool have_input_order = false;   // ... and they are there
   bool defer_sync = false;         // run_normals / run_rsd leave the stream running (cab_step_*: one sync per step)
   std::vector<double> shard_cum;   // empty: equal shares; else world + 1 cumulative shares of the modelled cost (0 ... 1), the
                                    // group's measured-time feedback (cab_comm.cu) -- identical on every rank by construction
@@ -193,7 +195,7 @@ struct cab_ctx {
   // device arena (grow-only)
   cab::DevBuf b_xyz, b_domoff, b_domid, b_bounds, b_domains, b_keys[3], b_vals[3], b_cubtmp, b_pos,
       b_perm, b_cellcnt, b_cellstart, b_rowpk, b_packets, b_nrm, b_nrm_in, b_rsd, b_rdif, b_kcount, b_stats,
-      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost, b_slab, b_sel, b_stats2, b_sorttmp, b_occ, b_thr_flag, b_knn_avg, b_knn_done, b_pfh[3], b_cluster;
+      b_out4, b_out1a, b_out1b, b_thr_d2, b_thr_idx, b_misc, b_pcost, b_slab, b_sel, b_stats2, b_sorttmp, b_occ, b_in_nrm, b_in_rsd, b_thr_flag, b_knn_avg, b_knn_done, b_pfh[3], b_cluster;
   std::vector<cab::DevBuf> graveyard;  // outgrown arena buffers (see reserve())
   size_t graveyard_bytes = 0;
   // pinned staging

@@ -734,6 +734,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
   }
 }
 
+// CAB_STEP_INPUT_ORDER: the points that are nobody's query (non-finite, sorted behind the finite ones) in input order
+__global__ void fill_invalid_input_order(const int* __restrict__ perm, int begin, int end, float v, float4* __restrict__ nrm,
+                                         float2* __restrict__ rsd) {
+  const int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= end) return;
+  const int j = perm[i];
+  const float nan = __int_as_float(0x7fc00000);
+  nrm[j] = make_float4(nan, nan, nan, nan);
+  rsd[j] = make_float2(v, v);
+}
+
 __global__ void fill_invalid_rsd(float2* out, float* rdif, int begin, int end, float v) {
   int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i < end) {
@@ -828,6 +839,18 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
     a.range_b = a.slab->r_bhi;
   }
   comm_push_targets(ctx, &a.push);
+  const bool scatter = ctx->step_input_order && a.push.world == 0 && !ctx->slab;
+  if (scatter) {  // a group of one: every result goes to its input index in this context's own arrays
+    if (int rc = reserve(ctx, ctx->b_in_nrm, (size_t)std::max(n, 1) * sizeof(float4))) return rc;
+    if (int rc = reserve(ctx, ctx->b_in_rsd, (size_t)std::max(n, 1) * sizeof(float2))) return rc;
+    a.push.world = 1;
+    a.push.layout = CAB_COMM_LAYOUT_INPUT_RANGES;
+    a.push.n = std::max(n, 1);
+    a.push.lo[0] = 0;
+    a.push.lo[1] = n;
+    a.push.nrm[0] = (float4*)ctx->b_in_nrm.p;
+    a.push.rsd[0] = (float2*)ctx->b_in_rsd.p;
+  }
   a.r = rf;
   a.r2 = r2;
   a.nrm = (const float4*)ctx->b_nrm.p;
@@ -889,7 +912,13 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
     fill_invalid_rsd<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((float2*)ctx->b_rsd.p, (float*)ctx->b_rdif.p, ctx->n_valid, n,
                                                                     (float)plane_radius);
     CAB_LAUNCH_CHECK(ctx);
+    if (scatter) {
+      fill_invalid_input_order<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, ctx->n_valid, n, (float)plane_radius,
+                                                                              (float4*)ctx->b_in_nrm.p, (float2*)ctx->b_in_rsd.p);
+      CAB_LAUNCH_CHECK(ctx);
+    }
   }
+  if (scatter) ctx->have_input_order = true;
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
   CAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_step + kStepStats1, ctx->b_stats.p, kStatBytes, cudaMemcpyDeviceToHost, st));
   ctx->have_rsd = true;

@@ -54,6 +54,36 @@ def test_step_equals_the_three_stages():
     c.close()
 
 
+class _DevArray:
+    """A device pointer as a __cuda_array_interface__ object (torch.as_tensor reads it without a copy)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+@pytest.mark.parametrize("max_nn", [0, 60])
+def test_step_input_order_arrays(max_nn):
+    """CAB_STEP_INPUT_ORDER: the RSD kernel of a single context's step also scatters normals and radii to their input
+    index (what a group's step leaves rank by rank); same bits as cab_download, non-finite points included."""
+    import torch
+
+    pts = synth.tabletop(40_000, noise_sigma=0.0003)
+    pts[[7, 11, 39_999]] = np.nan
+    n = pts.shape[0]
+    c = cab.Context(0)
+    c.upload(pts)
+    assert c.device_ptr(cab.BUF_NRM_INPUT_RANGE) == 0  # nothing yet
+    for _ in range(2):
+        c.step_normals_rsd(R, R, max_nn_rsd=max_nn, flags=cab.STEP_INPUT_ORDER)
+        f4, fmin, fmax = c.download()
+        in4 = torch.as_tensor(_DevArray(c.device_ptr(cab.BUF_NRM_INPUT_RANGE), (n, 4), "<f4"), device="cuda:0").cpu().numpy()
+        in2 = torch.as_tensor(_DevArray(c.device_ptr(cab.BUF_RSD_INPUT_RANGE), (n, 2), "<f4"), device="cuda:0").cpu().numpy()
+        assert _same(in4, f4) and _same(in2[:, 0], fmin) and _same(in2[:, 1], fmax)
+    c.step_normals_rsd(R, R)  # without the flag the arrays are not offered
+    assert c.device_ptr(cab.BUF_NRM_INPUT_RANGE) == 0
+    c.close()
+
+
 @pytest.mark.parametrize("max_nn", [60, 150])
 def test_step_with_truncated_rsd(max_nn):
     """Normals unlimited, RSD truncated at max_nn (the plugin defaults, radius_estimation.h:82): in one call the normals
