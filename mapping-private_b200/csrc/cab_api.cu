@@ -480,20 +480,36 @@ int cab_normals_rsd(cab_ctx* ctx, double r, int32_t max_nn_normals, const float 
   if (layout == CAB_OUT_INPUT_ORDER && (out_a == nullptr) != (out_b == nullptr))
     return fail(ctx, CAB_ERR_ARG, "cab_normals_rsd: r_min and r_max must be given together");
   const int n = (int)ctx->n;
-  const int ns = (int)ctx->n_sorted;
   cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
   if (layout == CAB_OUT_INPUT_ORDER && ctx->slab)
     return fail(ctx, CAB_ERR_STATE, "cab_normals_rsd: a shard returns its own slice (CAB_OUT_SHARD_SORTED); the concatenated "
                                      "results of a group come from cab_step_normals_rsd + cab_comm_download_range");
+  // Input-order layout: both pass kernels store every query's result at its input index as well (one scattered store
+  // per query next to the sorted-order one), so the device-to-host copies leave straight behind the kernels -- no
+  // permutation pass in between.
+  struct Fused {
+    cab_ctx* c;
+    explicit Fused(cab_ctx* x) : c(x) {}
+    ~Fused() { c->fuse_nrm_in = nullptr, c->fuse_rmin_in = c->fuse_rmax_in = nullptr; }
+  } fused(ctx);
+  if (layout == CAB_OUT_INPUT_ORDER && n > 0) {
+    if (nxyz_curv) {
+      if (int rc = reserve(ctx, ctx->b_out4, (size_t)n * sizeof(float4))) return rc;
+      ctx->fuse_nrm_in = (float4*)ctx->b_out4.p;
+    }
+    if (out_a) {
+      if (int rc = reserve(ctx, ctx->b_out1a, (size_t)n * sizeof(float))) return rc;
+      if (int rc = reserve(ctx, ctx->b_out1b, (size_t)n * sizeof(float))) return rc;
+    }
+  }
   // pass 1 on the compute stream
   // (an RSD pass truncated at max_nn_rsd follows at the same radius: the normals traversal takes its d2 histogram along)
   if (int rc = run_normals(ctx, (float)r, max_nn_normals, vp, nullptr, max_nn_normals == 0 ? max_nn_rsd : 0)) return rc;
+  ctx->fuse_nrm_in = nullptr;
   int64_t b = 0, e = 0;
   if (layout == CAB_OUT_SHARD_SORTED)
     if (int rc = cab_shard_range(ctx, &b, &e)) return rc;
   const size_t m = (size_t)(e - b);
-  if (nxyz_curv && n > 0 && layout == CAB_OUT_INPUT_ORDER)
-    if (int rc = reserve(ctx, ctx->b_out4, (size_t)n * sizeof(float4))) return rc;
   // From here on the copy stream may be writing into the caller's buffers: every exit goes through the epilogue below,
   // which drains both streams; the first error (a failing call, or a CUDA error of any enqueue) is the result.
   int rc = CAB_OK;
@@ -505,13 +521,7 @@ int cab_normals_rsd(cab_ctx* ctx, double r, int32_t max_nn_normals, const float 
   // the normals leave on the copy stream while pass 2 runs
   cuda(cudaEventRecord(ctx->ev[6], st));
   if (nxyz_curv && n > 0) {
-    if (layout == CAB_OUT_INPUT_ORDER) {
-      if (ns > 0) {
-        unpermute_kernel<<<(ns + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, 0, ns, (const float4*)ctx->b_nrm.p, nullptr,
-                                                           (float4*)ctx->b_out4.p, nullptr, nullptr);
-        ctx->tm.kernel_launches++;
-        cuda(cudaGetLastError());
-      }
+    if (layout == CAB_OUT_INPUT_ORDER) {  // b_out4 was filled by the normals kernel itself
       if (cuda(cudaEventRecord(ctx->ev_ready, st)) && cuda(cudaStreamWaitEvent(cs, ctx->ev_ready, 0)))
         cuda(cudaMemcpyAsync(nxyz_curv, ctx->b_out4.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, cs));
     } else if (m) {
@@ -522,21 +532,15 @@ int cab_normals_rsd(cab_ctx* ctx, double r, int32_t max_nn_normals, const float 
   if (ce == cudaSuccess && layout == CAB_OUT_SHARD_SORTED && input_index && m)
     cuda(cudaMemcpyAsync(input_index, (const int*)ctx->b_perm.p + b, m * sizeof(int), cudaMemcpyDeviceToHost, cs));
   // pass 2 (run_rsd synchronises the compute stream only)
+  if (layout == CAB_OUT_INPUT_ORDER && out_a && n > 0) {
+    ctx->fuse_rmin_in = (float*)ctx->b_out1a.p;
+    ctx->fuse_rmax_in = (float*)ctx->b_out1b.p;
+  }
   if (ce == cudaSuccess) rc = run_rsd(ctx, r, max_nn_rsd, ndiv, plane_radius, flags);
   if (rc == CAB_OK && ce == cudaSuccess && out_a && n > 0) {
-    if (layout == CAB_OUT_INPUT_ORDER) {
-      rc = reserve(ctx, ctx->b_out1a, (size_t)n * sizeof(float));
-      if (rc == CAB_OK) rc = reserve(ctx, ctx->b_out1b, (size_t)n * sizeof(float));
-      if (rc == CAB_OK) {
-        if (ns > 0) {
-          unpermute_kernel<<<(ns + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, 0, ns, nullptr, (const float2*)ctx->b_rsd.p,
-                                                             nullptr, (float*)ctx->b_out1a.p, (float*)ctx->b_out1b.p);
-          ctx->tm.kernel_launches++;
-          cuda(cudaGetLastError());
-        }
-        cuda(cudaMemcpyAsync(out_a, ctx->b_out1a.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
-        cuda(cudaMemcpyAsync(out_b, ctx->b_out1b.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
-      }
+    if (layout == CAB_OUT_INPUT_ORDER) {  // b_out1a / b_out1b were filled by the RSD kernel itself
+      cuda(cudaMemcpyAsync(out_a, ctx->b_out1a.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+      cuda(cudaMemcpyAsync(out_b, ctx->b_out1b.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
     } else if (m) {
       cuda(cudaMemcpyAsync(out_a, (const float2*)ctx->b_rsd.p + b, m * sizeof(float2), cudaMemcpyDeviceToHost, st));
     }

@@ -187,6 +187,11 @@ struct cab_ctx {
   bool want_halo_exchange = false; // set by cab_step_normals_rsd of a group: build_slab may choose the exchange mode
   bool step_input_order = false;   // CAB_STEP_INPUT_ORDER: the RSD kernel of this step also scatters the results into b_in_nrm / b_in_rsd
   bool have_input_order = false;   // ... and they are there
+  // cab_normals_rsd, input-order layout: the two pass kernels also store every query's result at its input index (the
+  // arrays the host copies leave from), so no permutation pass stands between a kernel and its device-to-host copy
+  float4* fuse_nrm_in = nullptr;
+  float* fuse_rmin_in = nullptr;
+  float* fuse_rmax_in = nullptr;
   bool defer_sync = false;         // run_normals / run_rsd leave the stream running (cab_step_*: one sync per step)
   std::vector<double> shard_cum;   // empty: equal shares; else world + 1 cumulative shares of the modelled cost (0 ... 1), the
                                    // group's measured-time feedback (cab_comm.cu) -- identical on every rank by construction

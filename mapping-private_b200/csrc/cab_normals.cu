@@ -57,6 +57,7 @@ struct NormalsArgs {
   float r, r2;
   float vpx, vpy, vpz;
   float4* nrm;              // sorted order
+  float4* nrm_in;           // optional: the same normals at their input indices (cab_normals_rsd, input-order layout)
   int* kcount;              // sorted order
   const float* thr_d2;      // optional max_nn thresholds (sorted order), may be null
   const int* thr_idx;
@@ -258,6 +259,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
   if (pc.active) {
     a.nrm[pc.qi] = out;
     a.kcount[pc.qi] = k;
+    if (a.nrm_in) {
+      const int ii = g.perm[pc.qi];
+      if (ii >= 0) a.nrm_in[ii] = out;
+    }
   }
   unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
 #pragma unroll
@@ -270,12 +275,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
   }  // persistent packet loop
 }
 
-__global__ void fill_invalid_normals(float4* nrm, int* kcount, int begin, int end) {
+__global__ void fill_invalid_normals(float4* nrm, int* kcount, int begin, int end, const int* __restrict__ perm, float4* nrm_in) {
   int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= end) return;
   const float nan = __int_as_float(0x7fc00000);
   nrm[i] = make_float4(nan, nan, nan, nan);
   kcount[i] = 0;
+  if (nrm_in && perm[i] >= 0) nrm_in[perm[i]] = make_float4(nan, nan, nan, nan);
 }
 
 }  // namespace
@@ -305,6 +311,7 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsi
   a.vpy = vp ? vp[1] : 0.f;
   a.vpz = vp ? vp[2] : 0.f;
   a.nrm = (float4*)ctx->b_nrm.p;
+  a.nrm_in = ctx->slab ? nullptr : ctx->fuse_nrm_in;
   a.kcount = (int*)ctx->b_kcount.p;
   a.thr_d2 = use_thr ? (const float*)ctx->b_thr_d2.p : nullptr;
   a.thr_idx = use_thr ? (const int*)ctx->b_thr_idx.p : nullptr;
@@ -348,7 +355,7 @@ int run_normals(cab_ctx* ctx, float r, int max_nn, const float vp[3], const unsi
   }
   if (!ctx->slab && n > ctx->n_valid) {  // non-finite points sit behind the sorted finite ones (a slab holds none)
     fill_invalid_normals<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((float4*)ctx->b_nrm.p, (int*)ctx->b_kcount.p,
-                                                                        ctx->n_valid, n);
+                                                                        ctx->n_valid, n, (const int*)ctx->b_perm.p, a.nrm_in);
     CAB_LAUNCH_CHECK(ctx);
   }
   CAB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));

@@ -47,6 +47,8 @@ struct RsdArgs {
   const float4* nrm;       // sorted order
   float2* out;             // sorted order (r_min, r_max)
   float* rdif;             // sorted order: (float)(max_radius - min_radius), the subtraction in double (:206)
+  float* rmin_in;          // optional: r_min / r_max at the queries' input indices (cab_normals_rsd, input-order layout)
+  float* rmax_in;
   const float* thr_d2;     // optional max_nn thresholds
   const int* thr_idx;
   const unsigned char* only;   // legacy kernel: optional per-packet flags (relative to p0), unflagged packets are skipped
@@ -58,6 +60,7 @@ struct RsdArgs {
   int ndiv;
   int flags;
   float bin_scale;         // ndiv / radius
+  float bin_scale_low;     // the same biased low by 2^-10 relative (fast kernel: the row estimate never exceeds the bin)
   double radius, plane_radius;
   unsigned long long* stats;
   int work_slot;           // which packet work counter this launch pulls from (next_packet)
@@ -130,6 +133,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ndiv = a.ndiv;
   for (int i = threadIdx.x; i <= ndiv; i += blockDim.x) thr[i] = a.bin_thr[i];
+  __shared__ double fbin[kMaxDiv];  // (di + 0.5) * radius / ndiv (:185), the same double expression, once per block
+  if (threadIdx.x < ndiv) fbin[threadIdx.x] = (threadIdx.x + 0.5) * a.radius / ndiv;
   __syncthreads();
   const GridView& g = a.g;
   ChunkTile* tile = &tiles[warp];
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
       if (fabsf(v.x) != INFINITY) {  // bin not empty (:181)
         const double p_min = fold_angle<kExact>(fminf(fmaxf(v.y, -1.f), 1.f));
         const double p_max = fold_angle<kExact>(fminf(fmaxf(v.x, -1.f), 1.f));
-        const double f = (di + 0.5) * a.radius / ndiv;
+        const double f = fbin[di];
         Amint_Amin = __dadd_rn(Amint_Amin, __dmul_rn(p_min, p_min));
         Amint_d = __dadd_rn(Amint_d, __dmul_rn(p_min, f));
         Amaxt_Amax = __dadd_rn(Amaxt_Amax, __dmul_rn(p_max, p_max));
@@ -245,6 +250,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
       rmax = fmaxf(x, y);
     }
     if (pc.active) a.out[pc.qi] = make_float2(rmin, rmax);
+    if (a.rmin_in && pc.active) {
+      const int ii = g.perm[pc.qi];
+      if (ii >= 0) {
+        a.rmin_in[ii] = rmin;
+        a.rmax_in[ii] = rmax;
+      }
+    }
     push_results(a.push, a.slab, g, pc, nq, make_float2(rmin, rmax));
     unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
 #pragma unroll
@@ -268,7 +280,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
 // chunks, and only those run the variant of the loop that knows the self bit); candidates whose normal is not finite
 // are staged far away (they never contribute, :158-172) and counted in a rare side path; the bins are two arrays
 // [bin][lane] (min |cos|, max |cos|), so that a warp's reductions never meet in a bank whatever bins its lanes hit.
-constexpr int kFastThr = 260;  // entries of the fast kernel's threshold table (257 used)
+constexpr int kFastThr = 260;  // entries of the fast kernel's threshold table (257 used; the truncated variant reads it)
+// One bin row of a warp in the fast kernel: min |cos| [32], max |cos| [32] and -- replicated per lane, so that the load
+// is a conflict-free access at a fixed offset from the reduction's own address -- the d2 threshold at which a candidate
+// belongs to the NEXT row [32].
+constexpr int kRowWords = 3 * kWarp;
+constexpr unsigned kRowBytes = kRowWords * sizeof(unsigned);  // 384 (spelled out in the inline PTX below)
+static_assert(kRowBytes == 384, "the inline PTX of fast_chunk hard-codes the row stride");
 struct alignas(16) FastTile {
   float x[kWarp], y[kWarp], z[kWarp];
   float nx[kWarp], ny[kWarp], nz[kWarp];
@@ -288,7 +306,8 @@ struct alignas(16) FastTile {
 template <bool kSelf, bool kCount, bool kTrunc>
 __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float qy, float qz, float nqx, float nqy, float nqz,
                                           float r2, float bscale, unsigned thr_addr, unsigned spare_off, unsigned bins_addr,
-                                          int sb, float hi, unsigned& tmask) {
+                                          int sb, float hi, unsigned& tmask, float bscale_low = 0.f, float vmax = 0.f,
+                                          unsigned row_k = 0u) {
   const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
   const f32x2 nqx2 = pack2(nqx, nqx), nqy2 = pack2(nqy, nqy), nqz2 = pack2(nqz, nqz);
   const float4* tx = reinterpret_cast<const float4*>(tile->x);
@@ -358,9 +377,9 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
               "setp.ne.s32 s, %8, %9;\n\t"
               "setp.lt.and.f32 p, %3, %4, s;\n\t"
               "setp.ge.and.f32 g, %3, t, p;\n\t"
-              "shl.b32 rb, be, 8;\n\t"
+              "mul.lo.u32 rb, be, 384;\n\t"
               "selp.u32 rb, rb, %6, p;\n\t"
-              "selp.u32 go, 256, 0, g;\n\t"
+              "selp.u32 go, 384, 0, g;\n\t"
               "add.u32 rb, rb, go;\n\t"
               "add.u32 %0, rb, %7;\n\t"
               "@p add.s32 %1, %1, 1;\n\t}"
@@ -373,60 +392,66 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
               "ld.shared.f32 t, [ta+4];\n\t"
               "setp.lt.f32 p, %3, %4;\n\t"
               "setp.ge.and.f32 g, %3, t, p;\n\t"
-              "shl.b32 rb, be, 8;\n\t"
+              "mul.lo.u32 rb, be, 384;\n\t"
               "selp.u32 rb, rb, %6, p;\n\t"
-              "selp.u32 go, 256, 0, g;\n\t"
+              "selp.u32 go, 384, 0, g;\n\t"
               "add.u32 rb, rb, go;\n\t"
               "add.u32 %0, rb, %7;\n\t"
               "@p add.s32 %1, %1, 1;\n\t}"
               : "=r"(addr[i]), "+r"(k)
               : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr));
         }
-      } else if (kSelf) {
-        asm("{\n\t.reg .pred p, g, s;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
-            "cvt.rzi.u8.f32 be, %2;\n\t"
-            "mad.lo.u32 ta, be, 4, %5;\n\t"
-            "ld.shared.f32 t, [ta+4];\n\t"
-            "setp.ne.s32 s, %8, %9;\n\t"
-            "setp.le.and.f32 p, %3, %4, s;\n\t"
-            "setp.ge.and.f32 g, %3, t, p;\n\t"
-            "shl.b32 rb, be, 8;\n\t"
-            "selp.u32 rb, rb, %6, p;\n\t"
-            "selp.u32 go, 256, 0, g;\n\t"
-            "add.u32 rb, rb, go;\n\t"
-            "add.u32 %0, rb, %7;\n\t"
-            "@p add.s32 %1, %1, 1;\n\t}"
-            : "=r"(addr[i]), "+r"(k)
-            : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr), "r"(4 * g4 + i), "r"(sb));
-      } else if (kCount) {
-        asm("{\n\t.reg .pred p, g;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
-            "cvt.rzi.u8.f32 be, %2;\n\t"
-            "mad.lo.u32 ta, be, 4, %5;\n\t"
-            "ld.shared.f32 t, [ta+4];\n\t"
-            "setp.le.f32 p, %3, %4;\n\t"
-            "setp.ge.and.f32 g, %3, t, p;\n\t"
-            "shl.b32 rb, be, 8;\n\t"
-            "selp.u32 rb, rb, %6, p;\n\t"
-            "selp.u32 go, 256, 0, g;\n\t"
-            "add.u32 rb, rb, go;\n\t"
-            "add.u32 %0, rb, %7;\n\t"
-            "@p add.s32 %1, %1, 1;\n\t}"
-            : "=r"(addr[i]), "+r"(k)
-            : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr));
-      } else {  // the neighbour counts of this radius are known from the normals pass
-        asm("{\n\t.reg .pred p, g;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
-            "cvt.rzi.u8.f32 be, %2;\n\t"
-            "mad.lo.u32 ta, be, 4, %5;\n\t"
-            "ld.shared.f32 t, [ta+4];\n\t"
-            "setp.le.f32 p, %3, %4;\n\t"
-            "setp.ge.and.f32 g, %3, t, p;\n\t"
-            "shl.b32 rb, be, 8;\n\t"
-            "selp.u32 rb, rb, %6, p;\n\t"
-            "selp.u32 go, 256, 0, g;\n\t"
-            "add.u32 rb, rb, go;\n\t"
-            "add.u32 %0, rb, %7;\n\t}"
-            : "=r"(addr[i]), "+r"(k)
-            : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr));
+      } else {
+        // Untruncated pass.  The row comes straight out of the floating-point pipe: v = 2^23 + floor(root * bscale_low)
+        // (fma.rz on the magic constant: the integer sits in the low mantissa bits; bscale_low carries the low bias, so
+        // the product is never negative), clamped to the spare row (misses, staged-away candidates: d2 = inf), and ONE
+        // integer multiply-add turns the float's bits into the lane's address of that row (row_k holds the lane's
+        // column minus 2^23's bits times the stride, modulo 2^32).  The row's own third column holds the d2 at which a
+        // candidate belongs to the next row: the last real row's is nextafter(r2) (a miss moves on to the spare row),
+        // the spare row's is NaN (never true).  7 issue slots against 11 for the table form above.
+        if (kSelf) {
+          asm("{\n\t.reg .pred p, g, s;\n\t.reg .f32 v, t;\n\t.reg .u32 vi;\n\t"
+              "sqrt.approx.ftz.f32 v, %2;\n\t"
+              "fma.rz.ftz.f32 v, v, %3, 0f4B000000;\n\t"
+              "min.f32 v, v, %4;\n\t"
+              "setp.eq.s32 s, %7, %8;\n\t"
+              "@s mov.f32 v, %4;\n\t"
+              "mov.b32 vi, v;\n\t"
+              "mad.lo.u32 %0, vi, 384, %5;\n\t"
+              "ld.shared.f32 t, [%0+256];\n\t"
+              "setp.ge.f32 g, %2, t;\n\t"
+              "@g add.u32 %0, %0, 384;\n\t"
+              "setp.le.and.f32 p, %2, %6, !s;\n\t"
+              "@p add.s32 %1, %1, 1;\n\t}"
+              : "=&r"(addr[i]), "+r"(k)
+              : "f"(d2[i]), "f"(bscale_low), "f"(vmax), "r"(row_k), "f"(r2), "r"(4 * g4 + i), "r"(sb));
+        } else if (kCount) {
+          asm("{\n\t.reg .pred p, g;\n\t.reg .f32 v, t;\n\t.reg .u32 vi;\n\t"
+              "sqrt.approx.ftz.f32 v, %2;\n\t"
+              "fma.rz.ftz.f32 v, v, %3, 0f4B000000;\n\t"
+              "min.f32 v, v, %4;\n\t"
+              "mov.b32 vi, v;\n\t"
+              "mad.lo.u32 %0, vi, 384, %5;\n\t"
+              "ld.shared.f32 t, [%0+256];\n\t"
+              "setp.ge.f32 g, %2, t;\n\t"
+              "@g add.u32 %0, %0, 384;\n\t"
+              "setp.le.f32 p, %2, %6;\n\t"
+              "@p add.s32 %1, %1, 1;\n\t}"
+              : "=&r"(addr[i]), "+r"(k)
+              : "f"(d2[i]), "f"(bscale_low), "f"(vmax), "r"(row_k), "f"(r2));
+        } else {  // the neighbour counts of this radius are known from the normals pass
+          asm("{\n\t.reg .pred g;\n\t.reg .f32 v, t;\n\t.reg .u32 vi;\n\t"
+              "sqrt.approx.ftz.f32 v, %1;\n\t"
+              "fma.rz.ftz.f32 v, v, %2, 0f4B000000;\n\t"
+              "min.f32 v, v, %3;\n\t"
+              "mov.b32 vi, v;\n\t"
+              "mad.lo.u32 %0, vi, 384, %4;\n\t"
+              "ld.shared.f32 t, [%0+256];\n\t"
+              "setp.ge.f32 g, %1, t;\n\t"
+              "@g add.u32 %0, %0, 384;\n\t}"
+              : "=&r"(addr[i])
+              : "f"(d2[i]), "f"(bscale_low), "f"(vmax), "r"(row_k));
+        }
       }
     }
 #pragma unroll
@@ -462,8 +487,8 @@ __device__ __forceinline__ int trunc_slow_chunk(const FastTile* tile, float qx, 
     const unsigned ua = __float_as_uint(fabsf(cs));
     int b = 0;
     while (b < ndiv - 1 && d2 >= thr[b + 1]) ++b;
-    my_min[b * 2 * kWarp] = min(my_min[b * 2 * kWarp], ua);
-    my_max[b * 2 * kWarp] = max(my_max[b * 2 * kWarp], ua);
+    my_min[b * kRowWords] = min(my_min[b * kRowWords], ua);
+    my_max[b * kRowWords] = max(my_max[b * kRowWords], ua);
   }
   tmask = tm;
   return k;
@@ -482,20 +507,31 @@ template <bool kCount, bool kTrunc>
 __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const RsdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastTile* tiles = reinterpret_cast<FastTile*>(smem_raw);                          // [W]
-  unsigned* bins = reinterpret_cast<unsigned*>(tiles + kWarpsPerBlock);                    // [W][ndiv + 1][2][32], row ndiv: the misses
-  float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * 2 * (a.ndiv + 1) * kWarp);  // [257], +inf from ndiv on
+  unsigned* bins = reinterpret_cast<unsigned*>(tiles + kWarpsPerBlock);                    // [W][ndiv + 1][3][32], row ndiv: the misses
+  float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * kRowWords * (a.ndiv + 1));  // [257], +inf from ndiv on
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ndiv = a.ndiv;
   int* lists = reinterpret_cast<int*>(thr + kFastThr);  // kTrunc: [W][kTruncCap][32], a lane's list of its target bin's candidates (sorted indices)
   for (int i = threadIdx.x; i < kFastThr; i += blockDim.x) thr[i] = i <= ndiv ? a.bin_thr[i] : INFINITY;
+  // the bins' distances (di + 0.5) * radius / ndiv (:185): the same double expression, evaluated once per block instead of
+  // once per bin and query
+  __shared__ double fbin[kMaxDiv];
+  if (threadIdx.x < ndiv) fbin[threadIdx.x] = (threadIdx.x + 0.5) * a.radius / ndiv;
   __syncthreads();
   const GridView& g = a.g;
   FastTile* tile = &tiles[warp];
   int* lst = lists + (size_t)warp * kTruncCap * kWarp + lane;
-  unsigned* my_min = bins + (size_t)warp * 2 * (ndiv + 1) * kWarp + lane;  // bin b: min |cos| at my_min[b * 64], max at my_max[b * 64]
+  unsigned* my_min = bins + (size_t)warp * kRowWords * (ndiv + 1) + lane;  // bin b: min |cos| at my_min[b * 96], max at my_max[b * 96]
   unsigned* my_max = my_min + kWarp;
   const unsigned bins_addr = smem_u32(my_min), thr_addr = smem_u32(thr);
   const float r2 = a.r2, bscale = a.bin_scale;
+  // the rows' threshold columns (see fast_chunk): written once, the packets only reset the two extremes
+  for (int b = 0; b <= ndiv; ++b)
+    my_min[b * kRowWords + 2 * kWarp] = b < ndiv - 1 ? __float_as_uint(a.bin_thr[b + 1])
+                                        : b == ndiv - 1 ? __float_as_uint(a.r2) + 1u  // nextafter(r2): d2 > r2 leaves the last bin
+                                                        : 0x7fc00000u;               // the spare row: NaN, nothing moves on
+  const float bscale_low = a.bin_scale_low, vmax = 8388608.f + (float)ndiv;
+  const unsigned row_k = bins_addr - 0x4B000000u * kRowBytes;  // modulo 2^32: the multiply-add of fast_chunk wraps the same way
   const int p0 = a.range ? a.range[0] : a.p0, n1 = (a.range ? a.range[1] : a.p1) - p0;
   const int pb = a.range_b ? a.range_b[0] : 0, n2 = a.range_b ? a.range_b[1] - pb : 0;
   for (;;) {
@@ -576,8 +612,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
     const float4 nq = a.nrm[pc.qi];
     const bool q_ok = isfinite(nq.x) && isfinite(nq.y) && isfinite(nq.z);
     for (int b = 0; b < ndiv; ++b) {
-      my_min[b * 2 * kWarp] = 0x7f800000u;  // +inf: empty
-      my_max[b * 2 * kWarp] = 0u;
+      my_min[b * kRowWords] = 0x7f800000u;  // +inf: empty
+      my_max[b * kRowWords] = 0u;
     }
     if (a.flags & CAB_RSD_SEED_BIN0) {
       my_min[0] = 0x3f800000u;
@@ -627,7 +663,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
         if (odd_mask)
           k += trunc_slow_chunk(tile, qx, qy, qz, nq.x, nq.y, nq.z, cut, hi, thr, ndiv, my_min, my_max, sb, tmask);
         else  // one body for chunks with and without queries of the packet (sb = -1 matches no slot): half the code
-          k += fast_chunk<true, true, true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, cut, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, sb, hi, tmask);
+          k += fast_chunk<true, true, true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, cut, bscale, thr_addr, kRowBytes * (unsigned)ndiv, bins_addr, sb, hi, tmask);
         k += (sb >= 0 && cut > 0.f) ? 1 : 0;  // the query itself, unless it sits in the target bin (then the list has it)
         while (tmask) {  // the chunk's candidates of the target bin (a handful per query and traversal): listed for the settlement
           const int m = __ffs(tmask) - 1;
@@ -637,11 +673,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
         }
       } else if (own_mask) {
         unsigned dummy_mask;
-        k += fast_chunk<true, true, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, tile->self_slot[lane], 0.f, dummy_mask);
+        k += fast_chunk<true, true, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, kRowBytes * (unsigned)ndiv, bins_addr, tile->self_slot[lane], 0.f, dummy_mask, bscale_low, vmax, row_k);
         k += tile->self_slot[lane] >= 0 ? 1 : 0;  // the query itself is a neighbour of the radius search (:120), just not a pair (:150)
       } else {
         unsigned dummy_mask;
-        k += fast_chunk<false, kCount, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, 256u * (unsigned)ndiv, bins_addr, -1, 0.f, dummy_mask);
+        k += fast_chunk<false, kCount, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, kRowBytes * (unsigned)ndiv, bins_addr, -1, 0.f, dummy_mask, bscale_low, vmax, row_k);
       }
       if (!kTrunc && odd_mask) {  // rare: neighbours without a normal still count as neighbours
         unsigned mm = odd_mask;
@@ -690,19 +726,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
         const unsigned ua = __float_as_uint(fabsf(cs));
         int b = 0;
         while (b < ndiv - 1 && de >= thr[b + 1]) ++b;
-        my_min[b * 2 * kWarp] = min(my_min[b * 2 * kWarp], ua);
-        my_max[b * 2 * kWarp] = max(my_max[b * 2 * kWarp], ua);
+        my_min[b * kRowWords] = min(my_min[b * kRowWords], ua);
+        my_max[b * kRowWords] = max(my_max[b * kRowWords], ua);
       }
     }
     // ---- least-squares fit of the min / max angle lines, radius_estimation.cpp:175-202 ----
     double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;
     if (q_ok) {
       for (int di = 0; di < ndiv; ++di) {
-        const float lo = __uint_as_float(my_min[di * 2 * kWarp]), hi = __uint_as_float(my_max[di * 2 * kWarp]);
+        const float lo = __uint_as_float(my_min[di * kRowWords]), hi = __uint_as_float(my_max[di * kRowWords]);
         if (lo != INFINITY) {  // bin not empty (:181)
           const double p_min = fold_angle<false>(fminf(hi, 1.f));
           const double p_max = fold_angle<false>(fminf(lo, 1.f));
-          const double f = (di + 0.5) * a.radius / ndiv;
+          const double f = fbin[di];
           Amint_Amin = __dadd_rn(Amint_Amin, __dmul_rn(p_min, p_min));
           Amint_d = __dadd_rn(Amint_d, __dmul_rn(p_min, f));
           Amaxt_Amax = __dadd_rn(Amaxt_Amax, __dmul_rn(p_max, p_max));
@@ -720,6 +756,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       rmax = fmaxf(x, y);
     }
     if (pc.active) a.out[pc.qi] = make_float2(rmin, rmax);
+    if (a.rmin_in && pc.active) {
+      const int ii = g.perm[pc.qi];
+      if (ii >= 0) {
+        a.rmin_in[ii] = rmin;
+        a.rmax_in[ii] = rmax;
+      }
+    }
     push_results(a.push, a.slab, g, pc, nq, make_float2(rmin, rmax));
     if (!kCount) k = a.kcount[pc.qi];  // same radius, same rule, no truncation: the normals pass counted these neighbours
     unsigned long long ks = pc.active ? (unsigned long long)k : 0ull;
@@ -745,11 +788,19 @@ __global__ void fill_invalid_input_order(const int* __restrict__ perm, int begin
   rsd[j] = make_float2(v, v);
 }
 
-__global__ void fill_invalid_rsd(float2* out, float* rdif, int begin, int end, float v) {
+__global__ void fill_invalid_rsd(float2* out, float* rdif, int begin, int end, float v, const int* __restrict__ perm, float* rmin_in,
+                                 float* rmax_in) {
   int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i < end) {
     out[i] = make_float2(v, v);
     rdif[i] = 0.f;
+    if (rmin_in) {
+      const int j = perm[i];
+      if (j >= 0) {
+        rmin_in[j] = v;
+        rmax_in[j] = v;
+      }
+    }
   }
 }
 
@@ -856,14 +907,18 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   a.nrm = (const float4*)ctx->b_nrm.p;
   a.out = (float2*)ctx->b_rsd.p;
   a.rdif = (float*)ctx->b_rdif.p;
+  a.rmin_in = ctx->slab ? nullptr : ctx->fuse_rmin_in;
+  a.rmax_in = ctx->slab ? nullptr : ctx->fuse_rmax_in;
   a.thr_d2 = use_thr ? (const float*)ctx->b_thr_d2.p : nullptr;
   a.thr_idx = use_thr ? (const int*)ctx->b_thr_idx.p : nullptr;
   a.bin_thr = (const float*)ctx->b_stats2.p;
   a.ndiv = ndiv;
   a.flags = flags;
   a.bin_scale = (float)(ndiv / r);
+  a.bin_scale_low = (float)(ndiv / r * (1.0 - 1.0 / 1024.0));
   a.radius = r;
   a.plane_radius = plane_radius;
+
   a.stats = (unsigned long long*)ctx->b_stats.p;
   a.work_slot = slot;
   const size_t smem = (size_t)kWarpsPerBlock * sizeof(ChunkTile) + (size_t)kWarpsPerBlock * ndiv * kWarp * sizeof(float2) +
@@ -873,7 +928,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
     const unsigned blocks = (np + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int rc;
     if (!ctx->cfg.exact && (!use_thr || trunc_fast) && !legacy) {
-      const size_t fsmem = (size_t)kWarpsPerBlock * sizeof(FastTile) + (size_t)kWarpsPerBlock * 2 * (ndiv + 1) * kWarp * sizeof(unsigned) +
+      const size_t fsmem = (size_t)kWarpsPerBlock * sizeof(FastTile) + (size_t)kWarpsPerBlock * (ndiv + 1) * kRowBytes +
                            (size_t)kFastThr * sizeof(float) + 256 +
                            (trunc_fast ? (size_t)kWarpsPerBlock * kTruncCap * kWarp * sizeof(int) : 0);
       // neighbour counts kept by the last normals pass are this pass's counts if radius and rule were the same
@@ -910,7 +965,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   }
   if (!ctx->slab && n > ctx->n_valid) {
     fill_invalid_rsd<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((float2*)ctx->b_rsd.p, (float*)ctx->b_rdif.p, ctx->n_valid, n,
-                                                                    (float)plane_radius);
+                                                                    (float)plane_radius, (const int*)ctx->b_perm.p, a.rmin_in, a.rmax_in);
     CAB_LAUNCH_CHECK(ctx);
     if (scatter) {
       fill_invalid_input_order<<<(n - ctx->n_valid + 255) / 256, 256, 0, st>>>((const int*)ctx->b_perm.p, ctx->n_valid, n, (float)plane_radius,
