@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) normals_kernel(const N
         }
         kk += c;
       }
-      const bool over = pc.active && bin != 255 && in_bin > kTruncCap;
+      // (the RSD pass lists the bin's candidates by their 16-bit position in the candidate stream)
+      const bool over = pc.active && bin != 255 && (in_bin > kTruncCap || pc.total > 65535);
       if (pc.active) a.code[pc.qi] = bin == 255 ? 255 : (bin | ((a.hist_max_nn - before) << 8));
       if (__any_sync(kFull, over) && lane == 0) a.flag[pid - a.p0] = 1;
       __syncwarp();

@@ -305,9 +305,8 @@ struct alignas(16) FastTile {
 // traversal.  Beyond the bin a candidate is dropped.  A query that keeps everything has cut = hi = nextafter(r2).
 template <bool kSelf, bool kCount, bool kTrunc>
 __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float qy, float qz, float nqx, float nqy, float nqz,
-                                          float r2, float bscale, unsigned thr_addr, unsigned spare_off, unsigned bins_addr,
-                                          int sb, float hi, unsigned& tmask, float bscale_low = 0.f, float vmax = 0.f,
-                                          unsigned row_k = 0u) {
+                                          float r2, float bscale_low, float vmax, unsigned row_k, int sb, float hi,
+                                          unsigned& tmask) {
   const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
   const f32x2 nqx2 = pack2(nqx, nqx), nqy2 = pack2(nqy, nqy), nqz2 = pack2(nqz, nqz);
   const float4* tx = reinterpret_cast<const float4*>(tile->x);
@@ -351,64 +350,41 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       ua[i] = __float_as_uint(fabsf(cs[i]));
-      // Bin estimate biased low by kBinBias: the bin is the estimate or the next one, the exact fp32 d2 threshold decides.
-      // The conversion saturates at 255 (misses may lie anywhere; thr[] has 257 entries, +inf from ndiv on).
-      float root;
-      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(root) : "f"(d2[i]));
-      const float est = fmaf(root, bscale, -kBinBias);
-      // The integer tail, spelled out so that it costs what it has to: threshold load, two compares, the row of the
-      // lane's column (hit: estimate, + 1 row if d2 reached the threshold; miss: the spare row and nothing else -- a
-      // staged-away candidate has d2 = inf, which "reaches" the +inf threshold), the neighbour count.
+      // The candidate's bin row, spelled out so that it costs what it has to.  The row comes straight out of the
+      // floating-point pipe: v = 2^23 + floor(root * bscale_low) (fma.rz on the magic constant: the integer sits in the
+      // low mantissa bits; bscale_low = ndiv / radius biased low by 2^-10 relative, so the estimate is the reference's
+      // bin or the one below and never negative), and ONE integer multiply-add turns the float's bits into the lane's
+      // address of that row (row_k holds the lane's column minus 2^23's bits times the stride, modulo 2^32).  The row's
+      // own third column holds the exact fp32 d2 at which a candidate belongs to the next row (computed on the host with
+      // the reference's double expression): the last real row's is nextafter(r2) -- a miss moves on to the spare row --
+      // and the spare row's is NaN (never true).
       // (ptxas turns a predicated shared-memory reduction into a branch around it, so the reductions below are
       // unconditional and the misses go to the spare row.)
       if (kTrunc) {
-        // r2 holds the query's cut: "d2 < cut" keeps the candidate; cut <= d2 < hi marks it in the chunk's target mask
+        // r2 holds the query's cut: "d2 < cut" keeps the candidate (a kept candidate lies inside the radius: its row
+        // needs no clamp; a dropped one goes to the spare row); cut <= d2 < hi marks it in the chunk's target mask
         asm("{\n\t.reg .pred q;\n\t"
             "setp.ge.f32 q, %1, %2;\n\t"
             "setp.lt.and.f32 q, %1, %3, q;\n\t"
             "@q or.b32 %0, %0, %4;\n\t}"
             : "+r"(tm)
             : "f"(d2[i]), "f"(r2), "f"(hi), "r"(1u << (4 * g4 + i)));
-        if (kSelf) {
-          asm("{\n\t.reg .pred p, g, s;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
-              "cvt.rzi.u8.f32 be, %2;\n\t"
-              "mad.lo.u32 ta, be, 4, %5;\n\t"
-              "ld.shared.f32 t, [ta+4];\n\t"
-              "setp.ne.s32 s, %8, %9;\n\t"
-              "setp.lt.and.f32 p, %3, %4, s;\n\t"
-              "setp.ge.and.f32 g, %3, t, p;\n\t"
-              "mul.lo.u32 rb, be, 384;\n\t"
-              "selp.u32 rb, rb, %6, p;\n\t"
-              "selp.u32 go, 384, 0, g;\n\t"
-              "add.u32 rb, rb, go;\n\t"
-              "add.u32 %0, rb, %7;\n\t"
-              "@p add.s32 %1, %1, 1;\n\t}"
-              : "=r"(addr[i]), "+r"(k)
-              : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr), "r"(4 * g4 + i), "r"(sb));
-        } else {  // no query of the packet among this chunk's candidates
-          asm("{\n\t.reg .pred p, g;\n\t.reg .u32 be, ta, rb, go;\n\t.reg .f32 t;\n\t"
-              "cvt.rzi.u8.f32 be, %2;\n\t"
-              "mad.lo.u32 ta, be, 4, %5;\n\t"
-              "ld.shared.f32 t, [ta+4];\n\t"
-              "setp.lt.f32 p, %3, %4;\n\t"
-              "setp.ge.and.f32 g, %3, t, p;\n\t"
-              "mul.lo.u32 rb, be, 384;\n\t"
-              "selp.u32 rb, rb, %6, p;\n\t"
-              "selp.u32 go, 384, 0, g;\n\t"
-              "add.u32 rb, rb, go;\n\t"
-              "add.u32 %0, rb, %7;\n\t"
-              "@p add.s32 %1, %1, 1;\n\t}"
-              : "=r"(addr[i]), "+r"(k)
-              : "f"(est), "f"(d2[i]), "f"(r2), "r"(thr_addr), "r"(spare_off), "r"(bins_addr));
-        }
+        asm("{\n\t.reg .pred p, g, s;\n\t.reg .f32 v, t;\n\t.reg .u32 vi;\n\t"
+            "sqrt.approx.ftz.f32 v, %2;\n\t"
+            "fma.rz.ftz.f32 v, v, %3, 0f4B000000;\n\t"
+            "setp.ne.s32 s, %7, %8;\n\t"
+            "setp.lt.and.f32 p, %2, %6, s;\n\t"
+            "@!p mov.f32 v, %4;\n\t"
+            "mov.b32 vi, v;\n\t"
+            "mad.lo.u32 %0, vi, 384, %5;\n\t"
+            "ld.shared.f32 t, [%0+256];\n\t"
+            "setp.ge.f32 g, %2, t;\n\t"
+            "@g add.u32 %0, %0, 384;\n\t"
+            "@p add.s32 %1, %1, 1;\n\t}"
+            : "=&r"(addr[i]), "+r"(k)
+            : "f"(d2[i]), "f"(bscale_low), "f"(vmax), "r"(row_k), "f"(r2), "r"(4 * g4 + i), "r"(sb));
       } else {
-        // Untruncated pass.  The row comes straight out of the floating-point pipe: v = 2^23 + floor(root * bscale_low)
-        // (fma.rz on the magic constant: the integer sits in the low mantissa bits; bscale_low carries the low bias, so
-        // the product is never negative), clamped to the spare row (misses, staged-away candidates: d2 = inf), and ONE
-        // integer multiply-add turns the float's bits into the lane's address of that row (row_k holds the lane's
-        // column minus 2^23's bits times the stride, modulo 2^32).  The row's own third column holds the d2 at which a
-        // candidate belongs to the next row: the last real row's is nextafter(r2) (a miss moves on to the spare row),
-        // the spare row's is NaN (never true).  7 issue slots against 11 for the table form above.
+        // Untruncated pass: the row is clamped to the spare row (misses, staged-away candidates: d2 = inf).
         if (kSelf) {
           asm("{\n\t.reg .pred p, g, s;\n\t.reg .f32 v, t;\n\t.reg .u32 vi;\n\t"
               "sqrt.approx.ftz.f32 v, %2;\n\t"
@@ -511,7 +487,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
   float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * kRowWords * (a.ndiv + 1));  // [257], +inf from ndiv on
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ndiv = a.ndiv;
-  int* lists = reinterpret_cast<int*>(thr + kFastThr);  // kTrunc: [W][kTruncCap][32], a lane's list of its target bin's candidates (sorted indices)
+  // kTrunc: [W][kTruncCap][32], a lane's list of its target bin's candidates: their positions in the packet's candidate
+  // stream (16 bits: the histogram kernels leave packets with 65536 candidates or more to the exact-threshold path)
+  unsigned short* lists = reinterpret_cast<unsigned short*>(thr + kFastThr);
   for (int i = threadIdx.x; i < kFastThr; i += blockDim.x) thr[i] = i <= ndiv ? a.bin_thr[i] : INFINITY;
   // the bins' distances (di + 0.5) * radius / ndiv (:185): the same double expression, evaluated once per block instead of
   // once per bin and query
@@ -520,11 +498,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
   __syncthreads();
   const GridView& g = a.g;
   FastTile* tile = &tiles[warp];
-  int* lst = lists + (size_t)warp * kTruncCap * kWarp + lane;
+  unsigned short* lst = lists + (size_t)warp * kTruncCap * kWarp + lane;
   unsigned* my_min = bins + (size_t)warp * kRowWords * (ndiv + 1) + lane;  // bin b: min |cos| at my_min[b * 96], max at my_max[b * 96]
   unsigned* my_max = my_min + kWarp;
-  const unsigned bins_addr = smem_u32(my_min), thr_addr = smem_u32(thr);
-  const float r2 = a.r2, bscale = a.bin_scale;
+  const unsigned bins_addr = smem_u32(my_min);
+  const float r2 = a.r2;
   // the rows' threshold columns (see fast_chunk): written once, the packets only reset the two extremes
   for (int b = 0; b <= ndiv; ++b)
     my_min[b * kRowWords + 2 * kWarp] = b < ndiv - 1 ? __float_as_uint(a.bin_thr[b + 1])
@@ -663,21 +641,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
         if (odd_mask)
           k += trunc_slow_chunk(tile, qx, qy, qz, nq.x, nq.y, nq.z, cut, hi, thr, ndiv, my_min, my_max, sb, tmask);
         else  // one body for chunks with and without queries of the packet (sb = -1 matches no slot): half the code
-          k += fast_chunk<true, true, true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, cut, bscale, thr_addr, kRowBytes * (unsigned)ndiv, bins_addr, sb, hi, tmask);
+          k += fast_chunk<true, true, true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, cut, bscale_low, vmax, row_k, sb, hi, tmask);
         k += (sb >= 0 && cut > 0.f) ? 1 : 0;  // the query itself, unless it sits in the target bin (then the list has it)
         while (tmask) {  // the chunk's candidates of the target bin (a handful per query and traversal): listed for the settlement
           const int m = __ffs(tmask) - 1;
           tmask &= tmask - 1;
-          if (lcnt < kTruncCap) lst[lcnt * kWarp] = tile->idx[m];
+          if (lcnt < kTruncCap) lst[lcnt * kWarp] = (unsigned short)(c0 * kWarp + m);
           ++lcnt;
         }
       } else if (own_mask) {
         unsigned dummy_mask;
-        k += fast_chunk<true, true, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, kRowBytes * (unsigned)ndiv, bins_addr, tile->self_slot[lane], 0.f, dummy_mask, bscale_low, vmax, row_k);
+        k += fast_chunk<true, true, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale_low, vmax, row_k, tile->self_slot[lane], 0.f, dummy_mask);
         k += tile->self_slot[lane] >= 0 ? 1 : 0;  // the query itself is a neighbour of the radius search (:120), just not a pair (:150)
       } else {
         unsigned dummy_mask;
-        k += fast_chunk<false, kCount, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale, thr_addr, kRowBytes * (unsigned)ndiv, bins_addr, -1, 0.f, dummy_mask, bscale_low, vmax, row_k);
+        k += fast_chunk<false, kCount, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale_low, vmax, row_k, -1, 0.f, dummy_mask);
       }
       if (!kTrunc && odd_mask) {  // rare: neighbours without a normal still count as neighbours
         unsigned mm = odd_mask;
@@ -699,23 +677,33 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       // the candidates' d2 (the bits the traversal saw): recomputed once each into the warp's tile, whose eight rows the
       // traversal no longer needs; entries beyond the eighth (rare) are recomputed where they are used
       float* scratch = reinterpret_cast<float*>(tile) + lane;
+      // sorted index of list entry e: its stream position looked up in the packet's run table (which sits behind the
+      // tile's eight rows and is still in place)
+      auto idx_of = [&](int e) {
+        const int p = lst[e * kWarp];
+        int t = (p >= tile->run_cum[4]) ? 4 : 0;
+        t += (p >= tile->run_cum[t + 2]) ? 2 : 0;
+        t += (p >= tile->run_cum[t + 1]) ? 1 : 0;
+        t += (t == 7 && p >= tile->run_cum[8]) ? 1 : 0;
+        return tile->run_begin[t] + (p - tile->run_cum[t]);
+      };
       auto d2_of = [&](int e) {
         if (e < 8) return scratch[e * kWarp];
-        const float4 pe = g.pos[lst[e * kWarp]];
+        const float4 pe = g.pos[idx_of(e)];
         return d2_rule(pe.x, pe.y, pe.z, qx, qy, qz);
       };
       for (int e = 0; e < min(L, 8); ++e) {
-        const float4 pe = g.pos[lst[e * kWarp]];
+        const float4 pe = g.pos[idx_of(e)];
         scratch[e * kWarp] = d2_rule(pe.x, pe.y, pe.z, qx, qy, qz);
       }
       for (int e = 0; e < L; ++e) {
-        const int je = lst[e * kWarp];
+        const int je = idx_of(e);
         const float de = d2_of(e);
         int rank = 0;
         for (int f = 0; f < L; ++f) {
           const float df = d2_of(f);
           if (df < de) ++rank;
-          else if (df == de && f != e && g.perm[lst[f * kWarp]] < g.perm[je]) ++rank;
+          else if (df == de && f != e && g.perm[idx_of(f)] < g.perm[je]) ++rank;
         }
         if (rank >= need) continue;
         ++k;
@@ -930,7 +918,7 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
     if (!ctx->cfg.exact && (!use_thr || trunc_fast) && !legacy) {
       const size_t fsmem = (size_t)kWarpsPerBlock * sizeof(FastTile) + (size_t)kWarpsPerBlock * (ndiv + 1) * kRowBytes +
                            (size_t)kFastThr * sizeof(float) + 256 +
-                           (trunc_fast ? (size_t)kWarpsPerBlock * kTruncCap * kWarp * sizeof(int) : 0);
+                           (trunc_fast ? (size_t)kWarpsPerBlock * kTruncCap * kWarp * sizeof(unsigned short) : 0);
       // neighbour counts kept by the last normals pass are this pass's counts if radius and rule were the same
       const bool counted = !trunc_fast && ctx->kcount_r == rf && ctx->kcount_valid;
       a.kcount = counted ? (const int*)ctx->b_kcount.p : nullptr;

@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(kSelWarps * kWarp) nn_hist_kernel(const ThrArg
       k += c;
     }
     // bin: holds neighbour number max_nn + 1, so at least one of its candidates is dropped; kept = max_nn - before of them
-    const bool over = pc.active && bin != 255 && in_bin > kTruncCap;
+    // (the RSD pass lists the bin's candidates by their 16-bit position in the candidate stream)
+    const bool over = pc.active && bin != 255 && (in_bin > kTruncCap || pc.total > 65535);
     if (pc.active) a.code[pc.qi] = bin == 255 ? 255 : (bin | ((a.max_nn - before) << 8));
     if (__any_sync(kFull, over) && lane == 0) a.fallback[pid - a.p0] = 1;
     __syncwarp();
