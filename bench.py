@@ -30,7 +30,7 @@ RADIUS = 0.02
 NDIV = 10
 PLANE_RADIUS = 0.1
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
-KERNELS_VERSION = "r02-v2"  # bumped with every kernel change: profiles/traffic.json is only quoted for the kernels it measured
+KERNELS_VERSION = "r02-v3"  # bumped with every kernel change: profiles/traffic.json is only quoted for the kernels it measured
 
 
 def parse_args():
@@ -706,7 +706,7 @@ def main():
         except Exception:
             traffic = None
     step_bytes = n * (48.0 * kbar + 72.0 + 120.0)
-    roofline = {"bound": "hbm", "kernel": "rsd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "rsd_fast_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": rsd_bytes, "kernel_ms": rsd_ms,
                 "binding_resource": "instruction issue and the shared-memory pipe, not DRAM: the x-sorted rows turn the neighbour "

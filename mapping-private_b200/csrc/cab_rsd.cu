@@ -60,7 +60,8 @@ struct RsdArgs {
   int ndiv;
   int flags;
   float bin_scale;         // ndiv / radius
-  float bin_scale_low;     // the same biased low by 2^-10 relative (fast kernel: the row estimate never exceeds the bin)
+  float magic;             // 2^23
+  float bin_scale_lo, bin_scale_hi;  // the same biased low / high by 2^-18 relative (fast kernel: the two estimates bracket the bin)
   double radius, plane_radius;
   unsigned long long* stats;
   int work_slot;           // which packet work counter this launch pulls from (next_packet)
@@ -281,12 +282,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_kernel(const RsdAr
 // are staged far away (they never contribute, :158-172) and counted in a rare side path; the bins are two arrays
 // [bin][lane] (min |cos|, max |cos|), so that a warp's reductions never meet in a bank whatever bins its lanes hit.
 constexpr int kFastThr = 260;  // entries of the fast kernel's threshold table (257 used; the truncated variant reads it)
-// One bin row of a warp in the fast kernel: min |cos| [32], max |cos| [32] and -- replicated per lane, so that the load
-// is a conflict-free access at a fixed offset from the reduction's own address -- the d2 threshold at which a candidate
-// belongs to the NEXT row [32].
-constexpr int kRowWords = 3 * kWarp;
-constexpr unsigned kRowBytes = kRowWords * sizeof(unsigned);  // 384 (spelled out in the inline PTX below)
-static_assert(kRowBytes == 384, "the inline PTX of fast_chunk hard-codes the row stride");
+// One bin row of a warp in the fast kernel: min |cos| [32], max |cos| [32] (the reductions below reach the second half
+// with a +128 byte offset)
+constexpr int kRowWords = 2 * kWarp;
+constexpr unsigned kRowBytes = kRowWords * sizeof(unsigned);
 struct alignas(16) FastTile {
   float x[kWarp], y[kWarp], z[kWarp];
   float nx[kWarp], ny[kWarp], nz[kWarp];
@@ -303,10 +302,22 @@ struct alignas(16) FastTile {
 // by d2 < cut (a neighbour below the target bin is kept outright), plus one bit per candidate of the target bin
 // (cut <= d2 < hi) in `tmask`: the caller lists those few candidates after the chunk and settles them after the
 // traversal.  Beyond the bin a candidate is dropped.  A query that keeps everything has cut = hi = nextafter(r2).
-template <bool kSelf, bool kCount, bool kTrunc>
+// The ambiguous candidates of fast_chunk (below): the low estimate n = lo - 2^23's bits is the reference's bin or the one
+// below it; thr[b] is the smallest fp32 d2 of bin b (thr[ndiv] = +inf: a neighbour never leaves the last bin).  What the
+// unambiguous path decided for the candidate otherwise -- dropped by the truncation, the query itself, beyond the radius
+// by more than the margin: its row is the spare one already -- stands.
+__device__ __noinline__ unsigned exact_row(unsigned lo, unsigned vb, float d2, float r2, const float* thr, int ndiv, unsigned row_k,
+                                           unsigned addr) {
+  const int n = (int)(lo - 0x4B000000u);
+  if (n >= ndiv || vb == 0x4B000000u + (unsigned)ndiv) return addr;
+  const int b = n + (d2 >= thr[n + 1] ? 1 : 0);
+  return (0x4B000000u + (unsigned)(d2 <= r2 ? min(b, ndiv - 1) : ndiv)) * kRowBytes + row_k;
+}
+
+template <bool kSelf, bool kCount, bool kTrunc, int kUnroll>
 __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float qy, float qz, float nqx, float nqy, float nqz,
-                                          float r2, float bscale_low, float vmax, unsigned row_k, int sb, float hi,
-                                          unsigned& tmask) {
+                                          float r2, float s_lo, float s_hi, float magic, float vmax, unsigned row_k,
+                                          const float* thr, int ndiv, int sb, float hi, unsigned& tmask) {
   const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
   const f32x2 nqx2 = pack2(nqx, nqx), nqy2 = pack2(nqy, nqy), nqz2 = pack2(nqz, nqz);
   const float4* tx = reinterpret_cast<const float4*>(tile->x);
@@ -322,7 +333,7 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
   // on the reductions: the warp barriers around the chunk order them against the plain accesses of the bins.
   // (the truncated variant is unrolled half as far: its body is longer, and fully unrolled the kernel's hot code no longer
   // fits the instruction cache -- ncu showed 3 issue slots in 10 waiting for instructions)
-#pragma unroll(kTrunc ? 4 : 8)
+#pragma unroll(kUnroll)
   for (int g4 = 0; g4 < kWarp / 4; ++g4) {
     const float4 X = tx[g4], Y = ty[g4], Z = tz[g4];
     const float4 NX = tnx[g4], NY = tny[g4], NZ = tnz[g4];
@@ -346,89 +357,67 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
       const f32x2 a = mul2(nqx2, pack2(NX.z, NX.w)), b = mul2(nqy2, pack2(NY.z, NY.w)), c = mul2(nqz2, pack2(NZ.z, NZ.w));
       unpack2(add2(add2(a, b), c), cs[2], cs[3]);
     }
-    unsigned ua[4], addr[4];
+    // The candidates' bin rows, straight out of the floating-point pipe: v = 2^23 + floor(root * scale) (fma.rz on the
+    // magic constant: the integer sits in the low mantissa bits), once with the scale ndiv / radius biased low and once
+    // biased high by 2^-18 relative -- far more than the errors of sqrt.approx (2^-22), of the scale's rounding and of the
+    // reference's own (double)sqrtf(d2) (2^-24) together.  Where the two floors agree, every value in between has that
+    // floor: it IS the reference's bin floor(ndiv * (double)sqrtf(d2) / radius) (:165-168), no threshold needed.  They
+    // disagree for about one candidate in 10^4 (d2 within 2^-17 relative of a bin edge, the radius included): the warp
+    // votes once per group of four and only then consults the exact fp32 d2 thresholds (computed on the host with the
+    // reference's double expression).  ONE integer multiply-add turns the float's bits into the lane's address of the
+    // row (row_k holds the lane's column minus 2^23's bits times the stride, modulo 2^32); misses and staged-away
+    // candidates (d2 = inf) are clamped to the spare row.
+    // (ptxas turns a predicated shared-memory reduction into a branch around it, so the reductions below are
+    // unconditional and the misses go to the spare row.)
+    unsigned ua[4], addr[4], lo[4], vb[4];
+    unsigned amb = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       ua[i] = __float_as_uint(fabsf(cs[i]));
-      // The candidate's bin row, spelled out so that it costs what it has to.  The row comes straight out of the
-      // floating-point pipe: v = 2^23 + floor(root * bscale_low) (fma.rz on the magic constant: the integer sits in the
-      // low mantissa bits; bscale_low = ndiv / radius biased low by 2^-10 relative, so the estimate is the reference's
-      // bin or the one below and never negative), and ONE integer multiply-add turns the float's bits into the lane's
-      // address of that row (row_k holds the lane's column minus 2^23's bits times the stride, modulo 2^32).  The row's
-      // own third column holds the exact fp32 d2 at which a candidate belongs to the next row (computed on the host with
-      // the reference's double expression): the last real row's is nextafter(r2) -- a miss moves on to the spare row --
-      // and the spare row's is NaN (never true).
-      // (ptxas turns a predicated shared-memory reduction into a branch around it, so the reductions below are
-      // unconditional and the misses go to the spare row.)
+      float root;
+      asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(root) : "f"(d2[i]));
+      const float vlo = __fmaf_rz(root, s_lo, magic), vhi = __fmaf_rz(root, s_hi, magic);
+      lo[i] = __float_as_uint(vlo);
+      amb |= lo[i] ^ __float_as_uint(vhi);
+      float v = fminf(vlo, vmax);
       if (kTrunc) {
-        // r2 holds the query's cut: "d2 < cut" keeps the candidate (a kept candidate lies inside the radius: its row
-        // needs no clamp; a dropped one goes to the spare row); cut <= d2 < hi marks it in the chunk's target mask
+        // r2 holds the query's cut: "d2 < cut" keeps the candidate (it lies inside the radius); a dropped one goes to the
+        // spare row; cut <= d2 < hi marks it in the chunk's target mask
         asm("{\n\t.reg .pred q;\n\t"
             "setp.ge.f32 q, %1, %2;\n\t"
             "setp.lt.and.f32 q, %1, %3, q;\n\t"
             "@q or.b32 %0, %0, %4;\n\t}"
             : "+r"(tm)
             : "f"(d2[i]), "f"(r2), "f"(hi), "r"(1u << (4 * g4 + i)));
-        asm("{\n\t.reg .pred p, g, s;\n\t.reg .f32 v, t;\n\t.reg .u32 vi;\n\t"
-            "sqrt.approx.ftz.f32 v, %2;\n\t"
-            "fma.rz.ftz.f32 v, v, %3, 0f4B000000;\n\t"
-            "setp.ne.s32 s, %7, %8;\n\t"
-            "setp.lt.and.f32 p, %2, %6, s;\n\t"
-            "@!p mov.f32 v, %4;\n\t"
-            "mov.b32 vi, v;\n\t"
-            "mad.lo.u32 %0, vi, 384, %5;\n\t"
-            "ld.shared.f32 t, [%0+256];\n\t"
-            "setp.ge.f32 g, %2, t;\n\t"
-            "@g add.u32 %0, %0, 384;\n\t"
+        asm("{\n\t.reg .pred p, s;\n\t"
+            "setp.ne.s32 s, %4, %5;\n\t"
+            "setp.lt.and.f32 p, %2, %3, s;\n\t"
+            "@!p mov.f32 %0, %6;\n\t"
             "@p add.s32 %1, %1, 1;\n\t}"
-            : "=&r"(addr[i]), "+r"(k)
-            : "f"(d2[i]), "f"(bscale_low), "f"(vmax), "r"(row_k), "f"(r2), "r"(4 * g4 + i), "r"(sb));
-      } else {
-        // Untruncated pass: the row is clamped to the spare row (misses, staged-away candidates: d2 = inf).
-        if (kSelf) {
-          asm("{\n\t.reg .pred p, g, s;\n\t.reg .f32 v, t;\n\t.reg .u32 vi;\n\t"
-              "sqrt.approx.ftz.f32 v, %2;\n\t"
-              "fma.rz.ftz.f32 v, v, %3, 0f4B000000;\n\t"
-              "min.f32 v, v, %4;\n\t"
-              "setp.eq.s32 s, %7, %8;\n\t"
-              "@s mov.f32 v, %4;\n\t"
-              "mov.b32 vi, v;\n\t"
-              "mad.lo.u32 %0, vi, 384, %5;\n\t"
-              "ld.shared.f32 t, [%0+256];\n\t"
-              "setp.ge.f32 g, %2, t;\n\t"
-              "@g add.u32 %0, %0, 384;\n\t"
-              "setp.le.and.f32 p, %2, %6, !s;\n\t"
-              "@p add.s32 %1, %1, 1;\n\t}"
-              : "=&r"(addr[i]), "+r"(k)
-              : "f"(d2[i]), "f"(bscale_low), "f"(vmax), "r"(row_k), "f"(r2), "r"(4 * g4 + i), "r"(sb));
-        } else if (kCount) {
-          asm("{\n\t.reg .pred p, g;\n\t.reg .f32 v, t;\n\t.reg .u32 vi;\n\t"
-              "sqrt.approx.ftz.f32 v, %2;\n\t"
-              "fma.rz.ftz.f32 v, v, %3, 0f4B000000;\n\t"
-              "min.f32 v, v, %4;\n\t"
-              "mov.b32 vi, v;\n\t"
-              "mad.lo.u32 %0, vi, 384, %5;\n\t"
-              "ld.shared.f32 t, [%0+256];\n\t"
-              "setp.ge.f32 g, %2, t;\n\t"
-              "@g add.u32 %0, %0, 384;\n\t"
-              "setp.le.f32 p, %2, %6;\n\t"
-              "@p add.s32 %1, %1, 1;\n\t}"
-              : "=&r"(addr[i]), "+r"(k)
-              : "f"(d2[i]), "f"(bscale_low), "f"(vmax), "r"(row_k), "f"(r2));
-        } else {  // the neighbour counts of this radius are known from the normals pass
-          asm("{\n\t.reg .pred g;\n\t.reg .f32 v, t;\n\t.reg .u32 vi;\n\t"
-              "sqrt.approx.ftz.f32 v, %1;\n\t"
-              "fma.rz.ftz.f32 v, v, %2, 0f4B000000;\n\t"
-              "min.f32 v, v, %3;\n\t"
-              "mov.b32 vi, v;\n\t"
-              "mad.lo.u32 %0, vi, 384, %4;\n\t"
-              "ld.shared.f32 t, [%0+256];\n\t"
-              "setp.ge.f32 g, %1, t;\n\t"
-              "@g add.u32 %0, %0, 384;\n\t}"
-              : "=&r"(addr[i])
-              : "f"(d2[i]), "f"(bscale_low), "f"(vmax), "r"(row_k));
-        }
+            : "+f"(v), "+r"(k)
+            : "f"(d2[i]), "f"(r2), "r"(4 * g4 + i), "r"(sb), "f"(vmax));
+      } else if (kSelf) {
+        asm("{\n\t.reg .pred p, s;\n\t"
+            "setp.eq.s32 s, %4, %5;\n\t"
+            "@s mov.f32 %0, %6;\n\t"
+            "setp.le.and.f32 p, %2, %3, !s;\n\t"
+            "@p add.s32 %1, %1, 1;\n\t}"
+            : "+f"(v), "+r"(k)
+            : "f"(d2[i]), "f"(r2), "r"(4 * g4 + i), "r"(sb), "f"(vmax));
+      } else if (kCount) {
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.le.f32 p, %1, %2;\n\t"
+            "@p add.s32 %0, %0, 1;\n\t}"
+            : "+r"(k)
+            : "f"(d2[i]), "f"(r2));
       }
+      vb[i] = __float_as_uint(v);
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr[i]) : "r"(vb[i]), "n"(kRowBytes), "r"(row_k));
+    }
+    if (__any_sync(kFull, amb != 0)) {
+      // some lane's candidate sits within 2^-17 of a bin edge: its row from the exact thresholds (out of line: rare)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) addr[i] = exact_row(lo[i], vb[i], d2[i], kTrunc ? INFINITY : r2, thr, ndiv, row_k, addr[i]);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -479,11 +468,11 @@ __device__ __forceinline__ float bin_edge(float t, float scale) {
   return x;
 }
 
-template <bool kCount, bool kTrunc>
+template <bool kCount, bool kTrunc, int kUnroll>
 __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const RsdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastTile* tiles = reinterpret_cast<FastTile*>(smem_raw);                          // [W]
-  unsigned* bins = reinterpret_cast<unsigned*>(tiles + kWarpsPerBlock);                    // [W][ndiv + 1][3][32], row ndiv: the misses
+  unsigned* bins = reinterpret_cast<unsigned*>(tiles + kWarpsPerBlock);                    // [W][ndiv + 1][2][32], row ndiv: the misses
   float* thr = reinterpret_cast<float*>(bins + kWarpsPerBlock * kRowWords * (a.ndiv + 1));  // [257], +inf from ndiv on
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ndiv = a.ndiv;
@@ -499,16 +488,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
   const GridView& g = a.g;
   FastTile* tile = &tiles[warp];
   unsigned short* lst = lists + (size_t)warp * kTruncCap * kWarp + lane;
-  unsigned* my_min = bins + (size_t)warp * kRowWords * (ndiv + 1) + lane;  // bin b: min |cos| at my_min[b * 96], max at my_max[b * 96]
+  unsigned* my_min = bins + (size_t)warp * kRowWords * (ndiv + 1) + lane;  // bin b: min |cos| at my_min[b * 64], max at my_max[b * 64]
   unsigned* my_max = my_min + kWarp;
   const unsigned bins_addr = smem_u32(my_min);
   const float r2 = a.r2;
-  // the rows' threshold columns (see fast_chunk): written once, the packets only reset the two extremes
-  for (int b = 0; b <= ndiv; ++b)
-    my_min[b * kRowWords + 2 * kWarp] = b < ndiv - 1 ? __float_as_uint(a.bin_thr[b + 1])
-                                        : b == ndiv - 1 ? __float_as_uint(a.r2) + 1u  // nextafter(r2): d2 > r2 leaves the last bin
-                                                        : 0x7fc00000u;               // the spare row: NaN, nothing moves on
-  const float bscale_low = a.bin_scale_low, vmax = 8388608.f + (float)ndiv;
+  // (2^23 arrives as a kernel argument: as an immediate it would take the operand slot the scales' constant-bank
+  // addresses need, and every group of candidates would load the scales again)
+  const float s_lo = a.bin_scale_lo, s_hi = a.bin_scale_hi, magic = a.magic, vmax = 8388608.f + (float)ndiv;
   const unsigned row_k = bins_addr - 0x4B000000u * kRowBytes;  // modulo 2^32: the multiply-add of fast_chunk wraps the same way
   const int p0 = a.range ? a.range[0] : a.p0, n1 = (a.range ? a.range[1] : a.p1) - p0;
   const int pb = a.range_b ? a.range_b[0] : 0, n2 = a.range_b ? a.range_b[1] - pb : 0;
@@ -641,7 +627,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
         if (odd_mask)
           k += trunc_slow_chunk(tile, qx, qy, qz, nq.x, nq.y, nq.z, cut, hi, thr, ndiv, my_min, my_max, sb, tmask);
         else  // one body for chunks with and without queries of the packet (sb = -1 matches no slot): half the code
-          k += fast_chunk<true, true, true>(tile, qx, qy, qz, nq.x, nq.y, nq.z, cut, bscale_low, vmax, row_k, sb, hi, tmask);
+          k += fast_chunk<true, true, true, kUnroll>(tile, qx, qy, qz, nq.x, nq.y, nq.z, cut, s_lo, s_hi, magic, vmax, row_k, thr, ndiv, sb, hi, tmask);
         k += (sb >= 0 && cut > 0.f) ? 1 : 0;  // the query itself, unless it sits in the target bin (then the list has it)
         while (tmask) {  // the chunk's candidates of the target bin (a handful per query and traversal): listed for the settlement
           const int m = __ffs(tmask) - 1;
@@ -651,11 +637,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
         }
       } else if (own_mask) {
         unsigned dummy_mask;
-        k += fast_chunk<true, true, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale_low, vmax, row_k, tile->self_slot[lane], 0.f, dummy_mask);
+        k += fast_chunk<true, true, false, kUnroll>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, s_lo, s_hi, magic, vmax, row_k, thr, ndiv, tile->self_slot[lane], 0.f, dummy_mask);
         k += tile->self_slot[lane] >= 0 ? 1 : 0;  // the query itself is a neighbour of the radius search (:120), just not a pair (:150)
       } else {
         unsigned dummy_mask;
-        k += fast_chunk<false, kCount, false>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, bscale_low, vmax, row_k, -1, 0.f, dummy_mask);
+        k += fast_chunk<false, kCount, false, kUnroll>(tile, qx, qy, qz, nq.x, nq.y, nq.z, r2, s_lo, s_hi, magic, vmax, row_k, thr, ndiv, -1, 0.f, dummy_mask);
       }
       if (!kTrunc && odd_mask) {  // rare: neighbours without a normal still count as neighbours
         unsigned mm = odd_mask;
@@ -903,7 +889,9 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
   a.ndiv = ndiv;
   a.flags = flags;
   a.bin_scale = (float)(ndiv / r);
-  a.bin_scale_low = (float)(ndiv / r * (1.0 - 1.0 / 1024.0));
+  a.magic = 8388608.f;
+  a.bin_scale_lo = (float)(ndiv / r * (1.0 - 1.0 / 262144.0));
+  a.bin_scale_hi = (float)(ndiv / r * (1.0 + 1.0 / 262144.0));
   a.radius = r;
   a.plane_radius = plane_radius;
 
@@ -927,7 +915,11 @@ int run_rsd(cab_ctx* ctx, double r, int max_nn, int ndiv, double plane_radius, i
         a.trunc_scale = (float)kTruncBins / r2;
         a.skip = (const unsigned char*)ctx->b_thr_flag.p;
       }
-      auto kernel = trunc_fast ? rsd_fast_kernel<true, true> : counted ? rsd_fast_kernel<false, false> : rsd_fast_kernel<true, false>;
+      static const int unroll_env = std::getenv("CAB_FAST_UNROLL") ? std::atoi(std::getenv("CAB_FAST_UNROLL")) : 0;  // A/B switch
+      const int un = unroll_env ? unroll_env : (trunc_fast ? 4 : 8);
+      auto kernel = trunc_fast ? (un == 2 ? rsd_fast_kernel<true, true, 2> : un == 8 ? rsd_fast_kernel<true, true, 8> : rsd_fast_kernel<true, true, 4>)
+                    : counted  ? (un == 2 ? rsd_fast_kernel<false, false, 2> : un == 4 ? rsd_fast_kernel<false, false, 4> : rsd_fast_kernel<false, false, 8>)
+                               : (un == 2 ? rsd_fast_kernel<true, false, 2> : un == 4 ? rsd_fast_kernel<true, false, 4> : rsd_fast_kernel<true, false, 8>);
       CAB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       int per_sm = 1;
       CAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * kWarp, fsmem));
