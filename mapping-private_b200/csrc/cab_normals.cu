@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 
 #include "cab_internal.cuh"
 #include "cab_traverse.cuh"
