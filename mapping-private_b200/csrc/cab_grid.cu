@@ -99,7 +99,7 @@ __device__ __forceinline__ unsigned long long point_key(float x, float y, float 
   if (!finite3(x, y, z)) return sentinel_row << xbits;
   int cy, cz;
   row_cells(dm, y, z, inv_cell, cy, cz);
-  const int xf = xfine_coord(x, dm.ox, inv_cell, dm.nx, dm.xshift);
+  const int xf = xfine_coord(x, dm.ox, inv_cell, dm.nx, dm.xshift, dm.xwide);
   const long long row_local = (long long)cz * dm.ny + cy;
   atomicAdd(cellcnt + dm.cell_base + row_local * dm.nx + (xf >> dm.xshift), 1);
   return ((unsigned long long)(dm.row_base + row_local) << xbits) | (unsigned)xf;
@@ -259,7 +259,11 @@ __global__ void __launch_bounds__(256) segment_kernel(const Domain* __restrict__
       len = 1;
       while (cx + len < dm.nx && cell_start[c + len + 1] > cell_start[c + len]) ++len;
       const int pts = cell_start[c + len] - cell_start[c];
-      npk = max((pts + kWarp - 1) / kWarp, (len + kSpanCap - 1) / kSpanCap);
+      // (wide cells say nothing about where in them the points sit -- a row that crosses a tilted surface has all of them
+      // within two or three edges -- so there the packets are cut by count alone; a full packet of a cloud sparse enough
+      // for wide cells spans about six edges)
+      npk = (pts + kWarp - 1) / kWarp;
+      if (dm.xwide == 0) npk = max(npk, (len + kSpanCap - 1) / kSpanCap);
       npk = min(npk, pts);
     }
   }
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(256) sample_hist_kernel(const float* __restric
     if (!finite3(x, y, z)) continue;
     int cy, cz;
     row_cells(dm, y, z, inv_cell, cy, cz);
-    const int cx = xfine_coord(x, dm.ox, inv_cell, dm.nx, dm.xshift) >> dm.xshift;
+    const int cx = xfine_coord(x, dm.ox, inv_cell, dm.nx, dm.xshift, dm.xwide) >> dm.xshift;
     atomicAdd(cellcnt + ((long long)cz * dm.ny + cy) * dm.nx + cx, 1);  // no return value: a fire-and-forget reduction
   }
 }
@@ -584,7 +588,7 @@ __global__ void __launch_bounds__(256) slab_key_kernel(const SelPoint* __restric
     const SelPoint p = stage[src];
     int cy, cz;
     row_cells(dm, p.y, p.z, inv_cell, cy, cz);
-    const int xf = xfine_coord(p.x, dm.ox, inv_cell, dm.nx, dm.xshift);
+    const int xf = xfine_coord(p.x, dm.ox, inv_cell, dm.nx, dm.xshift, dm.xwide);
     const long long lrow = (long long)cz * dm.ny + cy - dm.row_lo;
     atomicAdd(cellcnt + lrow * dm.nx + (xf >> dm.xshift), 1);
     keys[first + i] = (KeyT)(((unsigned long long)lrow << xbits) | (unsigned)xf);
@@ -736,14 +740,31 @@ int build_grid(cab_ctx* ctx, float cell) {
   // The cell table is dense.  A cloud too spread out for it at the requested cell size (an outdoor scan with a 2 cm
   // radius) gets coarser cells instead of an error: any edge >= the radius is correct, the passes just test more
   // candidates per query.
+  // A cloud much sparser than the table at the requested edge (few neighbours per query: tens of cells per point) gets
+  // cells that are 2^xwide edges WIDE along x before it gets coarser ones: a row's candidates are a range of its sorted
+  // points found by binary search over the fine x coordinate, so wide cells cost two or three more probes per search
+  // and no candidates, while the passes over the table (memset, scan, segments) shrink with it.
+  constexpr int kMaxWide = 4;
+  int xwide = 0;
   for (int attempt = 0;; ++attempt) {
     rows = cells = 0;
-    double want = 0;  // cells this edge would need, as a double (it may overflow int64)
-    bool too_big = false;
+    double want = 0;  // cells this edge would need at xwide = 0, as a double (it may overflow int64)
     for (int d = 0; d < nd; ++d) {
+      if (ctx->dom_count[d] == 0) continue;
+      double nn[3];
+      for (int a = 0; a < 3; ++a)
+        nn[a] = std::floor(((double)ctx->dom_bounds[6 * (size_t)d + 3 + a] - (double)ctx->dom_bounds[6 * (size_t)d + a]) / cell_eff) + 2;
+      want += nn[0] * nn[1] * nn[2];
+    }
+    xwide = 0;
+    while (xwide < kMaxWide && std::ldexp(want, -xwide) > std::max(4.0 * (double)n_valid, 1048576.0)) ++xwide;
+    bool too_big = false;
+    double have = 0;
+    for (int d = 0; d < nd && !too_big; ++d) {
       Domain& dm = ctx->domains[d];
       dm.row_base = rows;
       dm.cell_base = cells;
+      dm.xwide = xwide;
       if (ctx->dom_count[d] == 0) {
         dm.ox = dm.oy = dm.oz = 0.f;
         dm.nx = dm.ny = dm.nz = 1;
@@ -759,10 +780,11 @@ int build_grid(cab_ctx* ctx, float cell) {
         double ext[3] = {(double)hi[0] - lo[0], (double)hi[1] - lo[1], (double)hi[2] - lo[2]};
         double nn[3];
         for (int a = 0; a < 3; ++a) nn[a] = std::floor(ext[a] / cell_eff) + 2;  // +1 slack cell
-        want += nn[0] * nn[1] * nn[2];
-        if (nn[0] > (double)(1 << kXBits) || nn[1] * nn[2] > std::ldexp(1.0, 40) || want > (double)budget) {
+        nn[0] = std::ceil(std::ldexp(nn[0], -xwide));                          // wide cells along x
+        have += nn[0] * nn[1] * nn[2];
+        if (nn[0] > (double)(1 << kXBits) || nn[1] * nn[2] > std::ldexp(1.0, 40) || have > (double)budget) {
           too_big = true;
-          continue;
+          break;
         }
         dm.nx = (int)nn[0];
         dm.ny = (int)nn[1];
@@ -781,7 +803,7 @@ int build_grid(cab_ctx* ctx, float cell) {
     if (!too_big) break;
     if (attempt >= 60 || !std::isfinite(cell_eff))
       return fail(ctx, CAB_ERR_OOM, "cab_build_grid: no cell size fits the dense cell table (budget %lld cells)", (long long)budget);
-    cell_eff *= std::max(1.26, std::min(8.0, std::cbrt(want / (double)budget) * 1.02));
+    cell_eff *= std::max(1.26, std::min(8.0, std::cbrt(std::ldexp(want, -xwide) / (double)budget) * 1.02));
   }
   ctx->cell_eff = (float)cell_eff;
   if ((double)ctx->cell_eff < cell_eff) ctx->cell_eff = std::nextafter(ctx->cell_eff, INFINITY);
@@ -797,12 +819,12 @@ int build_grid(cab_ctx* ctx, float cell) {
   for (int d = 0; d < nd; ++d) nx_max = std::max(nx_max, ctx->domains[d].nx);
   int nx_bits = 0;
   while ((1 << nx_bits) < nx_max) ++nx_bits;
-  const bool key32 = row_bits + nx_bits + 2 <= 32;
+  const bool key32 = row_bits + nx_bits + xwide + 2 <= 32;  // (the sub-cell bits count from the cell EDGE, not the wide cell)
   const int xbits = key32 ? std::min(kXBits, 32 - row_bits) : kXBits;
   for (int d = 0; d < nd; ++d) {
     Domain& dm = ctx->domains[d];
-    dm.xshift = 0;
-    while (dm.xshift < 8 && ((int64_t)dm.nx << (dm.xshift + 1)) <= ((int64_t)1 << xbits)) dm.xshift++;
+    dm.xshift = dm.xwide;  // x_fine >> xshift = cell x; the fine steps are 2^-(xshift - xwide) of an edge
+    while (dm.xshift - dm.xwide < 8 && ((int64_t)dm.nx << (dm.xshift + 1)) <= ((int64_t)1 << xbits)) dm.xshift++;
     dm.row_lo = 0;
     dm.row_hi = dm.ny * dm.nz;
   }

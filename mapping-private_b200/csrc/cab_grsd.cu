@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) voxel_rsd_kernel(const VRsdArgs a) {
       return;
     }
   }
-  const int cx = xfine_coord(q.x, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift;
+  const int cx = xfine_coord(q.x, dm.ox, g.inv_cell, dm.nx, dm.xshift, dm.xwide) >> dm.xshift;
   const int cxlo = max(cx - 1, 0), cxhi = min(cx + 1, dm.nx - 1);
   int rb = 0, re = 0;
   if (lane < 9) {

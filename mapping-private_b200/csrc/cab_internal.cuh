@@ -27,6 +27,7 @@ struct Domain {
   float ox, oy, oz;      // grid origin
   int nx, ny, nz;        // cells per axis
   int xshift;            // x_fine >> xshift == cell x
+  int xwide;             // a cell is 2^xwide cell edges wide along x (0 unless the table would dwarf the cloud)
   int swap_yz;           // 1: the grid's y slot holds the physical z axis and its z slot the physical y axis
                          // (the slowest-varying slot gets the longer of the two extents: thinner shard halos)
   int64_t row_base;      // first row id of this domain (row = row_base + cz*ny + cy)
@@ -105,9 +106,10 @@ __device__ __forceinline__ bool row_in_table(const Domain& dm, int y, int z) {
   const int row = z * dm.ny + y;
   return row >= dm.row_lo && row < dm.row_hi;
 }
-// Fine x coordinate (sub-cell resolution 2^-xshift of a cell).
-__device__ __forceinline__ int xfine_coord(float x, float ox, float inv_cell, int nx, int xshift) {
-  float s = __fmul_rn(__fsub_rn(x, ox), __fmul_rn(inv_cell, (float)(1 << xshift)));
+// Fine x coordinate: steps of 2^-(xshift - xwide) of the cell edge; x_fine >> xshift is the cell along x, which is
+// 2^xwide edges wide (xwide > 0 only for clouds much sparser than the cell table, see build_grid).
+__device__ __forceinline__ int xfine_coord(float x, float ox, float inv_cell, int nx, int xshift, int xwide) {
+  float s = __fmul_rn(__fsub_rn(x, ox), __fmul_rn(inv_cell, (float)(1 << (xshift - xwide))));
   int c = (int)floorf(s);
   return min(max(c, 0), (nx << xshift) - 1);
 }

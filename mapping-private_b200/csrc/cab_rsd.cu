@@ -541,10 +541,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
         rc = fminf(rc, sqrtf(warp_max(hi)) * 1.00001f);
       }
       const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
-      const int cxlo = max((xfine_coord(xmin, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift) - 1, 0);
-      const int cxhi = min((xfine_coord(xmax, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift) + 1, dm.nx - 1);
-      const int xf_lo = xfine_coord(xmin - rc, dm.ox, g.inv_cell, dm.nx, dm.xshift);
-      const int xf_hi = xfine_coord(xmax + rc, dm.ox, g.inv_cell, dm.nx, dm.xshift);
+      const int cxlo = max((xfine_coord(xmin, dm.ox, g.inv_cell, dm.nx, dm.xshift, dm.xwide) >> dm.xshift) - 1, 0);
+      const int cxhi = min((xfine_coord(xmax, dm.ox, g.inv_cell, dm.nx, dm.xshift, dm.xwide) >> dm.xshift) + 1, dm.nx - 1);
+      const int xf_lo = xfine_coord(xmin - rc, dm.ox, g.inv_cell, dm.nx, dm.xshift, dm.xwide);
+      const int xf_hi = xfine_coord(xmax + rc, dm.ox, g.inv_cell, dm.nx, dm.xshift, dm.xwide);
       const int t = lane & 15;
       int lo = 0, hi = 0;
       if (t < 9) {
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * kWarp) rsd_fast_kernel(const 
       const int key = lane < 16 ? xf_lo : xf_hi + 1;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const int xf = xfine_coord(g.pos[mid].x, dm.ox, g.inv_cell, dm.nx, dm.xshift);
+        const int xf = xfine_coord(g.pos[mid].x, dm.ox, g.inv_cell, dm.nx, dm.xshift, dm.xwide);
         if (xf < key) lo = mid + 1; else hi = mid;
       }
       const int end = __shfl_sync(kFull, lo, (lane + 16) & 31);

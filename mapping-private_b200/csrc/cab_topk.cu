@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(128) neighbors_debug_kernel(const DbgArgs a) {
     const Domain dm = a.g.domains[d];
     int cy, cz;
     row_cells(dm, qy, qz, a.g.inv_cell, cy, cz);
-    const int cx = xfine_coord(qx, dm.ox, a.g.inv_cell, dm.nx, dm.xshift) >> dm.xshift;
+    const int cx = xfine_coord(qx, dm.ox, a.g.inv_cell, dm.nx, dm.xshift, dm.xwide) >> dm.xshift;
     const int cxlo = max(cx - 1, 0), cxhi = min(cx + 1, dm.nx - 1);
     float td2 = INFINITY;
     int tidx = INT_MAX;

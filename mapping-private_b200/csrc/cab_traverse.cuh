@@ -101,11 +101,11 @@ __device__ __forceinline__ PacketCtx load_packet(const GridView& g, int pid, int
   const float xmin = warp_min(pc.q.x), xmax = warp_max(pc.q.x);
   const float rc = r * 1.00001f;
   const int cy = pk.row_local % dm.ny, cz = pk.row_local / dm.ny;
-  const int cxlo = max((xfine_coord(xmin, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift) - 1, 0);
-  const int cxhi = min((xfine_coord(xmax, dm.ox, g.inv_cell, dm.nx, dm.xshift) >> dm.xshift) + 1, dm.nx - 1);
+  const int cxlo = max((xfine_coord(xmin, dm.ox, g.inv_cell, dm.nx, dm.xshift, dm.xwide) >> dm.xshift) - 1, 0);
+  const int cxhi = min((xfine_coord(xmax, dm.ox, g.inv_cell, dm.nx, dm.xshift, dm.xwide) >> dm.xshift) + 1, dm.nx - 1);
   // fine-x window: x >= xmin - rc  =>  xf(x) >= xf(xmin - rc) (xf is monotone), same at the top
-  const int xf_lo = xfine_coord(xmin - rc, dm.ox, g.inv_cell, dm.nx, dm.xshift);
-  const int xf_hi = xfine_coord(xmax + rc, dm.ox, g.inv_cell, dm.nx, dm.xshift);
+  const int xf_lo = xfine_coord(xmin - rc, dm.ox, g.inv_cell, dm.nx, dm.xshift, dm.xwide);
+  const int xf_hi = xfine_coord(xmax + rc, dm.ox, g.inv_cell, dm.nx, dm.xshift, dm.xwide);
   const int t = lane & 15;  // run handled by this lane (lanes 0..8 lower bound, 16..24 upper bound)
   int lo = 0, hi = 0;
   if (t < 9) {
@@ -120,7 +120,7 @@ __device__ __forceinline__ PacketCtx load_packet(const GridView& g, int pid, int
   const int key = lane < 16 ? xf_lo : xf_hi + 1;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    const int xf = xfine_coord(g.pos[mid].x, dm.ox, g.inv_cell, dm.nx, dm.xshift);
+    const int xf = xfine_coord(g.pos[mid].x, dm.ox, g.inv_cell, dm.nx, dm.xshift, dm.xwide);
     if (xf < key) lo = mid + 1; else hi = mid;
   }
   const int end = __shfl_sync(kFull, lo, (lane + 16) & 31);

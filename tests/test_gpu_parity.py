@@ -487,6 +487,39 @@ def test_density_patches_neighbour_sets(ctx, oracle, k_mean):
     gi, gd = _canon(off, idx, d2)
     assert np.array_equal(gi, oidx) and np.array_equal(gd.view(np.uint32), od2.view(np.uint32))
     assert 0.7 * k_mean < (off[-1] / (q1 - q0)) < 1.3 * k_mean
+    # the sparse end gets cells that are wide along x (the table would otherwise hold tens of cells per point); the
+    # dense end keeps cubic cells
+    ext = pts.max(axis=0).astype(np.float64) - pts.min(axis=0).astype(np.float64)
+    cubic = np.prod(np.floor(ext / (r * (1 + 1 / 1024))) + 2)
+    n_cells = ctx.profile()["n_cells"]
+    if k_mean == 16:
+        assert cubic > 16 * pts.shape[0] and n_cells < cubic / 4, (cubic, n_cells)
+    else:
+        assert n_cells > cubic / 2, (cubic, n_cells)
+
+
+def test_wide_cells_normals_and_radii(oracle):
+    """A sparse cloud (mean 16 neighbours): with the cell table 16 edges wide along x, normals and radii still are what the
+    oracle says for every point."""
+    pts = synth.density_patches(300_000, 16.0, 0.02)
+    r = 0.02
+    c = cab.Context(0)
+    c.upload(pts)
+    c.build_grid(r)
+    ext = pts.max(axis=0).astype(np.float64) - pts.min(axis=0).astype(np.float64)
+    assert c.profile()["n_cells"] < np.prod(np.floor(ext / (r * (1 + 1 / 1024))) + 2) / 4
+    n4 = c.normals(r)
+    o4, ok = oracle.normals(pts, r)
+    assert c.profile()["neighbour_sum"] == int(ok.sum())
+    good = ~np.isnan(o4[:, 0])
+    assert np.array_equal(np.isnan(n4[:, 0]), ~good)
+    ang = np.linalg.norm(np.cross(n4[good, :3].astype(np.float64), o4[good, :3].astype(np.float64)), axis=1)
+    assert np.mean(ang > NORMAL_TOL_RAD) < 5e-3  # (sparse neighbourhoods: a few near-degenerate covariances)
+    c.set_normals(np.nan_to_num(o4[:, :3], nan=0.0))
+    rmin, rmax = c.rsd(r)
+    omin, omax, _ = oracle.rsd(pts, np.nan_to_num(o4[:, :3], nan=0.0), r)
+    assert np.max(np.abs(rmin - omin) / omin) <= RADIUS_TOL_REL and np.max(np.abs(rmax - omax) / omax) <= RADIUS_TOL_REL
+    c.close()
 
 
 def test_spread_out_cloud_gets_coarser_cells(oracle):
