@@ -76,25 +76,35 @@ def slab_sample(pts, target):
 
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region.  NVML (what nvidia-smi reads) is polled from a
-    thread every few milliseconds, so that even a 50 ms region (8 GPUs) gets samples; nvidia-smi -lms is the fallback."""
+    thread every 10 ms, so that even a 60 ms region (8 GPUs) gets samples; nvidia-smi -lms is the fallback.  Only rank 0
+    polls (its line is the one printed), the constant maximum clock is read once, and the first query of every kind is
+    made before the region starts: NVML queries go through the driver's node-wide lock, and eight ranks polling four
+    queries every 4 ms were a measurable source of launch jitter in a 3 ms step."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, period_s=0.004):
+    def __init__(self, index, period_s=0.010, enabled=True):
         self.index = index
         self.period_s = period_s
+        self.enabled = enabled
         self.proc = None
         self.thread = None
         self.rows = []  # (sm MHz, max MHz, watts, reasons bit mask)
         self._stop = False
         self.nvml = None
+        self.max_mhz = None
+        if not enabled:
+            return
         try:
             import pynvml
 
             pynvml.nvmlInit()
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self._sample()  # the first query of every kind outside the timed region
+            self.rows.clear()
         except Exception:
             self.nvml = None
 
@@ -102,7 +112,7 @@ class ClockSampler:
         nv = self.nvml
         try:
             sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
-            mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+            mx = self.max_mhz
             try:
                 mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
             except Exception:
@@ -121,6 +131,8 @@ class ClockSampler:
             time.sleep(self.period_s)
 
     def start(self):
+        if not self.enabled:
+            return
         if self.nvml:
             import threading
 
@@ -137,6 +149,8 @@ class ClockSampler:
 
     def stop(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if not self.enabled:
+            return None
         if self.nvml:
             self._stop = True
             if self.thread:
@@ -457,7 +471,7 @@ def run_grsd(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         hist = step()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -614,7 +628,7 @@ def main():
     for _ in range(warmup):
         step()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -637,6 +651,10 @@ def main():
     prof = ctx.profile()
     launches = prof["kernel_launches"] - launches0
     my_phase = {k: statistics.mean(v) for k, v in phases.items()}
+    # (a single slow step -- a host hiccup on one rank -- shows here instead of hiding in the mean)
+    my_phase["step_ms_median"] = statistics.median(phases["step_ms"])
+    my_phase["step_ms_max"] = max(phases["step_ms"])
+    my_phase["build_ms_max"] = max(phases["build_ms"])
     my_phase["own_queries"] = (lambda b_e: b_e[1] - b_e[0])(ctx.shard_range())
     my_phase["points_sorted"] = prof["n_sorted"]
     if world > 1:

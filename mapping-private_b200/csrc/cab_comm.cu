@@ -675,7 +675,10 @@ int comm_step_finish(cab_ctx* ctx) {  // after the step's synchronisation
     if (ok && mean > 5e5) {
       double sum = 0;
       for (int p = 0; p < cs->world; ++p) {
-        double s = cs->share[p] * std::pow(mean / (double)busy[p], 0.75);
+        // (one step moves a share by a tenth at most: a single mistimed step -- a host hiccup that leaves a rank's kernels
+        // waiting -- then cannot hand a rank half the cloud; a real imbalance of a few percent still settles in two steps)
+        const double f = std::min(std::max(std::pow(mean / (double)busy[p], 0.75), 0.9), 1.1);
+        double s = cs->share[p] * f;
         s = std::min(std::max(s, 0.25 / cs->world), 4.0 / cs->world);
         cs->share[p] = s;
         sum += s;
