@@ -130,7 +130,9 @@ int cab_rsd(cab_ctx* ctx, double r, int32_t max_nn, int32_t ndiv, double plane_r
  * layout CAB_OUT_INPUT_ORDER: nxyz_curv n x 4, out_a = r_min[n], out_b = r_max[n] in input order
  * (input_index unused).  layout CAB_OUT_SHARD_SORTED (multi-GPU): this context's cab_shard_range
  * only, in sorted order: nxyz_curv m x 4, out_a = m x {r_min, r_max}, input_index[m] (out_b unused).
- * Any output pointer may be NULL.  Host buffers should be page-locked for the overlap to happen. */
+ * Any output pointer may be NULL.  Host buffers should be page-locked for the overlap to happen.
+ * (Input-order layout: the two pass kernels store every query's result at its input index themselves, next to the
+ * sorted-order arrays the second pass reads, so no permutation pass stands between a kernel and its copy.) */
 #define CAB_OUT_INPUT_ORDER 0
 #define CAB_OUT_SHARD_SORTED 1
 int cab_normals_rsd(cab_ctx* ctx, double r, int32_t max_nn_normals, const float vp[3], int32_t max_nn_rsd,
