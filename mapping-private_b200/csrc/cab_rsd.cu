@@ -374,7 +374,7 @@ __device__ __forceinline__ int fast_chunk(const FastTile* tile, float qx, float 
     unsigned amb = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      ua[i] = __float_as_uint(fabsf(cs[i]));
+      ua[i] = __float_as_uint(cs[i]) & 0x7fffffffu;  // |cos| on the integer pipe (the FP32 pipes are the busier ones)
       float root;
       asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(root) : "f"(d2[i]));
       float vlo, vhi;  // both estimates from one packed fma.rz

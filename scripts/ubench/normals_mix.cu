@@ -21,13 +21,41 @@ __device__ __forceinline__ void accum_pred(float d2, float r2, float dx, float d
       : "f"(d2), "f"(r2), "f"(dx), "f"(dy), "f"(dz));
 }
 
+// accumulate variants (second template parameter):
+//  0: predicated 3 FADD + 6 FFMA + IADD (the kernel in the tree)
+//  1: deltas zeroed for a miss (3 FSEL), then unpredicated 3 FADD + 6 FFMA, predicated IADD
+//  2: as 1 with the three additions written as FFMA(d, 1, s)
+//  3: predicated, the three additions written as FFMA(d, 1, s)
+template <int ACC>
+__device__ __forceinline__ void accum_var(float d2, float r2, float dx, float dy, float dz, float& s1x, float& s1y, float& s1z,
+                                          float& sxx, float& sxy, float& sxz, float& syy, float& syz, float& szz, int& k) {
+  if (ACC == 0) {
+    accum_pred(d2, r2, dx, dy, dz, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, k);
+  } else if (ACC == 1 || ACC == 2) {
+    float ex, ey, ez;
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %4, %5;\n\tselp.f32 %0, %6, 0f00000000, p;\n\tselp.f32 %1, %7, 0f00000000, p;\n\t"
+        "selp.f32 %2, %8, 0f00000000, p;\n\t@p add.s32 %3, %3, 1;\n\t}"
+        : "=f"(ex), "=f"(ey), "=f"(ez), "+r"(k) : "f"(d2), "f"(r2), "f"(dx), "f"(dy), "f"(dz));
+    if (ACC == 1) { s1x = __fadd_rn(s1x, ex); s1y = __fadd_rn(s1y, ey); s1z = __fadd_rn(s1z, ez); }
+    else { s1x = __fmaf_rn(ex, 1.0f, s1x); s1y = __fmaf_rn(ey, 1.0f, s1y); s1z = __fmaf_rn(ez, 1.0f, s1z); }
+    sxx = __fmaf_rn(ex, ex, sxx); sxy = __fmaf_rn(ex, ey, sxy); sxz = __fmaf_rn(ex, ez, sxz);
+    syy = __fmaf_rn(ey, ey, syy); syz = __fmaf_rn(ey, ez, syz); szz = __fmaf_rn(ez, ez, szz);
+  } else {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %10, %11;\n\t@p fma.rn.f32 %0, %12, %15, %0;\n\t@p fma.rn.f32 %1, %13, %15, %1;\n\t@p fma.rn.f32 %2, %14, %15, %2;\n\t"
+        "@p fma.rn.f32 %3, %12, %12, %3;\n\t@p fma.rn.f32 %4, %12, %13, %4;\n\t@p fma.rn.f32 %5, %12, %14, %5;\n\t"
+        "@p fma.rn.f32 %6, %13, %13, %6;\n\t@p fma.rn.f32 %7, %13, %14, %7;\n\t@p fma.rn.f32 %8, %14, %14, %8;\n\t@p add.s32 %9, %9, 1;\n\t}"
+        : "+f"(s1x), "+f"(s1y), "+f"(s1z), "+f"(sxx), "+f"(sxy), "+f"(sxz), "+f"(syy), "+f"(syz), "+f"(szz), "+r"(k)
+        : "f"(d2), "f"(r2), "f"(dx), "f"(dy), "f"(dz), "f"(r2 * 0.f + 1.0f));
+  }
+}
+
 #define ITER 2048
 // MODE 0: packed, no contraction (16 packed / 4 candidates)      -- the kernel in the tree
 // MODE 1: scalar, no contraction (32 scalar)
 // MODE 2: candidates 0,1 packed, 2,3 scalar
 // MODE 3: packed with FMA chain d2 = fma(dz,dz,fma(dy,dy,dx*dx)) (12 packed)
 // MODE 4: scalar with FMA chain (24 scalar)
-template <int MODE>
+template <int MODE, int ACC = 0>
 __global__ void __launch_bounds__(256) k(float* out, float seed) {
   __shared__ __align__(16) float tx[32], ty[32], tz[32];
   if (threadIdx.x < 32) { tx[threadIdx.x] = seed * threadIdx.x; ty[threadIdx.x] = seed * 2 * threadIdx.x; tz[threadIdx.x] = seed * 3 * threadIdx.x; }
@@ -54,8 +82,8 @@ __global__ void __launch_bounds__(256) k(float* out, float seed) {
     D2 = FMA ? __fmaf_rn(DZ, DZ, __fmaf_rn(DY, DY, __fmul_rn(DX, DX)))                                         \
              : __fadd_rn(__fadd_rn(__fmul_rn(DX, DX), __fmul_rn(DY, DY)), __fmul_rn(DZ, DZ));                  \
   }
-#define ACC2 accum_pred(d2a, r2, xa, ya, za, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, kk); \
-             accum_pred(d2b, r2, xb, yb, zb, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, kk);
+#define ACC2 accum_var<ACC>(d2a, r2, xa, ya, za, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, kk); \
+             accum_var<ACC>(d2b, r2, xb, yb, zb, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, kk);
       if (MODE == 0 || MODE == 3) {
         PACKED(X.x, X.y, Y.x, Y.y, Z.x, Z.y, MODE == 3) ACC2
         PACKED(X.z, X.w, Y.z, Y.w, Z.z, Z.w, MODE == 3) ACC2
@@ -71,14 +99,14 @@ __global__ void __launch_bounds__(256) k(float* out, float seed) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s1x + s1y + s1z + sxx + sxy + sxz + syy + syz + szz + kk;
 }
 
-template <int MODE>
+template <int MODE, int ACC = 0>
 void run(const char* name, int blocks_per_sm) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int blocks = sms * blocks_per_sm;
   float* out;
   cudaMalloc(&out, blocks * 256 * 4);
-  k<MODE><<<blocks, 256>>>(out, 0.01f);
+  k<MODE, ACC><<<blocks, 256>>>(out, 0.01f);
   cudaDeviceSynchronize();
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
@@ -86,7 +114,7 @@ void run(const char* name, int blocks_per_sm) {
   float best = 1e9f;
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0);
-    k<MODE><<<blocks, 256>>>(out, 0.01f);
+    k<MODE, ACC><<<blocks, 256>>>(out, 0.01f);
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms;
@@ -101,6 +129,13 @@ void run(const char* name, int blocks_per_sm) {
 }
 
 int main() {
+  run<0, 0>("packed dist, predicated acc (tree)", 4);
+  run<0, 1>("packed dist, zeroed deltas + plain FADD/FFMA", 4);
+  run<0, 2>("packed dist, zeroed deltas + all FFMA", 4);
+  run<0, 3>("packed dist, predicated all FFMA", 4);
+  run<1, 1>("scalar dist, zeroed deltas + plain FADD/FFMA", 4);
+  run<2, 1>("half packed dist, zeroed deltas", 4);
+
   for (int b : {4, 3}) {
     if (b == 4) {
       run<0>("packed, no FMA (tree)", 4); run<1>("scalar, no FMA", 4); run<2>("half packed / half scalar", 4);
