@@ -84,7 +84,34 @@ __global__ void __launch_bounds__(256) k(float* out, float seed) {
   }
 #define ACC2 accum_var<ACC>(d2a, r2, xa, ya, za, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, kk); \
              accum_var<ACC>(d2b, r2, xb, yb, zb, s1x, s1y, s1z, sxx, sxy, sxz, syy, syz, szz, kk);
-      if (MODE == 0 || MODE == 3) {
+      if (MODE >= 5) {
+        // mixed forms: which part of the distance test runs packed
+        //  5: subtractions packed (6 per 4 candidates), squares and sums scalar (20)
+        //  6: subtractions and squares packed (12), sums scalar (8)
+        //  7: subtractions scalar (12), squares and sums packed (10)
+#define MIXED(X0, X1, Y0, Y1, Z0, Z1)                                                                          \
+  {                                                                                                            \
+    if (MODE == 5) {                                                                                           \
+      const f32x2 dx = sub2(pack2(X0, X1), qx2), dy = sub2(pack2(Y0, Y1), qy2), dz = sub2(pack2(Z0, Z1), qz2); \
+      unpack2(dx, xa, xb); unpack2(dy, ya, yb); unpack2(dz, za, zb);                                           \
+      d2a = __fadd_rn(__fadd_rn(__fmul_rn(xa, xa), __fmul_rn(ya, ya)), __fmul_rn(za, za));                     \
+      d2b = __fadd_rn(__fadd_rn(__fmul_rn(xb, xb), __fmul_rn(yb, yb)), __fmul_rn(zb, zb));                     \
+    } else if (MODE == 6) {                                                                                    \
+      const f32x2 dx = sub2(pack2(X0, X1), qx2), dy = sub2(pack2(Y0, Y1), qy2), dz = sub2(pack2(Z0, Z1), qz2); \
+      float p0, p1, q0, q1, r0, r1;                                                                            \
+      unpack2(sq2(dx), p0, p1); unpack2(sq2(dy), q0, q1); unpack2(sq2(dz), r0, r1);                            \
+      unpack2(dx, xa, xb); unpack2(dy, ya, yb); unpack2(dz, za, zb);                                           \
+      d2a = __fadd_rn(__fadd_rn(p0, q0), r0); d2b = __fadd_rn(__fadd_rn(p1, q1), r1);                          \
+    } else {                                                                                                   \
+      xa = __fsub_rn(X0, qx); xb = __fsub_rn(X1, qx); ya = __fsub_rn(Y0, qy); yb = __fsub_rn(Y1, qy);          \
+      za = __fsub_rn(Z0, qz); zb = __fsub_rn(Z1, qz);                                                          \
+      const f32x2 dx = pack2(xa, xb), dy = pack2(ya, yb), dz = pack2(za, zb);                                  \
+      unpack2(add2(add2(sq2(dx), sq2(dy)), sq2(dz)), d2a, d2b);                                                \
+    }                                                                                                          \
+  }
+        MIXED(X.x, X.y, Y.x, Y.y, Z.x, Z.y) ACC2
+        MIXED(X.z, X.w, Y.z, Y.w, Z.z, Z.w) ACC2
+      } else if (MODE == 0 || MODE == 3) {
         PACKED(X.x, X.y, Y.x, Y.y, Z.x, Z.y, MODE == 3) ACC2
         PACKED(X.z, X.w, Y.z, Y.w, Z.z, Z.w, MODE == 3) ACC2
       } else if (MODE == 1 || MODE == 4) {
@@ -129,21 +156,12 @@ void run(const char* name, int blocks_per_sm) {
 }
 
 int main() {
-  run<0, 0>("packed dist, predicated acc (tree)", 4);
-  run<0, 1>("packed dist, zeroed deltas + plain FADD/FFMA", 4);
-  run<0, 2>("packed dist, zeroed deltas + all FFMA", 4);
-  run<0, 3>("packed dist, predicated all FFMA", 4);
-  run<1, 1>("scalar dist, zeroed deltas + plain FADD/FFMA", 4);
-  run<2, 1>("half packed dist, zeroed deltas", 4);
-
-  for (int b : {4, 3}) {
-    if (b == 4) {
-      run<0>("packed, no FMA (tree)", 4); run<1>("scalar, no FMA", 4); run<2>("half packed / half scalar", 4);
-      run<3>("packed, FMA chain", 4); run<4>("scalar, FMA chain", 4);
-    } else {
-      run<0>("packed, no FMA (tree)", 3); run<1>("scalar, no FMA", 3); run<2>("half packed / half scalar", 3);
-      run<3>("packed, FMA chain", 3); run<4>("scalar, FMA chain", 3);
-    }
-  }
+  run<0, 3>("packed dist (16P), all-FFMA acc", 4);
+  run<1, 3>("scalar dist (32S), all-FFMA acc", 4);
+  run<2, 3>("half packed / half scalar, all-FFMA acc", 4);
+  run<5, 3>("sub packed (6P) + 20S, all-FFMA acc", 4);
+  run<6, 3>("sub+sq packed (12P) + 8S, all-FFMA acc", 4);
+  run<7, 3>("sub scalar (12S) + sq/add packed (10P)", 4);
+  run<0, 0>("packed dist, predicated acc (old tree)", 4);
   return 0;
 }
