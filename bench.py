@@ -108,7 +108,7 @@ class ClockSampler:
         except Exception:
             self.nvml = None
 
-    def _sample(self):
+    def _sample(self, with_power=False):
         nv = self.nvml
         try:
             sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
@@ -117,11 +117,13 @@ class ClockSampler:
                 mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
             except Exception:
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-            try:
-                watts = nv.nvmlDeviceGetPowerUsage(self.handle) / 1e3
-            except Exception:
-                watts = None
-            self.rows.append((float(sm), float(mx), watts, int(mask)))
+            watts = None
+            if with_power:  # (the power query is the slow one: asked once when the region is over, not while it runs)
+                try:
+                    watts = nv.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+                except Exception:
+                    watts = None
+            self.rows.append((float(sm), float(mx) if mx is not None else float(sm), watts, int(mask)))
         except Exception:
             pass
 
@@ -155,6 +157,7 @@ class ClockSampler:
             self._stop = True
             if self.thread:
                 self.thread.join(timeout=2)
+            self._sample(with_power=True)  # one last sample, with the board power, right behind the region
             nv = self.nvml
             bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
