@@ -111,6 +111,43 @@ def test_step_with_truncated_rsd(max_nn):
     c.close()
 
 
+def test_local_group_on_a_sparse_cloud_with_wide_cells():
+    """A cloud sparse enough for cells that are wide along x (mean 16 neighbours; cab_grid.cu, Domain.xwide): the slab
+    build of a group's ranks dimensions its table the same way, and every rank ends up with the single-GPU results."""
+    pts = synth.density_patches(300_000, 16.0, R)
+    n = pts.shape[0]
+    n4, rmin, rmax, k = _single_gpu(pts)
+    world = 2
+    ctxs = [cab.Context(0) for _ in range(world)]
+    cab.comm_init_local(ctxs)
+    out, errs = [None] * world, []
+
+    def work(r):
+        try:
+            c = ctxs[r]
+            c.comm_upload_cloud(pts)
+            c.step_normals_rsd(R, R)
+            out[r] = (c.comm_download_range(0, n), c.profile())
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not errs, errs
+    ext = pts.max(axis=0).astype(np.float64) - pts.min(axis=0).astype(np.float64)
+    cubic = np.prod(np.floor(ext / (R * (1 + 1 / 1024))) + 2)
+    for r in range(world):
+        (f4, fmin, fmax), prof = out[r]
+        assert _same(f4, n4) and _same(fmin, rmin) and _same(fmax, rmax), f"rank {r}"
+        assert prof["n_cells"] < cubic / 4  # a slab of a wide table
+    assert sum(out[r][1]["neighbour_sum"] for r in range(world)) == k
+    for c in ctxs:
+        c.close()
+
+
 @pytest.mark.parametrize("world,max_nn", [(3, 0), (2, 60)])
 def test_local_group_every_rank_holds_all_results(world, max_nn):
     """Three contexts of this process on one GPU: after the step EVERY rank's concatenated arrays hold the single-GPU
