@@ -4,11 +4,15 @@
 // materialised; each query keeps per-distance-bin extreme cosines in shared memory while the
 // candidate chunks stream past, then solves the two one-parameter least-squares fits.
 //
-// Kernel structure (DESIGN.md "RSD kernel"):
-//  phase 1  per 32-candidate chunk: packed fp32x2 distance test -> one 32-bit hit mask per query
-//  phase 2  only the hits are visited (about one candidate in four is a hit, so the per-hit work
-//           must not be paid by the misses); the candidate's position and normal are fetched from
-//           the lane that staged it with warp shuffles.
+// Two kernels:
+//  rsd_fast_kernel  fast mode (fp32, the default): every staged candidate is processed under a predicate -- packed
+//           distance test and cosine, the bin row from two truncated products that bracket the reference's bin (the
+//           exact thresholds only where they disagree), two shared-memory reductions into lane-private bins; the
+//           truncated variant (max_nn) settles the target bin of the d2 histogram from a short per-query list.
+//  rsd_kernel       exact mode (signed cosines, double acos) and the exact-threshold fallback of the truncation:
+//    phase 1  per 32-candidate chunk: packed fp32x2 distance test -> one 32-bit hit mask per query
+//    phase 2  only the hits are visited; the candidate's position and normal are fetched from the lane that staged it
+//             with warp shuffles.
 // Arithmetic notes:
 //  * cosine is the reference's fp32 expression (nx*nx' + ny*ny') + nz*nz' (:153-155), not contracted.
 //  * angle = acos(cosine) folded at pi/2 (:160-161) is monotone in |cosine|, so per bin only the
